@@ -1,0 +1,15 @@
+"""B200-native AV1 partition-prediction cascade (drop-in for the v6 inference path of
+chiarorosa/cnn-av1-research).  See DESIGN.md and INTEGRATION.md at the repository root."""
+from .extraction import (BlockRecord, TorchBlockRecord, calculate_yuv420_10bit_sizes, extract_blocks_device,
+                         extract_blocks_with_validation)
+from .models import (CosineClassifier, FGVCModel, ImprovedBackbone, SEBlock, SpatialAttention, Stage1BinaryHead,
+                     Stage1Model, Stage2Model, Stage2ThreeWayHead, Stage3ABHead, Stage3ABModel, Stage3RectHead,
+                     Stage3RectModel)
+from .pipeline import HierarchicalPipelineV6, evaluate_pipeline
+
+__all__ = [
+    "BlockRecord", "TorchBlockRecord", "calculate_yuv420_10bit_sizes", "extract_blocks_device",
+    "extract_blocks_with_validation", "CosineClassifier", "FGVCModel", "ImprovedBackbone", "SEBlock",
+    "SpatialAttention", "Stage1BinaryHead", "Stage1Model", "Stage2Model", "Stage2ThreeWayHead", "Stage3ABHead",
+    "Stage3ABModel", "Stage3RectHead", "Stage3RectModel", "HierarchicalPipelineV6", "evaluate_pipeline",
+]

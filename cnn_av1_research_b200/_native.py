@@ -1,0 +1,123 @@
+"""ctypes binding of libav1p.so (include/av1p.h).  PyTorch is used for device memory and streams only.
+
+There is no fallback: if the shared library is missing or the device is not a Blackwell (sm_100)
+GPU, every call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import torch
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libav1p.so")
+_lib: Optional[C.CDLL] = None
+
+
+class Av1pError(RuntimeError):
+    pass
+
+
+class Input(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("width", C.c_int32), ("height", C.c_int32), ("pitch", C.c_int32),
+                ("n_frames", C.c_int32), ("frame_stride", C.c_int64), ("frames_dev", C.c_void_p),
+                ("images_dev", C.c_void_p)]
+
+
+class FcDesc(C.Structure):
+    _fields_ = [("a_dev", C.c_void_p * 4), ("a_cols", C.c_int32 * 4), ("rows", C.c_int32), ("n_dev", C.c_void_p),
+                ("w_dev", C.c_void_p), ("n_w_chunks", C.c_int32), ("n_kb_total", C.c_int32), ("n_tiles", C.c_int32),
+                ("block_n", C.c_int32), ("epi", C.c_int32), ("kb_begin", C.c_void_p), ("kb_src", C.c_void_p),
+                ("kb_w", C.c_void_p), ("bias_dev", C.c_void_p), ("row_scale_dev", C.c_void_p), ("acc_scale", C.c_float),
+                ("aux_dev", C.c_void_p), ("aux_lo_dev", C.c_void_p), ("aux_ld", C.c_int32), ("out_dev", C.c_void_p),
+                ("out_lo_dev", C.c_void_p), ("out_ld", C.c_int32), ("tail_w_dev", C.c_void_p),
+                ("tail_b_dev", C.c_void_p), ("logits_dev", C.c_void_p), ("tail_n", C.c_int32)]
+
+
+# name -> (restype, argtypes); kept in one table so tests can check the export list against av1p.h
+SIGNATURES = {
+    "av1p_last_error": (C.c_char_p, []),
+    "av1p_version": (C.c_int, []),
+    "av1p_debug_watchdog": (C.c_int, []),
+    "av1p_model_create": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
+    "av1p_model_destroy": (None, [C.c_void_p]),
+    "av1p_model_num_outputs": (C.c_int, [C.c_void_p]),
+    "av1p_stage_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int32]),
+    "av1p_stage_create": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
+    "av1p_stage_destroy": (None, [C.c_void_p]),
+    "av1p_stage_forward": (C.c_int, [C.c_void_p, C.POINTER(Input), C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "av1p_stage_launches_per_forward": (C.c_int, [C.c_void_p]),
+    "av1p_cascade_workspace_bytes": (C.c_size_t, [C.POINTER(C.c_void_p), C.c_int32]),
+    "av1p_cascade_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int32, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
+    "av1p_cascade_destroy": (None, [C.c_void_p]),
+    "av1p_cascade_predict": (C.c_int, [C.c_void_p, C.POINTER(Input), C.c_int32, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "av1p_cascade_buffer": (C.c_void_p, [C.c_void_p, C.c_int32]),
+    "av1p_cascade_launches_per_predict": (C.c_int, [C.c_void_p]),
+    "av1p_extract_u16": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "av1p_extract_norm_u16": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "av1p_route_scratch_bytes": (C.c_size_t, []),
+    "av1p_route_stage1": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_void_p]),
+    "av1p_route_stage2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "av1p_finalize_labels": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
+                                       C.c_void_p, C.c_void_p]),
+    "av1p_fc_forward": (C.c_int, [C.POINTER(FcDesc), C.c_void_p]),
+}
+
+
+def lib() -> C.CDLL:
+    """Load libav1p.so (built in-tree by __graft_entry__.build()).  Raises if it is absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            raise Av1pError(f"{_LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`. "
+                            "There is no CPU or PyTorch fallback for this path.")
+        handle = C.CDLL(_LIB_PATH)
+        for name, (restype, argtypes) in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype, fn.argtypes = restype, argtypes
+        _lib = handle
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise Av1pError(f"libav1p error {rc}: {lib().av1p_last_error().decode()}")
+
+
+def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise Av1pError("libav1p needs CUDA tensors; there is no CPU path")
+    if not t.is_contiguous():
+        raise Av1pError("libav1p needs contiguous tensors")
+    return t.data_ptr()
+
+
+def stream_handle(device=None) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def frames_input(frames: torch.Tensor, width: int, height: int, n_frames: int, pitch: Optional[int] = None,
+                 frame_stride: Optional[int] = None) -> Input:
+    """Planar YUV 4:2:0 10-bit LE frames as a flat uint16 (or int16) CUDA tensor."""
+    if frames.dtype not in (torch.uint16, torch.int16):
+        raise Av1pError("frames must be a 16-bit integer tensor")
+    pitch = width if pitch is None else pitch
+    if frame_stride is None:
+        frame_stride = width * height + 2 * ((width // 2) * (height // 2))
+    need = (n_frames - 1) * frame_stride + (height - 1) * pitch + width
+    if frames.numel() < need:
+        raise Av1pError(f"frame tensor holds {frames.numel()} samples, geometry needs {need}")
+    return Input(kind=0, width=width, height=height, pitch=pitch, n_frames=n_frames, frame_stride=frame_stride,
+                 frames_dev=ptr(frames), images_dev=None)
+
+
+def images_input(images: torch.Tensor) -> Input:
+    """float32 blocks [n,1,16,16] (or [n,256]) on the device."""
+    if images.dtype != torch.float32 or images.numel() % 256:
+        raise Av1pError("images must be float32 with 256 samples per block")
+    return Input(kind=1, width=16, height=16, pitch=16, n_frames=0, frame_stride=0, frames_dev=None, images_dev=ptr(images))

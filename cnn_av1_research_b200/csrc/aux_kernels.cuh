@@ -1,0 +1,339 @@
+// Small CUDA-core kernels around the tensor-core layers: spatial-attention gate, FGVC cosine
+// tail, standalone block extraction / normalisation, and the inter-stage routing (threshold /
+// argmax + stable stream compaction + label scatter).
+#pragma once
+#include "ptx_sm100.cuh"
+
+namespace av1p {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------
+// SpatialAttention at 1x1 spatial (reference models.py:56-61): only the centre tap of the 7x7
+// kernel touches data, so the module reduces to one scalar per block,
+//   g = sigmoid(w_avg * mean_c(x) + w_max * max_c(x)),
+// which the next linear layer applies as a row scale.  One warp per row of 512 fp16.
+__device__ __forceinline__ void load_row16(const __half* __restrict__ hi, const __half* __restrict__ lo, size_t off,
+                                           float (&x)[16]) {
+  // 16 consecutive values of a row as fp32 (hi + lo in split precision)
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const uint4 q = __ldg(reinterpret_cast<const uint4*>(hi + off) + j);
+    const __half2* h = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __half22float2(h[i]);
+      x[j * 8 + 2 * i] = f.x;
+      x[j * 8 + 2 * i + 1] = f.y;
+    }
+  }
+  if (lo) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const uint4 q = __ldg(reinterpret_cast<const uint4*>(lo + off) + j);
+      const __half2* h = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = __half22float2(h[i]);
+        x[j * 8 + 2 * i] += f.x;
+        x[j * 8 + 2 * i + 1] += f.y;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) sam_gate_kernel(const __half* __restrict__ x, const __half* __restrict__ x_lo,
+                                                       int ld, const int* n_dev, int n, float w_avg, float w_max,
+                                                       float* __restrict__ row_scale) {
+  const int rows = n_dev ? *n_dev : n;
+  const int lane = threadIdx.x & 31;
+  const int warps_per_grid = (gridDim.x * blockDim.x) >> 5;
+  for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < rows; r += warps_per_grid) {
+    float v[16];
+    load_row16(x, x_lo, size_t(r) * ld + lane * 16, v);
+    float s = 0.f, m = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      s += v[i];
+      m = fmaxf(m, v[i]);
+    }
+    s = warp_sum(s);
+    m = warp_max(m);
+    if (lane == 0) row_scale[r] = 1.0f / (1.0f + expf(-(w_avg * (s * (1.0f / 512.0f)) + w_max * m)));
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// FGVC tail (reference scripts/006_train_stage3_ab_fgvc.py:235-241, 290-293):
+//   f = h / max(||h||_2, 1e-12);  logits = 20 * f . What^T,  What = row-normalised classifier weight
+// (normalised once at pack time).  One warp per row of 512 fp16.
+__global__ void __launch_bounds__(256) fgvc_tail_kernel(const __half* __restrict__ h, const __half* __restrict__ h_lo,
+                                                        int ld, const int* n_dev, int n,
+                                                        const float* __restrict__ what, float scale,
+                                                        float* __restrict__ logits) {
+  const int rows = n_dev ? *n_dev : n;
+  const int lane = threadIdx.x & 31;
+  const int warps_per_grid = (gridDim.x * blockDim.x) >> 5;
+  for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < rows; r += warps_per_grid) {
+    float x[16];
+    load_row16(h, h_lo, size_t(r) * ld + lane * 16, x);
+    float ss = 0.f, d[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < 16; ++i) ss = fmaf(x[i], x[i], ss);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float4* w4 = reinterpret_cast<const float4*>(what + c * 512 + lane * 16);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 w = __ldg(w4 + i);
+        d[c] = fmaf(x[4 * i], w.x, d[c]);
+        d[c] = fmaf(x[4 * i + 1], w.y, d[c]);
+        d[c] = fmaf(x[4 * i + 2], w.z, d[c]);
+        d[c] = fmaf(x[4 * i + 3], w.w, d[c]);
+      }
+    }
+    ss = warp_sum(ss);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) d[c] = warp_sum(d[c]);
+    if (lane == 0) {
+      const float inv = scale / fmaxf(sqrtf(ss), 1e-12f);
+      *reinterpret_cast<float4*>(logits + size_t(r) * 4) = make_float4(d[0] * inv, d[1] * inv, d[2] * inv, d[3] * inv);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Standalone extraction (reference 005:353-457 + data_hub.py:70-77).  Each thread moves 8
+// consecutive luma samples (one 16-byte load) of one block row; blocks are emitted in row-major
+// grid order, out-of-frame samples are zero.  OUT = uint16_t: raw tiles; OUT = float: tiles / 1023.
+template <typename OUT>
+__global__ void __launch_bounds__(256) extract_blocks_kernel(const uint16_t* __restrict__ y, int width, int height,
+                                                             int pitch, int bs, int blocks_x, int blocks_y,
+                                                             OUT* __restrict__ out) {
+  const int chunks_x = blocks_x * bs / 8;                       // 8-sample chunks per padded row
+  const long long total = (long long)chunks_x * blocks_y * bs;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int cx = int(t % chunks_x);
+    const int py = int(t / chunks_x);                           // padded-frame row
+    const int x0 = cx * 8;
+    uint16_t v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (py < height) {
+      const uint16_t* src = y + size_t(py) * pitch + x0;
+      if (x0 + 7 < width && ((reinterpret_cast<uintptr_t>(src) & 15u) == 0)) {
+        *reinterpret_cast<uint4*>(v) = __ldg(reinterpret_cast<const uint4*>(src));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (x0 + j < width) v[j] = __ldg(src + j);
+      }
+    }
+    const int by = py / bs, r = py - by * bs;
+    const int bx = x0 / bs, c = x0 - bx * bs;
+    OUT* dst = out + ((size_t(by) * blocks_x + bx) * bs + r) * bs + c;
+    if constexpr (sizeof(OUT) == 2) {
+      *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(v);
+    } else {
+      float4 a, b;
+      a.x = __fdiv_rn(float(v[0]), 1023.0f); a.y = __fdiv_rn(float(v[1]), 1023.0f);
+      a.z = __fdiv_rn(float(v[2]), 1023.0f); a.w = __fdiv_rn(float(v[3]), 1023.0f);
+      b.x = __fdiv_rn(float(v[4]), 1023.0f); b.y = __fdiv_rn(float(v[5]), 1023.0f);
+      b.z = __fdiv_rn(float(v[6]), 1023.0f); b.w = __fdiv_rn(float(v[7]), 1023.0f);
+      reinterpret_cast<float4*>(dst)[0] = a;
+      reinterpret_cast<float4*>(dst)[1] = b;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Routing.  Reference scripts/008_run_pipeline_eval_v6.py:76-125.
+//
+// A routing step classifies n rows into up to two "keep" classes and writes, for each class, the
+// ascending list of original block ids (the order torch's nonzero / boolean-mask indexing gives),
+// its length (device counter, read by the next stage's kernels - no host sync), and labels.
+//   kind 0 (stage 1): row i is block i.  keep0 <=> sigmoid(logit) >= thr.  labels[i] = 0 for all i.
+//   kind 1 (stage 2): row i is block src[i].  cls = argmax softmax(logits[i, 0:3]) (first max wins);
+//                     cls 0 -> labels = 1 (SPLIT); keep0 <=> cls == 1 (RECT); keep1 <=> cls == 2 (AB).
+// Two passes over a tile decomposition: count (the last CTA to finish scans the tile counts), then
+// scatter with an in-tile scan.  No spinning on other CTAs anywhere.
+constexpr int ROUTE_THREADS = 256;
+constexpr int ROUTE_ITEMS = 4;
+constexpr int ROUTE_TILE = ROUTE_THREADS * ROUTE_ITEMS;
+constexpr int ROUTE_MAX_TILES = 8192;   // capacity 8 Mi rows
+
+struct RouteParams {
+  int kind;
+  const float* logits;
+  const int* src;          // kind 1: block id of each row
+  const int* n_dev;
+  int n;
+  float thr;
+  int* tile_counts;        // [2][ROUTE_MAX_TILES] scratch; holds exclusive offsets after pass 1
+  unsigned int* ticket;    // zero-initialised once; reset by the last CTA
+  int* out_idx0;
+  int* out_idx1;
+  int* counts;             // [2] device counters
+  uint8_t* labels_u8;      // optional
+  long long* labels_i64;   // optional
+};
+
+__device__ __forceinline__ int route_class(const RouteParams& p, int i) {
+  // returns 0 = not routed, 1 = keep0, 2 = keep1, 3 = SPLIT (stage 2 only)
+  if (p.kind == 0) {
+    const float x = p.logits[i];
+    const float prob = 1.0f / (1.0f + expf(-x));            // torch.sigmoid in fp32
+    return prob >= p.thr ? 1 : 0;
+  }
+  const float a = p.logits[3 * i], b = p.logits[3 * i + 1], c = p.logits[3 * i + 2];
+  const float m = fmaxf(a, fmaxf(b, c));
+  const float ea = expf(a - m), eb = expf(b - m), ec = expf(c - m);
+  const float s = (ea + eb) + ec;
+  const float pa = __fdiv_rn(ea, s), pb = __fdiv_rn(eb, s), pc = __fdiv_rn(ec, s);
+  int cls = 0;
+  float best = pa;
+  if (pb > best) { best = pb; cls = 1; }
+  if (pc > best) { best = pc; cls = 2; }
+  return cls == 0 ? 3 : cls;
+}
+
+__device__ __forceinline__ int block_exclusive_scan(int v, int* warp_tot /*[8]*/, int& total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) warp_tot[warp] = inc;
+  __syncthreads();
+  int base = 0, tot = 0;
+#pragma unroll
+  for (int w = 0; w < ROUTE_THREADS / 32; ++w) {
+    const int t = warp_tot[w];
+    if (w < warp) base += t;
+    tot += t;
+  }
+  __syncthreads();
+  total = tot;
+  return base + inc - v;
+}
+
+__global__ void __launch_bounds__(ROUTE_THREADS) route_count_kernel(const RouteParams p) {
+  __shared__ int warp_tot[ROUTE_THREADS / 32];
+  __shared__ bool is_last;
+  const int n = p.n_dev ? *p.n_dev : p.n;
+  const int tiles = gridDim.x;
+  const int i0 = blockIdx.x * ROUTE_TILE + threadIdx.x * ROUTE_ITEMS;
+  int c0 = 0, c1 = 0;
+#pragma unroll
+  for (int j = 0; j < ROUTE_ITEMS; ++j) {
+    const int i = i0 + j;
+    if (i < n) {
+      const int cls = route_class(p, i);
+      c0 += cls == 1;
+      c1 += cls == 2;
+    }
+  }
+  int t0, t1;
+  block_exclusive_scan(c0, warp_tot, t0);
+  block_exclusive_scan(c1, warp_tot, t1);
+  if (threadIdx.x == 0) {
+    p.tile_counts[blockIdx.x] = t0;
+    p.tile_counts[ROUTE_MAX_TILES + blockIdx.x] = t1;
+    __threadfence();
+    const unsigned int done = atomicAdd(p.ticket, 1u);
+    is_last = (done == unsigned(tiles - 1));
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  // last CTA: exclusive scan of the tile counts (tiles <= ROUTE_MAX_TILES), one class at a time
+  for (int k = 0; k < 2; ++k) {
+    int* tc = p.tile_counts + k * ROUTE_MAX_TILES;
+    int carry = 0;
+    for (int basei = 0; basei < tiles; basei += ROUTE_THREADS) {
+      const int i = basei + threadIdx.x;
+      const int v = i < tiles ? __ldcg(tc + i) : 0;
+      int tot;
+      const int ex = block_exclusive_scan(v, warp_tot, tot);
+      if (i < tiles) tc[i] = carry + ex;
+      carry += tot;
+    }
+    if (threadIdx.x == 0) p.counts[k] = carry;
+  }
+  if (threadIdx.x == 0) *p.ticket = 0u;
+}
+
+__global__ void __launch_bounds__(ROUTE_THREADS) route_scatter_kernel(const RouteParams p) {
+  __shared__ int warp_tot[ROUTE_THREADS / 32];
+  const int n = p.n_dev ? *p.n_dev : p.n;
+  const int i0 = blockIdx.x * ROUTE_TILE + threadIdx.x * ROUTE_ITEMS;
+  if (blockIdx.x * ROUTE_TILE >= n) return;
+  int cls[ROUTE_ITEMS];
+  int c0 = 0, c1 = 0;
+#pragma unroll
+  for (int j = 0; j < ROUTE_ITEMS; ++j) {
+    const int i = i0 + j;
+    cls[j] = i < n ? route_class(p, i) : 0;
+    c0 += cls[j] == 1;
+    c1 += cls[j] == 2;
+  }
+  int t;
+  int r0 = p.tile_counts[blockIdx.x] + block_exclusive_scan(c0, warp_tot, t);
+  int r1 = p.tile_counts[ROUTE_MAX_TILES + blockIdx.x] + block_exclusive_scan(c1, warp_tot, t);
+#pragma unroll
+  for (int j = 0; j < ROUTE_ITEMS; ++j) {
+    const int i = i0 + j;
+    if (i >= n) break;
+    const int g = p.kind == 0 ? i : p.src[i];
+    if (cls[j] == 1) p.out_idx0[r0++] = g;
+    if (cls[j] == 2) p.out_idx1[r1++] = g;
+    if (p.kind == 0) {
+      if (p.labels_u8) p.labels_u8[g] = 0;
+      if (p.labels_i64) p.labels_i64[g] = 0;
+    } else if (cls[j] == 3) {
+      if (p.labels_u8) p.labels_u8[g] = 1;
+      if (p.labels_i64) p.labels_i64[g] = 1;
+    }
+  }
+}
+
+// Stage-3 label scatter: labels[idx[i]] = base + argmax softmax(logits[i, 0:k]) (first max wins).
+__global__ void __launch_bounds__(256) finalize_labels_kernel(const float* __restrict__ logits, int k, int base,
+                                                              const int* __restrict__ idx, const int* n_dev, int n,
+                                                              uint8_t* labels_u8, long long* labels_i64) {
+  const int rows = n_dev ? *n_dev : n;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < rows; i += gridDim.x * blockDim.x) {
+    float x[4];
+    float m = -INFINITY;
+    for (int j = 0; j < k; ++j) {
+      x[j] = logits[i * k + j];
+      m = fmaxf(m, x[j]);
+    }
+    float e[4], s = 0.f;
+    for (int j = 0; j < k; ++j) {
+      e[j] = expf(x[j] - m);
+      s += e[j];
+    }
+    int cls = 0;
+    float best = __fdiv_rn(e[0], s);
+    for (int j = 1; j < k; ++j) {
+      const float pj = __fdiv_rn(e[j], s);
+      if (pj > best) { best = pj; cls = j; }
+    }
+    const int g = idx[i];
+    if (labels_u8) labels_u8[g] = uint8_t(base + cls);
+    if (labels_i64) labels_i64[g] = base + cls;
+  }
+}
+
+}  // namespace av1p

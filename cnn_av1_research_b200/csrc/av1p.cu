@@ -1,0 +1,673 @@
+// libav1p.so - host side: weight blob loader, op-list executor, cascade scheduler and the C ABI
+// declared in include/av1p.h.  All device work is hand-written sm_100a code from the .cuh files in
+// this directory; there is deliberately no CPU or library fallback - without a Blackwell device
+// every entry point fails with AV1P_ENODEV / AV1P_ECUDA.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/av1p.h"
+#include "aux_kernels.cuh"
+#include "blob_format.h"
+#include "fc_tcgen05.cuh"
+#include "stem.cuh"
+
+using namespace av1p;
+
+// ------------------------------------------------------------------------------ errors
+static thread_local std::string g_err;
+static int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+#define CUDA_TRY(expr)                                                                          \
+  do {                                                                                          \
+    cudaError_t e__ = (expr);                                                                   \
+    if (e__ != cudaSuccess) return fail(AV1P_ECUDA, "%s: %s", #expr, cudaGetErrorString(e__)); \
+  } while (0)
+
+extern "C" const char* av1p_last_error(void) { return g_err.c_str(); }
+extern "C" int av1p_version(void) { return 100; }
+
+// ------------------------------------------------------------------------------ device context
+namespace {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct DeviceCtx {
+  bool ok = false;
+  int sms = 0;
+  EncodeTiledFn encode = nullptr;
+  int* watchdog_host = nullptr;   // mapped pinned memory: survives a kernel trap
+  int* watchdog_dev = nullptr;
+};
+DeviceCtx g_ctx;
+std::mutex g_ctx_mu;
+
+int ensure_ctx() {
+  std::lock_guard<std::mutex> lk(g_ctx_mu);
+  if (g_ctx.ok) return AV1P_OK;
+  int dev = 0, cc_major = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return fail(AV1P_ENODEV, "no CUDA device: %s", cudaGetErrorString(e));
+  CUDA_TRY(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+  if (cc_major != 10) return fail(AV1P_ENODEV, "libav1p is built for sm_100a only; device has compute capability %d.x", cc_major);
+  CUDA_TRY(cudaDeviceGetAttribute(&g_ctx.sms, cudaDevAttrMultiProcessorCount, dev));
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  if (!fn || qres != cudaDriverEntryPointSuccess) return fail(AV1P_ECUDA, "cuTensorMapEncodeTiled not available");
+  g_ctx.encode = reinterpret_cast<EncodeTiledFn>(fn);
+  CUDA_TRY(cudaFuncSetAttribute(fc_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FC_SMEM_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(stem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, STEM_SMEM_BYTES));
+  CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&g_ctx.watchdog_host), sizeof(int), cudaHostAllocMapped));
+  *g_ctx.watchdog_host = 0;
+  CUDA_TRY(cudaHostGetDevicePointer(reinterpret_cast<void**>(&g_ctx.watchdog_dev), g_ctx.watchdog_host, 0));
+  g_ctx.ok = true;
+  return AV1P_OK;
+}
+
+// 2-D fp16 tensor map, row-major [rows][cols], box {64 cols, box_rows}, 128-byte swizzle.
+int make_map_2d(CUtensorMap* map, const void* base, uint64_t cols, uint64_t rows, uint64_t ld_elems,
+                uint32_t box_rows) {
+  if ((reinterpret_cast<uintptr_t>(base) & 15u) || (ld_elems * 2) % 16)
+    return fail(AV1P_EINVAL, "tensor map base/stride not 16-byte aligned");
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld_elems * 2};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_ctx.encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box,
+                            estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(AV1P_ECUDA, "cuTensorMapEncodeTiled failed with %d", int(r));
+  return AV1P_OK;
+}
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+}  // namespace
+
+extern "C" int av1p_debug_watchdog(void) { return g_ctx.watchdog_host ? *g_ctx.watchdog_host : 0; }
+
+// ------------------------------------------------------------------------------ model
+struct av1p_model {
+  std::vector<uint8_t> host;        // header + op table (host copy for planning)
+  uint8_t* dev = nullptr;           // whole blob on the device
+  Av1pBlobHeader hdr;
+  std::vector<Av1pBlobOp> ops;
+  std::vector<uint32_t> buf_cols;
+};
+
+extern "C" int av1p_model_create(const void* blob, size_t bytes, av1p_model** out) {
+  if (!blob || !out) return fail(AV1P_EINVAL, "null argument");
+  if (bytes < sizeof(Av1pBlobHeader)) return fail(AV1P_EINVAL, "blob too small");
+  Av1pBlobHeader h;
+  memcpy(&h, blob, sizeof h);
+  if (h.magic != AV1P_BLOB_MAGIC || h.version != AV1P_BLOB_VERSION)
+    return fail(AV1P_EINVAL, "bad blob magic/version (%08x, %u)", h.magic, h.version);
+  if (h.total_bytes != bytes || h.ops_off + uint64_t(h.n_ops) * sizeof(Av1pBlobOp) > bytes ||
+      h.bufs_off + uint64_t(h.n_bufs) * 4 > bytes)
+    return fail(AV1P_EINVAL, "blob table out of range");
+  if (int rc = ensure_ctx()) return rc;
+  av1p_model* m = new (std::nothrow) av1p_model();
+  if (!m) return fail(AV1P_ENOMEM, "host allocation failed");
+  m->hdr = h;
+  m->ops.resize(h.n_ops);
+  memcpy(m->ops.data(), static_cast<const uint8_t*>(blob) + h.ops_off, h.n_ops * sizeof(Av1pBlobOp));
+  m->buf_cols.resize(h.n_bufs);
+  memcpy(m->buf_cols.data(), static_cast<const uint8_t*>(blob) + h.bufs_off, h.n_bufs * 4);
+  for (const Av1pBlobOp& op : m->ops) {
+    auto bad_buf = [&](int b) { return b >= int(h.n_bufs); };
+    if (bad_buf(op.src[0]) || bad_buf(op.src[1]) || bad_buf(op.src[2]) || bad_buf(op.src[3]) || bad_buf(op.aux) ||
+        bad_buf(op.aux_lo) || bad_buf(op.out) || bad_buf(op.out_lo)) {
+      delete m;
+      return fail(AV1P_EINVAL, "op references a buffer that does not exist");
+    }
+    if (op.type == AV1P_OP_FC) {
+      if (op.n_tiles < 1 || op.n_tiles > FC_MAX_NT || op.block_n < 32 || op.block_n > FC_MAX_N || op.block_n % 32 ||
+          op.n_kb_total < 1 || op.n_kb_total > FC_MAX_KB || op.tail_n > FC_TAIL_MAX || op.n_w_chunks < 1 ||
+          op.w_off + uint64_t(op.n_w_chunks) * op.block_n * 128 > bytes) {
+        delete m;
+        return fail(AV1P_EINVAL, "malformed FC op");
+      }
+    }
+  }
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&m->dev), bytes);
+  if (e == cudaSuccess) e = cudaMemcpy(m->dev, blob, bytes, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    if (m->dev) cudaFree(m->dev);
+    delete m;
+    return fail(AV1P_ECUDA, "blob upload failed: %s", cudaGetErrorString(e));
+  }
+  *out = m;
+  return AV1P_OK;
+}
+extern "C" void av1p_model_destroy(av1p_model* m) {
+  if (!m) return;
+  if (m->dev) cudaFree(m->dev);
+  delete m;
+}
+extern "C" int av1p_model_num_outputs(const av1p_model* m) { return m ? int(m->hdr.n_out) : 0; }
+
+// ------------------------------------------------------------------------------ stage (plan)
+namespace {
+
+struct PlannedOp {
+  int type = 0;
+  FcParams fc;          // AV1P_OP_FC
+  StemParams stem;      // AV1P_OP_STEM
+  const __half* src = nullptr;   // SAM / FGVC
+  const __half* src_lo = nullptr;
+  int ld = 0;
+  float f0 = 0.f, f1 = 0.f;
+  const float* w = nullptr;
+};
+
+// Activation region shared by every stage of a cascade: buffer i has max-over-models cols.
+struct ActLayout {
+  std::vector<uint32_t> cols;
+  std::vector<size_t> off;
+  size_t row_scale_off = 0, bytes = 0;
+  int cap = 0;
+};
+
+ActLayout make_act_layout(const av1p_model* const* models, int n_models, int capacity) {
+  ActLayout L;
+  L.cap = ceil_div(std::max(capacity, 1), FC_TILE_M) * FC_TILE_M;
+  size_t nb = 0;
+  for (int i = 0; i < n_models; ++i) nb = std::max(nb, models[i]->buf_cols.size());
+  L.cols.assign(nb, 0);
+  for (int i = 0; i < n_models; ++i)
+    for (size_t b = 0; b < models[i]->buf_cols.size(); ++b) L.cols[b] = std::max(L.cols[b], models[i]->buf_cols[b]);
+  size_t o = 0;
+  for (size_t b = 0; b < nb; ++b) {
+    L.off.push_back(o);
+    o += align_up(size_t(L.cap) * L.cols[b] * 2, 1024);
+  }
+  L.row_scale_off = o;
+  o += align_up(size_t(L.cap) * 4, 1024);
+  L.bytes = o;
+  return L;
+}
+
+}  // namespace
+
+struct av1p_stage {
+  const av1p_model* model = nullptr;
+  int cap = 0;
+  std::vector<PlannedOp> ops;
+  float* row_scale = nullptr;
+  float* own_logits = nullptr;   // unused by the cascade (it passes its own logits buffers)
+};
+
+namespace {
+
+int plan_stage(const av1p_model* m, const ActLayout& L, uint8_t* act_base, av1p_stage* s) {
+  s->model = m;
+  s->cap = L.cap;
+  s->row_scale = reinterpret_cast<float*>(act_base + L.row_scale_off);
+  auto buf = [&](int id) -> __half* { return id < 0 ? nullptr : reinterpret_cast<__half*>(act_base + L.off[id]); };
+  auto at = [&](uint64_t off) -> const uint8_t* { return off ? m->dev + off : nullptr; };
+  for (const Av1pBlobOp& op : m->ops) {
+    PlannedOp P;
+    P.type = op.type;
+    switch (op.type) {
+      case AV1P_OP_STEM: {
+        memset(&P.stem, 0, sizeof P.stem);
+        P.stem.w = reinterpret_cast<const float*>(at(op.w_off));
+        P.stem.b = reinterpret_cast<const float*>(at(op.bias_off));
+        P.stem.out = buf(op.out);
+        P.stem.out_lo = buf(op.out_lo);
+        if (!P.stem.w || !P.stem.b || !P.stem.out || L.cols[op.out] != 1024) return fail(AV1P_EINVAL, "malformed stem op");
+        break;
+      }
+      case AV1P_OP_FC: {
+        FcParams& f = P.fc;
+        memset(&f, 0, sizeof f);
+        if (op.src[0] < 0 || (op.out < 0 && op.epi != FC_EPI_HEAD)) return fail(AV1P_EINVAL, "FC op without source/out");
+        for (int i = 0; i < FC_MAX_SRC; ++i) {
+          const int sb = op.src[i] >= 0 ? op.src[i] : op.src[0];
+          if (int rc = make_map_2d(&f.a_map[i], buf(sb), L.cols[sb], L.cap, L.cols[sb], FC_TILE_M)) return rc;
+        }
+        if (int rc = make_map_2d(&f.w_map, at(op.w_off), 64, uint64_t(op.n_w_chunks) * op.block_n, 64, op.block_n)) return rc;
+        f.n_tiles = op.n_tiles;
+        f.block_n = op.block_n;
+        f.epi = op.epi;
+        f.bias = reinterpret_cast<const float*>(at(op.bias_off));
+        f.row_scale = op.use_row_scale ? s->row_scale : nullptr;
+        f.acc_scale = op.f0;
+        f.aux = buf(op.aux);
+        f.aux_lo = buf(op.aux_lo);
+        f.aux_ld = op.aux >= 0 ? int(L.cols[op.aux]) : 0;
+        f.out = buf(op.out);
+        f.out_lo = buf(op.out_lo);
+        f.out_ld = op.out >= 0 ? int(L.cols[op.out]) : 0;
+        if ((op.aux_lo >= 0 && L.cols[op.aux_lo] != L.cols[op.aux]) || (op.out_lo >= 0 && L.cols[op.out_lo] != L.cols[op.out]))
+          return fail(AV1P_EINVAL, "hi/lo buffers differ in width");
+        f.tail_w = reinterpret_cast<const float*>(at(op.tail_w_off));
+        f.tail_b = reinterpret_cast<const float*>(at(op.tail_b_off));
+        f.tail_n = op.tail_n;
+        f.err_flag = g_ctx.watchdog_dev;
+        if ((op.epi == FC_EPI_ADD_RELU || op.epi == FC_EPI_GATE) && !f.aux) return fail(AV1P_EINVAL, "FC op needs aux");
+        if (op.epi == FC_EPI_HEAD && (!f.tail_w || !f.tail_b || op.n_tiles != 1 || op.tail_n < 1))
+          return fail(AV1P_EINVAL, "malformed head op");
+        if (op.epi != FC_EPI_HEAD && op.n_tiles * op.block_n > f.out_ld) return fail(AV1P_EINVAL, "FC output wider than its buffer");
+        for (int i = 0; i <= op.n_tiles; ++i) f.kb_begin[i] = op.kb_begin[i];
+        if (f.kb_begin[0] != 0 || f.kb_begin[op.n_tiles] != op.n_kb_total) return fail(AV1P_EINVAL, "bad K-block schedule");
+        for (int i = 0; i < op.n_kb_total; ++i) {
+          f.kb_src[i] = op.kb_src[i];
+          f.kb_w[i] = op.kb_w[i];
+          const int sb = op.src[op.kb_src[i] >> 14];
+          if (sb < 0 || uint32_t(op.kb_src[i] & 0x3FFF) * 64 + 64 > L.cols[sb]) return fail(AV1P_EINVAL, "K block outside its source buffer");
+          if (int(op.kb_w[i]) >= op.n_w_chunks) return fail(AV1P_EINVAL, "weight chunk index out of range");
+        }
+        break;
+      }
+      case AV1P_OP_SAM:
+      case AV1P_OP_FGVC_TAIL: {
+        P.src = buf(op.src[0]);
+        P.src_lo = buf(op.src[1]);
+        if (!P.src || L.cols[op.src[0]] != 512 || (op.src[1] >= 0 && L.cols[op.src[1]] != 512)) return fail(AV1P_EINVAL, "SAM/FGVC op needs a 512-wide source");
+        P.ld = 512;
+        P.f0 = op.f0;
+        P.f1 = op.f1;
+        P.w = reinterpret_cast<const float*>(at(op.w_off));
+        if (op.type == AV1P_OP_FGVC_TAIL && !P.w) return fail(AV1P_EINVAL, "FGVC tail without weights");
+        break;
+      }
+      default:
+        return fail(AV1P_EINVAL, "unknown op type %d", op.type);
+    }
+    s->ops.push_back(P);
+  }
+  return AV1P_OK;
+}
+
+int convert_input(const av1p_input* in, StemInput* si) {
+  memset(si, 0, sizeof *si);
+  if (!in) return fail(AV1P_EINVAL, "null input");
+  si->kind = in->kind;
+  if (in->kind == 0) {
+    if (!in->frames_dev || in->width <= 0 || in->height <= 0 || in->pitch < in->width)
+      return fail(AV1P_EINVAL, "bad frame geometry");
+    si->frames = in->frames_dev;
+    si->frame_stride = in->frame_stride;
+    si->width = in->width;
+    si->height = in->height;
+    si->pitch = in->pitch;
+    si->blocks_x = ceil_div(in->width, 16);
+    si->blocks_per_frame = si->blocks_x * ceil_div(in->height, 16);
+  } else if (in->kind == 1) {
+    if (!in->images_dev) return fail(AV1P_EINVAL, "null image tensor");
+    si->images = in->images_dev;
+    si->blocks_per_frame = 1;
+    si->blocks_x = 1;
+  } else {
+    return fail(AV1P_EINVAL, "unknown input kind %d", in->kind);
+  }
+  return AV1P_OK;
+}
+
+int run_stage(av1p_stage* s, const StemInput& si, const int32_t* idx, const int32_t* n_dev, int n, float* logits,
+              cudaStream_t st) {
+  if (n <= 0) return AV1P_OK;
+  if (n > s->cap) return fail(AV1P_EINVAL, "n=%d exceeds the stage capacity %d", n, s->cap);
+  for (PlannedOp& P : s->ops) {
+    switch (P.type) {
+      case AV1P_OP_STEM: {
+        StemParams sp = P.stem;
+        sp.in = si;
+        sp.idx = idx;
+        sp.n_dev = n_dev;
+        sp.n = n;
+        const int grid = std::min(ceil_div(n, STEM_NB), g_ctx.sms * 4);
+        stem_kernel<<<grid, STEM_THREADS, STEM_SMEM_BYTES, st>>>(sp);
+        break;
+      }
+      case AV1P_OP_FC: {
+        P.fc.n_rows_dev = n_dev;
+        P.fc.n_rows = n;
+        P.fc.logits = logits;
+        const int grid = std::min(g_ctx.sms, ceil_div(n, FC_TILE_M) * P.fc.n_tiles);
+        fc_tcgen05_kernel<<<grid, FC_THREADS, FC_SMEM_BYTES, st>>>(P.fc);
+        break;
+      }
+      case AV1P_OP_SAM: {
+        const int grid = std::min(ceil_div(n, 8), g_ctx.sms * 8);
+        sam_gate_kernel<<<grid, 256, 0, st>>>(P.src, P.src_lo, P.ld, n_dev, n, P.f0, P.f1, s->row_scale);
+        break;
+      }
+      case AV1P_OP_FGVC_TAIL: {
+        const int grid = std::min(ceil_div(n, 8), g_ctx.sms * 8);
+        fgvc_tail_kernel<<<grid, 256, 0, st>>>(P.src, P.src_lo, P.ld, n_dev, n, P.w, P.f0, logits);
+        break;
+      }
+    }
+  }
+  CUDA_TRY(cudaGetLastError());
+  return AV1P_OK;
+}
+
+}  // namespace
+
+extern "C" size_t av1p_stage_workspace_bytes(const av1p_model* m, int32_t capacity_rows) {
+  if (!m || capacity_rows <= 0) return 0;
+  return make_act_layout(&m, 1, capacity_rows).bytes + 1024;
+}
+
+extern "C" int av1p_stage_create(const av1p_model* m, int32_t capacity_rows, void* ws, size_t ws_bytes, av1p_stage** out) {
+  if (!m || !ws || !out || capacity_rows <= 0) return fail(AV1P_EINVAL, "bad argument");
+  if (int rc = ensure_ctx()) return rc;
+  ActLayout L = make_act_layout(&m, 1, capacity_rows);
+  uint8_t* base = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<uintptr_t>(ws), 1024));
+  if (size_t(base - static_cast<uint8_t*>(ws)) + L.bytes > ws_bytes)
+    return fail(AV1P_ENOMEM, "workspace too small: need %zu bytes", L.bytes + 1024);
+  av1p_stage* s = new (std::nothrow) av1p_stage();
+  if (!s) return fail(AV1P_ENOMEM, "host allocation failed");
+  if (int rc = plan_stage(m, L, base, s)) {
+    delete s;
+    return rc;
+  }
+  *out = s;
+  return AV1P_OK;
+}
+extern "C" void av1p_stage_destroy(av1p_stage* s) { delete s; }
+extern "C" int av1p_stage_launches_per_forward(const av1p_stage* s) { return s ? int(s->ops.size()) : 0; }
+
+extern "C" int av1p_stage_forward(av1p_stage* s, const av1p_input* in, const int32_t* idx_dev, const int32_t* n_dev,
+                                  int32_t n, float* logits_dev, void* stream) {
+  if (!s || !logits_dev) return fail(AV1P_EINVAL, "null argument");
+  StemInput si;
+  if (int rc = convert_input(in, &si)) return rc;
+  return run_stage(s, si, idx_dev, n_dev, n, logits_dev, static_cast<cudaStream_t>(stream));
+}
+
+// ------------------------------------------------------------------------------ routing ABI
+namespace {
+struct RouteScratch {
+  int tile_counts[2 * ROUTE_MAX_TILES];
+  unsigned int ticket;
+  int pad[63];
+};
+
+int launch_route(RouteParams rp, int n, cudaStream_t st) {
+  const int tiles = ceil_div(std::max(n, 1), ROUTE_TILE);
+  if (tiles > ROUTE_MAX_TILES) return fail(AV1P_EINVAL, "too many rows for one routing call (%d)", n);
+  route_count_kernel<<<tiles, ROUTE_THREADS, 0, st>>>(rp);
+  route_scatter_kernel<<<tiles, ROUTE_THREADS, 0, st>>>(rp);
+  CUDA_TRY(cudaGetLastError());
+  return AV1P_OK;
+}
+}  // namespace
+
+extern "C" size_t av1p_route_scratch_bytes(void) { return sizeof(RouteScratch); }
+
+extern "C" int av1p_route_stage1(const float* logits, const int32_t* n_dev, int32_t n, float thr, int32_t* idx,
+                                 int32_t* count, uint8_t* l8, int64_t* l64, void* scratch, void* stream) {
+  if (!logits || !idx || !count || !scratch || n < 0) return fail(AV1P_EINVAL, "bad argument");
+  if (n == 0) return AV1P_OK;
+  RouteScratch* sc = static_cast<RouteScratch*>(scratch);
+  RouteParams rp{};
+  rp.kind = 0;
+  rp.logits = logits;
+  rp.n_dev = n_dev;
+  rp.n = n;
+  rp.thr = thr;
+  rp.tile_counts = sc->tile_counts;
+  rp.ticket = &sc->ticket;
+  rp.out_idx0 = idx;
+  rp.out_idx1 = idx;   // never written for kind 0
+  rp.counts = count;   // counts[1] is written too: caller provides int32[2]
+  rp.labels_u8 = l8;
+  rp.labels_i64 = reinterpret_cast<long long*>(l64);
+  return launch_route(rp, n, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int av1p_route_stage2(const float* logits3, const int32_t* idx_in, const int32_t* n_dev, int32_t n,
+                                 int32_t* idx_rect, int32_t* idx_ab, int32_t* counts2, uint8_t* l8, int64_t* l64,
+                                 void* scratch, void* stream) {
+  if (!logits3 || !idx_in || !idx_rect || !idx_ab || !counts2 || !scratch || n < 0) return fail(AV1P_EINVAL, "bad argument");
+  if (n == 0) return AV1P_OK;
+  RouteScratch* sc = static_cast<RouteScratch*>(scratch);
+  RouteParams rp{};
+  rp.kind = 1;
+  rp.logits = logits3;
+  rp.src = idx_in;
+  rp.n_dev = n_dev;
+  rp.n = n;
+  rp.tile_counts = sc->tile_counts;
+  rp.ticket = &sc->ticket;
+  rp.out_idx0 = idx_rect;
+  rp.out_idx1 = idx_ab;
+  rp.counts = counts2;
+  rp.labels_u8 = l8;
+  rp.labels_i64 = reinterpret_cast<long long*>(l64);
+  return launch_route(rp, n, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int av1p_finalize_labels(const float* logits, int32_t k, int32_t base, const int32_t* idx,
+                                    const int32_t* n_dev, int32_t n, uint8_t* l8, int64_t* l64, void* stream) {
+  if (!logits || !idx || k < 1 || k > 4 || n < 0) return fail(AV1P_EINVAL, "bad argument");
+  if (n == 0) return AV1P_OK;
+  if (int rc = ensure_ctx()) return rc;
+  const int grid = std::min(ceil_div(n, 256), g_ctx.sms * 8);
+  finalize_labels_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      logits, k, base, idx, n_dev, n, l8, reinterpret_cast<long long*>(l64));
+  CUDA_TRY(cudaGetLastError());
+  return AV1P_OK;
+}
+
+// ------------------------------------------------------------------------------ extraction ABI
+template <typename OUT>
+static int launch_extract(const uint16_t* y, int w, int h, int pitch, int bs, OUT* out, void* stream) {
+  if (!y || !out || w <= 0 || h <= 0 || pitch < w) return fail(AV1P_EINVAL, "bad frame geometry");
+  if (bs != 8 && bs != 16 && bs != 32 && bs != 64) return fail(AV1P_EINVAL, "unsupported block size %d", bs);
+  if (int rc = ensure_ctx()) return rc;
+  const int bx = ceil_div(w, bs), by = ceil_div(h, bs);
+  const long long chunks = (long long)bx * bs / 8 * by * bs;
+  const int grid = int(std::min<long long>((chunks + 255) / 256, (long long)g_ctx.sms * 16));
+  extract_blocks_kernel<OUT><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(y, w, h, pitch, bs, bx, by, out);
+  CUDA_TRY(cudaGetLastError());
+  return AV1P_OK;
+}
+extern "C" int av1p_extract_u16(const uint16_t* y, int32_t w, int32_t h, int32_t pitch, int32_t bs, uint16_t* out, void* stream) {
+  return launch_extract<uint16_t>(y, w, h, pitch, bs, out, stream);
+}
+extern "C" int av1p_extract_norm_u16(const uint16_t* y, int32_t w, int32_t h, int32_t pitch, int32_t bs, float* out, void* stream) {
+  return launch_extract<float>(y, w, h, pitch, bs, out, stream);
+}
+
+// ------------------------------------------------------------------------------ cascade
+struct av1p_cascade {
+  av1p_stage stage[4];
+  int cap = 0;
+  float* logits[4] = {nullptr, nullptr, nullptr, nullptr};
+  int32_t* idx2 = nullptr;
+  int32_t* idx_rect = nullptr;
+  int32_t* idx_ab = nullptr;
+  int32_t* counts = nullptr;     // [0]=n2, [1]=scratch, [2]=nR, [3]=nA
+  RouteScratch* scratch = nullptr;
+};
+
+namespace {
+struct CascadeLayout {
+  ActLayout act;
+  size_t logits_off[4], idx_off[3], counts_off, scratch_off, bytes;
+};
+CascadeLayout make_cascade_layout(const av1p_model* const models[4], int capacity) {
+  CascadeLayout C;
+  C.act = make_act_layout(models, 4, capacity);
+  size_t o = C.act.bytes;
+  const int outs[4] = {1, 3, 2, 4};
+  for (int i = 0; i < 4; ++i) {
+    C.logits_off[i] = o;
+    o += align_up(size_t(C.act.cap) * outs[i] * 4, 1024);
+  }
+  for (int i = 0; i < 3; ++i) {
+    C.idx_off[i] = o;
+    o += align_up(size_t(C.act.cap) * 4, 1024);
+  }
+  C.counts_off = o;
+  o += 1024;
+  C.scratch_off = o;
+  o += align_up(sizeof(RouteScratch), 1024);
+  C.bytes = o;
+  return C;
+}
+}  // namespace
+
+extern "C" size_t av1p_cascade_workspace_bytes(const av1p_model* const models[4], int32_t capacity) {
+  if (!models || capacity <= 0) return 0;
+  for (int i = 0; i < 4; ++i)
+    if (!models[i]) return 0;
+  return make_cascade_layout(models, capacity).bytes + 1024;
+}
+
+extern "C" int av1p_cascade_create(const av1p_model* const models[4], int32_t capacity, void* ws, size_t ws_bytes,
+                                   av1p_cascade** out) {
+  if (!models || !ws || !out || capacity <= 0) return fail(AV1P_EINVAL, "bad argument");
+  const int outs[4] = {1, 3, 2, 4};
+  for (int i = 0; i < 4; ++i) {
+    if (!models[i]) return fail(AV1P_EINVAL, "null model %d", i);
+    if (int(models[i]->hdr.n_out) != outs[i])
+      return fail(AV1P_EINVAL, "model %d has %u outputs, the cascade needs %d", i, models[i]->hdr.n_out, outs[i]);
+  }
+  if (int rc = ensure_ctx()) return rc;
+  CascadeLayout C = make_cascade_layout(models, capacity);
+  uint8_t* base = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<uintptr_t>(ws), 1024));
+  if (size_t(base - static_cast<uint8_t*>(ws)) + C.bytes > ws_bytes)
+    return fail(AV1P_ENOMEM, "workspace too small: need %zu bytes", C.bytes + 1024);
+  av1p_cascade* c = new (std::nothrow) av1p_cascade();
+  if (!c) return fail(AV1P_ENOMEM, "host allocation failed");
+  c->cap = C.act.cap;
+  for (int i = 0; i < 4; ++i) {
+    if (int rc = plan_stage(models[i], C.act, base, &c->stage[i])) {
+      delete c;
+      return rc;
+    }
+    c->logits[i] = reinterpret_cast<float*>(base + C.logits_off[i]);
+  }
+  c->idx2 = reinterpret_cast<int32_t*>(base + C.idx_off[0]);
+  c->idx_rect = reinterpret_cast<int32_t*>(base + C.idx_off[1]);
+  c->idx_ab = reinterpret_cast<int32_t*>(base + C.idx_off[2]);
+  c->counts = reinterpret_cast<int32_t*>(base + C.counts_off);
+  c->scratch = reinterpret_cast<RouteScratch*>(base + C.scratch_off);
+  cudaError_t e = cudaMemset(base + C.counts_off, 0, C.bytes - C.counts_off);
+  if (e != cudaSuccess) {
+    delete c;
+    return fail(AV1P_ECUDA, "workspace init failed: %s", cudaGetErrorString(e));
+  }
+  *out = c;
+  return AV1P_OK;
+}
+extern "C" void av1p_cascade_destroy(av1p_cascade* c) { delete c; }
+
+extern "C" int av1p_cascade_launches_per_predict(const av1p_cascade* c) {
+  if (!c) return 0;
+  int n = 0;
+  for (int i = 0; i < 4; ++i) n += int(c->stage[i].ops.size());
+  return n + 2 /*route1*/ + 2 /*route2*/ + 2 /*finalize x2*/;
+}
+
+extern "C" const void* av1p_cascade_buffer(const av1p_cascade* c, int32_t which) {
+  if (!c) return nullptr;
+  switch (which) {
+    case 0: case 1: case 2: case 3: return c->logits[which];
+    case 4: return c->idx2;
+    case 5: return c->idx_rect;
+    case 6: return c->idx_ab;
+    case 7: return c->counts;
+  }
+  return nullptr;
+}
+
+// HierarchicalPipelineV6.predict (008:69-127) without its three host synchronisations: every
+// downstream kernel reads its row count from the device counters the routing kernels wrote.
+extern "C" int av1p_cascade_predict(av1p_cascade* c, const av1p_input* in, int32_t n_blocks, float thr, uint8_t* l8,
+                                    int64_t* l64, void* stream) {
+  if (!c) return fail(AV1P_EINVAL, "null cascade");
+  if (n_blocks < 0 || n_blocks > c->cap) return fail(AV1P_EINVAL, "n_blocks=%d outside [0, %d]", n_blocks, c->cap);
+  if (n_blocks == 0) return AV1P_OK;
+  StemInput si;
+  if (int rc = convert_input(in, &si)) return rc;
+  if (in->kind == 0 && (long long)si.blocks_per_frame * in->n_frames < n_blocks)
+    return fail(AV1P_EINVAL, "n_blocks exceeds the blocks in the given frames");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int32_t* n2 = c->counts + 0;
+  int32_t* n_rect = c->counts + 2;
+  int32_t* n_ab = c->counts + 3;
+  // Stage 1 on every block, then threshold + compaction (008:76-85)
+  if (int rc = run_stage(&c->stage[0], si, nullptr, nullptr, n_blocks, c->logits[0], st)) return rc;
+  if (int rc = av1p_route_stage1(c->logits[0], nullptr, n_blocks, thr, c->idx2, n2, l8, l64, c->scratch, st)) return rc;
+  // Stage 2 on the routed blocks, argmax + 3-way partition (008:91-103, 115-116)
+  if (int rc = run_stage(&c->stage[1], si, c->idx2, n2, n_blocks, c->logits[1], st)) return rc;
+  if (int rc = av1p_route_stage2(c->logits[1], c->idx2, n2, n_blocks, c->idx_rect, c->idx_ab, n_rect, l8, l64,
+                                 c->scratch, st))
+    return rc;
+  // Stage 3 specialists (008:105-125)
+  if (int rc = run_stage(&c->stage[2], si, c->idx_rect, n_rect, n_blocks, c->logits[2], st)) return rc;
+  if (int rc = av1p_finalize_labels(c->logits[2], 2, 2, c->idx_rect, n_rect, n_blocks, l8, l64, st)) return rc;
+  if (int rc = run_stage(&c->stage[3], si, c->idx_ab, n_ab, n_blocks, c->logits[3], st)) return rc;
+  if (int rc = av1p_finalize_labels(c->logits[3], 4, 4, c->idx_ab, n_ab, n_blocks, l8, l64, st)) return rc;
+  return AV1P_OK;
+}
+
+// ------------------------------------------------------------------------------ FC test hook
+extern "C" int av1p_fc_forward(const av1p_fc_desc* d, void* stream) {
+  if (!d || !d->a_dev[0] || !d->w_dev || !d->kb_begin || !d->kb_src || !d->kb_w) return fail(AV1P_EINVAL, "null argument");
+  if (int rc = ensure_ctx()) return rc;
+  if (d->n_tiles < 1 || d->n_tiles > FC_MAX_NT || d->block_n < 32 || d->block_n > FC_MAX_N || d->block_n % 32 ||
+      d->n_kb_total < 1 || d->n_kb_total > FC_MAX_KB || d->rows < 1 || d->n_w_chunks < 1)
+    return fail(AV1P_EINVAL, "bad FC shape");
+  FcParams f;
+  memset(&f, 0, sizeof f);
+  for (int i = 0; i < FC_MAX_SRC; ++i) {
+    const int j = d->a_dev[i] ? i : 0;
+    if (int rc = make_map_2d(&f.a_map[i], d->a_dev[j], d->a_cols[j], d->rows, d->a_cols[j], FC_TILE_M)) return rc;
+  }
+  if (int rc = make_map_2d(&f.w_map, d->w_dev, 64, uint64_t(d->n_w_chunks) * d->block_n, 64, d->block_n)) return rc;
+  f.n_rows_dev = d->n_dev;
+  f.n_rows = d->rows;
+  f.n_tiles = d->n_tiles;
+  f.block_n = d->block_n;
+  f.epi = d->epi;
+  f.bias = d->bias_dev;
+  f.row_scale = d->row_scale_dev;
+  f.acc_scale = d->acc_scale;
+  f.aux = static_cast<const __half*>(d->aux_dev);
+  f.aux_lo = static_cast<const __half*>(d->aux_lo_dev);
+  f.aux_ld = d->aux_ld;
+  f.out = static_cast<__half*>(d->out_dev);
+  f.out_lo = static_cast<__half*>(d->out_lo_dev);
+  f.out_ld = d->out_ld;
+  f.tail_w = d->tail_w_dev;
+  f.tail_b = d->tail_b_dev;
+  f.logits = d->logits_dev;
+  f.tail_n = d->tail_n;
+  f.err_flag = g_ctx.watchdog_dev;
+  for (int i = 0; i <= d->n_tiles; ++i) f.kb_begin[i] = d->kb_begin[i];
+  for (int i = 0; i < d->n_kb_total; ++i) {
+    f.kb_src[i] = d->kb_src[i];
+    f.kb_w[i] = d->kb_w[i];
+  }
+  const int grid = std::min(g_ctx.sms, ceil_div(d->rows, FC_TILE_M) * d->n_tiles);
+  fc_tcgen05_kernel<<<grid, FC_THREADS, FC_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(f);
+  CUDA_TRY(cudaGetLastError());
+  return AV1P_OK;
+}

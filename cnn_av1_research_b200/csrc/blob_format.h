@@ -1,0 +1,46 @@
+// On-disk / in-memory layout of a packed stage network ("blob").  Written by
+// cnn_av1_research_b200/packer.py, read by av1p_model_create.  Little-endian, all data offsets
+// are byte offsets from the start of the blob and 256-byte aligned.
+//
+// A blob is a tiny program over fp16 activation buffers: the packer decides the topology
+// (which reference layer reads / writes which buffer); the runtime only interprets ops.
+#pragma once
+#include <stdint.h>
+
+#define AV1P_BLOB_MAGIC 0x50315641u   /* "AV1P" */
+#define AV1P_BLOB_VERSION 3u
+#define AV1P_BLOB_MAX_NT 8
+#define AV1P_BLOB_MAX_KB 128
+
+enum Av1pOpType : int32_t {
+  AV1P_OP_STEM = 0,       // gather + /1023 + conv1/bn/relu/maxpool -> out buffer (1024 cols)
+  AV1P_OP_FC = 1,         // block-Toeplitz linear layer on tensor cores
+  AV1P_OP_SAM = 2,        // spatial-attention scalar of `src0` (512 cols) -> row_scale
+  AV1P_OP_FGVC_TAIL = 3,  // L2-normalise `src0` (512 cols) + cosine classifier -> logits[4]
+};
+
+#pragma pack(push, 1)
+struct Av1pBlobHeader {
+  uint32_t magic, version;
+  uint32_t stage_kind;    // informational (0 stage1, 1 stage2, 2 rect, 3 ab-fgvc, 4 ab-plain, 5 flat7)
+  uint32_t n_ops, n_bufs, n_out;
+  uint32_t reserved[2];
+  uint64_t ops_off, bufs_off, total_bytes;
+  uint64_t reserved2;
+};  // 64 bytes
+
+struct Av1pBlobOp {
+  int32_t type;
+  int32_t src[4];                   // activation sources (buffer ids, -1 = none).  Split precision: {x_hi, x_lo, y_hi, y_lo}
+  int32_t aux, aux_lo, out, out_lo; // buffer ids, -1 = none
+  int32_t n_tiles, block_n, epi, tail_n;
+  int32_t use_row_scale;
+  int32_t n_kb_total;               // schedule entries
+  int32_t n_w_chunks;               // [block_n x 64] fp16 weight tiles stored at w_off
+  float f0, f1;                     // SAM: w_avg, w_max.  FGVC tail: scale.  FC: f0 = acc_scale
+  uint64_t w_off, bias_off, tail_w_off, tail_b_off;   // 0 = absent
+  int32_t kb_begin[AV1P_BLOB_MAX_NT + 1];
+  uint16_t kb_src[AV1P_BLOB_MAX_KB];   // bits 14..15: index into src[], bits 0..13: K offset / 64
+  uint16_t kb_w[AV1P_BLOB_MAX_KB];     // weight chunk index
+};  // 16*4 + 2*4 + 4*8 + 9*4 + 2*128*2 = 652 bytes
+#pragma pack(pop)

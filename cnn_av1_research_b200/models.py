@@ -1,0 +1,278 @@
+"""Drop-in model classes with the reference's names, constructor signatures and `state_dict` keys.
+
+Reference: pesquisa_v6/v6_pipeline/models.py:24-251 (SEBlock, SpatialAttention, ImprovedBackbone, heads,
+Stage1Model/Stage2Model/Stage3RectModel/Stage3ABModel) and
+pesquisa_v6/scripts/006_train_stage3_ab_fgvc.py:217-297 (CosineClassifier, FGVCModel).
+
+The modules exist to hold parameters under the reference's key names, so that
+`model.load_state_dict(torch.load(ckpt)['model_state_dict'])` (scripts/008_run_pipeline_eval_v6.py:221-242)
+works unchanged.  `forward` does not run PyTorch layers: it packs the parameters once (BN folding,
+block-Toeplitz unrolling, see packer.py) and executes the hand-written sm_100a kernels of libav1p on
+the input's CUDA device.  There is no CPU path - calling `forward` on a CPU tensor raises.
+
+Only eval-mode inference is implemented (that is what the hot path, HierarchicalPipelineV6.predict,
+uses: 008:43-46).  Training-mode forward raises.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from . import _native as N
+from .runtime import NativeModel, NativeStage
+
+
+# ------------------------------------------------------------------------------------------------
+# Parameter containers (same attribute names as the reference => same state_dict keys)
+# ------------------------------------------------------------------------------------------------
+class SEBlock(nn.Module):
+    """models.py:24-43.  Keys: excitation.0.weight [C/r, C], excitation.2.weight [C, C/r]."""
+
+    def __init__(self, channels: int, reduction: int = 16):
+        super().__init__()
+        self.squeeze = nn.AdaptiveAvgPool2d(1)
+        self.excitation = nn.Sequential(
+            nn.Linear(channels, channels // reduction, bias=False), nn.ReLU(inplace=True),
+            nn.Linear(channels // reduction, channels, bias=False), nn.Sigmoid())
+
+
+class SpatialAttention(nn.Module):
+    """models.py:46-61.  Key: conv.weight [1, 2, 7, 7]."""
+
+    def __init__(self, kernel_size: int = 7):
+        super().__init__()
+        self.conv = nn.Conv2d(2, 1, kernel_size, padding=kernel_size // 2, bias=False)
+        self.sigmoid = nn.Sigmoid()
+
+
+class _ResidualUnit(nn.Module):
+    """Parameter layout of torchvision's BasicBlock (conv1, bn1, conv2, bn2, optional downsample.{0,1})."""
+
+    def __init__(self, c_in: int, c_out: int, stride: int):
+        super().__init__()
+        self.conv1 = nn.Conv2d(c_in, c_out, 3, stride, 1, bias=False)
+        self.bn1 = nn.BatchNorm2d(c_out)
+        self.relu = nn.ReLU(inplace=True)
+        self.conv2 = nn.Conv2d(c_out, c_out, 3, 1, 1, bias=False)
+        self.bn2 = nn.BatchNorm2d(c_out)
+        self.downsample = None
+        if stride != 1 or c_in != c_out:
+            self.downsample = nn.Sequential(nn.Conv2d(c_in, c_out, 1, stride, bias=False), nn.BatchNorm2d(c_out))
+
+
+def _init_like_torchvision(module: nn.Module) -> None:
+    # torchvision.models.resnet.ResNet.__init__: kaiming_normal_(fan_out, relu) for convs, BN weight 1 / bias 0
+    for m in module.modules():
+        if isinstance(m, nn.Conv2d):
+            nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+        elif isinstance(m, nn.BatchNorm2d):
+            nn.init.constant_(m.weight, 1.0)
+            nn.init.constant_(m.bias, 0.0)
+
+
+class ImprovedBackbone(nn.Module):
+    """models.py:64-126: ResNet-18 trunk with a 1-channel conv1, SE after every layer, spatial attention."""
+
+    def __init__(self, pretrained: bool = True):
+        super().__init__()
+        self.conv1 = nn.Conv2d(1, 64, kernel_size=7, stride=2, padding=3, bias=False)
+        self.bn1 = nn.BatchNorm2d(64)
+        self.relu = nn.ReLU(inplace=True)
+        self.maxpool = nn.MaxPool2d(kernel_size=3, stride=2, padding=1)
+        self.layer1 = nn.Sequential(_ResidualUnit(64, 64, 1), _ResidualUnit(64, 64, 1))
+        self.layer2 = nn.Sequential(_ResidualUnit(64, 128, 2), _ResidualUnit(128, 128, 1))
+        self.layer3 = nn.Sequential(_ResidualUnit(128, 256, 2), _ResidualUnit(256, 256, 1))
+        self.layer4 = nn.Sequential(_ResidualUnit(256, 512, 2), _ResidualUnit(512, 512, 1))
+        for layer in (self.layer1, self.layer2, self.layer3, self.layer4):
+            _init_like_torchvision(layer)
+        _init_like_torchvision(self.bn1)
+        self.se1, self.se2, self.se3, self.se4 = SEBlock(64), SEBlock(128), SEBlock(256), SEBlock(512)
+        self.spatial_attn = SpatialAttention()
+        self.avgpool = nn.AdaptiveAvgPool2d((1, 1))
+        if pretrained:
+            self._load_imagenet()
+
+    def _load_imagenet(self) -> None:
+        # models.py:73-80: ImageNet ResNet-18, conv1 = mean over RGB.  Needs torchvision and its cached weights.
+        try:
+            from torchvision.models import ResNet18_Weights, resnet18
+            ref = resnet18(weights=ResNet18_Weights.IMAGENET1K_V1)
+        except Exception as exc:  # offline box, no torchvision, ...
+            raise RuntimeError("pretrained=True needs torchvision's ImageNet ResNet-18 weights, which are not "
+                               "available here; construct with pretrained=False and load a checkpoint") from exc
+        own = self.state_dict()
+        for k, v in ref.state_dict().items():
+            if k == "conv1.weight":
+                own[k].copy_(v.mean(dim=1, keepdim=True))
+            elif k in own and own[k].shape == v.shape:
+                own[k].copy_(v)
+
+
+class Stage1BinaryHead(nn.Module):
+    """models.py:129-149.  Keys head.{0,3}.{weight,bias}, temperature."""
+
+    def __init__(self, in_features: int = 512, dropout: float = 0.3):
+        super().__init__()
+        self.head = nn.Sequential(nn.Linear(in_features, 256), nn.ReLU(inplace=True), nn.Dropout(dropout), nn.Linear(256, 1))
+        self.temperature = nn.Parameter(torch.ones(1) * 1.5)
+
+
+def _three_layer_head(in_features: int, h1: int, h2: int, n_out: int, dropout: float) -> nn.Sequential:
+    return nn.Sequential(nn.Linear(in_features, h1), nn.ReLU(inplace=True), nn.Dropout(dropout),
+                         nn.Linear(h1, h2), nn.ReLU(inplace=True), nn.Dropout(dropout), nn.Linear(h2, n_out))
+
+
+class Stage2ThreeWayHead(nn.Module):
+    """models.py:152-167."""
+
+    def __init__(self, in_features: int = 512, dropout: float = 0.4):
+        super().__init__()
+        self.head = _three_layer_head(in_features, 256, 128, 3, dropout)
+
+
+class Stage3RectHead(nn.Module):
+    """models.py:170-185."""
+
+    def __init__(self, in_features: int = 512, dropout: float = 0.2):
+        super().__init__()
+        self.head = _three_layer_head(in_features, 128, 64, 2, dropout)
+
+
+class Stage3ABHead(nn.Module):
+    """models.py:188-203."""
+
+    def __init__(self, in_features: int = 512, dropout: float = 0.5):
+        super().__init__()
+        self.head = _three_layer_head(in_features, 256, 128, 4, dropout)
+
+
+class CosineClassifier(nn.Module):
+    """006_train_stage3_ab_fgvc.py:217-243.  Key: weight [num_classes, feat_dim]."""
+
+    def __init__(self, feat_dim: int, num_classes: int, scale: float = 20.0):
+        super().__init__()
+        self.weight = nn.Parameter(torch.randn(num_classes, feat_dim))
+        self.scale = scale
+
+
+# ------------------------------------------------------------------------------------------------
+# Stage models: forward() runs on libav1p
+# ------------------------------------------------------------------------------------------------
+class _NativeStageModule(nn.Module):
+    """Shared machinery: pack on first use (and whenever a parameter changes), cache the plan."""
+
+    _kind: str = ""
+    #: "fp16x3" (split fp16 operands on the tensor cores, fp32-grade logits - the default) or "fp16"
+    #: (single product, ~3x less tensor work, logits within ~1e-1 of fp32).  Set before the first forward.
+    precision: str = "fp16x3"
+
+    def __init__(self):
+        super().__init__()
+        self._native_model: Optional[NativeModel] = None
+        self._native_stage: Optional[NativeStage] = None
+        self._native_key = None
+
+    def _param_key(self, device):
+        return (str(device),) + tuple((t.data_ptr(), t._version) for t in self.state_dict(keep_vars=True).values())
+
+    def native_model(self, device) -> NativeModel:
+        key = (self.precision,) + self._param_key(device)
+        if self._native_model is None or self._native_key != key:
+            sd = {k: v.detach().to("cpu", torch.float32) if v.is_floating_point() else v.detach().cpu()
+                  for k, v in self.state_dict().items()}
+            self._native_model = NativeModel(self._kind, sd, device, self.precision)
+            self._native_stage = None
+            self._native_key = key
+        return self._native_model
+
+    def _native_forward(self, x: torch.Tensor) -> torch.Tensor:
+        if self.training:
+            raise RuntimeError(f"{type(self).__name__}: only eval-mode inference is implemented on the B200 path; call .eval()")
+        if not x.is_cuda:
+            raise RuntimeError(f"{type(self).__name__}.forward needs a CUDA tensor: this package has no CPU path")
+        if x.dim() != 4 or tuple(x.shape[1:]) != (1, 16, 16):
+            raise ValueError(f"expected input [B,1,16,16], got {tuple(x.shape)}")
+        x = x.contiguous().float()
+        n = x.shape[0]
+        model = self.native_model(x.device)
+        if self._native_stage is None or self._native_stage.capacity < n:
+            self._native_stage = NativeStage(model, max(n, 256))
+        return self._native_stage.forward(N.images_input(x), n)
+
+
+class Stage1Model(_NativeStageModule):
+    """models.py:206-215."""
+    _kind = "stage1"
+
+    def __init__(self, pretrained: bool = True):
+        super().__init__()
+        self.backbone = ImprovedBackbone(pretrained)
+        self.head = Stage1BinaryHead()
+
+    def forward(self, x, apply_temp: bool = False):
+        logits = self._native_forward(x)
+        if apply_temp:  # models.py:147-148 (not used by predict)
+            logits = logits / self.head.temperature.to(logits.device)
+        return logits
+
+
+class Stage2Model(_NativeStageModule):
+    """models.py:218-227."""
+    _kind = "stage2"
+
+    def __init__(self, pretrained: bool = True):
+        super().__init__()
+        self.backbone = ImprovedBackbone(pretrained)
+        self.head = Stage2ThreeWayHead()
+
+    def forward(self, x):
+        return self._native_forward(x)
+
+
+class Stage3RectModel(_NativeStageModule):
+    """models.py:230-239."""
+    _kind = "rect"
+
+    def __init__(self, pretrained: bool = True):
+        super().__init__()
+        self.backbone = ImprovedBackbone(pretrained)
+        self.head = Stage3RectHead()
+
+    def forward(self, x):
+        return self._native_forward(x)
+
+
+class Stage3ABModel(_NativeStageModule):
+    """models.py:242-251."""
+    _kind = "ab"
+
+    def __init__(self, pretrained: bool = True):
+        super().__init__()
+        self.backbone = ImprovedBackbone(pretrained)
+        self.head = Stage3ABHead()
+
+    def forward(self, x):
+        return self._native_forward(x)
+
+
+class FGVCModel(_NativeStageModule):
+    """006_train_stage3_ab_fgvc.py:246-297: base_model.backbone + feat_proj + L2-norm + cosine classifier."""
+    _kind = "ab_fgvc"
+
+    def __init__(self, base_model, num_classes: int = 4, feat_dim: int = 512):
+        super().__init__()
+        if num_classes != 4 or feat_dim != 512:
+            raise ValueError("the B200 path implements the configuration the pipeline uses: num_classes=4, feat_dim=512")
+        self.backbone = base_model.backbone
+        self.feat_proj = nn.Sequential(
+            nn.Linear(512, feat_dim), nn.BatchNorm1d(feat_dim), nn.ReLU(inplace=True), nn.Dropout(0.3),
+            nn.Linear(feat_dim, feat_dim), nn.BatchNorm1d(feat_dim), nn.ReLU(inplace=True), nn.Dropout(0.3))
+        self.classifier = CosineClassifier(feat_dim, num_classes, scale=20.0)
+        self.feat_dim = feat_dim
+
+    def forward(self, x, return_features: bool = False):
+        if return_features:
+            raise NotImplementedError("return_features=True is a training-time (center loss) option; not on the inference path")
+        return self._native_forward(x)

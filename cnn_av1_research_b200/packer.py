@@ -1,0 +1,356 @@
+"""Weight packer: reference `state_dict` -> device blob for libav1p (csrc/blob_format.h).
+
+What it does, per stage network (reference pesquisa_v6/v6_pipeline/models.py:64-251 and
+scripts/006_train_stage3_ab_fgvc.py:246-297):
+
+* folds every eval-mode BatchNorm into the preceding bias-free convolution / linear layer in float64
+  (`W' = W * gamma / sqrt(var + eps)`, `b' = beta - mean * gamma / sqrt(var + eps)`, eps = 1e-5);
+* unrolls each convolution of the 16x16-input backbone over its tiny spatial grid (4x4, 2x2, 1x1)
+  into a block-Toeplitz matrix acting on activations stored `[position][channel]` per block, splits
+  it into `[block_n x 64]` fp16 tiles and keeps only the tiles that are not identically zero
+  (padding taps and out-of-window positions vanish exactly, so skipping them is numerically neutral);
+* merges a residual unit's 1x1 stride-2 downsample branch into its second convolution by
+  concatenating along K (two activation sources, one accumulator);
+* rewrites squeeze-excite as two linear layers (the spatial mean is folded into the first weight) with
+  a sigmoid-gate epilogue, and spatial attention at 1x1 as a per-row scalar applied by the next layer;
+* emits the op program the runtime interprets.
+
+Everything here is host-side numpy; it runs once per `state_dict`.
+"""
+from __future__ import annotations
+
+import struct
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+BLOB_MAGIC = 0x50315641
+BLOB_VERSION = 3
+MAX_NT = 8
+MAX_KB = 128
+TILE_K = 64
+
+OP_STEM, OP_FC, OP_SAM, OP_FGVC_TAIL = 0, 1, 2, 3
+EPI_LINEAR, EPI_RELU, EPI_ADD_RELU, EPI_GATE, EPI_HEAD = 0, 1, 2, 3, 4
+
+STAGE_KINDS = {"stage1": 0, "stage2": 1, "rect": 2, "ab_fgvc": 3, "ab": 4}
+NUM_OUTPUTS = {"stage1": 1, "stage2": 3, "rect": 2, "ab_fgvc": 4, "ab": 4}
+
+BN_EPS = 1e-5
+
+# activation buffers (fp16 columns per block row).  In split precision every buffer X has a twin X_lo
+# holding fp16(x - fp16(x)); the twins get ids len(BUF_COLS) + id(X).
+BUF_COLS = {"B0": 1024, "B1": 1024, "B2": 1024, "C0": 512, "C1": 512, "C2": 512, "D0": 256, "D1": 256, "D2": 256, "H": 64}
+BUF_IDS = {name: i for i, name in enumerate(BUF_COLS)}
+PRECISIONS = ("fp16x3", "fp16")
+
+
+def _hi(name: Optional[str]) -> int:
+    return BUF_IDS[name] if name else -1
+
+
+def _lo(name: Optional[str], precision: str) -> int:
+    return BUF_IDS[name] + len(BUF_COLS) if (name and precision == "fp16x3") else -1
+
+
+def _np64(t) -> np.ndarray:
+    if hasattr(t, "detach"):
+        t = t.detach().cpu().numpy()
+    return np.asarray(t, dtype=np.float64)
+
+
+def fold_bn(weight: np.ndarray, bias: Optional[np.ndarray], sd, bn: str) -> Tuple[np.ndarray, np.ndarray]:
+    """Fold eval-mode BN `bn` into the preceding layer (weight's dim 0 is the output channel)."""
+    scale = _np64(sd[bn + ".weight"]) / np.sqrt(_np64(sd[bn + ".running_var"]) + BN_EPS)
+    shift = _np64(sd[bn + ".bias"]) - _np64(sd[bn + ".running_mean"]) * scale
+    w = weight * scale.reshape((-1,) + (1,) * (weight.ndim - 1))
+    b = shift if bias is None else bias * scale + shift
+    return w, b
+
+
+def conv_as_dense(w: np.ndarray, h_in: int, w_in: int, stride: int, pad: int) -> Tuple[np.ndarray, int, int]:
+    """Unroll a convolution over an (h_in x w_in) grid: returns D[(oy,ox,co), (iy,ix,ci)], h_out, w_out."""
+    c_out, c_in, kh, kw = w.shape
+    h_out = (h_in + 2 * pad - kh) // stride + 1
+    w_out = (w_in + 2 * pad - kw) // stride + 1
+    d = np.zeros((h_out * w_out * c_out, h_in * w_in * c_in), dtype=np.float64)
+    for oy in range(h_out):
+        for ox in range(w_out):
+            r0 = (oy * w_out + ox) * c_out
+            for ky in range(kh):
+                iy = oy * stride - pad + ky
+                if not 0 <= iy < h_in:
+                    continue
+                for kx in range(kw):
+                    ix = ox * stride - pad + kx
+                    if not 0 <= ix < w_in:
+                        continue
+                    c0 = (iy * w_in + ix) * c_in
+                    d[r0:r0 + c_out, c0:c0 + c_in] = w[:, :, ky, kx]
+    return d, h_out, w_out
+
+
+@dataclass
+class _Op:
+    type: int
+    src: List[int] = field(default_factory=lambda: [-1, -1, -1, -1])
+    aux: int = -1
+    aux_lo: int = -1
+    out: int = -1
+    out_lo: int = -1
+    n_tiles: int = 0
+    block_n: int = 0
+    epi: int = 0
+    tail_n: int = 0
+    use_row_scale: int = 0
+    n_w_chunks: int = 0
+    f0: float = 0.0
+    f1: float = 0.0
+    kb_begin: List[int] = field(default_factory=list)
+    kb_src: List[int] = field(default_factory=list)
+    kb_w: List[int] = field(default_factory=list)
+    w: Optional[np.ndarray] = None        # fp16 [n_w_chunks*block_n, 64]  (stem / fgvc: float32 array)
+    bias: Optional[np.ndarray] = None     # float32
+    tail_w: Optional[np.ndarray] = None   # float32 [tail_n, block_n]
+    tail_b: Optional[np.ndarray] = None   # float32 [tail_n]
+    name: str = ""
+
+
+def make_fc_op(name: str, dense: Sequence[np.ndarray], srcs: Sequence[str], out: Optional[str], bias: Optional[np.ndarray],
+               epi: int, block_n: int, precision: str, aux: Optional[str] = None, use_row_scale: bool = False,
+               tail_w: Optional[np.ndarray] = None, tail_b: Optional[np.ndarray] = None) -> _Op:
+    """Tile dense matrices D_s [N, K_s] (one per activation source) into the block-sparse schedule.
+
+    Weights are multiplied by a power of two S (acc_scale = 1/S undoes it in the epilogue) so that both
+    the fp16 value and, in split precision, its fp16 residual sit in fp16's normal range.
+    """
+    n = dense[0].shape[0]
+    assert all(d.shape[0] == n for d in dense) and 1 <= len(dense) <= 2 and precision in PRECISIONS
+    n_pad = -(-n // block_n) * block_n
+    n_tiles = n_pad // block_n
+    assert n_tiles <= MAX_NT and block_n % 32 == 0 and block_n <= 256
+    wmax = max(float(np.abs(d).max()) for d in dense)
+    scale = 2.0 ** int(np.clip(np.floor(np.log2(8192.0 / wmax)), 0, 16)) if wmax > 0 else 1.0
+    split = precision == "fp16x3"
+    chunks, kb_begin, kb_src, kb_w = [], [0], [], []
+    for t in range(n_tiles):
+        r0, r1 = t * block_n, min((t + 1) * block_n, n)
+        for s, d in enumerate(dense):
+            k = d.shape[1]
+            assert k % TILE_K == 0 and k <= BUF_COLS[srcs[s]]
+            for kb in range(k // TILE_K):
+                blk = d[r0:r1, kb * TILE_K:(kb + 1) * TILE_K]
+                if not np.any(blk != 0.0):
+                    continue
+                tile = np.zeros((block_n, TILE_K), dtype=np.float64)
+                tile[: r1 - r0] = blk * scale
+                ci = len(chunks)
+                chunks.append(tile)
+                kb_src.append(((2 * s) << 14) | kb)
+                kb_w.append(ci)                     # (x_hi, w_hi)
+                if split:
+                    kb_src.append(((2 * s) << 14) | kb)
+                    kb_w.append(-(ci + 1))          # (x_hi, w_lo): patched below once the hi count is known
+                    kb_src.append(((2 * s + 1) << 14) | kb)
+                    kb_w.append(ci)                 # (x_lo, w_hi)
+        if len(kb_src) == kb_begin[-1]:
+            # an all-zero tile still needs one K block so that the accumulator is defined
+            kb_src.append(0)
+            kb_w.append(len(chunks))
+            chunks.append(np.zeros((block_n, TILE_K)))
+        kb_begin.append(len(kb_src))
+    assert len(kb_src) <= MAX_KB, f"{name}: {len(kb_src)} schedule entries"
+    w64 = np.concatenate(chunks, axis=0)
+    if np.abs(w64).max() >= 65504.0:
+        raise ValueError(f"{name}: folded weight {np.abs(w64).max():.3e} does not fit fp16")
+    w_hi = w64.astype(np.float16)
+    w = w_hi
+    if split:
+        w_lo = (w64 - w_hi.astype(np.float64)).astype(np.float16)
+        w = np.concatenate([w_hi, w_lo], axis=0)
+        kb_w = [i if i >= 0 else len(chunks) + (-i - 1) for i in kb_w]
+    b = None
+    if bias is not None:
+        b = np.zeros(n_pad, dtype=np.float32)
+        b[:n] = bias.astype(np.float32)
+    src = [-1, -1, -1, -1]
+    for i, nm in enumerate(srcs):
+        src[2 * i], src[2 * i + 1] = _hi(nm), _lo(nm, precision)
+    op = _Op(OP_FC, src=src, aux=_hi(aux), aux_lo=_lo(aux, precision), out=_hi(out), out_lo=_lo(out, precision),
+             n_tiles=n_tiles, block_n=block_n, epi=epi, use_row_scale=int(use_row_scale),
+             n_w_chunks=w.shape[0] // block_n, f0=1.0 / scale, kb_begin=kb_begin, kb_src=kb_src, kb_w=kb_w,
+             w=w, bias=b, name=name)
+    if epi == EPI_HEAD:
+        assert n_tiles == 1 and tail_w is not None and tail_w.shape[1] == n
+        tw = np.zeros((tail_w.shape[0], block_n), dtype=np.float32)
+        tw[:, :n] = tail_w.astype(np.float32)
+        op.tail_w, op.tail_b, op.tail_n = tw, tail_b.astype(np.float32), tail_w.shape[0]
+    return op
+
+
+def _block_n(n: int) -> int:
+    return 256 if n >= 256 else -(-n // 32) * 32
+
+
+def backbone_ops(sd, precision: str = "fp16x3", prefix: str = "backbone.") -> List[_Op]:
+    """Op program for ImprovedBackbone.forward (models.py:104-121).  Result: x4' in C1, SAM scalar in row_scale."""
+    p = prefix
+    ops: List[_Op] = []
+    # --- stem: conv1 + bn1 (+ relu + maxpool in the kernel).  fp32 weights, taps padded 49 -> 52.
+    w, b = fold_bn(_np64(sd[p + "conv1.weight"]), None, sd, p + "bn1")
+    wst = np.zeros((64, 52), dtype=np.float32)
+    wst[:, :49] = w.reshape(64, 49).astype(np.float32)
+    ops.append(_Op(OP_STEM, out=_hi("B0"), out_lo=_lo("B0", precision), w=wst, bias=b.astype(np.float32), name="stem"))
+
+    def conv_bn(unit: str, conv: str, bn: str, grid: int, stride: int):
+        wf, bf = fold_bn(_np64(sd[f"{unit}.{conv}.weight"]), None, sd, f"{unit}.{bn}")
+        pad = wf.shape[-1] // 2
+        d, ho, wo = conv_as_dense(wf, grid, grid, stride, pad)
+        return d, np.tile(bf, ho * wo), ho
+
+    def se(layer: int, grid: int, src: str, dst: str):
+        w1 = _np64(sd[f"{p}se{layer}.excitation.0.weight"])     # [C/16, C]
+        w2 = _np64(sd[f"{p}se{layer}.excitation.2.weight"])     # [C, C/16]
+        npos = grid * grid
+        d1 = np.zeros((64, npos * w1.shape[1]))
+        d1[: w1.shape[0]] = np.tile(w1 / npos, (1, npos))       # mean over positions folded in
+        d2 = np.zeros((npos * w2.shape[0], 64))
+        d2[:, : w2.shape[1]] = np.tile(w2, (npos, 1))
+        ops.append(make_fc_op(f"se{layer}.fc1", [d1], [src], "H", None, EPI_RELU, 64, precision))
+        ops.append(make_fc_op(f"se{layer}.fc2", [d2], ["H"], dst, None, EPI_GATE, _block_n(d2.shape[0]), precision, aux=src))
+
+    # --- layer1: 4x4 grid, 64 ch.  a0=B0
+    u = p + "layer1.0"
+    d, b, _ = conv_bn(u, "conv1", "bn1", 4, 1)
+    ops.append(make_fc_op(u + ".conv1", [d], ["B0"], "B1", b, EPI_RELU, 256, precision))
+    d, b, _ = conv_bn(u, "conv2", "bn2", 4, 1)
+    ops.append(make_fc_op(u + ".conv2", [d], ["B1"], "B2", b, EPI_ADD_RELU, 256, precision, aux="B0"))
+    u = p + "layer1.1"
+    d, b, _ = conv_bn(u, "conv1", "bn1", 4, 1)
+    ops.append(make_fc_op(u + ".conv1", [d], ["B2"], "B1", b, EPI_RELU, 256, precision))
+    d, b, _ = conv_bn(u, "conv2", "bn2", 4, 1)
+    ops.append(make_fc_op(u + ".conv2", [d], ["B1"], "B0", b, EPI_ADD_RELU, 256, precision, aux="B2"))
+    se(1, 4, "B0", "B1")                                         # x1 = B1
+
+    # --- layers 2..4: (input buffer, grid in, three scratch buffers of the output width)
+    plan = ((2, "B1", 4, ("C0", "C1", "C2")), (3, "C0", 2, ("D0", "D1", "D2")), (4, "D0", 1, ("C1", "C2", "C0")))
+    for layer, x_in, grid, (t0, t1, t2) in plan:
+        u = f"{p}layer{layer}.0"
+        d, b, g_out = conv_bn(u, "conv1", "bn1", grid, 2)
+        ops.append(make_fc_op(u + ".conv1", [d], [x_in], t0, b, EPI_RELU, _block_n(d.shape[0]), precision))
+        d2, b2, _ = conv_bn(u, "conv2", "bn2", g_out, 1)
+        dd, bd, _ = conv_bn(u, "downsample.0", "downsample.1", grid, 2)
+        ops.append(make_fc_op(u + ".conv2+downsample", [d2, dd], [t0, x_in], t1, b2 + bd, EPI_RELU, _block_n(d2.shape[0]), precision))
+        u = f"{p}layer{layer}.1"
+        d, b, _ = conv_bn(u, "conv1", "bn1", g_out, 1)
+        ops.append(make_fc_op(u + ".conv1", [d], [t1], t0, b, EPI_RELU, _block_n(d.shape[0]), precision))
+        d, b, _ = conv_bn(u, "conv2", "bn2", g_out, 1)
+        ops.append(make_fc_op(u + ".conv2", [d], [t0], t2, b, EPI_ADD_RELU, _block_n(d.shape[0]), precision, aux=t1))
+        se(layer, g_out, t2, t0)                                 # x_layer = t0
+    # after layer4: x4' = C1 (t0 of the last plan row)
+    # --- spatial attention at 1x1: centre tap of the 7x7 kernel only (models.py:56-61)
+    wsa = _np64(sd[p + "spatial_attn.conv.weight"])
+    ops.append(_Op(OP_SAM, src=[_hi("C1"), _lo("C1", precision), -1, -1], f0=float(wsa[0, 0, 3, 3]), f1=float(wsa[0, 1, 3, 3]),
+                   name="spatial_attn"))
+    return ops
+
+
+def head_ops(kind: str, sd, precision: str = "fp16x3") -> List[_Op]:
+    """Stage heads (models.py:129-203) and the FGVC tail (006:261-293); input x4' in C1 (+ row_scale)."""
+    ops: List[_Op] = []
+    lin = lambda k: (_np64(sd[f"head.head.{k}.weight"]), _np64(sd[f"head.head.{k}.bias"]))
+    if kind == "stage1":
+        w0, b0 = lin(0)
+        w1, b1 = lin(3)
+        ops.append(make_fc_op("head.0+3", [w0], ["C1"], None, b0, EPI_HEAD, 256, precision, use_row_scale=True, tail_w=w1, tail_b=b1))
+    elif kind in ("stage2", "ab", "rect"):
+        w0, b0 = lin(0)
+        w1, b1 = lin(3)
+        w2, b2 = lin(6)
+        ops.append(make_fc_op("head.0", [w0], ["C1"], "D0", b0, EPI_RELU, _block_n(w0.shape[0]), precision, use_row_scale=True))
+        # head.3 reads the first w0.shape[0] columns of D0
+        ops.append(make_fc_op("head.3+6", [w1], ["D0"], None, b1, EPI_HEAD, _block_n(w1.shape[0]), precision, tail_w=w2, tail_b=b2))
+    elif kind == "ab_fgvc":
+        w0, b0 = fold_bn(_np64(sd["feat_proj.0.weight"]), _np64(sd["feat_proj.0.bias"]), sd, "feat_proj.1")
+        w1, b1 = fold_bn(_np64(sd["feat_proj.4.weight"]), _np64(sd["feat_proj.4.bias"]), sd, "feat_proj.5")
+        ops.append(make_fc_op("feat_proj.0+1", [w0], ["C1"], "C0", b0, EPI_RELU, 256, precision, use_row_scale=True))
+        ops.append(make_fc_op("feat_proj.4+5", [w1], ["C0"], "C2", b1, EPI_RELU, 256, precision))
+        wc = _np64(sd["classifier.weight"])
+        wc = wc / np.maximum(np.linalg.norm(wc, axis=1, keepdims=True), 1e-12)    # F.normalize(weight)
+        ops.append(_Op(OP_FGVC_TAIL, src=[_hi("C2"), _lo("C2", precision), -1, -1], f0=20.0, w=wc.astype(np.float32),
+                       name="cosine_classifier"))
+    else:
+        raise ValueError(f"unknown stage kind {kind!r}")
+    return ops
+
+
+def _align(n: int, a: int = 256) -> int:
+    return -(-n // a) * a
+
+
+OP_FMT = "<16i2f4Q9i128H128H"
+OP_BYTES = struct.calcsize(OP_FMT)
+
+
+def serialise(kind: str, ops: List[_Op], precision: str) -> bytes:
+    header_fmt = "<8I4Q"
+    assert struct.calcsize(header_fmt) == 64 and OP_BYTES == 652
+    cols = list(BUF_COLS.values()) * (2 if precision == "fp16x3" else 1)
+    n_bufs = len(cols)
+    ops_off = 64
+    bufs_off = ops_off + OP_BYTES * len(ops)
+    cursor = _align(bufs_off + 4 * n_bufs)
+    data = []
+
+    def put(arr: Optional[np.ndarray]) -> int:
+        nonlocal cursor
+        if arr is None:
+            return 0
+        raw = np.ascontiguousarray(arr).tobytes()
+        off = cursor
+        data.append((off, raw))
+        cursor = _align(cursor + len(raw))
+        return off
+
+    table = b""
+    for op in ops:
+        w_off, b_off, tw_off, tb_off = put(op.w), put(op.bias), put(op.tail_w), put(op.tail_b)
+        kbb = list(op.kb_begin) + [0] * (MAX_NT + 1 - len(op.kb_begin))
+        kbs = list(op.kb_src) + [0] * (MAX_KB - len(op.kb_src))
+        kbw = list(op.kb_w) + [0] * (MAX_KB - len(op.kb_w))
+        table += struct.pack(OP_FMT, op.type, *op.src, op.aux, op.aux_lo, op.out, op.out_lo, op.n_tiles, op.block_n,
+                             op.epi, op.tail_n, op.use_row_scale, len(op.kb_src), op.n_w_chunks, op.f0, op.f1,
+                             w_off, b_off, tw_off, tb_off, *kbb, *kbs, *kbw)
+    total = cursor
+    blob = bytearray(total)
+    blob[0:64] = struct.pack(header_fmt, BLOB_MAGIC, BLOB_VERSION, STAGE_KINDS[kind], len(ops), n_bufs, NUM_OUTPUTS[kind],
+                             PRECISIONS.index(precision), 0, ops_off, bufs_off, total, 0)
+    blob[ops_off:ops_off + len(table)] = table
+    blob[bufs_off:bufs_off + 4 * n_bufs] = struct.pack(f"<{n_bufs}I", *cols)
+    for off, raw in data:
+        blob[off:off + len(raw)] = raw
+    return bytes(blob)
+
+
+def pack_stage(kind: str, state_dict, precision: str = "fp16x3") -> bytes:
+    """`state_dict` of Stage1Model / Stage2Model / Stage3RectModel / Stage3ABModel / FGVCModel -> blob.
+
+    precision: "fp16x3" (default; split fp16 operands, fp32-grade logits) or "fp16" (single product).
+    """
+    if kind not in STAGE_KINDS:
+        raise ValueError(f"unknown stage kind {kind!r}")
+    if precision not in PRECISIONS:
+        raise ValueError(f"unknown precision {precision!r}")
+    return serialise(kind, backbone_ops(state_dict, precision) + head_ops(kind, state_dict, precision), precision)
+
+
+def blob_stats(blob: bytes) -> Dict[str, float]:
+    """Work the packed program issues per block (for roofline accounting)."""
+    n_ops = struct.unpack_from("<I", blob, 12)[0]
+    macs = 0
+    for i in range(n_ops):
+        f = struct.unpack_from("<16i", blob, 64 + OP_BYTES * i)
+        if f[0] == OP_FC:
+            macs += f[14] * f[10] * TILE_K      # schedule entries * block_n * 64
+    return {"tensor_macs_per_block": float(macs), "bytes": float(len(blob))}

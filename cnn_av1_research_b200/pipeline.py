@@ -1,0 +1,115 @@
+"""HierarchicalPipelineV6 - drop-in for pesquisa_v6/scripts/008_run_pipeline_eval_v6.py:38-163.
+
+Same constructor and `predict(images) -> LongTensor[B] on CPU` contract; the work is one enqueue of
+the libav1p cascade (stage forwards + on-device routing, no host synchronisation between stages).
+Additive entry points: `predict_device` (labels stay on the GPU) and `predict_frames` (block
+extraction fused into the first kernel, straight from planar YUV 4:2:0 10-bit frames in HBM).
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional
+
+import torch
+
+from . import _native as N
+from .runtime import NativeCascade
+
+
+class HierarchicalPipelineV6:
+    """Complete hierarchical pipeline for V6 (008:38-127)."""
+
+    def __init__(self, stage1_model, stage2_model, stage3_rect_model, stage3_ab_model, stage1_threshold=0.5,
+                 device="cuda", *, capacity_blocks: int = 0, precision: Optional[str] = None):
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise RuntimeError("HierarchicalPipelineV6 (B200 build) runs on CUDA devices only; there is no CPU path")
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        self.stage1_model = stage1_model.to(dev).eval()
+        self.stage2_model = stage2_model.to(dev).eval()
+        self.stage3_rect_model = stage3_rect_model.to(dev).eval()
+        self.stage3_ab_model = stage3_ab_model.to(dev).eval()
+        if precision is not None:
+            for m in (self.stage1_model, self.stage2_model, self.stage3_rect_model, self.stage3_ab_model):
+                m.precision = precision
+        self.stage1_threshold = stage1_threshold
+        self.device = dev
+        # label maps of the reference (008:50-67); kept for API compatibility
+        self.stage2_to_original = {0: 1, 1: 2, 2: 3}
+        self.stage3_rect_to_original = {0: 2, 1: 3}
+        self.stage3_ab_to_original = {0: 4, 1: 5, 2: 6, 3: 7}
+        self._cascade: Optional[NativeCascade] = None
+        self._cascade_key = None
+        self._min_capacity = int(capacity_blocks)
+
+    # -------------------------------------------------------------------------------------------
+    def _models(self) -> List:
+        return [self.stage1_model, self.stage2_model, self.stage3_rect_model, self.stage3_ab_model]
+
+    def cascade(self, n_blocks: int) -> NativeCascade:
+        natives = [m.native_model(self.device) for m in self._models()]
+        key = tuple(id(nm) for nm in natives)
+        if self._cascade is None or self._cascade_key != key or self._cascade.capacity < n_blocks:
+            cap = max(n_blocks, self._min_capacity, 256)
+            self._cascade = NativeCascade(natives, cap)
+            self._cascade_key = key
+        return self._cascade
+
+    @property
+    def launches_per_predict(self) -> int:
+        return self._cascade.launches_per_predict if self._cascade else 0
+
+    # -------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def predict_device(self, images: torch.Tensor, out_u8: Optional[torch.Tensor] = None,
+                       out_i64: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Labels on the device.  Returns out_i64 if given (or created when out_u8 is None), else out_u8."""
+        images = images.to(self.device, non_blocking=True)
+        if images.dim() != 4 or tuple(images.shape[1:]) != (1, 16, 16):
+            raise ValueError(f"expected images [B,1,16,16], got {tuple(images.shape)}")
+        images = images.contiguous().float()
+        n = images.shape[0]
+        if out_u8 is None and out_i64 is None:
+            out_i64 = torch.empty(n, dtype=torch.int64, device=self.device)
+        if n:
+            self.cascade(n).predict(N.images_input(images), n, self.stage1_threshold, out_u8, out_i64)
+        return out_i64 if out_i64 is not None else out_u8
+
+    @torch.no_grad()
+    def predict(self, images: torch.Tensor) -> torch.Tensor:
+        """Run full hierarchical prediction (008:69-127): float32 [B,1,16,16] -> int64 [B] on the CPU."""
+        return self.predict_device(images).cpu()
+
+    @torch.no_grad()
+    def predict_frames(self, frames: torch.Tensor, width: int, height: int, n_frames: int,
+                       out_u8: Optional[torch.Tensor] = None, pitch: Optional[int] = None,
+                       frame_stride: Optional[int] = None) -> torch.Tensor:
+        """Partition labels for every 16x16 luma block of `n_frames` planar YUV 4:2:0 10-bit LE frames.
+
+        frames: flat uint16 tensor (device, or host - it is copied).  Block order: frame-major, then the
+        row-major grid of 005_rearrange_video_YUV_420_10bit_LOSSLESS.py:402-433; the zero padding of
+        :380-383 applies at the bottom/right edge.  Returns uint8 labels [n_frames * blocks_per_frame] on
+        the device, in predict()'s label space.
+        """
+        frames = frames.to(self.device, non_blocking=True)
+        bpf = math.ceil(height / 16) * math.ceil(width / 16)
+        n = bpf * n_frames
+        if out_u8 is None:
+            out_u8 = torch.empty(n, dtype=torch.uint8, device=self.device)
+        inp = N.frames_input(frames, width, height, n_frames, pitch, frame_stride)
+        self.cascade(n).predict(inp, n, self.stage1_threshold, out_u8, None)
+        return out_u8
+
+
+def evaluate_pipeline(pipeline, dataloader, class_names=None):
+    """Batch loop of 008:130-147: returns {'predictions', 'labels'} as numpy arrays.
+
+    The sklearn report / confusion-matrix post-processing of 008:149-163 is host-side analysis outside
+    the hot path and is left to the caller.
+    """
+    preds, labels = [], []
+    for batch in dataloader:
+        preds.append(pipeline.predict(batch["image"]))
+        labels.append(batch["label_stage0"])
+    return {"predictions": torch.cat(preds).numpy(), "labels": torch.cat(labels).numpy()}

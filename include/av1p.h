@@ -1,0 +1,142 @@
+/* av1p.h - C ABI of the B200-native AV1 partition-prediction cascade (libav1p.so).
+ *
+ * The reference (chiarorosa/cnn-av1-research) is pure Python: its "operator interface" for this
+ * path is a set of Python callables.  Each entry point below names the reference callable it
+ * replaces (paths relative to the reference repository root); the Python package
+ * cnn_av1_research_b200 re-exposes them under the reference's own names and signatures.
+ *
+ * Conventions: plain pointers and sizes only; every *_dev pointer is a CUDA device pointer owned by
+ * the caller; `stream` is a cudaStream_t passed as void*; all work is enqueued asynchronously on
+ * that stream and no function synchronises unless stated; functions return 0 on success or a
+ * negative AV1P_E* code, with a human-readable message available from av1p_last_error() (thread
+ * local).  No C++ exception crosses this boundary.  A handle is immutable after creation and may
+ * be shared by threads that use distinct streams and distinct workspaces.
+ */
+#ifndef AV1P_H_
+#define AV1P_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AV1P_OK 0
+#define AV1P_EINVAL (-1)   /* bad argument / malformed weight blob */
+#define AV1P_ECUDA (-2)    /* CUDA runtime or driver error */
+#define AV1P_ENOMEM (-3)   /* workspace too small */
+#define AV1P_ENODEV (-4)   /* no sm_100 device */
+
+typedef struct av1p_model av1p_model;       /* one packed stage network resident in HBM */
+typedef struct av1p_stage av1p_stage;       /* a model bound to a workspace (ready-to-launch plan) */
+typedef struct av1p_cascade av1p_cascade;   /* Stage1 -> Stage2 -> Stage3-RECT / Stage3-AB */
+
+/* Where the 16x16 luma blocks come from. */
+typedef struct av1p_input {
+  int32_t kind;             /* 0: planar YUV 4:2:0 10-bit LE frames in HBM; 1: float32 blocks [n][256] */
+  int32_t width, height;    /* kind 0: luma geometry in samples */
+  int32_t pitch;            /* kind 0: luma row pitch in samples (>= width) */
+  int32_t n_frames;         /* kind 0 */
+  int64_t frame_stride;     /* kind 0: samples between consecutive frames (Y+U+V = W*H*3/2 when packed) */
+  const uint16_t* frames_dev;
+  const float* images_dev;  /* kind 1: what HierarchicalPipelineV6.predict(images) receives */
+} av1p_input;
+
+const char* av1p_last_error(void);
+int av1p_version(void);
+/* Value written by a kernel watchdog (pipeline barrier that never completed), 0 if none. */
+int av1p_debug_watchdog(void);
+
+/* ---- model: replaces nn.Module construction + load_state_dict + .to(device).eval()
+ *      (pesquisa_v6/scripts/008_run_pipeline_eval_v6.py:219-250, models.py:206-251,
+ *       scripts/006_train_stage3_ab_fgvc.py:246-297).  `blob` is produced by
+ *      cnn_av1_research_b200.packer from a reference state_dict (BN folded, convolutions unrolled to
+ *      block-Toeplitz fp16 tiles).  The library copies it to the device. */
+int av1p_model_create(const void* blob, size_t bytes, av1p_model** out);
+void av1p_model_destroy(av1p_model* m);
+int av1p_model_num_outputs(const av1p_model* m);
+
+/* ---- single stage forward: replaces StageXModel.forward / FGVCModel.forward
+ *      (models.py:213-251, 006:277-297) fused with block extraction + normalisation
+ *      (pesquisa_v5/005_rearrange_video_YUV_420_10bit_LOSSLESS.py:353-457, data_hub.py:70-77). */
+size_t av1p_stage_workspace_bytes(const av1p_model* m, int32_t capacity_rows);
+int av1p_stage_create(const av1p_model* m, int32_t capacity_rows, void* workspace_dev, size_t workspace_bytes,
+                      av1p_stage** out);
+void av1p_stage_destroy(av1p_stage* s);
+/* Row r of the output is the network applied to block id idx_dev[r] (or r when idx_dev is NULL).
+ * n is the host-side upper bound on rows (sizes the grids); if n_dev is non-NULL the kernels read
+ * the actual row count from it on the device, so no host synchronisation is needed between stages.
+ * logits_dev: float32 [n][num_outputs]. */
+int av1p_stage_forward(av1p_stage* s, const av1p_input* in, const int32_t* idx_dev, const int32_t* n_dev, int32_t n,
+                       float* logits_dev, void* stream);
+
+/* ---- full cascade: replaces HierarchicalPipelineV6.__init__/predict (008:41-127).
+ *      models[] = {stage1, stage2, stage3_rect, stage3_ab}.  Labels use predict()'s label space:
+ *      0 NONE, 1 SPLIT, 2 HORZ, 3 VERT, 4 HORZ_A, 5 HORZ_B, 6 VERT_A, 7 VERT_B. */
+size_t av1p_cascade_workspace_bytes(const av1p_model* const models[4], int32_t capacity_blocks);
+int av1p_cascade_create(const av1p_model* const models[4], int32_t capacity_blocks, void* workspace_dev,
+                        size_t workspace_bytes, av1p_cascade** out);
+void av1p_cascade_destroy(av1p_cascade* c);
+/* Either label pointer may be NULL.  n_blocks <= capacity_blocks. */
+int av1p_cascade_predict(av1p_cascade* c, const av1p_input* in, int32_t n_blocks, float stage1_threshold,
+                         uint8_t* labels_u8_dev, int64_t* labels_i64_dev, void* stream);
+/* Introspection for the parity tests (device pointers into the workspace, valid after predict):
+ * which: 0 stage-1 logits [n][1], 1 stage-2 logits [n2][3], 2 RECT logits [nR][2], 3 AB logits [nA][4],
+ *        4 idx2 [n2], 5 idxR [nR], 6 idxA [nA], 7 counts int32[4] = {n2, unused, nR, nA}. */
+const void* av1p_cascade_buffer(const av1p_cascade* c, int32_t which);
+/* Number of kernels one predict() call enqueues (for launch accounting). */
+int av1p_cascade_launches_per_predict(const av1p_cascade* c);
+int av1p_stage_launches_per_forward(const av1p_stage* s);
+
+/* ---- extraction: replaces extract_blocks_with_validation (005:353-457) and
+ *      BlockRecord.to_torch (data_hub.py:70-77).  y_dev is one luma plane [height][pitch] uint16;
+ *      out is [ceil(H/b)*ceil(W/b)][b][b] in row-major grid order, zero padded bottom/right.
+ *      block in {8,16,32,64} (005:32). */
+int av1p_extract_u16(const uint16_t* y_dev, int32_t width, int32_t height, int32_t pitch, int32_t block,
+                     uint16_t* out_dev, void* stream);
+int av1p_extract_norm_u16(const uint16_t* y_dev, int32_t width, int32_t height, int32_t pitch, int32_t block,
+                          float* out_dev, void* stream);
+
+/* ---- routing operators (008:77-125), exposed on their own so they can be checked bit-exactly on
+ *      reference logits.  scratch_dev: av1p_route_scratch_bytes() bytes, zero-initialised once.
+ *      idx outputs are ascending block ids; counts are written to device memory:
+ *      count_dev is int32[2] ({n_routed, unused}), counts2_dev is int32[2] ({n_rect, n_ab}). */
+size_t av1p_route_scratch_bytes(void);
+int av1p_route_stage1(const float* logits_dev, const int32_t* n_dev, int32_t n, float threshold, int32_t* idx_dev,
+                      int32_t* count_dev, uint8_t* labels_u8_dev, int64_t* labels_i64_dev, void* scratch_dev,
+                      void* stream);
+int av1p_route_stage2(const float* logits3_dev, const int32_t* idx_in_dev, const int32_t* n_dev, int32_t n,
+                      int32_t* idx_rect_dev, int32_t* idx_ab_dev, int32_t* counts2_dev, uint8_t* labels_u8_dev,
+                      int64_t* labels_i64_dev, void* scratch_dev, void* stream);
+int av1p_finalize_labels(const float* logits_dev, int32_t num_classes, int32_t label_base, const int32_t* idx_dev,
+                         const int32_t* n_dev, int32_t n, uint8_t* labels_u8_dev, int64_t* labels_i64_dev,
+                         void* stream);
+
+/* ---- kernel-level test hook: one block-sparse FC layer  out = epi(act . W^T)  on the tcgen05 path.
+ *      a_dev[i]: fp16 [rows][a_cols[i]] activation sources (unused entries NULL);
+ *      w: fp16 [n_w_chunks*block_n][64]; kb_begin[n_tiles+1]; schedule entry e multiplies the 64-wide
+ *      K block (kb_src[e] & 0x3fff) of source (kb_src[e] >> 14) with weight chunk kb_w[e].
+ *      See csrc/fc_tcgen05.cuh for the epilogue codes. */
+typedef struct av1p_fc_desc {
+  const void* a_dev[4]; int32_t a_cols[4];
+  int32_t rows;
+  const int32_t* n_dev;
+  const void* w_dev; int32_t n_w_chunks;
+  int32_t n_kb_total, n_tiles, block_n, epi;
+  const int32_t* kb_begin;
+  const uint16_t* kb_src;
+  const uint16_t* kb_w;
+  const float* bias_dev;
+  const float* row_scale_dev;
+  float acc_scale;
+  const void* aux_dev; const void* aux_lo_dev; int32_t aux_ld;
+  void* out_dev; void* out_lo_dev; int32_t out_ld;
+  const float* tail_w_dev; const float* tail_b_dev; float* logits_dev; int32_t tail_n;
+} av1p_fc_desc;
+int av1p_fc_forward(const av1p_fc_desc* d, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AV1P_H_ */

@@ -1,0 +1,101 @@
+"""CPU emulation of the op program in a packed blob (csrc/blob_format.h).  TEST INFRASTRUCTURE ONLY.
+
+It interprets exactly what av1p.cu would launch - same buffers, K-block schedule, weight chunks,
+epilogues and fp16 (hi / lo) rounding points - with numpy/torch on the host, so that the packer (BN
+folding, block-Toeplitz unrolling, split precision, op topology) can be verified against the oracle
+without a GPU.  The product never imports it.
+"""
+import struct
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+OP_FMT = "<16i2f4Q9i128H128H"
+OP_BYTES = struct.calcsize(OP_FMT)
+
+
+def parse(blob: bytes):
+    magic, version, kind, n_ops, n_bufs, n_out, prec, _, ops_off, bufs_off, total, _ = struct.unpack_from("<8I4Q", blob, 0)
+    assert magic == 0x50315641 and version == 3 and total == len(blob)
+    cols = struct.unpack_from(f"<{n_bufs}I", blob, bufs_off)
+    ops = []
+    for i in range(n_ops):
+        f = struct.unpack_from(OP_FMT, blob, ops_off + OP_BYTES * i)
+        ops.append(dict(type=f[0], src=f[1:5], aux=f[5], aux_lo=f[6], out=f[7], out_lo=f[8], n_tiles=f[9], block_n=f[10],
+                        epi=f[11], tail_n=f[12], use_row_scale=f[13], n_kb=f[14], n_w_chunks=f[15], f0=f[16], f1=f[17],
+                        w_off=f[18], bias_off=f[19], tail_w_off=f[20], tail_b_off=f[21], kb_begin=f[22:31],
+                        kb_src=f[31:159], kb_w=f[159:287]))
+    return dict(kind=kind, n_out=n_out, cols=cols, ops=ops, precision=prec)
+
+
+def _arr(blob, off, dtype, count):
+    return np.frombuffer(blob, dtype=dtype, count=count, offset=off)
+
+
+def _h16(a):
+    return a.astype(np.float16).astype(np.float32)
+
+
+def run(blob: bytes, images: np.ndarray) -> np.ndarray:
+    """images: float32 [n,1,16,16] -> logits float32 [n, n_out] as the device program computes them."""
+    P = parse(blob)
+    n = images.shape[0]
+    bufs = [np.zeros((n, c), dtype=np.float32) for c in P["cols"]]
+    row_scale = np.ones(n, dtype=np.float32)
+    logits = None
+
+    def store(op, val, width):
+        hi = _h16(val)
+        bufs[op["out"]][:, :width] = hi
+        if op["out_lo"] >= 0:
+            bufs[op["out_lo"]][:, :width] = _h16(val - hi)
+
+    def load(hi_id, lo_id):
+        return bufs[hi_id] + (bufs[lo_id] if lo_id >= 0 else 0.0)
+
+    for op in P["ops"]:
+        t = op["type"]
+        if t == 0:  # stem
+            w = _arr(blob, op["w_off"], np.float32, 64 * 52).reshape(64, 52)[:, :49].reshape(64, 1, 7, 7)
+            b = _arr(blob, op["bias_off"], np.float32, 64)
+            x = F.conv2d(torch.from_numpy(images), torch.from_numpy(w.copy()), torch.from_numpy(b.copy()), stride=2, padding=3)
+            x = F.max_pool2d(F.relu(x), 3, 2, 1)                       # [n,64,4,4]
+            store(op, x.permute(0, 2, 3, 1).reshape(n, 1024).numpy(), 1024)
+        elif t == 1:  # block-sparse FC
+            bn, nt = op["block_n"], op["n_tiles"]
+            w = _arr(blob, op["w_off"], np.float16, op["n_w_chunks"] * bn * 64).reshape(op["n_w_chunks"], bn, 64).astype(np.float32)
+            acc = np.zeros((n, nt * bn), dtype=np.float32)
+            for ti in range(nt):
+                for e_i in range(op["kb_begin"][ti], op["kb_begin"][ti + 1]):
+                    e = op["kb_src"][e_i]
+                    src = bufs[op["src"][e >> 14]]
+                    k0 = (e & 0x3FFF) * 64
+                    acc[:, ti * bn:(ti + 1) * bn] += src[:, k0:k0 + 64] @ w[op["kb_w"][e_i]].T
+            acc *= (row_scale[:, None] if op["use_row_scale"] else 1.0) * np.float32(op["f0"])
+            if op["bias_off"]:
+                acc += _arr(blob, op["bias_off"], np.float32, nt * bn)[None, :]
+            epi = op["epi"]
+            if epi in (2, 3):
+                aux = load(op["aux"], op["aux_lo"])[:, : nt * bn]
+                acc = acc + aux if epi == 2 else aux / (1.0 + np.exp(-acc))
+            if epi in (1, 2, 4):
+                acc = np.maximum(acc, 0.0)
+            if epi == 4:
+                tw = _arr(blob, op["tail_w_off"], np.float32, op["tail_n"] * bn).reshape(op["tail_n"], bn)
+                tb = _arr(blob, op["tail_b_off"], np.float32, op["tail_n"])
+                logits = acc @ tw.T + tb[None, :]
+            else:
+                store(op, acc, nt * bn)
+        elif t == 2:  # spatial attention scalar
+            x = load(op["src"][0], op["src"][1])
+            a = op["f0"] * x.mean(axis=1) + op["f1"] * x.max(axis=1)
+            row_scale = (1.0 / (1.0 + np.exp(-a))).astype(np.float32)
+        elif t == 3:  # FGVC tail
+            x = load(op["src"][0], op["src"][1])
+            w = _arr(blob, op["w_off"], np.float32, 4 * 512).reshape(4, 512)
+            nrm = np.maximum(np.sqrt((x * x).sum(axis=1, keepdims=True)), 1e-12)
+            logits = op["f0"] * (x @ w.T) / nrm
+        else:
+            raise ValueError(t)
+    return logits.astype(np.float32)

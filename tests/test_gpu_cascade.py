@@ -1,0 +1,140 @@
+"""Parity of the stage networks and of the full cascade against the reference's outputs (golden
+fixtures produced by the reference's own modules) and against the CPU oracle.
+
+Tolerances.  The reference computes in fp32.  The default B200 path ("fp16x3") multiplies split fp16
+operands on the tensor cores with fp32 accumulation (~22 significant bits): logits must agree to
+max-abs <= 2e-3 on logits with sigma ~ 2 (measured ~1e-4); labels must agree on >= 99.9 % of blocks and
+every disagreeing block must have a reference decision margin below 1e-2.  The "fp16" fast mode is held
+to max-abs <= 0.25 and >= 98.5 % label agreement.  Routing *operators* are checked bit-exactly on
+reference logits in test_gpu_extraction_routing.py.
+"""
+import numpy as np
+import pytest
+import torch
+
+from cnn_av1_research_b200 import _native as N
+from cnn_av1_research_b200 import synth
+from cnn_av1_research_b200.testing import build_models, build_pipeline, frames_tensor
+from oracle import cascade_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+LOGIT_TOL = {"fp16x3": 2e-3, "fp16": 0.25}
+AGREE_MIN = {"fp16x3": 0.999, "fp16": 0.985}
+
+
+@pytest.mark.parametrize("precision", ["fp16x3", "fp16"])
+def test_stage_logits_match_reference(cuda_device, golden_dir, precision):
+    g = np.load(f"{golden_dir}/stage_logits.npz")
+    x = torch.from_numpy(g["images"]).to(cuda_device)
+    nets = build_models(seed=0)
+    from cnn_av1_research_b200.models import Stage3ABModel
+    ab = Stage3ABModel(pretrained=False)
+    ab.load_state_dict(synth.calibrated_state_dict("ab", 0))
+    nets["ab"] = ab.eval()
+    for kind, net in nets.items():
+        net.precision = precision
+        got = net.to(cuda_device)(x).cpu().numpy()
+        ref = g[f"logits_{kind}"]
+        assert got.shape == ref.shape
+        err = np.abs(got - ref).max()
+        assert err <= LOGIT_TOL[precision], f"{kind} [{precision}]: max-abs logit error {err:.3g}"
+
+
+def test_stage_forward_api_contract(cuda_device):
+    from cnn_av1_research_b200.models import Stage1Model
+    m = Stage1Model(pretrained=False)
+    with pytest.raises(RuntimeError):
+        m.eval()(torch.zeros(2, 1, 16, 16))                      # CPU tensor: no CPU path
+    with pytest.raises(RuntimeError):
+        m.train()(torch.zeros(2, 1, 16, 16, device=cuda_device))  # training mode is not on this path
+    m.eval().to(cuda_device)
+    assert m(torch.zeros(1, 1, 16, 16, device=cuda_device)).shape == (1, 1)     # B = 1 (008's squeeze() edge)
+    assert m(torch.zeros(0, 1, 16, 16, device=cuda_device)).shape == (0, 1)     # empty batch
+    y = m(torch.rand(5, 1, 16, 16, device=cuda_device))
+    assert torch.allclose(m(torch.rand(5, 1, 16, 16, device=cuda_device) * 0 + 0.5, apply_temp=True) * 1.5,
+                          m(torch.zeros(5, 1, 16, 16, device=cuda_device) + 0.5), atol=1e-6)
+    assert y.dtype == torch.float32 and y.is_cuda
+
+
+def _margins(g):
+    """Reference decision margin of every block: distance of its deciding logit(s) from a flip."""
+    n = g["labels"].shape[0]
+    thr = float(g["threshold"])
+    m = np.abs(g["logits1"][:, 0] - np.log(thr / (1 - thr)))
+    def top2(z):
+        s = np.sort(z, axis=1)
+        return s[:, -1] - s[:, -2]
+    m2 = np.full(n, np.inf); m2[g["idx2"]] = top2(g["logits2"])
+    m3 = np.full(n, np.inf); m3[g["idx_rect"]] = top2(g["logits_rect"]); m3[g["idx_ab"]] = top2(g["logits_ab"])
+    return np.minimum(m, np.minimum(m2, m3))
+
+
+@pytest.mark.parametrize("precision", ["fp16x3", "fp16"])
+def test_cascade_matches_reference_predict(cuda_device, golden_dir, precision):
+    g = np.load(f"{golden_dir}/cascade_360p.npz")
+    w, h, nf, thr = int(g["width"]), int(g["height"]), int(g["n_frames"]), float(g["threshold"])
+    words = synth.synth_frames(nf, w, h, seed=int(g["frame_seed"]))
+    pipe = build_pipeline(seed=0, threshold=thr, device=cuda_device, precision=precision)
+    # (1) frame path: extraction fused into the stem kernel
+    labels = pipe.predict_frames(frames_tensor(words, cuda_device), w, h, nf).cpu().numpy()
+    inter = {k: v.cpu().numpy() for k, v in pipe.cascade(labels.size).intermediates(labels.size).items()}
+    agree = (labels == g["labels"]).mean()
+    assert agree >= AGREE_MIN[precision], f"label agreement {agree:.5f}"
+    err1 = np.abs(inter["logits1"] - g["logits1"]).max()
+    assert err1 <= LOGIT_TOL[precision], f"stage-1 logits max-abs error {err1:.3g}"
+    if precision == "fp16x3":
+        bad = np.nonzero(labels != g["labels"])[0]
+        assert (_margins(g)[bad] < 1e-2).all(), "a block with a clear reference margin was mislabelled"
+        if np.array_equal(inter["idx2"], g["idx2"]):
+            assert np.abs(inter["logits2"] - g["logits2"]).max() <= LOGIT_TOL[precision]
+        if np.array_equal(inter["idx_rect"], g["idx_rect"]):
+            assert np.abs(inter["logits_rect"] - g["logits_rect"]).max() <= LOGIT_TOL[precision]
+        if np.array_equal(inter["idx_ab"], g["idx_ab"]):
+            assert np.abs(inter["logits_ab"] - g["logits_ab"]).max() <= LOGIT_TOL[precision]
+    # the routing lists are consistent with the path's own logits (bit-exact operators)
+    assert np.array_equal(inter["idx2"], O.route_stage1(torch.from_numpy(inter["logits1"]), thr).numpy())
+    _, r, a = O.route_stage2(torch.from_numpy(inter["logits2"]), torch.from_numpy(inter["idx2"]))
+    assert np.array_equal(inter["idx_rect"], r.numpy()) and np.array_equal(inter["idx_ab"], a.numpy())
+    # (2) reference API: predict(images) on the tensor the reference would build -> int64 on the CPU
+    images = O.frames_to_images(words, nf, w, h)
+    assert np.array_equal(images[:4].numpy(), g["images_head"])
+    out = pipe.predict(images)
+    assert out.dtype == torch.int64 and out.device.type == "cpu" and out.shape == (labels.size,)
+    assert np.array_equal(out.numpy(), labels), "frame path and image path disagree"
+
+
+def test_predict_edge_cases(cuda_device):
+    pipe = build_pipeline(seed=0, device=cuda_device)
+    assert pipe.predict(torch.zeros(0, 1, 16, 16)).shape == (0,)
+    one = pipe.predict(torch.full((1, 1, 16, 16), 0.5))
+    assert one.shape == (1,) and 0 <= int(one[0]) <= 7
+    # threshold above every probability: nothing is routed, every label is NONE (008:87-88)
+    hi = build_pipeline(seed=0, threshold=1.5, device=cuda_device)
+    assert (hi.predict(torch.rand(300, 1, 16, 16)) == 0).all()
+    # threshold 0: everything is routed to stage 2 (no NONE labels)
+    lo = build_pipeline(seed=0, threshold=0.0, device=cuda_device)
+    assert (lo.predict(torch.rand(300, 1, 16, 16)) >= 1).all()
+
+
+def test_full_size_properties_4k(cuda_device):
+    """Size-independent properties at BASELINE's 4K size (32,400 blocks per frame): determinism, block
+    independence (a batch equals the concatenation of its parts), frame path == image path, and a
+    random 384-block sample against the CPU oracle."""
+    w, h, nf, thr = 3840, 2160, 2, 0.45
+    words = synth.synth_frames(nf, w, h, seed=77)
+    pipe = build_pipeline(seed=0, threshold=thr, device=cuda_device, capacity_blocks=2 * 32400)
+    fr = frames_tensor(words, cuda_device)
+    both = pipe.predict_frames(fr, w, h, nf).cpu().numpy()
+    assert both.shape == (64800,) and both.max() <= 7
+    assert np.array_equal(both, pipe.predict_frames(fr, w, h, nf).cpu().numpy()), "not deterministic"
+    fw = synth.frame_words(w, h)
+    second = pipe.predict_frames(fr[fw:], w, h, 1).cpu().numpy()
+    assert np.array_equal(second, both[32400:]), "frame 1 alone differs from frame 1 inside the batch"
+    sel = np.sort(np.random.Generator(np.random.PCG64(3)).permutation(64800)[:384])
+    images = O.frames_to_images(words, nf, w, h)[torch.from_numpy(sel)]
+    ref = O.cascade_predict(synth.calibrated_cascade(0), images, thr)["labels"].numpy()
+    assert (both[sel] == ref).mean() >= 0.995
+    assert np.array_equal(pipe.predict(images).numpy(), both[sel]), "image path differs from frame path"
+    hist = np.bincount(both, minlength=8) / both.size
+    assert 0.3 < hist[0] < 0.75 and hist[1:].sum() > 0.2, f"degenerate routing mix {hist}"
