@@ -64,6 +64,9 @@ SIGNATURES = {
     "av1p_finalize_labels": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
                                        C.c_void_p, C.c_void_p]),
     "av1p_fc_forward": (C.c_int, [C.POINTER(FcDesc), C.c_void_p]),
+    "av1p_profile_begin": (C.c_int, []),
+    "av1p_profile_end": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
+    "av1p_upload_luma": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]),
 }
 
 

@@ -105,6 +105,77 @@ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 extern "C" int av1p_debug_watchdog(void) { return g_ctx.watchdog_host ? *g_ctx.watchdog_host : 0; }
 
+// ------------------------------------------------------------------------------ per-launch profiler
+// Optional CUDA-event bracket around every kernel launch (bench.py's roofline leg).  Events are
+// recorded on the launching stream; nothing synchronises until av1p_profile_end.
+namespace {
+enum ProfClass { PROF_STEM = 0, PROF_FC = 1, PROF_SAM = 2, PROF_FGVC = 3, PROF_ROUTE = 4, PROF_FINALIZE = 5, PROF_CLASSES = 6 };
+struct ProfRec { int cls; cudaEvent_t a, b; };
+struct Profiler {
+  bool on = false;
+  std::vector<ProfRec> recs;
+  std::vector<cudaEvent_t> pool;
+  cudaEvent_t get() {
+    if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+  }
+};
+thread_local Profiler g_prof;
+struct ProfScope {
+  cudaStream_t st;
+  bool active;
+  ProfRec r;
+  ProfScope(int cls, cudaStream_t s) : st(s), active(g_prof.on) {
+    if (!active) return;
+    r.cls = cls;
+    r.a = g_prof.get();
+    r.b = g_prof.get();
+    cudaEventRecord(r.a, st);
+  }
+  ~ProfScope() {
+    if (!active) return;
+    cudaEventRecord(r.b, st);
+    g_prof.recs.push_back(r);
+  }
+};
+}  // namespace
+
+extern "C" int av1p_profile_begin(void) {
+  g_prof.on = true;
+  return AV1P_OK;
+}
+extern "C" int av1p_profile_end(float* ms_by_class, int32_t* launches_by_class) {
+  g_prof.on = false;
+  for (int i = 0; i < PROF_CLASSES; ++i) {
+    if (ms_by_class) ms_by_class[i] = 0.f;
+    if (launches_by_class) launches_by_class[i] = 0;
+  }
+  for (ProfRec& r : g_prof.recs) {
+    CUDA_TRY(cudaEventSynchronize(r.b));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, r.a, r.b));
+    if (ms_by_class) ms_by_class[r.cls] += ms;
+    if (launches_by_class) launches_by_class[r.cls] += 1;
+    g_prof.pool.push_back(r.a);
+    g_prof.pool.push_back(r.b);
+  }
+  g_prof.recs.clear();
+  return AV1P_OK;
+}
+
+// Strided host->device copy of the luma planes only (2/3 of a 4:2:0 frame): one cudaMemcpy2DAsync.
+extern "C" int av1p_upload_luma(const uint16_t* frames_host, int32_t n_frames, int32_t width, int32_t height,
+                                int64_t frame_stride, uint16_t* luma_dev, void* stream) {
+  if (!frames_host || !luma_dev || n_frames <= 0 || width <= 0 || height <= 0 || frame_stride < int64_t(width) * height)
+    return fail(AV1P_EINVAL, "bad argument");
+  const size_t row = size_t(width) * height * 2;
+  CUDA_TRY(cudaMemcpy2DAsync(luma_dev, row, frames_host, size_t(frame_stride) * 2, row, size_t(n_frames),
+                             cudaMemcpyHostToDevice, static_cast<cudaStream_t>(stream)));
+  return AV1P_OK;
+}
+
 // ------------------------------------------------------------------------------ model
 struct av1p_model {
   std::vector<uint8_t> host;        // header + op table (host copy for planning)
@@ -337,6 +408,7 @@ int run_stage(av1p_stage* s, const StemInput& si, const int32_t* idx, const int3
         sp.n_dev = n_dev;
         sp.n = n;
         const int grid = std::min(ceil_div(n, STEM_NB), g_ctx.sms * 4);
+        ProfScope ps(PROF_STEM, st);
         stem_kernel<<<grid, STEM_THREADS, STEM_SMEM_BYTES, st>>>(sp);
         break;
       }
@@ -345,16 +417,19 @@ int run_stage(av1p_stage* s, const StemInput& si, const int32_t* idx, const int3
         P.fc.n_rows = n;
         P.fc.logits = logits;
         const int grid = std::min(g_ctx.sms, ceil_div(n, FC_TILE_M) * P.fc.n_tiles);
+        ProfScope ps(PROF_FC, st);
         fc_tcgen05_kernel<<<grid, FC_THREADS, FC_SMEM_BYTES, st>>>(P.fc);
         break;
       }
       case AV1P_OP_SAM: {
         const int grid = std::min(ceil_div(n, 8), g_ctx.sms * 8);
+        ProfScope ps(PROF_SAM, st);
         sam_gate_kernel<<<grid, 256, 0, st>>>(P.src, P.src_lo, P.ld, n_dev, n, P.f0, P.f1, s->row_scale);
         break;
       }
       case AV1P_OP_FGVC_TAIL: {
         const int grid = std::min(ceil_div(n, 8), g_ctx.sms * 8);
+        ProfScope ps(PROF_FGVC, st);
         fgvc_tail_kernel<<<grid, 256, 0, st>>>(P.src, P.src_lo, P.ld, n_dev, n, P.w, P.f0, logits);
         break;
       }
@@ -409,8 +484,14 @@ struct RouteScratch {
 int launch_route(RouteParams rp, int n, cudaStream_t st) {
   const int tiles = ceil_div(std::max(n, 1), ROUTE_TILE);
   if (tiles > ROUTE_MAX_TILES) return fail(AV1P_EINVAL, "too many rows for one routing call (%d)", n);
-  route_count_kernel<<<tiles, ROUTE_THREADS, 0, st>>>(rp);
-  route_scatter_kernel<<<tiles, ROUTE_THREADS, 0, st>>>(rp);
+  {
+    ProfScope ps(PROF_ROUTE, st);
+    route_count_kernel<<<tiles, ROUTE_THREADS, 0, st>>>(rp);
+  }
+  {
+    ProfScope ps(PROF_ROUTE, st);
+    route_scatter_kernel<<<tiles, ROUTE_THREADS, 0, st>>>(rp);
+  }
   CUDA_TRY(cudaGetLastError());
   return AV1P_OK;
 }
@@ -467,8 +548,11 @@ extern "C" int av1p_finalize_labels(const float* logits, int32_t k, int32_t base
   if (n == 0) return AV1P_OK;
   if (int rc = ensure_ctx()) return rc;
   const int grid = std::min(ceil_div(n, 256), g_ctx.sms * 8);
-  finalize_labels_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      logits, k, base, idx, n_dev, n, l8, reinterpret_cast<long long*>(l64));
+  {
+    ProfScope ps(PROF_FINALIZE, static_cast<cudaStream_t>(stream));
+    finalize_labels_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        logits, k, base, idx, n_dev, n, l8, reinterpret_cast<long long*>(l64));
+  }
   CUDA_TRY(cudaGetLastError());
   return AV1P_OK;
 }

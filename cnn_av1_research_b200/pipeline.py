@@ -102,6 +102,65 @@ class HierarchicalPipelineV6:
         return out_u8
 
 
+    @torch.no_grad()
+    def predict_frames_host(self, frames_host: torch.Tensor, width: int, height: int, n_frames: int,
+                            out_host: Optional[torch.Tensor] = None, chunk_frames: int = 8,
+                            frame_stride: Optional[int] = None) -> torch.Tensor:
+        """End-to-end variant of predict_frames: frames in (ideally pinned) HOST memory, labels back in HOST memory.
+
+        Only the luma planes cross PCIe (one strided cudaMemcpy2DAsync per chunk, av1p_upload_luma); uploads
+        run on a side stream, double-buffered against the cascade of the previous chunk.  Returns uint8
+        labels on the host (pinned when `out_host` is pinned).  Synchronises before returning.
+        """
+        if frames_host.is_cuda:
+            raise ValueError("predict_frames_host takes host memory; use predict_frames for device tensors")
+        if frames_host.dtype not in (torch.uint16, torch.int16) or not frames_host.is_contiguous():
+            raise ValueError("frames_host must be a contiguous 16-bit tensor")
+        import ctypes as C
+        bpf = math.ceil(height / 16) * math.ceil(width / 16)
+        luma = width * height
+        if frame_stride is None:
+            frame_stride = luma + 2 * ((width // 2) * (height // 2))
+        if frames_host.numel() < (n_frames - 1) * frame_stride + luma:
+            raise ValueError("frames_host is smaller than the geometry implies")
+        chunk = max(1, min(chunk_frames, n_frames))
+        dev = self.device
+        key = (chunk, luma)
+        if getattr(self, "_stage_key", None) != key:
+            self._staging = [torch.empty(chunk * luma, dtype=torch.uint16, device=dev) for _ in range(2)]
+            self._copy_stream = torch.cuda.Stream(device=dev)
+            self._stage_key = key
+        if getattr(self, "last_labels_dev", None) is None or self.last_labels_dev.numel() != n_frames * bpf:
+            self.last_labels_dev = torch.empty(n_frames * bpf, dtype=torch.uint8, device=dev)
+        labels = self.last_labels_dev
+        if out_host is None:
+            out_host = torch.empty(n_frames * bpf, dtype=torch.uint8).pin_memory()
+        main = torch.cuda.current_stream(dev)
+        cascade = self.cascade(chunk * bpf)
+        lib = N.lib()
+        esz = frames_host.element_size()
+        uploaded = [torch.cuda.Event(), torch.cuda.Event()]
+        consumed = [None, None]
+        with torch.cuda.device(dev):
+            self._copy_stream.wait_stream(main)
+            for ci, f0 in enumerate(range(0, n_frames, chunk)):
+                nf = min(chunk, n_frames - f0)
+                b = ci & 1
+                if consumed[b] is not None:
+                    self._copy_stream.wait_event(consumed[b])          # the cascade that read this buffer has finished
+                N.check(lib.av1p_upload_luma(C.c_void_p(frames_host.data_ptr() + f0 * frame_stride * esz), nf, width, height,
+                                             frame_stride, N.ptr(self._staging[b]), self._copy_stream.cuda_stream))
+                uploaded[b].record(self._copy_stream)
+                main.wait_event(uploaded[b])
+                inp = N.frames_input(self._staging[b], width, height, nf, width, luma)
+                cascade.predict(inp, nf * bpf, self.stage1_threshold, labels[f0 * bpf:(f0 + nf) * bpf], None)
+                consumed[b] = torch.cuda.Event()
+                consumed[b].record(main)
+            out_host.copy_(labels, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        return out_host
+
+
 def evaluate_pipeline(pipeline, dataloader, class_names=None):
     """Batch loop of 008:130-147: returns {'predictions', 'labels'} as numpy arrays.
 

@@ -113,6 +113,18 @@ int av1p_finalize_labels(const float* logits_dev, int32_t num_classes, int32_t l
                          const int32_t* n_dev, int32_t n, uint8_t* labels_u8_dev, int64_t* labels_i64_dev,
                          void* stream);
 
+/* ---- measurement support (bench.py): bracket every kernel launch of the calling thread with CUDA
+ *      events on its stream.  av1p_profile_end synchronises on those events and returns the summed
+ *      device time and launch count per kernel class: 0 stem, 1 tcgen05 FC, 2 SAM gate, 3 FGVC tail,
+ *      4 routing, 5 label finalize (arrays of 6). */
+int av1p_profile_begin(void);
+int av1p_profile_end(float* ms_by_class, int32_t* launches_by_class);
+
+/* ---- host -> device staging of the luma planes of planar 4:2:0 frames (pinned host memory
+ *      recommended): copies n_frames * width*height samples, skipping chroma. */
+int av1p_upload_luma(const uint16_t* frames_host, int32_t n_frames, int32_t width, int32_t height,
+                     int64_t frame_stride, uint16_t* luma_dev, void* stream);
+
 /* ---- kernel-level test hook: one block-sparse FC layer  out = epi(act . W^T)  on the tcgen05 path.
  *      a_dev[i]: fp16 [rows][a_cols[i]] activation sources (unused entries NULL);
  *      w: fp16 [n_w_chunks*block_n][64]; kb_begin[n_tiles+1]; schedule entry e multiplies the 64-wide

@@ -32,13 +32,19 @@ def test_stage_logits_match_reference(cuda_device, golden_dir, precision):
     ab = Stage3ABModel(pretrained=False)
     ab.load_state_dict(synth.calibrated_state_dict("ab", 0))
     nets["ab"] = ab.eval()
+    import blob_emulator as E
+    from cnn_av1_research_b200.packer import pack_stage
+    errs = {}
     for kind, net in nets.items():
         net.precision = precision
         got = net.to(cuda_device)(x).cpu().numpy()
         ref = g[f"logits_{kind}"]
         assert got.shape == ref.shape
-        err = np.abs(got - ref).max()
-        assert err <= LOGIT_TOL[precision], f"{kind} [{precision}]: max-abs logit error {err:.3g}"
+        emu = E.run(pack_stage(kind, synth.calibrated_state_dict(kind, 0), precision), g["images"])
+        errs[kind] = (float(np.abs(got - ref).max()), float(np.abs(got - emu).max()))
+    print(f"[{precision}] max-abs logit error vs reference / vs host emulation of the same program: {errs}")
+    for kind, (err, _) in errs.items():
+        assert err <= LOGIT_TOL[precision], f"{kind} [{precision}]: max-abs logit error {err:.3g}; all: {errs}"
 
 
 def test_stage_forward_api_contract(cuda_device):
@@ -138,3 +144,16 @@ def test_full_size_properties_4k(cuda_device):
     assert np.array_equal(pipe.predict(images).numpy(), both[sel]), "image path differs from frame path"
     hist = np.bincount(both, minlength=8) / both.size
     assert 0.3 < hist[0] < 0.75 and hist[1:].sum() > 0.2, f"degenerate routing mix {hist}"
+
+
+def test_host_frames_end_to_end_matches_resident(cuda_device):
+    """predict_frames_host (luma-only strided upload, double-buffered) == predict_frames on the same frames."""
+    w, h, nf = 640, 360, 5
+    words = synth.synth_frames(nf, w, h, seed=21)
+    pipe = build_pipeline(seed=0, threshold=0.45, device=cuda_device)
+    ref = pipe.predict_frames(frames_tensor(words, cuda_device), w, h, nf).cpu()
+    host = frames_tensor(words, pin=True)
+    got = pipe.predict_frames_host(host, w, h, nf, chunk_frames=2)
+    assert got.device.type == "cpu" and torch.equal(got, ref)
+    with pytest.raises(ValueError):
+        pipe.predict_frames_host(host.to(cuda_device), w, h, nf)

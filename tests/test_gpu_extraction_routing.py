@@ -112,4 +112,7 @@ def test_route_stage2_and_finalize_known_answers(cuda_device, golden_dir):
         N.check(lib.av1p_finalize_labels(N.ptr(z), k, base, N.ptr(idx), None, m, N.ptr(out8), N.ptr(out64), N.stream_handle(dev)))
         torch.cuda.synchronize()
         exp = (g[f"argmax{k}"] + base)[::-1]
-        assert np.array_equal(out8.cpu().numpy(), exp.astype(np.uint8)) and np.array_equal(out64.cpu().numpy(), exp.astype(np.int64))
+        got = out8.cpu().numpy()
+        bad = np.nonzero(got != exp.astype(np.uint8))[0]
+        assert bad.size == 0, f"k={k}: {bad.size} mismatches, rows {(m - 1 - bad)[:6]}, logits {g[f'z{k}'][(m - 1 - bad)[:6]]}, got {got[bad[:6]]}, exp {exp[bad[:6]]}"
+        assert np.array_equal(out64.cpu().numpy(), exp.astype(np.int64))

@@ -132,3 +132,20 @@ def test_device_side_row_count(cuda_device):
     ref = ref_fc([a], w, kb_begin, kb_src, kb_w, 128, 0)
     _check(out[:live], ref[:live], "live rows")
     assert torch.isnan(out[live:].float()).all(), "rows past the device-side count were written"
+
+
+def test_fp16_subnormal_operands_are_not_flushed(cuda_device):
+    """Split precision stores x - fp16(x) in fp16; for small x that residual is subnormal.  The tensor
+    cores must multiply subnormal operands exactly (no flush-to-zero) for the split to hold."""
+    dev = cuda_device
+    a = torch.full((128, 64), 2.0 ** -20, device=dev).half()          # subnormal in fp16 (min normal 2^-14)
+    assert a.float().min().item() == 2.0 ** -20
+    w = torch.zeros((64, 64), device=dev).half()
+    w[torch.arange(64), torch.arange(64)] = 1024.0
+    out, _, _ = run_fc([a], w, [0, 1], [0], [0], 64, epi=0)
+    assert torch.equal(out.float(), torch.full((128, 64), 2.0 ** -10, device=dev)), f"got {out.float().unique().tolist()}"
+    wsub = torch.zeros((64, 64), device=dev).half()
+    wsub[torch.arange(64), torch.arange(64)] = 2.0 ** -18              # subnormal weight
+    b = torch.full((128, 64), 512.0, device=dev).half()
+    out, _, _ = run_fc([b], wsub, [0, 1], [0], [0], 64, epi=0)
+    assert torch.equal(out.float(), torch.full((128, 64), 2.0 ** -9, device=dev)), f"got {out.float().unique().tolist()}"
