@@ -186,6 +186,15 @@ struct RouteParams {
   long long* labels_i64;   // optional
 };
 
+// exp(x - max) as torch's CPU softmax evaluates it.  Logits that differ by a few ulps give
+// arguments of ~1e-7; there the result must be the correctly rounded 1 - d (so that a 1-ulp gap is
+// not collapsed into a tie, or is collapsed exactly when fp32 rounding collapses it) - expf's 2-ulp
+// error bound is not enough, 1 - d is exact to half an ulp for d < 2^-12.
+__device__ __forceinline__ float softmax_exp(float x, float m) {
+  const float d = m - x;
+  return d < 2.44140625e-4f ? 1.0f - d : expf(-d);
+}
+
 __device__ __forceinline__ int route_class(const RouteParams& p, int i) {
   // returns 0 = not routed, 1 = keep0, 2 = keep1, 3 = SPLIT (stage 2 only)
   if (p.kind == 0) {
@@ -195,7 +204,7 @@ __device__ __forceinline__ int route_class(const RouteParams& p, int i) {
   }
   const float a = p.logits[3 * i], b = p.logits[3 * i + 1], c = p.logits[3 * i + 2];
   const float m = fmaxf(a, fmaxf(b, c));
-  const float ea = expf(a - m), eb = expf(b - m), ec = expf(c - m);
+  const float ea = softmax_exp(a, m), eb = softmax_exp(b, m), ec = softmax_exp(c, m);
   const float s = (ea + eb) + ec;
   const float pa = __fdiv_rn(ea, s), pb = __fdiv_rn(eb, s), pc = __fdiv_rn(ec, s);
   int cls = 0;
@@ -321,7 +330,7 @@ __global__ void __launch_bounds__(256) finalize_labels_kernel(const float* __res
     }
     float e[4], s = 0.f;
     for (int j = 0; j < k; ++j) {
-      e[j] = expf(x[j] - m);
+      e[j] = softmax_exp(x[j], m);
       s += e[j];
     }
     int cls = 0;
