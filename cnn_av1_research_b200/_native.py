@@ -29,7 +29,7 @@ class FcDesc(C.Structure):
     _fields_ = [("a_dev", C.c_void_p * 4), ("a_cols", C.c_int32 * 4), ("rows", C.c_int32), ("n_dev", C.c_void_p),
                 ("w_dev", C.c_void_p), ("n_w_chunks", C.c_int32), ("n_kb_total", C.c_int32), ("n_tiles", C.c_int32),
                 ("block_n", C.c_int32), ("epi", C.c_int32), ("kb_begin", C.c_void_p), ("kb_src", C.c_void_p),
-                ("kb_w", C.c_void_p), ("bias_dev", C.c_void_p), ("row_scale_dev", C.c_void_p), ("acc_scale", C.c_float),
+                ("kb_w", C.c_void_p), ("bias_dev", C.c_void_p), ("row_scale_dev", C.c_void_p), ("acc_scale", C.c_float), ("pair_mode", C.c_int32),
                 ("aux_dev", C.c_void_p), ("aux_lo_dev", C.c_void_p), ("aux_ld", C.c_int32), ("out_dev", C.c_void_p),
                 ("out_lo_dev", C.c_void_p), ("out_ld", C.c_int32), ("tail_w_dev", C.c_void_p),
                 ("tail_b_dev", C.c_void_p), ("logits_dev", C.c_void_p), ("tail_n", C.c_int32)]

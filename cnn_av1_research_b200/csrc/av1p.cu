@@ -323,6 +323,11 @@ int plan_stage(const av1p_model* m, const ActLayout& L, uint8_t* act_base, av1p_
         f.bias = reinterpret_cast<const float*>(at(op.bias_off));
         f.row_scale = op.use_row_scale ? s->row_scale : nullptr;
         f.acc_scale = op.f0;
+        f.pair_mode = op.pair_mode;
+        if (op.pair_mode) {
+          for (int i = 0; i <= op.n_tiles; ++i)
+            if (op.kb_begin[i] & 1) return fail(AV1P_EINVAL, "pair-mode schedule with an odd entry count");
+        }
         f.aux = buf(op.aux);
         f.aux_lo = buf(op.aux_lo);
         f.aux_ld = op.aux >= 0 ? int(L.cols[op.aux]) : 0;
@@ -734,6 +739,7 @@ extern "C" int av1p_fc_forward(const av1p_fc_desc* d, void* stream) {
   f.bias = d->bias_dev;
   f.row_scale = d->row_scale_dev;
   f.acc_scale = d->acc_scale;
+  f.pair_mode = d->pair_mode;
   f.aux = static_cast<const __half*>(d->aux_dev);
   f.aux_lo = static_cast<const __half*>(d->aux_lo_dev);
   f.aux_ld = d->aux_ld;

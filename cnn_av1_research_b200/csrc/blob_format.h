@@ -8,7 +8,7 @@
 #include <stdint.h>
 
 #define AV1P_BLOB_MAGIC 0x50315641u   /* "AV1P" */
-#define AV1P_BLOB_VERSION 3u
+#define AV1P_BLOB_VERSION 4u
 #define AV1P_BLOB_MAX_NT 8
 #define AV1P_BLOB_MAX_KB 128
 
@@ -37,10 +37,11 @@ struct Av1pBlobOp {
   int32_t use_row_scale;
   int32_t n_kb_total;               // schedule entries
   int32_t n_w_chunks;               // [block_n x 64] fp16 weight tiles stored at w_off
+  int32_t pair_mode;                // 1: entries are (x_hi,w_hi),(x_lo,w_lo) pairs; three products per pair
   float f0, f1;                     // SAM: w_avg, w_max.  FGVC tail: scale.  FC: f0 = acc_scale
   uint64_t w_off, bias_off, tail_w_off, tail_b_off;   // 0 = absent
   int32_t kb_begin[AV1P_BLOB_MAX_NT + 1];
   uint16_t kb_src[AV1P_BLOB_MAX_KB];   // bits 14..15: index into src[], bits 0..13: K offset / 64
   uint16_t kb_w[AV1P_BLOB_MAX_KB];     // weight chunk index
-};  // 16*4 + 2*4 + 4*8 + 9*4 + 2*128*2 = 652 bytes
+};  // 17*4 + 2*4 + 4*8 + 9*4 + 2*128*2 = 656 bytes
 #pragma pack(pop)

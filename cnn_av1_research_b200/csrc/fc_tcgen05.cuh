@@ -11,7 +11,8 @@
 // Kernel shape (persistent, warp specialised, one CTA per SM):
 //   warp 0      TMA producer : A tile [128 rows x 64 K] + W tile [block_n x 64 K] per K block
 //   warp 1      MMA issuer   : 4 x tcgen05.mma (M128, N=block_n, K16) per K block, fp32 acc in TMEM
-//   warps 2..5  epilogue     : tcgen05.ld -> bias / residual / ReLU / gate -> fp16 rows to global
+//   warps 2..9  epilogue     : tcgen05.ld -> bias / residual / ReLU / gate -> fp16 rows to global
+//                              (two warps per TMEM lane quadrant, each takes half of the tile's columns)
 // with a 4-deep smem ring (full/empty mbarriers) and a 2-deep TMEM accumulator ring.
 #pragma once
 #include <cuda.h>
@@ -30,7 +31,8 @@ constexpr int FC_MAX_NT = 8;           // N tiles per layer
 constexpr int FC_MAX_KB = 128;         // scheduled K blocks per layer (sum over N tiles)
 constexpr int FC_MAX_SRC = 4;          // activation sources per layer
 constexpr int FC_TAIL_MAX = 4;         // outputs of the in-epilogue final linear
-constexpr int FC_THREADS = 192;
+constexpr int FC_EPI_WARPS = 8;
+constexpr int FC_THREADS = 64 + 32 * FC_EPI_WARPS;
 constexpr int FC_SMEM_BYTES = FC_STAGES * FC_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ +
                               FC_TAIL_MAX * FC_MAX_N * 4 /*tail weights*/;
 
@@ -68,6 +70,8 @@ struct FcParams {
   const float* tail_b;         // [tail_n]
   float* logits;               // [rows][tail_n]
   int tail_n;
+  int pair_mode;               // split precision: schedule entries come in pairs e = (x_hi, w_hi), e+1 = (x_lo, w_lo)
+                               // of one K block; the MMA warp issues hi*hi, hi*lo, lo*hi (each tile is loaded once)
   int* err_flag;
   int kb_begin[FC_MAX_NT + 1]; // schedule range of each N tile
   uint16_t kb_src[FC_MAX_KB];  // bits 14..15: activation source, bits 0..13: K offset / 64
@@ -75,6 +79,29 @@ struct FcParams {
 };
 
 __device__ __forceinline__ float fast_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// 32 consecutive fp16 of a row (64 B) as four 16-byte loads
+struct Half32 {
+  uint4 q[4];
+};
+__device__ __forceinline__ void ld_half32(Half32& d, const __half* p) {
+  const uint4* s = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) d.q[i] = __ldg(s + i);
+}
+__device__ __forceinline__ void zero_half32(Half32& d) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) d.q[i] = make_uint4(0u, 0u, 0u, 0u);
+}
+__device__ __forceinline__ void add_half32(float (&f)[32], const Half32& d) {
+  const __half2* h = reinterpret_cast<const __half2*>(d.q);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float2 v = __half22float2(h[i]);
+    f[2 * i] += v.x;
+    f[2 * i + 1] += v.y;
+  }
+}
 
 __global__ void __launch_bounds__(FC_THREADS, 1) fc_tcgen05_kernel(const __grid_constant__ FcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -103,7 +130,7 @@ __global__ void __launch_bounds__(FC_THREADS, 1) fc_tcgen05_kernel(const __grid_
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], 4);
+      mbar_init(&acc_empty[s], FC_EPI_WARPS);
     }
     fence_mbar_init();
   }
@@ -151,24 +178,44 @@ __global__ void __launch_bounds__(FC_THREADS, 1) fc_tcgen05_kernel(const __grid_
       uint32_t acc_phase = 0;
       const uint32_t idesc = umma_idesc_f16(uint32_t(p.block_n));
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int mt = item / p.n_tiles;
-        const int nt = item - mt * p.n_tiles;
-        (void)mt;
+        const int nt = item % p.n_tiles;
         mbar_wait(&acc_empty[acc], acc_phase ^ 1u, p.err_flag, 200 + acc);
         tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + uint32_t(acc * FC_MAX_N);
         const int kb0 = p.kb_begin[nt], kb1 = p.kb_begin[nt + 1];
+        uint32_t prev_a = 0, prev_w = 0;
+        int prev_stage = 0;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase, p.err_flag, 300 + stage);
           tc_fence_after_sync();
           const uint32_t a_addr = base + stage * FC_STAGE_BYTES;
           const uint32_t w_addr = a_addr + FC_A_BYTES;
+          if (!p.pair_mode) {
 #pragma unroll
-          for (int k = 0; k < FC_TILE_K / 16; ++k) {
-            umma_f16_ss(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(w_addr + k * 32), idesc,
-                        (kb > kb0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < FC_TILE_K / 16; ++k)
+              umma_f16_ss(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(w_addr + k * 32), idesc,
+                          (kb > kb0 || k > 0) ? 1u : 0u);
+            umma_commit(&empty_bar[stage]);   // frees the smem slot once these MMAs have read it
+          } else if (((kb - kb0) & 1) == 0) {
+            // (x_hi, w_hi): the slot stays live until the cross products of the next entry are done
+#pragma unroll
+            for (int k = 0; k < FC_TILE_K / 16; ++k)
+              umma_f16_ss(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(w_addr + k * 32), idesc,
+                          (kb > kb0 || k > 0) ? 1u : 0u);
+            prev_a = a_addr;
+            prev_w = w_addr;
+            prev_stage = stage;
+          } else {
+            // this slot holds (x_lo, w_lo): issue x_hi * w_lo and x_lo * w_hi
+#pragma unroll
+            for (int k = 0; k < FC_TILE_K / 16; ++k)
+              umma_f16_ss(d_tmem, umma_desc_sw128(prev_a + k * 32), umma_desc_sw128(w_addr + k * 32), idesc, 1u);
+#pragma unroll
+            for (int k = 0; k < FC_TILE_K / 16; ++k)
+              umma_f16_ss(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(prev_w + k * 32), idesc, 1u);
+            umma_commit(&empty_bar[prev_stage]);
+            umma_commit(&empty_bar[stage]);
           }
-          umma_commit(&empty_bar[stage]);   // frees the smem slot once these MMAs have read it
           if (++stage == FC_STAGES) {
             stage = 0;
             phase ^= 1u;
@@ -182,8 +229,15 @@ __global__ void __launch_bounds__(FC_THREADS, 1) fc_tcgen05_kernel(const __grid_
       }
     }
   } else {
-    // ------------------------------------------------------------ epilogue (warps 2..5)
+    // ------------------------------------------------------------ epilogue (warps 2..9)
+    const int ew = warp - 2;
     const int quad = warp & 3;              // TMEM lane quadrant this warp may read
+    const int half = ew >> 2;               // which half of the tile's columns
+    // the in-thread head needs whole rows: there the first four warps take every column
+    const bool whole = (p.epi == FC_EPI_HEAD) || (p.block_n < 64);
+    const int c_begin = whole ? 0 : half * (p.block_n / 2);
+    const int c_end = whole ? (half == 0 ? p.block_n : 0) : c_begin + p.block_n / 2;
+    const bool needs_aux = (p.epi == FC_EPI_ADD_RELU || p.epi == FC_EPI_GATE);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -192,14 +246,30 @@ __global__ void __launch_bounds__(FC_THREADS, 1) fc_tcgen05_kernel(const __grid_
       const int row = mt * FC_TILE_M + quad * 32 + lane;
       const bool row_ok = row < n_rows;
       const int col0 = nt * p.block_n;
+      const float rs = ((p.row_scale && row_ok) ? p.row_scale[row] : 1.0f) * p.acc_scale;
+      // prefetch the first residual / gate chunk while the MMAs of this tile are still running
+      Half32 ax, axl;
+      zero_half32(ax);
+      zero_half32(axl);
+      if (needs_aux && row_ok && c_begin < c_end) {
+        ld_half32(ax, p.aux + size_t(row) * p.aux_ld + col0 + c_begin);
+        if (p.aux_lo) ld_half32(axl, p.aux_lo + size_t(row) * p.aux_ld + col0 + c_begin);
+      }
       mbar_wait(&acc_full[acc], acc_phase, p.err_flag, 400 + acc);
       tc_fence_after_sync();
       const uint32_t t_addr = tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(acc * FC_MAX_N);
-      const float rs = ((p.row_scale && row_ok) ? p.row_scale[row] : 1.0f) * p.acc_scale;
       float tail[FC_TAIL_MAX] = {0.f, 0.f, 0.f, 0.f};
-      for (int c = 0; c < p.block_n; c += 32) {
+      for (int c = c_begin; c < c_end; c += 32) {
         uint32_t v[32];
         tmem_ld_32x32(t_addr + uint32_t(c), v);
+        // next chunk's residual / gate input goes in flight before this chunk is consumed
+        Half32 nx, nxl;
+        zero_half32(nx);
+        zero_half32(nxl);
+        if (needs_aux && row_ok && c + 32 < c_end) {
+          ld_half32(nx, p.aux + size_t(row) * p.aux_ld + col0 + c + 32);
+          if (p.aux_lo) ld_half32(nxl, p.aux_lo + size_t(row) * p.aux_ld + col0 + c + 32);
+        }
         tmem_ld_wait();
         float f[32];
 #pragma unroll
@@ -215,33 +285,20 @@ __global__ void __launch_bounds__(FC_THREADS, 1) fc_tcgen05_kernel(const __grid_
             f[4 * i + 3] += b.w;
           }
         }
-        if (p.epi == FC_EPI_ADD_RELU || p.epi == FC_EPI_GATE) {
-          float ax[32];
+        if (p.epi == FC_EPI_ADD_RELU) {
+          add_half32(f, ax);
+          add_half32(f, axl);
+        } else if (p.epi == FC_EPI_GATE) {
+          float g[32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) ax[i] = 0.f;
-          if (row_ok) {
-            __align__(16) __half hx[32];
-            const uint4* a4 = reinterpret_cast<const uint4*>(p.aux + size_t(row) * p.aux_ld + col0 + c);
+          for (int i = 0; i < 32; ++i) g[i] = 0.f;
+          add_half32(g, ax);
+          add_half32(g, axl);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) reinterpret_cast<uint4*>(hx)[i] = __ldg(a4 + i);
-#pragma unroll
-            for (int i = 0; i < 32; ++i) ax[i] = __half2float(hx[i]);
-            if (p.aux_lo) {
-              const uint4* l4 = reinterpret_cast<const uint4*>(p.aux_lo + size_t(row) * p.aux_ld + col0 + c);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) reinterpret_cast<uint4*>(hx)[i] = __ldg(l4 + i);
-#pragma unroll
-              for (int i = 0; i < 32; ++i) ax[i] += __half2float(hx[i]);
-            }
-          }
-          if (p.epi == FC_EPI_ADD_RELU) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) f[i] += ax[i];
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) f[i] = ax[i] * fast_sigmoid(f[i]);
-          }
+          for (int i = 0; i < 32; ++i) f[i] = g[i] * fast_sigmoid(f[i]);
         }
+        ax = nx;
+        axl = nxl;
         if (p.epi == FC_EPI_RELU || p.epi == FC_EPI_ADD_RELU || p.epi == FC_EPI_HEAD) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
@@ -273,7 +330,7 @@ __global__ void __launch_bounds__(FC_THREADS, 1) fc_tcgen05_kernel(const __grid_
           }
         }
       }
-      if (p.epi == FC_EPI_HEAD && row_ok) {
+      if (p.epi == FC_EPI_HEAD && row_ok && c_begin < c_end) {
 #pragma unroll
         for (int j = 0; j < FC_TAIL_MAX; ++j)
           if (j < p.tail_n) p.logits[size_t(row) * p.tail_n + j] = tail[j] + p.tail_b[j];

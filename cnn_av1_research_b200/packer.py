@@ -26,7 +26,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import numpy as np
 
 BLOB_MAGIC = 0x50315641
-BLOB_VERSION = 3
+BLOB_VERSION = 4
 MAX_NT = 8
 MAX_KB = 128
 TILE_K = 64
@@ -105,6 +105,7 @@ class _Op:
     tail_n: int = 0
     use_row_scale: int = 0
     n_w_chunks: int = 0
+    pair_mode: int = 0
     f0: float = 0.0
     f1: float = 0.0
     kb_begin: List[int] = field(default_factory=list)
@@ -148,16 +149,16 @@ def make_fc_op(name: str, dense: Sequence[np.ndarray], srcs: Sequence[str], out:
                 ci = len(chunks)
                 chunks.append(tile)
                 kb_src.append(((2 * s) << 14) | kb)
-                kb_w.append(ci)                     # (x_hi, w_hi)
+                kb_w.append(ci)                     # slot (x_hi, w_hi)
                 if split:
-                    kb_src.append(((2 * s) << 14) | kb)
-                    kb_w.append(-(ci + 1))          # (x_hi, w_lo): patched below once the hi count is known
+                    # slot (x_lo, w_lo); the kernel issues hi*hi, hi*lo, lo*hi from the two slots (pair mode)
                     kb_src.append(((2 * s + 1) << 14) | kb)
-                    kb_w.append(ci)                 # (x_lo, w_hi)
+                    kb_w.append(-(ci + 1))          # patched below once the hi count is known
         if len(kb_src) == kb_begin[-1]:
             # an all-zero tile still needs one K block so that the accumulator is defined
-            kb_src.append(0)
-            kb_w.append(len(chunks))
+            for _ in range(2 if split else 1):
+                kb_src.append(0)
+                kb_w.append(len(chunks))
             chunks.append(np.zeros((block_n, TILE_K)))
         kb_begin.append(len(kb_src))
     assert len(kb_src) <= MAX_KB, f"{name}: {len(kb_src)} schedule entries"
@@ -179,7 +180,7 @@ def make_fc_op(name: str, dense: Sequence[np.ndarray], srcs: Sequence[str], out:
         src[2 * i], src[2 * i + 1] = _hi(nm), _lo(nm, precision)
     op = _Op(OP_FC, src=src, aux=_hi(aux), aux_lo=_lo(aux, precision), out=_hi(out), out_lo=_lo(out, precision),
              n_tiles=n_tiles, block_n=block_n, epi=epi, use_row_scale=int(use_row_scale),
-             n_w_chunks=w.shape[0] // block_n, f0=1.0 / scale, kb_begin=kb_begin, kb_src=kb_src, kb_w=kb_w,
+             n_w_chunks=w.shape[0] // block_n, pair_mode=int(split), f0=1.0 / scale, kb_begin=kb_begin, kb_src=kb_src, kb_w=kb_w,
              w=w, bias=b, name=name)
     if epi == EPI_HEAD:
         assert n_tiles == 1 and tail_w is not None and tail_w.shape[1] == n
@@ -289,13 +290,13 @@ def _align(n: int, a: int = 256) -> int:
     return -(-n // a) * a
 
 
-OP_FMT = "<16i2f4Q9i128H128H"
+OP_FMT = "<17i2f4Q9i128H128H"
 OP_BYTES = struct.calcsize(OP_FMT)
 
 
 def serialise(kind: str, ops: List[_Op], precision: str) -> bytes:
     header_fmt = "<8I4Q"
-    assert struct.calcsize(header_fmt) == 64 and OP_BYTES == 652
+    assert struct.calcsize(header_fmt) == 64 and OP_BYTES == 656
     cols = list(BUF_COLS.values()) * (2 if precision == "fp16x3" else 1)
     n_bufs = len(cols)
     ops_off = 64
@@ -320,7 +321,7 @@ def serialise(kind: str, ops: List[_Op], precision: str) -> bytes:
         kbs = list(op.kb_src) + [0] * (MAX_KB - len(op.kb_src))
         kbw = list(op.kb_w) + [0] * (MAX_KB - len(op.kb_w))
         table += struct.pack(OP_FMT, op.type, *op.src, op.aux, op.aux_lo, op.out, op.out_lo, op.n_tiles, op.block_n,
-                             op.epi, op.tail_n, op.use_row_scale, len(op.kb_src), op.n_w_chunks, op.f0, op.f1,
+                             op.epi, op.tail_n, op.use_row_scale, len(op.kb_src), op.n_w_chunks, op.pair_mode, op.f0, op.f1,
                              w_off, b_off, tw_off, tb_off, *kbb, *kbs, *kbw)
     total = cursor
     blob = bytearray(total)
@@ -350,7 +351,8 @@ def blob_stats(blob: bytes) -> Dict[str, float]:
     n_ops = struct.unpack_from("<I", blob, 12)[0]
     macs = 0
     for i in range(n_ops):
-        f = struct.unpack_from("<16i", blob, 64 + OP_BYTES * i)
+        f = struct.unpack_from("<17i", blob, 64 + OP_BYTES * i)
         if f[0] == OP_FC:
-            macs += f[14] * f[10] * TILE_K      # schedule entries * block_n * 64
+            products = f[14] * 3 // 2 if f[16] else f[14]     # pair mode: 3 products per 2 entries
+            macs += products * f[10] * TILE_K                  # products * block_n * 64
     return {"tensor_macs_per_block": float(macs), "bytes": float(len(blob))}

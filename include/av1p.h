@@ -142,6 +142,7 @@ typedef struct av1p_fc_desc {
   const float* bias_dev;
   const float* row_scale_dev;
   float acc_scale;
+  int32_t pair_mode;   /* 1: entries are (x_hi,w_hi),(x_lo,w_lo) pairs of one K block -> hi*hi + hi*lo + lo*hi */
   const void* aux_dev; const void* aux_lo_dev; int32_t aux_ld;
   void* out_dev; void* out_lo_dev; int32_t out_ld;
   const float* tail_w_dev; const float* tail_b_dev; float* logits_dev; int32_t tail_n;

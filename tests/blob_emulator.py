@@ -11,21 +11,21 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-OP_FMT = "<16i2f4Q9i128H128H"
+OP_FMT = "<17i2f4Q9i128H128H"
 OP_BYTES = struct.calcsize(OP_FMT)
 
 
 def parse(blob: bytes):
     magic, version, kind, n_ops, n_bufs, n_out, prec, _, ops_off, bufs_off, total, _ = struct.unpack_from("<8I4Q", blob, 0)
-    assert magic == 0x50315641 and version == 3 and total == len(blob)
+    assert magic == 0x50315641 and version == 4 and total == len(blob)
     cols = struct.unpack_from(f"<{n_bufs}I", blob, bufs_off)
     ops = []
     for i in range(n_ops):
         f = struct.unpack_from(OP_FMT, blob, ops_off + OP_BYTES * i)
         ops.append(dict(type=f[0], src=f[1:5], aux=f[5], aux_lo=f[6], out=f[7], out_lo=f[8], n_tiles=f[9], block_n=f[10],
-                        epi=f[11], tail_n=f[12], use_row_scale=f[13], n_kb=f[14], n_w_chunks=f[15], f0=f[16], f1=f[17],
-                        w_off=f[18], bias_off=f[19], tail_w_off=f[20], tail_b_off=f[21], kb_begin=f[22:31],
-                        kb_src=f[31:159], kb_w=f[159:287]))
+                        epi=f[11], tail_n=f[12], use_row_scale=f[13], n_kb=f[14], n_w_chunks=f[15], pair_mode=f[16], f0=f[17],
+                        f1=f[18], w_off=f[19], bias_off=f[20], tail_w_off=f[21], tail_b_off=f[22], kb_begin=f[23:32],
+                        kb_src=f[32:160], kb_w=f[160:288]))
     return dict(kind=kind, n_out=n_out, cols=cols, ops=ops, precision=prec)
 
 
@@ -66,12 +66,24 @@ def run(blob: bytes, images: np.ndarray) -> np.ndarray:
             bn, nt = op["block_n"], op["n_tiles"]
             w = _arr(blob, op["w_off"], np.float16, op["n_w_chunks"] * bn * 64).reshape(op["n_w_chunks"], bn, 64).astype(np.float32)
             acc = np.zeros((n, nt * bn), dtype=np.float32)
+            def a_tile(e_i):
+                e = op["kb_src"][e_i]
+                k0 = (e & 0x3FFF) * 64
+                return bufs[op["src"][e >> 14]][:, k0:k0 + 64]
+
             for ti in range(nt):
-                for e_i in range(op["kb_begin"][ti], op["kb_begin"][ti + 1]):
-                    e = op["kb_src"][e_i]
-                    src = bufs[op["src"][e >> 14]]
-                    k0 = (e & 0x3FFF) * 64
-                    acc[:, ti * bn:(ti + 1) * bn] += src[:, k0:k0 + 64] @ w[op["kb_w"][e_i]].T
+                b0, b1 = op["kb_begin"][ti], op["kb_begin"][ti + 1]
+                out = acc[:, ti * bn:(ti + 1) * bn]
+                if not op["pair_mode"]:
+                    for e_i in range(b0, b1):
+                        out += a_tile(e_i) @ w[op["kb_w"][e_i]].T
+                else:
+                    for e_i in range(b0, b1, 2):          # slots (x_hi, w_hi), (x_lo, w_lo)
+                        a_hi, a_lo = a_tile(e_i), a_tile(e_i + 1)
+                        w_hi, w_lo = w[op["kb_w"][e_i]], w[op["kb_w"][e_i + 1]]
+                        out += a_hi @ w_hi.T
+                        out += a_hi @ w_lo.T
+                        out += a_lo @ w_hi.T
             acc *= (row_scale[:, None] if op["use_row_scale"] else 1.0) * np.float32(op["f0"])
             if op["bias_off"]:
                 acc += _arr(blob, op["bias_off"], np.float32, nt * bn)[None, :]

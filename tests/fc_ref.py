@@ -8,7 +8,7 @@ from cnn_av1_research_b200 import _native as N
 
 
 def run_fc(srcs, w_chunks, kb_begin, kb_src, kb_w, block_n, epi, rows=None, bias=None, row_scale=None, acc_scale=1.0,
-           aux=None, aux_lo=None, out_cols=None, want_lo=False, tail_w=None, tail_b=None, n_dev=None):
+           aux=None, aux_lo=None, out_cols=None, want_lo=False, tail_w=None, tail_b=None, n_dev=None, pair_mode=0):
     """srcs: list of fp16 CUDA tensors [rows, cols]; w_chunks: fp16 CUDA [n_chunks*block_n, 64]."""
     dev = srcs[0].device
     rows = srcs[0].shape[0] if rows is None else rows
@@ -24,7 +24,7 @@ def run_fc(srcs, w_chunks, kb_begin, kb_src, kb_w, block_n, epi, rows=None, bias
     d.w_dev, d.n_w_chunks = w_chunks.data_ptr(), w_chunks.shape[0] // block_n
     d.n_kb_total, d.n_tiles, d.block_n, d.epi = len(kb_src), n_tiles, block_n, epi
     d.kb_begin, d.kb_src, d.kb_w = kbb.ctypes.data, kbs.ctypes.data, kbw.ctypes.data
-    d.bias_dev, d.row_scale_dev, d.acc_scale = N.ptr(bias), N.ptr(row_scale), acc_scale
+    d.bias_dev, d.row_scale_dev, d.acc_scale, d.pair_mode = N.ptr(bias), N.ptr(row_scale), acc_scale, pair_mode
     d.aux_dev, d.aux_lo_dev, d.aux_ld = N.ptr(aux), N.ptr(aux_lo), (aux.shape[1] if aux is not None else 0)
     out = out_lo = logits = None
     if epi != 4:
@@ -46,16 +46,24 @@ def run_fc(srcs, w_chunks, kb_begin, kb_src, kb_w, block_n, epi, rows=None, bias
 
 
 def ref_fc(srcs, w_chunks, kb_begin, kb_src, kb_w, block_n, epi, bias=None, row_scale=None, acc_scale=1.0, aux=None,
-           aux_lo=None, tail_w=None, tail_b=None):
+           aux_lo=None, tail_w=None, tail_b=None, pair_mode=0):
     """float64 reference of the same schedule."""
     rows = srcs[0].shape[0]
     n_tiles = len(kb_begin) - 1
     w = w_chunks.double().reshape(-1, block_n, 64)
     acc = torch.zeros((rows, n_tiles * block_n), dtype=torch.float64, device=srcs[0].device)
+    def a_tile(e):
+        s, k0 = kb_src[e] >> 14, (kb_src[e] & 0x3FFF) * 64
+        return srcs[s][:, k0:k0 + 64].double()
+
     for t in range(n_tiles):
-        for e in range(kb_begin[t], kb_begin[t + 1]):
-            s, k0 = kb_src[e] >> 14, (kb_src[e] & 0x3FFF) * 64
-            acc[:, t * block_n:(t + 1) * block_n] += srcs[s][:, k0:k0 + 64].double() @ w[kb_w[e]].T
+        out = acc[:, t * block_n:(t + 1) * block_n]
+        if not pair_mode:
+            for e in range(kb_begin[t], kb_begin[t + 1]):
+                out += a_tile(e) @ w[kb_w[e]].T
+        else:
+            for e in range(kb_begin[t], kb_begin[t + 1], 2):
+                out += a_tile(e) @ w[kb_w[e]].T + a_tile(e) @ w[kb_w[e + 1]].T + a_tile(e + 1) @ w[kb_w[e]].T
     acc = acc * acc_scale
     if row_scale is not None:
         acc = acc * row_scale.double()[:, None]

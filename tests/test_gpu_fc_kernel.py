@@ -149,3 +149,29 @@ def test_fp16_subnormal_operands_are_not_flushed(cuda_device):
     b = torch.full((128, 64), 512.0, device=dev).half()
     out, _, _ = run_fc([b], wsub, [0, 1], [0], [0], 64, epi=0)
     assert torch.equal(out.float(), torch.full((128, 64), 2.0 ** -9, device=dev)), f"got {out.float().unique().tolist()}"
+
+
+@pytest.mark.parametrize("rows,block_n,n_tiles,kblocks", [(1000, 256, 2, 5), (333, 64, 1, 3), (2048, 128, 3, 9)])
+def test_pair_mode_split_products(cuda_device, rows, block_n, n_tiles, kblocks):
+    """Split precision: slots (x_hi, w_hi), (x_lo, w_lo) -> hi*hi + hi*lo + lo*hi; result good to ~2^-21."""
+    dev = cuda_device
+    g = torch.Generator(device=dev).manual_seed(rows)
+    x = torch.randn((rows, kblocks * 64), device=dev, generator=g)
+    x_hi = x.half()
+    x_lo = (x - x_hi.float()).half()
+    kb_begin, kb_src, kb_w, nchunk = [0], [], [], n_tiles * kblocks
+    wf = torch.randn((nchunk * block_n, 64), device=dev, generator=g) * 8.0
+    w_hi = wf.half()
+    w_lo = (wf - w_hi.float()).half()
+    for t in range(n_tiles):
+        for kb in range(kblocks):
+            ci = t * kblocks + kb
+            kb_src += [(0 << 14) | kb, (1 << 14) | kb]
+            kb_w += [ci, nchunk + ci]
+        kb_begin.append(len(kb_src))
+    w = torch.cat([w_hi, w_lo]).contiguous()
+    out, out_lo, _ = run_fc([x_hi, x_lo], w, kb_begin, kb_src, kb_w, block_n, 0, acc_scale=0.125, want_lo=True, pair_mode=1)
+    ref = ref_fc([x_hi, x_lo], w, kb_begin, kb_src, kb_w, block_n, 0, acc_scale=0.125, pair_mode=1)
+    _check(out.double() + out_lo.double(), ref, "pair mode hi+lo", rel=2e-5)
+    exact = (x.double() @ wf.double().reshape(n_tiles, kblocks, block_n, 64).permute(0, 2, 1, 3).reshape(n_tiles * block_n, -1).T) * 0.125
+    _check(out.double() + out_lo.double(), exact, "pair mode vs unsplit fp32 operands", rel=2e-5)

@@ -49,7 +49,7 @@ def test_bn_folding_is_exact_in_float64():
 
 def test_schedule_skips_zero_blocks_and_fits_limits():
     sd = synth.random_state_dict("stage1", 3)
-    for precision, mult in (("fp16", 1), ("fp16x3", 3)):
+    for precision, mult in (("fp16", 1), ("fp16x3", 2)):
         ops = packer.backbone_ops(sd, precision) + packer.head_ops("stage1", sd, precision)
         fc = [o for o in ops if o.type == packer.OP_FC]
         by_name = {o.name: o for o in fc}
@@ -70,7 +70,7 @@ def test_schedule_skips_zero_blocks_and_fits_limits():
 def test_blob_layout():
     blob = packer.pack_stage("rect", synth.random_state_dict("rect", 0), "fp16x3")
     magic, version, kind, n_ops, n_bufs, n_out = struct.unpack_from("<6I", blob, 0)
-    assert (magic, version, kind, n_bufs, n_out) == (0x50315641, 3, 2, 20, 2)
+    assert (magic, version, kind, n_bufs, n_out) == (0x50315641, 4, 2, 20, 2)
     P = E.parse(blob)
     assert P["ops"][0]["type"] == packer.OP_STEM and P["ops"][-1]["epi"] == packer.EPI_HEAD
     for op in P["ops"]:
