@@ -73,6 +73,108 @@ __global__ void __launch_bounds__(256) sam_gate_kernel(const __half* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------
+// Squeeze-and-excitation block (reference models.py:24-43) as one memory-bound pass:
+//   s = sigmoid(W2 . relu(W1 . mean_positions(x)));   out[pos][c] = x[pos][c] * s[c]
+// One warp per block row ([NPOS][C] fp16, hi + optional lo); the two tiny weight matrices sit in
+// shared memory as fp32 ([H][C] and W2 transposed to [H][C], H = C/16).  Lane l owns the 8 channels of
+// channel group l % (C/8) at NPOS*C/256 positions, so every global access is a 16-byte vector and a
+// warp touches 512 contiguous bytes per instruction.  Used for se1..se3 (C = 64, 128, 256); se4's
+// 2 x 64 KB of weights do not fit this scheme and stay on the tensor-core path.
+template <int C, int NPOS>
+__global__ void __launch_bounds__(256) se_kernel(const __half* __restrict__ x, const __half* __restrict__ x_lo,
+                                                 __half* __restrict__ out, __half* __restrict__ out_lo,
+                                                 const int* n_dev, int n, const float* __restrict__ w /*[2][H][C]*/) {
+  constexpr int H = C / 16;
+  constexpr int L = C * NPOS;
+  constexpr int GROUPS = C / 8;           // channel groups of 8
+  constexpr int CPL = L / 256;            // 16-byte chunks per lane
+  static_assert(L % 256 == 0 && GROUPS <= 32, "unsupported SE shape");
+  extern __shared__ __align__(16) float se_w[];   // [H][C] W1, then [H][C] W2^T
+  for (int i = threadIdx.x; i < 2 * H * C; i += blockDim.x) se_w[i] = w[i];
+  __syncthreads();
+  const float* w1 = se_w;
+  const float* w2t = se_w + H * C;
+  const int rows = n_dev ? *n_dev : n;
+  const int lane = threadIdx.x & 31;
+  const int ch0 = (lane % GROUPS) * 8;
+  const int warps_per_grid = (gridDim.x * blockDim.x) >> 5;
+  for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < rows; r += warps_per_grid) {
+    float v[CPL][8];
+    float mean[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < CPL; ++i) {
+      const size_t off = size_t(r) * L + size_t(lane + 32 * i) * 8;
+      const uint4 q = __ldg(reinterpret_cast<const uint4*>(x + off));
+      const __half2* h = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = __half22float2(h[k]);
+        v[i][2 * k] = f.x;
+        v[i][2 * k + 1] = f.y;
+      }
+      if (x_lo) {
+        const uint4 ql = __ldg(reinterpret_cast<const uint4*>(x_lo + off));
+        const __half2* hl = reinterpret_cast<const __half2*>(&ql);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 f = __half22float2(hl[k]);
+          v[i][2 * k] += f.x;
+          v[i][2 * k + 1] += f.y;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) mean[k] += v[i][k];
+    }
+    // finish the spatial mean across the lanes that hold the same channel group
+#pragma unroll
+    for (int o = GROUPS; o < 32; o <<= 1)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) mean[k] += __shfl_xor_sync(0xffffffffu, mean[k], o);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) mean[k] *= (1.0f / NPOS);
+    // hidden = relu(W1 . mean): one leader lane per channel group contributes, then a warp reduction
+    float hid[H];
+#pragma unroll
+    for (int j = 0; j < H; ++j) {
+      float pj = 0.f;
+      if (lane < GROUPS) {
+        const float4 a = *reinterpret_cast<const float4*>(w1 + j * C + ch0);
+        const float4 b = *reinterpret_cast<const float4*>(w1 + j * C + ch0 + 4);
+        pj = mean[0] * a.x + mean[1] * a.y + mean[2] * a.z + mean[3] * a.w + mean[4] * b.x + mean[5] * b.y + mean[6] * b.z +
+             mean[7] * b.w;
+      }
+      hid[j] = fmaxf(warp_sum(pj), 0.f);
+    }
+    float sc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < H; ++j) {
+      const float4 a = *reinterpret_cast<const float4*>(w2t + j * C + ch0);
+      const float4 b = *reinterpret_cast<const float4*>(w2t + j * C + ch0 + 4);
+      sc[0] = fmaf(a.x, hid[j], sc[0]); sc[1] = fmaf(a.y, hid[j], sc[1]);
+      sc[2] = fmaf(a.z, hid[j], sc[2]); sc[3] = fmaf(a.w, hid[j], sc[3]);
+      sc[4] = fmaf(b.x, hid[j], sc[4]); sc[5] = fmaf(b.y, hid[j], sc[5]);
+      sc[6] = fmaf(b.z, hid[j], sc[6]); sc[7] = fmaf(b.w, hid[j], sc[7]);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sc[k] = 1.0f / (1.0f + expf(-sc[k]));
+#pragma unroll
+    for (int i = 0; i < CPL; ++i) {
+      const size_t off = size_t(r) * L + size_t(lane + 32 * i) * 8;
+      __align__(16) __half2 hi[4], lo[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float a = v[i][2 * k] * sc[2 * k], b = v[i][2 * k + 1] * sc[2 * k + 1];
+        hi[k] = __floats2half2_rn(a, b);
+        const float2 hf = __half22float2(hi[k]);
+        lo[k] = __floats2half2_rn(a - hf.x, b - hf.y);
+      }
+      *reinterpret_cast<uint4*>(out + off) = *reinterpret_cast<const uint4*>(hi);
+      if (out_lo) *reinterpret_cast<uint4*>(out_lo + off) = *reinterpret_cast<const uint4*>(lo);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // FGVC tail (reference scripts/006_train_stage3_ab_fgvc.py:235-241, 290-293):
 //   f = h / max(||h||_2, 1e-12);  logits = 20 * f . What^T,  What = row-normalised classifier weight
 // (normalised once at pack time).  One warp per row of 512 fp16.

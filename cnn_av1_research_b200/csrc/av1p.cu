@@ -109,7 +109,7 @@ extern "C" int av1p_debug_watchdog(void) { return g_ctx.watchdog_host ? *g_ctx.w
 // Optional CUDA-event bracket around every kernel launch (bench.py's roofline leg).  Events are
 // recorded on the launching stream; nothing synchronises until av1p_profile_end.
 namespace {
-enum ProfClass { PROF_STEM = 0, PROF_FC = 1, PROF_SAM = 2, PROF_FGVC = 3, PROF_ROUTE = 4, PROF_FINALIZE = 5, PROF_CLASSES = 6 };
+enum ProfClass { PROF_STEM = 0, PROF_FC = 1, PROF_SAM = 2, PROF_FGVC = 3, PROF_ROUTE = 4, PROF_FINALIZE = 5, PROF_SE = 6, PROF_CLASSES = 7 };
 struct ProfRec { int cls; cudaEvent_t a, b; };
 struct Profiler {
   bool on = false;
@@ -245,6 +245,9 @@ struct PlannedOp {
   StemParams stem;      // AV1P_OP_STEM
   const __half* src = nullptr;   // SAM / FGVC
   const __half* src_lo = nullptr;
+  __half* dst = nullptr;         // SE
+  __half* dst_lo = nullptr;
+  int se_c = 0, se_npos = 0;
   int ld = 0;
   float f0 = 0.f, f1 = 0.f;
   const float* w = nullptr;
@@ -367,6 +370,20 @@ int plan_stage(const av1p_model* m, const ActLayout& L, uint8_t* act_base, av1p_
         if (op.type == AV1P_OP_FGVC_TAIL && !P.w) return fail(AV1P_EINVAL, "FGVC tail without weights");
         break;
       }
+      case AV1P_OP_SE: {
+        P.src = buf(op.src[0]);
+        P.src_lo = buf(op.src[1]);
+        P.dst = buf(op.out);
+        P.dst_lo = buf(op.out_lo);
+        P.se_c = op.block_n;
+        P.se_npos = op.n_tiles;
+        P.w = reinterpret_cast<const float*>(at(op.w_off));
+        const bool shape_ok = (P.se_c == 64 && P.se_npos == 16) || (P.se_c == 128 && P.se_npos == 4) || (P.se_c == 256 && P.se_npos == 1);
+        if (!P.src || !P.dst || !P.w || !shape_ok || int(L.cols[op.src[0]]) != P.se_c * P.se_npos ||
+            int(L.cols[op.out]) != P.se_c * P.se_npos || (op.src[1] >= 0) != (op.out_lo >= 0))
+          return fail(AV1P_EINVAL, "malformed SE op");
+        break;
+      }
       default:
         return fail(AV1P_EINVAL, "unknown op type %d", op.type);
     }
@@ -430,6 +447,18 @@ int run_stage(av1p_stage* s, const StemInput& si, const int32_t* idx, const int3
         const int grid = std::min(ceil_div(n, 8), g_ctx.sms * 8);
         ProfScope ps(PROF_SAM, st);
         sam_gate_kernel<<<grid, 256, 0, st>>>(P.src, P.src_lo, P.ld, n_dev, n, P.f0, P.f1, s->row_scale);
+        break;
+      }
+      case AV1P_OP_SE: {
+        const int grid = std::min(ceil_div(n, 8), g_ctx.sms * 8);
+        ProfScope ps(PROF_SE, st);
+        const size_t smem = size_t(2) * (P.se_c / 16) * P.se_c * sizeof(float);
+        if (P.se_c == 64)
+          se_kernel<64, 16><<<grid, 256, smem, st>>>(P.src, P.src_lo, P.dst, P.dst_lo, n_dev, n, P.w);
+        else if (P.se_c == 128)
+          se_kernel<128, 4><<<grid, 256, smem, st>>>(P.src, P.src_lo, P.dst, P.dst_lo, n_dev, n, P.w);
+        else
+          se_kernel<256, 1><<<grid, 256, smem, st>>>(P.src, P.src_lo, P.dst, P.dst_lo, n_dev, n, P.w);
         break;
       }
       case AV1P_OP_FGVC_TAIL: {

@@ -8,7 +8,7 @@
 #include <stdint.h>
 
 #define AV1P_BLOB_MAGIC 0x50315641u   /* "AV1P" */
-#define AV1P_BLOB_VERSION 4u
+#define AV1P_BLOB_VERSION 5u
 #define AV1P_BLOB_MAX_NT 8
 #define AV1P_BLOB_MAX_KB 128
 
@@ -17,6 +17,7 @@ enum Av1pOpType : int32_t {
   AV1P_OP_FC = 1,         // block-Toeplitz linear layer on tensor cores
   AV1P_OP_SAM = 2,        // spatial-attention scalar of `src0` (512 cols) -> row_scale
   AV1P_OP_FGVC_TAIL = 3,  // L2-normalise `src0` (512 cols) + cosine classifier -> logits[4]
+  AV1P_OP_SE = 4,         // squeeze-excite on CUDA cores: block_n = channels (64/128/256), n_tiles = positions
 };
 
 #pragma pack(push, 1)

@@ -12,11 +12,12 @@
 
 namespace av1p {
 
-constexpr int STEM_NB = 4;                 // blocks per CTA pass
-constexpr int STEM_THREADS = 64 * STEM_NB; // one thread per (block, conv output position)
+constexpr int STEM_NB = 8;                 // blocks per CTA pass
+constexpr int STEM_THREADS = 32 * STEM_NB; // one thread per (block, conv column ox, pair of conv rows)
 constexpr int STEM_WPAD = 52;              // 49 taps padded to 13 float4
 constexpr int STEM_TILE_H = 22, STEM_TILE_W = 24;   // 16x16 block + 3-pixel zero halo (width padded)
-constexpr int STEM_CONV_LD = 65;           // floats per conv-output row (64 ch + 1 pad -> no bank conflicts)
+constexpr int STEM_CH_PASS = 32;           // output channels per pass (bounds the fp32 conv tile in smem)
+constexpr int STEM_CONV_LD = STEM_CH_PASS + 1;      // floats per conv-output row (+1 pad -> no bank conflicts)
 constexpr int STEM_SMEM_BYTES = 64 * STEM_WPAD * 4 + 64 * 4 + STEM_NB * STEM_TILE_H * STEM_TILE_W * 4 +
                                 STEM_NB * 64 * STEM_CONV_LD * 4;
 
@@ -43,12 +44,12 @@ struct StemParams {
   __half* out_lo;           // split precision: fp16(x - fp16(x)), nullptr otherwise
 };
 
-__global__ void __launch_bounds__(STEM_THREADS) stem_kernel(const StemParams p) {
+__global__ void __launch_bounds__(STEM_THREADS, 2) stem_kernel(const StemParams p) {
   extern __shared__ __align__(16) uint8_t stem_smem[];
   float* w_s = reinterpret_cast<float*>(stem_smem);                       // [64][52]
   float* b_s = w_s + 64 * STEM_WPAD;                                      // [64]
   float* tile = b_s + 64;                                                 // [NB][22][24]
-  float* conv = tile + STEM_NB * STEM_TILE_H * STEM_TILE_W;                // [NB][64][65] fp32
+  float* conv = tile + STEM_NB * STEM_TILE_H * STEM_TILE_W;                // [NB][64 pos][33] fp32, one channel pass
 
   const int n = p.n_dev ? *p.n_dev : p.n;
   const int groups = (n + STEM_NB - 1) / STEM_NB;
@@ -59,16 +60,17 @@ __global__ void __launch_bounds__(STEM_THREADS) stem_kernel(const StemParams p) 
   for (int i = threadIdx.x; i < STEM_NB * STEM_TILE_H * STEM_TILE_W; i += STEM_THREADS) tile[i] = 0.f;
   __syncthreads();
 
-  const int tb = threadIdx.x >> 6;       // block slot in this pass
-  const int pos = threadIdx.x & 63;      // conv output position 0..63 (8x8)
-  const int oy = pos >> 3, ox = pos & 7;
+  const int tb = threadIdx.x >> 5;       // block slot in this pass
+  const int lane = threadIdx.x & 31;
+  const int ox = lane & 7;               // conv output column
+  const int oy = (lane >> 3) * 2;        // first of the two conv output rows this thread computes
 
   for (int grp = blockIdx.x; grp < groups; grp += gridDim.x) {
-    // ---- gather + normalise: thread handles 4 pixels: row = pos/4, cols (pos%4)*4..+3 of block tb
+    // ---- gather + normalise: thread handles 8 pixels: row = lane/2, cols (lane%2)*8..+7 of block tb
     {
       const int r = grp * STEM_NB + tb;
-      const int py = pos >> 2, px0 = (pos & 3) * 4;
-      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      const int py = lane >> 1, px0 = (lane & 1) * 8;
+      float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       if (r < n) {
         const int g = p.idx ? p.idx[r] : r;
         if (p.in.kind == 0) {
@@ -78,92 +80,104 @@ __global__ void __launch_bounds__(STEM_THREADS) stem_kernel(const StemParams p) 
           const int y = by * 16 + py, x0 = bx * 16 + px0;
           if (y < p.in.height) {
             const uint16_t* src = p.in.frames + size_t(f) * p.in.frame_stride + size_t(y) * p.in.pitch + x0;
-            if (x0 + 3 < p.in.width && ((reinterpret_cast<uintptr_t>(src) & 7u) == 0)) {
-              const uint2 q = __ldg(reinterpret_cast<const uint2*>(src));
-              v[0] = float(q.x & 0xFFFFu);
-              v[1] = float(q.x >> 16);
-              v[2] = float(q.y & 0xFFFFu);
-              v[3] = float(q.y >> 16);
+            if (x0 + 7 < p.in.width && ((reinterpret_cast<uintptr_t>(src) & 15u) == 0)) {
+              const uint4 q = __ldg(reinterpret_cast<const uint4*>(src));
+              const uint32_t u[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                v[2 * j] = float(u[j] & 0xFFFFu);
+                v[2 * j + 1] = float(u[j] >> 16);
+              }
             } else {
 #pragma unroll
-              for (int j = 0; j < 4; ++j)
+              for (int j = 0; j < 8; ++j)
                 if (x0 + j < p.in.width) v[j] = float(__ldg(src + j));
             }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) v[j] = __fdiv_rn(v[j], 1023.0f);
+            for (int j = 0; j < 8; ++j) v[j] = __fdiv_rn(v[j], 1023.0f);
           }
         } else {
-          const float4 q = __ldg(reinterpret_cast<const float4*>(p.in.images + size_t(g) * 256 + py * 16 + px0));
-          v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+          const float4* src = reinterpret_cast<const float4*>(p.in.images + size_t(g) * 256 + py * 16 + px0);
+          const float4 a = __ldg(src), b = __ldg(src + 1);
+          v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+          v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
         }
       }
       float* t = tile + (tb * STEM_TILE_H + py + 3) * STEM_TILE_W + px0 + 3;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) t[j] = v[j];
+      for (int j = 0; j < 8; ++j) t[j] = v[j];
     }
     __syncthreads();
 
-    // ---- conv1: thread (tb, pos) holds its 7x7 patch, loops over the 64 output channels
-    float patch[49];
+    // ---- conv1: the thread keeps the 9x7 input patch of its two output rows in registers and walks
+    //      the channels two at a time (4 accumulators; every weight fetched from smem feeds 2 FMAs)
+    float patch[9][7];
     {
       const float* t = tile + (tb * STEM_TILE_H + 2 * oy) * STEM_TILE_W + 2 * ox;
 #pragma unroll
-      for (int ky = 0; ky < 7; ++ky)
+      for (int y = 0; y < 9; ++y)
 #pragma unroll
-        for (int kx = 0; kx < 7; ++kx) patch[ky * 7 + kx] = t[ky * STEM_TILE_W + kx];
+        for (int x = 0; x < 7; ++x) patch[y][x] = t[y * STEM_TILE_W + x];
     }
-    float* crow = conv + (tb * 64 + pos) * STEM_CONV_LD;
+    for (int pass = 0; pass < 64 / STEM_CH_PASS; ++pass) {
+      float* c0 = conv + (tb * 64 + oy * 8 + ox) * STEM_CONV_LD;     // conv row oy
+      float* c1 = c0 + 8 * STEM_CONV_LD;                             // conv row oy + 1
 #pragma unroll 1
-    for (int c = 0; c < 64; c += 2) {
-      float a0 = b_s[c], a1 = b_s[c + 1];
-      const float4* w0 = reinterpret_cast<const float4*>(w_s + c * STEM_WPAD);
-      const float4* w1 = reinterpret_cast<const float4*>(w_s + (c + 1) * STEM_WPAD);
+      for (int cc = 0; cc < STEM_CH_PASS; cc += 2) {
+        const int c = pass * STEM_CH_PASS + cc;
+        float a00 = b_s[c], a01 = a00, a10 = b_s[c + 1], a11 = a10;  // a<channel><row>
+        const float* w0 = w_s + c * STEM_WPAD;
+        const float* w1 = w0 + STEM_WPAD;
 #pragma unroll
-      for (int q = 0; q < 12; ++q) {
-        const float4 u0 = w0[q], u1 = w1[q];
-        a0 = fmaf(patch[4 * q + 0], u0.x, a0); a1 = fmaf(patch[4 * q + 0], u1.x, a1);
-        a0 = fmaf(patch[4 * q + 1], u0.y, a0); a1 = fmaf(patch[4 * q + 1], u1.y, a1);
-        a0 = fmaf(patch[4 * q + 2], u0.z, a0); a1 = fmaf(patch[4 * q + 2], u1.z, a1);
-        a0 = fmaf(patch[4 * q + 3], u0.w, a0); a1 = fmaf(patch[4 * q + 3], u1.w, a1);
+        for (int ky = 0; ky < 7; ++ky) {
+#pragma unroll
+          for (int kx = 0; kx < 7; ++kx) {
+            const float u0 = w0[ky * 7 + kx], u1 = w1[ky * 7 + kx];
+            a00 = fmaf(patch[ky][kx], u0, a00);
+            a01 = fmaf(patch[ky + 2][kx], u0, a01);
+            a10 = fmaf(patch[ky][kx], u1, a10);
+            a11 = fmaf(patch[ky + 2][kx], u1, a11);
+          }
+        }
+        c0[cc] = fmaxf(a00, 0.f);
+        c0[cc + 1] = fmaxf(a10, 0.f);
+        c1[cc] = fmaxf(a01, 0.f);
+        c1[cc + 1] = fmaxf(a11, 0.f);
       }
-      a0 = fmaf(patch[48], w_s[c * STEM_WPAD + 48], a0);
-      a1 = fmaf(patch[48], w_s[(c + 1) * STEM_WPAD + 48], a1);
-      crow[c] = fmaxf(a0, 0.f);
-      crow[c + 1] = fmaxf(a1, 0.f);
-    }
-    __syncthreads();
+      __syncthreads();
 
-    // ---- maxpool 3x3 s2 p1 (8x8 -> 4x4) in fp32, then fp16 (hi, and lo in split precision) stores
-    for (int o = threadIdx.x; o < STEM_NB * 16 * 32; o += STEM_THREADS) {
-      const int cp = o & 31;             // channel pair
-      const int q = (o >> 5) & 15;       // pooled position
-      const int b = o >> 9;
-      const int r = grp * STEM_NB + b;
-      if (r >= n) continue;
-      const int qy = q >> 2, qx = q & 3;
-      float m0 = 0.f, m1 = 0.f;          // inputs are post-ReLU (>= 0): 0 is the identity of max
+      // ---- maxpool 3x3 s2 p1 (8x8 -> 4x4) in fp32, then fp16 (hi, and lo in split precision) stores
+      for (int o = threadIdx.x; o < STEM_NB * 16 * (STEM_CH_PASS / 2); o += STEM_THREADS) {
+        const int cp = o % (STEM_CH_PASS / 2);        // channel pair inside this pass
+        const int q = (o / (STEM_CH_PASS / 2)) & 15;  // pooled position
+        const int b = o / (16 * (STEM_CH_PASS / 2));
+        const int r = grp * STEM_NB + b;
+        if (r >= n) continue;
+        const int qy = q >> 2, qx = q & 3;
+        float m0 = 0.f, m1 = 0.f;          // inputs are post-ReLU (>= 0): 0 is the identity of max
 #pragma unroll
-      for (int dy = -1; dy <= 1; ++dy) {
-        const int y = 2 * qy + dy;
-        if (y < 0 || y > 7) continue;
+        for (int dy = -1; dy <= 1; ++dy) {
+          const int y = 2 * qy + dy;
+          if (y < 0 || y > 7) continue;
 #pragma unroll
-        for (int dx = -1; dx <= 1; ++dx) {
-          const int x = 2 * qx + dx;
-          if (x < 0 || x > 7) continue;
-          const float* cv = conv + (b * 64 + y * 8 + x) * STEM_CONV_LD + 2 * cp;
-          m0 = fmaxf(m0, cv[0]);
-          m1 = fmaxf(m1, cv[1]);
+          for (int dx = -1; dx <= 1; ++dx) {
+            const int x = 2 * qx + dx;
+            if (x < 0 || x > 7) continue;
+            const float* cv = conv + (b * 64 + y * 8 + x) * STEM_CONV_LD + 2 * cp;
+            m0 = fmaxf(m0, cv[0]);
+            m1 = fmaxf(m1, cv[1]);
+          }
+        }
+        const __half2 hi = __floats2half2_rn(m0, m1);
+        const size_t off = size_t(r) * 1024 + q * 64 + pass * STEM_CH_PASS + 2 * cp;
+        *reinterpret_cast<__half2*>(p.out + off) = hi;
+        if (p.out_lo) {
+          const float2 hf = __half22float2(hi);
+          *reinterpret_cast<__half2*>(p.out_lo + off) = __floats2half2_rn(m0 - hf.x, m1 - hf.y);
         }
       }
-      const __half2 hi = __floats2half2_rn(m0, m1);
-      const size_t off = size_t(r) * 1024 + q * 64 + 2 * cp;
-      *reinterpret_cast<__half2*>(p.out + off) = hi;
-      if (p.out_lo) {
-        const float2 hf = __half22float2(hi);
-        *reinterpret_cast<__half2*>(p.out_lo + off) = __floats2half2_rn(m0 - hf.x, m1 - hf.y);
-      }
+      __syncthreads();
     }
-    __syncthreads();
   }
 }
 

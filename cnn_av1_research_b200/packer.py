@@ -26,12 +26,12 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import numpy as np
 
 BLOB_MAGIC = 0x50315641
-BLOB_VERSION = 4
+BLOB_VERSION = 5
 MAX_NT = 8
 MAX_KB = 128
 TILE_K = 64
 
-OP_STEM, OP_FC, OP_SAM, OP_FGVC_TAIL = 0, 1, 2, 3
+OP_STEM, OP_FC, OP_SAM, OP_FGVC_TAIL, OP_SE = 0, 1, 2, 3, 4
 EPI_LINEAR, EPI_RELU, EPI_ADD_RELU, EPI_GATE, EPI_HEAD = 0, 1, 2, 3, 4
 
 STAGE_KINDS = {"stage1": 0, "stage2": 1, "rect": 2, "ab_fgvc": 3, "ab": 4}
@@ -214,6 +214,13 @@ def backbone_ops(sd, precision: str = "fp16x3", prefix: str = "backbone.") -> Li
         w1 = _np64(sd[f"{p}se{layer}.excitation.0.weight"])     # [C/16, C]
         w2 = _np64(sd[f"{p}se{layer}.excitation.2.weight"])     # [C, C/16]
         npos = grid * grid
+        c = w1.shape[1]
+        if c <= 256:
+            # memory-bound fused CUDA-core kernel (csrc/aux_kernels.cuh: se_kernel); weights [W1 ; W2^T] fp32
+            ops.append(_Op(OP_SE, src=[_hi(src), _lo(src, precision), -1, -1], out=_hi(dst), out_lo=_lo(dst, precision),
+                           n_tiles=npos, block_n=c, w=np.concatenate([w1, w2.T], axis=0).astype(np.float32),
+                           name=f"se{layer}"))
+            return
         d1 = np.zeros((64, npos * w1.shape[1]))
         d1[: w1.shape[0]] = np.tile(w1 / npos, (1, npos))       # mean over positions folded in
         d2 = np.zeros((npos * w2.shape[0], 64))

@@ -116,7 +116,7 @@ int av1p_finalize_labels(const float* logits_dev, int32_t num_classes, int32_t l
 /* ---- measurement support (bench.py): bracket every kernel launch of the calling thread with CUDA
  *      events on its stream.  av1p_profile_end synchronises on those events and returns the summed
  *      device time and launch count per kernel class: 0 stem, 1 tcgen05 FC, 2 SAM gate, 3 FGVC tail,
- *      4 routing, 5 label finalize (arrays of 6). */
+ *      4 routing, 5 label finalize, 6 squeeze-excite (arrays of 8). */
 int av1p_profile_begin(void);
 int av1p_profile_end(float* ms_by_class, int32_t* launches_by_class);
 

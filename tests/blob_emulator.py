@@ -17,7 +17,7 @@ OP_BYTES = struct.calcsize(OP_FMT)
 
 def parse(blob: bytes):
     magic, version, kind, n_ops, n_bufs, n_out, prec, _, ops_off, bufs_off, total, _ = struct.unpack_from("<8I4Q", blob, 0)
-    assert magic == 0x50315641 and version == 4 and total == len(blob)
+    assert magic == 0x50315641 and version == 5 and total == len(blob)
     cols = struct.unpack_from(f"<{n_bufs}I", blob, bufs_off)
     ops = []
     for i in range(n_ops):
@@ -108,6 +108,14 @@ def run(blob: bytes, images: np.ndarray) -> np.ndarray:
             w = _arr(blob, op["w_off"], np.float32, 4 * 512).reshape(4, 512)
             nrm = np.maximum(np.sqrt((x * x).sum(axis=1, keepdims=True)), 1e-12)
             logits = op["f0"] * (x @ w.T) / nrm
+        elif t == 4:  # squeeze-excite (fp32 on CUDA cores)
+            c, npos = op["block_n"], op["n_tiles"]
+            hdim = c // 16
+            wt = _arr(blob, op["w_off"], np.float32, 2 * hdim * c).reshape(2, hdim, c)
+            x = load(op["src"][0], op["src"][1]).reshape(n, npos, c)
+            hid = np.maximum(x.mean(axis=1) @ wt[0].T, 0.0)
+            s = 1.0 / (1.0 + np.exp(-(hid @ wt[1])))
+            store(op, (x * s[:, None, :]).reshape(n, npos * c), npos * c)
         else:
             raise ValueError(t)
     return logits.astype(np.float32)
