@@ -18,7 +18,7 @@
 #include "aux_kernels.cuh"
 #include "blob_format.h"
 #include "fc_tcgen05.cuh"
-#include "stem.cuh"
+#include "stem_tc.cuh"
 
 using namespace av1p;
 
@@ -74,7 +74,7 @@ int ensure_ctx() {
   if (!fn || qres != cudaDriverEntryPointSuccess) return fail(AV1P_ECUDA, "cuTensorMapEncodeTiled not available");
   g_ctx.encode = reinterpret_cast<EncodeTiledFn>(fn);
   CUDA_TRY(cudaFuncSetAttribute(fc_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FC_SMEM_BYTES));
-  CUDA_TRY(cudaFuncSetAttribute(stem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, STEM_SMEM_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM_BYTES));
   CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&g_ctx.watchdog_host), sizeof(int), cudaHostAllocMapped));
   *g_ctx.watchdog_host = 0;
   CUDA_TRY(cudaHostGetDevicePointer(reinterpret_cast<void**>(&g_ctx.watchdog_dev), g_ctx.watchdog_host, 0));
@@ -304,7 +304,9 @@ int plan_stage(const av1p_model* m, const ActLayout& L, uint8_t* act_base, av1p_
     switch (op.type) {
       case AV1P_OP_STEM: {
         memset(&P.stem, 0, sizeof P.stem);
-        P.stem.w = reinterpret_cast<const float*>(at(op.w_off));
+        P.stem.w = reinterpret_cast<const __half*>(at(op.w_off));
+        P.stem.acc_scale = op.f0;
+        P.stem.err_flag = g_ctx.watchdog_dev;
         P.stem.b = reinterpret_cast<const float*>(at(op.bias_off));
         P.stem.out = buf(op.out);
         P.stem.out_lo = buf(op.out_lo);
@@ -429,9 +431,9 @@ int run_stage(av1p_stage* s, const StemInput& si, const int32_t* idx, const int3
         sp.idx = idx;
         sp.n_dev = n_dev;
         sp.n = n;
-        const int grid = std::min(ceil_div(n, STEM_NB), g_ctx.sms * 4);
+        const int grid = std::min(ceil_div(n, ST_BLOCKS), g_ctx.sms);
         ProfScope ps(PROF_STEM, st);
-        stem_kernel<<<grid, STEM_THREADS, STEM_SMEM_BYTES, st>>>(sp);
+        stem_tc_kernel<<<grid, ST_THREADS, ST_SMEM_BYTES, st>>>(sp);
         break;
       }
       case AV1P_OP_FC: {

@@ -8,12 +8,12 @@
 #include <stdint.h>
 
 #define AV1P_BLOB_MAGIC 0x50315641u   /* "AV1P" */
-#define AV1P_BLOB_VERSION 5u
+#define AV1P_BLOB_VERSION 6u
 #define AV1P_BLOB_MAX_NT 8
 #define AV1P_BLOB_MAX_KB 128
 
 enum Av1pOpType : int32_t {
-  AV1P_OP_STEM = 0,       // gather + /1023 + conv1/bn/relu/maxpool -> out buffer (1024 cols)
+  AV1P_OP_STEM = 0,       // gather + /1023 + conv1/bn/relu/maxpool -> out buffer (1024 cols); w = fp16 [2][128][64], f0 = acc_scale
   AV1P_OP_FC = 1,         // block-Toeplitz linear layer on tensor cores
   AV1P_OP_SAM = 2,        // spatial-attention scalar of `src0` (512 cols) -> row_scale
   AV1P_OP_FGVC_TAIL = 3,  // L2-normalise `src0` (512 cols) + cosine classifier -> logits[4]

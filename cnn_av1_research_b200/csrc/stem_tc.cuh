@@ -1,0 +1,295 @@
+// Stem on the tensor cores: block gather (straight from the planar 10-bit frame, or from a float
+// block tensor) -> /1023 -> conv1 7x7 s2 p3 (BN folded) -> ReLU -> maxpool 3x3 s2 p1 -> fp16 hi/lo
+// activation rows [block][4x4 positions][64 channels].
+//
+// Reference semantics: pesquisa_v5/005_rearrange_video_YUV_420_10bit_LOSSLESS.py:353-457 (tiling, zero
+// pad bottom/right, row-major block order), pesquisa_v6/v6_pipeline/data_hub.py:70-77 (float32(u16) /
+// 1023.0, true division) and models.py:105-108 (conv1 / bn1 / relu / maxpool).
+//
+// GEMM view, per tile of 4 blocks:   D[channel, (block, position)] = W[channel, tap] . patch[(block, position), tap]
+//   M operand : folded conv1 weights, 64 channels x 64 K (49 taps + zero pad), stacked twice to fill M = 128,
+//               fp16 hi and lo, resident in shared memory for the whole (persistent) kernel;
+//   N operand : im2col rows (4 blocks x 64 conv positions = 256) x 64 K, fp16 hi and lo, built by four
+//               producer warps from the pixel tile directly in the SWIZZLE_128B K-major layout;
+//   products  : W_hi.P_hi + W_hi.P_lo + W_lo.P_hi (split precision), fp32 accumulators in TMEM (256 cols x 2).
+// Because the channels are the accumulator rows (TMEM lanes), one epilogue thread owns a channel and sees all
+// 64 conv positions of a block in its columns: bias, ReLU and the 3x3/s2 max-pool run in registers, and a warp
+// stores 32 consecutive channels (64 contiguous bytes) per pooled position.
+#pragma once
+#include "ptx_sm100.cuh"
+
+namespace av1p {
+
+constexpr int ST_BLOCKS = 4;                     // blocks per tile
+constexpr int ST_N = ST_BLOCKS * 64;             // im2col rows per tile
+constexpr int ST_STAGES = 2;
+constexpr int ST_W_BYTES = 128 * 128;            // one weight plane (hi or lo): 128 rows x 128 B
+constexpr int ST_P_BYTES = ST_N * 128;           // one patch plane: 256 rows x 128 B
+constexpr int ST_STAGE_BYTES = 2 * ST_P_BYTES;   // hi + lo
+constexpr int ST_TILE_H = 22, ST_TILE_W = 24;    // 16x16 block + 3-pixel zero halo (width padded)
+constexpr int ST_PIX_BYTES = ST_BLOCKS * ST_TILE_H * ST_TILE_W * 4;
+constexpr int ST_PRODUCERS = 128;
+constexpr int ST_THREADS = ST_PRODUCERS + 32 + 128;   // producers, MMA warp, epilogue warps
+constexpr int ST_SMEM_BYTES = 1024 + 2 * ST_W_BYTES + ST_STAGES * ST_STAGE_BYTES + ST_PIX_BYTES + 256;
+
+struct StemInput {
+  // kind 0: planar YUV 4:2:0 10-bit LE frames resident in HBM.  Block id g -> frame g / blocks_per_frame,
+  //         grid row (g % bpf) / blocks_x, grid col (g % bpf) % blocks_x.
+  // kind 1: float32 blocks [n][16*16] (the tensor HierarchicalPipelineV6.predict receives).
+  int kind;
+  const uint16_t* frames;
+  long long frame_stride;   // elements between consecutive frames (Y + U + V)
+  int width, height, pitch; // luma geometry, pitch in elements
+  int blocks_x, blocks_per_frame;
+  const float* images;
+};
+
+struct StemParams {
+  StemInput in;
+  const int* idx;           // optional gather list: row r processes block id idx[r]
+  const int* n_dev;         // device-side row count (nullptr -> n)
+  int n;
+  const __half* w;          // [2][128][64] folded conv1 weights x 2^s: hi plane then lo plane, K = ky*7+kx (49..63 zero)
+  const float* b;           // [64] folded bias
+  float acc_scale;          // 2^-s
+  __half* out;              // [rows][1024]
+  __half* out_lo;           // split precision: fp16(x - fp16(x)), nullptr otherwise
+  int* err_flag;
+};
+
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+__global__ void __launch_bounds__(ST_THREADS, 1) stem_tc_kernel(const __grid_constant__ StemParams p) {
+  extern __shared__ uint8_t st_smem_raw[];
+  const uint32_t base = (smem_u32(st_smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = st_smem_raw + (base - smem_u32(st_smem_raw));
+  uint8_t* w_hi = smem;                                   // [128][128 B] swizzled
+  uint8_t* w_lo = smem + ST_W_BYTES;
+  uint8_t* stages = smem + 2 * ST_W_BYTES;                // [ST_STAGES][hi | lo]
+  float* pix = reinterpret_cast<float*>(stages + ST_STAGES * ST_STAGE_BYTES);   // [4][22][24]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(pix) + ST_PIX_BYTES);
+  uint64_t* empty_bar = full_bar + ST_STAGES;
+  uint64_t* acc_full = empty_bar + ST_STAGES;             // [2]
+  uint64_t* acc_empty = acc_full + 2;                     // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n = p.n_dev ? *p.n_dev : p.n;
+  const int tiles = (n + ST_BLOCKS - 1) / ST_BLOCKS;
+
+  // ---- one-time setup: weights into swizzled smem, zero halo, barriers, TMEM
+  for (int q = threadIdx.x; q < 2 * 128 * 8; q += ST_THREADS) {
+    const int plane = q >> 10, row = (q >> 3) & 127, c = q & 7;
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(p.w + (size_t(plane) * 128 + row) * 64 + c * 8));
+    *reinterpret_cast<uint4*>((plane ? w_lo : w_hi) + row * 128 + ((c ^ (row & 7)) << 4)) = v;
+  }
+  for (int i = threadIdx.x; i < ST_PIX_BYTES / 4; i += ST_THREADS) pix[i] = 0.f;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < ST_STAGES; ++s) {
+      mbar_init(&full_bar[s], ST_PRODUCERS);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 4) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  fence_proxy_async_smem();       // the weight tiles were written with generic stores, tcgen05.mma reads them
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // ------------------------------------------------------------ producers: gather + im2col
+    const int tid = threadIdx.x;                     // 0..127
+    const int c = tid & 7;                           // 16-byte K chunk this thread always writes
+    int tap_off[8];                                  // offset of tap k = 8c+j inside the pixel tile, -1 = zero pad
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = 8 * c + j;
+      tap_off[j] = k < 49 ? (k / 7) * ST_TILE_W + (k % 7) : -1;
+    }
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      // pixels: 4 blocks x 16 rows x 2 half-rows = 128 work items of 8 samples
+      {
+        const int b = tid >> 5, py = (tid >> 1) & 15, px0 = (tid & 1) * 8;
+        const int r = tile * ST_BLOCKS + b;
+        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (r < n) {
+          const int g = p.idx ? p.idx[r] : r;
+          if (p.in.kind == 0) {
+            const int f = g / p.in.blocks_per_frame;
+            const int gb = g - f * p.in.blocks_per_frame;
+            const int by = gb / p.in.blocks_x, bx = gb - by * p.in.blocks_x;
+            const int y = by * 16 + py, x0 = bx * 16 + px0;
+            if (y < p.in.height) {
+              const uint16_t* src = p.in.frames + size_t(f) * p.in.frame_stride + size_t(y) * p.in.pitch + x0;
+              if (x0 + 7 < p.in.width && ((reinterpret_cast<uintptr_t>(src) & 15u) == 0)) {
+                const uint4 q = __ldg(reinterpret_cast<const uint4*>(src));
+                const uint32_t u[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  v[2 * j] = float(u[j] & 0xFFFFu);
+                  v[2 * j + 1] = float(u[j] >> 16);
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                  if (x0 + j < p.in.width) v[j] = float(__ldg(src + j));
+              }
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = __fdiv_rn(v[j], 1023.0f);
+            }
+          } else {
+            const float4* src = reinterpret_cast<const float4*>(p.in.images + size_t(g) * 256 + py * 16 + px0);
+            const float4 a = __ldg(src), bb = __ldg(src + 1);
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+            v[4] = bb.x; v[5] = bb.y; v[6] = bb.z; v[7] = bb.w;
+          }
+        }
+        float* t = pix + (b * ST_TILE_H + py + 3) * ST_TILE_W + px0 + 3;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t[j] = v[j];
+      }
+      named_bar_sync(1, ST_PRODUCERS);
+      mbar_wait(&empty_bar[stage], phase ^ 1u, p.err_flag, 500 + stage);
+      uint8_t* s_hi = stages + stage * ST_STAGE_BYTES;
+      uint8_t* s_lo = s_hi + ST_P_BYTES;
+#pragma unroll 4
+      for (int i = 0; i < (ST_N * 8) / ST_PRODUCERS; ++i) {
+        const int row = (tid >> 3) + 16 * i;          // im2col row = block * 64 + conv position
+        const int b = row >> 6, pos = row & 63;
+        const float* t = pix + (b * ST_TILE_H + 2 * (pos >> 3)) * ST_TILE_W + 2 * (pos & 7);
+        __align__(16) __half2 hi[4], lo[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float x0 = tap_off[2 * j] >= 0 ? t[tap_off[2 * j]] : 0.f;
+          const float x1 = tap_off[2 * j + 1] >= 0 ? t[tap_off[2 * j + 1]] : 0.f;
+          hi[j] = __floats2half2_rn(x0, x1);
+          const float2 hf = __half22float2(hi[j]);
+          lo[j] = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+        }
+        const int dst = row * 128 + ((c ^ (row & 7)) << 4);
+        *reinterpret_cast<uint4*>(s_hi + dst) = *reinterpret_cast<const uint4*>(hi);
+        *reinterpret_cast<uint4*>(s_lo + dst) = *reinterpret_cast<const uint4*>(lo);
+      }
+      fence_proxy_async_smem();                       // generic-proxy stores -> visible to tcgen05.mma
+      mbar_arrive(&full_bar[stage]);
+      named_bar_sync(1, ST_PRODUCERS);                // nobody still reads the pixel tile
+      if (++stage == ST_STAGES) {
+        stage = 0;
+        phase ^= 1u;
+      }
+    }
+  } else if (warp == 4) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      const uint32_t idesc = umma_idesc_f16(ST_N);
+      const uint32_t a_hi = smem_u32(w_hi), a_lo = smem_u32(w_lo);
+      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        mbar_wait(&acc_empty[acc], acc_phase ^ 1u, p.err_flag, 600 + acc);
+        mbar_wait(&full_bar[stage], phase, p.err_flag, 700 + stage);
+        tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + uint32_t(acc * ST_N);
+        const uint32_t b_hi = smem_u32(stages + stage * ST_STAGE_BYTES), b_lo = b_hi + ST_P_BYTES;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_f16_ss(d_tmem, umma_desc_sw128(a_hi + k * 32), umma_desc_sw128(b_hi + k * 32), idesc, k > 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_f16_ss(d_tmem, umma_desc_sw128(a_hi + k * 32), umma_desc_sw128(b_lo + k * 32), idesc, 1u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_f16_ss(d_tmem, umma_desc_sw128(a_lo + k * 32), umma_desc_sw128(b_hi + k * 32), idesc, 1u);
+        umma_commit(&empty_bar[stage]);
+        umma_commit(&acc_full[acc]);
+        if (++stage == ST_STAGES) {
+          stage = 0;
+          phase ^= 1u;
+        }
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1u;
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue: bias, ReLU, max-pool, hi/lo stores
+    const int quad = warp & 3;
+    const int ch = (quad & 1) * 32 + lane;            // accumulator row -> channel (rows 64..127 repeat 0..63)
+    const int blk0 = (quad >> 1) * 2;                 // rows 0..63 take blocks 0,1 of the tile, rows 64..127 blocks 2,3
+    const float bias = p.b[ch];
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      mbar_wait(&acc_full[acc], acc_phase, p.err_flag, 800 + acc);
+      tc_fence_after_sync();
+      const uint32_t t_addr = tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(acc * ST_N);
+#pragma unroll 1
+      for (int bi = 0; bi < 2; ++bi) {
+        const int blk = blk0 + bi;
+        const int r = tile * ST_BLOCKS + blk;
+        uint32_t v0[32], v1[32];
+        tmem_ld_32x32(t_addr + uint32_t(blk * 64), v0);        // conv rows 0..3
+        tmem_ld_32x32(t_addr + uint32_t(blk * 64 + 32), v1);   // conv rows 4..7
+        tmem_ld_wait();
+        if (r >= n) continue;
+        float cv[64];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          cv[i] = fmaxf(fmaf(__uint_as_float(v0[i]), p.acc_scale, bias), 0.f);
+          cv[32 + i] = fmaxf(fmaf(__uint_as_float(v1[i]), p.acc_scale, bias), 0.f);
+        }
+        __half* o = p.out + size_t(r) * 1024 + ch;
+        __half* ol = p.out_lo ? p.out_lo + size_t(r) * 1024 + ch : nullptr;
+#pragma unroll
+        for (int qy = 0; qy < 4; ++qy) {
+#pragma unroll
+          for (int qx = 0; qx < 4; ++qx) {
+            float m = 0.f;                             // post-ReLU inputs: 0 is the identity of max
+#pragma unroll
+            for (int dy = -1; dy <= 1; ++dy) {
+#pragma unroll
+              for (int dx = -1; dx <= 1; ++dx) {
+                const int y = 2 * qy + dy, x = 2 * qx + dx;
+                if (y >= 0 && y < 8 && x >= 0 && x < 8) m = fmaxf(m, cv[y * 8 + x]);
+              }
+            }
+            const __half h = __float2half_rn(m);
+            o[(qy * 4 + qx) * 64] = h;
+            if (ol) ol[(qy * 4 + qx) * 64] = __float2half_rn(m - __half2float(h));
+          }
+        }
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1u;
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace av1p

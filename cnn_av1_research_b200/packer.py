@@ -26,7 +26,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import numpy as np
 
 BLOB_MAGIC = 0x50315641
-BLOB_VERSION = 5
+BLOB_VERSION = 6
 MAX_NT = 8
 MAX_KB = 128
 TILE_K = 64
@@ -198,11 +198,20 @@ def backbone_ops(sd, precision: str = "fp16x3", prefix: str = "backbone.") -> Li
     """Op program for ImprovedBackbone.forward (models.py:104-121).  Result: x4' in C1, SAM scalar in row_scale."""
     p = prefix
     ops: List[_Op] = []
-    # --- stem: conv1 + bn1 (+ relu + maxpool in the kernel).  fp32 weights, taps padded 49 -> 52.
+    # --- stem: conv1 + bn1 (+ relu + maxpool in the kernel's epilogue).  The 64 x 49 folded weights are the
+    #     M operand of the stem GEMM: K padded to 64, rows stacked twice (M = 128), fp16 hi / lo planes.
     w, b = fold_bn(_np64(sd[p + "conv1.weight"]), None, sd, p + "bn1")
-    wst = np.zeros((64, 52), dtype=np.float32)
-    wst[:, :49] = w.reshape(64, 49).astype(np.float32)
-    ops.append(_Op(OP_STEM, out=_hi("B0"), out_lo=_lo("B0", precision), w=wst, bias=b.astype(np.float32), name="stem"))
+    w = w.reshape(64, 49)
+    scale = 2.0 ** int(np.clip(np.floor(np.log2(8192.0 / np.abs(w).max())), 0, 16))
+    wk = np.zeros((128, 64), dtype=np.float64)
+    wk[:64, :49] = w * scale
+    wk[64:] = wk[:64]
+    w_hi = wk.astype(np.float16)
+    w_lo = (wk - w_hi.astype(np.float64)).astype(np.float16)
+    if precision != "fp16x3":
+        w_lo = np.zeros_like(w_lo)
+    ops.append(_Op(OP_STEM, out=_hi("B0"), out_lo=_lo("B0", precision), w=np.stack([w_hi, w_lo]), bias=b.astype(np.float32),
+                   f0=1.0 / scale, name="stem"))
 
     def conv_bn(unit: str, conv: str, bn: str, grid: int, stride: int):
         wf, bf = fold_bn(_np64(sd[f"{unit}.{conv}.weight"]), None, sd, f"{unit}.{bn}")
