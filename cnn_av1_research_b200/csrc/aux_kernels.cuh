@@ -132,8 +132,10 @@ __global__ void __launch_bounds__(256) se_kernel(const __half* __restrict__ x, c
       for (int k = 0; k < 8; ++k) mean[k] += __shfl_xor_sync(0xffffffffu, mean[k], o);
 #pragma unroll
     for (int k = 0; k < 8; ++k) mean[k] *= (1.0f / NPOS);
-    // hidden = relu(W1 . mean): one leader lane per channel group contributes, then a warp reduction
-    float hid[H];
+    // hidden = relu(W1 . mean): one leader lane per channel group contributes a partial for every hidden
+    // unit; the H partial vectors are summed with a reduce-scatter butterfly (H + H/2 + ... shuffles instead
+    // of 5 per unit) and broadcast back.
+    float part[H];
 #pragma unroll
     for (int j = 0; j < H; ++j) {
       float pj = 0.f;
@@ -143,7 +145,55 @@ __global__ void __launch_bounds__(256) se_kernel(const __half* __restrict__ x, c
         pj = mean[0] * a.x + mean[1] * a.y + mean[2] * a.z + mean[3] * a.w + mean[4] * b.x + mean[5] * b.y + mean[6] * b.z +
              mean[7] * b.w;
       }
-      hid[j] = fmaxf(warp_sum(pj), 0.f);
+      part[j] = pj;
+    }
+    float hid[H];
+    {
+      // after the step with offset o, lane keeps the units whose index bit (log2 of the step count) matches its bit
+      int width = H;
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) {
+        if (width > 1) {
+          const int half_w = width / 2;
+          const bool upper = (lane & o) != 0;
+#pragma unroll
+          for (int j = 0; j < half_w; ++j) {
+            const float keep = upper ? part[j + half_w] : part[j];
+            const float send = upper ? part[j] : part[j + half_w];
+            part[j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+          }
+          width = half_w;
+        } else {
+          part[0] += __shfl_xor_sync(0xffffffffu, part[0], o);
+        }
+      }
+      // lane now holds the total of unit u(lane) = sum over the first log2(H) steps of bit(lane, o) * (H >> step)
+      int unit = 0, w2 = H;
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) {
+        if (w2 > 1) {
+          w2 /= 2;
+          if (lane & o) unit += w2;
+        }
+      }
+      const float mine = fmaxf(part[0], 0.f);
+      // unit j lives in the lane whose selected bits spell j (other bits zero)
+#pragma unroll
+      for (int j = 0; j < H; ++j) {
+        int src_lane = 0, w3 = H, jj = j;
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) {
+          if (w3 > 1) {
+            w3 /= 2;
+            if (jj >= w3) {
+              src_lane |= o;
+              jj -= w3;
+            }
+          }
+        }
+        hid[j] = __shfl_sync(0xffffffffu, mine, src_lane);
+      }
+      (void)unit;
     }
     float sc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll

@@ -118,50 +118,62 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_tc_kernel(const __grid_con
       const int k = 8 * c + j;
       tap_off[j] = k < 49 ? (k / 7) * ST_TILE_W + (k % 7) : -1;
     }
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-      // pixels: 4 blocks x 16 rows x 2 half-rows = 128 work items of 8 samples
-      {
-        const int b = tid >> 5, py = (tid >> 1) & 15, px0 = (tid & 1) * 8;
-        const int r = tile * ST_BLOCKS + b;
-        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        if (r < n) {
-          const int g = p.idx ? p.idx[r] : r;
-          if (p.in.kind == 0) {
-            const int f = g / p.in.blocks_per_frame;
-            const int gb = g - f * p.in.blocks_per_frame;
-            const int by = gb / p.in.blocks_x, bx = gb - by * p.in.blocks_x;
-            const int y = by * 16 + py, x0 = bx * 16 + px0;
-            if (y < p.in.height) {
-              const uint16_t* src = p.in.frames + size_t(f) * p.in.frame_stride + size_t(y) * p.in.pitch + x0;
-              if (x0 + 7 < p.in.width && ((reinterpret_cast<uintptr_t>(src) & 15u) == 0)) {
-                const uint4 q = __ldg(reinterpret_cast<const uint4*>(src));
-                const uint32_t u[4] = {q.x, q.y, q.z, q.w};
+    // pixel gather: 4 blocks x 16 rows x 2 half-rows = 128 work items of 8 samples, one per producer thread.
+    // The loads of tile t+1 are issued before the im2col of tile t is built, so their latency is hidden.
+    const int pb = tid >> 5, ppy = (tid >> 1) & 15, ppx0 = (tid & 1) * 8;
+    // raw[] holds either four packed pairs of 16-bit samples (mode 1, converted when the tile is consumed, so
+    // that nothing waits on the load here) or eight ready float bit patterns (mode 0).
+    auto gather = [&](int tile, uint32_t (&raw)[8], int& mode) {
+      mode = 0;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  v[2 * j] = float(u[j] & 0xFFFFu);
-                  v[2 * j + 1] = float(u[j] >> 16);
-                }
-              } else {
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                  if (x0 + j < p.in.width) v[j] = float(__ldg(src + j));
-              }
-#pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] = __fdiv_rn(v[j], 1023.0f);
-            }
+      for (int j = 0; j < 8; ++j) raw[j] = 0u;
+      const int r = tile * ST_BLOCKS + pb;
+      if (tile >= tiles || r >= n) return;
+      const int g = p.idx ? __ldg(p.idx + r) : r;
+      if (p.in.kind == 0) {
+        const int f = g / p.in.blocks_per_frame;
+        const int gb = g - f * p.in.blocks_per_frame;
+        const int by = gb / p.in.blocks_x, bx = gb - by * p.in.blocks_x;
+        const int y = by * 16 + ppy, x0 = bx * 16 + ppx0;
+        if (y < p.in.height) {
+          const uint16_t* src = p.in.frames + size_t(f) * p.in.frame_stride + size_t(y) * p.in.pitch + x0;
+          if (x0 + 7 < p.in.width && ((reinterpret_cast<uintptr_t>(src) & 15u) == 0)) {
+            const uint4 q = __ldg(reinterpret_cast<const uint4*>(src));
+            raw[0] = q.x; raw[1] = q.y; raw[2] = q.z; raw[3] = q.w;
+            mode = 1;
           } else {
-            const float4* src = reinterpret_cast<const float4*>(p.in.images + size_t(g) * 256 + py * 16 + px0);
-            const float4 a = __ldg(src), bb = __ldg(src + 1);
-            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
-            v[4] = bb.x; v[5] = bb.y; v[6] = bb.z; v[7] = bb.w;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (x0 + j < p.in.width) raw[j] = __float_as_uint(__fdiv_rn(float(__ldg(src + j)), 1023.0f));
           }
         }
-        float* t = pix + (b * ST_TILE_H + py + 3) * ST_TILE_W + px0 + 3;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) t[j] = v[j];
+      } else {
+        const uint4* src = reinterpret_cast<const uint4*>(p.in.images + size_t(g) * 256 + ppy * 16 + ppx0);
+        const uint4 a = __ldg(src), bb = __ldg(src + 1);
+        raw[0] = a.x; raw[1] = a.y; raw[2] = a.z; raw[3] = a.w;
+        raw[4] = bb.x; raw[5] = bb.y; raw[6] = bb.z; raw[7] = bb.w;
       }
+    };
+    int stage = 0;
+    uint32_t phase = 0;
+    uint32_t nxt[8];
+    int nxt_mode;
+    gather(blockIdx.x, nxt, nxt_mode);
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      {
+        float* t = pix + (pb * ST_TILE_H + ppy + 3) * ST_TILE_W + ppx0 + 3;
+        if (nxt_mode) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            t[2 * j] = __fdiv_rn(float(nxt[j] & 0xFFFFu), 1023.0f);
+            t[2 * j + 1] = __fdiv_rn(float(nxt[j] >> 16), 1023.0f);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) t[j] = __uint_as_float(nxt[j]);
+        }
+      }
+      gather(tile + gridDim.x, nxt, nxt_mode);        // in flight while this tile's im2col is built
       named_bar_sync(1, ST_PRODUCERS);
       mbar_wait(&empty_bar[stage], phase ^ 1u, p.err_flag, 500 + stage);
       uint8_t* s_hi = stages + stage * ST_STAGE_BYTES;
