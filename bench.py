@@ -138,6 +138,7 @@ def main():
     ap.add_argument("--frames", type=int, default=64, help="4K frames per GPU per step")
     ap.add_argument("--precision", default="fp16x3", choices=["fp16x3", "fp16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--chunk", type=int, default=SUB, help="frames per cascade launch")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -166,8 +167,8 @@ def main():
     from cnn_av1_research_b200.testing import build_pipeline, frames_tensor
 
     F = args.frames
-    assert F % SUB == 0 or F < SUB, "--frames must be a multiple of 8 (or smaller than 8)"
-    sub = min(SUB, F)
+    assert F % min(args.chunk, F) == 0, "--frames must be a multiple of --chunk"
+    sub = min(args.chunk, F)
     fw = synth.frame_words(W4K, H4K)
     # synthetic sequence: 8 distinct frames generated on the host, tiled to F frames (content is irrelevant to the cost;
     # the routing mix of the calibrated weights is what matters).  Each rank gets its own seed.

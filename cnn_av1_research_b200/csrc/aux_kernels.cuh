@@ -89,11 +89,17 @@ __global__ void __launch_bounds__(256) se_kernel(const __half* __restrict__ x, c
   constexpr int GROUPS = C / 8;           // channel groups of 8
   constexpr int CPL = L / 256;            // 16-byte chunks per lane
   static_assert(L % 256 == 0 && GROUPS <= 32, "unsupported SE shape");
-  extern __shared__ __align__(16) float se_w[];   // [H][C] W1, then [H][C] W2^T
-  for (int i = threadIdx.x; i < 2 * H * C; i += blockDim.x) se_w[i] = w[i];
+  // smem copy of [W1 ; W2^T], each row permuted to [half][group][4] so that the lanes of a warp (one channel
+  // group each) read consecutive 16-byte words: channel g*8 + h*4 + k  ->  h*(C/2) + g*4 + k
+  extern __shared__ __align__(16) float se_w[];
+  for (int i = threadIdx.x; i < 2 * H * C; i += blockDim.x) {
+    const int row = i / C, ch = i - row * C;
+    se_w[row * C + ((ch >> 2) & 1) * (C / 2) + (ch >> 3) * 4 + (ch & 3)] = w[i];
+  }
   __syncthreads();
   const float* w1 = se_w;
   const float* w2t = se_w + H * C;
+  const int wg = (threadIdx.x & 31) % GROUPS * 4;      // this lane's word offset inside a half row
   const int rows = n_dev ? *n_dev : n;
   const int lane = threadIdx.x & 31;
   const int ch0 = (lane % GROUPS) * 8;
@@ -140,8 +146,8 @@ __global__ void __launch_bounds__(256) se_kernel(const __half* __restrict__ x, c
     for (int j = 0; j < H; ++j) {
       float pj = 0.f;
       if (lane < GROUPS) {
-        const float4 a = *reinterpret_cast<const float4*>(w1 + j * C + ch0);
-        const float4 b = *reinterpret_cast<const float4*>(w1 + j * C + ch0 + 4);
+        const float4 a = *reinterpret_cast<const float4*>(w1 + j * C + wg);
+        const float4 b = *reinterpret_cast<const float4*>(w1 + j * C + C / 2 + wg);
         pj = mean[0] * a.x + mean[1] * a.y + mean[2] * a.z + mean[3] * a.w + mean[4] * b.x + mean[5] * b.y + mean[6] * b.z +
              mean[7] * b.w;
       }
@@ -198,8 +204,8 @@ __global__ void __launch_bounds__(256) se_kernel(const __half* __restrict__ x, c
     float sc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int j = 0; j < H; ++j) {
-      const float4 a = *reinterpret_cast<const float4*>(w2t + j * C + ch0);
-      const float4 b = *reinterpret_cast<const float4*>(w2t + j * C + ch0 + 4);
+      const float4 a = *reinterpret_cast<const float4*>(w2t + j * C + wg);
+      const float4 b = *reinterpret_cast<const float4*>(w2t + j * C + C / 2 + wg);
       sc[0] = fmaf(a.x, hid[j], sc[0]); sc[1] = fmaf(a.y, hid[j], sc[1]);
       sc[2] = fmaf(a.z, hid[j], sc[2]); sc[3] = fmaf(a.w, hid[j], sc[3]);
       sc[4] = fmaf(b.x, hid[j], sc[4]); sc[5] = fmaf(b.y, hid[j], sc[5]);

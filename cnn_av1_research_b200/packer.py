@@ -118,8 +118,8 @@ class _Op:
     name: str = ""
 
 
-def make_fc_op(name: str, dense: Sequence[np.ndarray], srcs: Sequence[str], out: Optional[str], bias: Optional[np.ndarray],
-               epi: int, block_n: int, precision: str, aux: Optional[str] = None, use_row_scale: bool = False,
+def _make_fc_op_n(name: str, dense: Sequence[np.ndarray], srcs: Sequence[str], out: Optional[str], bias: Optional[np.ndarray],
+                  epi: int, block_n: int, precision: str, aux: Optional[str] = None, use_row_scale: bool = False,
                tail_w: Optional[np.ndarray] = None, tail_b: Optional[np.ndarray] = None) -> _Op:
     """Tile dense matrices D_s [N, K_s] (one per activation source) into the block-sparse schedule.
 
@@ -188,6 +188,31 @@ def make_fc_op(name: str, dense: Sequence[np.ndarray], srcs: Sequence[str], out:
         tw[:, :n] = tail_w.astype(np.float32)
         op.tail_w, op.tail_b, op.tail_n = tw, tail_b.astype(np.float32), tail_w.shape[0]
     return op
+
+
+def make_fc_op(name: str, dense: Sequence[np.ndarray], srcs: Sequence[str], out: Optional[str], bias: Optional[np.ndarray],
+               epi: int, block_n: int, precision: str, **kw) -> _Op:
+    """Build the FC op with the tile width (block_n or block_n / 2) that schedules the least tensor work.
+
+    Narrower N tiles see fewer input positions under their 3x3 windows, so more of the block-Toeplitz matrix
+    falls into skipped (all-zero) tiles: e.g. layer1's 3x3 convs need 40 K blocks x 256 columns with N = 256 but
+    60 x 128 with N = 128 (-25 % MMA work at the same operand traffic).  Cost model: entries x (block_n + 64),
+    i.e. MMA time plus a term for the activation tile every entry reloads.
+    """
+    best = None
+    for bn in (block_n, block_n // 2):
+        n = dense[0].shape[0]
+        if bn < 64 or bn % 32 or -(-n // bn) > MAX_NT or epi == EPI_HEAD and bn < n:
+            continue
+        try:
+            op = _make_fc_op_n(name, dense, srcs, out, bias, epi, bn, precision, **kw)
+        except AssertionError:
+            continue
+        cost = len(op.kb_src) * (bn + 64)
+        if best is None or cost < best[0] * 0.97:
+            best = (cost, op)
+    assert best is not None, name
+    return best[1]
 
 
 def _block_n(n: int) -> int:

@@ -53,8 +53,10 @@ def test_schedule_skips_zero_blocks_and_fits_limits():
         ops = packer.backbone_ops(sd, precision) + packer.head_ops("stage1", sd, precision)
         fc = [o for o in ops if o.type == packer.OP_FC]
         by_name = {o.name: o for o in fc}
-        # layer1 3x3 conv on a 4x4 grid: output row y sees input rows y-1..y+1 -> 8+12+12+8 live K blocks of 16*4
-        assert len(by_name["backbone.layer1.0.conv1"].kb_src) == 40 * mult
+        # layer1 3x3 conv on a 4x4 grid, N tiles of 2 horizontally adjacent positions (block_n 128): a tile sees
+        # 3 input columns x (2 or 3) input rows -> 2*(6+9+9+6) = 60 live K blocks of the 8*16 = 128 possible
+        assert by_name["backbone.layer1.0.conv1"].block_n == 128
+        assert len(by_name["backbone.layer1.0.conv1"].kb_src) == 60 * mult
         # layer3 3x3 convs at 1x1 spatial keep only the centre tap: 256 -> 256 is 4 K blocks
         assert len(by_name["backbone.layer3.1.conv1"].kb_src) == 4 * mult
         # layer4.0 conv2 (512->512, 8 blocks per tile) + downsample (256 wide, 4 blocks per tile), two N tiles
