@@ -102,7 +102,6 @@ __global__ void __launch_bounds__(256) se_kernel(const __half* __restrict__ x, c
   const int wg = (threadIdx.x & 31) % GROUPS * 4;      // this lane's word offset inside a half row
   const int rows = n_dev ? *n_dev : n;
   const int lane = threadIdx.x & 31;
-  const int ch0 = (lane % GROUPS) * 8;
   const int warps_per_grid = (gridDim.x * blockDim.x) >> 5;
   for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < rows; r += warps_per_grid) {
     float v[CPL][8];

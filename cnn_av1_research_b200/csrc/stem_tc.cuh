@@ -28,7 +28,7 @@ constexpr int ST_P_BYTES = ST_N * 128;           // one patch plane: 256 rows x 
 constexpr int ST_STAGE_BYTES = 2 * ST_P_BYTES;   // hi + lo
 constexpr int ST_TILE_H = 22, ST_TILE_W = 24;    // 16x16 block + 3-pixel zero halo (width padded)
 constexpr int ST_PIX_BYTES = ST_BLOCKS * ST_TILE_H * ST_TILE_W * 4;
-constexpr int ST_PRODUCERS = 128;
+constexpr int ST_PRODUCERS = 256;                // 8 warps (2 per scheduler) so the im2col LDS latency overlaps
 constexpr int ST_THREADS = ST_PRODUCERS + 32 + 128;   // producers, MMA warp, epilogue warps
 constexpr int ST_SMEM_BYTES = 1024 + 2 * ST_W_BYTES + ST_STAGES * ST_STAGE_BYTES + ST_PIX_BYTES + 256;
 
@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_tc_kernel(const __grid_con
     }
     fence_mbar_init();
   }
-  if (warp == 4) {
+  if (warp == ST_PRODUCERS / 32) {
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
@@ -108,9 +108,9 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_tc_kernel(const __grid_con
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 4) {
+  if (warp < ST_PRODUCERS / 32) {
     // ------------------------------------------------------------ producers: gather + im2col
-    const int tid = threadIdx.x;                     // 0..127
+    const int tid = threadIdx.x;                     // 0..ST_PRODUCERS-1
     const int c = tid & 7;                           // 16-byte K chunk this thread always writes
     int tap_off[8];                                  // offset of tap k = 8c+j inside the pixel tile, -1 = zero pad
 #pragma unroll
@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_tc_kernel(const __grid_con
       const int k = 8 * c + j;
       tap_off[j] = k < 49 ? (k / 7) * ST_TILE_W + (k % 7) : -1;
     }
-    // pixel gather: 4 blocks x 16 rows x 2 half-rows = 128 work items of 8 samples, one per producer thread.
+    // pixel gather: 4 blocks x 16 rows x 2 half-rows = 128 work items of 8 samples (producer threads 0..127).
     // The loads of tile t+1 are issued before the im2col of tile t is built, so their latency is hidden.
     const int pb = tid >> 5, ppy = (tid >> 1) & 15, ppx0 = (tid & 1) * 8;
     // raw[] holds either four packed pairs of 16-bit samples (mode 1, converted when the tile is consumed, so
@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_tc_kernel(const __grid_con
 #pragma unroll
       for (int j = 0; j < 8; ++j) raw[j] = 0u;
       const int r = tile * ST_BLOCKS + pb;
-      if (tile >= tiles || r >= n) return;
+      if (tid >= 128 || tile >= tiles || r >= n) return;
       const int g = p.idx ? __ldg(p.idx + r) : r;
       if (p.in.kind == 0) {
         const int f = g / p.in.blocks_per_frame;
@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_tc_kernel(const __grid_con
     int nxt_mode;
     gather(blockIdx.x, nxt, nxt_mode);
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-      {
+      if (tid < 128) {
         float* t = pix + (pb * ST_TILE_H + ppy + 3) * ST_TILE_W + ppx0 + 3;
         if (nxt_mode) {
 #pragma unroll
@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_tc_kernel(const __grid_con
       uint8_t* s_lo = s_hi + ST_P_BYTES;
 #pragma unroll 4
       for (int i = 0; i < (ST_N * 8) / ST_PRODUCERS; ++i) {
-        const int row = (tid >> 3) + 16 * i;          // im2col row = block * 64 + conv position
+        const int row = (tid >> 3) + (ST_PRODUCERS / 8) * i;   // im2col row = block * 64 + conv position
         const int b = row >> 6, pos = row & 63;
         const float* t = pix + (b * ST_TILE_H + 2 * (pos >> 3)) * ST_TILE_W + 2 * (pos & 7);
         __align__(16) __half2 hi[4], lo[4];
@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_tc_kernel(const __grid_con
         phase ^= 1u;
       }
     }
-  } else if (warp == 4) {
+  } else if (warp == ST_PRODUCERS / 32) {
     // ------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       int stage = 0, acc = 0;
@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_tc_kernel(const __grid_con
 
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == ST_PRODUCERS / 32) {
     tc_fence_after_sync();
     tmem_dealloc(tmem_base, 512);
   }
