@@ -35,6 +35,12 @@ class FcDesc(C.Structure):
                 ("tail_b_dev", C.c_void_p), ("logits_dev", C.c_void_p), ("tail_n", C.c_int32)]
 
 
+class ConvResDesc(C.Structure):
+    _fields_ = [("x_dev", C.c_void_p), ("x_lo_dev", C.c_void_p), ("rows", C.c_int32), ("n_dev", C.c_void_p), ("w_dev", C.c_void_p),
+                ("split", C.c_int32), ("epi", C.c_int32), ("bias_dev", C.c_void_p), ("acc_scale", C.c_float),
+                ("aux_dev", C.c_void_p), ("aux_lo_dev", C.c_void_p), ("out_dev", C.c_void_p), ("out_lo_dev", C.c_void_p)]
+
+
 # name -> (restype, argtypes); kept in one table so tests can check the export list against av1p.h
 SIGNATURES = {
     "av1p_last_error": (C.c_char_p, []),
@@ -64,6 +70,7 @@ SIGNATURES = {
     "av1p_finalize_labels": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
                                        C.c_void_p, C.c_void_p]),
     "av1p_fc_forward": (C.c_int, [C.POINTER(FcDesc), C.c_void_p]),
+    "av1p_conv_res_forward": (C.c_int, [C.POINTER(ConvResDesc), C.c_void_p]),
     "av1p_profile_begin": (C.c_int, []),
     "av1p_profile_end": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
     "av1p_upload_luma": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]),

@@ -18,6 +18,7 @@
 #include "aux_kernels.cuh"
 #include "blob_format.h"
 #include "fc_tcgen05.cuh"
+#include "conv_res_tcgen05.cuh"
 #include "stem_tc.cuh"
 
 using namespace av1p;
@@ -74,6 +75,7 @@ int ensure_ctx() {
   if (!fn || qres != cudaDriverEntryPointSuccess) return fail(AV1P_ECUDA, "cuTensorMapEncodeTiled not available");
   g_ctx.encode = reinterpret_cast<EncodeTiledFn>(fn);
   CUDA_TRY(cudaFuncSetAttribute(fc_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FC_SMEM_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(conv_res_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CR_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM_BYTES));
   CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&g_ctx.watchdog_host), sizeof(int), cudaHostAllocMapped));
   *g_ctx.watchdog_host = 0;
@@ -109,7 +111,7 @@ extern "C" int av1p_debug_watchdog(void) { return g_ctx.watchdog_host ? *g_ctx.w
 // Optional CUDA-event bracket around every kernel launch (bench.py's roofline leg).  Events are
 // recorded on the launching stream; nothing synchronises until av1p_profile_end.
 namespace {
-enum ProfClass { PROF_STEM = 0, PROF_FC = 1, PROF_SAM = 2, PROF_FGVC = 3, PROF_ROUTE = 4, PROF_FINALIZE = 5, PROF_SE = 6, PROF_CLASSES = 7 };
+enum ProfClass { PROF_STEM = 0, PROF_FC = 1, PROF_SAM = 2, PROF_FGVC = 3, PROF_ROUTE = 4, PROF_FINALIZE = 5, PROF_SE = 6, PROF_CONV = 7, PROF_CLASSES = 8 };
 struct ProfRec { int cls; cudaEvent_t a, b; };
 struct Profiler {
   bool on = false;
@@ -242,6 +244,7 @@ namespace {
 struct PlannedOp {
   int type = 0;
   FcParams fc;          // AV1P_OP_FC
+  ConvResParams cr;     // AV1P_OP_CONV_RES
   StemParams stem;      // AV1P_OP_STEM
   const __half* src = nullptr;   // SAM / FGVC
   const __half* src_lo = nullptr;
@@ -360,6 +363,31 @@ int plan_stage(const av1p_model* m, const ActLayout& L, uint8_t* act_base, av1p_
         }
         break;
       }
+      case AV1P_OP_CONV_RES: {
+        ConvResParams& f = P.cr;
+        memset(&f, 0, sizeof f);
+        const bool split = op.pair_mode != 0;
+        if (op.src[0] < 0 || op.out < 0 || L.cols[op.src[0]] != 1024 || L.cols[op.out] != 1024 || (split && (op.src[1] < 0 || op.out_lo < 0)) ||
+            !op.w_off || !op.bias_off || op.w_off + uint64_t(split ? 2 : 1) * CR_W_PLANE_BYTES > m->hdr.total_bytes)
+          return fail(AV1P_EINVAL, "malformed resident-conv op");
+        if (int rc = make_map_2d(&f.a_map[0], buf(op.src[0]), 1024, L.cap, 1024, FC_TILE_M)) return rc;
+        if (int rc = make_map_2d(&f.a_map[1], buf(split ? op.src[1] : op.src[0]), 1024, L.cap, 1024, FC_TILE_M)) return rc;
+        if (int rc = make_map_2d(&f.w_map, at(op.w_off), 64, uint64_t(split ? 2 : 1) * 9 * 64, 64, 64)) return rc;
+        f.split = split ? 1 : 0;
+        f.epi = op.epi;
+        f.bias = reinterpret_cast<const float*>(at(op.bias_off));
+        f.acc_scale = op.f0;
+        f.aux = buf(op.aux);
+        f.aux_lo = buf(op.aux_lo);
+        f.aux_ld = op.aux >= 0 ? int(L.cols[op.aux]) : 0;
+        f.out = buf(op.out);
+        f.out_lo = buf(op.out_lo);
+        f.out_ld = 1024;
+        f.err_flag = g_ctx.watchdog_dev;
+        if (op.epi != FC_EPI_RELU && op.epi != FC_EPI_ADD_RELU && op.epi != FC_EPI_LINEAR) return fail(AV1P_EINVAL, "resident-conv epilogue %d", op.epi);
+        if (op.epi == FC_EPI_ADD_RELU && (!f.aux || f.aux_ld != 1024)) return fail(AV1P_EINVAL, "resident-conv op needs a 1024-wide aux");
+        break;
+      }
       case AV1P_OP_SAM:
       case AV1P_OP_FGVC_TAIL: {
         P.src = buf(op.src[0]);
@@ -443,6 +471,14 @@ int run_stage(av1p_stage* s, const StemInput& si, const int32_t* idx, const int3
         const int grid = std::min(g_ctx.sms, ceil_div(n, FC_TILE_M) * P.fc.n_tiles);
         ProfScope ps(PROF_FC, st);
         fc_tcgen05_kernel<<<grid, FC_THREADS, FC_SMEM_BYTES, st>>>(P.fc);
+        break;
+      }
+      case AV1P_OP_CONV_RES: {
+        P.cr.n_rows_dev = n_dev;
+        P.cr.n_rows = n;
+        const int grid = std::min(g_ctx.sms, ceil_div(n, FC_TILE_M));
+        ProfScope ps(PROF_CONV, st);
+        conv_res_tcgen05_kernel<<<grid, CR_THREADS, CR_SMEM_BYTES, st>>>(P.cr);
         break;
       }
       case AV1P_OP_SAM: {
@@ -789,6 +825,36 @@ extern "C" int av1p_fc_forward(const av1p_fc_desc* d, void* stream) {
   }
   const int grid = std::min(g_ctx.sms, ceil_div(d->rows, FC_TILE_M) * d->n_tiles);
   fc_tcgen05_kernel<<<grid, FC_THREADS, FC_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(f);
+  CUDA_TRY(cudaGetLastError());
+  return AV1P_OK;
+}
+
+// ------------------------------------------------------------------------------ resident-conv test hook
+extern "C" int av1p_conv_res_forward(const av1p_conv_res_desc* d, void* stream) {
+  if (!d || !d->x_dev || !d->w_dev || !d->out_dev || !d->bias_dev || d->rows < 1) return fail(AV1P_EINVAL, "null argument");
+  if (d->split && (!d->x_lo_dev || !d->out_lo_dev)) return fail(AV1P_EINVAL, "split precision needs the lo planes");
+  if (d->epi < 0 || d->epi > 2 || (d->epi == 2 && !d->aux_dev)) return fail(AV1P_EINVAL, "bad epilogue");
+  if (int rc = ensure_ctx()) return rc;
+  ConvResParams f;
+  memset(&f, 0, sizeof f);
+  if (int rc = make_map_2d(&f.a_map[0], d->x_dev, 1024, d->rows, 1024, FC_TILE_M)) return rc;
+  if (int rc = make_map_2d(&f.a_map[1], d->split ? d->x_lo_dev : d->x_dev, 1024, d->rows, 1024, FC_TILE_M)) return rc;
+  if (int rc = make_map_2d(&f.w_map, d->w_dev, 64, uint64_t(d->split ? 2 : 1) * 9 * 64, 64, 64)) return rc;
+  f.n_rows_dev = d->n_dev;
+  f.n_rows = d->rows;
+  f.split = d->split ? 1 : 0;
+  f.epi = d->epi;
+  f.bias = d->bias_dev;
+  f.acc_scale = d->acc_scale;
+  f.aux = static_cast<const __half*>(d->aux_dev);
+  f.aux_lo = static_cast<const __half*>(d->aux_lo_dev);
+  f.aux_ld = 1024;
+  f.out = static_cast<__half*>(d->out_dev);
+  f.out_lo = static_cast<__half*>(d->out_lo_dev);
+  f.out_ld = 1024;
+  f.err_flag = g_ctx.watchdog_dev;
+  const int grid = std::min(g_ctx.sms, ceil_div(d->rows, FC_TILE_M));
+  conv_res_tcgen05_kernel<<<grid, CR_THREADS, CR_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(f);
   CUDA_TRY(cudaGetLastError());
   return AV1P_OK;
 }

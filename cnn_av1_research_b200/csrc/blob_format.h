@@ -8,7 +8,7 @@
 #include <stdint.h>
 
 #define AV1P_BLOB_MAGIC 0x50315641u   /* "AV1P" */
-#define AV1P_BLOB_VERSION 6u
+#define AV1P_BLOB_VERSION 7u
 #define AV1P_BLOB_MAX_NT 8
 #define AV1P_BLOB_MAX_KB 128
 
@@ -18,6 +18,9 @@ enum Av1pOpType : int32_t {
   AV1P_OP_SAM = 2,        // spatial-attention scalar of `src0` (512 cols) -> row_scale
   AV1P_OP_FGVC_TAIL = 3,  // L2-normalise `src0` (512 cols) + cosine classifier -> logits[4]
   AV1P_OP_SE = 4,         // squeeze-excite on CUDA cores: block_n = channels (64/128/256), n_tiles = positions
+  AV1P_OP_CONV_RES = 5,   // 3x3 s1 conv 64->64 on the 4x4 map with SMEM-resident weights (csrc/conv_res_tcgen05.cuh):
+                          // src = {x_hi, x_lo}, w = fp16 [planes][ky][kx = 2,1,0][64 co][64 ci], bias[1024], f0 = acc_scale,
+                          // pair_mode = 1 for hi/lo planes (three products)
 };
 
 #pragma pack(push, 1)

@@ -1,0 +1,239 @@
+// layer1 convolutions (3x3, stride 1, 64 -> 64 channels on the 4x4 map) with SMEM-resident weights.
+//
+// The generic block-Toeplitz FC kernel (fc_tcgen05.cuh) streams a weight tile next to every activation
+// tile; for layer1 that makes it L2->SM bandwidth bound (ncu: 9.7 TB/s of TMA fill, tensor pipe 40-48 %).
+// A 3x3 conv has only nine distinct [64 co x 64 ci] weight matrices, 72 KB in fp16 (144 KB as hi + lo
+// planes), so this kernel keeps them in shared memory for its whole life and streams activations only:
+//
+//   out[block, (oy,ox), co] = epi( sum_{(iy,ix) in 3x3 window of (oy,ox)} act[block, (iy,ix), :] . W[ky,kx][co, :] )
+//       ky = iy - oy + 1, kx = ix - ox + 1     (reference: torchvision BasicBlock conv3x3, models.py:110)
+//
+// Work decomposition per 128-block M tile: two halves (output rows {0,1}, then {2,3}); a half needs
+// three input rows = 12 activation tiles [128 x 64] per plane, each loaded once per half and multiplied
+// into every output position that sees it.  One accumulator = one output row = 4 positions x 64
+// channels = 256 TMEM columns; the two accumulators alternate exactly like the FC kernel's double
+// buffer (output rows 0,1,2,3 -> slots 0,1,0,1), so output row r's epilogue overlaps the MMAs of r+1.
+// The three horizontally adjacent output positions fed by one input tile use taps kx = 2,1,0 - the
+// resident weights are stored in that order per ky, so they are ONE tcgen05.mma with N = 192
+// (N = 128 at the left/right edge): B = rows [(2-kx_first)*64, ...) of the ky stack.
+//
+// Split precision (fp16x3): hi and lo activation tiles arrive as consecutive ring slots; products
+// x_hi.w_hi, x_hi.w_lo, x_lo.w_hi.  L2->SM traffic: 24 x 32 KB per M tile (vs 120 x 32 KB before).
+#pragma once
+#include <cuda.h>
+#include "fc_tcgen05.cuh"
+
+namespace av1p {
+
+constexpr int CR_STAGES = 5;
+constexpr int CR_A_BYTES = FC_TILE_M * FC_TILE_K * 2;             // 16 KB
+constexpr int CR_W_TILE_BYTES = 64 * 64 * 2;                      // one tap, one plane: 8 KB
+constexpr int CR_W_PLANE_BYTES = 9 * CR_W_TILE_BYTES;             // 72 KB
+constexpr int CR_W_BYTES = 2 * CR_W_PLANE_BYTES;                  // hi + lo planes
+constexpr int CR_SMEM_BYTES = CR_STAGES * CR_A_BYTES + CR_W_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int CR_THREADS = FC_THREADS;
+
+struct ConvResParams {
+  CUtensorMap a_map[2];        // x_hi, x_lo: 2-D [rows][1024] fp16, box {64, 128}, SWIZZLE_128B
+  CUtensorMap w_map;           // resident weights: 2-D [planes*9*64][64] fp16, box {64, 64}; tile (plane, ky, 2-kx)
+  const int* n_rows_dev;
+  int n_rows;
+  int split;                   // 1: hi/lo planes, three products; 0: single fp16 product
+  // epilogue members (names shared with FcParams, see fc_epilogue_tile)
+  int epi;
+  const float* bias;           // [1024]
+  const float* row_scale;      // always nullptr here
+  float acc_scale;
+  const __half* aux;
+  const __half* aux_lo;
+  int aux_ld;
+  __half* out;
+  __half* out_lo;
+  int out_ld;
+  const float* tail_b;         // unused
+  float* logits;               // unused
+  int tail_n;                  // 0
+  int* err_flag;
+};
+
+__global__ void __launch_bounds__(CR_THREADS, 1) conv_res_tcgen05_kernel(const __grid_constant__ ConvResParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t w_base = base + CR_STAGES * CR_A_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + CR_STAGES * CR_A_BYTES + CR_W_BYTES);
+  uint64_t* empty_bar = full_bar + CR_STAGES;
+  uint64_t* acc_full = empty_bar + CR_STAGES;   // [2]
+  uint64_t* acc_empty = acc_full + 2;           // [2]
+  uint64_t* w_bar = acc_empty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_rows = p.n_rows_dev ? *p.n_rows_dev : p.n_rows;
+  const int m_tiles = (n_rows + FC_TILE_M - 1) / FC_TILE_M;
+  const int planes = p.split ? 2 : 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.a_map[0]);
+    tma_prefetch_desc(&p.a_map[1]);
+    tma_prefetch_desc(&p.w_map);
+    for (int s = 0; s < CR_STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], FC_EPI_WARPS);
+    }
+    mbar_init(w_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0 && blockIdx.x < m_tiles) {
+      // resident weights first: planes x 9 tiles of 8 KB on one barrier
+      mbar_arrive_expect_tx(w_bar, uint32_t(planes * CR_W_PLANE_BYTES));
+      for (int t = 0; t < planes * 9; ++t)
+        tma_load_2d(smem + CR_STAGES * CR_A_BYTES + t * CR_W_TILE_BYTES, &p.w_map, w_bar, 0, t * 64);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x) {
+        for (int h = 0; h < 2; ++h) {
+          for (int iy = h; iy < h + 3; ++iy) {
+            for (int ix = 0; ix < 4; ++ix) {
+              for (int pl = 0; pl < planes; ++pl) {
+                mbar_wait(&empty_bar[stage], phase ^ 1u, p.err_flag, 100 + stage);
+                mbar_arrive_expect_tx(&full_bar[stage], CR_A_BYTES);
+                tma_load_2d(smem + stage * CR_A_BYTES, &p.a_map[pl], &full_bar[stage], (iy * 4 + ix) * FC_TILE_K,
+                            mt * FC_TILE_M);
+                if (++stage == CR_STAGES) {
+                  stage = 0;
+                  phase ^= 1u;
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0 && blockIdx.x < m_tiles) {
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t acc_phase = 0u;               // bit s: parity of accumulator slot s
+      mbar_wait(w_bar, 0u, p.err_flag, 500);
+      tc_fence_after_sync();
+      for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x) {
+        for (int h = 0; h < 2; ++h) {
+          uint32_t init_mask = 0u;               // bit 4*slot + ox: that output position's accumulator holds data
+          uint32_t acquired = 0u;                // bit slot
+          for (int iy = h; iy < h + 3; ++iy) {
+            for (int ix = 0; ix < 4; ++ix) {
+              // ring slots of this input position: hi (and lo)
+              const int st_hi = stage;
+              mbar_wait(&full_bar[stage], phase, p.err_flag, 300 + stage);
+              if (++stage == CR_STAGES) {
+                stage = 0;
+                phase ^= 1u;
+              }
+              int st_lo = st_hi;
+              if (p.split) {
+                st_lo = stage;
+                mbar_wait(&full_bar[stage], phase, p.err_flag, 300 + stage);
+                if (++stage == CR_STAGES) {
+                  stage = 0;
+                  phase ^= 1u;
+                }
+              }
+              tc_fence_after_sync();
+              const uint32_t a_hi = base + st_hi * CR_A_BYTES;
+              const uint32_t a_lo = base + st_lo * CR_A_BYTES;
+              const int ox0 = ix > 0 ? ix - 1 : 0;
+              const int ox1 = ix < 3 ? ix + 1 : 3;
+              for (int oy = 2 * h; oy < 2 * h + 2; ++oy) {
+                const int ky = iy - oy + 1;
+                if (ky < 0 || ky > 2) continue;
+                const int slot = oy & 1;
+                if (!((acquired >> slot) & 1u)) {
+                  mbar_wait(&acc_empty[slot], ((acc_phase >> slot) & 1u) ^ 1u, p.err_flag, 200 + slot);
+                  tc_fence_after_sync();
+                  acquired |= 1u << slot;
+                }
+                const uint32_t im = (init_mask >> (4 * slot)) & 0xFu;
+                // runs of output positions with the same accumulate state -> one MMA group each
+                int ox = ox0;
+                while (ox <= ox1) {
+                  const uint32_t st = (im >> ox) & 1u;
+                  int oe = ox;
+                  while (oe + 1 <= ox1 && ((im >> (oe + 1)) & 1u) == st) ++oe;
+                  const uint32_t n = uint32_t(oe - ox + 1) * 64u;
+                  const uint32_t idesc = umma_idesc_f16(n);
+                  const uint32_t d_tmem = tmem_base + uint32_t(slot * 256 + ox * 64);
+                  // taps for ox..oe are kx = ix-ox+1 .. ix-oe+1 (descending) = rows (2-kx_first)*64.. of the ky stack
+                  const uint32_t w_hi = w_base + uint32_t(ky * 3 + (2 - (ix - ox + 1))) * CR_W_TILE_BYTES;
+                  const uint32_t w_lo = w_hi + CR_W_PLANE_BYTES;
+#pragma unroll
+                  for (int k = 0; k < FC_TILE_K / 16; ++k)
+                    umma_f16_ss(d_tmem, umma_desc_sw128(a_hi + k * 32), umma_desc_sw128(w_hi + k * 32), idesc,
+                                (st || k > 0) ? 1u : 0u);
+                  if (p.split) {
+#pragma unroll
+                    for (int k = 0; k < FC_TILE_K / 16; ++k)
+                      umma_f16_ss(d_tmem, umma_desc_sw128(a_hi + k * 32), umma_desc_sw128(w_lo + k * 32), idesc, 1u);
+#pragma unroll
+                    for (int k = 0; k < FC_TILE_K / 16; ++k)
+                      umma_f16_ss(d_tmem, umma_desc_sw128(a_lo + k * 32), umma_desc_sw128(w_hi + k * 32), idesc, 1u);
+                  }
+                  ox = oe + 1;
+                }
+                init_mask |= ((1u << (ox1 + 1)) - (1u << ox0)) << (4 * slot);
+              }
+              umma_commit(&empty_bar[st_hi]);   // frees the ring slots once these MMAs have read them
+              if (p.split) umma_commit(&empty_bar[st_lo]);
+            }
+            // output row complete once its last input row (oy + 1, clamped) has been consumed
+            for (int oy = 2 * h; oy < 2 * h + 2; ++oy) {
+              const int last_iy = oy < 3 ? oy + 1 : 3;
+              if (iy == last_iy) {
+                const int slot = oy & 1;
+                umma_commit(&acc_full[slot]);
+                acc_phase ^= 1u << slot;
+              }
+            }
+          }
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue (warps 2..9): output rows 0..3 -> slots 0,1,0,1
+    uint32_t acc_phase = 0u;
+    for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x) {
+      for (int oy = 0; oy < 4; ++oy) {
+        const int slot = oy & 1;
+        fc_epilogue_tile(p, n_rows, mt, oy * 256, 256, tmem_base + uint32_t(slot * 256), &acc_full[slot], acc_phase,
+                         &acc_empty[slot], static_cast<const float*>(nullptr), warp, lane, 400 + slot);
+        if (slot) acc_phase ^= 1u;
+      }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace av1p

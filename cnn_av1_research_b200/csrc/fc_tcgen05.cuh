@@ -103,6 +103,119 @@ __device__ __forceinline__ void add_half32(float (&f)[32], const Half32& d) {
   }
 }
 
+// Epilogue of one accumulator tile [128 rows x block_n fp32 columns at TMEM column t_col]: warps 2..9,
+// two warps per TMEM lane quadrant, each takes half of the tile's columns.  Waits on `full`, applies
+// bias / residual / ReLU / gate / in-thread final linear, stores fp16 hi (+lo) rows, then arrives on `empty`.
+// P is FcParams or any struct with the same epilogue members.
+template <typename P>
+__device__ __forceinline__ void fc_epilogue_tile(const P& p, int n_rows, int mt, int col0, int block_n, uint32_t t_col,
+                                                 uint64_t* full, uint32_t full_phase, uint64_t* empty,
+                                                 const float* tail_w_s, int warp, int lane, int tag) {
+  const int ew = warp - 2;
+  const int quad = warp & 3;              // TMEM lane quadrant this warp may read
+  const int half = ew >> 2;               // which half of the tile's columns
+  // the in-thread head needs whole rows: there the first four warps take every column
+  const bool whole = (p.epi == FC_EPI_HEAD) || (block_n < 64);
+  const int c_begin = whole ? 0 : half * (block_n / 2);
+  const int c_end = whole ? (half == 0 ? block_n : 0) : c_begin + block_n / 2;
+  const bool needs_aux = (p.epi == FC_EPI_ADD_RELU || p.epi == FC_EPI_GATE);
+  const int row = mt * FC_TILE_M + quad * 32 + lane;
+  const bool row_ok = row < n_rows;
+  const float rs = ((p.row_scale && row_ok) ? p.row_scale[row] : 1.0f) * p.acc_scale;
+  // prefetch the first residual / gate chunk while the MMAs of this tile are still running
+  Half32 ax, axl;
+  zero_half32(ax);
+  zero_half32(axl);
+  if (needs_aux && row_ok && c_begin < c_end) {
+    ld_half32(ax, p.aux + size_t(row) * p.aux_ld + col0 + c_begin);
+    if (p.aux_lo) ld_half32(axl, p.aux_lo + size_t(row) * p.aux_ld + col0 + c_begin);
+  }
+  mbar_wait(full, full_phase, p.err_flag, tag);
+  tc_fence_after_sync();
+  const uint32_t t_addr = t_col + (uint32_t(quad * 32) << 16);
+  float tail[FC_TAIL_MAX] = {0.f, 0.f, 0.f, 0.f};
+  for (int c = c_begin; c < c_end; c += 32) {
+    uint32_t v[32];
+    tmem_ld_32x32(t_addr + uint32_t(c), v);
+    // next chunk's residual / gate input goes in flight before this chunk is consumed
+    Half32 nx, nxl;
+    zero_half32(nx);
+    zero_half32(nxl);
+    if (needs_aux && row_ok && c + 32 < c_end) {
+      ld_half32(nx, p.aux + size_t(row) * p.aux_ld + col0 + c + 32);
+      if (p.aux_lo) ld_half32(nxl, p.aux_lo + size_t(row) * p.aux_ld + col0 + c + 32);
+    }
+    tmem_ld_wait();
+    float f[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) * rs;
+    if (p.bias) {
+      const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0 + c);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 b = __ldg(b4 + i);
+        f[4 * i + 0] += b.x;
+        f[4 * i + 1] += b.y;
+        f[4 * i + 2] += b.z;
+        f[4 * i + 3] += b.w;
+      }
+    }
+    if (p.epi == FC_EPI_ADD_RELU) {
+      add_half32(f, ax);
+      add_half32(f, axl);
+    } else if (p.epi == FC_EPI_GATE) {
+      float g[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) g[i] = 0.f;
+      add_half32(g, ax);
+      add_half32(g, axl);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) f[i] = g[i] * fast_sigmoid(f[i]);
+    }
+    ax = nx;
+    axl = nxl;
+    if (p.epi == FC_EPI_RELU || p.epi == FC_EPI_ADD_RELU || p.epi == FC_EPI_HEAD) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
+    }
+    if (p.epi == FC_EPI_HEAD) {
+#pragma unroll
+      for (int j = 0; j < FC_TAIL_MAX; ++j) {
+        if (j < p.tail_n) {
+          const float* w = tail_w_s + j * block_n + c;
+          float t = tail[j];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) t = fmaf(f[i], w[i], t);
+          tail[j] = t;
+        }
+      }
+    } else if (row_ok) {
+      __align__(16) __half h[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) h[i] = __float2half_rn(f[i]);
+      uint4* o4 = reinterpret_cast<uint4*>(p.out + size_t(row) * p.out_ld + col0 + c);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) o4[i] = reinterpret_cast<const uint4*>(h)[i];
+      if (p.out_lo) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) h[i] = __float2half_rn(f[i] - __half2float(h[i]));
+        uint4* l4 = reinterpret_cast<uint4*>(p.out_lo + size_t(row) * p.out_ld + col0 + c);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) l4[i] = reinterpret_cast<const uint4*>(h)[i];
+      }
+    }
+  }
+  if (p.epi == FC_EPI_HEAD && row_ok && c_begin < c_end) {
+#pragma unroll
+    for (int j = 0; j < FC_TAIL_MAX; ++j)
+      if (j < p.tail_n) p.logits[size_t(row) * p.tail_n + j] = tail[j] + p.tail_b[j];
+  }
+  // all TMEM reads of this accumulator are complete (tmem_ld_wait above) -> hand it back
+  tc_fence_before_sync();
+  __syncwarp();
+  if (lane == 0) mbar_arrive(empty);
+}
+
 __global__ void __launch_bounds__(FC_THREADS, 1) fc_tcgen05_kernel(const __grid_constant__ FcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -230,115 +343,13 @@ __global__ void __launch_bounds__(FC_THREADS, 1) fc_tcgen05_kernel(const __grid_
     }
   } else {
     // ------------------------------------------------------------ epilogue (warps 2..9)
-    const int ew = warp - 2;
-    const int quad = warp & 3;              // TMEM lane quadrant this warp may read
-    const int half = ew >> 2;               // which half of the tile's columns
-    // the in-thread head needs whole rows: there the first four warps take every column
-    const bool whole = (p.epi == FC_EPI_HEAD) || (p.block_n < 64);
-    const int c_begin = whole ? 0 : half * (p.block_n / 2);
-    const int c_end = whole ? (half == 0 ? p.block_n : 0) : c_begin + p.block_n / 2;
-    const bool needs_aux = (p.epi == FC_EPI_ADD_RELU || p.epi == FC_EPI_GATE);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int mt = item / p.n_tiles;
       const int nt = item - mt * p.n_tiles;
-      const int row = mt * FC_TILE_M + quad * 32 + lane;
-      const bool row_ok = row < n_rows;
-      const int col0 = nt * p.block_n;
-      const float rs = ((p.row_scale && row_ok) ? p.row_scale[row] : 1.0f) * p.acc_scale;
-      // prefetch the first residual / gate chunk while the MMAs of this tile are still running
-      Half32 ax, axl;
-      zero_half32(ax);
-      zero_half32(axl);
-      if (needs_aux && row_ok && c_begin < c_end) {
-        ld_half32(ax, p.aux + size_t(row) * p.aux_ld + col0 + c_begin);
-        if (p.aux_lo) ld_half32(axl, p.aux_lo + size_t(row) * p.aux_ld + col0 + c_begin);
-      }
-      mbar_wait(&acc_full[acc], acc_phase, p.err_flag, 400 + acc);
-      tc_fence_after_sync();
-      const uint32_t t_addr = tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(acc * FC_MAX_N);
-      float tail[FC_TAIL_MAX] = {0.f, 0.f, 0.f, 0.f};
-      for (int c = c_begin; c < c_end; c += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32(t_addr + uint32_t(c), v);
-        // next chunk's residual / gate input goes in flight before this chunk is consumed
-        Half32 nx, nxl;
-        zero_half32(nx);
-        zero_half32(nxl);
-        if (needs_aux && row_ok && c + 32 < c_end) {
-          ld_half32(nx, p.aux + size_t(row) * p.aux_ld + col0 + c + 32);
-          if (p.aux_lo) ld_half32(nxl, p.aux_lo + size_t(row) * p.aux_ld + col0 + c + 32);
-        }
-        tmem_ld_wait();
-        float f[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) * rs;
-        if (p.bias) {
-          const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0 + c);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float4 b = __ldg(b4 + i);
-            f[4 * i + 0] += b.x;
-            f[4 * i + 1] += b.y;
-            f[4 * i + 2] += b.z;
-            f[4 * i + 3] += b.w;
-          }
-        }
-        if (p.epi == FC_EPI_ADD_RELU) {
-          add_half32(f, ax);
-          add_half32(f, axl);
-        } else if (p.epi == FC_EPI_GATE) {
-          float g[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) g[i] = 0.f;
-          add_half32(g, ax);
-          add_half32(g, axl);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) f[i] = g[i] * fast_sigmoid(f[i]);
-        }
-        ax = nx;
-        axl = nxl;
-        if (p.epi == FC_EPI_RELU || p.epi == FC_EPI_ADD_RELU || p.epi == FC_EPI_HEAD) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
-        }
-        if (p.epi == FC_EPI_HEAD) {
-#pragma unroll
-          for (int j = 0; j < FC_TAIL_MAX; ++j) {
-            if (j < p.tail_n) {
-              const float* w = tail_w_s + j * p.block_n + c;
-              float t = tail[j];
-#pragma unroll
-              for (int i = 0; i < 32; ++i) t = fmaf(f[i], w[i], t);
-              tail[j] = t;
-            }
-          }
-        } else if (row_ok) {
-          __align__(16) __half h[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) h[i] = __float2half_rn(f[i]);
-          uint4* o4 = reinterpret_cast<uint4*>(p.out + size_t(row) * p.out_ld + col0 + c);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) o4[i] = reinterpret_cast<const uint4*>(h)[i];
-          if (p.out_lo) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) h[i] = __float2half_rn(f[i] - __half2float(h[i]));
-            uint4* l4 = reinterpret_cast<uint4*>(p.out_lo + size_t(row) * p.out_ld + col0 + c);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) l4[i] = reinterpret_cast<const uint4*>(h)[i];
-          }
-        }
-      }
-      if (p.epi == FC_EPI_HEAD && row_ok && c_begin < c_end) {
-#pragma unroll
-        for (int j = 0; j < FC_TAIL_MAX; ++j)
-          if (j < p.tail_n) p.logits[size_t(row) * p.tail_n + j] = tail[j] + p.tail_b[j];
-      }
-      // all TMEM reads of this accumulator are complete (tmem_ld_wait above) -> hand it back
-      tc_fence_before_sync();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[acc]);
+      fc_epilogue_tile(p, n_rows, mt, nt * p.block_n, p.block_n, tmem_base + uint32_t(acc * FC_MAX_N), &acc_full[acc],
+                       acc_phase, &acc_empty[acc], tail_w_s, warp, lane, 400 + acc);
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1u;

@@ -26,12 +26,12 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import numpy as np
 
 BLOB_MAGIC = 0x50315641
-BLOB_VERSION = 6
+BLOB_VERSION = 7
 MAX_NT = 8
 MAX_KB = 128
 TILE_K = 64
 
-OP_STEM, OP_FC, OP_SAM, OP_FGVC_TAIL, OP_SE = 0, 1, 2, 3, 4
+OP_STEM, OP_FC, OP_SAM, OP_FGVC_TAIL, OP_SE, OP_CONV_RES = 0, 1, 2, 3, 4, 5
 EPI_LINEAR, EPI_RELU, EPI_ADD_RELU, EPI_GATE, EPI_HEAD = 0, 1, 2, 3, 4
 
 STAGE_KINDS = {"stage1": 0, "stage2": 1, "rect": 2, "ab_fgvc": 3, "ab": 4}
@@ -215,11 +215,30 @@ def make_fc_op(name: str, dense: Sequence[np.ndarray], srcs: Sequence[str], out:
     return best[1]
 
 
+def make_conv_res_op(name: str, wf: np.ndarray, bf: np.ndarray, src: str, out: str, epi: int, precision: str,
+                     aux: Optional[str] = None) -> _Op:
+    """layer1 3x3 / stride-1 / 64->64 convolution on the 4x4 map for the resident-weight kernel
+    (csrc/conv_res_tcgen05.cuh): the nine folded [co, ci] tap matrices, ordered (ky, kx = 2, 1, 0) so that the taps
+    of horizontally adjacent output positions are consecutive rows of one B operand; hi (+ lo) fp16 planes."""
+    assert wf.shape == (64, 64, 3, 3) and BUF_COLS[src] == 1024 and BUF_COLS[out] == 1024
+    wmax = float(np.abs(wf).max())
+    scale = 2.0 ** int(np.clip(np.floor(np.log2(8192.0 / wmax)), 0, 16)) if wmax > 0 else 1.0
+    taps = np.stack([wf[:, :, ky, 2 - j] for ky in range(3) for j in range(3)]) * scale     # [9, co, ci]
+    if np.abs(taps).max() >= 65504.0:
+        raise ValueError(f"{name}: folded weight does not fit fp16")
+    w_hi = taps.astype(np.float16)
+    split = precision == "fp16x3"
+    w = np.stack([w_hi, (taps - w_hi.astype(np.float64)).astype(np.float16)]) if split else w_hi[None]
+    return _Op(OP_CONV_RES, src=[_hi(src), _lo(src, precision), -1, -1], aux=_hi(aux), aux_lo=_lo(aux, precision),
+               out=_hi(out), out_lo=_lo(out, precision), n_tiles=16, block_n=64, epi=epi, pair_mode=int(split), f0=1.0 / scale,
+               w=w.reshape(-1, 64), bias=np.tile(bf, 16).astype(np.float32), name=name)
+
+
 def _block_n(n: int) -> int:
     return 256 if n >= 256 else -(-n // 32) * 32
 
 
-def backbone_ops(sd, precision: str = "fp16x3", prefix: str = "backbone.") -> List[_Op]:
+def backbone_ops(sd, precision: str = "fp16x3", prefix: str = "backbone.", layer1_fc: bool = False) -> List[_Op]:
     """Op program for ImprovedBackbone.forward (models.py:104-121).  Result: x4' in C1, SAM scalar in row_scale."""
     p = prefix
     ops: List[_Op] = []
@@ -262,17 +281,20 @@ def backbone_ops(sd, precision: str = "fp16x3", prefix: str = "backbone.") -> Li
         ops.append(make_fc_op(f"se{layer}.fc1", [d1], [src], "H", None, EPI_RELU, 64, precision))
         ops.append(make_fc_op(f"se{layer}.fc2", [d2], ["H"], dst, None, EPI_GATE, _block_n(d2.shape[0]), precision, aux=src))
 
-    # --- layer1: 4x4 grid, 64 ch.  a0=B0
-    u = p + "layer1.0"
-    d, b, _ = conv_bn(u, "conv1", "bn1", 4, 1)
-    ops.append(make_fc_op(u + ".conv1", [d], ["B0"], "B1", b, EPI_RELU, 256, precision))
-    d, b, _ = conv_bn(u, "conv2", "bn2", 4, 1)
-    ops.append(make_fc_op(u + ".conv2", [d], ["B1"], "B2", b, EPI_ADD_RELU, 256, precision, aux="B0"))
-    u = p + "layer1.1"
-    d, b, _ = conv_bn(u, "conv1", "bn1", 4, 1)
-    ops.append(make_fc_op(u + ".conv1", [d], ["B2"], "B1", b, EPI_RELU, 256, precision))
-    d, b, _ = conv_bn(u, "conv2", "bn2", 4, 1)
-    ops.append(make_fc_op(u + ".conv2", [d], ["B1"], "B0", b, EPI_ADD_RELU, 256, precision, aux="B2"))
+    # --- layer1: 4x4 grid, 64 ch.  a0=B0.  Resident-weight conv kernel by default; `layer1_fc=True` keeps the
+    #     generic block-Toeplitz FC form (used by the kernel-level comparison tests).
+    def l1(unit: str, conv: str, bn: str, src: str, out: str, epi: int, aux: Optional[str] = None):
+        wf, bf = fold_bn(_np64(sd[f"{unit}.{conv}.weight"]), None, sd, f"{unit}.{bn}")
+        if layer1_fc:
+            d, ho, _ = conv_as_dense(wf, 4, 4, 1, 1)
+            kw = {"aux": aux} if aux else {}
+            return make_fc_op(f"{unit}.{conv}", [d], [src], out, np.tile(bf, ho * ho), epi, 256, precision, **kw)
+        return make_conv_res_op(f"{unit}.{conv}", wf, bf, src, out, epi, precision, aux=aux)
+
+    ops.append(l1(p + "layer1.0", "conv1", "bn1", "B0", "B1", EPI_RELU))
+    ops.append(l1(p + "layer1.0", "conv2", "bn2", "B1", "B2", EPI_ADD_RELU, aux="B0"))
+    ops.append(l1(p + "layer1.1", "conv1", "bn1", "B2", "B1", EPI_RELU))
+    ops.append(l1(p + "layer1.1", "conv2", "bn2", "B1", "B0", EPI_ADD_RELU, aux="B2"))
     se(1, 4, "B0", "B1")                                         # x1 = B1
 
     # --- layers 2..4: (input buffer, grid in, three scratch buffers of the output width)
@@ -375,7 +397,7 @@ def serialise(kind: str, ops: List[_Op], precision: str) -> bytes:
     return bytes(blob)
 
 
-def pack_stage(kind: str, state_dict, precision: str = "fp16x3") -> bytes:
+def pack_stage(kind: str, state_dict, precision: str = "fp16x3", layer1_fc: bool = False) -> bytes:
     """`state_dict` of Stage1Model / Stage2Model / Stage3RectModel / Stage3ABModel / FGVCModel -> blob.
 
     precision: "fp16x3" (default; split fp16 operands, fp32-grade logits) or "fp16" (single product).
@@ -384,7 +406,7 @@ def pack_stage(kind: str, state_dict, precision: str = "fp16x3") -> bytes:
         raise ValueError(f"unknown stage kind {kind!r}")
     if precision not in PRECISIONS:
         raise ValueError(f"unknown precision {precision!r}")
-    return serialise(kind, backbone_ops(state_dict, precision) + head_ops(kind, state_dict, precision), precision)
+    return serialise(kind, backbone_ops(state_dict, precision, layer1_fc=layer1_fc) + head_ops(kind, state_dict, precision), precision)
 
 
 def blob_stats(blob: bytes) -> Dict[str, float]:
@@ -396,4 +418,6 @@ def blob_stats(blob: bytes) -> Dict[str, float]:
         if f[0] == OP_FC:
             products = f[14] * 3 // 2 if f[16] else f[14]     # pair mode: 3 products per 2 entries
             macs += products * f[10] * TILE_K                  # products * block_n * 64
+        elif f[0] == OP_CONV_RES:
+            macs += 100 * 64 * 64 * (3 if f[16] else 1)         # 100 (output, input) position pairs under the 3x3 window
     return {"tensor_macs_per_block": float(macs), "bytes": float(len(blob))}

@@ -6,6 +6,7 @@ PyTorch's current stream.  Nothing here computes on the host.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, Optional, Sequence
 
 import torch
@@ -21,7 +22,9 @@ class NativeModel:
         self.kind = kind
         self.precision = precision
         self.device = torch.device(device)
-        blob = pack_stage(kind, state_dict, precision)
+        # AV1P_LAYER1_FC=1: run layer1 on the generic block-Toeplitz FC kernel instead of the resident-weight conv kernel
+        # (A/B measurements only; both are tcgen05 device paths)
+        blob = pack_stage(kind, state_dict, precision, layer1_fc=os.environ.get("AV1P_LAYER1_FC", "0") == "1")
         self.stats = blob_stats(blob)
         self.num_outputs = NUM_OUTPUTS[kind]
         handle = C.c_void_p()

@@ -116,7 +116,7 @@ int av1p_finalize_labels(const float* logits_dev, int32_t num_classes, int32_t l
 /* ---- measurement support (bench.py): bracket every kernel launch of the calling thread with CUDA
  *      events on its stream.  av1p_profile_end synchronises on those events and returns the summed
  *      device time and launch count per kernel class: 0 stem, 1 tcgen05 FC, 2 SAM gate, 3 FGVC tail,
- *      4 routing, 5 label finalize, 6 squeeze-excite (arrays of 8). */
+ *      4 routing, 5 label finalize, 6 squeeze-excite, 7 resident-weight layer1 conv (arrays of 8). */
 int av1p_profile_begin(void);
 int av1p_profile_end(float* ms_by_class, int32_t* launches_by_class);
 
@@ -148,6 +148,24 @@ typedef struct av1p_fc_desc {
   const float* tail_w_dev; const float* tail_b_dev; float* logits_dev; int32_t tail_n;
 } av1p_fc_desc;
 int av1p_fc_forward(const av1p_fc_desc* d, void* stream);
+
+/* ---- kernel-level test hook: one layer1 convolution (3x3, stride 1, 64 -> 64 channels on the 4x4 map,
+ *      torchvision BasicBlock conv3x3 as used by models.py:110) on the resident-weight tcgen05 path
+ *      (csrc/conv_res_tcgen05.cuh).  x: fp16 [rows][1024] ([position][channel] per block), x_lo its low
+ *      plane (split != 0); w: fp16 [planes][ky][kx = 2,1,0][64 co][64 ci]; bias float32[1024];
+ *      epi 0 linear, 1 relu, 2 relu(acc + bias + aux). */
+typedef struct av1p_conv_res_desc {
+  const void* x_dev; const void* x_lo_dev;
+  int32_t rows;
+  const int32_t* n_dev;
+  const void* w_dev;
+  int32_t split, epi;
+  const float* bias_dev;
+  float acc_scale;
+  const void* aux_dev; const void* aux_lo_dev;
+  void* out_dev; void* out_lo_dev;
+} av1p_conv_res_desc;
+int av1p_conv_res_forward(const av1p_conv_res_desc* d, void* stream);
 
 #ifdef __cplusplus
 }

@@ -17,7 +17,7 @@ OP_BYTES = struct.calcsize(OP_FMT)
 
 def parse(blob: bytes):
     magic, version, kind, n_ops, n_bufs, n_out, prec, _, ops_off, bufs_off, total, _ = struct.unpack_from("<8I4Q", blob, 0)
-    assert magic == 0x50315641 and version == 6 and total == len(blob)
+    assert magic == 0x50315641 and version == 7 and total == len(blob)
     cols = struct.unpack_from(f"<{n_bufs}I", blob, bufs_off)
     ops = []
     for i in range(n_ops):
@@ -117,6 +117,28 @@ def run(blob: bytes, images: np.ndarray) -> np.ndarray:
             hid = np.maximum(x.mean(axis=1) @ wt[0].T, 0.0)
             s = 1.0 / (1.0 + np.exp(-(hid @ wt[1])))
             store(op, (x * s[:, None, :]).reshape(n, npos * c), npos * c)
+        elif t == 5:  # resident-weight 3x3 conv on the 4x4x64 map
+            planes = 2 if op["pair_mode"] else 1
+            w = _arr(blob, op["w_off"], np.float16, planes * 9 * 64 * 64).reshape(planes, 3, 3, 64, 64).astype(np.float32)
+            x_hi = bufs[op["src"][0]].reshape(n, 4, 4, 64)
+            x_lo = bufs[op["src"][1]].reshape(n, 4, 4, 64) if planes == 2 else None
+            acc = np.zeros((n, 4, 4, 64), dtype=np.float32)
+            for oy in range(4):
+                for ox in range(4):
+                    for ky in range(3):
+                        for kx in range(3):
+                            iy, ix = oy + ky - 1, ox + kx - 1
+                            if 0 <= iy < 4 and 0 <= ix < 4:
+                                acc[:, oy, ox] += x_hi[:, iy, ix] @ w[0, ky, 2 - kx].T
+                                if planes == 2:
+                                    acc[:, oy, ox] += x_hi[:, iy, ix] @ w[1, ky, 2 - kx].T
+                                    acc[:, oy, ox] += x_lo[:, iy, ix] @ w[0, ky, 2 - kx].T
+            acc = acc.reshape(n, 1024) * np.float32(op["f0"]) + _arr(blob, op["bias_off"], np.float32, 1024)[None, :]
+            if op["epi"] == 2:
+                acc = acc + load(op["aux"], op["aux_lo"])
+            if op["epi"] in (1, 2):
+                acc = np.maximum(acc, 0.0)
+            store(op, acc, 1024)
         else:
             raise ValueError(t)
     return logits.astype(np.float32)

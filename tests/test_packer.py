@@ -50,7 +50,7 @@ def test_bn_folding_is_exact_in_float64():
 def test_schedule_skips_zero_blocks_and_fits_limits():
     sd = synth.random_state_dict("stage1", 3)
     for precision, mult in (("fp16", 1), ("fp16x3", 2)):
-        ops = packer.backbone_ops(sd, precision) + packer.head_ops("stage1", sd, precision)
+        ops = packer.backbone_ops(sd, precision, layer1_fc=True) + packer.head_ops("stage1", sd, precision)
         fc = [o for o in ops if o.type == packer.OP_FC]
         by_name = {o.name: o for o in fc}
         # layer1 3x3 conv on a 4x4 grid, N tiles of 2 horizontally adjacent positions (block_n 128): a tile sees
@@ -65,14 +65,29 @@ def test_schedule_skips_zero_blocks_and_fits_limits():
             assert len(o.kb_src) <= packer.MAX_KB and o.n_tiles <= packer.MAX_NT and o.block_n % 32 == 0
             assert max(o.kb_w) < o.n_w_chunks and o.kb_begin[-1] == len(o.kb_src)
             assert 0 < o.f0 <= 1.0 and np.log2(o.f0) == int(np.log2(o.f0))          # power-of-two weight scale
+        # default program: layer1 runs on the resident-weight conv kernel (9 taps x planes, kx stored 2,1,0)
+        res = [o for o in packer.backbone_ops(sd, precision) if o.type == packer.OP_CONV_RES]
+        assert [o.name for o in res] == [f"backbone.layer1.{u}.conv{c}" for u in (0, 1) for c in (1, 2)]
+        for o in res:
+            assert o.w.shape == (mult * 9 * 64, 64) and o.w.dtype == np.float16 and o.bias.shape == (1024,) and o.pair_mode == mult - 1
+    macs_fc = packer.blob_stats(packer.pack_stage("stage1", sd, "fp16", layer1_fc=True))["tensor_macs_per_block"]
     macs = packer.blob_stats(packer.pack_stage("stage1", sd, "fp16"))["tensor_macs_per_block"]
-    assert 4.2e6 < macs < 6.5e6        # live MACs are 4.4 M/block; the block-Toeplitz form adds < 40 %
+    assert 4.2e6 < macs < macs_fc < 6.5e6   # live MACs are 4.4 M/block; the block-Toeplitz form adds < 40 %
+
+
+def test_resident_conv_program_equals_block_toeplitz_program(stage_fixture):
+    """Both layer1 formulations must give the same logits (the emulator interprets each op type independently)."""
+    sd = synth.calibrated_state_dict("stage1", 0)
+    x = stage_fixture["images"][:64]
+    a = E.run(packer.pack_stage("stage1", sd, "fp16x3"), x)
+    b = E.run(packer.pack_stage("stage1", sd, "fp16x3", layer1_fc=True), x)
+    assert np.abs(a - b).max() <= 2e-4
 
 
 def test_blob_layout():
     blob = packer.pack_stage("rect", synth.random_state_dict("rect", 0), "fp16x3")
     magic, version, kind, n_ops, n_bufs, n_out = struct.unpack_from("<6I", blob, 0)
-    assert (magic, version, kind, n_bufs, n_out) == (0x50315641, 6, 2, 20, 2)
+    assert (magic, version, kind, n_bufs, n_out) == (0x50315641, 7, 2, 20, 2)
     P = E.parse(blob)
     assert P["ops"][0]["type"] == packer.OP_STEM and P["ops"][-1]["epi"] == packer.EPI_HEAD
     for op in P["ops"]:
