@@ -242,7 +242,7 @@ def main():
         for c in range(F // sub):
             pipe.predict_frames(dev_frames[c * sub * fw:], W4K, H4K, sub, out_u8=labels_dev[c * sub * BPF:(c + 1) * sub * BPF])
     N.check(lib.av1p_profile_end(ms_cls, n_cls))
-    cls_names = ("stem", "fc_tcgen05", "sam_gate", "fgvc_tail", "route", "finalize", "squeeze_excite")
+    cls_names = ("stem", "fc_tcgen05", "sam_gate", "fgvc_tail", "route", "finalize", "squeeze_excite", "conv_res_tcgen05")
     per_class = {nm: {"ms_per_step": ms_cls[i] / prof_steps, "launches_per_step": n_cls[i] // prof_steps} for i, nm in enumerate(cls_names)}
     fc_ms = per_class["fc_tcgen05"]["ms_per_step"]
     fc_launches = per_class["fc_tcgen05"]["launches_per_step"]

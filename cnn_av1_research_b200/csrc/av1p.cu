@@ -84,19 +84,63 @@ int ensure_ctx() {
   return AV1P_OK;
 }
 
-// 2-D fp16 tensor map, row-major [rows][cols], box {64 cols, box_rows}, 128-byte swizzle.
+// 2-D fp16 tensor map, row-major [rows][cols].  Operand tiles: box {64 cols, box_rows}, 128-byte swizzle
+// (one swizzle atom per row = the K-major layout tcgen05.mma reads).  Epilogue staging tiles (TMA stores):
+// box {32 cols, 128 rows}, 64-byte swizzle.
 int make_map_2d(CUtensorMap* map, const void* base, uint64_t cols, uint64_t rows, uint64_t ld_elems,
-                uint32_t box_rows) {
+                uint32_t box_rows, uint32_t box_cols = 64, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   if ((reinterpret_cast<uintptr_t>(base) & 15u) || (ld_elems * 2) % 16)
     return fail(AV1P_EINVAL, "tensor map base/stride not 16-byte aligned");
   cuuint64_t dims[2] = {cols, rows};
   cuuint64_t strides[1] = {ld_elems * 2};
-  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = g_ctx.encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box,
-                            estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                            estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(AV1P_ECUDA, "cuTensorMapEncodeTiled failed with %d", int(r));
+  return AV1P_OK;
+}
+int make_store_map(CUtensorMap* map, const void* base, uint64_t cols, uint64_t rows) {
+  return make_map_2d(map, base, cols, rows, cols, FC_TILE_M, EPI_CHUNK, CU_TENSOR_MAP_SWIZZLE_64B);
+}
+
+// Residual connection of an FC layer (FC_EPI_ADD_RELU): the identity branch is accumulated on the tensor
+// core.  Appends, to every N tile's schedule, one FC_W_IDENT entry per 64-wide K block of the residual
+// buffer that falls inside the tile (hi plane through source 2, lo plane through source 3).  The caller
+// has pointed a_map[2] / a_map[3] at the residual planes.
+int add_residual_entries(FcParams& f, bool has_lo) {
+  if (f.block_n % FC_TILE_K) return fail(AV1P_EINVAL, "residual FC layer needs block_n to be a multiple of 64");
+  if (f.row_scale) return fail(AV1P_EINVAL, "residual FC layer cannot use a row scale");
+  const float s = 1.0f / f.acc_scale;
+  if (!(s >= 1.0f && s <= 32768.0f)) return fail(AV1P_EINVAL, "residual FC layer: weight scale %g outside [1, 2^15]", double(s));
+  std::vector<uint16_t> src, w;
+  int begin[FC_MAX_NT + 1];
+  begin[0] = 0;
+  const int per_tile = f.block_n / FC_TILE_K;
+  for (int t = 0; t < f.n_tiles; ++t) {
+    for (int e = f.kb_begin[t]; e < f.kb_begin[t + 1]; ++e) {
+      if ((f.kb_src[e] >> 14) >= 2) return fail(AV1P_EINVAL, "residual FC layer uses more than one activation source");
+      src.push_back(f.kb_src[e]);
+      w.push_back(f.kb_w[e]);
+    }
+    for (int j = 0; j < per_tile; ++j) {
+      const uint16_t kb = uint16_t(t * per_tile + j);
+      src.push_back(uint16_t((2u << 14) | kb));
+      w.push_back(FC_W_IDENT);
+      if (has_lo) {
+        src.push_back(uint16_t((3u << 14) | kb));
+        w.push_back(FC_W_IDENT);
+      }
+    }
+    begin[t + 1] = int(src.size());
+  }
+  if (src.size() > size_t(FC_MAX_KB)) return fail(AV1P_EINVAL, "residual FC layer: %zu schedule entries exceed %d", src.size(), FC_MAX_KB);
+  for (size_t i = 0; i < src.size(); ++i) {
+    f.kb_src[i] = src[i];
+    f.kb_w[i] = w[i];
+  }
+  for (int t = 0; t <= f.n_tiles; ++t) f.kb_begin[t] = begin[t];
   return AV1P_OK;
 }
 
@@ -361,6 +405,18 @@ int plan_stage(const av1p_model* m, const ActLayout& L, uint8_t* act_base, av1p_
           if (sb < 0 || uint32_t(op.kb_src[i] & 0x3FFF) * 64 + 64 > L.cols[sb]) return fail(AV1P_EINVAL, "K block outside its source buffer");
           if (int(op.kb_w[i]) >= op.n_w_chunks) return fail(AV1P_EINVAL, "weight chunk index out of range");
         }
+        if (op.out >= 0) {
+          if (int rc = make_store_map(&f.out_map[0], buf(op.out), L.cols[op.out], L.cap)) return rc;
+          if (op.out_lo >= 0)
+            if (int rc = make_store_map(&f.out_map[1], buf(op.out_lo), L.cols[op.out_lo], L.cap)) return rc;
+        }
+        if (op.epi == FC_EPI_ADD_RELU) {
+          if (op.n_tiles * op.block_n > int(L.cols[op.aux])) return fail(AV1P_EINVAL, "residual narrower than the FC output");
+          if (int rc = make_map_2d(&f.a_map[2], buf(op.aux), L.cols[op.aux], L.cap, L.cols[op.aux], FC_TILE_M)) return rc;
+          if (op.aux_lo >= 0)
+            if (int rc = make_map_2d(&f.a_map[3], buf(op.aux_lo), L.cols[op.aux_lo], L.cap, L.cols[op.aux_lo], FC_TILE_M)) return rc;
+          if (int rc = add_residual_entries(f, op.aux_lo >= 0)) return rc;
+        }
         break;
       }
       case AV1P_OP_CONV_RES: {
@@ -377,15 +433,22 @@ int plan_stage(const av1p_model* m, const ActLayout& L, uint8_t* act_base, av1p_
         f.epi = op.epi;
         f.bias = reinterpret_cast<const float*>(at(op.bias_off));
         f.acc_scale = op.f0;
-        f.aux = buf(op.aux);
-        f.aux_lo = buf(op.aux_lo);
-        f.aux_ld = op.aux >= 0 ? int(L.cols[op.aux]) : 0;
         f.out = buf(op.out);
         f.out_lo = buf(op.out_lo);
         f.out_ld = 1024;
         f.err_flag = g_ctx.watchdog_dev;
         if (op.epi != FC_EPI_RELU && op.epi != FC_EPI_ADD_RELU && op.epi != FC_EPI_LINEAR) return fail(AV1P_EINVAL, "resident-conv epilogue %d", op.epi);
-        if (op.epi == FC_EPI_ADD_RELU && (!f.aux || f.aux_ld != 1024)) return fail(AV1P_EINVAL, "resident-conv op needs a 1024-wide aux");
+        if (!(1.0f / op.f0 >= 1.0f && 1.0f / op.f0 <= 32768.0f)) return fail(AV1P_EINVAL, "resident-conv weight scale outside [1, 2^15]");
+        if (int rc = make_store_map(&f.out_map[0], buf(op.out), 1024, L.cap)) return rc;
+        if (op.out_lo >= 0)
+          if (int rc = make_store_map(&f.out_map[1], buf(op.out_lo), 1024, L.cap)) return rc;
+        if (op.epi == FC_EPI_ADD_RELU) {
+          if (op.aux < 0 || L.cols[op.aux] != 1024 || (op.aux_lo >= 0 && L.cols[op.aux_lo] != 1024))
+            return fail(AV1P_EINVAL, "resident-conv op needs a 1024-wide residual");
+          if (int rc = make_map_2d(&f.aux_map[0], buf(op.aux), 1024, L.cap, 1024, FC_TILE_M)) return rc;
+          if (int rc = make_map_2d(&f.aux_map[1], buf(op.aux_lo >= 0 ? op.aux_lo : op.aux), 1024, L.cap, 1024, FC_TILE_M)) return rc;
+          f.has_aux_lo = op.aux_lo >= 0 ? 1 : 0;
+        }
         break;
       }
       case AV1P_OP_SAM:
@@ -823,6 +886,19 @@ extern "C" int av1p_fc_forward(const av1p_fc_desc* d, void* stream) {
     f.kb_src[i] = d->kb_src[i];
     f.kb_w[i] = d->kb_w[i];
   }
+  if (d->epi != FC_EPI_HEAD) {
+    if (!d->out_dev || d->out_ld < d->n_tiles * d->block_n) return fail(AV1P_EINVAL, "FC output missing or too narrow");
+    if (int rc = make_store_map(&f.out_map[0], d->out_dev, uint64_t(d->out_ld), uint64_t(d->rows))) return rc;
+    if (d->out_lo_dev)
+      if (int rc = make_store_map(&f.out_map[1], d->out_lo_dev, uint64_t(d->out_ld), uint64_t(d->rows))) return rc;
+  }
+  if (d->epi == FC_EPI_ADD_RELU) {
+    if (!d->aux_dev || d->aux_ld < d->n_tiles * d->block_n) return fail(AV1P_EINVAL, "residual missing or too narrow");
+    if (int rc = make_map_2d(&f.a_map[2], d->aux_dev, uint64_t(d->aux_ld), uint64_t(d->rows), uint64_t(d->aux_ld), FC_TILE_M)) return rc;
+    if (d->aux_lo_dev)
+      if (int rc = make_map_2d(&f.a_map[3], d->aux_lo_dev, uint64_t(d->aux_ld), uint64_t(d->rows), uint64_t(d->aux_ld), FC_TILE_M)) return rc;
+    if (int rc = add_residual_entries(f, d->aux_lo_dev != nullptr)) return rc;
+  }
   const int grid = std::min(g_ctx.sms, ceil_div(d->rows, FC_TILE_M) * d->n_tiles);
   fc_tcgen05_kernel<<<grid, FC_THREADS, FC_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(f);
   CUDA_TRY(cudaGetLastError());
@@ -840,15 +916,21 @@ extern "C" int av1p_conv_res_forward(const av1p_conv_res_desc* d, void* stream) 
   if (int rc = make_map_2d(&f.a_map[0], d->x_dev, 1024, d->rows, 1024, FC_TILE_M)) return rc;
   if (int rc = make_map_2d(&f.a_map[1], d->split ? d->x_lo_dev : d->x_dev, 1024, d->rows, 1024, FC_TILE_M)) return rc;
   if (int rc = make_map_2d(&f.w_map, d->w_dev, 64, uint64_t(d->split ? 2 : 1) * 9 * 64, 64, 64)) return rc;
+  if (int rc = make_store_map(&f.out_map[0], d->out_dev, 1024, uint64_t(d->rows))) return rc;
+  if (d->out_lo_dev)
+    if (int rc = make_store_map(&f.out_map[1], d->out_lo_dev, 1024, uint64_t(d->rows))) return rc;
+  if (d->epi == FC_EPI_ADD_RELU) {
+    if (int rc = make_map_2d(&f.aux_map[0], d->aux_dev, 1024, d->rows, 1024, FC_TILE_M)) return rc;
+    if (int rc = make_map_2d(&f.aux_map[1], d->aux_lo_dev ? d->aux_lo_dev : d->aux_dev, 1024, d->rows, 1024, FC_TILE_M)) return rc;
+    f.has_aux_lo = d->aux_lo_dev ? 1 : 0;
+  }
+  if (!(1.0f / d->acc_scale >= 1.0f && 1.0f / d->acc_scale <= 32768.0f)) return fail(AV1P_EINVAL, "weight scale outside [1, 2^15]");
   f.n_rows_dev = d->n_dev;
   f.n_rows = d->rows;
   f.split = d->split ? 1 : 0;
   f.epi = d->epi;
   f.bias = d->bias_dev;
   f.acc_scale = d->acc_scale;
-  f.aux = static_cast<const __half*>(d->aux_dev);
-  f.aux_lo = static_cast<const __half*>(d->aux_lo_dev);
-  f.aux_ld = 1024;
   f.out = static_cast<__half*>(d->out_dev);
   f.out_lo = static_cast<__half*>(d->out_lo_dev);
   f.out_ld = 1024;

@@ -11,9 +11,17 @@
 // Kernel shape (persistent, warp specialised, one CTA per SM):
 //   warp 0      TMA producer : A tile [128 rows x 64 K] + W tile [block_n x 64 K] per K block
 //   warp 1      MMA issuer   : 4 x tcgen05.mma (M128, N=block_n, K16) per K block, fp32 acc in TMEM
-//   warps 2..9  epilogue     : tcgen05.ld -> bias / residual / ReLU / gate -> fp16 rows to global
-//                              (two warps per TMEM lane quadrant, each takes half of the tile's columns)
-// with a 4-deep smem ring (full/empty mbarriers) and a 2-deep TMEM accumulator ring.
+//   warps 2..9  epilogue     : tcgen05.ld -> bias / ReLU / gate -> fp16 hi/lo -> swizzled smem staging tile
+//   warp 10     store        : one TMA bulk store per staged [128 rows x 32 cols] tile (hi and lo planes)
+// with a 4-deep smem ring (full/empty mbarriers), a 2-deep TMEM accumulator ring and a hi/lo pair of
+// staging tiles (full/free mbarriers).
+//
+// Why the staging: a TMEM lane is an output row, so an epilogue warp holds 32 different rows; storing
+// them straight to global touches 32 cache lines per instruction and the L1 wavefront pipe, not the
+// tensor pipe, bounded the kernel (ncu, round 1: l1tex lsu wavefronts 43-67 % vs tensor 38-47 %).
+// Residual connections never pass through the epilogue either: the identity branch is accumulated
+// on the tensor core as  x . (S I)  (S = the layer's power-of-two weight scale), K block by K block,
+// from the same TMA ring - see FC_W_IDENT.
 #pragma once
 #include <cuda.h>
 #include "ptx_sm100.cuh"
@@ -32,9 +40,17 @@ constexpr int FC_MAX_KB = 128;         // scheduled K blocks per layer (sum over
 constexpr int FC_MAX_SRC = 4;          // activation sources per layer
 constexpr int FC_TAIL_MAX = 4;         // outputs of the in-epilogue final linear
 constexpr int FC_EPI_WARPS = 8;
-constexpr int FC_THREADS = 64 + 32 * FC_EPI_WARPS;
-constexpr int FC_SMEM_BYTES = FC_STAGES * FC_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ +
-                              FC_TAIL_MAX * FC_MAX_N * 4 /*tail weights*/;
+constexpr int FC_THREADS = 64 + 32 * FC_EPI_WARPS + 32;      // producer, MMA, epilogue, store
+constexpr int FC_STORE_WARP = 2 + FC_EPI_WARPS;
+constexpr int EPI_CHUNK = 32;                                // output columns per staging tile
+constexpr int EPI_UNIT_BYTES = FC_TILE_M * EPI_CHUNK * 2;    // 8 KB: [128 rows][64 B], SWIZZLE_64B
+constexpr int EPI_IDENT_BYTES = 512;                         // 16 x 16 fp16 scaled identity, no swizzle
+constexpr int FC_OFF_STAGING = FC_STAGES * FC_STAGE_BYTES;
+constexpr int FC_OFF_IDENT = FC_OFF_STAGING + 2 * EPI_UNIT_BYTES;
+constexpr int FC_OFF_BARS = FC_OFF_IDENT + EPI_IDENT_BYTES;
+constexpr int FC_OFF_TAIL = FC_OFF_BARS + 256;
+constexpr int FC_SMEM_BYTES = FC_OFF_TAIL + FC_TAIL_MAX * FC_MAX_N * 4 + 1024 /*align*/;
+constexpr uint16_t FC_W_IDENT = 0xFFFFu;   // schedule entry: A tile is a residual K block, B is the scaled identity
 
 // Precision.  Operands are fp16, accumulation is fp32 in TMEM.  In split mode ("fp16x3") every
 // activation x is stored as hi = fp16(x), lo = fp16(x - hi), every weight as hi/lo likewise, and the
@@ -44,7 +60,7 @@ constexpr int FC_SMEM_BYTES = FC_STAGES * FC_STAGE_BYTES + 1024 /*align*/ + 256 
 enum FcEpilogue : int {
   FC_EPI_LINEAR = 0,    // out = s*acc + b
   FC_EPI_RELU = 1,      // out = relu(s*acc + b)
-  FC_EPI_ADD_RELU = 2,  // out = relu(acc + b + aux)            (identity residual)
+  FC_EPI_ADD_RELU = 2,  // out = relu(s*acc + b) where acc already holds S * residual (FC_W_IDENT schedule entries)
   FC_EPI_GATE = 3,      // out = aux * sigmoid(acc)             (SE excitation)
   FC_EPI_HEAD = 4,      // h = relu(s*acc + b); logits = h . tail_w^T + tail_b   (fp32, no fp16 store)
 };
@@ -52,6 +68,7 @@ enum FcEpilogue : int {
 struct FcParams {
   CUtensorMap a_map[FC_MAX_SRC]; // activation sources, 2-D [rows][K] fp16, box {64, 128}, SWIZZLE_128B
   CUtensorMap w_map;           // packed weights, 2-D [n_kb_total*block_n][64] fp16, box {64, block_n}
+  CUtensorMap out_map[2];      // output hi / lo planes, 2-D [rows][out_ld] fp16, box {32, 128}, SWIZZLE_64B
   const int* n_rows_dev;       // device-side row count (nullptr -> n_rows)
   int n_rows;
   int n_tiles;                 // number of N tiles
@@ -60,7 +77,7 @@ struct FcParams {
   const float* bias;           // [n_tiles*block_n] or nullptr
   const float* row_scale;      // [rows] or nullptr (spatial-attention scalar folded into the next linear)
   float acc_scale;             // power of two undoing the weight pre-scale
-  const __half* aux;           // residual / gate input rows
+  const __half* aux;           // gate input rows (FC_EPI_GATE only)
   const __half* aux_lo;        // split mode: low part of aux (nullptr otherwise)
   int aux_ld;
   __half* out;
@@ -75,84 +92,129 @@ struct FcParams {
   int* err_flag;
   int kb_begin[FC_MAX_NT + 1]; // schedule range of each N tile
   uint16_t kb_src[FC_MAX_KB];  // bits 14..15: activation source, bits 0..13: K offset / 64
-  uint16_t kb_w[FC_MAX_KB];    // weight chunk ([block_n x 64] tile) index
+  uint16_t kb_w[FC_MAX_KB];    // weight chunk ([block_n x 64] tile) index, or FC_W_IDENT
 };
 
 __device__ __forceinline__ float fast_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
 
-// 32 consecutive fp16 of a row (64 B) as four 16-byte loads
-struct Half32 {
-  uint4 q[4];
+// ------------------------------------------------------------------------------------------------
+// Epilogue staging: two [128 rows x 32 cols] fp16 tiles (hi plane, lo plane) in the SWIZZLE_64B layout
+// a TMA store expects.  full[u] : 8 epilogue warps -> store thread ("tile u is written and fenced");
+// free_[u]: store thread -> epilogue warps ("the bulk store has finished reading tile u").
+struct EpiStage {
+  uint8_t* unit[2];
+  uint64_t* full;    // [2], count FC_EPI_WARPS
+  uint64_t* free_;   // [2], count 1
 };
-__device__ __forceinline__ void ld_half32(Half32& d, const __half* p) {
-  const uint4* s = reinterpret_cast<const uint4*>(p);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) d.q[i] = __ldg(s + i);
+
+// 16 consecutive fp16 of row r (two 16-byte chunks, index 2*half and 2*half+1 of the 64-byte row)
+__device__ __forceinline__ void stage_store16(uint8_t* unit, int r_local, int half, const uint4& a, const uint4& b) {
+  const int sw = (r_local >> 1) & 3;                     // Swizzle<2,4,3>: chunk index ^= address bits [7,9)
+  uint8_t* rowp = unit + r_local * (EPI_CHUNK * 2);
+  *reinterpret_cast<uint4*>(rowp + (((2 * half) ^ sw) << 4)) = a;
+  *reinterpret_cast<uint4*>(rowp + (((2 * half + 1) ^ sw) << 4)) = b;
 }
-__device__ __forceinline__ void zero_half32(Half32& d) {
-#pragma unroll
-  for (int i = 0; i < 4; ++i) d.q[i] = make_uint4(0u, 0u, 0u, 0u);
+
+// 16 x 16 identity scaled by `s` in the no-swizzle K-major core-matrix layout (LBO 128 B, SBO 256 B)
+__device__ __forceinline__ void write_ident_tile(uint8_t* ident, float s, int tid, int nthreads) {
+  for (int i = tid; i < EPI_IDENT_BYTES / 2; i += nthreads) {
+    // element index i -> (16-byte unit u, element e); unit u = (n & 7) + 8 * (k >> 3) + 16 * (n >> 3)
+    const int u = i >> 3, e = i & 7;
+    const int n = (u & 7) + ((u >> 4) << 3), k = (((u >> 3) & 1) << 3) + e;
+    reinterpret_cast<__half*>(ident)[i] = __float2half_rn(n == k ? s : 0.f);
+  }
 }
-__device__ __forceinline__ void add_half32(float (&f)[32], const Half32& d) {
-  const __half2* h = reinterpret_cast<const __half2*>(d.q);
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const float2 v = __half22float2(h[i]);
-    f[2 * i] += v.x;
-    f[2 * i + 1] += v.y;
+__device__ __forceinline__ uint64_t ident_desc(uint32_t ident_addr) { return umma_desc_nosw(ident_addr, 128, 256); }
+
+// Store thread: drain `n_chunks` staged tiles of one accumulator (columns col0 .., rows row0 ..).
+__device__ __forceinline__ void epi_store_chunks(const EpiStage& es, uint32_t& g, const CUtensorMap* map_hi,
+                                                 const CUtensorMap* map_lo, bool has_lo, int col0, int n_chunks, int row0,
+                                                 int* err_flag) {
+  for (int c = 0; c < n_chunks; ++c, ++g) {
+    mbar_wait(&es.full[0], g & 1u, err_flag, 900);
+    tma_store_2d(map_hi, es.unit[0], col0 + c * EPI_CHUNK, row0);
+    tma_store_commit();
+    if (has_lo) {
+      mbar_wait(&es.full[1], g & 1u, err_flag, 901);
+      tma_store_2d(map_lo, es.unit[1], col0 + c * EPI_CHUNK, row0);
+      tma_store_commit();
+      tma_store_wait_read<1>();
+      mbar_arrive(&es.free_[0]);
+      tma_store_wait_read<0>();
+      mbar_arrive(&es.free_[1]);
+    } else {
+      tma_store_wait_read<0>();
+      mbar_arrive(&es.free_[0]);
+    }
   }
 }
 
-// Epilogue of one accumulator tile [128 rows x block_n fp32 columns at TMEM column t_col]: warps 2..9,
-// two warps per TMEM lane quadrant, each takes half of the tile's columns.  Waits on `full`, applies
-// bias / residual / ReLU / gate / in-thread final linear, stores fp16 hi (+lo) rows, then arrives on `empty`.
-// P is FcParams or any struct with the same epilogue members.
+// Epilogue of one accumulator tile [128 rows x block_n fp32 columns at TMEM column t_col]: warps 2..9, two
+// warps per TMEM lane quadrant; both work on the same 32-column chunk (16 columns each).  Waits on `full`,
+// applies scale / bias / gate / ReLU, writes fp16 hi (+lo) either into the staging tiles (whole M tiles) or
+// straight to global (the last, partial M tile: rows past n_rows stay untouched), arrives on `empty` as soon as
+// the last TMEM read has completed.  P is FcParams or any struct with the same epilogue members.
 template <typename P>
-__device__ __forceinline__ void fc_epilogue_tile(const P& p, int n_rows, int mt, int col0, int block_n, uint32_t t_col,
-                                                 uint64_t* full, uint32_t full_phase, uint64_t* empty,
-                                                 const float* tail_w_s, int warp, int lane, int tag) {
-  const int ew = warp - 2;
+__device__ __forceinline__ void epi_tile_store(const P& p, const EpiStage& es, uint32_t& g, int n_rows, int mt, int col0,
+                                               int block_n, uint32_t t_col, uint64_t* full, uint32_t full_phase,
+                                               uint64_t* empty, int warp, int lane, int tag) {
   const int quad = warp & 3;              // TMEM lane quadrant this warp may read
-  const int half = ew >> 2;               // which half of the tile's columns
-  // the in-thread head needs whole rows: there the first four warps take every column
-  const bool whole = (p.epi == FC_EPI_HEAD) || (block_n < 64);
-  const int c_begin = whole ? 0 : half * (block_n / 2);
-  const int c_end = whole ? (half == 0 ? block_n : 0) : c_begin + block_n / 2;
-  const bool needs_aux = (p.epi == FC_EPI_ADD_RELU || p.epi == FC_EPI_GATE);
-  const int row = mt * FC_TILE_M + quad * 32 + lane;
+  const int half = (warp - 2) >> 2;       // which 16 columns of every 32-column chunk
+  const int r_local = quad * 32 + lane;
+  const int row = mt * FC_TILE_M + r_local;
   const bool row_ok = row < n_rows;
+  const bool staged = (mt + 1) * FC_TILE_M <= n_rows;
+  const bool gate = p.epi == FC_EPI_GATE;
+  const bool relu = p.epi == FC_EPI_RELU || p.epi == FC_EPI_ADD_RELU;
+  const bool has_lo = p.out_lo != nullptr;
   const float rs = ((p.row_scale && row_ok) ? p.row_scale[row] : 1.0f) * p.acc_scale;
-  // prefetch the first residual / gate chunk while the MMAs of this tile are still running
-  Half32 ax, axl;
-  zero_half32(ax);
-  zero_half32(axl);
-  if (needs_aux && row_ok && c_begin < c_end) {
-    ld_half32(ax, p.aux + size_t(row) * p.aux_ld + col0 + c_begin);
-    if (p.aux_lo) ld_half32(axl, p.aux_lo + size_t(row) * p.aux_ld + col0 + c_begin);
+  const int n_chunks = block_n / EPI_CHUNK;
+  const int tcol = half * 16;
+  uint4 ax[2], axl[2];
+  ax[0] = ax[1] = axl[0] = axl[1] = make_uint4(0u, 0u, 0u, 0u);
+  if (gate && row_ok) {
+    const uint4* s = reinterpret_cast<const uint4*>(p.aux + size_t(row) * p.aux_ld + col0 + tcol);
+    ax[0] = __ldg(s);
+    ax[1] = __ldg(s + 1);
+    if (p.aux_lo) {
+      const uint4* sl = reinterpret_cast<const uint4*>(p.aux_lo + size_t(row) * p.aux_ld + col0 + tcol);
+      axl[0] = __ldg(sl);
+      axl[1] = __ldg(sl + 1);
+    }
   }
   mbar_wait(full, full_phase, p.err_flag, tag);
   tc_fence_after_sync();
-  const uint32_t t_addr = t_col + (uint32_t(quad * 32) << 16);
-  float tail[FC_TAIL_MAX] = {0.f, 0.f, 0.f, 0.f};
-  for (int c = c_begin; c < c_end; c += 32) {
-    uint32_t v[32];
-    tmem_ld_32x32(t_addr + uint32_t(c), v);
-    // next chunk's residual / gate input goes in flight before this chunk is consumed
-    Half32 nx, nxl;
-    zero_half32(nx);
-    zero_half32(nxl);
-    if (needs_aux && row_ok && c + 32 < c_end) {
-      ld_half32(nx, p.aux + size_t(row) * p.aux_ld + col0 + c + 32);
-      if (p.aux_lo) ld_half32(nxl, p.aux_lo + size_t(row) * p.aux_ld + col0 + c + 32);
+  const uint32_t t_addr = t_col + (uint32_t(quad * 32) << 16) + uint32_t(tcol);
+  for (int c = 0; c < n_chunks; ++c) {
+    const int col = col0 + c * EPI_CHUNK + tcol;
+    uint32_t v[16];
+    tmem_ld_32x16(t_addr + uint32_t(c * EPI_CHUNK), v);
+    uint4 nx[2], nxl[2];
+    nx[0] = nx[1] = nxl[0] = nxl[1] = make_uint4(0u, 0u, 0u, 0u);
+    if (gate && row_ok && c + 1 < n_chunks) {
+      const uint4* s = reinterpret_cast<const uint4*>(p.aux + size_t(row) * p.aux_ld + col + EPI_CHUNK);
+      nx[0] = __ldg(s);
+      nx[1] = __ldg(s + 1);
+      if (p.aux_lo) {
+        const uint4* sl = reinterpret_cast<const uint4*>(p.aux_lo + size_t(row) * p.aux_ld + col + EPI_CHUNK);
+        nxl[0] = __ldg(sl);
+        nxl[1] = __ldg(sl + 1);
+      }
     }
     tmem_ld_wait();
-    float f[32];
+    if (c == n_chunks - 1) {
+      // every TMEM read of this accumulator is complete -> hand it back to the MMA warp
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty);
+    }
+    float f[16];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) * rs;
+    for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) * rs;
     if (p.bias) {
-      const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0 + c);
+      const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < 4; ++i) {
         const float4 b = __ldg(b4 + i);
         f[4 * i + 0] += b.x;
         f[4 * i + 1] += b.y;
@@ -160,25 +222,95 @@ __device__ __forceinline__ void fc_epilogue_tile(const P& p, int n_rows, int mt,
         f[4 * i + 3] += b.w;
       }
     }
-    if (p.epi == FC_EPI_ADD_RELU) {
-      add_half32(f, ax);
-      add_half32(f, axl);
-    } else if (p.epi == FC_EPI_GATE) {
-      float g[32];
+    if (gate) {
+      const __half2* h = reinterpret_cast<const __half2*>(ax);
+      const __half2* hl = reinterpret_cast<const __half2*>(axl);
 #pragma unroll
-      for (int i = 0; i < 32; ++i) g[i] = 0.f;
-      add_half32(g, ax);
-      add_half32(g, axl);
-#pragma unroll
-      for (int i = 0; i < 32; ++i) f[i] = g[i] * fast_sigmoid(f[i]);
+      for (int i = 0; i < 8; ++i) {
+        const float2 a = __half22float2(h[i]), al = __half22float2(hl[i]);
+        f[2 * i] = (a.x + al.x) * fast_sigmoid(f[2 * i]);
+        f[2 * i + 1] = (a.y + al.y) * fast_sigmoid(f[2 * i + 1]);
+      }
+      ax[0] = nx[0]; ax[1] = nx[1]; axl[0] = nxl[0]; axl[1] = nxl[1];
     }
-    ax = nx;
-    axl = nxl;
-    if (p.epi == FC_EPI_RELU || p.epi == FC_EPI_ADD_RELU || p.epi == FC_EPI_HEAD) {
+    if (relu) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
+    }
+    __align__(16) __half2 hi[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) hi[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+    const uint4* hq = reinterpret_cast<const uint4*>(hi);
+    if (staged) {
+      mbar_wait(&es.free_[0], (g & 1u) ^ 1u, p.err_flag, tag + 10);
+      stage_store16(es.unit[0], r_local, half, hq[0], hq[1]);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&es.full[0]);
+    } else if (row_ok) {
+      uint4* o4 = reinterpret_cast<uint4*>(p.out + size_t(row) * p.out_ld + col);
+      o4[0] = hq[0];
+      o4[1] = hq[1];
+    }
+    if (has_lo) {
+      __align__(16) __half2 lo[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float2 hf = __half22float2(hi[i]);
+        lo[i] = __floats2half2_rn(f[2 * i] - hf.x, f[2 * i + 1] - hf.y);
+      }
+      const uint4* lq = reinterpret_cast<const uint4*>(lo);
+      if (staged) {
+        mbar_wait(&es.free_[1], (g & 1u) ^ 1u, p.err_flag, tag + 11);
+        stage_store16(es.unit[1], r_local, half, lq[0], lq[1]);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&es.full[1]);
+      } else if (row_ok) {
+        uint4* l4 = reinterpret_cast<uint4*>(p.out_lo + size_t(row) * p.out_ld + col);
+        l4[0] = lq[0];
+        l4[1] = lq[1];
+      }
+    }
+    if (staged) ++g;
+  }
+}
+
+// Head epilogue (FC_EPI_HEAD): h = relu(s*acc + b), logits = h . tail_w^T + tail_b in the thread that owns the row.
+// The first four epilogue warps take every column; the other four only release the accumulator.
+__device__ __forceinline__ void epi_tile_head(const FcParams& p, int n_rows, int mt, int block_n, uint32_t t_col,
+                                              uint64_t* full, uint32_t full_phase, uint64_t* empty, const float* tail_w_s,
+                                              int warp, int lane, int tag) {
+  const int quad = warp & 3;
+  const int half = (warp - 2) >> 2;
+  const int row = mt * FC_TILE_M + quad * 32 + lane;
+  const bool row_ok = row < n_rows;
+  const float rs = ((p.row_scale && row_ok) ? p.row_scale[row] : 1.0f) * p.acc_scale;
+  mbar_wait(full, full_phase, p.err_flag, tag);
+  tc_fence_after_sync();
+  if (half == 0) {
+    const uint32_t t_addr = t_col + (uint32_t(quad * 32) << 16);
+    float tail[FC_TAIL_MAX] = {0.f, 0.f, 0.f, 0.f};
+    for (int c = 0; c < block_n; c += 32) {
+      uint32_t v[32];
+      tmem_ld_32x32(t_addr + uint32_t(c), v);
+      tmem_ld_wait();
+      float f[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) * rs;
+      if (p.bias) {
+        const float4* b4 = reinterpret_cast<const float4*>(p.bias + c);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 b = __ldg(b4 + i);
+          f[4 * i + 0] += b.x;
+          f[4 * i + 1] += b.y;
+          f[4 * i + 2] += b.z;
+          f[4 * i + 3] += b.w;
+        }
+      }
 #pragma unroll
       for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
-    }
-    if (p.epi == FC_EPI_HEAD) {
 #pragma unroll
       for (int j = 0; j < FC_TAIL_MAX; ++j) {
         if (j < p.tail_n) {
@@ -189,28 +321,13 @@ __device__ __forceinline__ void fc_epilogue_tile(const P& p, int n_rows, int mt,
           tail[j] = t;
         }
       }
-    } else if (row_ok) {
-      __align__(16) __half h[32];
+    }
+    if (row_ok) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) h[i] = __float2half_rn(f[i]);
-      uint4* o4 = reinterpret_cast<uint4*>(p.out + size_t(row) * p.out_ld + col0 + c);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) o4[i] = reinterpret_cast<const uint4*>(h)[i];
-      if (p.out_lo) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) h[i] = __float2half_rn(f[i] - __half2float(h[i]));
-        uint4* l4 = reinterpret_cast<uint4*>(p.out_lo + size_t(row) * p.out_ld + col0 + c);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) l4[i] = reinterpret_cast<const uint4*>(h)[i];
-      }
+      for (int j = 0; j < FC_TAIL_MAX; ++j)
+        if (j < p.tail_n) p.logits[size_t(row) * p.tail_n + j] = tail[j] + p.tail_b[j];
     }
   }
-  if (p.epi == FC_EPI_HEAD && row_ok && c_begin < c_end) {
-#pragma unroll
-    for (int j = 0; j < FC_TAIL_MAX; ++j)
-      if (j < p.tail_n) p.logits[size_t(row) * p.tail_n + j] = tail[j] + p.tail_b[j];
-  }
-  // all TMEM reads of this accumulator are complete (tmem_ld_wait above) -> hand it back
   tc_fence_before_sync();
   __syncwarp();
   if (lane == 0) mbar_arrive(empty);
@@ -220,12 +337,19 @@ __global__ void __launch_bounds__(FC_THREADS, 1) fc_tcgen05_kernel(const __grid_
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + FC_STAGES * FC_STAGE_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + FC_OFF_BARS);
   uint64_t* empty_bar = full_bar + FC_STAGES;
   uint64_t* acc_full = empty_bar + FC_STAGES;   // [2]
   uint64_t* acc_empty = acc_full + 2;           // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-  float* tail_w_s = reinterpret_cast<float*>(smem + FC_STAGES * FC_STAGE_BYTES + 256);
+  uint64_t* stg_full = acc_empty + 2;           // [2]
+  uint64_t* stg_free = stg_full + 2;            // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stg_free + 2);
+  float* tail_w_s = reinterpret_cast<float*>(smem + FC_OFF_TAIL);
+  EpiStage es;
+  es.unit[0] = smem + FC_OFF_STAGING;
+  es.unit[1] = smem + FC_OFF_STAGING + EPI_UNIT_BYTES;
+  es.full = stg_full;
+  es.free_ = stg_free;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -237,6 +361,8 @@ __global__ void __launch_bounds__(FC_THREADS, 1) fc_tcgen05_kernel(const __grid_
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < FC_MAX_SRC; ++i) tma_prefetch_desc(&p.a_map[i]);
     tma_prefetch_desc(&p.w_map);
+    if (p.out) tma_prefetch_desc(&p.out_map[0]);
+    if (p.out_lo) tma_prefetch_desc(&p.out_map[1]);
     for (int s = 0; s < FC_STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -244,6 +370,8 @@ __global__ void __launch_bounds__(FC_THREADS, 1) fc_tcgen05_kernel(const __grid_
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
       mbar_init(&acc_empty[s], FC_EPI_WARPS);
+      mbar_init(&stg_full[s], FC_EPI_WARPS);
+      mbar_init(&stg_free[s], 1);
     }
     fence_mbar_init();
   }
@@ -254,6 +382,8 @@ __global__ void __launch_bounds__(FC_THREADS, 1) fc_tcgen05_kernel(const __grid_
   if (p.epi == FC_EPI_HEAD) {
     for (int i = threadIdx.x; i < p.tail_n * p.block_n; i += FC_THREADS) tail_w_s[i] = p.tail_w[i];
   }
+  write_ident_tile(smem + FC_OFF_IDENT, 1.0f / p.acc_scale, threadIdx.x, FC_THREADS);
+  fence_proxy_async_smem();       // identity tile: generic stores, read by tcgen05.mma
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -270,11 +400,12 @@ __global__ void __launch_bounds__(FC_THREADS, 1) fc_tcgen05_kernel(const __grid_
         const int nt = item - mt * p.n_tiles;
         for (int kb = p.kb_begin[nt]; kb < p.kb_begin[nt + 1]; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1u, p.err_flag, 100 + stage);
-          mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
           const uint32_t e = p.kb_src[kb];
+          const uint32_t wi = p.kb_w[kb];
           uint8_t* a_dst = smem + stage * FC_STAGE_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], wi == FC_W_IDENT ? uint32_t(FC_A_BYTES) : tx_bytes);
           tma_load_2d(a_dst, &p.a_map[e >> 14], &full_bar[stage], int(e & 0x3FFFu) * FC_TILE_K, mt * FC_TILE_M);
-          tma_load_2d(a_dst + FC_A_BYTES, &p.w_map, &full_bar[stage], 0, int(p.kb_w[kb]) * p.block_n);
+          if (wi != FC_W_IDENT) tma_load_2d(a_dst + FC_A_BYTES, &p.w_map, &full_bar[stage], 0, int(wi) * p.block_n);
           if (++stage == FC_STAGES) {
             stage = 0;
             phase ^= 1u;
@@ -290,6 +421,8 @@ __global__ void __launch_bounds__(FC_THREADS, 1) fc_tcgen05_kernel(const __grid_
       int acc = 0;
       uint32_t acc_phase = 0;
       const uint32_t idesc = umma_idesc_f16(uint32_t(p.block_n));
+      const uint32_t idesc_id = umma_idesc_f16(16u);
+      const uint64_t id_desc = ident_desc(base + FC_OFF_IDENT);
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int nt = item % p.n_tiles;
         mbar_wait(&acc_empty[acc], acc_phase ^ 1u, p.err_flag, 200 + acc);
@@ -303,7 +436,15 @@ __global__ void __launch_bounds__(FC_THREADS, 1) fc_tcgen05_kernel(const __grid_
           tc_fence_after_sync();
           const uint32_t a_addr = base + stage * FC_STAGE_BYTES;
           const uint32_t w_addr = a_addr + FC_A_BYTES;
-          if (!p.pair_mode) {
+          if (p.kb_w[kb] == FC_W_IDENT) {
+            // residual K block: acc[:, c0 .. c0+63] += A . (S I), 16 columns per instruction.  These entries
+            // close a tile's schedule, so the accumulator already holds data.
+            const uint32_t c0 = (uint32_t(p.kb_src[kb]) & 0x3FFFu) * FC_TILE_K - uint32_t(nt * p.block_n);
+#pragma unroll
+            for (int j = 0; j < FC_TILE_K / 16; ++j)
+              umma_f16_ss(d_tmem + c0 + j * 16, umma_desc_sw128(a_addr + j * 32), id_desc, idesc_id, 1u);
+            umma_commit(&empty_bar[stage]);
+          } else if (!p.pair_mode) {
 #pragma unroll
             for (int k = 0; k < FC_TILE_K / 16; ++k)
               umma_f16_ss(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(w_addr + k * 32), idesc,
@@ -341,19 +482,37 @@ __global__ void __launch_bounds__(FC_THREADS, 1) fc_tcgen05_kernel(const __grid_
         }
       }
     }
-  } else {
+  } else if (warp < FC_STORE_WARP) {
     // ------------------------------------------------------------ epilogue (warps 2..9)
     int acc = 0;
     uint32_t acc_phase = 0;
+    uint32_t g = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int mt = item / p.n_tiles;
       const int nt = item - mt * p.n_tiles;
-      fc_epilogue_tile(p, n_rows, mt, nt * p.block_n, p.block_n, tmem_base + uint32_t(acc * FC_MAX_N), &acc_full[acc],
-                       acc_phase, &acc_empty[acc], tail_w_s, warp, lane, 400 + acc);
+      const uint32_t t_col = tmem_base + uint32_t(acc * FC_MAX_N);
+      if (p.epi == FC_EPI_HEAD)
+        epi_tile_head(p, n_rows, mt, p.block_n, t_col, &acc_full[acc], acc_phase, &acc_empty[acc], tail_w_s, warp, lane, 400 + acc);
+      else
+        epi_tile_store(p, es, g, n_rows, mt, nt * p.block_n, p.block_n, t_col, &acc_full[acc], acc_phase, &acc_empty[acc], warp,
+                       lane, 400 + acc);
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1u;
       }
+    }
+  } else {
+    // ------------------------------------------------------------ store warp: staged tiles -> global (TMA)
+    if (lane == 0 && p.epi != FC_EPI_HEAD) {
+      uint32_t g = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int mt = item / p.n_tiles;
+        const int nt = item - mt * p.n_tiles;
+        if ((mt + 1) * FC_TILE_M > n_rows) continue;      // partial tile: the epilogue stores it directly
+        epi_store_chunks(es, g, &p.out_map[0], &p.out_map[1], p.out_lo != nullptr, nt * p.block_n, p.block_n / EPI_CHUNK,
+                         mt * FC_TILE_M, p.err_flag);
+      }
+      tma_store_wait_all<0>();
     }
   }
 

@@ -132,7 +132,7 @@ def _make_fc_op_n(name: str, dense: Sequence[np.ndarray], srcs: Sequence[str], o
     n_tiles = n_pad // block_n
     assert n_tiles <= MAX_NT and block_n % 32 == 0 and block_n <= 256
     wmax = max(float(np.abs(d).max()) for d in dense)
-    scale = 2.0 ** int(np.clip(np.floor(np.log2(8192.0 / wmax)), 0, 16)) if wmax > 0 else 1.0
+    scale = 2.0 ** int(np.clip(np.floor(np.log2(8192.0 / wmax)), 0, 15)) if wmax > 0 else 1.0
     split = precision == "fp16x3"
     chunks, kb_begin, kb_src, kb_w = [], [0], [], []
     for t in range(n_tiles):
@@ -222,7 +222,7 @@ def make_conv_res_op(name: str, wf: np.ndarray, bf: np.ndarray, src: str, out: s
     of horizontally adjacent output positions are consecutive rows of one B operand; hi (+ lo) fp16 planes."""
     assert wf.shape == (64, 64, 3, 3) and BUF_COLS[src] == 1024 and BUF_COLS[out] == 1024
     wmax = float(np.abs(wf).max())
-    scale = 2.0 ** int(np.clip(np.floor(np.log2(8192.0 / wmax)), 0, 16)) if wmax > 0 else 1.0
+    scale = 2.0 ** int(np.clip(np.floor(np.log2(8192.0 / wmax)), 0, 15)) if wmax > 0 else 1.0
     taps = np.stack([wf[:, :, ky, 2 - j] for ky in range(3) for j in range(3)]) * scale     # [9, co, ci]
     if np.abs(taps).max() >= 65504.0:
         raise ValueError(f"{name}: folded weight does not fit fp16")
@@ -246,7 +246,7 @@ def backbone_ops(sd, precision: str = "fp16x3", prefix: str = "backbone.", layer
     #     M operand of the stem GEMM: K padded to 64, rows stacked twice (M = 128), fp16 hi / lo planes.
     w, b = fold_bn(_np64(sd[p + "conv1.weight"]), None, sd, p + "bn1")
     w = w.reshape(64, 49)
-    scale = 2.0 ** int(np.clip(np.floor(np.log2(8192.0 / np.abs(w).max())), 0, 16))
+    scale = 2.0 ** int(np.clip(np.floor(np.log2(8192.0 / np.abs(w).max())), 0, 15))
     wk = np.zeros((128, 64), dtype=np.float64)
     wk[:64, :49] = w * scale
     wk[64:] = wk[:64]
