@@ -135,18 +135,24 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_res_tcgen05_kernel(const _
   //                                       for every output row oy of the half whose last input row is iy:
   //                                           (residual only) for ox in 0..3: aux tile (oy,ox) hi[, lo] }
   if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer
-    if (lane == 0 && blockIdx.x < m_tiles) {
+    // ------------------------------------------------------------ TMA producer (warp-uniform loop, one lane issues)
+    if (blockIdx.x < m_tiles) {
       // resident weights first: planes x 9 tiles of 8 KB on one barrier
-      mbar_arrive_expect_tx(w_bar, uint32_t(planes * CR_W_PLANE_BYTES));
-      for (int t = 0; t < planes * 9; ++t)
-        tma_load_2d(smem + CR_OFF_W + t * CR_W_TILE_BYTES, &p.w_map, w_bar, 0, t * 64);
+      if (elect_one_sync()) {
+        mbar_arrive_expect_tx(w_bar, uint32_t(planes * CR_W_PLANE_BYTES));
+        for (int t = 0; t < planes * 9; ++t)
+          tma_load_2d(smem + CR_OFF_W + t * CR_W_TILE_BYTES, &p.w_map, w_bar, 0, t * 64);
+      }
+      __syncwarp();
       int stage = 0;
       uint32_t phase = 0;
       auto load = [&](const CUtensorMap* map, int pos, int mt) {
         mbar_wait(&empty_bar[stage], phase ^ 1u, p.err_flag, 100 + stage);
-        mbar_arrive_expect_tx(&full_bar[stage], CR_A_BYTES);
-        tma_load_2d(smem + stage * CR_A_BYTES, map, &full_bar[stage], pos * FC_TILE_K, mt * FC_TILE_M);
+        if (elect_one_sync()) {
+          mbar_arrive_expect_tx(&full_bar[stage], CR_A_BYTES);
+          tma_load_2d(smem + stage * CR_A_BYTES, map, &full_bar[stage], pos * FC_TILE_K, mt * FC_TILE_M);
+        }
+        __syncwarp();
         if (++stage == CR_STAGES) {
           stage = 0;
           phase ^= 1u;
@@ -169,8 +175,8 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_res_tcgen05_kernel(const _
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer
-    if (lane == 0 && blockIdx.x < m_tiles) {
+    // ------------------------------------------------------------ MMA issuer (warp-uniform loop, one lane issues)
+    if (blockIdx.x < m_tiles) {
       int stage = 0;
       uint32_t phase = 0;
       uint32_t acc_phase = 0u;               // bit s: parity of accumulator slot s
@@ -181,8 +187,7 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_res_tcgen05_kernel(const _
         tc_fence_after_sync();
         return base + stage * CR_A_BYTES;
       };
-      auto release = [&]() {                 // frees the ring slot once the MMAs issued so far have read it
-        umma_commit(&empty_bar[stage]);
+      auto advance = [&]() {
         if (++stage == CR_STAGES) {
           stage = 0;
           phase ^= 1u;
@@ -200,44 +205,57 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_res_tcgen05_kernel(const _
               const int ox1 = ix < 3 ? ix + 1 : 3;
               for (int pl = 0; pl < planes; ++pl) {
                 const uint32_t a_addr = acquire();
+                // accumulator slots this tile feeds must have been drained by the epilogue
                 for (int oy = 2 * h; oy < 2 * h + 2; ++oy) {
                   const int ky = iy - oy + 1;
-                  if (ky < 0 || ky > 2) continue;
                   const int slot = oy & 1;
-                  if (!((acquired >> slot) & 1u)) {
-                    mbar_wait(&acc_empty[slot], ((acc_phase >> slot) & 1u) ^ 1u, p.err_flag, 200 + slot);
-                    tc_fence_after_sync();
-                    acquired |= 1u << slot;
-                  }
-                  // the lo plane always accumulates (its hi twin ran first); the hi plane starts positions
-                  // whose accumulator is still empty
-                  const uint32_t im = pl ? 0xFu : ((init_mask >> (4 * slot)) & 0xFu);
-                  // runs of output positions with the same accumulate state -> one MMA group each
-                  int ox = ox0;
-                  while (ox <= ox1) {
-                    const uint32_t st = (im >> ox) & 1u;
-                    int oe = ox;
-                    while (oe + 1 <= ox1 && ((im >> (oe + 1)) & 1u) == st) ++oe;
-                    const uint32_t n = uint32_t(oe - ox + 1) * 64u;
-                    const uint32_t idesc = umma_idesc_f16(n);
-                    const uint32_t d_tmem = tmem_base + uint32_t(slot * 256 + ox * 64);
-                    // taps for ox..oe are kx = ix-ox+1 .. ix-oe+1 (descending) = rows (2-kx_first)*64.. of the ky stack
-                    const uint32_t w_hi = w_base + uint32_t(ky * 3 + (2 - (ix - ox + 1))) * CR_W_TILE_BYTES;
-                    const uint32_t w_lo = w_hi + CR_W_PLANE_BYTES;
-#pragma unroll
-                    for (int k = 0; k < FC_TILE_K / 16; ++k)
-                      umma_f16_ss(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(w_hi + k * 32), idesc,
-                                  (st || k > 0) ? 1u : 0u);
-                    if (p.split && pl == 0) {
+                  if (ky < 0 || ky > 2 || ((acquired >> slot) & 1u)) continue;
+                  mbar_wait(&acc_empty[slot], ((acc_phase >> slot) & 1u) ^ 1u, p.err_flag, 200 + slot);
+                  tc_fence_after_sync();
+                  acquired |= 1u << slot;
+                }
+                if (elect_one_sync()) {
+                  for (int oy = 2 * h; oy < 2 * h + 2; ++oy) {
+                    const int ky = iy - oy + 1;
+                    if (ky < 0 || ky > 2) continue;
+                    const int slot = oy & 1;
+                    // the lo plane always accumulates (its hi twin ran first); the hi plane starts positions
+                    // whose accumulator is still empty
+                    const uint32_t im = pl ? 0xFu : ((init_mask >> (4 * slot)) & 0xFu);
+                    // runs of output positions with the same accumulate state -> one MMA group each
+                    int ox = ox0;
+                    while (ox <= ox1) {
+                      const uint32_t st = (im >> ox) & 1u;
+                      int oe = ox;
+                      while (oe + 1 <= ox1 && ((im >> (oe + 1)) & 1u) == st) ++oe;
+                      const uint32_t n = uint32_t(oe - ox + 1) * 64u;
+                      const uint32_t idesc = umma_idesc_f16(n);
+                      const uint32_t d_tmem = tmem_base + uint32_t(slot * 256 + ox * 64);
+                      // taps for ox..oe are kx = ix-ox+1 .. ix-oe+1 (descending) = rows (2-kx_first)*64.. of the ky stack
+                      const uint32_t w_hi = w_base + uint32_t(ky * 3 + (2 - (ix - ox + 1))) * CR_W_TILE_BYTES;
+                      const uint32_t w_lo = w_hi + CR_W_PLANE_BYTES;
 #pragma unroll
                       for (int k = 0; k < FC_TILE_K / 16; ++k)
-                        umma_f16_ss(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(w_lo + k * 32), idesc, 1u);
+                        umma_f16_ss(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(w_hi + k * 32), idesc,
+                                    (st || k > 0) ? 1u : 0u);
+                      if (p.split && pl == 0) {
+#pragma unroll
+                        for (int k = 0; k < FC_TILE_K / 16; ++k)
+                          umma_f16_ss(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(w_lo + k * 32), idesc, 1u);
+                      }
+                      ox = oe + 1;
                     }
-                    ox = oe + 1;
                   }
-                  if (pl == 0) init_mask |= ((1u << (ox1 + 1)) - (1u << ox0)) << (4 * slot);
+                  umma_commit(&empty_bar[stage]);   // frees the ring slot once these MMAs have read it
                 }
-                release();
+                __syncwarp();
+                if (pl == 0) {
+                  for (int oy = 2 * h; oy < 2 * h + 2; ++oy) {
+                    const int ky = iy - oy + 1;
+                    if (ky >= 0 && ky <= 2) init_mask |= ((1u << (ox1 + 1)) - (1u << ox0)) << (4 * (oy & 1));
+                  }
+                }
+                advance();
               }
             }
             // output row complete once its last input row (oy + 1, clamped) has been consumed
@@ -248,15 +266,20 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_res_tcgen05_kernel(const _
                 for (int ox = 0; ox < 4; ++ox) {
                   for (int pl = 0; pl < aux_planes; ++pl) {
                     const uint32_t a_addr = acquire();
-                    const uint32_t d_tmem = tmem_base + uint32_t(slot * 256 + ox * 64);
+                    if (elect_one_sync()) {
+                      const uint32_t d_tmem = tmem_base + uint32_t(slot * 256 + ox * 64);
 #pragma unroll
-                    for (int j = 0; j < FC_TILE_K / 16; ++j)
-                      umma_f16_ss(d_tmem + j * 16, umma_desc_sw128(a_addr + j * 32), id_desc, idesc_id, 1u);
-                    release();
+                      for (int j = 0; j < FC_TILE_K / 16; ++j)
+                        umma_f16_ss(d_tmem + j * 16, umma_desc_sw128(a_addr + j * 32), id_desc, idesc_id, 1u);
+                      umma_commit(&empty_bar[stage]);
+                    }
+                    __syncwarp();
+                    advance();
                   }
                 }
               }
-              umma_commit(&acc_full[slot]);
+              if (elect_one_sync()) umma_commit(&acc_full[slot]);
+              __syncwarp();
               acc_phase ^= 1u << slot;
             }
           }
@@ -277,15 +300,14 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_res_tcgen05_kernel(const _
     }
   } else {
     // ------------------------------------------------------------ store warp
-    if (lane == 0) {
-      uint32_t g = 0;
-      for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x) {
-        if ((mt + 1) * FC_TILE_M > n_rows) continue;
-        epi_store_chunks(es, g, &p.out_map[0], &p.out_map[1], p.out_lo != nullptr, 0, 1024 / EPI_CHUNK, mt * FC_TILE_M,
-                         p.err_flag);
-      }
-      tma_store_wait_all<0>();
+    uint32_t g = 0;
+    for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x) {
+      if ((mt + 1) * FC_TILE_M > n_rows) continue;
+      epi_store_chunks(es, g, &p.out_map[0], &p.out_map[1], p.out_lo != nullptr, 0, 1024 / EPI_CHUNK, mt * FC_TILE_M,
+                       p.err_flag);
     }
+    if (lane == 0) tma_store_wait_all<0>();
+    __syncwarp();
   }
 
   tc_fence_before_sync();

@@ -126,26 +126,34 @@ __device__ __forceinline__ void write_ident_tile(uint8_t* ident, float s, int ti
 }
 __device__ __forceinline__ uint64_t ident_desc(uint32_t ident_addr) { return umma_desc_nosw(ident_addr, 128, 256); }
 
-// Store thread: drain `n_chunks` staged tiles of one accumulator (columns col0 .., rows row0 ..).
+// Store warp: drain `n_chunks` staged tiles of one accumulator (columns col0 .., rows row0 ..).  The whole warp
+// walks the loop; the bulk stores, their commit groups and the read-completion waits are all issued by lane 0
+// (bulk async-groups are per-thread state, so one fixed lane must own them).
 __device__ __forceinline__ void epi_store_chunks(const EpiStage& es, uint32_t& g, const CUtensorMap* map_hi,
                                                  const CUtensorMap* map_lo, bool has_lo, int col0, int n_chunks, int row0,
                                                  int* err_flag) {
+  const bool leader = (threadIdx.x & 31) == 0;
   for (int c = 0; c < n_chunks; ++c, ++g) {
     mbar_wait(&es.full[0], g & 1u, err_flag, 900);
-    tma_store_2d(map_hi, es.unit[0], col0 + c * EPI_CHUNK, row0);
-    tma_store_commit();
+    if (leader) {
+      tma_store_2d(map_hi, es.unit[0], col0 + c * EPI_CHUNK, row0);
+      tma_store_commit();
+    }
     if (has_lo) {
       mbar_wait(&es.full[1], g & 1u, err_flag, 901);
-      tma_store_2d(map_lo, es.unit[1], col0 + c * EPI_CHUNK, row0);
-      tma_store_commit();
-      tma_store_wait_read<1>();
-      mbar_arrive(&es.free_[0]);
-      tma_store_wait_read<0>();
-      mbar_arrive(&es.free_[1]);
-    } else {
+      if (leader) {
+        tma_store_2d(map_lo, es.unit[1], col0 + c * EPI_CHUNK, row0);
+        tma_store_commit();
+        tma_store_wait_read<1>();
+        mbar_arrive(&es.free_[0]);
+        tma_store_wait_read<0>();
+        mbar_arrive(&es.free_[1]);
+      }
+    } else if (leader) {
       tma_store_wait_read<0>();
       mbar_arrive(&es.free_[0]);
     }
+    __syncwarp();
   }
 }
 
@@ -390,53 +398,56 @@ __global__ void __launch_bounds__(FC_THREADS, 1) fc_tcgen05_kernel(const __grid_
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      const uint32_t tx_bytes = FC_A_BYTES + p.block_n * FC_TILE_K * 2;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int mt = item / p.n_tiles;
-        const int nt = item - mt * p.n_tiles;
-        for (int kb = p.kb_begin[nt]; kb < p.kb_begin[nt + 1]; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1u, p.err_flag, 100 + stage);
-          const uint32_t e = p.kb_src[kb];
-          const uint32_t wi = p.kb_w[kb];
-          uint8_t* a_dst = smem + stage * FC_STAGE_BYTES;
+    // ------------------------------------------------------------ TMA producer (warp-uniform loop, one lane issues)
+    int stage = 0;
+    uint32_t phase = 0;
+    const uint32_t tx_bytes = FC_A_BYTES + p.block_n * FC_TILE_K * 2;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int mt = item / p.n_tiles;
+      const int nt = item - mt * p.n_tiles;
+      for (int kb = p.kb_begin[nt]; kb < p.kb_begin[nt + 1]; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1u, p.err_flag, 100 + stage);
+        const uint32_t e = p.kb_src[kb];
+        const uint32_t wi = p.kb_w[kb];
+        uint8_t* a_dst = smem + stage * FC_STAGE_BYTES;
+        if (elect_one_sync()) {
           mbar_arrive_expect_tx(&full_bar[stage], wi == FC_W_IDENT ? uint32_t(FC_A_BYTES) : tx_bytes);
           tma_load_2d(a_dst, &p.a_map[e >> 14], &full_bar[stage], int(e & 0x3FFFu) * FC_TILE_K, mt * FC_TILE_M);
           if (wi != FC_W_IDENT) tma_load_2d(a_dst + FC_A_BYTES, &p.w_map, &full_bar[stage], 0, int(wi) * p.block_n);
-          if (++stage == FC_STAGES) {
-            stage = 0;
-            phase ^= 1u;
-          }
+        }
+        __syncwarp();
+        if (++stage == FC_STAGES) {
+          stage = 0;
+          phase ^= 1u;
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      const uint32_t idesc = umma_idesc_f16(uint32_t(p.block_n));
-      const uint32_t idesc_id = umma_idesc_f16(16u);
-      const uint64_t id_desc = ident_desc(base + FC_OFF_IDENT);
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int nt = item % p.n_tiles;
-        mbar_wait(&acc_empty[acc], acc_phase ^ 1u, p.err_flag, 200 + acc);
+    // ------------------------------------------------------------ MMA issuer (warp-uniform loop, one lane issues)
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const uint32_t idesc = umma_idesc_f16(uint32_t(p.block_n));
+    const uint32_t idesc_id = umma_idesc_f16(16u);
+    const uint64_t id_desc = ident_desc(base + FC_OFF_IDENT);
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int nt = item % p.n_tiles;
+      mbar_wait(&acc_empty[acc], acc_phase ^ 1u, p.err_flag, 200 + acc);
+      tc_fence_after_sync();
+      const uint32_t d_tmem = tmem_base + uint32_t(acc * FC_MAX_N);
+      const int kb0 = p.kb_begin[nt], kb1 = p.kb_begin[nt + 1];
+      uint32_t prev_a = 0, prev_w = 0;
+      int prev_stage = 0;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&full_bar[stage], phase, p.err_flag, 300 + stage);
         tc_fence_after_sync();
-        const uint32_t d_tmem = tmem_base + uint32_t(acc * FC_MAX_N);
-        const int kb0 = p.kb_begin[nt], kb1 = p.kb_begin[nt + 1];
-        uint32_t prev_a = 0, prev_w = 0;
-        int prev_stage = 0;
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&full_bar[stage], phase, p.err_flag, 300 + stage);
-          tc_fence_after_sync();
-          const uint32_t a_addr = base + stage * FC_STAGE_BYTES;
-          const uint32_t w_addr = a_addr + FC_A_BYTES;
-          if (p.kb_w[kb] == FC_W_IDENT) {
+        const uint32_t a_addr = base + stage * FC_STAGE_BYTES;
+        const uint32_t w_addr = a_addr + FC_A_BYTES;
+        const bool ident = p.kb_w[kb] == FC_W_IDENT;
+        const bool first_of_pair = p.pair_mode && !ident && ((kb - kb0) & 1) == 0;
+        if (elect_one_sync()) {
+          if (ident) {
             // residual K block: acc[:, c0 .. c0+63] += A . (S I), 16 columns per instruction.  These entries
             // close a tile's schedule, so the accumulator already holds data.
             const uint32_t c0 = (uint32_t(p.kb_src[kb]) & 0x3FFFu) * FC_TILE_K - uint32_t(nt * p.block_n);
@@ -450,15 +461,12 @@ __global__ void __launch_bounds__(FC_THREADS, 1) fc_tcgen05_kernel(const __grid_
               umma_f16_ss(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(w_addr + k * 32), idesc,
                           (kb > kb0 || k > 0) ? 1u : 0u);
             umma_commit(&empty_bar[stage]);   // frees the smem slot once these MMAs have read it
-          } else if (((kb - kb0) & 1) == 0) {
+          } else if (first_of_pair) {
             // (x_hi, w_hi): the slot stays live until the cross products of the next entry are done
 #pragma unroll
             for (int k = 0; k < FC_TILE_K / 16; ++k)
               umma_f16_ss(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(w_addr + k * 32), idesc,
                           (kb > kb0 || k > 0) ? 1u : 0u);
-            prev_a = a_addr;
-            prev_w = w_addr;
-            prev_stage = stage;
           } else {
             // this slot holds (x_lo, w_lo): issue x_hi * w_lo and x_lo * w_hi
 #pragma unroll
@@ -470,16 +478,22 @@ __global__ void __launch_bounds__(FC_THREADS, 1) fc_tcgen05_kernel(const __grid_
             umma_commit(&empty_bar[prev_stage]);
             umma_commit(&empty_bar[stage]);
           }
-          if (++stage == FC_STAGES) {
-            stage = 0;
-            phase ^= 1u;
-          }
+          if (kb + 1 == kb1) umma_commit(&acc_full[acc]);   // accumulator complete -> epilogue
         }
-        umma_commit(&acc_full[acc]);        // accumulator complete -> epilogue
-        if (++acc == 2) {
-          acc = 0;
-          acc_phase ^= 1u;
+        __syncwarp();
+        if (first_of_pair) {
+          prev_a = a_addr;
+          prev_w = w_addr;
+          prev_stage = stage;
         }
+        if (++stage == FC_STAGES) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1u;
       }
     }
   } else if (warp < FC_STORE_WARP) {
@@ -503,7 +517,7 @@ __global__ void __launch_bounds__(FC_THREADS, 1) fc_tcgen05_kernel(const __grid_
     }
   } else {
     // ------------------------------------------------------------ store warp: staged tiles -> global (TMA)
-    if (lane == 0 && p.epi != FC_EPI_HEAD) {
+    if (p.epi != FC_EPI_HEAD) {
       uint32_t g = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int mt = item / p.n_tiles;
@@ -512,7 +526,8 @@ __global__ void __launch_bounds__(FC_THREADS, 1) fc_tcgen05_kernel(const __grid_
         epi_store_chunks(es, g, &p.out_map[0], &p.out_map[1], p.out_lo != nullptr, nt * p.block_n, p.block_n / EPI_CHUNK,
                          mt * FC_TILE_M, p.err_flag);
       }
-      tma_store_wait_all<0>();
+      if (lane == 0) tma_store_wait_all<0>();
+      __syncwarp();
     }
   }
 

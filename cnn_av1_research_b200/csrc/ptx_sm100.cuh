@@ -13,6 +13,23 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// One lane of a fully converged warp.  The single-thread instructions (tcgen05.mma / commit, TMA) take
+// uniform-register operands: issued under `if (lane == 0)` the compiler cannot prove uniformity and wraps
+// every one of them in an election loop (ELECT / BRA.U.ANY, ~190 cycles per MMA measured with ncu, i.e.
+// the issuing thread, not the tensor pipe, paced the kernels).  Role loops therefore run on all 32 lanes
+// with warp-uniform state and only the issue itself sits under elect_one_sync().
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

@@ -205,16 +205,16 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_tc_kernel(const __grid_con
       }
     }
   } else if (warp == ST_PRODUCERS / 32) {
-    // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      int stage = 0, acc = 0;
-      uint32_t phase = 0, acc_phase = 0;
-      const uint32_t idesc = umma_idesc_f16(ST_N);
-      const uint32_t a_hi = smem_u32(w_hi), a_lo = smem_u32(w_lo);
-      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        mbar_wait(&acc_empty[acc], acc_phase ^ 1u, p.err_flag, 600 + acc);
-        mbar_wait(&full_bar[stage], phase, p.err_flag, 700 + stage);
-        tc_fence_after_sync();
+    // ------------------------------------------------------------ MMA issuer (warp-uniform loop, one lane issues)
+    int stage = 0, acc = 0;
+    uint32_t phase = 0, acc_phase = 0;
+    const uint32_t idesc = umma_idesc_f16(ST_N);
+    const uint32_t a_hi = smem_u32(w_hi), a_lo = smem_u32(w_lo);
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      mbar_wait(&acc_empty[acc], acc_phase ^ 1u, p.err_flag, 600 + acc);
+      mbar_wait(&full_bar[stage], phase, p.err_flag, 700 + stage);
+      tc_fence_after_sync();
+      if (elect_one_sync()) {
         const uint32_t d_tmem = tmem_base + uint32_t(acc * ST_N);
         const uint32_t b_hi = smem_u32(stages + stage * ST_STAGE_BYTES), b_lo = b_hi + ST_P_BYTES;
 #pragma unroll
@@ -228,14 +228,15 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_tc_kernel(const __grid_con
           umma_f16_ss(d_tmem, umma_desc_sw128(a_lo + k * 32), umma_desc_sw128(b_hi + k * 32), idesc, 1u);
         umma_commit(&empty_bar[stage]);
         umma_commit(&acc_full[acc]);
-        if (++stage == ST_STAGES) {
-          stage = 0;
-          phase ^= 1u;
-        }
-        if (++acc == 2) {
-          acc = 0;
-          acc_phase ^= 1u;
-        }
+      }
+      __syncwarp();
+      if (++stage == ST_STAGES) {
+        stage = 0;
+        phase ^= 1u;
+      }
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1u;
       }
     }
   } else {
