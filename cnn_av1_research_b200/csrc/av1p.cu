@@ -445,10 +445,11 @@ int plan_stage(const av1p_model* m, const ActLayout& L, uint8_t* act_base, av1p_
         if (op.epi == FC_EPI_ADD_RELU) {
           if (op.aux < 0 || L.cols[op.aux] != 1024 || (op.aux_lo >= 0 && L.cols[op.aux_lo] != 1024))
             return fail(AV1P_EINVAL, "resident-conv op needs a 1024-wide residual");
-          if (int rc = make_map_2d(&f.aux_map[0], buf(op.aux), 1024, L.cap, 1024, FC_TILE_M)) return rc;
-          if (int rc = make_map_2d(&f.aux_map[1], buf(op.aux_lo >= 0 ? op.aux_lo : op.aux), 1024, L.cap, 1024, FC_TILE_M)) return rc;
+          if (int rc = make_map_2d(&f.a_map[2], buf(op.aux), 1024, L.cap, 1024, FC_TILE_M)) return rc;
+          if (int rc = make_map_2d(&f.a_map[3], buf(op.aux_lo >= 0 ? op.aux_lo : op.aux), 1024, L.cap, 1024, FC_TILE_M)) return rc;
           f.has_aux_lo = op.aux_lo >= 0 ? 1 : 0;
         }
+        if (!conv_res_build_schedule(f)) return fail(AV1P_EINVAL, "resident-conv schedule does not fit its tables");
         break;
       }
       case AV1P_OP_SAM:
@@ -920,8 +921,8 @@ extern "C" int av1p_conv_res_forward(const av1p_conv_res_desc* d, void* stream) 
   if (d->out_lo_dev)
     if (int rc = make_store_map(&f.out_map[1], d->out_lo_dev, 1024, uint64_t(d->rows))) return rc;
   if (d->epi == FC_EPI_ADD_RELU) {
-    if (int rc = make_map_2d(&f.aux_map[0], d->aux_dev, 1024, d->rows, 1024, FC_TILE_M)) return rc;
-    if (int rc = make_map_2d(&f.aux_map[1], d->aux_lo_dev ? d->aux_lo_dev : d->aux_dev, 1024, d->rows, 1024, FC_TILE_M)) return rc;
+    if (int rc = make_map_2d(&f.a_map[2], d->aux_dev, 1024, d->rows, 1024, FC_TILE_M)) return rc;
+    if (int rc = make_map_2d(&f.a_map[3], d->aux_lo_dev ? d->aux_lo_dev : d->aux_dev, 1024, d->rows, 1024, FC_TILE_M)) return rc;
     f.has_aux_lo = d->aux_lo_dev ? 1 : 0;
   }
   if (!(1.0f / d->acc_scale >= 1.0f && 1.0f / d->acc_scale <= 32768.0f)) return fail(AV1P_EINVAL, "weight scale outside [1, 2^15]");
@@ -935,6 +936,7 @@ extern "C" int av1p_conv_res_forward(const av1p_conv_res_desc* d, void* stream) 
   f.out_lo = static_cast<__half*>(d->out_lo_dev);
   f.out_ld = 1024;
   f.err_flag = g_ctx.watchdog_dev;
+  if (!conv_res_build_schedule(f)) return fail(AV1P_EINVAL, "resident-conv schedule does not fit its tables");
   const int grid = std::min(g_ctx.sms, ceil_div(d->rows, FC_TILE_M));
   conv_res_tcgen05_kernel<<<grid, CR_THREADS, CR_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(f);
   CUDA_TRY(cudaGetLastError());

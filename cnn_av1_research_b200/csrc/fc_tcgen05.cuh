@@ -11,8 +11,8 @@
 // Kernel shape (persistent, warp specialised, one CTA per SM):
 //   warp 0      TMA producer : A tile [128 rows x 64 K] + W tile [block_n x 64 K] per K block
 //   warp 1      MMA issuer   : 4 x tcgen05.mma (M128, N=block_n, K16) per K block, fp32 acc in TMEM
-//   warps 2..9  epilogue     : tcgen05.ld -> bias / ReLU / gate -> fp16 hi/lo -> swizzled smem staging tile
-//   warp 10     store        : one TMA bulk store per staged [128 rows x 32 cols] tile (hi and lo planes)
+//   warps 2..17 epilogue     : tcgen05.ld -> bias / ReLU / gate -> fp16 hi/lo -> swizzled smem staging tile
+//   warp 18     store        : one TMA bulk store per staged [128 rows x 32 cols] tile (hi and lo planes)
 // with a 4-deep smem ring (full/empty mbarriers), a 2-deep TMEM accumulator ring and a hi/lo pair of
 // staging tiles (full/free mbarriers).
 //
@@ -39,17 +39,20 @@ constexpr int FC_MAX_NT = 8;           // N tiles per layer
 constexpr int FC_MAX_KB = 128;         // scheduled K blocks per layer (sum over N tiles)
 constexpr int FC_MAX_SRC = 4;          // activation sources per layer
 constexpr int FC_TAIL_MAX = 4;         // outputs of the in-epilogue final linear
-constexpr int FC_EPI_WARPS = 8;
+constexpr int FC_EPI_WARPS = 16;         // four per TMEM lane quadrant: 8 of every 32 staged columns each
 constexpr int FC_THREADS = 64 + 32 * FC_EPI_WARPS + 32;      // producer, MMA, epilogue, store
 constexpr int FC_STORE_WARP = 2 + FC_EPI_WARPS;
 constexpr int EPI_CHUNK = 32;                                // output columns per staging tile
 constexpr int EPI_UNIT_BYTES = FC_TILE_M * EPI_CHUNK * 2;    // 8 KB: [128 rows][64 B], SWIZZLE_64B
 constexpr int EPI_IDENT_BYTES = 512;                         // 16 x 16 fp16 scaled identity, no swizzle
+constexpr int EPI_SETS = 2;                                  // staging is double buffered: chunk g uses set g & 1
+constexpr int EPI_STAGING_BYTES = EPI_SETS * 2 * EPI_UNIT_BYTES;   // {hi, lo} x 2 sets = 32 KB
 constexpr int FC_OFF_STAGING = FC_STAGES * FC_STAGE_BYTES;
-constexpr int FC_OFF_IDENT = FC_OFF_STAGING + 2 * EPI_UNIT_BYTES;
+constexpr int FC_OFF_TAIL = FC_OFF_STAGING;                  // head layers store nothing: their tail weights reuse the staging area
+constexpr int FC_OFF_IDENT = FC_OFF_STAGING + EPI_STAGING_BYTES;
 constexpr int FC_OFF_BARS = FC_OFF_IDENT + EPI_IDENT_BYTES;
-constexpr int FC_OFF_TAIL = FC_OFF_BARS + 256;
-constexpr int FC_SMEM_BYTES = FC_OFF_TAIL + FC_TAIL_MAX * FC_MAX_N * 4 + 1024 /*align*/;
+constexpr int FC_SMEM_BYTES = FC_OFF_BARS + 256 + 1024 /*align*/;
+static_assert(FC_TAIL_MAX * FC_MAX_N * 4 <= EPI_STAGING_BYTES, "tail weights must fit the staging area");
 constexpr uint16_t FC_W_IDENT = 0xFFFFu;   // schedule entry: A tile is a residual K block, B is the scaled identity
 
 // Precision.  Operands are fp16, accumulation is fp32 in TMEM.  In split mode ("fp16x3") every
@@ -98,21 +101,28 @@ struct FcParams {
 __device__ __forceinline__ float fast_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 // ------------------------------------------------------------------------------------------------
-// Epilogue staging: two [128 rows x 32 cols] fp16 tiles (hi plane, lo plane) in the SWIZZLE_64B layout
-// a TMA store expects.  full[u] : 8 epilogue warps -> store thread ("tile u is written and fenced");
-// free_[u]: store thread -> epilogue warps ("the bulk store has finished reading tile u").
+// Epilogue staging: two sets of two [128 rows x 32 cols] fp16 tiles (hi plane, lo plane) in the SWIZZLE_64B layout
+// a TMA store expects; chunk g of a CTA's output stream uses set g & 1.
+//   full[s] : 16 epilogue warps -> store warp ("both tiles of set s are written and fenced")
+//   free_[s]: store warp -> epilogue warps ("the bulk stores have finished reading set s")
 struct EpiStage {
-  uint8_t* unit[2];
-  uint64_t* full;    // [2], count FC_EPI_WARPS
-  uint64_t* free_;   // [2], count 1
+  uint8_t* staging;  // [EPI_SETS][2 planes][EPI_UNIT_BYTES]
+  uint64_t* full;    // [EPI_SETS], count FC_EPI_WARPS
+  uint64_t* free_;   // [EPI_SETS], count 1
+  __device__ __forceinline__ uint8_t* unit(uint32_t set, int plane) const {
+    return staging + (set * 2u + uint32_t(plane)) * EPI_UNIT_BYTES;
+  }
 };
+__device__ __forceinline__ void epi_stage_init(EpiStage& es, uint8_t* staging, uint64_t* full, uint64_t* free_) {
+  es.staging = staging;
+  es.full = full;
+  es.free_ = free_;
+}
 
-// 16 consecutive fp16 of row r (two 16-byte chunks, index 2*half and 2*half+1 of the 64-byte row)
-__device__ __forceinline__ void stage_store16(uint8_t* unit, int r_local, int half, const uint4& a, const uint4& b) {
+// 8 consecutive fp16 of row r: 16-byte chunk `part` (0..3) of the 64-byte row
+__device__ __forceinline__ void stage_store8(uint8_t* unit, int r_local, int part, const uint4& a) {
   const int sw = (r_local >> 1) & 3;                     // Swizzle<2,4,3>: chunk index ^= address bits [7,9)
-  uint8_t* rowp = unit + r_local * (EPI_CHUNK * 2);
-  *reinterpret_cast<uint4*>(rowp + (((2 * half) ^ sw) << 4)) = a;
-  *reinterpret_cast<uint4*>(rowp + (((2 * half + 1) ^ sw) << 4)) = b;
+  *reinterpret_cast<uint4*>(unit + r_local * (EPI_CHUNK * 2) + ((part ^ sw) << 4)) = a;
 }
 
 // 16 x 16 identity scaled by `s` in the no-swizzle K-major core-matrix layout (LBO 128 B, SBO 256 B)
@@ -126,48 +136,49 @@ __device__ __forceinline__ void write_ident_tile(uint8_t* ident, float s, int ti
 }
 __device__ __forceinline__ uint64_t ident_desc(uint32_t ident_addr) { return umma_desc_nosw(ident_addr, 128, 256); }
 
-// Store warp: drain `n_chunks` staged tiles of one accumulator (columns col0 .., rows row0 ..).  The whole warp
+// Store warp: drain `n_chunks` staged chunks of one accumulator (columns col0 .., rows row0 ..).  The whole warp
 // walks the loop; the bulk stores, their commit groups and the read-completion waits are all issued by lane 0
-// (bulk async-groups are per-thread state, so one fixed lane must own them).
+// (bulk async-groups are per-thread state, so one fixed lane must own them).  One commit group per chunk; after
+// chunk g is issued the previous group's smem reads are awaited and its set handed back, so the TMA read of one
+// set overlaps the epilogue writing the other.
 __device__ __forceinline__ void epi_store_chunks(const EpiStage& es, uint32_t& g, const CUtensorMap* map_hi,
                                                  const CUtensorMap* map_lo, bool has_lo, int col0, int n_chunks, int row0,
                                                  int* err_flag) {
   const bool leader = (threadIdx.x & 31) == 0;
   for (int c = 0; c < n_chunks; ++c, ++g) {
-    mbar_wait(&es.full[0], g & 1u, err_flag, 900);
+    const uint32_t set = g & 1u;
+    mbar_wait(&es.full[set], (g >> 1) & 1u, err_flag, 900);
     if (leader) {
-      tma_store_2d(map_hi, es.unit[0], col0 + c * EPI_CHUNK, row0);
+      tma_store_2d(map_hi, es.unit(set, 0), col0 + c * EPI_CHUNK, row0);
+      if (has_lo) tma_store_2d(map_lo, es.unit(set, 1), col0 + c * EPI_CHUNK, row0);
       tma_store_commit();
-    }
-    if (has_lo) {
-      mbar_wait(&es.full[1], g & 1u, err_flag, 901);
-      if (leader) {
-        tma_store_2d(map_lo, es.unit[1], col0 + c * EPI_CHUNK, row0);
-        tma_store_commit();
-        tma_store_wait_read<1>();
-        mbar_arrive(&es.free_[0]);
-        tma_store_wait_read<0>();
-        mbar_arrive(&es.free_[1]);
+      if (g > 0) {
+        tma_store_wait_read<1>();               // every group but the one just committed has been read
+        mbar_arrive(&es.free_[set ^ 1u]);
       }
-    } else if (leader) {
-      tma_store_wait_read<0>();
-      mbar_arrive(&es.free_[0]);
     }
     __syncwarp();
   }
 }
+// After the last chunk of the kernel: nothing hands the final set back (nobody waits for it) but the stores must
+// have left shared memory before the CTA exits.
+__device__ __forceinline__ void epi_store_drain() {
+  if ((threadIdx.x & 31) == 0) tma_store_wait_all<0>();
+  __syncwarp();
+}
 
-// Epilogue of one accumulator tile [128 rows x block_n fp32 columns at TMEM column t_col]: warps 2..9, two
-// warps per TMEM lane quadrant; both work on the same 32-column chunk (16 columns each).  Waits on `full`,
-// applies scale / bias / gate / ReLU, writes fp16 hi (+lo) either into the staging tiles (whole M tiles) or
-// straight to global (the last, partial M tile: rows past n_rows stay untouched), arrives on `empty` as soon as
-// the last TMEM read has completed.  P is FcParams or any struct with the same epilogue members.
+// Epilogue of one accumulator tile [128 rows x block_n fp32 columns at TMEM column t_col]: warps 2..17, four
+// warps per TMEM lane quadrant, all on the same 32-column chunk (8 columns each).  Waits on `full`, applies
+// scale / bias / gate / ReLU, writes fp16 hi (+lo) either into the staging tiles (whole M tiles) or straight to
+// global (the last, partial M tile: rows past n_rows stay untouched), arrives on `empty` as soon as the last
+// TMEM read has completed.  The TMEM read of chunk c+1 is in flight while chunk c is converted and staged.
+// P is FcParams or any struct with the same epilogue members.
 template <typename P>
 __device__ __forceinline__ void epi_tile_store(const P& p, const EpiStage& es, uint32_t& g, int n_rows, int mt, int col0,
                                                int block_n, uint32_t t_col, uint64_t* full, uint32_t full_phase,
                                                uint64_t* empty, int warp, int lane, int tag) {
   const int quad = warp & 3;              // TMEM lane quadrant this warp may read
-  const int half = (warp - 2) >> 2;       // which 16 columns of every 32-column chunk
+  const int part = (warp - 2) >> 2;       // which 8 columns of every 32-column chunk
   const int r_local = quad * 32 + lane;
   const int row = mt * FC_TILE_M + r_local;
   const bool row_ok = row < n_rows;
@@ -177,115 +188,89 @@ __device__ __forceinline__ void epi_tile_store(const P& p, const EpiStage& es, u
   const bool has_lo = p.out_lo != nullptr;
   const float rs = ((p.row_scale && row_ok) ? p.row_scale[row] : 1.0f) * p.acc_scale;
   const int n_chunks = block_n / EPI_CHUNK;
-  const int tcol = half * 16;
-  uint4 ax[2], axl[2];
-  ax[0] = ax[1] = axl[0] = axl[1] = make_uint4(0u, 0u, 0u, 0u);
+  const int tcol = part * 8;
+  const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+  uint4 ax = zero4, axl = zero4;
   if (gate && row_ok) {
-    const uint4* s = reinterpret_cast<const uint4*>(p.aux + size_t(row) * p.aux_ld + col0 + tcol);
-    ax[0] = __ldg(s);
-    ax[1] = __ldg(s + 1);
-    if (p.aux_lo) {
-      const uint4* sl = reinterpret_cast<const uint4*>(p.aux_lo + size_t(row) * p.aux_ld + col0 + tcol);
-      axl[0] = __ldg(sl);
-      axl[1] = __ldg(sl + 1);
-    }
+    ax = __ldg(reinterpret_cast<const uint4*>(p.aux + size_t(row) * p.aux_ld + col0 + tcol));
+    if (p.aux_lo) axl = __ldg(reinterpret_cast<const uint4*>(p.aux_lo + size_t(row) * p.aux_ld + col0 + tcol));
   }
   mbar_wait(full, full_phase, p.err_flag, tag);
   tc_fence_after_sync();
   const uint32_t t_addr = t_col + (uint32_t(quad * 32) << 16) + uint32_t(tcol);
+  uint32_t v[8];
+  tmem_ld_32x8(t_addr, v);
   for (int c = 0; c < n_chunks; ++c) {
     const int col = col0 + c * EPI_CHUNK + tcol;
-    uint32_t v[16];
-    tmem_ld_32x16(t_addr + uint32_t(c * EPI_CHUNK), v);
-    uint4 nx[2], nxl[2];
-    nx[0] = nx[1] = nxl[0] = nxl[1] = make_uint4(0u, 0u, 0u, 0u);
+    float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+    if (p.bias) {
+      b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+      b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col) + 1);
+    }
+    uint4 nx = zero4, nxl = zero4;
     if (gate && row_ok && c + 1 < n_chunks) {
-      const uint4* s = reinterpret_cast<const uint4*>(p.aux + size_t(row) * p.aux_ld + col + EPI_CHUNK);
-      nx[0] = __ldg(s);
-      nx[1] = __ldg(s + 1);
-      if (p.aux_lo) {
-        const uint4* sl = reinterpret_cast<const uint4*>(p.aux_lo + size_t(row) * p.aux_ld + col + EPI_CHUNK);
-        nxl[0] = __ldg(sl);
-        nxl[1] = __ldg(sl + 1);
-      }
+      nx = __ldg(reinterpret_cast<const uint4*>(p.aux + size_t(row) * p.aux_ld + col + EPI_CHUNK));
+      if (p.aux_lo) nxl = __ldg(reinterpret_cast<const uint4*>(p.aux_lo + size_t(row) * p.aux_ld + col + EPI_CHUNK));
     }
     tmem_ld_wait();
-    if (c == n_chunks - 1) {
+    float f[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[i]) * rs;
+    if (c + 1 < n_chunks) {
+      tmem_ld_32x8(t_addr + uint32_t((c + 1) * EPI_CHUNK), v);     // next chunk's accumulator in flight
+    } else {
       // every TMEM read of this accumulator is complete -> hand it back to the MMA warp
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(empty);
     }
-    float f[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) * rs;
-    if (p.bias) {
-      const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
+    f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+    f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+    if (gate) {
+      const __half2* h = reinterpret_cast<const __half2*>(&ax);
+      const __half2* hl = reinterpret_cast<const __half2*>(&axl);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const float4 b = __ldg(b4 + i);
-        f[4 * i + 0] += b.x;
-        f[4 * i + 1] += b.y;
-        f[4 * i + 2] += b.z;
-        f[4 * i + 3] += b.w;
-      }
-    }
-    if (gate) {
-      const __half2* h = reinterpret_cast<const __half2*>(ax);
-      const __half2* hl = reinterpret_cast<const __half2*>(axl);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
         const float2 a = __half22float2(h[i]), al = __half22float2(hl[i]);
         f[2 * i] = (a.x + al.x) * fast_sigmoid(f[2 * i]);
         f[2 * i + 1] = (a.y + al.y) * fast_sigmoid(f[2 * i + 1]);
       }
-      ax[0] = nx[0]; ax[1] = nx[1]; axl[0] = nxl[0]; axl[1] = nxl[1];
+      ax = nx;
+      axl = nxl;
     }
     if (relu) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
+      for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
     }
-    __align__(16) __half2 hi[8];
+    __align__(16) __half2 hi[4], lo[4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) hi[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
-    const uint4* hq = reinterpret_cast<const uint4*>(hi);
+    for (int i = 0; i < 4; ++i) {
+      hi[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+      const float2 hf = __half22float2(hi[i]);
+      lo[i] = __floats2half2_rn(f[2 * i] - hf.x, f[2 * i + 1] - hf.y);
+    }
+    const uint4 hq = *reinterpret_cast<const uint4*>(hi);
+    const uint4 lq = *reinterpret_cast<const uint4*>(lo);
     if (staged) {
-      mbar_wait(&es.free_[0], (g & 1u) ^ 1u, p.err_flag, tag + 10);
-      stage_store16(es.unit[0], r_local, half, hq[0], hq[1]);
+      const uint32_t set = g & 1u;
+      // use u = g >> 1 of this set: the first use of a set needs no wait (parity trick), use u waits for the
+      // (u-1)-th hand-back
+      mbar_wait(&es.free_[set], ((g >> 1) & 1u) ^ 1u, p.err_flag, tag + 10);
+      stage_store8(es.unit(set, 0), r_local, part, hq);
+      if (has_lo) stage_store8(es.unit(set, 1), r_local, part, lq);
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&es.full[0]);
+      if (lane == 0) mbar_arrive(&es.full[set]);
+      ++g;
     } else if (row_ok) {
-      uint4* o4 = reinterpret_cast<uint4*>(p.out + size_t(row) * p.out_ld + col);
-      o4[0] = hq[0];
-      o4[1] = hq[1];
+      *reinterpret_cast<uint4*>(p.out + size_t(row) * p.out_ld + col) = hq;
+      if (has_lo) *reinterpret_cast<uint4*>(p.out_lo + size_t(row) * p.out_ld + col) = lq;
     }
-    if (has_lo) {
-      __align__(16) __half2 lo[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float2 hf = __half22float2(hi[i]);
-        lo[i] = __floats2half2_rn(f[2 * i] - hf.x, f[2 * i + 1] - hf.y);
-      }
-      const uint4* lq = reinterpret_cast<const uint4*>(lo);
-      if (staged) {
-        mbar_wait(&es.free_[1], (g & 1u) ^ 1u, p.err_flag, tag + 11);
-        stage_store16(es.unit[1], r_local, half, lq[0], lq[1]);
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&es.full[1]);
-      } else if (row_ok) {
-        uint4* l4 = reinterpret_cast<uint4*>(p.out_lo + size_t(row) * p.out_ld + col);
-        l4[0] = lq[0];
-        l4[1] = lq[1];
-      }
-    }
-    if (staged) ++g;
   }
 }
 
 // Head epilogue (FC_EPI_HEAD): h = relu(s*acc + b), logits = h . tail_w^T + tail_b in the thread that owns the row.
-// The first four epilogue warps take every column; the other four only release the accumulator.
+// The first four epilogue warps take every column; the others only release the accumulator.
 __device__ __forceinline__ void epi_tile_head(const FcParams& p, int n_rows, int mt, int block_n, uint32_t t_col,
                                               uint64_t* full, uint32_t full_phase, uint64_t* empty, const float* tail_w_s,
                                               int warp, int lane, int tag) {
@@ -354,10 +339,7 @@ __global__ void __launch_bounds__(FC_THREADS, 1) fc_tcgen05_kernel(const __grid_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stg_free + 2);
   float* tail_w_s = reinterpret_cast<float*>(smem + FC_OFF_TAIL);
   EpiStage es;
-  es.unit[0] = smem + FC_OFF_STAGING;
-  es.unit[1] = smem + FC_OFF_STAGING + EPI_UNIT_BYTES;
-  es.full = stg_full;
-  es.free_ = stg_free;
+  epi_stage_init(es, smem + FC_OFF_STAGING, stg_full, stg_free);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -526,8 +508,7 @@ __global__ void __launch_bounds__(FC_THREADS, 1) fc_tcgen05_kernel(const __grid_
         epi_store_chunks(es, g, &p.out_map[0], &p.out_map[1], p.out_lo != nullptr, nt * p.block_n, p.block_n / EPI_CHUNK,
                          mt * FC_TILE_M, p.err_flag);
       }
-      if (lane == 0) tma_store_wait_all<0>();
-      __syncwarp();
+      epi_store_drain();
     }
   }
 

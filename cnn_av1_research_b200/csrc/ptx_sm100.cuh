@@ -85,6 +85,13 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, ui
       : "memory");
 }
 
+// Pull a tile into L2 ahead of the TMA load that will need it (no shared memory, no barrier): lets a shallow
+// smem ring run at L2-hit latency instead of DRAM latency.
+__device__ __forceinline__ void tma_prefetch_l2_2d(const void* tmap, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
+               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1)
+               : "memory");
+}
 // Bulk tensor store smem -> global (epilogue staging tiles).  The writer threads fence their generic
 // stores (fence.proxy.async) and synchronise with the issuing thread before this is called.
 __device__ __forceinline__ void tma_store_2d(const void* tmap, const void* smem_src, int c0, int c1) {
@@ -151,6 +158,13 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32])
         "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr)
       : "memory");
+}
+// 32 lanes x 8 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
 }
 // 32 lanes x 16 consecutive fp32 columns
 __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16]) {
