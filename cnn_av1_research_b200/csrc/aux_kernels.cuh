@@ -22,6 +22,7 @@ __device__ __forceinline__ float warp_max(float v) {
 // kernel touches data, so the module reduces to one scalar per block,
 //   g = sigmoid(w_avg * mean_c(x) + w_max * max_c(x)),
 // which the next linear layer applies as a row scale.  One warp per row of 512 fp16.
+// (`off` = act_off(row, col, kb): 16 consecutive columns never straddle a 64-column block)
 __device__ __forceinline__ void load_row16(const __half* __restrict__ hi, const __half* __restrict__ lo, size_t off,
                                            float (&x)[16]) {
   // 16 consecutive values of a row as fp32 (hi + lo in split precision)
@@ -59,7 +60,7 @@ __global__ void __launch_bounds__(256) sam_gate_kernel(const __half* __restrict_
   const int warps_per_grid = (gridDim.x * blockDim.x) >> 5;
   for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < rows; r += warps_per_grid) {
     float v[16];
-    load_row16(x, x_lo, size_t(r) * ld + lane * 16, v);
+    load_row16(x, x_lo, act_off(r, lane * 16, ld >> 6), v);
     float s = 0.f, m = -INFINITY;
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
@@ -108,7 +109,7 @@ __global__ void __launch_bounds__(256) se_kernel(const __half* __restrict__ x, c
     float mean[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int i = 0; i < CPL; ++i) {
-      const size_t off = size_t(r) * L + size_t(lane + 32 * i) * 8;
+      const size_t off = act_off(r, (lane + 32 * i) * 8, L / 64);
       const uint4 q = __ldg(reinterpret_cast<const uint4*>(x + off));
       const __half2* h = reinterpret_cast<const __half2*>(&q);
 #pragma unroll
@@ -214,7 +215,7 @@ __global__ void __launch_bounds__(256) se_kernel(const __half* __restrict__ x, c
     for (int k = 0; k < 8; ++k) sc[k] = 1.0f / (1.0f + expf(-sc[k]));
 #pragma unroll
     for (int i = 0; i < CPL; ++i) {
-      const size_t off = size_t(r) * L + size_t(lane + 32 * i) * 8;
+      const size_t off = act_off(r, (lane + 32 * i) * 8, L / 64);
       __align__(16) __half2 hi[4], lo[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
@@ -242,7 +243,7 @@ __global__ void __launch_bounds__(256) fgvc_tail_kernel(const __half* __restrict
   const int warps_per_grid = (gridDim.x * blockDim.x) >> 5;
   for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < rows; r += warps_per_grid) {
     float x[16];
-    load_row16(h, h_lo, size_t(r) * ld + lane * 16, x);
+    load_row16(h, h_lo, act_off(r, lane * 16, ld >> 6), x);
     float ss = 0.f, d[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int i = 0; i < 16; ++i) ss = fmaf(x[i], x[i], ss);

@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -75,7 +76,11 @@ int ensure_ctx() {
   if (!fn || qres != cudaDriverEntryPointSuccess) return fail(AV1P_ECUDA, "cuTensorMapEncodeTiled not available");
   g_ctx.encode = reinterpret_cast<EncodeTiledFn>(fn);
   CUDA_TRY(cudaFuncSetAttribute(fc_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FC_SMEM_BYTES));
-  CUDA_TRY(cudaFuncSetAttribute(conv_res_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CR_SMEM_BYTES));
+  {
+    int n_k = 0;
+    const ConvResKernel* ks = conv_res_all_kernels(&n_k);
+    for (int i = 0; i < n_k; ++i) CUDA_TRY(cudaFuncSetAttribute(ks[i], cudaFuncAttributeMaxDynamicSharedMemorySize, CR_SMEM_BYTES));
+  }
   CUDA_TRY(cudaFuncSetAttribute(stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM_BYTES));
   CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&g_ctx.watchdog_host), sizeof(int), cudaHostAllocMapped));
   *g_ctx.watchdog_host = 0;
@@ -101,8 +106,13 @@ int make_map_2d(CUtensorMap* map, const void* base, uint64_t cols, uint64_t rows
   if (r != CUDA_SUCCESS) return fail(AV1P_ECUDA, "cuTensorMapEncodeTiled failed with %d", int(r));
   return AV1P_OK;
 }
-int make_store_map(CUtensorMap* map, const void* base, uint64_t cols, uint64_t rows) {
-  return make_map_2d(map, base, cols, rows, cols, FC_TILE_M, EPI_CHUNK, CU_TENSOR_MAP_SWIZZLE_64B);
+// Activation buffer in the tiled layout (act_off): `cols` columns (multiple of 64), `rows` rows (padded to 128)
+// = a plain 2-D tensor [rows_padded * cols / 64][64]; tile (mt, kb) starts at tensor row (mt * cols/64 + kb) * 128.
+int make_act_map(CUtensorMap* map, const void* base, uint64_t cols, uint64_t rows, bool store) {
+  if (cols == 0 || cols % 64) return fail(AV1P_EINVAL, "activation buffer width %llu is not a multiple of 64", (unsigned long long)cols);
+  const uint64_t rows_padded = (rows + FC_TILE_M - 1) / FC_TILE_M * FC_TILE_M;
+  return store ? make_map_2d(map, base, 64, rows_padded * (cols / 64), 64, FC_TILE_M, EPI_CHUNK, CU_TENSOR_MAP_SWIZZLE_64B)
+               : make_map_2d(map, base, 64, rows_padded * (cols / 64), 64, FC_TILE_M);
 }
 
 // Residual connection of an FC layer (FC_EPI_ADD_RELU): the identity branch is accumulated on the tensor
@@ -366,7 +376,8 @@ int plan_stage(const av1p_model* m, const ActLayout& L, uint8_t* act_base, av1p_
         if (op.src[0] < 0 || (op.out < 0 && op.epi != FC_EPI_HEAD)) return fail(AV1P_EINVAL, "FC op without source/out");
         for (int i = 0; i < FC_MAX_SRC; ++i) {
           const int sb = op.src[i] >= 0 ? op.src[i] : op.src[0];
-          if (int rc = make_map_2d(&f.a_map[i], buf(sb), L.cols[sb], L.cap, L.cols[sb], FC_TILE_M)) return rc;
+          if (int rc = make_act_map(&f.a_map[i], buf(sb), L.cols[sb], L.cap, false)) return rc;
+          f.src_kb[i] = int(L.cols[sb] / 64);
         }
         if (int rc = make_map_2d(&f.w_map, at(op.w_off), 64, uint64_t(op.n_w_chunks) * op.block_n, 64, op.block_n)) return rc;
         f.n_tiles = op.n_tiles;
@@ -382,10 +393,10 @@ int plan_stage(const av1p_model* m, const ActLayout& L, uint8_t* act_base, av1p_
         }
         f.aux = buf(op.aux);
         f.aux_lo = buf(op.aux_lo);
-        f.aux_ld = op.aux >= 0 ? int(L.cols[op.aux]) : 0;
+        f.aux_kb = op.aux >= 0 ? int(L.cols[op.aux] / 64) : 0;
         f.out = buf(op.out);
         f.out_lo = buf(op.out_lo);
-        f.out_ld = op.out >= 0 ? int(L.cols[op.out]) : 0;
+        f.out_kb = op.out >= 0 ? int(L.cols[op.out] / 64) : 0;
         if ((op.aux_lo >= 0 && L.cols[op.aux_lo] != L.cols[op.aux]) || (op.out_lo >= 0 && L.cols[op.out_lo] != L.cols[op.out]))
           return fail(AV1P_EINVAL, "hi/lo buffers differ in width");
         f.tail_w = reinterpret_cast<const float*>(at(op.tail_w_off));
@@ -395,7 +406,7 @@ int plan_stage(const av1p_model* m, const ActLayout& L, uint8_t* act_base, av1p_
         if ((op.epi == FC_EPI_ADD_RELU || op.epi == FC_EPI_GATE) && !f.aux) return fail(AV1P_EINVAL, "FC op needs aux");
         if (op.epi == FC_EPI_HEAD && (!f.tail_w || !f.tail_b || op.n_tiles != 1 || op.tail_n < 1))
           return fail(AV1P_EINVAL, "malformed head op");
-        if (op.epi != FC_EPI_HEAD && op.n_tiles * op.block_n > f.out_ld) return fail(AV1P_EINVAL, "FC output wider than its buffer");
+        if (op.epi != FC_EPI_HEAD && op.n_tiles * op.block_n > f.out_kb * 64) return fail(AV1P_EINVAL, "FC output wider than its buffer");
         for (int i = 0; i <= op.n_tiles; ++i) f.kb_begin[i] = op.kb_begin[i];
         if (f.kb_begin[0] != 0 || f.kb_begin[op.n_tiles] != op.n_kb_total) return fail(AV1P_EINVAL, "bad K-block schedule");
         for (int i = 0; i < op.n_kb_total; ++i) {
@@ -406,15 +417,16 @@ int plan_stage(const av1p_model* m, const ActLayout& L, uint8_t* act_base, av1p_
           if (int(op.kb_w[i]) >= op.n_w_chunks) return fail(AV1P_EINVAL, "weight chunk index out of range");
         }
         if (op.out >= 0) {
-          if (int rc = make_store_map(&f.out_map[0], buf(op.out), L.cols[op.out], L.cap)) return rc;
+          if (int rc = make_act_map(&f.out_map[0], buf(op.out), L.cols[op.out], L.cap, true)) return rc;
           if (op.out_lo >= 0)
-            if (int rc = make_store_map(&f.out_map[1], buf(op.out_lo), L.cols[op.out_lo], L.cap)) return rc;
+            if (int rc = make_act_map(&f.out_map[1], buf(op.out_lo), L.cols[op.out_lo], L.cap, true)) return rc;
         }
         if (op.epi == FC_EPI_ADD_RELU) {
           if (op.n_tiles * op.block_n > int(L.cols[op.aux])) return fail(AV1P_EINVAL, "residual narrower than the FC output");
-          if (int rc = make_map_2d(&f.a_map[2], buf(op.aux), L.cols[op.aux], L.cap, L.cols[op.aux], FC_TILE_M)) return rc;
+          if (int rc = make_act_map(&f.a_map[2], buf(op.aux), L.cols[op.aux], L.cap, false)) return rc;
+          f.src_kb[2] = f.src_kb[3] = int(L.cols[op.aux] / 64);
           if (op.aux_lo >= 0)
-            if (int rc = make_map_2d(&f.a_map[3], buf(op.aux_lo), L.cols[op.aux_lo], L.cap, L.cols[op.aux_lo], FC_TILE_M)) return rc;
+            if (int rc = make_act_map(&f.a_map[3], buf(op.aux_lo), L.cols[op.aux_lo], L.cap, false)) return rc;
           if (int rc = add_residual_entries(f, op.aux_lo >= 0)) return rc;
         }
         break;
@@ -426,8 +438,8 @@ int plan_stage(const av1p_model* m, const ActLayout& L, uint8_t* act_base, av1p_
         if (op.src[0] < 0 || op.out < 0 || L.cols[op.src[0]] != 1024 || L.cols[op.out] != 1024 || (split && (op.src[1] < 0 || op.out_lo < 0)) ||
             !op.w_off || !op.bias_off || op.w_off + uint64_t(split ? 2 : 1) * CR_W_PLANE_BYTES > m->hdr.total_bytes)
           return fail(AV1P_EINVAL, "malformed resident-conv op");
-        if (int rc = make_map_2d(&f.a_map[0], buf(op.src[0]), 1024, L.cap, 1024, FC_TILE_M)) return rc;
-        if (int rc = make_map_2d(&f.a_map[1], buf(split ? op.src[1] : op.src[0]), 1024, L.cap, 1024, FC_TILE_M)) return rc;
+        if (int rc = make_act_map(&f.a_map[0], buf(op.src[0]), 1024, L.cap, false)) return rc;
+        if (int rc = make_act_map(&f.a_map[1], buf(split ? op.src[1] : op.src[0]), 1024, L.cap, false)) return rc;
         if (int rc = make_map_2d(&f.w_map, at(op.w_off), 64, uint64_t(split ? 2 : 1) * 9 * 64, 64, 64)) return rc;
         f.split = split ? 1 : 0;
         f.epi = op.epi;
@@ -435,18 +447,18 @@ int plan_stage(const av1p_model* m, const ActLayout& L, uint8_t* act_base, av1p_
         f.acc_scale = op.f0;
         f.out = buf(op.out);
         f.out_lo = buf(op.out_lo);
-        f.out_ld = 1024;
+        f.out_kb = 16;
         f.err_flag = g_ctx.watchdog_dev;
         if (op.epi != FC_EPI_RELU && op.epi != FC_EPI_ADD_RELU && op.epi != FC_EPI_LINEAR) return fail(AV1P_EINVAL, "resident-conv epilogue %d", op.epi);
         if (!(1.0f / op.f0 >= 1.0f && 1.0f / op.f0 <= 32768.0f)) return fail(AV1P_EINVAL, "resident-conv weight scale outside [1, 2^15]");
-        if (int rc = make_store_map(&f.out_map[0], buf(op.out), 1024, L.cap)) return rc;
+        if (int rc = make_act_map(&f.out_map[0], buf(op.out), 1024, L.cap, true)) return rc;
         if (op.out_lo >= 0)
-          if (int rc = make_store_map(&f.out_map[1], buf(op.out_lo), 1024, L.cap)) return rc;
+          if (int rc = make_act_map(&f.out_map[1], buf(op.out_lo), 1024, L.cap, true)) return rc;
         if (op.epi == FC_EPI_ADD_RELU) {
           if (op.aux < 0 || L.cols[op.aux] != 1024 || (op.aux_lo >= 0 && L.cols[op.aux_lo] != 1024))
             return fail(AV1P_EINVAL, "resident-conv op needs a 1024-wide residual");
-          if (int rc = make_map_2d(&f.a_map[2], buf(op.aux), 1024, L.cap, 1024, FC_TILE_M)) return rc;
-          if (int rc = make_map_2d(&f.a_map[3], buf(op.aux_lo >= 0 ? op.aux_lo : op.aux), 1024, L.cap, 1024, FC_TILE_M)) return rc;
+          if (int rc = make_act_map(&f.a_map[2], buf(op.aux), 1024, L.cap, false)) return rc;
+          if (int rc = make_act_map(&f.a_map[3], buf(op.aux_lo >= 0 ? op.aux_lo : op.aux), 1024, L.cap, false)) return rc;
           f.has_aux_lo = op.aux_lo >= 0 ? 1 : 0;
         }
         if (!conv_res_build_schedule(f)) return fail(AV1P_EINVAL, "resident-conv schedule does not fit its tables");
@@ -542,7 +554,7 @@ int run_stage(av1p_stage* s, const StemInput& si, const int32_t* idx, const int3
         P.cr.n_rows = n;
         const int grid = std::min(g_ctx.sms, ceil_div(n, FC_TILE_M));
         ProfScope ps(PROF_CONV, st);
-        conv_res_tcgen05_kernel<<<grid, CR_THREADS, CR_SMEM_BYTES, st>>>(P.cr);
+        conv_res_kernel_for(P.cr)<<<grid, CR_THREADS, CR_SMEM_BYTES, st>>>(P.cr);
         break;
       }
       case AV1P_OP_SAM: {
@@ -859,7 +871,8 @@ extern "C" int av1p_fc_forward(const av1p_fc_desc* d, void* stream) {
   memset(&f, 0, sizeof f);
   for (int i = 0; i < FC_MAX_SRC; ++i) {
     const int j = d->a_dev[i] ? i : 0;
-    if (int rc = make_map_2d(&f.a_map[i], d->a_dev[j], d->a_cols[j], d->rows, d->a_cols[j], FC_TILE_M)) return rc;
+    if (int rc = make_act_map(&f.a_map[i], d->a_dev[j], uint64_t(d->a_cols[j]), uint64_t(d->rows), false)) return rc;
+    f.src_kb[i] = d->a_cols[j] / 64;
   }
   if (int rc = make_map_2d(&f.w_map, d->w_dev, 64, uint64_t(d->n_w_chunks) * d->block_n, 64, d->block_n)) return rc;
   f.n_rows_dev = d->n_dev;
@@ -873,10 +886,10 @@ extern "C" int av1p_fc_forward(const av1p_fc_desc* d, void* stream) {
   f.pair_mode = d->pair_mode;
   f.aux = static_cast<const __half*>(d->aux_dev);
   f.aux_lo = static_cast<const __half*>(d->aux_lo_dev);
-  f.aux_ld = d->aux_ld;
+  f.aux_kb = d->aux_ld / 64;
   f.out = static_cast<__half*>(d->out_dev);
   f.out_lo = static_cast<__half*>(d->out_lo_dev);
-  f.out_ld = d->out_ld;
+  f.out_kb = d->out_ld / 64;
   f.tail_w = d->tail_w_dev;
   f.tail_b = d->tail_b_dev;
   f.logits = d->logits_dev;
@@ -889,15 +902,16 @@ extern "C" int av1p_fc_forward(const av1p_fc_desc* d, void* stream) {
   }
   if (d->epi != FC_EPI_HEAD) {
     if (!d->out_dev || d->out_ld < d->n_tiles * d->block_n) return fail(AV1P_EINVAL, "FC output missing or too narrow");
-    if (int rc = make_store_map(&f.out_map[0], d->out_dev, uint64_t(d->out_ld), uint64_t(d->rows))) return rc;
+    if (int rc = make_act_map(&f.out_map[0], d->out_dev, uint64_t(d->out_ld), uint64_t(d->rows), true)) return rc;
     if (d->out_lo_dev)
-      if (int rc = make_store_map(&f.out_map[1], d->out_lo_dev, uint64_t(d->out_ld), uint64_t(d->rows))) return rc;
+      if (int rc = make_act_map(&f.out_map[1], d->out_lo_dev, uint64_t(d->out_ld), uint64_t(d->rows), true)) return rc;
   }
   if (d->epi == FC_EPI_ADD_RELU) {
     if (!d->aux_dev || d->aux_ld < d->n_tiles * d->block_n) return fail(AV1P_EINVAL, "residual missing or too narrow");
-    if (int rc = make_map_2d(&f.a_map[2], d->aux_dev, uint64_t(d->aux_ld), uint64_t(d->rows), uint64_t(d->aux_ld), FC_TILE_M)) return rc;
+    if (int rc = make_act_map(&f.a_map[2], d->aux_dev, uint64_t(d->aux_ld), uint64_t(d->rows), false)) return rc;
+    f.src_kb[2] = f.src_kb[3] = d->aux_ld / 64;
     if (d->aux_lo_dev)
-      if (int rc = make_map_2d(&f.a_map[3], d->aux_lo_dev, uint64_t(d->aux_ld), uint64_t(d->rows), uint64_t(d->aux_ld), FC_TILE_M)) return rc;
+      if (int rc = make_act_map(&f.a_map[3], d->aux_lo_dev, uint64_t(d->aux_ld), uint64_t(d->rows), false)) return rc;
     if (int rc = add_residual_entries(f, d->aux_lo_dev != nullptr)) return rc;
   }
   const int grid = std::min(g_ctx.sms, ceil_div(d->rows, FC_TILE_M) * d->n_tiles);
@@ -914,15 +928,15 @@ extern "C" int av1p_conv_res_forward(const av1p_conv_res_desc* d, void* stream) 
   if (int rc = ensure_ctx()) return rc;
   ConvResParams f;
   memset(&f, 0, sizeof f);
-  if (int rc = make_map_2d(&f.a_map[0], d->x_dev, 1024, d->rows, 1024, FC_TILE_M)) return rc;
-  if (int rc = make_map_2d(&f.a_map[1], d->split ? d->x_lo_dev : d->x_dev, 1024, d->rows, 1024, FC_TILE_M)) return rc;
+  if (int rc = make_act_map(&f.a_map[0], d->x_dev, 1024, uint64_t(d->rows), false)) return rc;
+  if (int rc = make_act_map(&f.a_map[1], d->split ? d->x_lo_dev : d->x_dev, 1024, uint64_t(d->rows), false)) return rc;
   if (int rc = make_map_2d(&f.w_map, d->w_dev, 64, uint64_t(d->split ? 2 : 1) * 9 * 64, 64, 64)) return rc;
-  if (int rc = make_store_map(&f.out_map[0], d->out_dev, 1024, uint64_t(d->rows))) return rc;
+  if (int rc = make_act_map(&f.out_map[0], d->out_dev, 1024, uint64_t(d->rows), true)) return rc;
   if (d->out_lo_dev)
-    if (int rc = make_store_map(&f.out_map[1], d->out_lo_dev, 1024, uint64_t(d->rows))) return rc;
+    if (int rc = make_act_map(&f.out_map[1], d->out_lo_dev, 1024, uint64_t(d->rows), true)) return rc;
   if (d->epi == FC_EPI_ADD_RELU) {
-    if (int rc = make_map_2d(&f.a_map[2], d->aux_dev, 1024, d->rows, 1024, FC_TILE_M)) return rc;
-    if (int rc = make_map_2d(&f.a_map[3], d->aux_lo_dev ? d->aux_lo_dev : d->aux_dev, 1024, d->rows, 1024, FC_TILE_M)) return rc;
+    if (int rc = make_act_map(&f.a_map[2], d->aux_dev, 1024, uint64_t(d->rows), false)) return rc;
+    if (int rc = make_act_map(&f.a_map[3], d->aux_lo_dev ? d->aux_lo_dev : d->aux_dev, 1024, uint64_t(d->rows), false)) return rc;
     f.has_aux_lo = d->aux_lo_dev ? 1 : 0;
   }
   if (!(1.0f / d->acc_scale >= 1.0f && 1.0f / d->acc_scale <= 32768.0f)) return fail(AV1P_EINVAL, "weight scale outside [1, 2^15]");
@@ -934,11 +948,12 @@ extern "C" int av1p_conv_res_forward(const av1p_conv_res_desc* d, void* stream) 
   f.acc_scale = d->acc_scale;
   f.out = static_cast<__half*>(d->out_dev);
   f.out_lo = static_cast<__half*>(d->out_lo_dev);
-  f.out_ld = 1024;
+  f.out_kb = 16;
   f.err_flag = g_ctx.watchdog_dev;
   if (!conv_res_build_schedule(f)) return fail(AV1P_EINVAL, "resident-conv schedule does not fit its tables");
+  if (const char* dbg = getenv("AV1P_CR_DEBUG")) f.debug = atoi(dbg);   // kernel-development switch of this test hook only
   const int grid = std::min(g_ctx.sms, ceil_div(d->rows, FC_TILE_M));
-  conv_res_tcgen05_kernel<<<grid, CR_THREADS, CR_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(f);
+  conv_res_kernel_for(f)<<<grid, CR_THREADS, CR_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(f);
   CUDA_TRY(cudaGetLastError());
   return AV1P_OK;
 }

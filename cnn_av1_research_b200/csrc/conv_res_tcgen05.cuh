@@ -47,33 +47,24 @@ constexpr int CR_THREADS = FC_THREADS;
 static_assert(CR_SMEM_BYTES <= 232448, "conv_res shared memory exceeds the 227 KB opt-in limit");
 static_assert(FC_SMEM_BYTES <= 232448, "fc shared memory exceeds the 227 KB opt-in limit");
 
-// The per-M-tile work list is static, so the host compiles it once (conv_res_build_schedule) and the device
-// roles only interpret it: `ring[i]` = which [128 x 64] activation tile the producer loads i-th (map << 4 | position),
-// `tab[j]` = one MMA group (four K=16 instructions on the current ring tile):
-//   bits  0..13  B operand: smem offset / 16 from the aligned base (a run of 64-row tap tiles of the resident weights)
-//   bits 14..22  accumulator column (slot * 256 + ox * 64)
-//   bit  23      identity group: 4 x (N = 16) instructions spreading the tile over 64 columns (residual branch)
-//   bit  24      accumulate flag of the first instruction (0 = the group starts these output positions)
-//   bits 25..26  N / 64 - 1
-//   bit  27      first group of a ring tile (wait for the tile)     bit 28  last group of a ring tile (release it)
-//   bit  29/30   output row in accumulator slot 0/1 is complete after this group
-//   bit  31      first use of the accumulator slot in this half (wait until the epilogue has drained it)
-constexpr int CR_MAX_GROUPS = 176;
+// The per-M-tile work list is static.  The producer walks `ring[i]` = which [128 x 64] activation tile to load
+// i-th (map << 4 | position), compiled on the host by conv_res_build_schedule; the MMA issuer runs the same order as
+// fully unrolled straight-line code (cr_issue_mtile): with one thread issuing, every instruction between two
+// tcgen05.mma is tensor-pipe idle time, and an interpreted schedule cost ~350 cycles per group of four MMAs
+// (measured: the skeleton without any MMA / memory traffic ran at 60 % of the full kernel's time).
 constexpr int CR_MAX_RING = 80;
-constexpr uint32_t CR_G_IDENT = 1u << 23, CR_G_ACC = 1u << 24, CR_G_FIRST = 1u << 27, CR_G_LAST = 1u << 28,
-                   CR_G_DONE0 = 1u << 29, CR_G_DONE1 = 1u << 30, CR_G_NEED_ACC = 1u << 31;
 
 struct ConvResParams {
-  CUtensorMap a_map[4];        // x_hi, x_lo, residual hi, residual lo: 2-D [rows][1024] fp16, box {64, 128}, SWIZZLE_128B
+  CUtensorMap a_map[4];        // x_hi, x_lo, residual hi, residual lo (tiled layout): 2-D [rows*16][64] fp16, box {64, 128}, SWIZZLE_128B
   CUtensorMap w_map;           // resident weights: 2-D [planes*9*64][64] fp16, box {64, 64}; tile (plane, ky, 2-kx)
-  CUtensorMap out_map[2];      // output hi, lo: 2-D [rows][1024] fp16, box {32, 128}, SWIZZLE_64B
+  CUtensorMap out_map[2];      // output hi, lo (tiled layout): 2-D [rows*16][64] fp16, box {32, 128}, SWIZZLE_64B
   const int* n_rows_dev;
   int n_rows;
   int split;                   // 1: hi/lo planes, three products; 0: single fp16 product
   int has_aux_lo;              // residual has a lo plane
-  int n_ring, n_groups;
+  int debug;                   // test hook only (AV1P_CR_DEBUG): 1 skip MMA issue, 2 skip staging/stores, 4 skip TMA loads, 8 skip L2 prefetch, 16 skip the epilogue
+  int n_ring;
   uint8_t ring[CR_MAX_RING];
-  uint32_t tab[CR_MAX_GROUPS];
   // epilogue members (names shared with FcParams, see epi_tile_store)
   int epi;
   const float* bias;           // [1024]
@@ -81,13 +72,150 @@ struct ConvResParams {
   float acc_scale;
   const __half* aux;           // unused (no gate epilogue here)
   const __half* aux_lo;
-  int aux_ld;
+  int aux_kb;
   __half* out;
   __half* out_lo;
-  int out_ld;
+  int out_kb;                  // 16
   int* err_flag;
 };
 
+// One group = four K=16 instructions of one ring tile against a run of n64 resident tap tiles.
+__device__ __forceinline__ void cr_group(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t n64, uint32_t acc0) {
+  const uint32_t idesc = 0x08000010u + (n64 << 20);          // umma_idesc_f16(64 * n64)
+  umma_f16_ss_lo(d_tmem, a_lo, b_lo, idesc, acc0);
+  umma_f16_ss_lo(d_tmem, a_lo + 2, b_lo + 2, idesc, 1u);
+  umma_f16_ss_lo(d_tmem, a_lo + 4, b_lo + 4, idesc, 1u);
+  umma_f16_ss_lo(d_tmem, a_lo + 6, b_lo + 6, idesc, 1u);
+}
+
+struct CrPipe {
+  uint64_t* full_bar;
+  uint64_t* empty_bar;
+  uint64_t* acc_full;
+  uint64_t* acc_empty;
+  int stage;
+  uint32_t phase;
+  uint32_t acc_phase;      // bit s: parity of accumulator slot s
+};
+
+// MMA issue for one M tile, straight-line (every loop below has compile-time bounds and unrolls completely).
+template <bool SPLIT, bool RESID, bool AUX_LO>
+__device__ __forceinline__ void cr_issue_mtile(CrPipe& q, uint32_t base, uint32_t tmem_base, uint64_t id_desc, int* err_flag,
+                                               bool skip_mma) {
+  constexpr int PLANES = SPLIT ? 2 : 1;
+  constexpr int AUX_PLANES = AUX_LO ? 2 : 1;
+  const uint32_t w_lo0 = umma_desc_lo_sw128(base + CR_OFF_W);
+  const uint32_t idesc_id = umma_idesc_f16(16u);
+  auto wait_tile = [&]() -> uint32_t {
+    mbar_wait(&q.full_bar[q.stage], q.phase, err_flag, 300 + q.stage);
+    return umma_desc_lo_sw128(base + q.stage * CR_A_BYTES);
+  };
+  auto next_stage = [&]() {
+    if (++q.stage == CR_STAGES) {
+      q.stage = 0;
+      q.phase ^= 1u;
+    }
+  };
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+#pragma unroll
+    for (int iyi = 0; iyi < 3; ++iyi) {
+      const int iy = h + iyi;
+#pragma unroll
+      for (int xi = 0; xi < 4; ++xi) {
+        const int ix = xi == 0 ? 1 : (xi == 1 ? 0 : xi);        // order 1, 0, 2, 3: a fresh output row starts with one N = 192 group
+        const int ox0 = ix > 0 ? ix - 1 : 0;
+        const int ox1 = ix < 3 ? ix + 1 : 3;
+#pragma unroll
+        for (int pl = 0; pl < PLANES; ++pl) {
+          const uint32_t a_lo = wait_tile();
+          if (xi == 0 && pl == 0) {
+            // first use of an accumulator slot in this half: the epilogue must have drained it
+#pragma unroll
+            for (int o = 0; o < 2; ++o) {
+              const int oy = 2 * h + o;
+              const int first_iy = oy < 2 ? 0 : oy - 1;
+              if (iy == first_iy) mbar_wait(&q.acc_empty[o], ((q.acc_phase >> o) & 1u) ^ 1u, err_flag, 200 + o);
+            }
+          }
+          tc_fence_after_sync();
+          if (elect_one_sync()) {
+            if (!skip_mma) {
+#pragma unroll
+              for (int o = 0; o < 2; ++o) {
+                const int oy = 2 * h + o;
+                const int ky = iy - oy + 1;
+                if (ky < 0 || ky > 2) continue;
+                const int first_iy = oy < 2 ? 0 : oy - 1;
+                const bool fresh = (iy == first_iy) && pl == 0;      // positions may still hold the previous tile's sums
+                const uint32_t d_row = tmem_base + uint32_t(o * 256);
+                // taps for ox..oe are kx = ix-ox+1 .. (descending) = tiles (2 - kx_first).. of the ky stack
+                auto run = [&](int ox, int oe, uint32_t acc0) {
+                  const uint32_t tile = uint32_t(ky * 3 + (2 - (ix - ox + 1)));
+                  const uint32_t b_hi = w_lo0 + tile * (CR_W_TILE_BYTES >> 4);
+                  cr_group(d_row + uint32_t(ox * 64), a_lo, b_hi, uint32_t(oe - ox + 1), acc0);
+                  if (SPLIT && pl == 0)
+                    cr_group(d_row + uint32_t(ox * 64), a_lo, b_hi + (CR_W_PLANE_BYTES >> 4), uint32_t(oe - ox + 1), 1u);
+                };
+                if (!fresh || xi == 1 || xi == 3) {
+                  run(ox0, ox1, 1u);
+                } else if (xi == 0) {
+                  run(ox0, ox1, 0u);          // ix = 1: positions 0..2, all fresh
+                } else {
+                  run(1, 2, 1u);              // ix = 2: positions 1, 2 were started by ix = 1 ...
+                  run(3, 3, 0u);              // ... position 3 is new
+                }
+              }
+            }
+            umma_commit(&q.empty_bar[q.stage]);     // frees the ring slot once these MMAs have read it
+            if (!RESID && xi == 3 && pl == PLANES - 1) {
+#pragma unroll
+              for (int o = 0; o < 2; ++o) {
+                const int oy = 2 * h + o;
+                if (iy == (oy < 3 ? oy + 1 : 3)) umma_commit(&q.acc_full[o]);    // output row complete -> epilogue
+              }
+            }
+          }
+          __syncwarp();
+          next_stage();
+        }
+      }
+      // output rows whose last input row is iy
+#pragma unroll
+      for (int o = 0; o < 2; ++o) {
+        const int oy = 2 * h + o;
+        if (iy != (oy < 3 ? oy + 1 : 3)) continue;
+        if (RESID) {
+#pragma unroll
+          for (int ox = 0; ox < 4; ++ox) {
+#pragma unroll
+            for (int pl = 0; pl < AUX_PLANES; ++pl) {
+              const uint32_t a_lo = wait_tile();
+              tc_fence_after_sync();
+              if (elect_one_sync()) {
+                const uint32_t d_tmem = tmem_base + uint32_t(o * 256 + ox * 64);
+                if (!skip_mma) {
+#pragma unroll
+                  for (int j = 0; j < FC_TILE_K / 16; ++j) {
+                    const uint64_t a_desc = (uint64_t(0x40004040u) << 32) | uint64_t(a_lo + 2 * j);
+                    umma_f16_ss(d_tmem + j * 16, a_desc, id_desc, idesc_id, 1u);
+                  }
+                }
+                umma_commit(&q.empty_bar[q.stage]);
+                if (ox == 3 && pl == AUX_PLANES - 1) umma_commit(&q.acc_full[o]);
+              }
+              __syncwarp();
+              next_stage();
+            }
+          }
+        }
+        q.acc_phase ^= 1u << o;
+      }
+    }
+  }
+}
+
+template <bool SPLIT, bool RESID, bool AUX_LO>
 __global__ void __launch_bounds__(CR_THREADS, 1) conv_res_tcgen05_kernel(const __grid_constant__ ConvResParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -107,8 +235,8 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_res_tcgen05_kernel(const _
   const int lane = threadIdx.x & 31;
   const int n_rows = p.n_rows_dev ? *p.n_rows_dev : p.n_rows;
   const int m_tiles = (n_rows + FC_TILE_M - 1) / FC_TILE_M;
-  const int planes = p.split ? 2 : 1;
-  const bool residual = p.epi == FC_EPI_ADD_RELU;
+  constexpr int planes = SPLIT ? 2 : 1;
+  constexpr bool residual = RESID;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.a_map[0]);
@@ -161,7 +289,7 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_res_tcgen05_kernel(const _
       auto prefetch_next = [&]() {
         if (pf_mt >= m_tiles) return;
         const uint32_t e = p.ring[pf_i];
-        if (elect_one_sync()) tma_prefetch_l2_2d(&p.a_map[e >> 4], int(e & 15u) * FC_TILE_K, pf_mt * FC_TILE_M);
+        if (!(p.debug & 8) && elect_one_sync()) tma_prefetch_l2_2d(&p.a_map[e >> 4], 0, (pf_mt * 16 + int(e & 15u)) * FC_TILE_M);
         __syncwarp();
         if (++pf_i == p.n_ring) {
           pf_i = 0;
@@ -175,8 +303,12 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_res_tcgen05_kernel(const _
           prefetch_next();
           mbar_wait(&empty_bar[stage], phase ^ 1u, p.err_flag, 100 + stage);
           if (elect_one_sync()) {
-            mbar_arrive_expect_tx(&full_bar[stage], CR_A_BYTES);
-            tma_load_2d(smem + stage * CR_A_BYTES, &p.a_map[e >> 4], &full_bar[stage], int(e & 15u) * FC_TILE_K, mt * FC_TILE_M);
+            if (p.debug & 4) {
+              mbar_arrive(&full_bar[stage]);
+            } else {
+              mbar_arrive_expect_tx(&full_bar[stage], CR_A_BYTES);
+              tma_load_2d(smem + stage * CR_A_BYTES, &p.a_map[e >> 4], &full_bar[stage], 0, (mt * 16 + int(e & 15u)) * FC_TILE_M);
+            }
           }
           __syncwarp();
           if (++stage == CR_STAGES) {
@@ -187,56 +319,14 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_res_tcgen05_kernel(const _
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer (warp-uniform loop, one lane issues)
+    // ------------------------------------------------------------ MMA issuer (warp-uniform, one lane issues)
     if (blockIdx.x < m_tiles) {
-      int stage = 0;
-      uint32_t phase = 0;
-      uint32_t acc_phase = 0u;               // bit s: parity of accumulator slot s
-      const uint32_t idesc_id = umma_idesc_f16(16u);
+      CrPipe q{full_bar, empty_bar, acc_full, acc_empty, 0, 0u, 0u};
       const uint64_t id_desc = ident_desc(base + CR_OFF_IDENT);
       mbar_wait(w_bar, 0u, p.err_flag, 500);
       tc_fence_after_sync();
-      for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x) {
-        uint32_t a_addr = 0;
-        for (int gi = 0; gi < p.n_groups; ++gi) {
-          const uint32_t w = p.tab[gi];
-          const uint32_t d_col = (w >> 14) & 0x1FFu;
-          const uint32_t slot = d_col >> 8;
-          if (w & CR_G_FIRST) {
-            mbar_wait(&full_bar[stage], phase, p.err_flag, 300 + stage);
-            a_addr = base + stage * CR_A_BYTES;
-          }
-          if (w & CR_G_NEED_ACC) mbar_wait(&acc_empty[slot], ((acc_phase >> slot) & 1u) ^ 1u, p.err_flag, 200 + slot);
-          tc_fence_after_sync();
-          if (elect_one_sync()) {
-            const uint32_t d_tmem = tmem_base + d_col;
-            if (w & CR_G_IDENT) {
-#pragma unroll
-              for (int j = 0; j < FC_TILE_K / 16; ++j)
-                umma_f16_ss(d_tmem + j * 16, umma_desc_sw128(a_addr + j * 32), id_desc, idesc_id, 1u);
-            } else {
-              const uint32_t b_addr = base + ((w & 0x3FFFu) << 4);
-              const uint32_t idesc = umma_idesc_f16((((w >> 25) & 3u) + 1u) * 64u);
-              const uint32_t acc0 = (w >> 24) & 1u;
-#pragma unroll
-              for (int k = 0; k < FC_TILE_K / 16; ++k)
-                umma_f16_ss(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32), idesc,
-                            k > 0 ? 1u : acc0);
-            }
-            if (w & CR_G_LAST) umma_commit(&empty_bar[stage]);   // frees the ring slot once these MMAs have read it
-            if (w & CR_G_DONE0) umma_commit(&acc_full[0]);
-            if (w & CR_G_DONE1) umma_commit(&acc_full[1]);
-          }
-          __syncwarp();
-          if (w & CR_G_LAST) {
-            if (++stage == CR_STAGES) {
-              stage = 0;
-              phase ^= 1u;
-            }
-          }
-          acc_phase ^= (w >> 29) & 3u;
-        }
-      }
+      for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x)
+        cr_issue_mtile<SPLIT, RESID, AUX_LO>(q, base, tmem_base, id_desc, p.err_flag, (p.debug & 1) != 0);
     }
   } else if (warp < FC_STORE_WARP) {
     // ------------------------------------------------------------ epilogue (warps 2..9): output rows 0..3 -> slots 0,1,0,1
@@ -254,9 +344,8 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_res_tcgen05_kernel(const _
     // ------------------------------------------------------------ store warp
     uint32_t g = 0;
     for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x) {
-      if ((mt + 1) * FC_TILE_M > n_rows) continue;
-      epi_store_chunks(es, g, &p.out_map[0], &p.out_map[1], p.out_lo != nullptr, 0, 1024 / EPI_CHUNK, mt * FC_TILE_M,
-                       p.err_flag);
+      if ((mt + 1) * FC_TILE_M > n_rows || (p.debug & 18)) continue;
+      epi_store_chunks(es, g, &p.out_map[0], &p.out_map[1], p.out_lo != nullptr, 0, 1024 / EPI_CHUNK, mt, 16, p.err_flag);
     }
     epi_store_drain();
   }
@@ -269,85 +358,53 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_res_tcgen05_kernel(const _
   }
 }
 
-// Host side: compile the static per-M-tile schedule (see ConvResParams) for the given precision / residual shape.
-// Order: two halves (output rows {0,1}, {2,3}); per half the three input rows it needs; per input row the
-// positions ix = 1, 0, 2, 3 (ix = 1 first so that a fresh output row starts with one N = 192 group); hi plane then
-// lo plane; after the last input row of an output row its residual tiles; groups of one ring tile are contiguous.
+// Host side: the producer's per-M-tile load order (must match cr_issue_mtile): two halves (output rows {0,1},
+// {2,3}); per half the three input rows it needs; per input row the positions ix = 1, 0, 2, 3; hi plane then lo
+// plane; after the last input row of an output row its four residual tiles.
 inline bool conv_res_build_schedule(ConvResParams& f) {
   const int planes = f.split ? 2 : 1;
   const bool residual = f.epi == FC_EPI_ADD_RELU;
   const int aux_planes = f.has_aux_lo ? 2 : 1;
-  int n_ring = 0, n_groups = 0;
-  auto push_group = [&](uint32_t w) -> bool {
-    if (n_groups >= CR_MAX_GROUPS) return false;
-    f.tab[n_groups++] = w;
-    return true;
-  };
   static const int ix_order[4] = {1, 0, 2, 3};
+  int n = 0;
   for (int h = 0; h < 2; ++h) {
-    uint32_t init_mask[2] = {0u, 0u};
-    bool touched[2] = {false, false};
     for (int iy = h; iy < h + 3; ++iy) {
-      for (int xi = 0; xi < 4; ++xi) {
-        const int ix = ix_order[xi];
-        const int ox0 = ix > 0 ? ix - 1 : 0, ox1 = ix < 3 ? ix + 1 : 3;
+      for (int xi = 0; xi < 4; ++xi)
         for (int pl = 0; pl < planes; ++pl) {
-          if (n_ring >= CR_MAX_RING) return false;
-          f.ring[n_ring++] = uint8_t((pl << 4) | (iy * 4 + ix));
-          const int g_first = n_groups;
-          for (int oy = 2 * h; oy < 2 * h + 2; ++oy) {
-            const int ky = iy - oy + 1;
-            if (ky < 0 || ky > 2) continue;
-            const int slot = oy & 1;
-            uint32_t need = 0u;
-            if (!touched[slot]) {
-              need = CR_G_NEED_ACC;
-              touched[slot] = true;
-            }
-            const uint32_t im = pl ? 0xFu : init_mask[slot];
-            int ox = ox0;
-            while (ox <= ox1) {
-              const uint32_t st = (im >> ox) & 1u;
-              int oe = ox;
-              while (oe + 1 <= ox1 && ((im >> (oe + 1)) & 1u) == st) ++oe;
-              const uint32_t n64 = uint32_t(oe - ox + 1);
-              const uint32_t d_col = uint32_t(slot * 256 + ox * 64);
-              // taps for ox..oe are kx = ix-ox+1 .. ix-oe+1 (descending) = tiles (2-kx_first).. of the ky stack
-              const uint32_t tile = uint32_t(ky * 3 + (2 - (ix - ox + 1)));
-              const uint32_t w_hi = (uint32_t(CR_OFF_W) + tile * CR_W_TILE_BYTES) >> 4;
-              const uint32_t w_lo = (uint32_t(CR_OFF_W) + CR_W_PLANE_BYTES + tile * CR_W_TILE_BYTES) >> 4;
-              const uint32_t common = (d_col << 14) | ((n64 - 1u) << 25);
-              if (!push_group(w_hi | common | (st ? CR_G_ACC : 0u) | need)) return false;
-              need = 0u;
-              if (f.split && pl == 0)
-                if (!push_group(w_lo | common | CR_G_ACC)) return false;
-              ox = oe + 1;
-            }
-            if (pl == 0) init_mask[slot] |= (1u << (ox1 + 1)) - (1u << ox0);
-          }
-          f.tab[g_first] |= CR_G_FIRST;
-          f.tab[n_groups - 1] |= CR_G_LAST;
+          if (n >= CR_MAX_RING) return false;
+          f.ring[n++] = uint8_t((pl << 4) | (iy * 4 + ix_order[xi]));
         }
-      }
       for (int oy = 2 * h; oy < 2 * h + 2; ++oy) {
-        if (iy != (oy < 3 ? oy + 1 : 3)) continue;
-        const int slot = oy & 1;
-        if (residual) {
-          for (int ox = 0; ox < 4; ++ox) {
-            for (int pl = 0; pl < aux_planes; ++pl) {
-              if (n_ring >= CR_MAX_RING) return false;
-              f.ring[n_ring++] = uint8_t(((2 + pl) << 4) | (oy * 4 + ox));
-              if (!push_group((uint32_t(slot * 256 + ox * 64) << 14) | CR_G_IDENT | CR_G_ACC | CR_G_FIRST | CR_G_LAST)) return false;
-            }
+        if (!residual || iy != (oy < 3 ? oy + 1 : 3)) continue;
+        for (int ox = 0; ox < 4; ++ox)
+          for (int pl = 0; pl < aux_planes; ++pl) {
+            if (n >= CR_MAX_RING) return false;
+            f.ring[n++] = uint8_t(((2 + pl) << 4) | (oy * 4 + ox));
           }
-        }
-        f.tab[n_groups - 1] |= slot ? CR_G_DONE1 : CR_G_DONE0;
       }
     }
   }
-  f.n_ring = n_ring;
-  f.n_groups = n_groups;
+  f.n_ring = n;
   return true;
+}
+
+// Kernel variant for the given shape (split precision / residual branch / residual lo plane).
+typedef void (*ConvResKernel)(const ConvResParams);
+inline ConvResKernel conv_res_kernel_for(const ConvResParams& f) {
+  const bool resid = f.epi == FC_EPI_ADD_RELU;
+  if (f.split) {
+    if (!resid) return conv_res_tcgen05_kernel<true, false, false>;
+    return f.has_aux_lo ? conv_res_tcgen05_kernel<true, true, true> : conv_res_tcgen05_kernel<true, true, false>;
+  }
+  if (!resid) return conv_res_tcgen05_kernel<false, false, false>;
+  return f.has_aux_lo ? conv_res_tcgen05_kernel<false, true, true> : conv_res_tcgen05_kernel<false, true, false>;
+}
+inline const ConvResKernel* conv_res_all_kernels(int* n) {
+  static const ConvResKernel all[6] = {conv_res_tcgen05_kernel<true, false, false>, conv_res_tcgen05_kernel<true, true, true>,
+                                       conv_res_tcgen05_kernel<true, true, false>, conv_res_tcgen05_kernel<false, false, false>,
+                                       conv_res_tcgen05_kernel<false, true, true>, conv_res_tcgen05_kernel<false, true, false>};
+  *n = 6;
+  return all;
 }
 
 }  // namespace av1p

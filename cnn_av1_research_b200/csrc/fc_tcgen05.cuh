@@ -69,9 +69,10 @@ enum FcEpilogue : int {
 };
 
 struct FcParams {
-  CUtensorMap a_map[FC_MAX_SRC]; // activation sources, 2-D [rows][K] fp16, box {64, 128}, SWIZZLE_128B
+  CUtensorMap a_map[FC_MAX_SRC]; // activation sources (tiled layout, see act_off): 2-D [rows*KB][64] fp16, box {64, 128}, SWIZZLE_128B
   CUtensorMap w_map;           // packed weights, 2-D [n_kb_total*block_n][64] fp16, box {64, block_n}
-  CUtensorMap out_map[2];      // output hi / lo planes, 2-D [rows][out_ld] fp16, box {32, 128}, SWIZZLE_64B
+  CUtensorMap out_map[2];      // output hi / lo planes (tiled layout): 2-D [rows*KB][64] fp16, box {32, 128}, SWIZZLE_64B
+  int src_kb[FC_MAX_SRC];      // 64-column blocks per row of each source buffer
   const int* n_rows_dev;       // device-side row count (nullptr -> n_rows)
   int n_rows;
   int n_tiles;                 // number of N tiles
@@ -82,10 +83,10 @@ struct FcParams {
   float acc_scale;             // power of two undoing the weight pre-scale
   const __half* aux;           // gate input rows (FC_EPI_GATE only)
   const __half* aux_lo;        // split mode: low part of aux (nullptr otherwise)
-  int aux_ld;
+  int aux_kb;                  // 64-column blocks per row of the aux buffer
   __half* out;
   __half* out_lo;              // split mode: low part of the output (nullptr otherwise)
-  int out_ld;
+  int out_kb;                  // 64-column blocks per row of the output buffer
   const float* tail_w;         // [tail_n][block_n]
   const float* tail_b;         // [tail_n]
   float* logits;               // [rows][tail_n]
@@ -142,15 +143,17 @@ __device__ __forceinline__ uint64_t ident_desc(uint32_t ident_addr) { return umm
 // chunk g is issued the previous group's smem reads are awaited and its set handed back, so the TMA read of one
 // set overlaps the epilogue writing the other.
 __device__ __forceinline__ void epi_store_chunks(const EpiStage& es, uint32_t& g, const CUtensorMap* map_hi,
-                                                 const CUtensorMap* map_lo, bool has_lo, int col0, int n_chunks, int row0,
-                                                 int* err_flag) {
+                                                 const CUtensorMap* map_lo, bool has_lo, int col0, int n_chunks, int mt,
+                                                 int out_kb, int* err_flag) {
   const bool leader = (threadIdx.x & 31) == 0;
   for (int c = 0; c < n_chunks; ++c, ++g) {
     const uint32_t set = g & 1u;
     mbar_wait(&es.full[set], (g >> 1) & 1u, err_flag, 900);
     if (leader) {
-      tma_store_2d(map_hi, es.unit(set, 0), col0 + c * EPI_CHUNK, row0);
-      if (has_lo) tma_store_2d(map_lo, es.unit(set, 1), col0 + c * EPI_CHUNK, row0);
+      const int col = col0 + c * EPI_CHUNK;
+      const int trow = (mt * out_kb + (col >> 6)) * FC_TILE_M;      // tiled layout: tile (mt, col / 64)
+      tma_store_2d(map_hi, es.unit(set, 0), col & 63, trow);
+      if (has_lo) tma_store_2d(map_lo, es.unit(set, 1), col & 63, trow);
       tma_store_commit();
       if (g > 0) {
         tma_store_wait_read<1>();               // every group but the one just committed has been read
@@ -174,6 +177,10 @@ __device__ __forceinline__ void epi_store_drain() {
 // TMEM read has completed.  The TMEM read of chunk c+1 is in flight while chunk c is converted and staged.
 // P is FcParams or any struct with the same epilogue members.
 template <typename P>
+__device__ __forceinline__ int epi_debug(const P& p) {
+  if constexpr (requires { p.debug; }) return p.debug; else return 0;
+}
+template <typename P>
 __device__ __forceinline__ void epi_tile_store(const P& p, const EpiStage& es, uint32_t& g, int n_rows, int mt, int col0,
                                                int block_n, uint32_t t_col, uint64_t* full, uint32_t full_phase,
                                                uint64_t* empty, int warp, int lane, int tag) {
@@ -182,7 +189,8 @@ __device__ __forceinline__ void epi_tile_store(const P& p, const EpiStage& es, u
   const int r_local = quad * 32 + lane;
   const int row = mt * FC_TILE_M + r_local;
   const bool row_ok = row < n_rows;
-  const bool staged = (mt + 1) * FC_TILE_M <= n_rows;
+  const bool skip_out = (epi_debug(p) & 2) != 0;
+  const bool staged = (mt + 1) * FC_TILE_M <= n_rows && !skip_out;
   const bool gate = p.epi == FC_EPI_GATE;
   const bool relu = p.epi == FC_EPI_RELU || p.epi == FC_EPI_ADD_RELU;
   const bool has_lo = p.out_lo != nullptr;
@@ -192,11 +200,18 @@ __device__ __forceinline__ void epi_tile_store(const P& p, const EpiStage& es, u
   const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
   uint4 ax = zero4, axl = zero4;
   if (gate && row_ok) {
-    ax = __ldg(reinterpret_cast<const uint4*>(p.aux + size_t(row) * p.aux_ld + col0 + tcol));
-    if (p.aux_lo) axl = __ldg(reinterpret_cast<const uint4*>(p.aux_lo + size_t(row) * p.aux_ld + col0 + tcol));
+    const size_t o = act_off(row, col0 + tcol, p.aux_kb);
+    ax = __ldg(reinterpret_cast<const uint4*>(p.aux + o));
+    if (p.aux_lo) axl = __ldg(reinterpret_cast<const uint4*>(p.aux_lo + o));
   }
   mbar_wait(full, full_phase, p.err_flag, tag);
   tc_fence_after_sync();
+  if (epi_debug(p) & 16) {        // development switch: hand the accumulator straight back
+    tc_fence_before_sync();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty);
+    return;
+  }
   const uint32_t t_addr = t_col + (uint32_t(quad * 32) << 16) + uint32_t(tcol);
   uint32_t v[8];
   tmem_ld_32x8(t_addr, v);
@@ -209,8 +224,9 @@ __device__ __forceinline__ void epi_tile_store(const P& p, const EpiStage& es, u
     }
     uint4 nx = zero4, nxl = zero4;
     if (gate && row_ok && c + 1 < n_chunks) {
-      nx = __ldg(reinterpret_cast<const uint4*>(p.aux + size_t(row) * p.aux_ld + col + EPI_CHUNK));
-      if (p.aux_lo) nxl = __ldg(reinterpret_cast<const uint4*>(p.aux_lo + size_t(row) * p.aux_ld + col + EPI_CHUNK));
+      const size_t o = act_off(row, col + EPI_CHUNK, p.aux_kb);
+      nx = __ldg(reinterpret_cast<const uint4*>(p.aux + o));
+      if (p.aux_lo) nxl = __ldg(reinterpret_cast<const uint4*>(p.aux_lo + o));
     }
     tmem_ld_wait();
     float f[8];
@@ -262,9 +278,10 @@ __device__ __forceinline__ void epi_tile_store(const P& p, const EpiStage& es, u
       __syncwarp();
       if (lane == 0) mbar_arrive(&es.full[set]);
       ++g;
-    } else if (row_ok) {
-      *reinterpret_cast<uint4*>(p.out + size_t(row) * p.out_ld + col) = hq;
-      if (has_lo) *reinterpret_cast<uint4*>(p.out_lo + size_t(row) * p.out_ld + col) = lq;
+    } else if (row_ok && !skip_out) {
+      const size_t o = act_off(row, col, p.out_kb);
+      *reinterpret_cast<uint4*>(p.out + o) = hq;
+      if (has_lo) *reinterpret_cast<uint4*>(p.out_lo + o) = lq;
     }
   }
 }
@@ -394,7 +411,8 @@ __global__ void __launch_bounds__(FC_THREADS, 1) fc_tcgen05_kernel(const __grid_
         uint8_t* a_dst = smem + stage * FC_STAGE_BYTES;
         if (elect_one_sync()) {
           mbar_arrive_expect_tx(&full_bar[stage], wi == FC_W_IDENT ? uint32_t(FC_A_BYTES) : tx_bytes);
-          tma_load_2d(a_dst, &p.a_map[e >> 14], &full_bar[stage], int(e & 0x3FFFu) * FC_TILE_K, mt * FC_TILE_M);
+          tma_load_2d(a_dst, &p.a_map[e >> 14], &full_bar[stage], 0,
+                      (mt * p.src_kb[e >> 14] + int(e & 0x3FFFu)) * FC_TILE_M);
           if (wi != FC_W_IDENT) tma_load_2d(a_dst + FC_A_BYTES, &p.w_map, &full_bar[stage], 0, int(wi) * p.block_n);
         }
         __syncwarp();
@@ -506,7 +524,7 @@ __global__ void __launch_bounds__(FC_THREADS, 1) fc_tcgen05_kernel(const __grid_
         const int nt = item - mt * p.n_tiles;
         if ((mt + 1) * FC_TILE_M > n_rows) continue;      // partial tile: the epilogue stores it directly
         epi_store_chunks(es, g, &p.out_map[0], &p.out_map[1], p.out_lo != nullptr, nt * p.block_n, p.block_n / EPI_CHUNK,
-                         mt * FC_TILE_M, p.err_flag);
+                         mt, p.out_kb, p.err_flag);
       }
       epi_store_drain();
     }

@@ -9,6 +9,14 @@
 
 namespace av1p {
 
+// Activation buffers use a TILED layout: a buffer of C fp16 columns (C a multiple of 64, KB = C / 64) and R rows
+// (R a multiple of 128) is stored as [R / 128][KB][128 rows][64 cols], i.e. every [128 x 64] operand tile the
+// tensor-core kernels load with one TMA box is one contiguous 16 KB region (row-major buffers made each tile 128
+// scattered 128-byte pieces at a 2 KB pitch and DRAM ran at ~45 % of its bandwidth).  Element (row, col):
+__host__ __device__ __forceinline__ size_t act_off(int row, int col, int kb_per_row) {
+  return ((size_t(row >> 7) * size_t(kb_per_row) + size_t(col >> 6)) << 13) + (size_t(row & 127) << 6) + size_t(col & 63);
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
@@ -139,6 +147,23 @@ __device__ __forceinline__ void umma_f16_ss(uint32_t tmem_d, uint64_t desc_a, ui
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
       "}"
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Same with both operands in the SWIZZLE_128B K-major layout given by the LOW descriptor words only
+// (umma_desc_lo_sw128); the high word is the constant 0x40004040 (SBO 1024 B, version 1, SWIZZLE_128B).  Advancing
+// along K by 16 elements (32 B) is +2 on the low word.  Keeps the issuing thread's work per instruction to one add.
+__device__ __forceinline__ uint32_t umma_desc_lo_sw128(uint32_t smem_addr) { return ((smem_addr >> 4) & 0x3FFFu) | (1u << 16); }
+__device__ __forceinline__ void umma_f16_ss_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t"
+      "}"
+      ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(0x40004040u)
       : "memory");
 }
 // Arrive on an mbarrier once every previously issued tcgen05.mma of this thread has completed.

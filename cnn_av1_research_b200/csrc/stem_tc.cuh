@@ -52,7 +52,7 @@ struct StemParams {
   const __half* w;          // [2][128][64] folded conv1 weights x 2^s: hi plane then lo plane, K = ky*7+kx (49..63 zero)
   const float* b;           // [64] folded bias
   float acc_scale;          // 2^-s
-  __half* out;              // [rows][1024]
+  __half* out;              // [rows][1024] in the tiled activation layout (act_off, 16 blocks per row)
   __half* out_lo;           // split precision: fp16(x - fp16(x)), nullptr otherwise
   int* err_flag;
 };
@@ -266,8 +266,10 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_tc_kernel(const __grid_con
           cv[i] = fmaxf(fmaf(__uint_as_float(v0[i]), p.acc_scale, bias), 0.f);
           cv[32 + i] = fmaxf(fmaf(__uint_as_float(v1[i]), p.acc_scale, bias), 0.f);
         }
-        __half* o = p.out + size_t(r) * 1024 + ch;
-        __half* ol = p.out_lo ? p.out_lo + size_t(r) * 1024 + ch : nullptr;
+        // tiled activation layout (act_off): position q is the 64-column block q of row r
+        const size_t obase = act_off(r, ch, 16);
+        __half* o = p.out + obase;
+        __half* ol = p.out_lo ? p.out_lo + obase : nullptr;
 #pragma unroll
         for (int qy = 0; qy < 4; ++qy) {
 #pragma unroll
@@ -282,8 +284,8 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_tc_kernel(const __grid_con
               }
             }
             const __half h = __float2half_rn(m);
-            o[(qy * 4 + qx) * 64] = h;
-            if (ol) ol[(qy * 4 + qx) * 64] = __float2half_rn(m - __half2float(h));
+            o[size_t(qy * 4 + qx) << 13] = h;
+            if (ol) ol[size_t(qy * 4 + qx) << 13] = __float2half_rn(m - __half2float(h));
           }
         }
       }

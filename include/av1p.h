@@ -129,7 +129,10 @@ int av1p_upload_luma(const uint16_t* frames_host, int32_t n_frames, int32_t widt
  *      a_dev[i]: fp16 [rows][a_cols[i]] activation sources (unused entries NULL);
  *      w: fp16 [n_w_chunks*block_n][64]; kb_begin[n_tiles+1]; schedule entry e multiplies the 64-wide
  *      K block (kb_src[e] & 0x3fff) of source (kb_src[e] >> 14) with weight chunk kb_w[e].
- *      See csrc/fc_tcgen05.cuh for the epilogue codes. */
+ *      See csrc/fc_tcgen05.cuh for the epilogue codes.
+ *      Every activation matrix (a_dev, aux_dev, out_dev, their lo planes) is in the library's TILED layout:
+ *      rows padded to a multiple of 128, columns (a_cols / aux_ld / out_ld) a multiple of 64, stored as
+ *      [rows/128][cols/64][128][64] - element (r, c) at ((r/128 * cols/64 + c/64) * 128 + r%128) * 64 + c%64. */
 typedef struct av1p_fc_desc {
   const void* a_dev[4]; int32_t a_cols[4];
   int32_t rows;
@@ -153,7 +156,8 @@ int av1p_fc_forward(const av1p_fc_desc* d, void* stream);
  *      torchvision BasicBlock conv3x3 as used by models.py:110) on the resident-weight tcgen05 path
  *      (csrc/conv_res_tcgen05.cuh).  x: fp16 [rows][1024] ([position][channel] per block), x_lo its low
  *      plane (split != 0); w: fp16 [planes][ky][kx = 2,1,0][64 co][64 ci]; bias float32[1024];
- *      epi 0 linear, 1 relu, 2 relu(acc + bias + aux). */
+ *      epi 0 linear, 1 relu, 2 relu(acc + bias + aux).  x, aux and out use the tiled layout described above
+ *      (rows padded to 128, 16 column blocks). */
 typedef struct av1p_conv_res_desc {
   const void* x_dev; const void* x_lo_dev;
   int32_t rows;

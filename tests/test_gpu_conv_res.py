@@ -12,6 +12,7 @@ import torch
 import torch.nn.functional as F
 
 from cnn_av1_research_b200 import _native as N
+from fc_ref import from_tiled, to_tiled
 
 pytestmark = pytest.mark.gpu
 
@@ -26,10 +27,13 @@ def _run(x_hi, x_lo, w_hi, w_lo, bias, epi, aux_hi=None, aux_lo=None, acc_scale=
     rows = x_hi.shape[0]
     split = x_lo is not None
     wp = torch.cat([_pack_taps(w_hi), _pack_taps(w_lo)]) if split else _pack_taps(w_hi)
-    out = torch.full((rows, 1024), float("nan"), dtype=torch.float16, device=dev)
-    out_lo = torch.full((rows, 1024), float("nan"), dtype=torch.float16, device=dev) if split else None
-    d = N.ConvResDesc(x_dev=N.ptr(x_hi), x_lo_dev=N.ptr(x_lo), rows=rows, n_dev=N.ptr(n_dev), w_dev=N.ptr(wp), split=int(split),
-                      epi=epi, bias_dev=N.ptr(bias), acc_scale=acc_scale, aux_dev=N.ptr(aux_hi), aux_lo_dev=N.ptr(aux_lo),
+    nan = float("nan")
+    out = to_tiled(torch.full((rows, 1024), nan, dtype=torch.float16, device=dev), fill=nan)
+    out_lo = to_tiled(torch.full((rows, 1024), nan, dtype=torch.float16, device=dev), fill=nan) if split else None
+    tl = lambda t: to_tiled(t) if t is not None else None       # the kernel reads / writes the tiled activation layout
+    xt, xlt, at, alt = tl(x_hi), tl(x_lo), tl(aux_hi), tl(aux_lo)
+    d = N.ConvResDesc(x_dev=N.ptr(xt), x_lo_dev=N.ptr(xlt), rows=rows, n_dev=N.ptr(n_dev), w_dev=N.ptr(wp), split=int(split),
+                      epi=epi, bias_dev=N.ptr(bias), acc_scale=acc_scale, aux_dev=N.ptr(at), aux_lo_dev=N.ptr(alt),
                       out_dev=N.ptr(out), out_lo_dev=N.ptr(out_lo))
     with torch.cuda.device(dev):
         N.check(N.lib().av1p_conv_res_forward(C.byref(d), N.stream_handle(dev)))
@@ -37,7 +41,7 @@ def _run(x_hi, x_lo, w_hi, w_lo, bias, epi, aux_hi=None, aux_lo=None, acc_scale=
             torch.cuda.synchronize(dev)
         except Exception as exc:
             raise RuntimeError(f"conv kernel failed (watchdog tag {N.lib().av1p_debug_watchdog()}): {exc}") from exc
-    return out, out_lo
+    return from_tiled(out, rows, 1024), (from_tiled(out_lo, rows, 1024) if out_lo is not None else None)
 
 
 def _ref(x, w, bias, epi, aux=None, acc_scale=1.0):

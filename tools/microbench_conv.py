@@ -7,6 +7,7 @@ from cnn_av1_research_b200 import _native as N
 
 dev = torch.device("cuda:0")
 rows = int(sys.argv[1]) if len(sys.argv) > 1 else 259200
+assert rows % 128 == 0, 'rows must be a multiple of 128 (tiled layout; contents are random so no conversion is needed)'
 g = torch.Generator(device=dev).manual_seed(0)
 x_hi = torch.randn((rows, 1024), device=dev, generator=g).half()
 x_lo = (torch.randn((rows, 1024), device=dev, generator=g) * 1e-3).half()
@@ -38,7 +39,8 @@ def run(split, epi, lo_out=True, iters=5):
         ts.append(e0.elapsed_time(e1))
     return min(ts), sum(ts) / len(ts)
 
+dbg = os.environ.get("AV1P_CR_DEBUG", "0")
 for split in (0, 1):
     for epi in (1, 2):
         mn, av = run(split, epi)
-        print(f"rows {rows} split {split} epi {epi}: min {mn*1e3:.0f} us avg {av*1e3:.0f} us", flush=True)
+        print(f"debug {dbg} rows {rows} split {split} epi {epi}: min {mn*1e3:.0f} us avg {av*1e3:.0f} us", flush=True)
