@@ -2,9 +2,11 @@
 chiarorosa/cnn-av1-research).  See DESIGN.md and INTEGRATION.md at the repository root."""
 from .extraction import (BlockRecord, TorchBlockRecord, calculate_yuv420_10bit_sizes, extract_blocks_device,
                          extract_blocks_with_validation)
+from .flatten import (FlattenPipeline, evaluate_with_threshold, remap_flatten_to_original, run_pipeline_inference,
+                      sweep_thresholds)
 from .models import (CosineClassifier, FGVCModel, ImprovedBackbone, SEBlock, SpatialAttention, Stage1BinaryHead,
-                     Stage1Model, Stage2Model, Stage2ThreeWayHead, Stage3ABHead, Stage3ABModel, Stage3RectHead,
-                     Stage3RectModel)
+                     Stage1Model, Stage2FlatModel, Stage2Model, Stage2ThreeWayHead, Stage3ABHead, Stage3ABModel,
+                     Stage3RectHead, Stage3RectModel)
 from .pipeline import HierarchicalPipelineV6, evaluate_pipeline
 
 __all__ = [
@@ -12,4 +14,6 @@ __all__ = [
     "extract_blocks_with_validation", "CosineClassifier", "FGVCModel", "ImprovedBackbone", "SEBlock",
     "SpatialAttention", "Stage1BinaryHead", "Stage1Model", "Stage2Model", "Stage2ThreeWayHead", "Stage3ABHead",
     "Stage3ABModel", "Stage3RectHead", "Stage3RectModel", "HierarchicalPipelineV6", "evaluate_pipeline",
+    "Stage2FlatModel", "FlattenPipeline", "run_pipeline_inference", "remap_flatten_to_original",
+    "evaluate_with_threshold", "sweep_thresholds",
 ]

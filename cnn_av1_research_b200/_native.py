@@ -69,6 +69,15 @@ SIGNATURES = {
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "av1p_finalize_labels": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
                                        C.c_void_p, C.c_void_p]),
+    "av1p_finalize_labels_argmax": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
+                                              C.c_void_p, C.c_void_p]),
+    "av1p_flat_cascade_workspace_bytes": (C.c_size_t, [C.POINTER(C.c_void_p), C.c_int32]),
+    "av1p_flat_cascade_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int32, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
+    "av1p_flat_cascade_destroy": (None, [C.c_void_p]),
+    "av1p_flat_cascade_predict": (C.c_int, [C.c_void_p, C.POINTER(Input), C.c_int32, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "av1p_flat_cascade_buffer": (C.c_void_p, [C.c_void_p, C.c_int32]),
+    "av1p_threshold_sweep": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_double), C.c_int32, C.c_void_p, C.c_void_p,
+                                       C.c_void_p]),
     "av1p_fc_forward": (C.c_int, [C.POINTER(FcDesc), C.c_void_p]),
     "av1p_conv_res_forward": (C.c_int, [C.POINTER(ConvResDesc), C.c_void_p]),
     "av1p_profile_begin": (C.c_int, []),

@@ -474,33 +474,92 @@ __global__ void __launch_bounds__(ROUTE_THREADS) route_scatter_kernel(const Rout
   }
 }
 
-// Stage-3 label scatter: labels[idx[i]] = base + argmax softmax(logits[i, 0:k]) (first max wins).
+// Label scatter: labels[idx[i]] = base + argmax_j logits[i, j] (first max wins), k <= 8 classes.
+//   use_softmax = 1: argmax over softmax probabilities exactly as torch evaluates them (stage 3, 008:108-125);
+//   use_softmax = 0: argmax over the raw logits (flatten cascade, 008b:213 `stage2_logits.argmax(dim=1)`).
+constexpr int FINALIZE_MAX_K = 8;
 __global__ void __launch_bounds__(256) finalize_labels_kernel(const float* __restrict__ logits, int k, int base,
                                                               const int* __restrict__ idx, const int* n_dev, int n,
-                                                              uint8_t* labels_u8, long long* labels_i64) {
+                                                              uint8_t* labels_u8, long long* labels_i64, int use_softmax) {
   const int rows = n_dev ? *n_dev : n;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < rows; i += gridDim.x * blockDim.x) {
-    float x[4];
+    float x[FINALIZE_MAX_K];
     float m = -INFINITY;
-    for (int j = 0; j < k; ++j) {
-      x[j] = logits[i * k + j];
+#pragma unroll
+    for (int j = 0; j < FINALIZE_MAX_K; ++j) {
+      x[j] = j < k ? logits[size_t(i) * k + j] : -INFINITY;
       m = fmaxf(m, x[j]);
     }
-    float e[4], s = 0.f;
-    for (int j = 0; j < k; ++j) {
-      e[j] = softmax_exp(x[j], m);
-      s += e[j];
-    }
     int cls = 0;
-    float best = __fdiv_rn(e[0], s);
-    for (int j = 1; j < k; ++j) {
-      const float pj = __fdiv_rn(e[j], s);
-      if (pj > best) { best = pj; cls = j; }
+    if (use_softmax) {
+      float e[FINALIZE_MAX_K], s = 0.f;
+#pragma unroll
+      for (int j = 0; j < FINALIZE_MAX_K; ++j) {
+        e[j] = j < k ? softmax_exp(x[j], m) : 0.f;
+        if (j < k) s += e[j];
+      }
+      float best = __fdiv_rn(e[0], s);
+#pragma unroll
+      for (int j = 1; j < FINALIZE_MAX_K; ++j) {
+        const float pj = __fdiv_rn(e[j], s);
+        if (j < k && pj > best) { best = pj; cls = j; }
+      }
+    } else {
+      float best = x[0];
+#pragma unroll
+      for (int j = 1; j < FINALIZE_MAX_K; ++j)
+        if (j < k && x[j] > best) { best = x[j]; cls = j; }
     }
     const int g = idx[i];
     if (labels_u8) labels_u8[g] = uint8_t(base + cls);
     if (labels_i64) labels_i64[g] = base + cls;
   }
+}
+
+// ------------------------------------------------------------------------------------------
+// Stage-1 threshold sweep (reference scripts/007_optimize_thresholds.py:24-71): prob = sigmoid(logit) in fp32,
+// pred_t = prob >= thr[t], and for every threshold the confusion counts against the binary stage-1 label:
+// counts[t][0..3] = {tn, fp, fn, tp}.  One pass over the logits, warp-aggregated integer atomics -> exact.
+// Optionally writes the probabilities (what 007 collects on the host).  The reference compares a float32 numpy
+// array with np.float64 thresholds (np.arange, 007:153): under NumPy >= 2 that comparison runs in float64, so the
+// probability is widened, not the threshold narrowed.
+constexpr int SWEEP_MAX_T = 32;
+struct SweepParams {
+  const float* logits;
+  const uint8_t* labels;     // 0 / 1
+  int n;
+  int n_thr;
+  double thr[SWEEP_MAX_T];
+  float* probs;              // optional
+  unsigned long long* counts;   // [n_thr][4], zeroed by the caller
+};
+__global__ void __launch_bounds__(256) threshold_sweep_kernel(const SweepParams p) {
+  __shared__ unsigned int sm[SWEEP_MAX_T * 4];
+  for (int i = threadIdx.x; i < p.n_thr * 4; i += blockDim.x) sm[i] = 0u;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  for (int base = blockIdx.x * blockDim.x; base < p.n; base += gridDim.x * blockDim.x) {
+    const int i = base + threadIdx.x;
+    const bool ok = i < p.n;
+    float prob = 0.f;
+    int lab = 0;
+    if (ok) {
+      prob = 1.0f / (1.0f + expf(-p.logits[i]));            // torch.sigmoid in fp32
+      lab = p.labels[i] != 0;
+      if (p.probs) p.probs[i] = prob;
+    }
+    for (int t = 0; t < p.n_thr; ++t) {
+      const int cls = ok ? lab * 2 + (double(prob) >= p.thr[t] ? 1 : 0) : -1;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const unsigned int votes = __ballot_sync(0xffffffffu, cls == c);
+        if (lane == 0 && votes) atomicAdd(&sm[t * 4 + c], __popc(votes));
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < p.n_thr * 4; i += blockDim.x)
+    if (sm[i]) atomicAdd(&p.counts[i], (unsigned long long)sm[i]);
 }
 
 }  // namespace av1p

@@ -690,17 +690,47 @@ extern "C" int av1p_route_stage2(const float* logits3, const int32_t* idx_in, co
   return launch_route(rp, n, static_cast<cudaStream_t>(stream));
 }
 
-extern "C" int av1p_finalize_labels(const float* logits, int32_t k, int32_t base, const int32_t* idx,
-                                    const int32_t* n_dev, int32_t n, uint8_t* l8, int64_t* l64, void* stream) {
-  if (!logits || !idx || k < 1 || k > 4 || n < 0) return fail(AV1P_EINVAL, "bad argument");
+static int launch_finalize(const float* logits, int32_t k, int32_t base, const int32_t* idx, const int32_t* n_dev, int32_t n,
+                           uint8_t* l8, int64_t* l64, int use_softmax, void* stream) {
+  if (!logits || !idx || k < 1 || k > FINALIZE_MAX_K || n < 0) return fail(AV1P_EINVAL, "bad argument");
   if (n == 0) return AV1P_OK;
   if (int rc = ensure_ctx()) return rc;
   const int grid = std::min(ceil_div(n, 256), g_ctx.sms * 8);
   {
     ProfScope ps(PROF_FINALIZE, static_cast<cudaStream_t>(stream));
     finalize_labels_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        logits, k, base, idx, n_dev, n, l8, reinterpret_cast<long long*>(l64));
+        logits, k, base, idx, n_dev, n, l8, reinterpret_cast<long long*>(l64), use_softmax);
   }
+  CUDA_TRY(cudaGetLastError());
+  return AV1P_OK;
+}
+extern "C" int av1p_finalize_labels(const float* logits, int32_t k, int32_t base, const int32_t* idx,
+                                    const int32_t* n_dev, int32_t n, uint8_t* l8, int64_t* l64, void* stream) {
+  return launch_finalize(logits, k, base, idx, n_dev, n, l8, l64, 1, stream);
+}
+extern "C" int av1p_finalize_labels_argmax(const float* logits, int32_t k, int32_t base, const int32_t* idx,
+                                           const int32_t* n_dev, int32_t n, uint8_t* l8, int64_t* l64, void* stream) {
+  return launch_finalize(logits, k, base, idx, n_dev, n, l8, l64, 0, stream);
+}
+
+extern "C" int av1p_threshold_sweep(const float* logits, const uint8_t* labels, int32_t n, const double* thresholds_host,
+                                    int32_t n_thr, float* probs, uint64_t* counts, void* stream) {
+  if (!logits || !labels || !thresholds_host || !counts || n < 0 || n_thr < 1 || n_thr > SWEEP_MAX_T)
+    return fail(AV1P_EINVAL, "bad argument (1..%d thresholds per call)", SWEEP_MAX_T);
+  if (int rc = ensure_ctx()) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CUDA_TRY(cudaMemsetAsync(counts, 0, size_t(n_thr) * 4 * sizeof(uint64_t), st));
+  if (n == 0) return AV1P_OK;
+  SweepParams sp{};
+  sp.logits = logits;
+  sp.labels = labels;
+  sp.n = n;
+  sp.n_thr = n_thr;
+  for (int i = 0; i < n_thr; ++i) sp.thr[i] = thresholds_host[i];
+  sp.probs = probs;
+  sp.counts = reinterpret_cast<unsigned long long*>(counts);
+  const int grid = std::min(ceil_div(n, 256), g_ctx.sms * 8);
+  threshold_sweep_kernel<<<grid, 256, 0, st>>>(sp);
   CUDA_TRY(cudaGetLastError());
   return AV1P_OK;
 }
@@ -858,6 +888,108 @@ extern "C" int av1p_cascade_predict(av1p_cascade* c, const av1p_input* in, int32
   if (int rc = run_stage(&c->stage[3], si, c->idx_ab, n_ab, n_blocks, c->logits[3], st)) return rc;
   if (int rc = av1p_finalize_labels(c->logits[3], 4, 4, c->idx_ab, n_ab, n_blocks, l8, l64, st)) return rc;
   return AV1P_OK;
+}
+
+// ------------------------------------------------------------------------------ flatten cascade
+// Stage 1 -> 7-way Stage2FlatModel (reference scripts/008b_run_pipeline_flatten_eval.py:177-229): blocks whose
+// stage-1 probability reaches the threshold get label 1 + argmax of the 7 flat logits, the others label 0.
+struct av1p_flat_cascade {
+  av1p_stage stage[2];
+  int cap = 0;
+  float* logits[2] = {nullptr, nullptr};
+  int32_t* idx2 = nullptr;
+  int32_t* counts = nullptr;
+  RouteScratch* scratch = nullptr;
+};
+
+namespace {
+struct FlatLayout {
+  ActLayout act;
+  size_t logits_off[2], idx_off, counts_off, scratch_off, bytes;
+};
+FlatLayout make_flat_layout(const av1p_model* const models[2], int capacity) {
+  FlatLayout C;
+  C.act = make_act_layout(models, 2, capacity);
+  size_t o = C.act.bytes;
+  const int outs[2] = {1, 7};
+  for (int i = 0; i < 2; ++i) {
+    C.logits_off[i] = o;
+    o += align_up(size_t(C.act.cap) * outs[i] * 4, 1024);
+  }
+  C.idx_off = o;
+  o += align_up(size_t(C.act.cap) * 4, 1024);
+  C.counts_off = o;
+  o += 1024;
+  C.scratch_off = o;
+  o += align_up(sizeof(RouteScratch), 1024);
+  C.bytes = o;
+  return C;
+}
+}  // namespace
+
+extern "C" size_t av1p_flat_cascade_workspace_bytes(const av1p_model* const models[2], int32_t capacity) {
+  if (!models || !models[0] || !models[1] || capacity <= 0) return 0;
+  return make_flat_layout(models, capacity).bytes + 1024;
+}
+
+extern "C" int av1p_flat_cascade_create(const av1p_model* const models[2], int32_t capacity, void* ws, size_t ws_bytes,
+                                        av1p_flat_cascade** out) {
+  if (!models || !models[0] || !models[1] || !ws || !out || capacity <= 0) return fail(AV1P_EINVAL, "bad argument");
+  if (models[0]->hdr.n_out != 1 || models[1]->hdr.n_out != 7)
+    return fail(AV1P_EINVAL, "the flatten cascade needs a 1-output stage-1 model and a 7-output flat model");
+  if (int rc = ensure_ctx()) return rc;
+  FlatLayout C = make_flat_layout(models, capacity);
+  uint8_t* base = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<uintptr_t>(ws), 1024));
+  if (size_t(base - static_cast<uint8_t*>(ws)) + C.bytes > ws_bytes)
+    return fail(AV1P_ENOMEM, "workspace too small: need %zu bytes", C.bytes + 1024);
+  av1p_flat_cascade* c = new (std::nothrow) av1p_flat_cascade();
+  if (!c) return fail(AV1P_ENOMEM, "host allocation failed");
+  c->cap = C.act.cap;
+  for (int i = 0; i < 2; ++i) {
+    if (int rc = plan_stage(models[i], C.act, base, &c->stage[i])) {
+      delete c;
+      return rc;
+    }
+    c->logits[i] = reinterpret_cast<float*>(base + C.logits_off[i]);
+  }
+  c->idx2 = reinterpret_cast<int32_t*>(base + C.idx_off);
+  c->counts = reinterpret_cast<int32_t*>(base + C.counts_off);
+  c->scratch = reinterpret_cast<RouteScratch*>(base + C.scratch_off);
+  cudaError_t e = cudaMemset(base + C.counts_off, 0, C.bytes - C.counts_off);
+  if (e != cudaSuccess) {
+    delete c;
+    return fail(AV1P_ECUDA, "workspace init failed: %s", cudaGetErrorString(e));
+  }
+  *out = c;
+  return AV1P_OK;
+}
+extern "C" void av1p_flat_cascade_destroy(av1p_flat_cascade* c) { delete c; }
+
+extern "C" const void* av1p_flat_cascade_buffer(const av1p_flat_cascade* c, int32_t which) {
+  if (!c) return nullptr;
+  switch (which) {
+    case 0: case 1: return c->logits[which];
+    case 2: return c->idx2;
+    case 3: return c->counts;
+  }
+  return nullptr;
+}
+
+extern "C" int av1p_flat_cascade_predict(av1p_flat_cascade* c, const av1p_input* in, int32_t n_blocks, float thr, uint8_t* l8,
+                                         int64_t* l64, void* stream) {
+  if (!c) return fail(AV1P_EINVAL, "null cascade");
+  if (n_blocks < 0 || n_blocks > c->cap) return fail(AV1P_EINVAL, "n_blocks=%d outside [0, %d]", n_blocks, c->cap);
+  if (n_blocks == 0) return AV1P_OK;
+  StemInput si;
+  if (int rc = convert_input(in, &si)) return rc;
+  if (in->kind == 0 && (long long)si.blocks_per_frame * in->n_frames < n_blocks)
+    return fail(AV1P_EINVAL, "n_blocks exceeds the blocks in the given frames");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int32_t* n2 = c->counts;
+  if (int rc = run_stage(&c->stage[0], si, nullptr, nullptr, n_blocks, c->logits[0], st)) return rc;
+  if (int rc = av1p_route_stage1(c->logits[0], nullptr, n_blocks, thr, c->idx2, n2, l8, l64, c->scratch, st)) return rc;
+  if (int rc = run_stage(&c->stage[1], si, c->idx2, n2, n_blocks, c->logits[1], st)) return rc;
+  return av1p_finalize_labels_argmax(c->logits[1], 7, 1, c->idx2, n2, n_blocks, l8, l64, st);
 }
 
 // ------------------------------------------------------------------------------ FC test hook

@@ -38,7 +38,7 @@ constexpr int FC_STAGE_BYTES = FC_A_BYTES + FC_W_BYTES;      // 48 KB
 constexpr int FC_MAX_NT = 8;           // N tiles per layer
 constexpr int FC_MAX_KB = 128;         // scheduled K blocks per layer (sum over N tiles)
 constexpr int FC_MAX_SRC = 4;          // activation sources per layer
-constexpr int FC_TAIL_MAX = 4;         // outputs of the in-epilogue final linear
+constexpr int FC_TAIL_MAX = 8;         // outputs of the in-epilogue final linear (7 for the flatten head)
 constexpr int FC_EPI_WARPS = 16;         // four per TMEM lane quadrant: 8 of every 32 staged columns each
 constexpr int FC_THREADS = 64 + 32 * FC_EPI_WARPS + 32;      // producer, MMA, epilogue, store
 constexpr int FC_STORE_WARP = 2 + FC_EPI_WARPS;
@@ -300,7 +300,9 @@ __device__ __forceinline__ void epi_tile_head(const FcParams& p, int n_rows, int
   tc_fence_after_sync();
   if (half == 0) {
     const uint32_t t_addr = t_col + (uint32_t(quad * 32) << 16);
-    float tail[FC_TAIL_MAX] = {0.f, 0.f, 0.f, 0.f};
+    float tail[FC_TAIL_MAX];
+#pragma unroll
+    for (int j = 0; j < FC_TAIL_MAX; ++j) tail[j] = 0.f;
     for (int c = 0; c < block_n; c += 32) {
       uint32_t v[32];
       tmem_ld_32x32(t_addr + uint32_t(c), v);
@@ -431,6 +433,7 @@ __global__ void __launch_bounds__(FC_THREADS, 1) fc_tcgen05_kernel(const __grid_
     const uint32_t idesc = umma_idesc_f16(uint32_t(p.block_n));
     const uint32_t idesc_id = umma_idesc_f16(16u);
     const uint64_t id_desc = ident_desc(base + FC_OFF_IDENT);
+    const uint32_t a_lo0 = umma_desc_lo_sw128(base);
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int nt = item % p.n_tiles;
       mbar_wait(&acc_empty[acc], acc_phase ^ 1u, p.err_flag, 200 + acc);
@@ -442,8 +445,9 @@ __global__ void __launch_bounds__(FC_THREADS, 1) fc_tcgen05_kernel(const __grid_
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&full_bar[stage], phase, p.err_flag, 300 + stage);
         tc_fence_after_sync();
-        const uint32_t a_addr = base + stage * FC_STAGE_BYTES;
-        const uint32_t w_addr = a_addr + FC_A_BYTES;
+        // low descriptor words of this slot's A and W tiles (+2 per K step of 16 elements)
+        const uint32_t a_lo = a_lo0 + uint32_t(stage) * (FC_STAGE_BYTES >> 4);
+        const uint32_t w_lo = a_lo + (FC_A_BYTES >> 4);
         const bool ident = p.kb_w[kb] == FC_W_IDENT;
         const bool first_of_pair = p.pair_mode && !ident && ((kb - kb0) & 1) == 0;
         if (elect_one_sync()) {
@@ -453,28 +457,26 @@ __global__ void __launch_bounds__(FC_THREADS, 1) fc_tcgen05_kernel(const __grid_
             const uint32_t c0 = (uint32_t(p.kb_src[kb]) & 0x3FFFu) * FC_TILE_K - uint32_t(nt * p.block_n);
 #pragma unroll
             for (int j = 0; j < FC_TILE_K / 16; ++j)
-              umma_f16_ss(d_tmem + c0 + j * 16, umma_desc_sw128(a_addr + j * 32), id_desc, idesc_id, 1u);
+              umma_f16_ss(d_tmem + c0 + j * 16, (uint64_t(0x40004040u) << 32) | uint64_t(a_lo + 2 * j), id_desc, idesc_id, 1u);
             umma_commit(&empty_bar[stage]);
           } else if (!p.pair_mode) {
-#pragma unroll
-            for (int k = 0; k < FC_TILE_K / 16; ++k)
-              umma_f16_ss(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(w_addr + k * 32), idesc,
-                          (kb > kb0 || k > 0) ? 1u : 0u);
+            umma_f16_ss_lo(d_tmem, a_lo, w_lo, idesc, kb > kb0 ? 1u : 0u);
+            umma_f16_ss_lo(d_tmem, a_lo + 2, w_lo + 2, idesc, 1u);
+            umma_f16_ss_lo(d_tmem, a_lo + 4, w_lo + 4, idesc, 1u);
+            umma_f16_ss_lo(d_tmem, a_lo + 6, w_lo + 6, idesc, 1u);
             umma_commit(&empty_bar[stage]);   // frees the smem slot once these MMAs have read it
           } else if (first_of_pair) {
             // (x_hi, w_hi): the slot stays live until the cross products of the next entry are done
-#pragma unroll
-            for (int k = 0; k < FC_TILE_K / 16; ++k)
-              umma_f16_ss(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(w_addr + k * 32), idesc,
-                          (kb > kb0 || k > 0) ? 1u : 0u);
+            umma_f16_ss_lo(d_tmem, a_lo, w_lo, idesc, kb > kb0 ? 1u : 0u);
+            umma_f16_ss_lo(d_tmem, a_lo + 2, w_lo + 2, idesc, 1u);
+            umma_f16_ss_lo(d_tmem, a_lo + 4, w_lo + 4, idesc, 1u);
+            umma_f16_ss_lo(d_tmem, a_lo + 6, w_lo + 6, idesc, 1u);
           } else {
             // this slot holds (x_lo, w_lo): issue x_hi * w_lo and x_lo * w_hi
 #pragma unroll
-            for (int k = 0; k < FC_TILE_K / 16; ++k)
-              umma_f16_ss(d_tmem, umma_desc_sw128(prev_a + k * 32), umma_desc_sw128(w_addr + k * 32), idesc, 1u);
+            for (int k = 0; k < FC_TILE_K / 16; ++k) umma_f16_ss_lo(d_tmem, prev_a + 2 * k, w_lo + 2 * k, idesc, 1u);
 #pragma unroll
-            for (int k = 0; k < FC_TILE_K / 16; ++k)
-              umma_f16_ss(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(prev_w + k * 32), idesc, 1u);
+            for (int k = 0; k < FC_TILE_K / 16; ++k) umma_f16_ss_lo(d_tmem, a_lo + 2 * k, prev_w + 2 * k, idesc, 1u);
             umma_commit(&empty_bar[prev_stage]);
             umma_commit(&empty_bar[stage]);
           }
@@ -482,8 +484,8 @@ __global__ void __launch_bounds__(FC_THREADS, 1) fc_tcgen05_kernel(const __grid_
         }
         __syncwarp();
         if (first_of_pair) {
-          prev_a = a_addr;
-          prev_w = w_addr;
+          prev_a = a_lo;
+          prev_w = w_lo;
           prev_stage = stage;
         }
         if (++stage == FC_STAGES) {

@@ -209,23 +209,20 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_tc_kernel(const __grid_con
     int stage = 0, acc = 0;
     uint32_t phase = 0, acc_phase = 0;
     const uint32_t idesc = umma_idesc_f16(ST_N);
-    const uint32_t a_hi = smem_u32(w_hi), a_lo = smem_u32(w_lo);
+    const uint32_t a_hi = umma_desc_lo_sw128(smem_u32(w_hi)), a_lo = umma_desc_lo_sw128(smem_u32(w_lo));
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
       mbar_wait(&acc_empty[acc], acc_phase ^ 1u, p.err_flag, 600 + acc);
       mbar_wait(&full_bar[stage], phase, p.err_flag, 700 + stage);
       tc_fence_after_sync();
       if (elect_one_sync()) {
         const uint32_t d_tmem = tmem_base + uint32_t(acc * ST_N);
-        const uint32_t b_hi = smem_u32(stages + stage * ST_STAGE_BYTES), b_lo = b_hi + ST_P_BYTES;
+        const uint32_t b_hi = umma_desc_lo_sw128(smem_u32(stages + stage * ST_STAGE_BYTES)), b_lo = b_hi + (ST_P_BYTES >> 4);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_f16_ss(d_tmem, umma_desc_sw128(a_hi + k * 32), umma_desc_sw128(b_hi + k * 32), idesc, k > 0 ? 1u : 0u);
+        for (int k = 0; k < 4; ++k) umma_f16_ss_lo(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, k > 0 ? 1u : 0u);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_f16_ss(d_tmem, umma_desc_sw128(a_hi + k * 32), umma_desc_sw128(b_lo + k * 32), idesc, 1u);
+        for (int k = 0; k < 4; ++k) umma_f16_ss_lo(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_f16_ss(d_tmem, umma_desc_sw128(a_lo + k * 32), umma_desc_sw128(b_hi + k * 32), idesc, 1u);
+        for (int k = 0; k < 4; ++k) umma_f16_ss_lo(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
         umma_commit(&empty_bar[stage]);
         umma_commit(&acc_full[acc]);
       }

@@ -257,6 +257,21 @@ class Stage3ABModel(_NativeStageModule):
         return self._native_forward(x)
 
 
+class Stage2FlatModel(_NativeStageModule):
+    """scripts/008b_run_pipeline_flatten_eval.py:110-132 (the class is local to load_stage2_flat_model there):
+    backbone + 7-way head for HORZ .. VERT_B.  Keys: backbone.*, head.{1,5}.{weight,bias}, head.2.* (BatchNorm1d)."""
+    _kind = "flat7"
+
+    def __init__(self, pretrained: bool = True):
+        super().__init__()
+        self.backbone = ImprovedBackbone(pretrained)
+        self.head = nn.Sequential(nn.Dropout(0.3), nn.Linear(512, 256), nn.BatchNorm1d(256), nn.ReLU(), nn.Dropout(0.2),
+                                  nn.Linear(256, 7))
+
+    def forward(self, x):
+        return self._native_forward(x)
+
+
 class FGVCModel(_NativeStageModule):
     """006_train_stage3_ab_fgvc.py:246-297: base_model.backbone + feat_proj + L2-norm + cosine classifier."""
     _kind = "ab_fgvc"

@@ -34,8 +34,8 @@ TILE_K = 64
 OP_STEM, OP_FC, OP_SAM, OP_FGVC_TAIL, OP_SE, OP_CONV_RES = 0, 1, 2, 3, 4, 5
 EPI_LINEAR, EPI_RELU, EPI_ADD_RELU, EPI_GATE, EPI_HEAD = 0, 1, 2, 3, 4
 
-STAGE_KINDS = {"stage1": 0, "stage2": 1, "rect": 2, "ab_fgvc": 3, "ab": 4}
-NUM_OUTPUTS = {"stage1": 1, "stage2": 3, "rect": 2, "ab_fgvc": 4, "ab": 4}
+STAGE_KINDS = {"stage1": 0, "stage2": 1, "rect": 2, "ab_fgvc": 3, "ab": 4, "flat7": 5}
+NUM_OUTPUTS = {"stage1": 1, "stage2": 3, "rect": 2, "ab_fgvc": 4, "ab": 4, "flat7": 7}
 
 BN_EPS = 1e-5
 
@@ -335,6 +335,11 @@ def head_ops(kind: str, sd, precision: str = "fp16x3") -> List[_Op]:
         ops.append(make_fc_op("head.0", [w0], ["C1"], "D0", b0, EPI_RELU, _block_n(w0.shape[0]), precision, use_row_scale=True))
         # head.3 reads the first w0.shape[0] columns of D0
         ops.append(make_fc_op("head.3+6", [w1], ["D0"], None, b1, EPI_HEAD, _block_n(w1.shape[0]), precision, tail_w=w2, tail_b=b2))
+    elif kind == "flat7":
+        # Stage2FlatModel head (008b_run_pipeline_flatten_eval.py:120-127): Dropout, Linear(512,256), BN1d, ReLU, Dropout, Linear(256,7)
+        w0, b0 = fold_bn(_np64(sd["head.1.weight"]), _np64(sd["head.1.bias"]), sd, "head.2")
+        w1, b1 = _np64(sd["head.5.weight"]), _np64(sd["head.5.bias"])
+        ops.append(make_fc_op("head.1+2+5", [w0], ["C1"], None, b0, EPI_HEAD, 256, precision, use_row_scale=True, tail_w=w1, tail_b=b1))
     elif kind == "ab_fgvc":
         w0, b0 = fold_bn(_np64(sd["feat_proj.0.weight"]), _np64(sd["feat_proj.0.bias"]), sd, "feat_proj.1")
         w1, b1 = fold_bn(_np64(sd["feat_proj.4.weight"]), _np64(sd["feat_proj.4.bias"]), sd, "feat_proj.5")

@@ -138,3 +138,53 @@ class NativeCascade:
                 self.handle = None
         except Exception:
             pass
+
+
+class NativeFlatCascade:
+    """Stage1 -> 7-way flat model plan over one shared workspace (av1p_flat_cascade)."""
+
+    def __init__(self, models: Sequence[NativeModel], capacity: int):
+        assert len(models) == 2
+        self.models = list(models)
+        self.capacity = int(capacity)
+        self.device = models[0].device
+        arr = (C.c_void_p * 2)(*[m.handle for m in models])
+        with torch.cuda.device(self.device):
+            nbytes = N.lib().av1p_flat_cascade_workspace_bytes(arr, self.capacity)
+            if nbytes == 0:
+                raise N.Av1pError("av1p_flat_cascade_workspace_bytes failed")
+            self.workspace = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            handle = C.c_void_p()
+            N.check(N.lib().av1p_flat_cascade_create(arr, self.capacity, N.ptr(self.workspace), nbytes, C.byref(handle)))
+        self.handle = handle
+
+    def predict(self, inp: N.Input, n_blocks: int, threshold: float, labels_u8: Optional[torch.Tensor] = None,
+                labels_i64: Optional[torch.Tensor] = None) -> None:
+        if n_blocks > self.capacity:
+            raise N.Av1pError(f"{n_blocks} blocks exceed the cascade capacity {self.capacity}")
+        with torch.cuda.device(self.device):
+            N.check(N.lib().av1p_flat_cascade_predict(self.handle, C.byref(inp), n_blocks, float(threshold), N.ptr(labels_u8),
+                                                      N.ptr(labels_i64), N.stream_handle(self.device)))
+
+    def intermediates(self, n_blocks: int) -> Dict[str, torch.Tensor]:
+        torch.cuda.synchronize(self.device)
+        base = self.workspace.data_ptr()
+
+        def view(which: int, dtype, numel: int) -> torch.Tensor:
+            p = N.lib().av1p_flat_cascade_buffer(self.handle, which)
+            esz = torch.empty(0, dtype=dtype).element_size()
+            off = p - base
+            return self.workspace[off:off + numel * esz].view(dtype)
+
+        n2 = int(view(3, torch.int32, 2).cpu()[0])
+        return {"logits1": view(0, torch.float32, n_blocks).reshape(n_blocks, 1).clone(),
+                "logits_flat": view(1, torch.float32, n2 * 7).reshape(n2, 7).clone(),
+                "idx2": view(2, torch.int32, n2).clone()}
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                N.lib().av1p_flat_cascade_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass

@@ -23,7 +23,11 @@ import numpy as np
 import torch
 
 _CAL_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "synth_calibration.npz")
+_CAL_FLAT_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "synth_calibration_flat.npz")
 KINDS = ("stage1", "stage2", "rect", "ab", "ab_fgvc")
+# networks of the callers next to the cascade; their calibration lives in its own file
+# (tools/make_golden_flat.py) so that the cascade fixtures never change when one is added
+EXTRA_KINDS = ("flat7",)
 
 
 def frame_words(width: int, height: int) -> int:
@@ -66,9 +70,10 @@ def synth_frames(n_frames: int, width: int, height: int, seed: int = 1234, noise
 def random_state_dict(kind: str, seed: int) -> Dict[str, torch.Tensor]:
     """Seeded random weights with the key names / shapes of the reference's stage models."""
     from . import models as M
-    module = {"stage1": M.Stage1Model, "stage2": M.Stage2Model, "rect": M.Stage3RectModel, "ab": M.Stage3ABModel}.get(kind)
+    module = {"stage1": M.Stage1Model, "stage2": M.Stage2Model, "rect": M.Stage3RectModel, "ab": M.Stage3ABModel,
+              "flat7": M.Stage2FlatModel}.get(kind)
     net = M.FGVCModel(M.Stage3ABModel(pretrained=False)) if kind == "ab_fgvc" else module(pretrained=False)
-    rng = np.random.Generator(np.random.PCG64(seed * 7919 + KINDS.index(kind)))
+    rng = np.random.Generator(np.random.PCG64(seed * 7919 + (KINDS + EXTRA_KINDS).index(kind)))
     sd = {}
     for key, ref in net.state_dict().items():
         shape = tuple(ref.shape)
@@ -98,9 +103,10 @@ def random_state_dict(kind: str, seed: int) -> Dict[str, torch.Tensor]:
 def calibrated_state_dict(kind: str, seed: int = 0) -> Dict[str, torch.Tensor]:
     """random_state_dict + the stored calibration (BN running statistics, last-layer gain and bias)."""
     sd = random_state_dict(kind, seed)
-    if not os.path.exists(_CAL_PATH):
-        raise FileNotFoundError(f"{_CAL_PATH} is missing (generated by tools/make_golden.py)")
-    cal = np.load(_CAL_PATH)
+    path = _CAL_FLAT_PATH if kind in EXTRA_KINDS else _CAL_PATH
+    if not os.path.exists(path):
+        raise FileNotFoundError(f"{path} is missing (generated by tools/make_golden*.py)")
+    cal = np.load(path)
     if int(cal["seed"]) != seed:
         raise ValueError(f"stored calibration is for seed {int(cal['seed'])}")
     prefix = kind + "/"

@@ -31,6 +31,7 @@ extern "C" {
 typedef struct av1p_model av1p_model;       /* one packed stage network resident in HBM */
 typedef struct av1p_stage av1p_stage;       /* a model bound to a workspace (ready-to-launch plan) */
 typedef struct av1p_cascade av1p_cascade;   /* Stage1 -> Stage2 -> Stage3-RECT / Stage3-AB */
+typedef struct av1p_flat_cascade av1p_flat_cascade;   /* Stage1 -> 7-way Stage2FlatModel (008b) */
 
 /* Where the 16x16 luma blocks come from. */
 typedef struct av1p_input {
@@ -112,6 +113,33 @@ int av1p_route_stage2(const float* logits3_dev, const int32_t* idx_in_dev, const
 int av1p_finalize_labels(const float* logits_dev, int32_t num_classes, int32_t label_base, const int32_t* idx_dev,
                          const int32_t* n_dev, int32_t n, uint8_t* labels_u8_dev, int64_t* labels_i64_dev,
                          void* stream);
+
+/* Same scatter with a plain argmax over the raw logits (first max wins), num_classes <= 8: the flatten cascade's
+ * `stage2_logits.argmax(dim=1)` (scripts/008b_run_pipeline_flatten_eval.py:213). */
+int av1p_finalize_labels_argmax(const float* logits_dev, int32_t num_classes, int32_t label_base, const int32_t* idx_dev,
+                                const int32_t* n_dev, int32_t n, uint8_t* labels_u8_dev, int64_t* labels_i64_dev,
+                                void* stream);
+
+/* ---- flatten cascade: replaces run_pipeline_inference's per-batch body
+ *      (pesquisa_v6/scripts/008b_run_pipeline_flatten_eval.py:177-229): Stage1Model -> threshold -> compaction ->
+ *      Stage2FlatModel (backbone + Linear/BN1d/ReLU/Linear head, 008b:110-127) -> label = 1 + argmax (008b:163-175),
+ *      label 0 for blocks below the threshold.  models[] = {stage1, flat7}. */
+size_t av1p_flat_cascade_workspace_bytes(const av1p_model* const models[2], int32_t capacity_blocks);
+int av1p_flat_cascade_create(const av1p_model* const models[2], int32_t capacity_blocks, void* workspace_dev,
+                             size_t workspace_bytes, av1p_flat_cascade** out);
+void av1p_flat_cascade_destroy(av1p_flat_cascade* c);
+int av1p_flat_cascade_predict(av1p_flat_cascade* c, const av1p_input* in, int32_t n_blocks, float stage1_threshold,
+                              uint8_t* labels_u8_dev, int64_t* labels_i64_dev, void* stream);
+/* which: 0 stage-1 logits [n][1], 1 flat logits [n2][7], 2 idx2 [n2], 3 counts int32[2] = {n2, unused}. */
+const void* av1p_flat_cascade_buffer(const av1p_flat_cascade* c, int32_t which);
+
+/* ---- stage-1 threshold sweep: replaces the accumulation inside evaluate_with_threshold
+ *      (pesquisa_v6/scripts/007_optimize_thresholds.py:24-71) for up to 32 thresholds in one pass over the
+ *      stage-1 logits: prob = sigmoid(logit) (fp32), pred = (double)prob >= threshold (the reference compares a
+ *      float32 array with np.float64 thresholds); counts_dev[t][4] = {tn, fp, fn, tp} against labels_dev (uint8
+ *      0/1).  probs_dev (float32 [n]) is optional.  thresholds_host is read at call time. */
+int av1p_threshold_sweep(const float* logits_dev, const uint8_t* labels_dev, int32_t n, const double* thresholds_host,
+                         int32_t n_thresholds, float* probs_dev, uint64_t* counts_dev, void* stream);
 
 /* ---- measurement support (bench.py): bracket every kernel launch of the calling thread with CUDA
  *      events on its stream.  av1p_profile_end synchronises on those events and returns the summed

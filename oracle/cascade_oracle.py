@@ -128,7 +128,8 @@ def stage_logits(kind: str, sd: StateDict, x: torch.Tensor) -> torch.Tensor:
 
     kind: 'stage1' (models.py:129-149,206-215; apply_temp=False so no temperature division),
           'stage2' (:152-167), 'rect' (:170-185), 'ab' (Stage3ABModel :188-203),
-          'ab_fgvc' (scripts/006_train_stage3_ab_fgvc.py:217-297).
+          'ab_fgvc' (scripts/006_train_stage3_ab_fgvc.py:217-297),
+          'flat7' (Stage2FlatModel, scripts/008b_run_pipeline_flatten_eval.py:110-132).
     """
     with torch.no_grad():
         f = backbone_features(sd, x)
@@ -136,6 +137,11 @@ def stage_logits(kind: str, sd: StateDict, x: torch.Tensor) -> torch.Tensor:
             return _mlp_head(sd, f, (0, 3))
         if kind in ("stage2", "rect", "ab"):
             return _mlp_head(sd, f, (0, 3, 6))
+        if kind == "flat7":
+            # Stage2FlatModel head (scripts/008b_run_pipeline_flatten_eval.py:120-127), eval mode: Dropout = identity
+            f = F.linear(f, sd["head.1.weight"], sd["head.1.bias"])
+            f = F.relu(_bn(f, sd, "head.2"))
+            return F.linear(f, sd["head.5.weight"], sd["head.5.bias"])
         if kind == "ab_fgvc":
             for lin, bn in ((0, 1), (4, 5)):
                 f = F.linear(f, sd[f"feat_proj.{lin}.weight"], sd[f"feat_proj.{lin}.bias"])
@@ -200,6 +206,40 @@ def cascade_predict(sds: Dict[str, StateDict], images: torch.Tensor, threshold: 
         la = run("ab_fgvc", images[ab_idx])
         out["labels"][ab_idx] = argmax_softmax(la) + 4
         out["logits_ab"] = la
+    return out
+
+
+def flatten_predict(sd_stage1: StateDict, sd_flat: StateDict, images: torch.Tensor, threshold: float,
+                    chunk: Optional[int] = None):
+    """Per-batch body of run_pipeline_inference (scripts/008b_run_pipeline_flatten_eval.py:196-219): stage-1 sigmoid
+    >= threshold -> Stage2FlatModel on the routed blocks -> argmax over the raw logits -> +1 (:163-175)."""
+    def run(kind, sd, x):
+        if chunk is None or x.shape[0] <= chunk:
+            return stage_logits(kind, sd, x)
+        return torch.cat([stage_logits(kind, sd, x[i:i + chunk]) for i in range(0, x.shape[0], chunk)])
+
+    l1 = run("stage1", sd_stage1, images)
+    mask = torch.sigmoid(l1).squeeze(-1) >= threshold
+    labels = torch.zeros(images.shape[0], dtype=torch.int64)
+    idx2 = mask.nonzero(as_tuple=True)[0]
+    lf = torch.zeros(0, 7)
+    if idx2.numel():
+        lf = run("flat7", sd_flat, images[idx2])
+        labels[idx2] = lf.argmax(dim=1) + 1
+    return {"labels": labels, "logits1": l1, "idx2": idx2, "logits_flat": lf}
+
+
+def threshold_confusion(logits1: torch.Tensor, labels_stage1: np.ndarray, thresholds) -> np.ndarray:
+    """Confusion counts {tn, fp, fn, tp} per threshold as evaluate_with_threshold computes them
+    (scripts/007_optimize_thresholds.py:36-58): float32 sigmoid probabilities as a numpy array compared with np.float64
+    thresholds (np.arange, :153) - a float64 comparison under NumPy >= 2."""
+    probs = torch.sigmoid(logits1.float()).reshape(-1).numpy()
+    lab = np.asarray(labels_stage1).reshape(-1).astype(np.int64)
+    out = np.zeros((len(thresholds), 4), dtype=np.int64)
+    for i, t in enumerate(np.asarray(thresholds, dtype=np.float64)):
+        pred = (probs >= t).astype(np.int64)
+        for c in range(4):
+            out[i, c] = int(np.sum(lab * 2 + pred == c))
     return out
 
 
