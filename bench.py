@@ -37,7 +37,8 @@ SUB = 8                                    # frames per cascade launch
 THRESHOLD = 0.45                           # 008 CLI default (:187)
 # Live (non-padding) conv+linear FLOPs per block, SURVEY.md section 8(d) / BASELINE.md section 2
 F_LIVE = {"stage1": 8.813e6, "stage2": 8.878e6, "rect": 8.698e6, "ab_fgvc": 9.603e6}
-F_CONV1_LIVE = 0.32e6                      # conv1 runs in the stem kernel (CUDA cores), not in the FC kernel
+F_CONV1_LIVE = 0.32e6                      # conv1 runs in the stem kernel
+F_LAYER1_LIVE = 4 * 100 * 64 * 64 * 2      # layer1: 4 convs x 100 live (output, input) position pairs x 64x64 MACs (conv_res kernel)
 F_NOMINAL = {"stage1": 30.636e6, "stage2": 30.702e6, "rect": 30.521e6, "ab_fgvc": 31.426e6}
 
 
@@ -48,6 +49,21 @@ def measured_peaks():
         return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"], "bf16_tflops_sustained": p["bf16_tflops_sustained"],
                 "source": "measured (MEASURED_PEAKS.json)"}
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+def ncu_traffic(kernel_class, rows_per_step, launches_per_step):
+    """Average DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the dominant kernel class, from the
+    committed `ncu --set full` capture (profiles/r01_ncu_traffic.json).  The capture measured every launch of that class in
+    one Stage-1 forward; the traffic of these kernels is proportional to their block rows, so the per-row figure is scaled
+    to this step's rows (all four stages) and divided by its launches - the same averaging as `achieved`."""
+    path = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+    try:
+        e = json.load(open(path)).get(kernel_class)
+        if e:
+            return e["dram_bytes_per_row_per_stage_forward"] * rows_per_step / max(launches_per_step, 1)
+    except Exception:
+        pass
+    return None
 
 
 class ClockSampler:
@@ -244,26 +260,35 @@ def main():
     N.check(lib.av1p_profile_end(ms_cls, n_cls))
     cls_names = ("stem", "fc_tcgen05", "sam_gate", "fgvc_tail", "route", "finalize", "squeeze_excite", "conv_res_tcgen05")
     per_class = {nm: {"ms_per_step": ms_cls[i] / prof_steps, "launches_per_step": n_cls[i] // prof_steps} for i, nm in enumerate(cls_names)}
-    fc_ms = per_class["fc_tcgen05"]["ms_per_step"]
-    fc_launches = per_class["fc_tcgen05"]["launches_per_step"]
     blocks = F * BPF
     stage_rows = {"stage1": blocks, "stage2": mix["stage2"] * blocks, "rect": mix["rect"] * blocks, "ab_fgvc": mix["ab"] * blocks}
-    flops_live_fc = sum((F_LIVE[k] - F_CONV1_LIVE) * r for k, r in stage_rows.items())
+    rows_total = sum(stage_rows.values())
     flops_nominal = sum(F_NOMINAL[k] * r for k, r in stage_rows.items())
-    issued_macs = sum(pipe._models()[i].native_model(dev).stats["tensor_macs_per_block"] * r
-                      for i, r in enumerate(stage_rows.values()))
+    natives = [m.native_model(dev) for m in pipe._models()]
+    # algorithmic (live, single-precision-product) FLOPs and issued tensor MACs of the two tensor-core kernel classes
+    alg = {"fc_tcgen05": sum((F_LIVE[k] - F_CONV1_LIVE - F_LAYER1_LIVE) * r for k, r in stage_rows.items()),
+           "conv_res_tcgen05": F_LAYER1_LIVE * rows_total}
+    issued = {"fc_tcgen05": sum(nm.stats["fc_macs_per_block"] * r for nm, r in zip(natives, stage_rows.values())),
+              "conv_res_tcgen05": sum(nm.stats["conv_macs_per_block"] * r for nm, r in zip(natives, stage_rows.values()))}
     peaks = measured_peaks()
     peak_tf = peaks["bf16_tflops_sustained"]
-    achieved_tf = flops_live_fc / (fc_ms * 1e-3) / 1e12
-    roofline = {"bound": "tensor", "kernel": "fc_tcgen05_kernel", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": achieved_tf / peak_tf, "traffic": None,
+    total_ms = sum(v["ms_per_step"] for v in per_class.values())
+    dom = max(alg, key=lambda k: per_class[k]["ms_per_step"])
+
+    def tensor_entry(name):
+        ms, launches = per_class[name]["ms_per_step"], max(per_class[name]["launches_per_step"], 1)
+        ach = alg[name] / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
+        iss = 2 * issued[name] / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
+        return {"kernel": name + "_kernel", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
+                "algorithmic_flops_per_launch": alg[name] / launches, "avg_launch_ms": ms / launches, "launches_per_step": launches,
+                "issued_tensor_tflops": iss, "issued_frac_of_peak": iss / peak_tf, "kernel_share_of_step": ms / total_ms}
+
+    roofline = {"bound": "tensor", **tensor_entry(dom), "traffic": ncu_traffic(dom, rows_total, per_class[dom]["launches_per_step"]),
                 "peak_source": peaks["source"] + ", sustained cuBLAS bf16 (kernel timed inside a long step)",
-                "algorithmic_flops_per_launch": flops_live_fc / max(fc_launches, 1),
-                "avg_launch_ms": fc_ms / max(fc_launches, 1), "launches_per_step": fc_launches,
-                "issued_tensor_tflops": 2 * issued_macs / (fc_ms * 1e-3) / 1e12,
-                "issued_frac_of_peak": 2 * issued_macs / (fc_ms * 1e-3) / 1e12 / peak_tf,
-                "reference_equivalent_tflops_whole_step": flops_nominal / (ms_step * 1e-3) / 1e12,
-                "kernel_share_of_step": fc_ms / sum(v["ms_per_step"] for v in per_class.values())}
+                "note": "achieved counts live (non-padding) FLOPs once; fp16x3 issues three tensor products per live MAC plus "
+                        "block-Toeplitz padding - issued_* is what the tensor pipe actually executes",
+                "other_tensor_kernel": tensor_entry([k for k in alg if k != dom][0]),
+                "reference_equivalent_tflops_whole_step": flops_nominal / (ms_step * 1e-3) / 1e12}
     log(f"[b200] kernel classes per step: {json.dumps(per_class)}")
 
     # ---------------------------------------------------------------- CPU baseline (rank 0, N = 1 only)

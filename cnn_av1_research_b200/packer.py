@@ -417,12 +417,17 @@ def pack_stage(kind: str, state_dict, precision: str = "fp16x3", layer1_fc: bool
 def blob_stats(blob: bytes) -> Dict[str, float]:
     """Work the packed program issues per block (for roofline accounting)."""
     n_ops = struct.unpack_from("<I", blob, 12)[0]
-    macs = 0
+    fc = conv = 0
     for i in range(n_ops):
         f = struct.unpack_from("<17i", blob, 64 + OP_BYTES * i)
         if f[0] == OP_FC:
             products = f[14] * 3 // 2 if f[16] else f[14]     # pair mode: 3 products per 2 entries
-            macs += products * f[10] * TILE_K                  # products * block_n * 64
+            fc += products * f[10] * TILE_K                    # products * block_n * 64
+            if f[11] == EPI_ADD_RELU:                          # residual branch on the tensor core: x_hi.I + x_lo.I
+                fc += (2 if f[16] else 1) * f[9] * f[10] * 16  # per 64-wide K block four (N=16, K=16) instructions
         elif f[0] == OP_CONV_RES:
-            macs += 100 * 64 * 64 * (3 if f[16] else 1)         # 100 (output, input) position pairs under the 3x3 window
-    return {"tensor_macs_per_block": float(macs), "bytes": float(len(blob))}
+            conv += 100 * 64 * 64 * (3 if f[16] else 1)         # 100 (output, input) position pairs under the 3x3 window
+            if f[11] == EPI_ADD_RELU:
+                conv += (2 if f[16] else 1) * 16 * 64 * 16
+    return {"tensor_macs_per_block": float(fc + conv), "fc_macs_per_block": float(fc), "conv_macs_per_block": float(conv),
+            "bytes": float(len(blob))}
