@@ -55,6 +55,7 @@ struct DeviceCtx {
   bool ok = false;
   int sms = 0;
   EncodeTiledFn encode = nullptr;
+  bool fc_pair = true;            // FC layers on CTA pairs (tcgen05 cta_group::2); AV1P_FC_PAIR=0 selects the single-CTA kernel
   int* watchdog_host = nullptr;   // mapped pinned memory: survives a kernel trap
   int* watchdog_dev = nullptr;
 };
@@ -75,7 +76,9 @@ int ensure_ctx() {
   CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
   if (!fn || qres != cudaDriverEntryPointSuccess) return fail(AV1P_ECUDA, "cuTensorMapEncodeTiled not available");
   g_ctx.encode = reinterpret_cast<EncodeTiledFn>(fn);
-  CUDA_TRY(cudaFuncSetAttribute(fc_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FC_SMEM_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(fc_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FC_SMEM_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(fc_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FC_SMEM_BYTES));
+  if (const char* e = getenv("AV1P_FC_PAIR")) g_ctx.fc_pair = atoi(e) != 0;
   {
     int n_k = 0;
     const ConvResKernel* ks = conv_res_all_kernels(&n_k);
@@ -160,6 +163,32 @@ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 }  // namespace
 
 extern "C" int av1p_debug_watchdog(void) { return g_ctx.watchdog_host ? *g_ctx.watchdog_host : 0; }
+
+// One FC layer: `rows` is the host-side upper bound on block rows (sizes the grid).  CTA-pair variant: clusters of two
+// CTAs, each pair takes two M tiles of an item.
+static int launch_fc(const FcParams& f, int rows, cudaStream_t st) {
+  const int m_tiles = ceil_div(rows, FC_TILE_M);
+  if (g_ctx.fc_pair && f.block_n % 16 == 0) {
+    const int pairs = std::min(g_ctx.sms / 2, ceil_div(m_tiles, 2) * f.n_tiles);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(unsigned(2 * std::max(pairs, 1)));
+    cfg.blockDim = dim3(FC_THREADS);
+    cfg.dynamicSmemBytes = FC_SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, fc_tcgen05_kernel<true>, f));
+  } else {
+    const int grid = std::min(g_ctx.sms, m_tiles * f.n_tiles);
+    fc_tcgen05_kernel<false><<<grid, FC_THREADS, FC_SMEM_BYTES, st>>>(f);
+  }
+  return AV1P_OK;
+}
 
 // ------------------------------------------------------------------------------ per-launch profiler
 // Optional CUDA-event bracket around every kernel launch (bench.py's roofline leg).  Events are
@@ -380,6 +409,7 @@ int plan_stage(const av1p_model* m, const ActLayout& L, uint8_t* act_base, av1p_
           f.src_kb[i] = int(L.cols[sb] / 64);
         }
         if (int rc = make_map_2d(&f.w_map, at(op.w_off), 64, uint64_t(op.n_w_chunks) * op.block_n, 64, op.block_n)) return rc;
+        if (int rc = make_map_2d(&f.w_half_map, at(op.w_off), 64, uint64_t(op.n_w_chunks) * op.block_n, 64, op.block_n / 2)) return rc;
         f.n_tiles = op.n_tiles;
         f.block_n = op.block_n;
         f.epi = op.epi;
@@ -544,9 +574,8 @@ int run_stage(av1p_stage* s, const StemInput& si, const int32_t* idx, const int3
         P.fc.n_rows_dev = n_dev;
         P.fc.n_rows = n;
         P.fc.logits = logits;
-        const int grid = std::min(g_ctx.sms, ceil_div(n, FC_TILE_M) * P.fc.n_tiles);
         ProfScope ps(PROF_FC, st);
-        fc_tcgen05_kernel<<<grid, FC_THREADS, FC_SMEM_BYTES, st>>>(P.fc);
+        if (int rc = launch_fc(P.fc, n, st)) return rc;
         break;
       }
       case AV1P_OP_CONV_RES: {
@@ -1007,6 +1036,7 @@ extern "C" int av1p_fc_forward(const av1p_fc_desc* d, void* stream) {
     f.src_kb[i] = d->a_cols[j] / 64;
   }
   if (int rc = make_map_2d(&f.w_map, d->w_dev, 64, uint64_t(d->n_w_chunks) * d->block_n, 64, d->block_n)) return rc;
+  if (int rc = make_map_2d(&f.w_half_map, d->w_dev, 64, uint64_t(d->n_w_chunks) * d->block_n, 64, d->block_n / 2)) return rc;
   f.n_rows_dev = d->n_dev;
   f.n_rows = d->rows;
   f.n_tiles = d->n_tiles;
@@ -1046,8 +1076,7 @@ extern "C" int av1p_fc_forward(const av1p_fc_desc* d, void* stream) {
       if (int rc = make_act_map(&f.a_map[3], d->aux_lo_dev, uint64_t(d->aux_ld), uint64_t(d->rows), false)) return rc;
     if (int rc = add_residual_entries(f, d->aux_lo_dev != nullptr)) return rc;
   }
-  const int grid = std::min(g_ctx.sms, ceil_div(d->rows, FC_TILE_M) * d->n_tiles);
-  fc_tcgen05_kernel<<<grid, FC_THREADS, FC_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(f);
+  if (int rc = launch_fc(f, d->rows, static_cast<cudaStream_t>(stream))) return rc;
   CUDA_TRY(cudaGetLastError());
   return AV1P_OK;
 }

@@ -35,6 +35,13 @@ constexpr int FC_STAGES = 4;
 constexpr int FC_A_BYTES = FC_TILE_M * FC_TILE_K * 2;        // 16 KB
 constexpr int FC_W_BYTES = FC_MAX_N * FC_TILE_K * 2;         // 32 KB
 constexpr int FC_STAGE_BYTES = FC_A_BYTES + FC_W_BYTES;      // 48 KB
+// CTA-pair variant (cta_group::2): each CTA of the pair loads its own A tile and HALF of the W tile per K block, so a
+// stage is 32 KB and six of them fit the same ring area; the W half the MMA needs from the other CTA never crosses
+// this SM's L2->SM port (62 -> 42 B/clk/SM at full tensor rate).
+constexpr int FC2_STAGES = 6;
+constexpr int FC2_W_BYTES = FC_W_BYTES / 2;                  // 16 KB
+constexpr int FC2_STAGE_BYTES = FC_A_BYTES + FC2_W_BYTES;    // 32 KB
+static_assert(FC2_STAGES * FC2_STAGE_BYTES == FC_STAGES * FC_STAGE_BYTES, "both variants share one shared-memory layout");
 constexpr int FC_MAX_NT = 8;           // N tiles per layer
 constexpr int FC_MAX_KB = 128;         // scheduled K blocks per layer (sum over N tiles)
 constexpr int FC_MAX_SRC = 4;          // activation sources per layer
@@ -71,6 +78,7 @@ enum FcEpilogue : int {
 struct FcParams {
   CUtensorMap a_map[FC_MAX_SRC]; // activation sources (tiled layout, see act_off): 2-D [rows*KB][64] fp16, box {64, 128}, SWIZZLE_128B
   CUtensorMap w_map;           // packed weights, 2-D [n_kb_total*block_n][64] fp16, box {64, block_n}
+  CUtensorMap w_half_map;      // same tensor, box {64, block_n / 2} (CTA-pair variant)
   CUtensorMap out_map[2];      // output hi / lo planes (tiled layout): 2-D [rows*KB][64] fp16, box {32, 128}, SWIZZLE_64B
   int src_kb[FC_MAX_SRC];      // 64-column blocks per row of each source buffer
   const int* n_rows_dev;       // device-side row count (nullptr -> n_rows)
@@ -176,6 +184,12 @@ __device__ __forceinline__ void epi_store_drain() {
 // global (the last, partial M tile: rows past n_rows stay untouched), arrives on `empty` as soon as the last
 // TMEM read has completed.  The TMEM read of chunk c+1 is in flight while chunk c is converted and staged.
 // P is FcParams or any struct with the same epilogue members.
+// Hand an accumulator back to the MMA issuer: a local arrive, or (peer CTA of a pair) an arrive on the leader's barrier.
+__device__ __forceinline__ void acc_release(uint64_t* empty, uint32_t empty_cluster_addr) {
+  if (empty_cluster_addr) mbar_arrive_cluster(empty_cluster_addr);
+  else mbar_arrive(empty);
+}
+
 template <typename P>
 __device__ __forceinline__ int epi_debug(const P& p) {
   if constexpr (requires { p.debug; }) return p.debug; else return 0;
@@ -183,7 +197,7 @@ __device__ __forceinline__ int epi_debug(const P& p) {
 template <typename P>
 __device__ __forceinline__ void epi_tile_store(const P& p, const EpiStage& es, uint32_t& g, int n_rows, int mt, int col0,
                                                int block_n, uint32_t t_col, uint64_t* full, uint32_t full_phase,
-                                               uint64_t* empty, int warp, int lane, int tag) {
+                                               uint64_t* empty, int warp, int lane, int tag, uint32_t empty_remote = 0u) {
   const int quad = warp & 3;              // TMEM lane quadrant this warp may read
   const int part = (warp - 2) >> 2;       // which 8 columns of every 32-column chunk
   const int r_local = quad * 32 + lane;
@@ -209,7 +223,7 @@ __device__ __forceinline__ void epi_tile_store(const P& p, const EpiStage& es, u
   if (epi_debug(p) & 16) {        // development switch: hand the accumulator straight back
     tc_fence_before_sync();
     __syncwarp();
-    if (lane == 0) mbar_arrive(empty);
+    if (lane == 0) acc_release(empty, empty_remote);
     return;
   }
   const uint32_t t_addr = t_col + (uint32_t(quad * 32) << 16) + uint32_t(tcol);
@@ -238,7 +252,7 @@ __device__ __forceinline__ void epi_tile_store(const P& p, const EpiStage& es, u
       // every TMEM read of this accumulator is complete -> hand it back to the MMA warp
       tc_fence_before_sync();
       __syncwarp();
-      if (lane == 0) mbar_arrive(empty);
+      if (lane == 0) acc_release(empty, empty_remote);
     }
     f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
     f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
@@ -290,7 +304,7 @@ __device__ __forceinline__ void epi_tile_store(const P& p, const EpiStage& es, u
 // The first four epilogue warps take every column; the others only release the accumulator.
 __device__ __forceinline__ void epi_tile_head(const FcParams& p, int n_rows, int mt, int block_n, uint32_t t_col,
                                               uint64_t* full, uint32_t full_phase, uint64_t* empty, const float* tail_w_s,
-                                              int warp, int lane, int tag) {
+                                              int warp, int lane, int tag, uint32_t empty_remote = 0u) {
   const int quad = warp & 3;
   const int half = (warp - 2) >> 2;
   const int row = mt * FC_TILE_M + quad * 32 + lane;
@@ -342,19 +356,35 @@ __device__ __forceinline__ void epi_tile_head(const FcParams& p, int n_rows, int
   }
   tc_fence_before_sync();
   __syncwarp();
-  if (lane == 0) mbar_arrive(empty);
+  if (lane == 0) acc_release(empty, empty_remote);
 }
 
+// 16 x 16 scaled identity for the CTA-pair variant: the pair MMA takes B rows 0..7 from the leader and rows 8..15 from
+// the peer, each at the descriptor's start address, so CTA `rank` stores rows 8*rank .. 8*rank+7 as its first row group.
+__device__ __forceinline__ void write_ident_tile_pair(uint8_t* ident, float s, uint32_t rank, int tid, int nthreads) {
+  for (int i = tid; i < EPI_IDENT_BYTES / 2; i += nthreads) {
+    const int u = i >> 3, e = i & 7;
+    const int n_local = (u & 7) + ((u >> 4) << 3), k = (((u >> 3) & 1) << 3) + e;
+    reinterpret_cast<__half*>(ident)[i] = __float2half_rn((n_local < 8 && int(rank) * 8 + n_local == k) ? s : 0.f);
+  }
+}
+
+// PAIR = false: one CTA per SM, tcgen05.mma.cta_group::1 (M = 128).
+// PAIR = true : clusters of two CTAs (launch with cluster dimension 2); CTA rank r of a cluster works on M tile 2*mp + r
+//               of its item (mp, nt); the leader (rank 0) issues tcgen05.mma.cta_group::2 (M = 256) for both.
+template <bool PAIR>
 __global__ void __launch_bounds__(FC_THREADS, 1) fc_tcgen05_kernel(const __grid_constant__ FcParams p) {
+  constexpr int STAGES = PAIR ? FC2_STAGES : FC_STAGES;
+  constexpr int STAGE_BYTES = PAIR ? FC2_STAGE_BYTES : FC_STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + FC_OFF_BARS);
-  uint64_t* empty_bar = full_bar + FC_STAGES;
-  uint64_t* acc_full = empty_bar + FC_STAGES;   // [2]
-  uint64_t* acc_empty = acc_full + 2;           // [2]
-  uint64_t* stg_full = acc_empty + 2;           // [2]
-  uint64_t* stg_free = stg_full + 2;            // [2]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + FC_OFF_BARS);   // [STAGES] (pair: the leader's are used)
+  uint64_t* empty_bar = full_bar + FC2_STAGES;                            // [STAGES]
+  uint64_t* acc_full = empty_bar + FC2_STAGES;   // [2]
+  uint64_t* acc_empty = acc_full + 2;            // [2] (pair: the leader's collect both CTAs' epilogue warps)
+  uint64_t* stg_full = acc_empty + 2;            // [2]
+  uint64_t* stg_free = stg_full + 2;             // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stg_free + 2);
   float* tail_w_s = reinterpret_cast<float*>(smem + FC_OFF_TAIL);
   EpiStage es;
@@ -362,39 +392,52 @@ __global__ void __launch_bounds__(FC_THREADS, 1) fc_tcgen05_kernel(const __grid_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0u;
+  const int worker = PAIR ? int(blockIdx.x >> 1) : int(blockIdx.x);        // index of this CTA (pair) among the workers
+  const int n_workers = PAIR ? int(gridDim.x >> 1) : int(gridDim.x);
 
   const int n_rows = p.n_rows_dev ? *p.n_rows_dev : p.n_rows;
   const int m_tiles = (n_rows + FC_TILE_M - 1) / FC_TILE_M;
-  const int n_items = m_tiles * p.n_tiles;
+  const int m_groups = PAIR ? (m_tiles + 1) / 2 : m_tiles;                  // M tiles (pairs of M tiles) to process
+  const int n_items = m_groups * p.n_tiles;
+  auto item_mt = [&](int item) { return PAIR ? 2 * (item / p.n_tiles) + int(rank) : item / p.n_tiles; };
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < FC_MAX_SRC; ++i) tma_prefetch_desc(&p.a_map[i]);
-    tma_prefetch_desc(&p.w_map);
+    tma_prefetch_desc(PAIR ? &p.w_half_map : &p.w_map);
     if (p.out) tma_prefetch_desc(&p.out_map[0]);
     if (p.out_lo) tma_prefetch_desc(&p.out_map[1]);
-    for (int s = 0; s < FC_STAGES; ++s) {
+    for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], FC_EPI_WARPS);
+      mbar_init(&acc_empty[s], PAIR ? 2 * FC_EPI_WARPS : FC_EPI_WARPS);
       mbar_init(&stg_full[s], FC_EPI_WARPS);
       mbar_init(&stg_free[s], 1);
     }
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, 512);
-    tmem_relinquish();
+    if constexpr (PAIR) {
+      tmem_alloc_pair(tmem_slot, 512);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_slot, 512);
+      tmem_relinquish();
+    }
   }
   if (p.epi == FC_EPI_HEAD) {
     for (int i = threadIdx.x; i < p.tail_n * p.block_n; i += FC_THREADS) tail_w_s[i] = p.tail_w[i];
   }
-  write_ident_tile(smem + FC_OFF_IDENT, 1.0f / p.acc_scale, threadIdx.x, FC_THREADS);
+  if constexpr (PAIR) write_ident_tile_pair(smem + FC_OFF_IDENT, 1.0f / p.acc_scale, rank, threadIdx.x, FC_THREADS);
+  else write_ident_tile(smem + FC_OFF_IDENT, 1.0f / p.acc_scale, threadIdx.x, FC_THREADS);
   fence_proxy_async_smem();       // identity tile: generic stores, read by tcgen05.mma
   tc_fence_before_sync();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();   // the peer's barriers must be initialised before anything signals them
+  else __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -402,116 +445,143 @@ __global__ void __launch_bounds__(FC_THREADS, 1) fc_tcgen05_kernel(const __grid_
     // ------------------------------------------------------------ TMA producer (warp-uniform loop, one lane issues)
     int stage = 0;
     uint32_t phase = 0;
-    const uint32_t tx_bytes = FC_A_BYTES + p.block_n * FC_TILE_K * 2;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-      const int mt = item / p.n_tiles;
-      const int nt = item - mt * p.n_tiles;
+    const uint32_t w_rows = PAIR ? uint32_t(p.block_n) / 2u : uint32_t(p.block_n);
+    const uint32_t tx_bytes = FC_A_BYTES + w_rows * FC_TILE_K * 2;
+    for (int item = worker; item < n_items; item += n_workers) {
+      const int mt = item_mt(item);
+      const int nt = item % p.n_tiles;
       for (int kb = p.kb_begin[nt]; kb < p.kb_begin[nt + 1]; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1u, p.err_flag, 100 + stage);
         const uint32_t e = p.kb_src[kb];
         const uint32_t wi = p.kb_w[kb];
-        uint8_t* a_dst = smem + stage * FC_STAGE_BYTES;
+        uint8_t* a_dst = smem + stage * STAGE_BYTES;
         if (elect_one_sync()) {
-          mbar_arrive_expect_tx(&full_bar[stage], wi == FC_W_IDENT ? uint32_t(FC_A_BYTES) : tx_bytes);
-          tma_load_2d(a_dst, &p.a_map[e >> 14], &full_bar[stage], 0,
-                      (mt * p.src_kb[e >> 14] + int(e & 0x3FFFu)) * FC_TILE_M);
-          if (wi != FC_W_IDENT) tma_load_2d(a_dst + FC_A_BYTES, &p.w_map, &full_bar[stage], 0, int(wi) * p.block_n);
+          const uint32_t bytes = wi == FC_W_IDENT ? uint32_t(FC_A_BYTES) : tx_bytes;
+          const int a_row = (mt * p.src_kb[e >> 14] + int(e & 0x3FFFu)) * FC_TILE_M;
+          if constexpr (PAIR) {
+            // the leader's barrier counts both CTAs' bytes; only the leader posts the expectation
+            if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2u * bytes);
+            tma_load_2d_pair(a_dst, &p.a_map[e >> 14], &full_bar[stage], 0, a_row);
+            if (wi != FC_W_IDENT)
+              tma_load_2d_pair(a_dst + FC_A_BYTES, &p.w_half_map, &full_bar[stage], 0, int(wi) * p.block_n + int(rank * w_rows));
+          } else {
+            mbar_arrive_expect_tx(&full_bar[stage], bytes);
+            tma_load_2d(a_dst, &p.a_map[e >> 14], &full_bar[stage], 0, a_row);
+            if (wi != FC_W_IDENT) tma_load_2d(a_dst + FC_A_BYTES, &p.w_map, &full_bar[stage], 0, int(wi) * p.block_n);
+          }
         }
         __syncwarp();
-        if (++stage == FC_STAGES) {
+        if (++stage == STAGES) {
           stage = 0;
           phase ^= 1u;
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer (warp-uniform loop, one lane issues)
-    int stage = 0;
-    uint32_t phase = 0;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    const uint32_t idesc = umma_idesc_f16(uint32_t(p.block_n));
-    const uint32_t idesc_id = umma_idesc_f16(16u);
-    const uint64_t id_desc = ident_desc(base + FC_OFF_IDENT);
-    const uint32_t a_lo0 = umma_desc_lo_sw128(base);
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-      const int nt = item % p.n_tiles;
-      mbar_wait(&acc_empty[acc], acc_phase ^ 1u, p.err_flag, 200 + acc);
-      tc_fence_after_sync();
-      const uint32_t d_tmem = tmem_base + uint32_t(acc * FC_MAX_N);
-      const int kb0 = p.kb_begin[nt], kb1 = p.kb_begin[nt + 1];
-      uint32_t prev_a = 0, prev_w = 0;
-      int prev_stage = 0;
-      for (int kb = kb0; kb < kb1; ++kb) {
-        mbar_wait(&full_bar[stage], phase, p.err_flag, 300 + stage);
+    // ------------------------------------------------------------ MMA issuer (warp-uniform loop, one lane issues; pair: leader only)
+    if (leader) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      const uint32_t idesc = PAIR ? umma_idesc_f16_pair(uint32_t(p.block_n)) : umma_idesc_f16(uint32_t(p.block_n));
+      const uint32_t idesc_id = PAIR ? umma_idesc_f16_pair(16u) : umma_idesc_f16(16u);
+      const uint64_t id_desc = ident_desc(base + FC_OFF_IDENT);
+      const uint32_t a_lo0 = umma_desc_lo_sw128(base);
+      auto mma = [&](uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t acc0) {
+        if constexpr (PAIR) umma_f16_ss_lo_pair(d, a_lo, b_lo, idesc, acc0);
+        else umma_f16_ss_lo(d, a_lo, b_lo, idesc, acc0);
+      };
+      auto commit = [&](uint64_t* bar) {
+        if constexpr (PAIR) umma_commit_pair(bar);
+        else umma_commit(bar);
+      };
+      for (int item = worker; item < n_items; item += n_workers) {
+        const int nt = item % p.n_tiles;
+        mbar_wait(&acc_empty[acc], acc_phase ^ 1u, p.err_flag, 200 + acc);
         tc_fence_after_sync();
-        // low descriptor words of this slot's A and W tiles (+2 per K step of 16 elements)
-        const uint32_t a_lo = a_lo0 + uint32_t(stage) * (FC_STAGE_BYTES >> 4);
-        const uint32_t w_lo = a_lo + (FC_A_BYTES >> 4);
-        const bool ident = p.kb_w[kb] == FC_W_IDENT;
-        const bool first_of_pair = p.pair_mode && !ident && ((kb - kb0) & 1) == 0;
-        if (elect_one_sync()) {
-          if (ident) {
-            // residual K block: acc[:, c0 .. c0+63] += A . (S I), 16 columns per instruction.  These entries
-            // close a tile's schedule, so the accumulator already holds data.
-            const uint32_t c0 = (uint32_t(p.kb_src[kb]) & 0x3FFFu) * FC_TILE_K - uint32_t(nt * p.block_n);
+        const uint32_t d_tmem = tmem_base + uint32_t(acc * FC_MAX_N);
+        const int kb0 = p.kb_begin[nt], kb1 = p.kb_begin[nt + 1];
+        uint32_t prev_a = 0, prev_w = 0;
+        int prev_stage = 0;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase, p.err_flag, 300 + stage);
+          tc_fence_after_sync();
+          // low descriptor words of this slot's A and W tiles (+2 per K step of 16 elements)
+          const uint32_t a_lo = a_lo0 + uint32_t(stage) * (STAGE_BYTES >> 4);
+          const uint32_t w_lo = a_lo + (FC_A_BYTES >> 4);
+          const bool ident = p.kb_w[kb] == FC_W_IDENT;
+          const bool first_of_pair = p.pair_mode && !ident && ((kb - kb0) & 1) == 0;
+          if (elect_one_sync()) {
+            if (ident) {
+              // residual K block: acc[:, c0 .. c0+63] += A . (S I), 16 columns per instruction.  These entries
+              // close a tile's schedule, so the accumulator already holds data.
+              const uint32_t c0 = (uint32_t(p.kb_src[kb]) & 0x3FFFu) * FC_TILE_K - uint32_t(nt * p.block_n);
 #pragma unroll
-            for (int j = 0; j < FC_TILE_K / 16; ++j)
-              umma_f16_ss(d_tmem + c0 + j * 16, (uint64_t(0x40004040u) << 32) | uint64_t(a_lo + 2 * j), id_desc, idesc_id, 1u);
-            umma_commit(&empty_bar[stage]);
-          } else if (!p.pair_mode) {
-            umma_f16_ss_lo(d_tmem, a_lo, w_lo, idesc, kb > kb0 ? 1u : 0u);
-            umma_f16_ss_lo(d_tmem, a_lo + 2, w_lo + 2, idesc, 1u);
-            umma_f16_ss_lo(d_tmem, a_lo + 4, w_lo + 4, idesc, 1u);
-            umma_f16_ss_lo(d_tmem, a_lo + 6, w_lo + 6, idesc, 1u);
-            umma_commit(&empty_bar[stage]);   // frees the smem slot once these MMAs have read it
-          } else if (first_of_pair) {
-            // (x_hi, w_hi): the slot stays live until the cross products of the next entry are done
-            umma_f16_ss_lo(d_tmem, a_lo, w_lo, idesc, kb > kb0 ? 1u : 0u);
-            umma_f16_ss_lo(d_tmem, a_lo + 2, w_lo + 2, idesc, 1u);
-            umma_f16_ss_lo(d_tmem, a_lo + 4, w_lo + 4, idesc, 1u);
-            umma_f16_ss_lo(d_tmem, a_lo + 6, w_lo + 6, idesc, 1u);
-          } else {
-            // this slot holds (x_lo, w_lo): issue x_hi * w_lo and x_lo * w_hi
+              for (int j = 0; j < FC_TILE_K / 16; ++j) {
+                const uint64_t a_desc = (uint64_t(0x40004040u) << 32) | uint64_t(a_lo + 2 * j);
+                if constexpr (PAIR) umma_f16_ss_pair(d_tmem + c0 + j * 16, a_desc, id_desc, idesc_id, 1u);
+                else umma_f16_ss(d_tmem + c0 + j * 16, a_desc, id_desc, idesc_id, 1u);
+              }
+              commit(&empty_bar[stage]);
+            } else if (!p.pair_mode) {
+              mma(d_tmem, a_lo, w_lo, kb > kb0 ? 1u : 0u);
+              mma(d_tmem, a_lo + 2, w_lo + 2, 1u);
+              mma(d_tmem, a_lo + 4, w_lo + 4, 1u);
+              mma(d_tmem, a_lo + 6, w_lo + 6, 1u);
+              commit(&empty_bar[stage]);   // frees the smem slot once these MMAs have read it
+            } else if (first_of_pair) {
+              // (x_hi, w_hi): the slot stays live until the cross products of the next entry are done
+              mma(d_tmem, a_lo, w_lo, kb > kb0 ? 1u : 0u);
+              mma(d_tmem, a_lo + 2, w_lo + 2, 1u);
+              mma(d_tmem, a_lo + 4, w_lo + 4, 1u);
+              mma(d_tmem, a_lo + 6, w_lo + 6, 1u);
+            } else {
+              // this slot holds (x_lo, w_lo): issue x_hi * w_lo and x_lo * w_hi
 #pragma unroll
-            for (int k = 0; k < FC_TILE_K / 16; ++k) umma_f16_ss_lo(d_tmem, prev_a + 2 * k, w_lo + 2 * k, idesc, 1u);
+              for (int k = 0; k < FC_TILE_K / 16; ++k) mma(d_tmem, prev_a + 2 * k, w_lo + 2 * k, 1u);
 #pragma unroll
-            for (int k = 0; k < FC_TILE_K / 16; ++k) umma_f16_ss_lo(d_tmem, a_lo + 2 * k, prev_w + 2 * k, idesc, 1u);
-            umma_commit(&empty_bar[prev_stage]);
-            umma_commit(&empty_bar[stage]);
+              for (int k = 0; k < FC_TILE_K / 16; ++k) mma(d_tmem, a_lo + 2 * k, prev_w + 2 * k, 1u);
+              commit(&empty_bar[prev_stage]);
+              commit(&empty_bar[stage]);
+            }
+            if (kb + 1 == kb1) commit(&acc_full[acc]);   // accumulator complete -> epilogue (of both CTAs)
           }
-          if (kb + 1 == kb1) umma_commit(&acc_full[acc]);   // accumulator complete -> epilogue
+          __syncwarp();
+          if (first_of_pair) {
+            prev_a = a_lo;
+            prev_w = w_lo;
+            prev_stage = stage;
+          }
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
         }
-        __syncwarp();
-        if (first_of_pair) {
-          prev_a = a_lo;
-          prev_w = w_lo;
-          prev_stage = stage;
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1u;
         }
-        if (++stage == FC_STAGES) {
-          stage = 0;
-          phase ^= 1u;
-        }
-      }
-      if (++acc == 2) {
-        acc = 0;
-        acc_phase ^= 1u;
       }
     }
   } else if (warp < FC_STORE_WARP) {
-    // ------------------------------------------------------------ epilogue (warps 2..9)
+    // ------------------------------------------------------------ epilogue (warps 2..17)
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t g = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-      const int mt = item / p.n_tiles;
-      const int nt = item - mt * p.n_tiles;
+    // pair: the peer's epilogue warps hand accumulators back on the leader's barriers
+    const uint32_t rem0 = (PAIR && !leader) ? mapa_shared(smem_u32(&acc_empty[0]), 0u) : 0u;
+    const uint32_t rem1 = (PAIR && !leader) ? mapa_shared(smem_u32(&acc_empty[1]), 0u) : 0u;
+    for (int item = worker; item < n_items; item += n_workers) {
+      const int mt = item_mt(item);
+      const int nt = item % p.n_tiles;
       const uint32_t t_col = tmem_base + uint32_t(acc * FC_MAX_N);
+      const uint32_t rem = acc ? rem1 : rem0;
       if (p.epi == FC_EPI_HEAD)
-        epi_tile_head(p, n_rows, mt, p.block_n, t_col, &acc_full[acc], acc_phase, &acc_empty[acc], tail_w_s, warp, lane, 400 + acc);
+        epi_tile_head(p, n_rows, mt, p.block_n, t_col, &acc_full[acc], acc_phase, &acc_empty[acc], tail_w_s, warp, lane, 400 + acc, rem);
       else
         epi_tile_store(p, es, g, n_rows, mt, nt * p.block_n, p.block_n, t_col, &acc_full[acc], acc_phase, &acc_empty[acc], warp,
-                       lane, 400 + acc);
+                       lane, 400 + acc, rem);
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1u;
@@ -521,9 +591,9 @@ __global__ void __launch_bounds__(FC_THREADS, 1) fc_tcgen05_kernel(const __grid_
     // ------------------------------------------------------------ store warp: staged tiles -> global (TMA)
     if (p.epi != FC_EPI_HEAD) {
       uint32_t g = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int mt = item / p.n_tiles;
-        const int nt = item - mt * p.n_tiles;
+      for (int item = worker; item < n_items; item += n_workers) {
+        const int mt = item_mt(item);
+        const int nt = item % p.n_tiles;
         if ((mt + 1) * FC_TILE_M > n_rows) continue;      // partial tile: the epilogue stores it directly
         epi_store_chunks(es, g, &p.out_map[0], &p.out_map[1], p.out_lo != nullptr, nt * p.block_n, p.block_n / EPI_CHUNK,
                          mt, p.out_kb, p.err_flag);
@@ -533,10 +603,12 @@ __global__ void __launch_bounds__(FC_THREADS, 1) fc_tcgen05_kernel(const __grid_
   }
 
   tc_fence_before_sync();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();     // nobody may exit while the other CTA can still signal its barriers
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after_sync();
-    tmem_dealloc(tmem_base, 512);
+    if constexpr (PAIR) tmem_dealloc_pair(tmem_base, 512);
+    else tmem_dealloc(tmem_base, 512);
   }
 }
 
