@@ -131,21 +131,30 @@ int add_residual_entries(FcParams& f, bool has_lo) {
   int begin[FC_MAX_NT + 1];
   begin[0] = 0;
   const int per_tile = f.block_n / FC_TILE_K;
+  const int step = f.pair_mode ? 2 : 1;             // regular entries come in (hi, lo) pairs in split precision
+  if (f.pair_mode && !has_lo) return fail(AV1P_EINVAL, "split-precision residual FC layer needs the residual's lo plane");
   for (int t = 0; t < f.n_tiles; ++t) {
-    for (int e = f.kb_begin[t]; e < f.kb_begin[t + 1]; ++e) {
-      if ((f.kb_src[e] >> 14) >= 2) return fail(AV1P_EINVAL, "residual FC layer uses more than one activation source");
-      src.push_back(f.kb_src[e]);
-      w.push_back(f.kb_w[e]);
-    }
-    for (int j = 0; j < per_tile; ++j) {
-      const uint16_t kb = uint16_t(t * per_tile + j);
+    // Residual K blocks carry almost no tensor work, so a run of them would expose one producer<->MMA ring round trip
+    // each; interleave them with the regular entries (after the first one, which initialises the accumulator).
+    int next_res = 0;
+    auto push_res = [&]() {
+      const uint16_t kb = uint16_t(t * per_tile + next_res++);
       src.push_back(uint16_t((2u << 14) | kb));
       w.push_back(FC_W_IDENT);
       if (has_lo) {
         src.push_back(uint16_t((3u << 14) | kb));
         w.push_back(FC_W_IDENT);
       }
+    };
+    for (int e = f.kb_begin[t]; e < f.kb_begin[t + 1]; e += step) {
+      for (int j = 0; j < step && e + j < f.kb_begin[t + 1]; ++j) {
+        if ((f.kb_src[e + j] >> 14) >= 2) return fail(AV1P_EINVAL, "residual FC layer uses more than one activation source");
+        src.push_back(f.kb_src[e + j]);
+        w.push_back(f.kb_w[e + j]);
+      }
+      if (next_res < per_tile) push_res();
     }
+    while (next_res < per_tile) push_res();
     begin[t + 1] = int(src.size());
   }
   if (src.size() > size_t(FC_MAX_KB)) return fail(AV1P_EINVAL, "residual FC layer: %zu schedule entries exceed %d", src.size(), FC_MAX_KB);

@@ -179,37 +179,39 @@ __device__ __forceinline__ void cr_issue_mtile(CrPipe& q, uint32_t base, uint32_
           __syncwarp();
           next_stage();
         }
+        // Output rows whose last input row is iy: their residual tile of position ox = xi follows immediately, so the
+        // (almost MMA-free) residual ring tiles interleave with conv tiles instead of exposing a ring round trip each.
+#pragma unroll
+        for (int o = 0; o < 2; ++o) {
+          const int oy = 2 * h + o;
+          if (!RESID || iy != (oy < 3 ? oy + 1 : 3)) continue;
+          const int ox = xi;
+#pragma unroll
+          for (int pl = 0; pl < AUX_PLANES; ++pl) {
+            const uint32_t a_lo = wait_tile();
+            tc_fence_after_sync();
+            if (elect_one_sync()) {
+              const uint32_t d_tmem = tmem_base + uint32_t(o * 256 + ox * 64);
+              if (!skip_mma) {
+#pragma unroll
+                for (int j = 0; j < FC_TILE_K / 16; ++j) {
+                  const uint64_t a_desc = (uint64_t(0x40004040u) << 32) | uint64_t(a_lo + 2 * j);
+                  umma_f16_ss(d_tmem + j * 16, a_desc, id_desc, idesc_id, 1u);
+                }
+              }
+              umma_commit(&q.empty_bar[q.stage]);
+              if (ox == 3 && pl == AUX_PLANES - 1) umma_commit(&q.acc_full[o]);
+            }
+            __syncwarp();
+            next_stage();
+          }
+        }
       }
-      // output rows whose last input row is iy
+      // accumulator parity of the output rows completed by this input row
 #pragma unroll
       for (int o = 0; o < 2; ++o) {
         const int oy = 2 * h + o;
-        if (iy != (oy < 3 ? oy + 1 : 3)) continue;
-        if (RESID) {
-#pragma unroll
-          for (int ox = 0; ox < 4; ++ox) {
-#pragma unroll
-            for (int pl = 0; pl < AUX_PLANES; ++pl) {
-              const uint32_t a_lo = wait_tile();
-              tc_fence_after_sync();
-              if (elect_one_sync()) {
-                const uint32_t d_tmem = tmem_base + uint32_t(o * 256 + ox * 64);
-                if (!skip_mma) {
-#pragma unroll
-                  for (int j = 0; j < FC_TILE_K / 16; ++j) {
-                    const uint64_t a_desc = (uint64_t(0x40004040u) << 32) | uint64_t(a_lo + 2 * j);
-                    umma_f16_ss(d_tmem + j * 16, a_desc, id_desc, idesc_id, 1u);
-                  }
-                }
-                umma_commit(&q.empty_bar[q.stage]);
-                if (ox == 3 && pl == AUX_PLANES - 1) umma_commit(&q.acc_full[o]);
-              }
-              __syncwarp();
-              next_stage();
-            }
-          }
-        }
-        q.acc_phase ^= 1u << o;
+        if (iy == (oy < 3 ? oy + 1 : 3)) q.acc_phase ^= 1u << o;
       }
     }
   }
@@ -360,7 +362,7 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_res_tcgen05_kernel(const _
 
 // Host side: the producer's per-M-tile load order (must match cr_issue_mtile): two halves (output rows {0,1},
 // {2,3}); per half the three input rows it needs; per input row the positions ix = 1, 0, 2, 3; hi plane then lo
-// plane; after the last input row of an output row its four residual tiles.
+// plane; while an output row's last input row streams by, its residual tile of position xi follows x tile xi.
 inline bool conv_res_build_schedule(ConvResParams& f) {
   const int planes = f.split ? 2 : 1;
   const bool residual = f.epi == FC_EPI_ADD_RELU;
@@ -369,18 +371,18 @@ inline bool conv_res_build_schedule(ConvResParams& f) {
   int n = 0;
   for (int h = 0; h < 2; ++h) {
     for (int iy = h; iy < h + 3; ++iy) {
-      for (int xi = 0; xi < 4; ++xi)
+      for (int xi = 0; xi < 4; ++xi) {
         for (int pl = 0; pl < planes; ++pl) {
           if (n >= CR_MAX_RING) return false;
           f.ring[n++] = uint8_t((pl << 4) | (iy * 4 + ix_order[xi]));
         }
-      for (int oy = 2 * h; oy < 2 * h + 2; ++oy) {
-        if (!residual || iy != (oy < 3 ? oy + 1 : 3)) continue;
-        for (int ox = 0; ox < 4; ++ox)
+        for (int oy = 2 * h; oy < 2 * h + 2; ++oy) {
+          if (!residual || iy != (oy < 3 ? oy + 1 : 3)) continue;
           for (int pl = 0; pl < aux_planes; ++pl) {
             if (n >= CR_MAX_RING) return false;
-            f.ring[n++] = uint8_t(((2 + pl) << 4) | (oy * 4 + ox));
+            f.ring[n++] = uint8_t(((2 + pl) << 4) | (oy * 4 + xi));
           }
+        }
       }
     }
   }
