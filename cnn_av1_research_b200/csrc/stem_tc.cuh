@@ -9,8 +9,11 @@
 // GEMM view, per tile of 4 blocks:   D[channel, (block, position)] = W[channel, tap] . patch[(block, position), tap]
 //   M operand : folded conv1 weights, 64 channels x 64 K (49 taps + zero pad), stacked twice to fill M = 128,
 //               fp16 hi and lo, resident in shared memory for the whole (persistent) kernel;
-//   N operand : im2col rows (4 blocks x 64 conv positions = 256) x 64 K, fp16 hi and lo, built by four
-//               producer warps from the pixel tile directly in the SWIZZLE_128B K-major layout;
+//   N operand : im2col rows (4 blocks x 64 conv positions = 256) x 64 K, fp16 hi and lo, built by the producer
+//               warps directly in the SWIZZLE_128B K-major layout.  K is laid out as ky * 8 + kx (the kernel row
+//               padded to eight taps, weight 0 for kx = 7 and for k >= 56), so one 16-byte K chunk of an im2col row
+//               is eight CONSECUTIVE pixels of one row of the pixel tile: the tile is kept as fp16 hi / lo planes
+//               (split once per pixel) and a chunk is four 32-bit shared loads per plane, no per-tap arithmetic;
 //   products  : W_hi.P_hi + W_hi.P_lo + W_lo.P_hi (split precision), fp32 accumulators in TMEM (256 cols x 2).
 // Because the channels are the accumulator rows (TMEM lanes), one epilogue thread owns a channel and sees all
 // 64 conv positions of a block in its columns: bias, ReLU and the 3x3/s2 max-pool run in registers, and a warp
@@ -27,9 +30,11 @@ constexpr int ST_W_BYTES = 128 * 128;            // one weight plane (hi or lo):
 constexpr int ST_P_BYTES = ST_N * 128;           // one patch plane: 256 rows x 128 B
 constexpr int ST_STAGE_BYTES = 2 * ST_P_BYTES;   // hi + lo
 constexpr int ST_TILE_H = 22, ST_TILE_W = 24;    // 16x16 block + 3-pixel zero halo (width padded)
-constexpr int ST_PIX_BYTES = ST_BLOCKS * ST_TILE_H * ST_TILE_W * 4;
+constexpr int ST_PIX_PLANE = ST_BLOCKS * ST_TILE_H * ST_TILE_W;   // fp16 elements per plane
+constexpr int ST_PIX_BYTES = 2 * 2 * ST_PIX_PLANE * 2;           // two buffers x (hi + lo) planes
 constexpr int ST_PRODUCERS = 256;                // 8 warps (2 per scheduler) so the im2col LDS latency overlaps
-constexpr int ST_THREADS = ST_PRODUCERS + 32 + 128;   // producers, MMA warp, epilogue warps
+constexpr int ST_EPI_WARPS = 8;                  // two per TMEM lane quadrant: one block of the pair each
+constexpr int ST_THREADS = ST_PRODUCERS + 32 + 32 * ST_EPI_WARPS;   // producers, MMA warp, epilogue warps
 constexpr int ST_SMEM_BYTES = 1024 + 2 * ST_W_BYTES + ST_STAGES * ST_STAGE_BYTES + ST_PIX_BYTES + 256;
 
 struct StemInput {
@@ -49,7 +54,7 @@ struct StemParams {
   const int* idx;           // optional gather list: row r processes block id idx[r]
   const int* n_dev;         // device-side row count (nullptr -> n)
   int n;
-  const __half* w;          // [2][128][64] folded conv1 weights x 2^s: hi plane then lo plane, K = ky*7+kx (49..63 zero)
+  const __half* w;          // [2][128][64] folded conv1 weights x 2^s: hi plane then lo plane, K = ky*8+kx (kx = 7 and k >= 56 zero)
   const float* b;           // [64] folded bias
   float acc_scale;          // 2^-s
   __half* out;              // [rows][1024] in the tiled activation layout (act_off, 16 blocks per row)
@@ -68,8 +73,9 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_tc_kernel(const __grid_con
   uint8_t* w_hi = smem;                                   // [128][128 B] swizzled
   uint8_t* w_lo = smem + ST_W_BYTES;
   uint8_t* stages = smem + 2 * ST_W_BYTES;                // [ST_STAGES][hi | lo]
-  float* pix = reinterpret_cast<float*>(stages + ST_STAGES * ST_STAGE_BYTES);   // [4][22][24]
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(pix) + ST_PIX_BYTES);
+  // pixel tiles: [2 buffers][hi, lo][4 blocks][22][24] fp16; hi = fp16(x), lo = fp16(x - hi), 3-pixel zero halo
+  __half* pix_hi = reinterpret_cast<__half*>(stages + ST_STAGES * ST_STAGE_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(pix_hi) + ST_PIX_BYTES);
   uint64_t* empty_bar = full_bar + ST_STAGES;
   uint64_t* acc_full = empty_bar + ST_STAGES;             // [2]
   uint64_t* acc_empty = acc_full + 2;                     // [2]
@@ -86,15 +92,15 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_tc_kernel(const __grid_con
     const uint4 v = __ldg(reinterpret_cast<const uint4*>(p.w + (size_t(plane) * 128 + row) * 64 + c * 8));
     *reinterpret_cast<uint4*>((plane ? w_lo : w_hi) + row * 128 + ((c ^ (row & 7)) << 4)) = v;
   }
-  for (int i = threadIdx.x; i < ST_PIX_BYTES / 4; i += ST_THREADS) pix[i] = 0.f;
+  for (int i = threadIdx.x; i < ST_PIX_BYTES / 4; i += ST_THREADS) reinterpret_cast<uint32_t*>(pix_hi)[i] = 0u;   // halo stays zero
   if (threadIdx.x == 0) {
     for (int s = 0; s < ST_STAGES; ++s) {
-      mbar_init(&full_bar[s], ST_PRODUCERS);
+      mbar_init(&full_bar[s], ST_PRODUCERS / 32);
       mbar_init(&empty_bar[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], 4);
+      mbar_init(&acc_empty[s], ST_EPI_WARPS);
     }
     fence_mbar_init();
   }
@@ -111,24 +117,19 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_tc_kernel(const __grid_con
   if (warp < ST_PRODUCERS / 32) {
     // ------------------------------------------------------------ producers: gather + im2col
     const int tid = threadIdx.x;                     // 0..ST_PRODUCERS-1
-    const int c = tid & 7;                           // 16-byte K chunk this thread always writes
-    int tap_off[8];                                  // offset of tap k = 8c+j inside the pixel tile, -1 = zero pad
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int k = 8 * c + j;
-      tap_off[j] = k < 49 ? (k / 7) * ST_TILE_W + (k % 7) : -1;
-    }
-    // pixel gather: 4 blocks x 16 rows x 2 half-rows = 128 work items of 8 samples (producer threads 0..127).
-    // The loads of tile t+1 are issued before the im2col of tile t is built, so their latency is hidden.
-    const int pb = tid >> 5, ppy = (tid >> 1) & 15, ppx0 = (tid & 1) * 8;
-    // raw[] holds either four packed pairs of 16-bit samples (mode 1, converted when the tile is consumed, so
-    // that nothing waits on the load here) or eight ready float bit patterns (mode 0).
-    auto gather = [&](int tile, uint32_t (&raw)[8], int& mode) {
+    const int c = tid & 7;                           // 16-byte K chunk this thread always writes = kernel row ky (7: zero pad)
+    // pixel gather: 4 blocks x 16 rows x 4 quarter-rows = 256 work items of 4 samples, one per producer thread.
+    // The raw samples of tile t+2 are in flight (registers) while tile t+1 is split into the spare pixel buffer and
+    // tile t's im2col is built from the current one: one barrier per tile.
+    const int pb = tid >> 6, ppy = (tid >> 2) & 15, ppx0 = (tid & 3) * 4;
+    // raw[] holds either two packed pairs of 16-bit samples (mode 1, converted when the tile is consumed, so that
+    // nothing waits on the load here) or four ready float bit patterns (mode 0).
+    auto gather = [&](int tile, uint32_t (&raw)[4], int& mode) {
       mode = 0;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) raw[j] = 0u;
+      for (int j = 0; j < 4; ++j) raw[j] = 0u;
       const int r = tile * ST_BLOCKS + pb;
-      if (tid >= 128 || tile >= tiles || r >= n) return;
+      if (tile >= tiles || r >= n) return;
       const int g = p.idx ? __ldg(p.idx + r) : r;
       if (p.in.kind == 0) {
         const int f = g / p.in.blocks_per_frame;
@@ -137,68 +138,78 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_tc_kernel(const __grid_con
         const int y = by * 16 + ppy, x0 = bx * 16 + ppx0;
         if (y < p.in.height) {
           const uint16_t* src = p.in.frames + size_t(f) * p.in.frame_stride + size_t(y) * p.in.pitch + x0;
-          if (x0 + 7 < p.in.width && ((reinterpret_cast<uintptr_t>(src) & 15u) == 0)) {
-            const uint4 q = __ldg(reinterpret_cast<const uint4*>(src));
-            raw[0] = q.x; raw[1] = q.y; raw[2] = q.z; raw[3] = q.w;
+          if (x0 + 3 < p.in.width && ((reinterpret_cast<uintptr_t>(src) & 7u) == 0)) {
+            const uint2 q = __ldg(reinterpret_cast<const uint2*>(src));
+            raw[0] = q.x; raw[1] = q.y;
             mode = 1;
           } else {
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
+            for (int j = 0; j < 4; ++j)
               if (x0 + j < p.in.width) raw[j] = __float_as_uint(__fdiv_rn(float(__ldg(src + j)), 1023.0f));
           }
         }
       } else {
-        const uint4* src = reinterpret_cast<const uint4*>(p.in.images + size_t(g) * 256 + ppy * 16 + ppx0);
-        const uint4 a = __ldg(src), bb = __ldg(src + 1);
+        const uint4 a = __ldg(reinterpret_cast<const uint4*>(p.in.images + size_t(g) * 256 + ppy * 16 + ppx0));
         raw[0] = a.x; raw[1] = a.y; raw[2] = a.z; raw[3] = a.w;
-        raw[4] = bb.x; raw[5] = bb.y; raw[6] = bb.z; raw[7] = bb.w;
       }
     };
-    int stage = 0;
+    // split the four samples into the fp16 hi / lo planes of pixel buffer `buf`
+    auto write_pix = [&](int buf, const uint32_t (&raw)[4], int mode) {
+      const int o = buf * 2 * ST_PIX_PLANE + (pb * ST_TILE_H + ppy + 3) * ST_TILE_W + ppx0 + 3;
+      float x[4];
+      if (mode) {
+        x[0] = __fdiv_rn(float(raw[0] & 0xFFFFu), 1023.0f);
+        x[1] = __fdiv_rn(float(raw[0] >> 16), 1023.0f);
+        x[2] = __fdiv_rn(float(raw[1] & 0xFFFFu), 1023.0f);
+        x[3] = __fdiv_rn(float(raw[1] >> 16), 1023.0f);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) x[j] = __uint_as_float(raw[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {                   // o is odd: scalar fp16 stores
+        const __half h = __float2half_rn(x[j]);
+        pix_hi[o + j] = h;
+        pix_hi[o + ST_PIX_PLANE + j] = __float2half_rn(x[j] - __half2float(h));
+      }
+    };
+    int stage = 0, cur = 0;
     uint32_t phase = 0;
-    uint32_t nxt[8];
+    uint32_t nxt[4];
     int nxt_mode;
     gather(blockIdx.x, nxt, nxt_mode);
+    write_pix(0, nxt, nxt_mode);
+    gather(blockIdx.x + gridDim.x, nxt, nxt_mode);
+    named_bar_sync(1, ST_PRODUCERS);
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-      if (tid < 128) {
-        float* t = pix + (pb * ST_TILE_H + ppy + 3) * ST_TILE_W + ppx0 + 3;
-        if (nxt_mode) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            t[2 * j] = __fdiv_rn(float(nxt[j] & 0xFFFFu), 1023.0f);
-            t[2 * j + 1] = __fdiv_rn(float(nxt[j] >> 16), 1023.0f);
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) t[j] = __uint_as_float(nxt[j]);
-        }
-      }
-      gather(tile + gridDim.x, nxt, nxt_mode);        // in flight while this tile's im2col is built
-      named_bar_sync(1, ST_PRODUCERS);
+      write_pix(cur ^ 1, nxt, nxt_mode);               // tile t+1 -> spare buffer
+      gather(tile + 2 * gridDim.x, nxt, nxt_mode);     // tile t+2 in flight
       mbar_wait(&empty_bar[stage], phase ^ 1u, p.err_flag, 500 + stage);
       uint8_t* s_hi = stages + stage * ST_STAGE_BYTES;
       uint8_t* s_lo = s_hi + ST_P_BYTES;
+      const __half* ph_base = pix_hi + cur * 2 * ST_PIX_PLANE;
 #pragma unroll 4
       for (int i = 0; i < (ST_N * 8) / ST_PRODUCERS; ++i) {
         const int row = (tid >> 3) + (ST_PRODUCERS / 8) * i;   // im2col row = block * 64 + conv position
         const int b = row >> 6, pos = row & 63;
-        const float* t = pix + (b * ST_TILE_H + 2 * (pos >> 3)) * ST_TILE_W + 2 * (pos & 7);
-        __align__(16) __half2 hi[4], lo[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float x0 = tap_off[2 * j] >= 0 ? t[tap_off[2 * j]] : 0.f;
-          const float x1 = tap_off[2 * j + 1] >= 0 ? t[tap_off[2 * j + 1]] : 0.f;
-          hi[j] = __floats2half2_rn(x0, x1);
-          const float2 hf = __half22float2(hi[j]);
-          lo[j] = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+        uint4 hi = make_uint4(0u, 0u, 0u, 0u), lo = hi;
+        if (c < 7) {
+          // kernel row c of conv position (py, px): tile row 2*py + c, tile columns 2*px .. 2*px + 7 (4-byte aligned)
+          const int o = (b * ST_TILE_H + 2 * (pos >> 3) + c) * ST_TILE_W + 2 * (pos & 7);
+          const uint32_t* ph = reinterpret_cast<const uint32_t*>(ph_base + o);
+          const uint32_t* pl = reinterpret_cast<const uint32_t*>(ph_base + ST_PIX_PLANE + o);
+          hi = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+          lo = make_uint4(pl[0], pl[1], pl[2], pl[3]);
         }
         const int dst = row * 128 + ((c ^ (row & 7)) << 4);
-        *reinterpret_cast<uint4*>(s_hi + dst) = *reinterpret_cast<const uint4*>(hi);
-        *reinterpret_cast<uint4*>(s_lo + dst) = *reinterpret_cast<const uint4*>(lo);
+        *reinterpret_cast<uint4*>(s_hi + dst) = hi;
+        *reinterpret_cast<uint4*>(s_lo + dst) = lo;
       }
       fence_proxy_async_smem();                       // generic-proxy stores -> visible to tcgen05.mma
-      mbar_arrive(&full_bar[stage]);
-      named_bar_sync(1, ST_PRODUCERS);                // nobody still reads the pixel tile
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full_bar[stage]);
+      named_bar_sync(1, ST_PRODUCERS);                // tile t+1's pixels are complete; nobody still reads buffer `cur`
+      cur ^= 1;
       if (++stage == ST_STAGES) {
         stage = 0;
         phase ^= 1u;
@@ -241,6 +252,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_tc_kernel(const __grid_con
     const int quad = warp & 3;
     const int ch = (quad & 1) * 32 + lane;            // accumulator row -> channel (rows 64..127 repeat 0..63)
     const int blk0 = (quad >> 1) * 2;                 // rows 0..63 take blocks 0,1 of the tile, rows 64..127 blocks 2,3
+    const int bi = (warp - (ST_PRODUCERS / 32 + 1)) >> 2;   // which block of that pair this warp handles
     const float bias = p.b[ch];
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -248,15 +260,14 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_tc_kernel(const __grid_con
       mbar_wait(&acc_full[acc], acc_phase, p.err_flag, 800 + acc);
       tc_fence_after_sync();
       const uint32_t t_addr = tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(acc * ST_N);
-#pragma unroll 1
-      for (int bi = 0; bi < 2; ++bi) {
+      {
         const int blk = blk0 + bi;
         const int r = tile * ST_BLOCKS + blk;
         uint32_t v0[32], v1[32];
         tmem_ld_32x32(t_addr + uint32_t(blk * 64), v0);        // conv rows 0..3
         tmem_ld_32x32(t_addr + uint32_t(blk * 64 + 32), v1);   // conv rows 4..7
         tmem_ld_wait();
-        if (r >= n) continue;
+        if (r < n) {
         float cv[64];
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
@@ -284,6 +295,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_tc_kernel(const __grid_con
             o[size_t(qy * 4 + qx) << 13] = h;
             if (ol) ol[size_t(qy * 4 + qx) << 13] = __float2half_rn(m - __half2float(h));
           }
+        }
         }
       }
       tc_fence_before_sync();

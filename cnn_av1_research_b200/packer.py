@@ -26,7 +26,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import numpy as np
 
 BLOB_MAGIC = 0x50315641
-BLOB_VERSION = 7
+BLOB_VERSION = 8
 MAX_NT = 8
 MAX_KB = 128
 TILE_K = 64
@@ -243,12 +243,13 @@ def backbone_ops(sd, precision: str = "fp16x3", prefix: str = "backbone.", layer
     p = prefix
     ops: List[_Op] = []
     # --- stem: conv1 + bn1 (+ relu + maxpool in the kernel's epilogue).  The 64 x 49 folded weights are the
-    #     M operand of the stem GEMM: K padded to 64, rows stacked twice (M = 128), fp16 hi / lo planes.
+    #     M operand of the stem GEMM: K = ky * 8 + kx (64), rows stacked twice (M = 128), fp16 hi / lo planes.
     w, b = fold_bn(_np64(sd[p + "conv1.weight"]), None, sd, p + "bn1")
-    w = w.reshape(64, 49)
     scale = 2.0 ** int(np.clip(np.floor(np.log2(8192.0 / np.abs(w).max())), 0, 15))
     wk = np.zeros((128, 64), dtype=np.float64)
-    wk[:64, :49] = w * scale
+    wrow = np.zeros((64, 8, 8), dtype=np.float64)          # K = ky * 8 + kx: kernel rows padded to eight taps (kx = 7 and ky = 7 zero)
+    wrow[:, :7, :7] = w[:, 0] * scale
+    wk[:64] = wrow.reshape(64, 64)
     wk[64:] = wk[:64]
     w_hi = wk.astype(np.float16)
     w_lo = (wk - w_hi.astype(np.float64)).astype(np.float16)

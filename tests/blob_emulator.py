@@ -17,7 +17,7 @@ OP_BYTES = struct.calcsize(OP_FMT)
 
 def parse(blob: bytes):
     magic, version, kind, n_ops, n_bufs, n_out, prec, _, ops_off, bufs_off, total, _ = struct.unpack_from("<8I4Q", blob, 0)
-    assert magic == 0x50315641 and version == 7 and total == len(blob)
+    assert magic == 0x50315641 and version == 8 and total == len(blob)
     cols = struct.unpack_from(f"<{n_bufs}I", blob, bufs_off)
     ops = []
     for i in range(n_ops):
@@ -58,7 +58,7 @@ def run(blob: bytes, images: np.ndarray) -> np.ndarray:
         t = op["type"]
         if t == 0:  # stem
             wp = _arr(blob, op["w_off"], np.float16, 2 * 128 * 64).reshape(2, 128, 64).astype(np.float32)
-            w = ((wp[0, :64, :49] + wp[1, :64, :49]) * np.float32(op["f0"])).reshape(64, 1, 7, 7)
+            w = ((wp[0, :64] + wp[1, :64]) * np.float32(op["f0"])).reshape(64, 8, 8)[:, :7, :7].reshape(64, 1, 7, 7)   # K = ky*8 + kx
             b = _arr(blob, op["bias_off"], np.float32, 64)
             x = F.conv2d(torch.from_numpy(images), torch.from_numpy(w.copy()), torch.from_numpy(b.copy()), stride=2, padding=3)
             x = F.max_pool2d(F.relu(x), 3, 2, 1)                       # [n,64,4,4]

@@ -87,7 +87,7 @@ def test_resident_conv_program_equals_block_toeplitz_program(stage_fixture):
 def test_blob_layout():
     blob = packer.pack_stage("rect", synth.random_state_dict("rect", 0), "fp16x3")
     magic, version, kind, n_ops, n_bufs, n_out = struct.unpack_from("<6I", blob, 0)
-    assert (magic, version, kind, n_bufs, n_out) == (0x50315641, 7, 2, 20, 2)
+    assert (magic, version, kind, n_bufs, n_out) == (0x50315641, packer.BLOB_VERSION, 2, 20, 2)
     P = E.parse(blob)
     assert P["ops"][0]["type"] == packer.OP_STEM and P["ops"][-1]["epi"] == packer.EPI_HEAD
     for op in P["ops"]:
