@@ -159,3 +159,43 @@ def test_host_frames_end_to_end_matches_resident(cuda_device):
     assert got.device.type == "cpu" and torch.equal(got, ref)
     with pytest.raises(ValueError):
         pipe.predict_frames_host(host.to(cuda_device), w, h, nf)
+
+
+def test_config3_full_cascade_on_a_1080p_frame(cuda_device):
+    """BASELINE configs[2]: full cascade on one 1920x1080 frame, extraction included (68 x 120 = 8,160 blocks, the last grid
+    row is half padding) - every label against the CPU oracle on the same frame."""
+    w, h, thr = 1920, 1080, 0.45
+    words = synth.synth_frames(1, w, h, seed=31)
+    pipe = build_pipeline(seed=0, threshold=thr, device=cuda_device)
+    labels = pipe.predict_frames(frames_tensor(words, cuda_device), w, h, 1).cpu().numpy()
+    assert labels.shape == (8160,)
+    ref = O.cascade_predict(synth.calibrated_cascade(0), O.frames_to_images(words, 1, w, h), thr, chunk=2048)
+    agree = float((labels == ref["labels"].numpy()).mean())
+    assert agree >= 0.999, agree
+    mid = pipe.cascade(8160).intermediates(8160)
+    assert np.array_equal(mid["idx2"].cpu().numpy(), ref["idx2"].numpy().astype(np.int32)) or agree < 1.0
+    assert np.abs(mid["logits1"].cpu().numpy() - ref["logits1"].numpy()).max() <= 5e-3
+
+
+def test_config2_stage2_forward_on_routed_blocks_of_a_4k_frame(cuda_device):
+    """BASELINE configs[1]: Stage-2 forward on the blocks Stage 1 routes out of a 4K frame (index list taken from the
+    reference path), gathered by the kernel straight from the planar frame: logits against the CPU oracle."""
+    import ctypes as C
+    from cnn_av1_research_b200.runtime import NativeStage
+    w, h, thr = 3840, 2160, 0.45
+    words = synth.synth_frames(1, w, h, seed=55)
+    images = O.frames_to_images(words, 1, w, h)
+    sds = synth.calibrated_cascade(0)
+    idx2 = O.route_stage1(O.stage_logits("stage1", sds["stage1"], images[:8192]), thr)      # reference routing of the first 8,192 blocks
+    assert 0.3 < idx2.numel() / 8192 < 0.6
+    nets = build_models(seed=0)
+    model = nets["stage2"].native_model(cuda_device)
+    stage = NativeStage(model, 8192)
+    idx_dev = idx2.to(torch.int32).to(cuda_device)
+    n_dev = torch.tensor([idx2.numel()], dtype=torch.int32, device=cuda_device)
+    inp = N.frames_input(frames_tensor(words, cuda_device), w, h, 1)
+    got = stage.forward(inp, idx2.numel(), idx=idx_dev, n_dev=n_dev).cpu().numpy()
+    ref = O.stage_logits("stage2", sds["stage2"], images[idx2]).numpy()
+    err = float(np.abs(got - ref).max())
+    assert got.shape == ref.shape and err <= 5e-3, err
+    assert (got.argmax(1) == ref.argmax(1)).mean() >= 0.999
