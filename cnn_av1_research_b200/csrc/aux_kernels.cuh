@@ -81,10 +81,47 @@ __global__ void __launch_bounds__(256) sam_gate_kernel(const __half* __restrict_
 // channel group l % (C/8) at NPOS*C/256 positions, so every global access is a 16-byte vector and a
 // warp touches 512 contiguous bytes per instruction.  Used for se1..se3 (C = 64, 128, 256); se4's
 // 2 x 64 KB of weights do not fit this scheme and stay on the tensor-core path.
-template <int C, int NPOS>
+// Sum the H per-lane partial vectors of a warp (reduce-scatter butterfly), apply ReLU and broadcast: hid[j] in every lane.
+template <int H>
+__device__ __forceinline__ void se_hidden(float (&part)[H], float (&hid)[H], int lane) {
+  // after the step with offset o, a lane keeps the units whose index bit matches its lane bit
+  constexpr int STEPS = H == 16 ? 4 : (H == 8 ? 3 : (H == 4 ? 2 : 1));
+#pragma unroll
+  for (int st = 0; st < 5; ++st) {
+    const int o = 16 >> st;
+    if (st < STEPS) {
+      const int half_w = H >> (st + 1);
+      const bool upper = (lane & o) != 0;
+#pragma unroll
+      for (int j = 0; j < H / 2; ++j) {
+        if (j < half_w) {
+          const float keep = upper ? part[j + half_w] : part[j];
+          const float send = upper ? part[j] : part[j + half_w];
+          part[j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+      }
+    } else {
+      part[0] += __shfl_xor_sync(0xffffffffu, part[0], o);
+    }
+  }
+  const float mine = fmaxf(part[0], 0.f);
+  // unit j lives in the lane whose first STEPS bits (16, 8, ...) spell j, other bits zero
+#pragma unroll
+  for (int j = 0; j < H; ++j) {
+    int src_lane = 0;
+#pragma unroll
+    for (int st = 0; st < STEPS; ++st)
+      if (j & (H >> (st + 1))) src_lane |= 16 >> st;
+    hid[j] = __shfl_sync(0xffffffffu, mine, src_lane);
+  }
+}
+
+template <int C, int NPOS, int R>
 __global__ void __launch_bounds__(256) se_kernel(const __half* __restrict__ x, const __half* __restrict__ x_lo,
                                                  __half* __restrict__ out, __half* __restrict__ out_lo,
                                                  const int* n_dev, int n, const float* __restrict__ w /*[2][H][C]*/) {
+  // R = block rows a warp processes together: every shared-memory weight word is loaded once per R rows (the C = 256
+  // instance was bound by its weight LDS wavefronts, not by HBM).
   constexpr int H = C / 16;
   constexpr int L = C * NPOS;
   constexpr int GROUPS = C / 8;           // channel groups of 8
@@ -104,128 +141,107 @@ __global__ void __launch_bounds__(256) se_kernel(const __half* __restrict__ x, c
   const int rows = n_dev ? *n_dev : n;
   const int lane = threadIdx.x & 31;
   const int warps_per_grid = (gridDim.x * blockDim.x) >> 5;
-  for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < rows; r += warps_per_grid) {
-    float v[CPL][8];
-    float mean[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int r0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * R; r0 < rows; r0 += warps_per_grid * R) {
+    float v[R][CPL][8];
+    float mean[R][8];
 #pragma unroll
-    for (int i = 0; i < CPL; ++i) {
-      const size_t off = act_off(r, (lane + 32 * i) * 8, L / 64);
-      const uint4 q = __ldg(reinterpret_cast<const uint4*>(x + off));
-      const __half2* h = reinterpret_cast<const __half2*>(&q);
+    for (int q = 0; q < R; ++q) {
+      const int r = r0 + q;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float2 f = __half22float2(h[k]);
-        v[i][2 * k] = f.x;
-        v[i][2 * k + 1] = f.y;
-      }
-      if (x_lo) {
-        const uint4 ql = __ldg(reinterpret_cast<const uint4*>(x_lo + off));
-        const __half2* hl = reinterpret_cast<const __half2*>(&ql);
+      for (int k = 0; k < 8; ++k) mean[q][k] = 0.f;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float2 f = __half22float2(hl[k]);
-          v[i][2 * k] += f.x;
-          v[i][2 * k + 1] += f.y;
-        }
-      }
+      for (int i = 0; i < CPL; ++i) {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) mean[k] += v[i][k];
-    }
-    // finish the spatial mean across the lanes that hold the same channel group
+        for (int k = 0; k < 8; ++k) v[q][i][k] = 0.f;
+        if (r < rows) {
+          const size_t off = act_off(r, (lane + 32 * i) * 8, L / 64);
+          const uint4 qh = __ldg(reinterpret_cast<const uint4*>(x + off));
+          const __half2* h = reinterpret_cast<const __half2*>(&qh);
 #pragma unroll
-    for (int o = GROUPS; o < 32; o <<= 1)
-#pragma unroll
-      for (int k = 0; k < 8; ++k) mean[k] += __shfl_xor_sync(0xffffffffu, mean[k], o);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) mean[k] *= (1.0f / NPOS);
-    // hidden = relu(W1 . mean): one leader lane per channel group contributes a partial for every hidden
-    // unit; the H partial vectors are summed with a reduce-scatter butterfly (H + H/2 + ... shuffles instead
-    // of 5 per unit) and broadcast back.
-    float part[H];
-#pragma unroll
-    for (int j = 0; j < H; ++j) {
-      float pj = 0.f;
-      if (lane < GROUPS) {
-        const float4 a = *reinterpret_cast<const float4*>(w1 + j * C + wg);
-        const float4 b = *reinterpret_cast<const float4*>(w1 + j * C + C / 2 + wg);
-        pj = mean[0] * a.x + mean[1] * a.y + mean[2] * a.z + mean[3] * a.w + mean[4] * b.x + mean[5] * b.y + mean[6] * b.z +
-             mean[7] * b.w;
-      }
-      part[j] = pj;
-    }
-    float hid[H];
-    {
-      // after the step with offset o, lane keeps the units whose index bit (log2 of the step count) matches its bit
-      int width = H;
-#pragma unroll
-      for (int o = 16; o >= 1; o >>= 1) {
-        if (width > 1) {
-          const int half_w = width / 2;
-          const bool upper = (lane & o) != 0;
-#pragma unroll
-          for (int j = 0; j < half_w; ++j) {
-            const float keep = upper ? part[j + half_w] : part[j];
-            const float send = upper ? part[j] : part[j + half_w];
-            part[j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+          for (int k = 0; k < 4; ++k) {
+            const float2 f = __half22float2(h[k]);
+            v[q][i][2 * k] = f.x;
+            v[q][i][2 * k + 1] = f.y;
           }
-          width = half_w;
-        } else {
-          part[0] += __shfl_xor_sync(0xffffffffu, part[0], o);
-        }
-      }
-      // lane now holds the total of unit u(lane) = sum over the first log2(H) steps of bit(lane, o) * (H >> step)
-      int unit = 0, w2 = H;
+          if (x_lo) {
+            const uint4 ql = __ldg(reinterpret_cast<const uint4*>(x_lo + off));
+            const __half2* hl = reinterpret_cast<const __half2*>(&ql);
 #pragma unroll
-      for (int o = 16; o >= 1; o >>= 1) {
-        if (w2 > 1) {
-          w2 /= 2;
-          if (lane & o) unit += w2;
-        }
-      }
-      const float mine = fmaxf(part[0], 0.f);
-      // unit j lives in the lane whose selected bits spell j (other bits zero)
-#pragma unroll
-      for (int j = 0; j < H; ++j) {
-        int src_lane = 0, w3 = H, jj = j;
-#pragma unroll
-        for (int o = 16; o >= 1; o >>= 1) {
-          if (w3 > 1) {
-            w3 /= 2;
-            if (jj >= w3) {
-              src_lane |= o;
-              jj -= w3;
+            for (int k = 0; k < 4; ++k) {
+              const float2 f = __half22float2(hl[k]);
+              v[q][i][2 * k] += f.x;
+              v[q][i][2 * k + 1] += f.y;
             }
           }
         }
-        hid[j] = __shfl_sync(0xffffffffu, mine, src_lane);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) mean[q][k] += v[q][i][k];
       }
-      (void)unit;
+      // finish the spatial mean across the lanes that hold the same channel group
+#pragma unroll
+      for (int o = GROUPS; o < 32; o <<= 1)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) mean[q][k] += __shfl_xor_sync(0xffffffffu, mean[q][k], o);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) mean[q][k] *= (1.0f / NPOS);
     }
-    float sc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    // hidden = relu(W1 . mean): one leader lane per channel group contributes a partial for every hidden unit; per
+    // row the H partial vectors are summed with a reduce-scatter butterfly (H + H/2 + ... shuffles instead of 5 per
+    // unit) and broadcast back.
+    float part[R][H];
+#pragma unroll
+    for (int j = 0; j < H; ++j) {
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+      if (lane < GROUPS) {
+        a = *reinterpret_cast<const float4*>(w1 + j * C + wg);
+        b = *reinterpret_cast<const float4*>(w1 + j * C + C / 2 + wg);
+      }
+#pragma unroll
+      for (int q = 0; q < R; ++q)
+        part[q][j] = mean[q][0] * a.x + mean[q][1] * a.y + mean[q][2] * a.z + mean[q][3] * a.w + mean[q][4] * b.x +
+                     mean[q][5] * b.y + mean[q][6] * b.z + mean[q][7] * b.w;
+    }
+    float hid[R][H];
+#pragma unroll
+    for (int q = 0; q < R; ++q) se_hidden<H>(part[q], hid[q], lane);
+    float sc[R][8];
+#pragma unroll
+    for (int q = 0; q < R; ++q)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) sc[q][k] = 0.f;
 #pragma unroll
     for (int j = 0; j < H; ++j) {
       const float4 a = *reinterpret_cast<const float4*>(w2t + j * C + wg);
       const float4 b = *reinterpret_cast<const float4*>(w2t + j * C + C / 2 + wg);
-      sc[0] = fmaf(a.x, hid[j], sc[0]); sc[1] = fmaf(a.y, hid[j], sc[1]);
-      sc[2] = fmaf(a.z, hid[j], sc[2]); sc[3] = fmaf(a.w, hid[j], sc[3]);
-      sc[4] = fmaf(b.x, hid[j], sc[4]); sc[5] = fmaf(b.y, hid[j], sc[5]);
-      sc[6] = fmaf(b.z, hid[j], sc[6]); sc[7] = fmaf(b.w, hid[j], sc[7]);
+#pragma unroll
+      for (int q = 0; q < R; ++q) {
+        const float hj = hid[q][j];
+        sc[q][0] = fmaf(a.x, hj, sc[q][0]); sc[q][1] = fmaf(a.y, hj, sc[q][1]);
+        sc[q][2] = fmaf(a.z, hj, sc[q][2]); sc[q][3] = fmaf(a.w, hj, sc[q][3]);
+        sc[q][4] = fmaf(b.x, hj, sc[q][4]); sc[q][5] = fmaf(b.y, hj, sc[q][5]);
+        sc[q][6] = fmaf(b.z, hj, sc[q][6]); sc[q][7] = fmaf(b.w, hj, sc[q][7]);
+      }
     }
 #pragma unroll
-    for (int k = 0; k < 8; ++k) sc[k] = 1.0f / (1.0f + expf(-sc[k]));
+    for (int q = 0; q < R; ++q) {
+      const int r = r0 + q;
+      if (r >= rows) continue;
 #pragma unroll
-    for (int i = 0; i < CPL; ++i) {
-      const size_t off = act_off(r, (lane + 32 * i) * 8, L / 64);
-      __align__(16) __half2 hi[4], lo[4];
+      for (int k = 0; k < 8; ++k) sc[q][k] = 1.0f / (1.0f + expf(-sc[q][k]));
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float a = v[i][2 * k] * sc[2 * k], b = v[i][2 * k + 1] * sc[2 * k + 1];
-        hi[k] = __floats2half2_rn(a, b);
-        const float2 hf = __half22float2(hi[k]);
-        lo[k] = __floats2half2_rn(a - hf.x, b - hf.y);
+      for (int i = 0; i < CPL; ++i) {
+        const size_t off = act_off(r, (lane + 32 * i) * 8, L / 64);
+        __align__(16) __half2 hi[4], lo[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float a = v[q][i][2 * k] * sc[q][2 * k], b = v[q][i][2 * k + 1] * sc[q][2 * k + 1];
+          hi[k] = __floats2half2_rn(a, b);
+          const float2 hf = __half22float2(hi[k]);
+          lo[k] = __floats2half2_rn(a - hf.x, b - hf.y);
+        }
+        *reinterpret_cast<uint4*>(out + off) = *reinterpret_cast<const uint4*>(hi);
+        if (out_lo) *reinterpret_cast<uint4*>(out_lo + off) = *reinterpret_cast<const uint4*>(lo);
       }
-      *reinterpret_cast<uint4*>(out + off) = *reinterpret_cast<const uint4*>(hi);
-      if (out_lo) *reinterpret_cast<uint4*>(out_lo + off) = *reinterpret_cast<const uint4*>(lo);
     }
   }
 }

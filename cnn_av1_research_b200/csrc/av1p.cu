@@ -602,15 +602,16 @@ int run_stage(av1p_stage* s, const StemInput& si, const int32_t* idx, const int3
         break;
       }
       case AV1P_OP_SE: {
-        const int grid = std::min(ceil_div(n, 8), g_ctx.sms * 8);
         ProfScope ps(PROF_SE, st);
         const size_t smem = size_t(2) * (P.se_c / 16) * P.se_c * sizeof(float);
+        // rows per warp iteration (template R): sharing one pass over the shared-memory weights between two rows measured
+        // slower (fewer warps in flight), so every shape runs with R = 1
         if (P.se_c == 64)
-          se_kernel<64, 16><<<grid, 256, smem, st>>>(P.src, P.src_lo, P.dst, P.dst_lo, n_dev, n, P.w);
+          se_kernel<64, 16, 1><<<std::min(ceil_div(n, 8), g_ctx.sms * 8), 256, smem, st>>>(P.src, P.src_lo, P.dst, P.dst_lo, n_dev, n, P.w);
         else if (P.se_c == 128)
-          se_kernel<128, 4><<<grid, 256, smem, st>>>(P.src, P.src_lo, P.dst, P.dst_lo, n_dev, n, P.w);
+          se_kernel<128, 4, 1><<<std::min(ceil_div(n, 8), g_ctx.sms * 8), 256, smem, st>>>(P.src, P.src_lo, P.dst, P.dst_lo, n_dev, n, P.w);
         else
-          se_kernel<256, 1><<<grid, 256, smem, st>>>(P.src, P.src_lo, P.dst, P.dst_lo, n_dev, n, P.w);
+          se_kernel<256, 1, 1><<<std::min(ceil_div(n, 8), g_ctx.sms * 8), 256, smem, st>>>(P.src, P.src_lo, P.dst, P.dst_lo, n_dev, n, P.w);
         break;
       }
       case AV1P_OP_FGVC_TAIL: {
