@@ -1,0 +1,132 @@
+"""Optional data-parallel Stage-1 training step (BASELINE.json configs[4]).
+
+Reference: pesquisa_v6/scripts/003_train_stage1_improved.py:57-82 (train_epoch body: zero_grad -> forward in train
+mode -> FocalLoss -> backward -> AdamW step), pesquisa_v6/v6_pipeline/losses.py:12-53 (FocalLoss, binary branch
+:29-38, alpha 0.25 / gamma 2.5 from 003:240), optimiser AdamW(lr 1e-3, weight_decay 1e-4) (003:250-254), batch 128
+per process (003:139).
+
+Scope.  The inference cascade is the product of this repository and runs on hand-written sm_100a kernels; training
+is NOT on that path.  This module exists so that the data-parallel configuration of the benchmark list can be run and
+measured: forward/backward are plain PyTorch ops (bf16 autocast on CUDA), written functionally over the SAME
+parameter tensors as the drop-in `Stage1Model` (identical state_dict keys, so a checkpoint trained here loads into
+the inference path and vice versa), and the only communication is ONE flat-bucket all-reduce of the 11,345,444
+gradients per step (NCCL over NVLink on GPUs, gloo in the CPU tests), followed by the identical AdamW update on every
+rank.  BatchNorm uses per-rank batch statistics (plain DDP semantics, as the single-GPU reference would with its own
+batch).
+"""
+from __future__ import annotations
+
+from typing import Dict, Iterable, Optional
+
+import torch
+import torch.distributed as dist
+import torch.nn.functional as F
+
+
+def focal_loss_binary(logits: torch.Tensor, targets: torch.Tensor, alpha: float = 0.25, gamma: float = 2.5) -> torch.Tensor:
+    """losses.py:29-38 + mean reduction (:48-49): logits [N,1], targets [N] in {0,1}."""
+    x = logits.float().squeeze(1)
+    t = targets.float()
+    bce = F.binary_cross_entropy_with_logits(x, t, reduction="none")
+    probs = torch.sigmoid(x)
+    pt = probs * t + (1 - probs) * (1 - t)
+    alpha_t = alpha * t + (1 - alpha) * (1 - t)
+    return (alpha_t * (1 - pt) ** gamma * bce).mean()
+
+
+def _bn(x, sd, name, training, momentum=0.1):
+    return F.batch_norm(x, sd[name + ".running_mean"], sd[name + ".running_var"], sd[name + ".weight"], sd[name + ".bias"],
+                        training=training, momentum=momentum, eps=1e-5)
+
+
+def _unit(x, sd, name, stride, training):
+    out = F.relu(_bn(F.conv2d(x, sd[name + ".conv1.weight"], None, stride=stride, padding=1), sd, name + ".bn1", training))
+    out = _bn(F.conv2d(out, sd[name + ".conv2.weight"], None, stride=1, padding=1), sd, name + ".bn2", training)
+    if (name + ".downsample.0.weight") in sd:
+        x = _bn(F.conv2d(x, sd[name + ".downsample.0.weight"], None, stride=stride), sd, name + ".downsample.1", training)
+    return F.relu(out + x)
+
+
+def stage1_forward_torch(sd: Dict[str, torch.Tensor], x: torch.Tensor, training: bool, dropout_p: float = 0.3) -> torch.Tensor:
+    """Stage1Model.forward (models.py:104-126, 136-149, 206-215) over a dict of tensors with the model's state_dict keys.
+    `training` selects batch statistics for BatchNorm (running stats are updated in place) and live Dropout."""
+    p = "backbone."
+    x = F.conv2d(x, sd[p + "conv1.weight"], None, stride=2, padding=3)
+    x = F.max_pool2d(F.relu(_bn(x, sd, p + "bn1", training)), kernel_size=3, stride=2, padding=1)
+    for layer, stride in ((1, 1), (2, 2), (3, 2), (4, 2)):
+        x = _unit(x, sd, f"{p}layer{layer}.0", stride, training)
+        x = _unit(x, sd, f"{p}layer{layer}.1", 1, training)
+        s = x.mean(dim=(2, 3))
+        s = torch.sigmoid(F.linear(F.relu(F.linear(s, sd[f"{p}se{layer}.excitation.0.weight"])), sd[f"{p}se{layer}.excitation.2.weight"]))
+        x = x * s[:, :, None, None]
+    att = torch.cat([x.mean(dim=1, keepdim=True), x.max(dim=1, keepdim=True).values], dim=1)
+    x = x * torch.sigmoid(F.conv2d(att, sd[p + "spatial_attn.conv.weight"], None, padding=3))
+    f = torch.flatten(F.adaptive_avg_pool2d(x, 1), 1)
+    h = F.relu(F.linear(f, sd["head.head.0.weight"], sd["head.head.0.bias"]))
+    h = F.dropout(h, dropout_p, training)
+    return F.linear(h, sd["head.head.3.weight"], sd["head.head.3.bias"])
+
+
+class Stage1DataParallelTrainer:
+    """One replica of the Stage-1 training step; all replicas stay bit-identical because they apply the same averaged
+    gradient with the same optimiser state."""
+
+    def __init__(self, model, device, lr: float = 1e-3, weight_decay: float = 1e-4, alpha: float = 0.25, gamma: float = 2.5,
+                 dropout_p: float = 0.3, autocast_bf16: Optional[bool] = None, group=None):
+        self.model = model.to(device)
+        self.device = torch.device(device)
+        self.group = group
+        self.alpha, self.gamma, self.dropout_p = alpha, gamma, dropout_p
+        self.autocast_bf16 = (self.device.type == "cuda") if autocast_bf16 is None else autocast_bf16
+        # parameters (trainable, the reference's AdamW covers model.parameters() incl. the unused temperature) + buffers
+        self.named_params = [(k, v) for k, v in model.named_parameters()]
+        self.sd = {k: v for k, v in model.named_parameters()}
+        self.sd.update({k: v for k, v in model.named_buffers()})
+        self.params = [v for _, v in self.named_params]
+        self.optimizer = torch.optim.AdamW(self.params, lr=lr, weight_decay=weight_decay)
+        n = sum(p.numel() for p in self.params)
+        self.flat_grad = torch.zeros(n, dtype=torch.float32, device=self.device)      # ONE bucket: 11,345,444 fp32 = 45.4 MB
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+
+    def forward(self, images: torch.Tensor, training: bool = True) -> torch.Tensor:
+        with torch.autocast(self.device.type, dtype=torch.bfloat16, enabled=self.autocast_bf16):
+            return stage1_forward_torch(self.sd, images, training, self.dropout_p)
+
+    def step(self, images: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+        """003:64-73 on this rank's batch, with the gradient averaged over the ranks.  Returns the local loss (detached)."""
+        self.optimizer.zero_grad(set_to_none=True)
+        logits = self.forward(images.to(self.device, non_blocking=True), training=True)
+        loss = focal_loss_binary(logits, labels.to(self.device, non_blocking=True), self.alpha, self.gamma)
+        loss.backward()
+        # flatten -> one all-reduce -> unflatten (parameters without a gradient, e.g. the unused temperature, contribute zeros)
+        off = 0
+        for p in self.params:
+            n = p.numel()
+            if p.grad is None:
+                self.flat_grad[off:off + n].zero_()
+            else:
+                self.flat_grad[off:off + n].copy_(p.grad.reshape(-1))
+            off += n
+        if self.world > 1:
+            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.group)
+            self.flat_grad.div_(self.world)
+        off = 0
+        for p in self.params:
+            n = p.numel()
+            if p.grad is not None:
+                p.grad.copy_(self.flat_grad[off:off + n].view_as(p.grad))
+            off += n
+        self.optimizer.step()
+        return loss.detach()
+
+    def allreduce_bytes(self) -> int:
+        return self.flat_grad.numel() * self.flat_grad.element_size()
+
+
+def synthetic_labelled_blocks(n: int, seed: int, positive_rate: float = 0.42, device=None):
+    """Synthetic training batch: uniform 10-bit blocks / 1023 and Bernoulli(0.42) stage-1 labels (the validation set's
+    PARTITION share is 42.14 %, pesquisa_v6/docs_v6/05_avaliacao_pipeline_completo.md:140)."""
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randint(0, 1024, (n, 1, 16, 16), generator=g).float() / 1023.0
+    y = (torch.rand(n, generator=g) < positive_rate).long()
+    return (x.to(device), y.to(device)) if device is not None else (x, y)

@@ -1,0 +1,78 @@
+"""Stage-1 data-parallel training step benchmark (BASELINE.json configs[4]) - NOT the headline metric (bench.py is).
+
+    python tools/bench_train.py [--steps K] [--warmup W] [--batch 128]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P tools/bench_train.py --gpus N
+
+One process per GPU, NCCL; per-GPU batch 128 (reference default, 003:139) of synthetic labelled blocks, bf16 autocast
+forward/backward in PyTorch, ONE flat all-reduce of the 11,345,444 fp32 gradients per step, AdamW.  Weak scaling;
+CUDA-event time, max over ranks.  Prints one JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--batch", type=int, default=128)
+    args = ap.parse_args()
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from cnn_av1_research_b200 import synth
+    from cnn_av1_research_b200.models import Stage1Model
+    from cnn_av1_research_b200.training import Stage1DataParallelTrainer, synthetic_labelled_blocks
+    model = Stage1Model(pretrained=False)
+    model.load_state_dict(synth.calibrated_state_dict("stage1", 0), strict=True)
+    tr = Stage1DataParallelTrainer(model, dev)
+    batches = [synthetic_labelled_blocks(args.batch, 1000 * rank + i, device=dev) for i in range(4)]
+    for i in range(args.warmup):
+        tr.step(*batches[i % 4])
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        loss = tr.step(*batches[i % 4])
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    # replicas must still be identical
+    flat = torch.cat([p.detach().reshape(-1) for p in tr.params])
+    same = True
+    if world > 1:
+        ref = flat.clone()
+        dist.broadcast(ref, src=0)
+        ok = torch.tensor([int(torch.equal(ref, flat))], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        same = bool(ok.item())
+    if rank == 0:
+        print(json.dumps({"metric": "stage1_dp_training_samples_per_sec", "value": args.batch * world / (ms.item() * 1e-3), "unit": "samples/s",
+                          "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms.item(), "scaling": "weak",
+                          "dtype": "bf16 autocast (PyTorch fwd/bwd), fp32 gradient all-reduce", "data": "synthetic",
+                          "config": {"workload": "Stage1 data-parallel training step (BASELINE configs[4])", "per_gpu_batch": args.batch,
+                                     "allreduce_bytes_per_step": tr.allreduce_bytes(), "optimizer": "AdamW lr 1e-3 wd 1e-4",
+                                     "loss": "FocalLoss alpha 0.25 gamma 2.5"},
+                          "replicas_identical": same, "final_loss": float(loss)}), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
