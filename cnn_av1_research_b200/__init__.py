@@ -2,6 +2,8 @@
 chiarorosa/cnn-av1-research).  See DESIGN.md and INTEGRATION.md at the repository root."""
 from .extraction import (BlockRecord, TorchBlockRecord, calculate_yuv420_10bit_sizes, extract_blocks_device,
                          extract_blocks_with_validation)
+from .fileio import (load_block_file, predict_yuv_file, read_frames_yuv420p10, read_y_component_10bit_lossless,
+                     save_blocks_binary_10bit)
 from .flatten import (FlattenPipeline, evaluate_with_threshold, remap_flatten_to_original, run_pipeline_inference,
                       sweep_thresholds)
 from .models import (CosineClassifier, FGVCModel, ImprovedBackbone, SEBlock, SpatialAttention, Stage1BinaryHead,
@@ -15,5 +17,6 @@ __all__ = [
     "SpatialAttention", "Stage1BinaryHead", "Stage1Model", "Stage2Model", "Stage2ThreeWayHead", "Stage3ABHead",
     "Stage3ABModel", "Stage3RectHead", "Stage3RectModel", "HierarchicalPipelineV6", "evaluate_pipeline",
     "Stage2FlatModel", "FlattenPipeline", "run_pipeline_inference", "remap_flatten_to_original",
-    "evaluate_with_threshold", "sweep_thresholds",
+    "evaluate_with_threshold", "sweep_thresholds", "read_y_component_10bit_lossless", "read_frames_yuv420p10",
+    "predict_yuv_file", "save_blocks_binary_10bit", "load_block_file",
 ]
