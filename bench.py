@@ -33,7 +33,7 @@ sys.path.insert(0, ROOT)
 
 W4K, H4K = 3840, 2160
 BPF = (W4K // 16) * (H4K // 16)            # 32,400 blocks per 4K frame
-SUB = 8                                    # frames per cascade launch
+SUB = 16                                   # frames per cascade launch
 THRESHOLD = 0.45                           # 008 CLI default (:187)
 # Live (non-padding) conv+linear FLOPs per block, SURVEY.md section 8(d) / BASELINE.md section 2
 F_LIVE = {"stage1": 8.813e6, "stage2": 8.878e6, "rect": 8.698e6, "ab_fgvc": 9.603e6}

@@ -259,6 +259,28 @@ extern "C" int av1p_profile_end(float* ms_by_class, int32_t* launches_by_class) 
   return AV1P_OK;
 }
 
+// Per-launch variant: device time and class of every bracketed launch in issue order (tools/profile_ops.py pairs them
+// with the packed op names).  Writes at most `cap` entries, *n_out = number of launches recorded.
+extern "C" int av1p_profile_end_launches(float* ms, int32_t* cls, int32_t cap, int32_t* n_out) {
+  g_prof.on = false;
+  int n = 0;
+  for (ProfRec& r : g_prof.recs) {
+    CUDA_TRY(cudaEventSynchronize(r.b));
+    float t = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&t, r.a, r.b));
+    if (n < cap) {
+      if (ms) ms[n] = t;
+      if (cls) cls[n] = r.cls;
+    }
+    ++n;
+    g_prof.pool.push_back(r.a);
+    g_prof.pool.push_back(r.b);
+  }
+  g_prof.recs.clear();
+  if (n_out) *n_out = n;
+  return AV1P_OK;
+}
+
 // Strided host->device copy of the luma planes only (2/3 of a 4:2:0 frame): one cudaMemcpy2DAsync.
 extern "C" int av1p_upload_luma(const uint16_t* frames_host, int32_t n_frames, int32_t width, int32_t height,
                                 int64_t frame_stride, uint16_t* luma_dev, void* stream) {
@@ -459,6 +481,12 @@ int plan_stage(const av1p_model* m, const ActLayout& L, uint8_t* act_base, av1p_
           if (int rc = make_act_map(&f.out_map[0], buf(op.out), L.cols[op.out], L.cap, true)) return rc;
           if (op.out_lo >= 0)
             if (int rc = make_act_map(&f.out_map[1], buf(op.out_lo), L.cols[op.out_lo], L.cap, true)) return rc;
+        }
+        if (op.epi == FC_EPI_GATE) {
+          if (op.n_tiles * op.block_n > int(L.cols[op.aux])) return fail(AV1P_EINVAL, "gate input narrower than the FC output");
+          if (int rc = make_act_map(&f.aux_map[0], buf(op.aux), L.cols[op.aux], L.cap, true)) return rc;
+          if (op.aux_lo >= 0)
+            if (int rc = make_act_map(&f.aux_map[1], buf(op.aux_lo), L.cols[op.aux_lo], L.cap, true)) return rc;
         }
         if (op.epi == FC_EPI_ADD_RELU) {
           if (op.n_tiles * op.block_n > int(L.cols[op.aux])) return fail(AV1P_EINVAL, "residual narrower than the FC output");
@@ -1077,6 +1105,12 @@ extern "C" int av1p_fc_forward(const av1p_fc_desc* d, void* stream) {
     if (int rc = make_act_map(&f.out_map[0], d->out_dev, uint64_t(d->out_ld), uint64_t(d->rows), true)) return rc;
     if (d->out_lo_dev)
       if (int rc = make_act_map(&f.out_map[1], d->out_lo_dev, uint64_t(d->out_ld), uint64_t(d->rows), true)) return rc;
+  }
+  if (d->epi == FC_EPI_GATE) {
+    if (!d->aux_dev || d->aux_ld < d->n_tiles * d->block_n) return fail(AV1P_EINVAL, "gate input missing or too narrow");
+    if (int rc = make_act_map(&f.aux_map[0], d->aux_dev, uint64_t(d->aux_ld), uint64_t(d->rows), true)) return rc;
+    if (d->aux_lo_dev)
+      if (int rc = make_act_map(&f.aux_map[1], d->aux_lo_dev, uint64_t(d->aux_ld), uint64_t(d->rows), true)) return rc;
   }
   if (d->epi == FC_EPI_ADD_RELU) {
     if (!d->aux_dev || d->aux_ld < d->n_tiles * d->block_n) return fail(AV1P_EINVAL, "residual missing or too narrow");

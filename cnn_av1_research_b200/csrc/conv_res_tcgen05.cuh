@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_res_tcgen05_kernel(const _
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
       mbar_init(&acc_empty[s], FC_EPI_WARPS);
-      mbar_init(&stg_full[s], FC_EPI_WARPS);
+      mbar_init(&stg_full[s], FC_EPI_WARPS / 2);
       mbar_init(&stg_free[s], 1);
     }
     mbar_init(w_bar, 1);
@@ -347,7 +347,8 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_res_tcgen05_kernel(const _
     uint32_t g = 0;
     for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x) {
       if ((mt + 1) * FC_TILE_M > n_rows || (p.debug & 18)) continue;
-      epi_store_chunks(es, g, &p.out_map[0], &p.out_map[1], p.out_lo != nullptr, 0, 1024 / EPI_CHUNK, mt, 16, p.err_flag);
+      epi_store_chunks(es, g, &p.out_map[0], &p.out_map[1], p.out_lo != nullptr, 0, 1024 / EPI_CHUNK, mt, 16, p.err_flag,
+                       uint32_t(warp - FC_STORE_WARP));
     }
     epi_store_drain();
   }

@@ -12,7 +12,7 @@
 //   warp 0      TMA producer : A tile [128 rows x 64 K] + W tile [block_n x 64 K] per K block
 //   warp 1      MMA issuer   : 4 x tcgen05.mma (M128, N=block_n, K16) per K block, fp32 acc in TMEM
 //   warps 2..17 epilogue     : tcgen05.ld -> bias / ReLU / gate -> fp16 hi/lo -> swizzled smem staging tile
-//   warp 18     store        : one TMA bulk store per staged [128 rows x 32 cols] tile (hi and lo planes)
+//   warps 18,19 store        : one TMA bulk store per staged [128 rows x 32 cols] tile (hi and lo planes), one warp per set
 // with a 4-deep smem ring (full/empty mbarriers), a 2-deep TMEM accumulator ring and a hi/lo pair of
 // staging tiles (full/free mbarriers).
 //
@@ -47,7 +47,8 @@ constexpr int FC_MAX_KB = 128;         // scheduled K blocks per layer (sum over
 constexpr int FC_MAX_SRC = 4;          // activation sources per layer
 constexpr int FC_TAIL_MAX = 8;         // outputs of the in-epilogue final linear (7 for the flatten head)
 constexpr int FC_EPI_WARPS = 16;         // four per TMEM lane quadrant: 8 of every 32 staged columns each
-constexpr int FC_THREADS = 64 + 32 * FC_EPI_WARPS + 32;      // producer, MMA, epilogue, store
+constexpr int FC_STORE_WARPS = 2;                            // one per staging set
+constexpr int FC_THREADS = 64 + 32 * FC_EPI_WARPS + 32 * FC_STORE_WARPS;   // producer, MMA, epilogue, store
 constexpr int FC_STORE_WARP = 2 + FC_EPI_WARPS;
 constexpr int EPI_CHUNK = 32;                                // output columns per staging tile
 constexpr int EPI_UNIT_BYTES = FC_TILE_M * EPI_CHUNK * 2;    // 8 KB: [128 rows][64 B], SWIZZLE_64B
@@ -55,6 +56,18 @@ constexpr int EPI_IDENT_BYTES = 512;                         // 16 x 16 fp16 sca
 constexpr int EPI_SETS = 2;                                  // staging is double buffered: chunk g uses set g & 1
 constexpr int EPI_STAGING_BYTES = EPI_SETS * 2 * EPI_UNIT_BYTES;   // {hi, lo} x 2 sets = 32 KB
 constexpr int FC_OFF_STAGING = FC_STAGES * FC_STAGE_BYTES;
+// Gate layers (FC_EPI_GATE: out = aux * sigmoid(acc), the SE excitation) have one tiny K block per item, so they run on a
+// shortened operand ring and the upper part of the ring area becomes a ring of AUX tiles: the [128 rows x 32 cols]
+// hi / lo pieces of the gate input the epilogue multiplies with, loaded by the producer warp with TMA in the staging
+// tiles' SWIZZLE_64B layout.  (Reading aux straight from global touched 32 cache lines per load instruction - one per
+// accumulator row - and made se4.fc2 the slowest FC layer at 5 % tensor activity.)
+constexpr int GATE_AUX_SETS = 4;
+constexpr int GATE_AUX_SET_BYTES = 2 * EPI_UNIT_BYTES;       // hi + lo tile
+constexpr int FC_OFF_GATE_AUX = 128 * 1024;
+constexpr int FC_GATE_STAGES = 2;                            // 2 x 48 KB (single CTA) ...
+constexpr int FC2_GATE_STAGES = 4;                           // ... 4 x 32 KB (CTA pair) stay below FC_OFF_GATE_AUX
+static_assert(FC_GATE_STAGES * FC_STAGE_BYTES <= FC_OFF_GATE_AUX && FC2_GATE_STAGES * FC2_STAGE_BYTES <= FC_OFF_GATE_AUX &&
+              FC_OFF_GATE_AUX + GATE_AUX_SETS * GATE_AUX_SET_BYTES <= FC_OFF_STAGING, "gate aux ring must fit the ring area");
 constexpr int FC_OFF_TAIL = FC_OFF_STAGING;                  // head layers store nothing: their tail weights reuse the staging area
 constexpr int FC_OFF_IDENT = FC_OFF_STAGING + EPI_STAGING_BYTES;
 constexpr int FC_OFF_BARS = FC_OFF_IDENT + EPI_IDENT_BYTES;
@@ -80,6 +93,7 @@ struct FcParams {
   CUtensorMap w_map;           // packed weights, 2-D [n_kb_total*block_n][64] fp16, box {64, block_n}
   CUtensorMap w_half_map;      // same tensor, box {64, block_n / 2} (CTA-pair variant)
   CUtensorMap out_map[2];      // output hi / lo planes (tiled layout): 2-D [rows*KB][64] fp16, box {32, 128}, SWIZZLE_64B
+  CUtensorMap aux_map[2];      // FC_EPI_GATE: gate input hi / lo planes, same box as out_map (loaded, not stored)
   int src_kb[FC_MAX_SRC];      // 64-column blocks per row of each source buffer
   const int* n_rows_dev;       // device-side row count (nullptr -> n_rows)
   int n_rows;
@@ -112,11 +126,11 @@ __device__ __forceinline__ float fast_sigmoid(float x) { return 1.0f / (1.0f + e
 // ------------------------------------------------------------------------------------------------
 // Epilogue staging: two sets of two [128 rows x 32 cols] fp16 tiles (hi plane, lo plane) in the SWIZZLE_64B layout
 // a TMA store expects; chunk g of a CTA's output stream uses set g & 1.
-//   full[s] : 16 epilogue warps -> store warp ("both tiles of set s are written and fenced")
+//   full[s] : the 8 epilogue warps of group s -> store warp s ("both tiles of set s are written and fenced")
 //   free_[s]: store warp -> epilogue warps ("the bulk stores have finished reading set s")
 struct EpiStage {
   uint8_t* staging;  // [EPI_SETS][2 planes][EPI_UNIT_BYTES]
-  uint64_t* full;    // [EPI_SETS], count FC_EPI_WARPS
+  uint64_t* full;    // [EPI_SETS], count FC_EPI_WARPS / 2
   uint64_t* free_;   // [EPI_SETS], count 1
   __device__ __forceinline__ uint8_t* unit(uint32_t set, int plane) const {
     return staging + (set * 2u + uint32_t(plane)) * EPI_UNIT_BYTES;
@@ -134,6 +148,20 @@ __device__ __forceinline__ void stage_store8(uint8_t* unit, int r_local, int par
   *reinterpret_cast<uint4*>(unit + r_local * (EPI_CHUNK * 2) + ((part ^ sw) << 4)) = a;
 }
 
+__device__ __forceinline__ uint4 stage_load8(const uint8_t* unit, int r_local, int part) {
+  const int sw = (r_local >> 1) & 3;
+  return *reinterpret_cast<const uint4*>(unit + r_local * (EPI_CHUNK * 2) + ((part ^ sw) << 4));
+}
+
+// Gate input ring (FC_EPI_GATE): set ga % GATE_AUX_SETS holds the hi (+ lo) aux tile of the ga-th output chunk of this CTA.
+//   full[s] : TMA transaction barrier (producer warp posts the expectation);  empty[s]: the 16 epilogue warps hand it back
+struct GateAux {
+  const uint8_t* tiles;
+  uint64_t* full;
+  uint64_t* empty;
+  uint32_t ga;
+};
+
 // 16 x 16 identity scaled by `s` in the no-swizzle K-major core-matrix layout (LBO 128 B, SBO 256 B)
 __device__ __forceinline__ void write_ident_tile(uint8_t* ident, float s, int tid, int nthreads) {
   for (int i = tid; i < EPI_IDENT_BYTES / 2; i += nthreads) {
@@ -145,28 +173,30 @@ __device__ __forceinline__ void write_ident_tile(uint8_t* ident, float s, int ti
 }
 __device__ __forceinline__ uint64_t ident_desc(uint32_t ident_addr) { return umma_desc_nosw(ident_addr, 128, 256); }
 
-// Store warp: drain `n_chunks` staged chunks of one accumulator (columns col0 .., rows row0 ..).  The whole warp
-// walks the loop; the bulk stores, their commit groups and the read-completion waits are all issued by lane 0
-// (bulk async-groups are per-thread state, so one fixed lane must own them).  One commit group per chunk; after
-// chunk g is issued the previous group's smem reads are awaited and its set handed back, so the TMA read of one
-// set overlaps the epilogue writing the other.
+// Store warps: drain `n_chunks` staged chunks of one accumulator (columns col0 .., rows row0 ..).  There is one store
+// warp per staging set (`my_set`); each walks the whole chunk sequence and handles the chunks that land in its set:
+// wait until the 16 epilogue warps have filled it, issue the bulk stores (lane 0: bulk async-groups are per-thread
+// state, so one fixed lane owns them), wait until the TMA engine has READ the tiles and hand the set straight back.
+// A set therefore returns to the epilogue as soon as its own stores have left shared memory, independently of the
+// other set's progress.  (With a single store warp the hand-back of set s waited for the NEXT chunk to be staged and
+// issued - wait_group.read cannot be polled - which serialised epilogue and stores at ~1.3 us per chunk, the pace of
+// every store-heavy layer.)
 __device__ __forceinline__ void epi_store_chunks(const EpiStage& es, uint32_t& g, const CUtensorMap* map_hi,
                                                  const CUtensorMap* map_lo, bool has_lo, int col0, int n_chunks, int mt,
-                                                 int out_kb, int* err_flag) {
+                                                 int out_kb, int* err_flag, uint32_t my_set) {
   const bool leader = (threadIdx.x & 31) == 0;
   for (int c = 0; c < n_chunks; ++c, ++g) {
     const uint32_t set = g & 1u;
-    mbar_wait(&es.full[set], (g >> 1) & 1u, err_flag, 900);
+    if (set != my_set) continue;
+    mbar_wait(&es.full[set], (g >> 1) & 1u, err_flag, 900 + int(set));
     if (leader) {
       const int col = col0 + c * EPI_CHUNK;
       const int trow = (mt * out_kb + (col >> 6)) * FC_TILE_M;      // tiled layout: tile (mt, col / 64)
       tma_store_2d(map_hi, es.unit(set, 0), col & 63, trow);
       if (has_lo) tma_store_2d(map_lo, es.unit(set, 1), col & 63, trow);
       tma_store_commit();
-      if (g > 0) {
-        tma_store_wait_read<1>();               // every group but the one just committed has been read
-        mbar_arrive(&es.free_[set ^ 1u]);
-      }
+      tma_store_wait_read<0>();
+      mbar_arrive(&es.free_[set]);
     }
     __syncwarp();
   }
@@ -197,27 +227,26 @@ __device__ __forceinline__ int epi_debug(const P& p) {
 template <typename P>
 __device__ __forceinline__ void epi_tile_store(const P& p, const EpiStage& es, uint32_t& g, int n_rows, int mt, int col0,
                                                int block_n, uint32_t t_col, uint64_t* full, uint32_t full_phase,
-                                               uint64_t* empty, int warp, int lane, int tag, uint32_t empty_remote = 0u) {
+                                               uint64_t* empty, int warp, int lane, int tag, uint32_t empty_remote = 0u,
+                                               GateAux* gx = nullptr) {
+  // The 16 epilogue warps form two groups of eight (two warps per TMEM lane quadrant).  Group k owns staging set k and
+  // handles the chunks whose running index has parity k, 16 columns per thread (two 8-column halves), so two chunks are
+  // in flight per CTA and a group only ever synchronises with its own store warp.  (All 16 warps sharing every
+  // 32-column chunk left each warp 8 columns of work per barrier round trip: ~1.3 us per chunk, latency-bound.)
   const int quad = warp & 3;              // TMEM lane quadrant this warp may read
-  const int part = (warp - 2) >> 2;       // which 8 columns of every 32-column chunk
+  const uint32_t grp = uint32_t(warp - 2) >> 3;
+  const int sub = ((warp - 2) >> 2) & 1;  // which 16 columns of the chunk
   const int r_local = quad * 32 + lane;
   const int row = mt * FC_TILE_M + r_local;
   const bool row_ok = row < n_rows;
   const bool skip_out = (epi_debug(p) & 2) != 0;
   const bool staged = (mt + 1) * FC_TILE_M <= n_rows && !skip_out;
-  const bool gate = p.epi == FC_EPI_GATE;
+  const bool gate = p.epi == FC_EPI_GATE && gx != nullptr;
   const bool relu = p.epi == FC_EPI_RELU || p.epi == FC_EPI_ADD_RELU;
   const bool has_lo = p.out_lo != nullptr;
   const float rs = ((p.row_scale && row_ok) ? p.row_scale[row] : 1.0f) * p.acc_scale;
   const int n_chunks = block_n / EPI_CHUNK;
-  const int tcol = part * 8;
   const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
-  uint4 ax = zero4, axl = zero4;
-  if (gate && row_ok) {
-    const size_t o = act_off(row, col0 + tcol, p.aux_kb);
-    ax = __ldg(reinterpret_cast<const uint4*>(p.aux + o));
-    if (p.aux_lo) axl = __ldg(reinterpret_cast<const uint4*>(p.aux_lo + o));
-  }
   mbar_wait(full, full_phase, p.err_flag, tag);
   tc_fence_after_sync();
   if (epi_debug(p) & 16) {        // development switch: hand the accumulator straight back
@@ -226,78 +255,101 @@ __device__ __forceinline__ void epi_tile_store(const P& p, const EpiStage& es, u
     if (lane == 0) acc_release(empty, empty_remote);
     return;
   }
-  const uint32_t t_addr = t_col + (uint32_t(quad * 32) << 16) + uint32_t(tcol);
+  const uint32_t g0 = g;
+  const uint32_t ga0 = gate ? gx->ga : 0u;
+  const int c_first = int((g0 & 1u) ^ grp);                  // first chunk of this tile with (g0 + c) & 1 == grp
+  const uint32_t t_addr = t_col + (uint32_t(quad * 32) << 16) + uint32_t(sub * 16);
   uint32_t v[8];
-  tmem_ld_32x8(t_addr, v);
-  for (int c = 0; c < n_chunks; ++c) {
-    const int col = col0 + c * EPI_CHUNK + tcol;
-    float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
-    if (p.bias) {
-      b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-      b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col) + 1);
-    }
-    uint4 nx = zero4, nxl = zero4;
-    if (gate && row_ok && c + 1 < n_chunks) {
-      const size_t o = act_off(row, col + EPI_CHUNK, p.aux_kb);
-      nx = __ldg(reinterpret_cast<const uint4*>(p.aux + o));
-      if (p.aux_lo) nxl = __ldg(reinterpret_cast<const uint4*>(p.aux_lo + o));
-    }
-    tmem_ld_wait();
-    float f[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[i]) * rs;
-    if (c + 1 < n_chunks) {
-      tmem_ld_32x8(t_addr + uint32_t((c + 1) * EPI_CHUNK), v);     // next chunk's accumulator in flight
-    } else {
-      // every TMEM read of this accumulator is complete -> hand it back to the MMA warp
-      tc_fence_before_sync();
-      __syncwarp();
-      if (lane == 0) acc_release(empty, empty_remote);
-    }
-    f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
-    f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+  bool released = false;
+  if (c_first < n_chunks) tmem_ld_32x8(t_addr + uint32_t(c_first * EPI_CHUNK), v);
+  for (int c = c_first; c < n_chunks; c += 2) {
+    uint4 ax[2] = {zero4, zero4}, axl[2] = {zero4, zero4};
     if (gate) {
-      const __half2* h = reinterpret_cast<const __half2*>(&ax);
-      const __half2* hl = reinterpret_cast<const __half2*>(&axl);
+      // this chunk's gate input from the aux ring (both halves), then the set goes back to the producer
+      const uint32_t ga = ga0 + uint32_t(c);
+      const uint32_t aset = ga % GATE_AUX_SETS;
+      mbar_wait(&gx->full[aset], (ga / GATE_AUX_SETS) & 1u, p.err_flag, tag + 20);
+      const uint8_t* u = gx->tiles + aset * GATE_AUX_SET_BYTES;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        ax[h] = stage_load8(u, r_local, sub * 2 + h);
+        if (p.aux_lo) axl[h] = stage_load8(u + EPI_UNIT_BYTES, r_local, sub * 2 + h);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&gx->empty[aset]);
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int col = col0 + c * EPI_CHUNK + sub * 16 + h * 8;
+      float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+      if (p.bias) {
+        b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+        b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col) + 1);
+      }
+      tmem_ld_wait();
+      float f[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[i]) * rs;
+      if (h == 0) {
+        tmem_ld_32x8(t_addr + uint32_t(c * EPI_CHUNK + 8), v);             // second half in flight
+      } else if (c + 2 < n_chunks) {
+        tmem_ld_32x8(t_addr + uint32_t((c + 2) * EPI_CHUNK), v);           // this group's next chunk in flight
+      } else {
+        // every TMEM read of this accumulator by this warp is complete -> hand it back to the MMA warp
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) acc_release(empty, empty_remote);
+        released = true;
+      }
+      f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+      f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+      if (gate) {
+        const __half2* hh = reinterpret_cast<const __half2*>(&ax[h]);
+        const __half2* hl = reinterpret_cast<const __half2*>(&axl[h]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 a = __half22float2(hh[i]), al = __half22float2(hl[i]);
+          f[2 * i] = (a.x + al.x) * fast_sigmoid(f[2 * i]);
+          f[2 * i + 1] = (a.y + al.y) * fast_sigmoid(f[2 * i + 1]);
+        }
+      }
+      if (relu) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
+      }
+      __align__(16) __half2 hi[4], lo[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const float2 a = __half22float2(h[i]), al = __half22float2(hl[i]);
-        f[2 * i] = (a.x + al.x) * fast_sigmoid(f[2 * i]);
-        f[2 * i + 1] = (a.y + al.y) * fast_sigmoid(f[2 * i + 1]);
+        hi[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+        const float2 hf = __half22float2(hi[i]);
+        lo[i] = __floats2half2_rn(f[2 * i] - hf.x, f[2 * i + 1] - hf.y);
       }
-      ax = nx;
-      axl = nxl;
-    }
-    if (relu) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
-    }
-    __align__(16) __half2 hi[4], lo[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      hi[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
-      const float2 hf = __half22float2(hi[i]);
-      lo[i] = __floats2half2_rn(f[2 * i] - hf.x, f[2 * i + 1] - hf.y);
-    }
-    const uint4 hq = *reinterpret_cast<const uint4*>(hi);
-    const uint4 lq = *reinterpret_cast<const uint4*>(lo);
-    if (staged) {
-      const uint32_t set = g & 1u;
-      // use u = g >> 1 of this set: the first use of a set needs no wait (parity trick), use u waits for the
-      // (u-1)-th hand-back
-      mbar_wait(&es.free_[set], ((g >> 1) & 1u) ^ 1u, p.err_flag, tag + 10);
-      stage_store8(es.unit(set, 0), r_local, part, hq);
-      if (has_lo) stage_store8(es.unit(set, 1), r_local, part, lq);
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&es.full[set]);
-      ++g;
-    } else if (row_ok && !skip_out) {
-      const size_t o = act_off(row, col, p.out_kb);
-      *reinterpret_cast<uint4*>(p.out + o) = hq;
-      if (has_lo) *reinterpret_cast<uint4*>(p.out_lo + o) = lq;
+      const uint4 hq = *reinterpret_cast<const uint4*>(hi);
+      const uint4 lq = *reinterpret_cast<const uint4*>(lo);
+      if (staged) {
+        // use u = (g0 + c) >> 1 of set `grp`: the first use needs no wait (parity trick), use u waits for the (u-1)-th hand-back
+        if (h == 0) mbar_wait(&es.free_[grp], (((g0 + uint32_t(c)) >> 1) & 1u) ^ 1u, p.err_flag, tag + 10);
+        stage_store8(es.unit(grp, 0), r_local, sub * 2 + h, hq);
+        if (has_lo) stage_store8(es.unit(grp, 1), r_local, sub * 2 + h, lq);
+        if (h == 1) {
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&es.full[grp]);
+        }
+      } else if (row_ok && !skip_out) {
+        const size_t o = act_off(row, col, p.out_kb);
+        *reinterpret_cast<uint4*>(p.out + o) = hq;
+        if (has_lo) *reinterpret_cast<uint4*>(p.out_lo + o) = lq;
+      }
     }
   }
+  if (!released) {                // a group without a chunk in this tile (odd chunk counts) still signs off
+    tc_fence_before_sync();
+    __syncwarp();
+    if (lane == 0) acc_release(empty, empty_remote);
+  }
+  if (staged) g = g0 + uint32_t(n_chunks);
+  if (gate) gx->ga = ga0 + uint32_t(n_chunks);
 }
 
 // Head epilogue (FC_EPI_HEAD): h = relu(s*acc + b), logits = h . tail_w^T + tail_b in the thread that owns the row.
@@ -385,7 +437,10 @@ __global__ void __launch_bounds__(FC_THREADS, 1) fc_tcgen05_kernel(const __grid_
   uint64_t* acc_empty = acc_full + 2;            // [2] (pair: the leader's collect both CTAs' epilogue warps)
   uint64_t* stg_full = acc_empty + 2;            // [2]
   uint64_t* stg_free = stg_full + 2;             // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stg_free + 2);
+  uint64_t* aux_full = stg_free + 2;             // [GATE_AUX_SETS] gate layers only
+  uint64_t* aux_empty = aux_full + GATE_AUX_SETS; // [GATE_AUX_SETS]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_empty + GATE_AUX_SETS);
+  static_assert((2 * FC2_STAGES + 8 + 2 * GATE_AUX_SETS) * 8 + 4 <= 256, "barrier area");
   float* tail_w_s = reinterpret_cast<float*>(smem + FC_OFF_TAIL);
   EpiStage es;
   epi_stage_init(es, smem + FC_OFF_STAGING, stg_full, stg_free);
@@ -394,6 +449,8 @@ __global__ void __launch_bounds__(FC_THREADS, 1) fc_tcgen05_kernel(const __grid_
   const int lane = threadIdx.x & 31;
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
   const bool leader = rank == 0u;
+  const bool gate = p.epi == FC_EPI_GATE;
+  const int stages = gate ? (PAIR ? FC2_GATE_STAGES : FC_GATE_STAGES) : STAGES;   // operand ring depth of this layer
   const int worker = PAIR ? int(blockIdx.x >> 1) : int(blockIdx.x);        // index of this CTA (pair) among the workers
   const int n_workers = PAIR ? int(gridDim.x >> 1) : int(gridDim.x);
 
@@ -415,8 +472,16 @@ __global__ void __launch_bounds__(FC_THREADS, 1) fc_tcgen05_kernel(const __grid_
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
       mbar_init(&acc_empty[s], PAIR ? 2 * FC_EPI_WARPS : FC_EPI_WARPS);
-      mbar_init(&stg_full[s], FC_EPI_WARPS);
+      mbar_init(&stg_full[s], FC_EPI_WARPS / 2);
       mbar_init(&stg_free[s], 1);
+    }
+    for (int s = 0; s < GATE_AUX_SETS; ++s) {
+      mbar_init(&aux_full[s], 1);
+      mbar_init(&aux_empty[s], FC_EPI_WARPS / 2);
+    }
+    if (gate) {
+      tma_prefetch_desc(&p.aux_map[0]);
+      if (p.aux_lo) tma_prefetch_desc(&p.aux_map[1]);
     }
     fence_mbar_init();
   }
@@ -445,6 +510,7 @@ __global__ void __launch_bounds__(FC_THREADS, 1) fc_tcgen05_kernel(const __grid_
     // ------------------------------------------------------------ TMA producer (warp-uniform loop, one lane issues)
     int stage = 0;
     uint32_t phase = 0;
+    uint32_t ga = 0;
     const uint32_t w_rows = PAIR ? uint32_t(p.block_n) / 2u : uint32_t(p.block_n);
     const uint32_t tx_bytes = FC_A_BYTES + w_rows * FC_TILE_K * 2;
     for (int item = worker; item < n_items; item += n_workers) {
@@ -471,9 +537,27 @@ __global__ void __launch_bounds__(FC_THREADS, 1) fc_tcgen05_kernel(const __grid_
           }
         }
         __syncwarp();
-        if (++stage == STAGES) {
+        if (++stage == stages) {
           stage = 0;
           phase ^= 1u;
+        }
+      }
+      if (gate) {
+        // gate input of this item's output chunks, in the order the epilogue consumes them (local barriers: every CTA
+        // of a pair feeds its own epilogue)
+        const int n_chunks = p.block_n / EPI_CHUNK;
+        for (int c = 0; c < n_chunks; ++c, ++ga) {
+          const uint32_t set = ga % GATE_AUX_SETS;
+          mbar_wait(&aux_empty[set], ((ga / GATE_AUX_SETS) & 1u) ^ 1u, p.err_flag, 150 + int(set));
+          if (elect_one_sync()) {
+            const int col = nt * p.block_n + c * EPI_CHUNK;
+            const int trow = (mt * p.aux_kb + (col >> 6)) * FC_TILE_M;
+            uint8_t* dst = smem + FC_OFF_GATE_AUX + set * GATE_AUX_SET_BYTES;
+            mbar_arrive_expect_tx(&aux_full[set], p.aux_lo ? 2u * EPI_UNIT_BYTES : uint32_t(EPI_UNIT_BYTES));
+            tma_load_2d(dst, &p.aux_map[0], &aux_full[set], col & 63, trow);
+            if (p.aux_lo) tma_load_2d(dst + EPI_UNIT_BYTES, &p.aux_map[1], &aux_full[set], col & 63, trow);
+          }
+          __syncwarp();
         }
       }
     }
@@ -553,7 +637,7 @@ __global__ void __launch_bounds__(FC_THREADS, 1) fc_tcgen05_kernel(const __grid_
             prev_w = w_lo;
             prev_stage = stage;
           }
-          if (++stage == STAGES) {
+          if (++stage == stages) {
             stage = 0;
             phase ^= 1u;
           }
@@ -569,6 +653,7 @@ __global__ void __launch_bounds__(FC_THREADS, 1) fc_tcgen05_kernel(const __grid_
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t g = 0;
+    GateAux gx{smem + FC_OFF_GATE_AUX, aux_full, aux_empty, 0u};
     // pair: the peer's epilogue warps hand accumulators back on the leader's barriers
     const uint32_t rem0 = (PAIR && !leader) ? mapa_shared(smem_u32(&acc_empty[0]), 0u) : 0u;
     const uint32_t rem1 = (PAIR && !leader) ? mapa_shared(smem_u32(&acc_empty[1]), 0u) : 0u;
@@ -581,7 +666,7 @@ __global__ void __launch_bounds__(FC_THREADS, 1) fc_tcgen05_kernel(const __grid_
         epi_tile_head(p, n_rows, mt, p.block_n, t_col, &acc_full[acc], acc_phase, &acc_empty[acc], tail_w_s, warp, lane, 400 + acc, rem);
       else
         epi_tile_store(p, es, g, n_rows, mt, nt * p.block_n, p.block_n, t_col, &acc_full[acc], acc_phase, &acc_empty[acc], warp,
-                       lane, 400 + acc, rem);
+                       lane, 400 + acc, rem, gate ? &gx : nullptr);
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1u;
@@ -596,7 +681,7 @@ __global__ void __launch_bounds__(FC_THREADS, 1) fc_tcgen05_kernel(const __grid_
         const int nt = item % p.n_tiles;
         if ((mt + 1) * FC_TILE_M > n_rows) continue;      // partial tile: the epilogue stores it directly
         epi_store_chunks(es, g, &p.out_map[0], &p.out_map[1], p.out_lo != nullptr, nt * p.block_n, p.block_n / EPI_CHUNK,
-                         mt, p.out_kb, p.err_flag);
+                         mt, p.out_kb, p.err_flag, uint32_t(warp - FC_STORE_WARP));
       }
       epi_store_drain();
     }

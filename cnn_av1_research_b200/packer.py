@@ -19,6 +19,7 @@ Everything here is host-side numpy; it runs once per `state_dict`.
 """
 from __future__ import annotations
 
+import os
 import struct
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence, Tuple
@@ -269,7 +270,7 @@ def backbone_ops(sd, precision: str = "fp16x3", prefix: str = "backbone.", layer
         w2 = _np64(sd[f"{p}se{layer}.excitation.2.weight"])     # [C, C/16]
         npos = grid * grid
         c = w1.shape[1]
-        if c <= 256:
+        if c < int(os.environ.get("AV1P_SE_FC_MIN_C", "512")):
             # memory-bound fused CUDA-core kernel (csrc/aux_kernels.cuh: se_kernel); weights [W1 ; W2^T] fp32
             ops.append(_Op(OP_SE, src=[_hi(src), _lo(src, precision), -1, -1], out=_hi(dst), out_lo=_lo(dst, precision),
                            n_tiles=npos, block_n=c, w=np.concatenate([w1, w2.T], axis=0).astype(np.float32),

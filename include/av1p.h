@@ -147,6 +147,8 @@ int av1p_threshold_sweep(const float* logits_dev, const uint8_t* labels_dev, int
  *      4 routing, 5 label finalize, 6 squeeze-excite, 7 resident-weight layer1 conv (arrays of 8). */
 int av1p_profile_begin(void);
 int av1p_profile_end(float* ms_by_class, int32_t* launches_by_class);
+/* Same, per launch in issue order: ms[i] / cls[i] for the first `cap` launches, *n_out = launches recorded. */
+int av1p_profile_end_launches(float* ms, int32_t* cls, int32_t cap, int32_t* n_out);
 
 /* ---- host -> device staging of the luma planes of planar 4:2:0 frames (pinned host memory
  *      recommended): copies n_frames * width*height samples, skipping chroma. */

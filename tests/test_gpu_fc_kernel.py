@@ -103,6 +103,23 @@ def test_residual_gate_and_row_scale(cuda_device):
     _check(out, ref_fc([a], w, kb_begin, kb_src, kb_w, block_n, 1, bias=bias, row_scale=rs), "row scale")
 
 
+@pytest.mark.parametrize("rows,block_n,n_tiles", [(128, 256, 2), (391, 256, 2), (5000, 128, 4), (700, 64, 1), (40000, 256, 2)])
+def test_gate_epilogue_reads_aux_through_the_tma_ring(cuda_device, rows, block_n, n_tiles):
+    """FC_EPI_GATE (SE excitation): out = (aux_hi + aux_lo) * sigmoid(acc); the gate input arrives through the aux ring."""
+    dev = cuda_device
+    g = torch.Generator(device=dev).manual_seed(rows + block_n)
+    a = _rand16((rows, 64), dev, g)
+    kb_begin, kb_src, kb_w = _dense_schedule(n_tiles, [1])
+    w = _rand16((len(kb_w) * block_n, 64), dev, g, 0.2)
+    width = n_tiles * block_n
+    aux = _rand16((rows, -(-width // 64) * 64), dev, g)
+    aux_lo = _rand16((rows, -(-width // 64) * 64), dev, g, 1e-3)
+    out, out_lo, _ = run_fc([a], w, kb_begin, kb_src, kb_w, block_n, 3, aux=aux, aux_lo=aux_lo, want_lo=True)
+    ref = ref_fc([a], w, kb_begin, kb_src, kb_w, block_n, 3, aux=aux[:, :width], aux_lo=aux_lo[:, :width])
+    _check(out, ref, "gate hi")
+    _check(out.double() + out_lo.double(), ref, "gate hi+lo", rel=5e-5)
+
+
 @pytest.mark.parametrize("block_n,tail_n", [(256, 1), (128, 3), (64, 2)])
 def test_head_epilogue(cuda_device, block_n, tail_n):
     dev = cuda_device
