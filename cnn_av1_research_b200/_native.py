@@ -94,8 +94,12 @@ def lib() -> C.CDLL:
         if not os.path.exists(_LIB_PATH):
             raise Av1pError(f"{_LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`. "
                             "There is no CPU or PyTorch fallback for this path.")
-        handle = C.CDLL(_LIB_PATH)
+        # AV1P_LIB_OVERRIDE: kernel-development switch (A/B runs of an older build of the same library)
+        override = os.environ.get("AV1P_LIB_OVERRIDE")
+        handle = C.CDLL(override or _LIB_PATH)
         for name, (restype, argtypes) in SIGNATURES.items():
+            if override and not hasattr(handle, name):
+                continue
             fn = getattr(handle, name)
             fn.restype, fn.argtypes = restype, argtypes
         _lib = handle

@@ -11,8 +11,8 @@
 // Work decomposition per 128-block M tile: two halves (output rows {0,1}, then {2,3}); a half needs
 // three input rows = 12 activation tiles [128 x 64] per plane, each loaded once per half and multiplied
 // into every output position that sees it.  One accumulator = one output row = 4 positions x 64
-// channels = 256 TMEM columns; the two accumulators alternate exactly like the FC kernel's double
-// buffer (output rows 0,1,2,3 -> slots 0,1,0,1), so output row r's epilogue overlaps the MMAs of r+1.
+// channels = 256 TMEM columns (rows 0,1,2,3 -> column halves 0,1,0,1), handed to the epilogue position by
+// position (CR_SLOTS below) so that the stores of a tile's tail overlap the MMAs of the next tile's head.
 // The three horizontally adjacent output positions fed by one input tile use taps kx = 2,1,0 - the
 // resident weights are stored in that order per ky, so they are ONE tcgen05.mma with N = 192
 // (N = 128 at the left/right edge): B = rows [(2-kx_first)*64, ...) of the ky stack.
@@ -53,6 +53,15 @@ static_assert(FC_SMEM_BYTES <= 232448, "fc shared memory exceeds the 227 KB opt-
 // tcgen05.mma is tensor-pipe idle time, and an interpreted schedule cost ~350 cycles per group of four MMAs
 // (measured: the skeleton without any MMA / memory traffic ran at 60 % of the full kernel's time).
 constexpr int CR_MAX_RING = 80;
+// Accumulators: the 512 TMEM columns are eight 64-column POSITION slots; output position p = oy * 4 + ox of an M tile
+// lives in slot p & 7 (rows 0/2 -> slots 0..3, rows 1/3 -> slots 4..7).  The issuer commits every position as soon as
+// its last input tile has been multiplied in and waits for a slot only right before the first product into it; the
+// epilogue drains positions in the order below (= completion order: during the last input row the positions of rows 2
+// and 3 complete in lock-step), so the next M tile starts while the tail of this one is still being stored.  (With two
+// whole-row accumulators both rows of a half completed together and the issuer idled for two row epilogues per tile.)
+constexpr int CR_SLOTS = 8;
+__device__ __constant__ const uint8_t CR_DRAIN[16] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 12, 9, 13, 10, 14, 11, 15};
+static_assert((2 * CR_STAGES + 2 * CR_SLOTS + 4 + 1) * 8 + 4 <= 256, "barrier area");
 
 struct ConvResParams {
   CUtensorMap a_map[4];        // x_hi, x_lo, residual hi, residual lo (tiled layout): 2-D [rows*16][64] fp16, box {64, 128}, SWIZZLE_128B
@@ -95,7 +104,7 @@ struct CrPipe {
   uint64_t* acc_empty;
   int stage;
   uint32_t phase;
-  uint32_t acc_phase;      // bit s: parity of accumulator slot s
+  uint32_t acc_phase;      // bit s: parity of position slot s (0..7)
 };
 
 // MMA issue for one M tile, straight-line (every loop below has compile-time bounds and unrolls completely).
@@ -129,13 +138,19 @@ __device__ __forceinline__ void cr_issue_mtile(CrPipe& q, uint32_t base, uint32_
 #pragma unroll
         for (int pl = 0; pl < PLANES; ++pl) {
           const uint32_t a_lo = wait_tile();
-          if (xi == 0 && pl == 0) {
-            // first use of an accumulator slot in this half: the epilogue must have drained it
+          if (pl == 0 && (xi == 0 || xi == 2)) {
+            // first touch of output positions (tile ix = 1 starts positions 0..2 of a row, tile ix = 2 position 3): the
+            // epilogue must have drained the previous tenant of each 64-column position slot
 #pragma unroll
             for (int o = 0; o < 2; ++o) {
               const int oy = 2 * h + o;
               const int first_iy = oy < 2 ? 0 : oy - 1;
-              if (iy == first_iy) mbar_wait(&q.acc_empty[o], ((q.acc_phase >> o) & 1u) ^ 1u, err_flag, 200 + o);
+              if (iy != first_iy) continue;
+#pragma unroll
+              for (int ox = (xi == 0 ? 0 : 3); ox < (xi == 0 ? 3 : 4); ++ox) {
+                const int slot = o * 4 + ox;
+                mbar_wait(&q.acc_empty[slot], ((q.acc_phase >> slot) & 1u) ^ 1u, err_flag, 200 + slot);
+              }
             }
           }
           tc_fence_after_sync();
@@ -168,15 +183,29 @@ __device__ __forceinline__ void cr_issue_mtile(CrPipe& q, uint32_t base, uint32_
               }
             }
             umma_commit(&q.empty_bar[q.stage]);     // frees the ring slot once these MMAs have read it
-            if (!RESID && xi == 3 && pl == PLANES - 1) {
+            if (pl == PLANES - 1 && xi > 0) {
+              // positions of the output rows whose last input row this is, complete once tile ix has been multiplied in:
+              // ix = 0 (xi 1) -> position 0, ix = 2 -> position 1, ix = 3 -> positions 2 and 3 (with a residual branch
+              // position 3 still waits for its residual tile, which closes the row below)
 #pragma unroll
               for (int o = 0; o < 2; ++o) {
                 const int oy = 2 * h + o;
-                if (iy == (oy < 3 ? oy + 1 : 3)) umma_commit(&q.acc_full[o]);    // output row complete -> epilogue
+                if (iy != (oy < 3 ? oy + 1 : 3)) continue;
+                umma_commit(&q.acc_full[o * 4 + xi - 1]);
+                if (!RESID && xi == 3) umma_commit(&q.acc_full[o * 4 + 3]);
               }
             }
           }
           __syncwarp();
+          if (pl == PLANES - 1 && xi > 0) {
+#pragma unroll
+            for (int o = 0; o < 2; ++o) {
+              const int oy = 2 * h + o;
+              if (iy != (oy < 3 ? oy + 1 : 3)) continue;
+              q.acc_phase ^= 1u << (o * 4 + xi - 1);
+              if (!RESID && xi == 3) q.acc_phase ^= 1u << (o * 4 + 3);
+            }
+          }
           next_stage();
         }
         // Output rows whose last input row is iy: their residual tile of position ox = xi follows immediately, so the
@@ -200,18 +229,13 @@ __device__ __forceinline__ void cr_issue_mtile(CrPipe& q, uint32_t base, uint32_
                 }
               }
               umma_commit(&q.empty_bar[q.stage]);
-              if (ox == 3 && pl == AUX_PLANES - 1) umma_commit(&q.acc_full[o]);
+              if (ox == 3 && pl == AUX_PLANES - 1) umma_commit(&q.acc_full[o * 4 + 3]);
             }
             __syncwarp();
+            if (ox == 3 && pl == AUX_PLANES - 1) q.acc_phase ^= 1u << (o * 4 + 3);
             next_stage();
           }
         }
-      }
-      // accumulator parity of the output rows completed by this input row
-#pragma unroll
-      for (int o = 0; o < 2; ++o) {
-        const int oy = 2 * h + o;
-        if (iy == (oy < 3 ? oy + 1 : 3)) q.acc_phase ^= 1u << o;
       }
     }
   }
@@ -224,9 +248,9 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_res_tcgen05_kernel(const _
   uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + CR_OFF_BARS);
   uint64_t* empty_bar = full_bar + CR_STAGES;
-  uint64_t* acc_full = empty_bar + CR_STAGES;   // [2]
-  uint64_t* acc_empty = acc_full + 2;           // [2]
-  uint64_t* stg_full = acc_empty + 2;           // [2]
+  uint64_t* acc_full = empty_bar + CR_STAGES;   // [CR_SLOTS]
+  uint64_t* acc_empty = acc_full + CR_SLOTS;    // [CR_SLOTS]
+  uint64_t* stg_full = acc_empty + CR_SLOTS;    // [2]
   uint64_t* stg_free = stg_full + 2;            // [2]
   uint64_t* w_bar = stg_free + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
@@ -254,9 +278,11 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_res_tcgen05_kernel(const _
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < CR_SLOTS; ++s) {
       mbar_init(&acc_full[s], 1);
       mbar_init(&acc_empty[s], FC_EPI_WARPS);
+    }
+    for (int s = 0; s < 2; ++s) {
       mbar_init(&stg_full[s], FC_EPI_WARPS / 2);
       mbar_init(&stg_free[s], 1);
     }
@@ -332,14 +358,16 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_res_tcgen05_kernel(const _
     }
   } else if (warp < FC_STORE_WARP) {
     // ------------------------------------------------------------ epilogue (warps 2..9): output rows 0..3 -> slots 0,1,0,1
-    uint32_t acc_phase = 0u;
+    uint32_t acc_phase = 0u;      // bit s: parity of position slot s
     uint32_t g = 0;
     for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x) {
-      for (int oy = 0; oy < 4; ++oy) {
-        const int slot = oy & 1;
-        epi_tile_store(p, es, g, n_rows, mt, oy * 256, 256, tmem_base + uint32_t(slot * 256), &acc_full[slot], acc_phase,
-                       &acc_empty[slot], warp, lane, 400 + slot);
-        if (slot) acc_phase ^= 1u;
+#pragma unroll 1
+      for (int i = 0; i < 16; ++i) {
+        const int pos = CR_DRAIN[i];
+        const int slot = pos & 7;
+        epi_tile_store(p, es, g, n_rows, mt, pos * 64, 64, tmem_base + uint32_t(slot * 64), &acc_full[slot],
+                       (acc_phase >> slot) & 1u, &acc_empty[slot], warp, lane, 400 + slot);
+        acc_phase ^= 1u << slot;
       }
     }
   } else {
@@ -347,8 +375,10 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_res_tcgen05_kernel(const _
     uint32_t g = 0;
     for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x) {
       if ((mt + 1) * FC_TILE_M > n_rows || (p.debug & 18)) continue;
-      epi_store_chunks(es, g, &p.out_map[0], &p.out_map[1], p.out_lo != nullptr, 0, 1024 / EPI_CHUNK, mt, 16, p.err_flag,
-                       uint32_t(warp - FC_STORE_WARP));
+#pragma unroll 1
+      for (int i = 0; i < 16; ++i)
+        epi_store_chunks(es, g, &p.out_map[0], &p.out_map[1], p.out_lo != nullptr, int(CR_DRAIN[i]) * 64, 64 / EPI_CHUNK, mt, 16,
+                         p.err_flag, uint32_t(warp - FC_STORE_WARP));
     }
     epi_store_drain();
   }

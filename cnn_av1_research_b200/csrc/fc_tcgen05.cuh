@@ -121,7 +121,11 @@ struct FcParams {
   uint16_t kb_w[FC_MAX_KB];    // weight chunk ([block_n x 64] tile) index, or FC_W_IDENT
 };
 
-__device__ __forceinline__ float fast_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
+// SE / attention gates: ex2.approx + rcp.approx (relative error ~2e-7 + 1e-7, far inside the split-precision budget);
+// the accurate expf + IEEE division cost ~25 instructions per element and were ~40 % of the gate layers' time.
+// Routing decisions (aux_kernels.cuh) keep the accurate form.
+// (the clamp keeps 1 + e^-x finite: __fdividef(1, inf) is NaN, not 0)
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-fmaxf(x, -80.0f))); }
 
 // ------------------------------------------------------------------------------------------------
 // Epilogue staging: two sets of two [128 rows x 32 cols] fp16 tiles (hi plane, lo plane) in the SWIZZLE_64B layout
@@ -264,10 +268,15 @@ __device__ __forceinline__ void epi_tile_store(const P& p, const EpiStage& es, u
   if (c_first < n_chunks) tmem_ld_32x8(t_addr + uint32_t(c_first * EPI_CHUNK), v);
   for (int c = c_first; c < n_chunks; c += 2) {
     uint4 ax[2] = {zero4, zero4}, axl[2] = {zero4, zero4};
+    uint32_t aset = 0;
     if (gate) {
-      // this chunk's gate input from the aux ring (both halves), then the set goes back to the producer
+      // this chunk's gate input from the aux ring (both halves).  The set is handed back to the producer only after the
+      // values have been USED (below): an mbarrier arrive is not ordered behind shared-memory loads still queued in the
+      // LSU (here behind the partial tile's direct global stores), and the refill is an async-proxy write - released
+      // right after issuing the loads, a late load read the NEXT chunk's tile (seen as run-to-run differences in the
+      // partial last M tile once the gate math became fast).
       const uint32_t ga = ga0 + uint32_t(c);
-      const uint32_t aset = ga % GATE_AUX_SETS;
+      aset = ga % GATE_AUX_SETS;
       mbar_wait(&gx->full[aset], (ga / GATE_AUX_SETS) & 1u, p.err_flag, tag + 20);
       const uint8_t* u = gx->tiles + aset * GATE_AUX_SET_BYTES;
 #pragma unroll
@@ -275,8 +284,6 @@ __device__ __forceinline__ void epi_tile_store(const P& p, const EpiStage& es, u
         ax[h] = stage_load8(u, r_local, sub * 2 + h);
         if (p.aux_lo) axl[h] = stage_load8(u + EPI_UNIT_BYTES, r_local, sub * 2 + h);
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&gx->empty[aset]);
     }
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -311,6 +318,10 @@ __device__ __forceinline__ void epi_tile_store(const P& p, const EpiStage& es, u
           const float2 a = __half22float2(hh[i]), al = __half22float2(hl[i]);
           f[2 * i] = (a.x + al.x) * fast_sigmoid(f[2 * i]);
           f[2 * i + 1] = (a.y + al.y) * fast_sigmoid(f[2 * i + 1]);
+        }
+        if (h == 1) {             // both halves' aux registers have been consumed: the loads are complete
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&gx->empty[aset]);
         }
       }
       if (relu) {

@@ -270,7 +270,9 @@ def backbone_ops(sd, precision: str = "fp16x3", prefix: str = "backbone.", layer
         w2 = _np64(sd[f"{p}se{layer}.excitation.2.weight"])     # [C, C/16]
         npos = grid * grid
         c = w1.shape[1]
-        if c < int(os.environ.get("AV1P_SE_FC_MIN_C", "512")):
+        # se1 / se2: memory-bound fused CUDA-core kernel; se3 / se4 (1x1 maps): two tensor-core FC layers whose gate epilogue
+        # reads its input through the TMA aux ring (383 us vs 771 us for se3 on 518 k rows).  AV1P_SE_FC_MIN_C is an A/B knob.
+        if c < int(os.environ.get("AV1P_SE_FC_MIN_C", "256")):
             # memory-bound fused CUDA-core kernel (csrc/aux_kernels.cuh: se_kernel); weights [W1 ; W2^T] fp32
             ops.append(_Op(OP_SE, src=[_hi(src), _lo(src, precision), -1, -1], out=_hi(dst), out_lo=_lo(dst, precision),
                            n_tiles=npos, block_n=c, w=np.concatenate([w1, w2.T], axis=0).astype(np.float32),

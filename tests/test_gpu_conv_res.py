@@ -89,7 +89,7 @@ def test_fp16_conv(cuda_device, rows, epi):
     assert torch.isfinite(out).all() and err <= 2e-3 * ref.abs().max().item(), err
 
 
-@pytest.mark.parametrize("rows,epi", [(300, 1), (4096 + 17, 2)])
+@pytest.mark.parametrize("rows,epi", [(300, 1), (4096 + 17, 2), (148 * 128 * 3 + 77, 1), (148 * 128 * 4 + 300, 2)])
 def test_split_precision_conv(cuda_device, rows, epi):
     """hi/lo planes, three products: the result (hi + lo) must be fp32-grade."""
     dev = cuda_device
