@@ -84,7 +84,8 @@ int ensure_ctx() {
     const ConvResKernel* ks = conv_res_all_kernels(&n_k);
     for (int i = 0; i < n_k; ++i) CUDA_TRY(cudaFuncSetAttribute(ks[i], cudaFuncAttributeMaxDynamicSharedMemorySize, CR_SMEM_BYTES));
   }
-  CUDA_TRY(cudaFuncSetAttribute(stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(stem_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(stem_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM_BYTES));
   CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&g_ctx.watchdog_host), sizeof(int), cudaHostAllocMapped));
   *g_ctx.watchdog_host = 0;
   CUDA_TRY(cudaHostGetDevicePointer(reinterpret_cast<void**>(&g_ctx.watchdog_dev), g_ctx.watchdog_host, 0));
@@ -360,6 +361,8 @@ struct PlannedOp {
   FcParams fc;          // AV1P_OP_FC
   ConvResParams cr;     // AV1P_OP_CONV_RES
   StemParams stem;      // AV1P_OP_STEM
+  const __half* stem_w_int = nullptr;   // integer-pixel weight set (frames input) and its scale
+  float stem_scale_int = 0.f;
   const __half* src = nullptr;   // SAM / FGVC
   const __half* src_lo = nullptr;
   __half* dst = nullptr;         // SE
@@ -423,6 +426,9 @@ int plan_stage(const av1p_model* m, const ActLayout& L, uint8_t* act_base, av1p_
         memset(&P.stem, 0, sizeof P.stem);
         P.stem.w = reinterpret_cast<const __half*>(at(op.w_off));
         P.stem.acc_scale = op.f0;
+        P.stem_w_int = P.stem.w ? P.stem.w + 2 * 128 * 64 : nullptr;
+        P.stem_scale_int = op.f1;
+        if (!(op.f1 > 0.f)) return fail(AV1P_EINVAL, "stem op without the integer-pixel weight set");
         P.stem.err_flag = g_ctx.watchdog_dev;
         P.stem.b = reinterpret_cast<const float*>(at(op.bias_off));
         P.stem.out = buf(op.out);
@@ -604,7 +610,14 @@ int run_stage(av1p_stage* s, const StemInput& si, const int32_t* idx, const int3
         sp.n = n;
         const int grid = std::min(ceil_div(n, ST_BLOCKS), g_ctx.sms);
         ProfScope ps(PROF_STEM, st);
-        stem_tc_kernel<<<grid, ST_THREADS, ST_SMEM_BYTES, st>>>(sp);
+        if (si.kind == 0) {
+          // frames: integer pixel plane + the / 1023 weight set (see stem_tc.cuh, INT_PIX)
+          sp.w = P.stem_w_int;
+          sp.acc_scale = P.stem_scale_int;
+          stem_tc_kernel<true><<<grid, ST_THREADS, ST_SMEM_BYTES, st>>>(sp);
+        } else {
+          stem_tc_kernel<false><<<grid, ST_THREADS, ST_SMEM_BYTES, st>>>(sp);
+        }
         break;
       }
       case AV1P_OP_FC: {

@@ -8,12 +8,14 @@
 #include <stdint.h>
 
 #define AV1P_BLOB_MAGIC 0x50315641u   /* "AV1P" */
-#define AV1P_BLOB_VERSION 8u
+#define AV1P_BLOB_VERSION 9u
 #define AV1P_BLOB_MAX_NT 8
 #define AV1P_BLOB_MAX_KB 128
 
 enum Av1pOpType : int32_t {
-  AV1P_OP_STEM = 0,       // gather + /1023 + conv1/bn/relu/maxpool -> out buffer (1024 cols); w = fp16 [2][128][64], f0 = acc_scale
+  AV1P_OP_STEM = 0,       // gather + /1023 + conv1/bn/relu/maxpool -> out buffer (1024 cols); w = fp16 [4][128][64]: planes 0,1 =
+                          // hi/lo weights for float blocks (f0 = acc_scale), planes 2,3 = hi/lo of w / 1023 for integer
+                          // frame samples (f1 = acc_scale)
   AV1P_OP_FC = 1,         // block-Toeplitz linear layer on tensor cores
   AV1P_OP_SAM = 2,        // spatial-attention scalar of `src0` (512 cols) -> row_scale
   AV1P_OP_FGVC_TAIL = 3,  // L2-normalise `src0` (512 cols) + cosine classifier -> logits[4]

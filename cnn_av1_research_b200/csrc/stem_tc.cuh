@@ -15,6 +15,11 @@
 //               is eight CONSECUTIVE pixels of one row of the pixel tile: the tile is kept as fp16 hi / lo planes
 //               (split once per pixel) and a chunk is four 32-bit shared loads per plane, no per-tap arithmetic;
 //   products  : W_hi.P_hi + W_hi.P_lo + W_lo.P_hi (split precision), fp32 accumulators in TMEM (256 cols x 2).
+//   INT_PIX   : frame input (kind 0).  A 10-bit sample is an integer that fp16 holds exactly, so the pixel tile keeps the
+//               raw integers in ONE plane and the /1023 moves into a second weight set (w / 1023 folded in float64 by the
+//               packer, split hi/lo): two products W_hi.P + W_lo.P instead of three and half the im2col traffic.
+//               (Exact for samples < 2048; a sample above that is rounded to fp16's 11 bits - such a value is outside
+//               the 10-bit format the reference's reader warns about, 005:198-204.)
 // Because the channels are the accumulator rows (TMEM lanes), one epilogue thread owns a channel and sees all
 // 64 conv positions of a block in its columns: bias, ReLU and the 3x3/s2 max-pool run in registers, and a warp
 // stores 32 consecutive channels (64 contiguous bytes) per pooled position.
@@ -55,6 +60,7 @@ struct StemParams {
   const int* n_dev;         // device-side row count (nullptr -> n)
   int n;
   const __half* w;          // [2][128][64] folded conv1 weights x 2^s: hi plane then lo plane, K = ky*8+kx (kx = 7 and k >= 56 zero)
+                            // (INT_PIX: the integer-pixel set, weights / 1023)
   const float* b;           // [64] folded bias
   float acc_scale;          // 2^-s
   __half* out;              // [rows][1024] in the tiled activation layout (act_off, 16 blocks per row)
@@ -66,6 +72,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
+template <bool INT_PIX>
 __global__ void __launch_bounds__(ST_THREADS, 1) stem_tc_kernel(const __grid_constant__ StemParams p) {
   extern __shared__ uint8_t st_smem_raw[];
   const uint32_t base = (smem_u32(st_smem_raw) + 1023u) & ~1023u;
@@ -145,7 +152,8 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_tc_kernel(const __grid_con
           } else {
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              if (x0 + j < p.in.width) raw[j] = __float_as_uint(__fdiv_rn(float(__ldg(src + j)), 1023.0f));
+              if (x0 + j < p.in.width)
+                raw[j] = __float_as_uint(INT_PIX ? float(__ldg(src + j)) : __fdiv_rn(float(__ldg(src + j)), 1023.0f));
           }
         }
       } else {
@@ -157,7 +165,12 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_tc_kernel(const __grid_con
     auto write_pix = [&](int buf, const uint32_t (&raw)[4], int mode) {
       const int o = buf * 2 * ST_PIX_PLANE + (pb * ST_TILE_H + ppy + 3) * ST_TILE_W + ppx0 + 3;
       float x[4];
-      if (mode) {
+      if (mode && INT_PIX) {
+        x[0] = float(raw[0] & 0xFFFFu);
+        x[1] = float(raw[0] >> 16);
+        x[2] = float(raw[1] & 0xFFFFu);
+        x[3] = float(raw[1] >> 16);
+      } else if (mode) {
         x[0] = __fdiv_rn(float(raw[0] & 0xFFFFu), 1023.0f);
         x[1] = __fdiv_rn(float(raw[0] >> 16), 1023.0f);
         x[2] = __fdiv_rn(float(raw[1] & 0xFFFFu), 1023.0f);
@@ -170,7 +183,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_tc_kernel(const __grid_con
       for (int j = 0; j < 4; ++j) {                   // o is odd: scalar fp16 stores
         const __half h = __float2half_rn(x[j]);
         pix_hi[o + j] = h;
-        pix_hi[o + ST_PIX_PLANE + j] = __float2half_rn(x[j] - __half2float(h));
+        if (!INT_PIX) pix_hi[o + ST_PIX_PLANE + j] = __float2half_rn(x[j] - __half2float(h));
       }
     };
     int stage = 0, cur = 0;
@@ -197,13 +210,15 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_tc_kernel(const __grid_con
           // kernel row c of conv position (py, px): tile row 2*py + c, tile columns 2*px .. 2*px + 7 (4-byte aligned)
           const int o = (b * ST_TILE_H + 2 * (pos >> 3) + c) * ST_TILE_W + 2 * (pos & 7);
           const uint32_t* ph = reinterpret_cast<const uint32_t*>(ph_base + o);
-          const uint32_t* pl = reinterpret_cast<const uint32_t*>(ph_base + ST_PIX_PLANE + o);
           hi = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-          lo = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+          if (!INT_PIX) {
+            const uint32_t* pl = reinterpret_cast<const uint32_t*>(ph_base + ST_PIX_PLANE + o);
+            lo = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+          }
         }
         const int dst = row * 128 + ((c ^ (row & 7)) << 4);
         *reinterpret_cast<uint4*>(s_hi + dst) = hi;
-        *reinterpret_cast<uint4*>(s_lo + dst) = lo;
+        if (!INT_PIX) *reinterpret_cast<uint4*>(s_lo + dst) = lo;
       }
       fence_proxy_async_smem();                       // generic-proxy stores -> visible to tcgen05.mma
       __syncwarp();
@@ -230,8 +245,10 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_tc_kernel(const __grid_con
         const uint32_t b_hi = umma_desc_lo_sw128(smem_u32(stages + stage * ST_STAGE_BYTES)), b_lo = b_hi + (ST_P_BYTES >> 4);
 #pragma unroll
         for (int k = 0; k < 4; ++k) umma_f16_ss_lo(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, k > 0 ? 1u : 0u);
+        if (!INT_PIX) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_f16_ss_lo(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
+          for (int k = 0; k < 4; ++k) umma_f16_ss_lo(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
+        }
 #pragma unroll
         for (int k = 0; k < 4; ++k) umma_f16_ss_lo(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
         umma_commit(&empty_bar[stage]);

@@ -27,7 +27,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import numpy as np
 
 BLOB_MAGIC = 0x50315641
-BLOB_VERSION = 8
+BLOB_VERSION = 9
 MAX_NT = 8
 MAX_KB = 128
 TILE_K = 64
@@ -254,10 +254,16 @@ def backbone_ops(sd, precision: str = "fp16x3", prefix: str = "backbone.", layer
     wk[64:] = wk[:64]
     w_hi = wk.astype(np.float16)
     w_lo = (wk - w_hi.astype(np.float64)).astype(np.float16)
+    # second set for frame input: the kernel keeps the raw 10-bit integers (exact in fp16) and the / 1023 lives here
+    scale_i = 2.0 ** int(np.clip(np.floor(np.log2(8192.0 / (np.abs(w).max() / 1023.0))), 0, 15))
+    wi = wk / scale * scale_i / 1023.0
+    wi_hi = wi.astype(np.float16)
+    wi_lo = (wi - wi_hi.astype(np.float64)).astype(np.float16)
     if precision != "fp16x3":
         w_lo = np.zeros_like(w_lo)
-    ops.append(_Op(OP_STEM, out=_hi("B0"), out_lo=_lo("B0", precision), w=np.stack([w_hi, w_lo]), bias=b.astype(np.float32),
-                   f0=1.0 / scale, name="stem"))
+        wi_lo = np.zeros_like(wi_lo)
+    ops.append(_Op(OP_STEM, out=_hi("B0"), out_lo=_lo("B0", precision), w=np.stack([w_hi, w_lo, wi_hi, wi_lo]),
+                   bias=b.astype(np.float32), f0=1.0 / scale, f1=1.0 / scale_i, name="stem"))
 
     def conv_bn(unit: str, conv: str, bn: str, grid: int, stride: int):
         wf, bf = fold_bn(_np64(sd[f"{unit}.{conv}.weight"]), None, sd, f"{unit}.{bn}")

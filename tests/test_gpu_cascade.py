@@ -109,7 +109,15 @@ def test_cascade_matches_reference_predict(cuda_device, golden_dir, precision):
     assert np.array_equal(images[:4].numpy(), g["images_head"])
     out = pipe.predict(images)
     assert out.dtype == torch.int64 and out.device.type == "cpu" and out.shape == (labels.size,)
-    assert np.array_equal(out.numpy(), labels), "frame path and image path disagree"
+    # The frame path keeps the integer samples and folds / 1023 into the stem weights, the image path multiplies the
+    # float32 blocks it is given: the same numbers up to fp32 rounding in split precision (a label can only flip on a
+    # block whose decision margin is ~1e-6), while in the fp16 fast mode the frame path is the more exact one.
+    same = (out.numpy() == labels).mean()
+    if precision == "fp16x3":
+        bad = np.nonzero(out.numpy() != labels)[0]
+        assert bad.size <= 1 and (_margins(g)[bad] < 1e-4).all(), f"frame path and image path disagree on blocks {bad}"
+    else:
+        assert same >= AGREE_MIN[precision], f"frame path vs image path agreement {same:.5f}"
 
 
 def test_predict_edge_cases(cuda_device):
@@ -143,9 +151,36 @@ def test_full_size_properties_4k(cuda_device):
     images = O.frames_to_images(words, nf, w, h)[torch.from_numpy(sel)]
     ref = O.cascade_predict(synth.calibrated_cascade(0), images, thr)["labels"].numpy()
     assert (both[sel] == ref).mean() >= 0.995
-    assert np.array_equal(pipe.predict(images).numpy(), both[sel]), "image path differs from frame path"
+    assert (pipe.predict(images).numpy() != both[sel]).sum() <= 1, "image path differs from frame path"
     hist = np.bincount(both, minlength=8) / both.size
     assert 0.3 < hist[0] < 0.75 and hist[1:].sum() > 0.2, f"degenerate routing mix {hist}"
+
+
+def test_frame_path_logits_on_in_format_and_out_of_format_samples(cuda_device):
+    """Stage-1 logits straight from a planar frame (the stem keeps the integer samples in fp16 and folds the / 1023 into its
+    weights) against the CPU oracle: 10-bit noise frames - the worst case for the stem - must meet the normal logit
+    tolerance; samples above the 10-bit range (up to 4095, outside the format, 005:198-204 only warns) stay within it too
+    although values >= 2048 are rounded to fp16's 11 significant bits."""
+    from cnn_av1_research_b200.runtime import NativeModel, NativeStage
+    w, h = 640, 368
+    n = (w // 16) * (h // 16)
+    sd = synth.calibrated_state_dict("stage1", 0)
+    model = NativeModel("stage1", sd, torch.device(cuda_device))
+    stage = NativeStage(model, n)
+    for top in (1024, 4096):
+        rng = np.random.default_rng(top)
+        words = np.full(synth.frame_words(w, h), 512, dtype=np.uint16)
+        if top == 1024:
+            words[: w * h] = rng.integers(0, top, size=w * h, dtype=np.uint16)
+        else:       # structured content stretched to 12 bits (plus odd offsets, so that many samples >= 2048 are not fp16-exact)
+            base = synth.synth_frames(1, w, h, seed=9)[: w * h].astype(np.uint32)
+            words[: w * h] = np.minimum(base * 4 + rng.integers(0, 4, size=w * h), top - 1).astype(np.uint16)
+        fr = frames_tensor(words, cuda_device)
+        got = stage.forward(N.frames_input(fr, w, h, 1), n).cpu().numpy()
+        ref = O.stage_logits("stage1", sd, O.frames_to_images(words, 1, w, h)).numpy()
+        err = float(np.abs(got - ref).max())
+        print(f"samples < {top}: max-abs stage-1 logit error {err:.3g} (logit sigma {ref.std():.2f})")
+        assert err <= LOGIT_TOL["fp16x3"], (top, err)
 
 
 def test_run_to_run_determinism_with_partial_last_tiles(cuda_device):
