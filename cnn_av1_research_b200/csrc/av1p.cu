@@ -56,6 +56,9 @@ struct DeviceCtx {
   int sms = 0;
   EncodeTiledFn encode = nullptr;
   bool fc_pair = true;            // FC layers on CTA pairs (tcgen05 cta_group::2); AV1P_FC_PAIR=0 selects the single-CTA kernel
+  bool fc_resid_epi = false;      // AV1P_FC_RESID_EPI=1: residual FC layers add the identity branch in the epilogue (aux ring)
+                                  // instead of on the tensor core (FC_W_IDENT schedule entries).  Measured slower (layer2.1.conv2
+                                  // 859 vs 740 us on 518 k rows): the aux ring costs two of the six operand-ring stages.
   int* watchdog_host = nullptr;   // mapped pinned memory: survives a kernel trap
   int* watchdog_dev = nullptr;
 };
@@ -79,6 +82,7 @@ int ensure_ctx() {
   CUDA_TRY(cudaFuncSetAttribute(fc_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FC_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(fc_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FC_SMEM_BYTES));
   if (const char* e = getenv("AV1P_FC_PAIR")) g_ctx.fc_pair = atoi(e) != 0;
+  if (const char* e = getenv("AV1P_FC_RESID_EPI")) g_ctx.fc_resid_epi = atoi(e) != 0;
   {
     int n_k = 0;
     const ConvResKernel* ks = conv_res_all_kernels(&n_k);
@@ -494,7 +498,15 @@ int plan_stage(const av1p_model* m, const ActLayout& L, uint8_t* act_base, av1p_
           if (op.aux_lo >= 0)
             if (int rc = make_act_map(&f.aux_map[1], buf(op.aux_lo), L.cols[op.aux_lo], L.cap, true)) return rc;
         }
-        if (op.epi == FC_EPI_ADD_RELU) {
+        if (op.epi == FC_EPI_ADD_RELU && g_ctx.fc_resid_epi) {
+          // residual added by the epilogue from the aux ring
+          if (op.n_tiles * op.block_n > int(L.cols[op.aux])) return fail(AV1P_EINVAL, "residual narrower than the FC output");
+          if (f.row_scale) return fail(AV1P_EINVAL, "residual FC layer cannot use a row scale");
+          f.aux_epi = 1;
+          if (int rc = make_act_map(&f.aux_map[0], buf(op.aux), L.cols[op.aux], L.cap, true)) return rc;
+          if (op.aux_lo >= 0)
+            if (int rc = make_act_map(&f.aux_map[1], buf(op.aux_lo), L.cols[op.aux_lo], L.cap, true)) return rc;
+        } else if (op.epi == FC_EPI_ADD_RELU) {
           if (op.n_tiles * op.block_n > int(L.cols[op.aux])) return fail(AV1P_EINVAL, "residual narrower than the FC output");
           if (int rc = make_act_map(&f.a_map[2], buf(op.aux), L.cols[op.aux], L.cap, false)) return rc;
           f.src_kb[2] = f.src_kb[3] = int(L.cols[op.aux] / 64);
@@ -1125,7 +1137,14 @@ extern "C" int av1p_fc_forward(const av1p_fc_desc* d, void* stream) {
     if (d->aux_lo_dev)
       if (int rc = make_act_map(&f.aux_map[1], d->aux_lo_dev, uint64_t(d->aux_ld), uint64_t(d->rows), true)) return rc;
   }
-  if (d->epi == FC_EPI_ADD_RELU) {
+  if (d->epi == FC_EPI_ADD_RELU && g_ctx.fc_resid_epi) {
+    if (!d->aux_dev || d->aux_ld < d->n_tiles * d->block_n) return fail(AV1P_EINVAL, "residual missing or too narrow");
+    if (f.row_scale) return fail(AV1P_EINVAL, "residual FC layer cannot use a row scale");
+    f.aux_epi = 1;
+    if (int rc = make_act_map(&f.aux_map[0], d->aux_dev, uint64_t(d->aux_ld), uint64_t(d->rows), true)) return rc;
+    if (d->aux_lo_dev)
+      if (int rc = make_act_map(&f.aux_map[1], d->aux_lo_dev, uint64_t(d->aux_ld), uint64_t(d->rows), true)) return rc;
+  } else if (d->epi == FC_EPI_ADD_RELU) {
     if (!d->aux_dev || d->aux_ld < d->n_tiles * d->block_n) return fail(AV1P_EINVAL, "residual missing or too narrow");
     if (int rc = make_act_map(&f.a_map[2], d->aux_dev, uint64_t(d->aux_ld), uint64_t(d->rows), false)) return rc;
     f.src_kb[2] = f.src_kb[3] = d->aux_ld / 64;

@@ -56,10 +56,11 @@ constexpr int EPI_IDENT_BYTES = 512;                         // 16 x 16 fp16 sca
 constexpr int EPI_SETS = 2;                                  // staging is double buffered: chunk g uses set g & 1
 constexpr int EPI_STAGING_BYTES = EPI_SETS * 2 * EPI_UNIT_BYTES;   // {hi, lo} x 2 sets = 32 KB
 constexpr int FC_OFF_STAGING = FC_STAGES * FC_STAGE_BYTES;
-// Gate layers (FC_EPI_GATE: out = aux * sigmoid(acc), the SE excitation) have one tiny K block per item, so they run on a
-// shortened operand ring and the upper part of the ring area becomes a ring of AUX tiles: the [128 rows x 32 cols]
-// hi / lo pieces of the gate input the epilogue multiplies with, loaded by the producer warp with TMA in the staging
-// tiles' SWIZZLE_64B layout.  (Reading aux straight from global touched 32 cache lines per load instruction - one per
+// Layers whose epilogue needs a second activation operand - gate layers (FC_EPI_GATE: out = aux * sigmoid(acc), the SE
+// excitation) and residual layers (FC_EPI_ADD_RELU with aux_epi) - run on a shortened operand ring and the upper part of
+// the ring area becomes a ring of AUX tiles: the [128 rows x 32 cols] hi / lo pieces of that operand, loaded by the
+// producer warp with TMA in the staging tiles' SWIZZLE_64B layout.  (For the residual layers this measured SLOWER than
+// residual K blocks on the tensor core - the MMA pipeline misses the two operand-ring stages - so aux_epi is off by default.)  (Reading aux straight from global touched 32 cache lines per load instruction - one per
 // accumulator row - and made se4.fc2 the slowest FC layer at 5 % tensor activity.)
 constexpr int GATE_AUX_SETS = 4;
 constexpr int GATE_AUX_SET_BYTES = 2 * EPI_UNIT_BYTES;       // hi + lo tile
@@ -83,7 +84,8 @@ constexpr uint16_t FC_W_IDENT = 0xFFFFu;   // schedule entry: A tile is a residu
 enum FcEpilogue : int {
   FC_EPI_LINEAR = 0,    // out = s*acc + b
   FC_EPI_RELU = 1,      // out = relu(s*acc + b)
-  FC_EPI_ADD_RELU = 2,  // out = relu(s*acc + b) where acc already holds S * residual (FC_W_IDENT schedule entries)
+  FC_EPI_ADD_RELU = 2,  // out = relu(s*acc + b + residual): acc already holds S * residual (FC_W_IDENT schedule entries; default),
+                        // or, with aux_epi = 1, the residual arrives through the aux ring and is added here (A/B knob)
   FC_EPI_GATE = 3,      // out = aux * sigmoid(acc)             (SE excitation)
   FC_EPI_HEAD = 4,      // h = relu(s*acc + b); logits = h . tail_w^T + tail_b   (fp32, no fp16 store)
 };
@@ -106,6 +108,7 @@ struct FcParams {
   const __half* aux;           // gate input rows (FC_EPI_GATE only)
   const __half* aux_lo;        // split mode: low part of aux (nullptr otherwise)
   int aux_kb;                  // 64-column blocks per row of the aux buffer
+  int aux_epi;                 // FC_EPI_ADD_RELU: 1 = the epilogue adds the residual from the aux ring (no FC_W_IDENT entries)
   __half* out;
   __half* out_lo;              // split mode: low part of the output (nullptr otherwise)
   int out_kb;                  // 64-column blocks per row of the output buffer
@@ -246,6 +249,8 @@ __device__ __forceinline__ void epi_tile_store(const P& p, const EpiStage& es, u
   const bool skip_out = (epi_debug(p) & 2) != 0;
   const bool staged = (mt + 1) * FC_TILE_M <= n_rows && !skip_out;
   const bool gate = p.epi == FC_EPI_GATE && gx != nullptr;
+  const bool resid = p.epi == FC_EPI_ADD_RELU && gx != nullptr;      // residual through the aux ring
+  const bool aux_on = gate || resid;
   const bool relu = p.epi == FC_EPI_RELU || p.epi == FC_EPI_ADD_RELU;
   const bool has_lo = p.out_lo != nullptr;
   const float rs = ((p.row_scale && row_ok) ? p.row_scale[row] : 1.0f) * p.acc_scale;
@@ -260,7 +265,7 @@ __device__ __forceinline__ void epi_tile_store(const P& p, const EpiStage& es, u
     return;
   }
   const uint32_t g0 = g;
-  const uint32_t ga0 = gate ? gx->ga : 0u;
+  const uint32_t ga0 = aux_on ? gx->ga : 0u;
   const int c_first = int((g0 & 1u) ^ grp);                  // first chunk of this tile with (g0 + c) & 1 == grp
   const uint32_t t_addr = t_col + (uint32_t(quad * 32) << 16) + uint32_t(sub * 16);
   uint32_t v[8];
@@ -269,7 +274,7 @@ __device__ __forceinline__ void epi_tile_store(const P& p, const EpiStage& es, u
   for (int c = c_first; c < n_chunks; c += 2) {
     uint4 ax[2] = {zero4, zero4}, axl[2] = {zero4, zero4};
     uint32_t aset = 0;
-    if (gate) {
+    if (aux_on) {
       // this chunk's gate input from the aux ring (both halves).  The set is handed back to the producer only after the
       // values have been USED (below): an mbarrier arrive is not ordered behind shared-memory loads still queued in the
       // LSU (here behind the partial tile's direct global stores), and the refill is an async-proxy write - released
@@ -310,14 +315,19 @@ __device__ __forceinline__ void epi_tile_store(const P& p, const EpiStage& es, u
       }
       f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
       f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
-      if (gate) {
+      if (aux_on) {
         const __half2* hh = reinterpret_cast<const __half2*>(&ax[h]);
         const __half2* hl = reinterpret_cast<const __half2*>(&axl[h]);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const float2 a = __half22float2(hh[i]), al = __half22float2(hl[i]);
-          f[2 * i] = (a.x + al.x) * fast_sigmoid(f[2 * i]);
-          f[2 * i + 1] = (a.y + al.y) * fast_sigmoid(f[2 * i + 1]);
+          if (gate) {
+            f[2 * i] = (a.x + al.x) * fast_sigmoid(f[2 * i]);
+            f[2 * i + 1] = (a.y + al.y) * fast_sigmoid(f[2 * i + 1]);
+          } else {
+            f[2 * i] += a.x + al.x;
+            f[2 * i + 1] += a.y + al.y;
+          }
         }
         if (h == 1) {             // both halves' aux registers have been consumed: the loads are complete
           __syncwarp();
@@ -360,7 +370,7 @@ __device__ __forceinline__ void epi_tile_store(const P& p, const EpiStage& es, u
     if (lane == 0) acc_release(empty, empty_remote);
   }
   if (staged) g = g0 + uint32_t(n_chunks);
-  if (gate) gx->ga = ga0 + uint32_t(n_chunks);
+  if (aux_on) gx->ga = ga0 + uint32_t(n_chunks);
 }
 
 // Head epilogue (FC_EPI_HEAD): h = relu(s*acc + b), logits = h . tail_w^T + tail_b in the thread that owns the row.
@@ -460,7 +470,7 @@ __global__ void __launch_bounds__(FC_THREADS, 1) fc_tcgen05_kernel(const __grid_
   const int lane = threadIdx.x & 31;
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
   const bool leader = rank == 0u;
-  const bool gate = p.epi == FC_EPI_GATE;
+  const bool gate = p.epi == FC_EPI_GATE || (p.epi == FC_EPI_ADD_RELU && p.aux_epi);    // layers that use the aux ring
   const int stages = gate ? (PAIR ? FC2_GATE_STAGES : FC_GATE_STAGES) : STAGES;   // operand ring depth of this layer
   const int worker = PAIR ? int(blockIdx.x >> 1) : int(blockIdx.x);        // index of this CTA (pair) among the workers
   const int n_workers = PAIR ? int(gridDim.x >> 1) : int(gridDim.x);
