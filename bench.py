@@ -279,14 +279,23 @@ def main():
         ms, launches = per_class[name]["ms_per_step"], max(per_class[name]["launches_per_step"], 1)
         ach = alg[name] / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
         iss = 2 * issued[name] / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
-        return {"kernel": name + "_kernel", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
-                "algorithmic_flops_per_launch": alg[name] / launches, "avg_launch_ms": ms / launches, "launches_per_step": launches,
-                "issued_tensor_tflops": iss, "issued_frac_of_peak": iss / peak_tf, "kernel_share_of_step": ms / total_ms}
+        e = {"kernel": name + "_kernel", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
+             "algorithmic_flops_per_launch": alg[name] / launches, "avg_launch_ms": ms / launches, "launches_per_step": launches,
+             "issued_tensor_tflops": iss, "issued_frac_of_peak": iss / peak_tf, "kernel_share_of_step": ms / total_ms}
+        # the same launches seen from the memory side: ncu-measured DRAM bytes of this class (profiles/r01_ncu_traffic.json,
+        # scaled to this step's rows) over the live CUDA-event time - most layers of the class are HBM-bound, five are not
+        tr = ncu_traffic(name, rows_total, launches)
+        if tr and ms > 0:
+            gbs = tr * launches / (ms * 1e-3) / 1e9
+            e["hbm_view"] = {"achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
+                             "dram_bytes_per_launch": tr}
+        return e
 
     roofline = {"bound": "tensor", **tensor_entry(dom), "traffic": ncu_traffic(dom, rows_total, per_class[dom]["launches_per_step"]),
                 "peak_source": peaks["source"] + ", sustained cuBLAS bf16 (kernel timed inside a long step)",
                 "note": "achieved counts live (non-padding) FLOPs once; fp16x3 issues three tensor products per live MAC plus "
-                        "block-Toeplitz padding - issued_* is what the tensor pipe actually executes",
+                        "block-Toeplitz padding - issued_* is what the tensor pipe actually executes; hbm_view is the same "
+                        "class against the HBM roofline (ncu DRAM bytes / live time): the big layers are tensor-bound, the rest HBM-bound",
                 "other_tensor_kernel": tensor_entry([k for k in alg if k != dom][0]),
                 "reference_equivalent_tflops_whole_step": flops_nominal / (ms_step * 1e-3) / 1e12}
     log(f"[b200] kernel classes per step: {json.dumps(per_class)}")
