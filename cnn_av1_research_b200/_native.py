@@ -78,6 +78,8 @@ SIGNATURES = {
     "av1p_flat_cascade_buffer": (C.c_void_p, [C.c_void_p, C.c_int32]),
     "av1p_threshold_sweep": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_double), C.c_int32, C.c_void_p, C.c_void_p,
                                        C.c_void_p]),
+    "av1p_ensemble_vote": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "av1p_fc_forward": (C.c_int, [C.POINTER(FcDesc), C.c_void_p]),
     "av1p_conv_res_forward": (C.c_int, [C.POINTER(ConvResDesc), C.c_void_p]),
     "av1p_profile_begin": (C.c_int, []),

@@ -578,4 +578,102 @@ __global__ void __launch_bounds__(256) threshold_sweep_kernel(const SweepParams 
     if (sm[i]) atomicAdd(&p.counts[i], (unsigned long long)sm[i]);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Ensemble voting over the logits of several Stage-3-AB models (reference pesquisa_v6/v6_pipeline/ensemble.py):
+//   mode 0  hard voting  (:57-79)  : per-model argmax (first maximum), majority class; torch.unique sorts the votes and
+//                                    counts.argmax() takes the first maximum, so ties go to the SMALLEST class id;
+//                                    confidence = majority count / n_models
+//   mode 1  soft voting  (:50-55)  : softmax per model (fp32), mean over models, argmax / max of the mean
+//   mode 2  weighted soft (:165-183): sum_m w_m * softmax_m with the caller's normalised weights
+// Optional outputs of predict_with_uncertainty (:83-116): mean / unbiased std of the probabilities over the models, the
+// share of models whose argmax equals the prediction, and all probabilities.  One thread per block row; k <= 8, M <= 8.
+constexpr int ENS_MAX_K = 8;
+constexpr int ENS_MAX_M = 8;
+struct EnsembleParams {
+  const float* logits;      // [M][n][k]
+  const float* weights;     // [M] (mode 2)
+  int n_models, n, k, mode;
+  long long* pred;          // [n]
+  float* conf;              // [n] or nullptr
+  float* mean_probs;        // [n][k] or nullptr
+  float* std_probs;         // [n][k] or nullptr
+  float* agreement;         // [n] or nullptr
+  float* all_probs;         // [M][n][k] or nullptr
+};
+__global__ void __launch_bounds__(256) ensemble_vote_kernel(const EnsembleParams p) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += gridDim.x * blockDim.x) {
+    float acc[ENS_MAX_K];
+    int votes[ENS_MAX_K], am[ENS_MAX_M];
+#pragma unroll
+    for (int c = 0; c < ENS_MAX_K; ++c) {
+      acc[c] = 0.f;
+      votes[c] = 0;
+    }
+    float prob[ENS_MAX_M][ENS_MAX_K];
+    for (int m = 0; m < p.n_models; ++m) {
+      const float* l = p.logits + (size_t(m) * p.n + i) * p.k;
+      float mx = l[0];
+      int best = 0;
+      for (int c = 1; c < p.k; ++c)
+        if (l[c] > mx) {             // strict: the first maximum wins, as torch.argmax
+          mx = l[c];
+          best = c;
+        }
+      am[m] = best;
+      votes[best] += 1;
+      float e[ENS_MAX_K], sum = 0.f;
+      for (int c = 0; c < p.k; ++c) {
+        e[c] = expf(l[c] - mx);
+        sum += e[c];
+      }
+      const float w = p.mode == 2 ? p.weights[m] : 1.0f;
+      for (int c = 0; c < p.k; ++c) {
+        const float q = e[c] / sum;
+        prob[m][c] = q;
+        acc[c] += p.mode == 2 ? q * w : q;
+        if (p.all_probs) p.all_probs[(size_t(m) * p.n + i) * p.k + c] = q;
+      }
+    }
+    if (p.mode != 2)
+      for (int c = 0; c < p.k; ++c) acc[c] = acc[c] / float(p.n_models);      // torch .mean(dim=0)
+    int pred = 0;
+    float conf = 0.f;
+    if (p.mode == 0) {
+      int top = votes[0];
+      for (int c = 1; c < p.k; ++c)
+        if (votes[c] > top) {
+          top = votes[c];
+          pred = c;
+        }
+      conf = float(top) / float(p.n_models);
+    } else {
+      conf = acc[0];
+      for (int c = 1; c < p.k; ++c)
+        if (acc[c] > conf) {
+          conf = acc[c];
+          pred = c;
+        }
+    }
+    p.pred[i] = pred;
+    if (p.conf) p.conf[i] = conf;
+    if (p.mean_probs)
+      for (int c = 0; c < p.k; ++c) p.mean_probs[size_t(i) * p.k + c] = acc[c];
+    if (p.std_probs) {
+      for (int c = 0; c < p.k; ++c) {
+        float s2 = 0.f;
+        for (int m = 0; m < p.n_models; ++m) {
+          const float d = prob[m][c] - acc[c];
+          s2 += d * d;
+        }
+        p.std_probs[size_t(i) * p.k + c] = p.n_models > 1 ? sqrtf(s2 / float(p.n_models - 1)) : nanf("");
+      }
+    }
+    if (p.agreement) {
+      int same = 0;
+      for (int m = 0; m < p.n_models; ++m) same += am[m] == pred;
+      p.agreement[i] = float(same) / float(p.n_models);
+    }
+  }
+}
+
 }  // namespace av1p

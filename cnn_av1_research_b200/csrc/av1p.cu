@@ -827,6 +827,34 @@ extern "C" int av1p_threshold_sweep(const float* logits, const uint8_t* labels, 
   return AV1P_OK;
 }
 
+// ------------------------------------------------------------------------------ ensemble voting ABI
+extern "C" int av1p_ensemble_vote(const float* logits, int32_t n_models, int32_t n, int32_t k, int32_t mode, const float* weights,
+                                  int64_t* pred, float* conf, float* mean_probs, float* std_probs, float* agreement,
+                                  float* all_probs, void* stream) {
+  if (n < 0 || n_models < 1 || n_models > ENS_MAX_M || k < 1 || k > ENS_MAX_K || mode < 0 || mode > 2 || (mode == 2 && !weights))
+    return fail(AV1P_EINVAL, "bad argument (1..%d models, 1..%d classes, mode 0/1/2, weights for mode 2)", ENS_MAX_M, ENS_MAX_K);
+  if (int rc = ensure_ctx()) return rc;
+  if (n == 0) return AV1P_OK;             // an empty batch has no buffers to check
+  if (!logits || !pred) return fail(AV1P_EINVAL, "null logits / predictions");
+  EnsembleParams ep{};
+  ep.logits = logits;
+  ep.weights = weights;
+  ep.n_models = n_models;
+  ep.n = n;
+  ep.k = k;
+  ep.mode = mode;
+  ep.pred = reinterpret_cast<long long*>(pred);
+  ep.conf = conf;
+  ep.mean_probs = mean_probs;
+  ep.std_probs = std_probs;
+  ep.agreement = agreement;
+  ep.all_probs = all_probs;
+  const int grid = std::min(ceil_div(n, 256), g_ctx.sms * 8);
+  ensemble_vote_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(ep);
+  CUDA_TRY(cudaGetLastError());
+  return AV1P_OK;
+}
+
 // ------------------------------------------------------------------------------ extraction ABI
 template <typename OUT>
 static int launch_extract(const uint16_t* y, int w, int h, int pitch, int bs, OUT* out, void* stream) {

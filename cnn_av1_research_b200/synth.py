@@ -120,3 +120,18 @@ def calibrated_state_dict(kind: str, seed: int = 0) -> Dict[str, torch.Tensor]:
 
 def calibrated_cascade(seed: int = 0) -> Dict[str, Dict[str, torch.Tensor]]:
     return {k: calibrated_state_dict(k, seed) for k in ("stage1", "stage2", "rect", "ab_fgvc")}
+
+
+def ensemble_state_dicts(n_models: int = 3, seed: int = 0):
+    """Member checkpoints for the Stage-3-AB ensemble tests (ensemble.py): the calibrated-random `ab` network plus copies
+    whose last linear layer is perturbed with seeded noise (30 % of its spread), i.e. diverse but sane members."""
+    base = calibrated_state_dict("ab", seed)
+    out = [base]
+    for i in range(1, n_models):
+        rng = np.random.Generator(np.random.PCG64(1000 + 17 * seed + i))
+        sd = {k: v.clone() for k, v in base.items()}
+        for key in ("head.head.6.weight", "head.head.6.bias"):
+            v = sd[key].numpy()
+            sd[key] = torch.from_numpy((v + 0.3 * max(float(v.std()), 1e-3) * rng.standard_normal(v.shape)).astype(np.float32))
+        out.append(sd)
+    return out

@@ -141,6 +141,17 @@ const void* av1p_flat_cascade_buffer(const av1p_flat_cascade* c, int32_t which);
 int av1p_threshold_sweep(const float* logits_dev, const uint8_t* labels_dev, int32_t n, const double* thresholds_host,
                          int32_t n_thresholds, float* probs_dev, uint64_t* counts_dev, void* stream);
 
+/* ---- ensemble voting over the logits of several Stage-3-AB models: replaces the voting inside ABEnsemble.predict /
+ *      predict_with_uncertainty and WeightedEnsemble.predict (pesquisa_v6/v6_pipeline/ensemble.py:29-116, 165-183).
+ *      logits_dev: float32 [n_models][n][k] (n_models <= 8, k <= 8).  mode 0 = hard (majority, ties to the smallest class
+ *      id as torch.unique + argmax give; conf = majority share), 1 = soft (mean of the per-model softmax), 2 = weighted
+ *      soft (weights_dev [n_models], already normalised).  pred_dev int64 [n]; conf_dev float32 [n]; the remaining outputs
+ *      are optional (NULL): mean_probs / std_probs [n][k] (unbiased std over the models), agreement [n], all_probs
+ *      [n_models][n][k]. */
+int av1p_ensemble_vote(const float* logits_dev, int32_t n_models, int32_t n, int32_t k, int32_t mode, const float* weights_dev,
+                       int64_t* pred_dev, float* conf_dev, float* mean_probs_dev, float* std_probs_dev, float* agreement_dev,
+                       float* all_probs_dev, void* stream);
+
 /* ---- measurement support (bench.py): bracket every kernel launch of the calling thread with CUDA
  *      events on its stream.  av1p_profile_end synchronises on those events and returns the summed
  *      device time and launch count per kernel class: 0 stem, 1 tcgen05 FC, 2 SAM gate, 3 FGVC tail,

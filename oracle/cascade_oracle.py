@@ -243,6 +243,37 @@ def threshold_confusion(logits1: torch.Tensor, labels_stage1: np.ndarray, thresh
     return out
 
 
+def ensemble_vote(all_logits: torch.Tensor, mode: str = "hard", weights: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+    """Voting of the Stage-3-AB ensembles (pesquisa_v6/v6_pipeline/ensemble.py) on stacked logits [models, B, classes].
+
+    "hard" (:57-79): per-model argmax, majority; the reference counts votes with torch.unique (sorted) and takes
+    counts.argmax(), i.e. ties go to the smallest class id; confidence = majority count / models.
+    "soft" (:50-55): mean of the per-model softmax, argmax / max.   "weighted" (:165-183): sum of softmax * normalised weight.
+    Also returns the predict_with_uncertainty outputs (:83-116) for the soft prediction."""
+    m, b, k = all_logits.shape
+    probs = torch.softmax(all_logits, dim=-1)
+    preds_m = all_logits.argmax(dim=-1)                                      # [m, b]
+    out: Dict[str, torch.Tensor] = {}
+    if mode == "hard":
+        counts = torch.stack([(preds_m == c).sum(dim=0) for c in range(k)], dim=1)     # [b, k]
+        out["predictions"] = counts.argmax(dim=1)                            # first maximum = smallest class among ties
+        out["confidences"] = counts.max(dim=1)[0].float() / m
+    elif mode == "soft":
+        avg = probs.mean(dim=0)
+        out["predictions"], out["confidences"] = avg.argmax(dim=-1), avg.max(dim=-1)[0]
+    elif mode == "weighted":
+        w = weights / weights.sum()
+        avg = (probs * w.view(-1, 1, 1)).sum(dim=0)
+        out["predictions"], out["confidences"] = avg.argmax(dim=-1), avg.max(dim=-1)[0]
+    else:
+        raise ValueError(mode)
+    mean_probs = probs.mean(dim=0)
+    soft_pred = mean_probs.argmax(dim=-1)
+    out.update(mean_probs=mean_probs, std_probs=probs.std(dim=0), all_probs=probs,
+               agreement=(preds_m == soft_pred.unsqueeze(0)).float().mean(dim=0))
+    return out
+
+
 def frames_to_images(frame_words: np.ndarray, n_frames: int, width: int, height: int) -> torch.Tensor:
     """Reference data path from a planar YUV420p10le buffer to predict()'s input tensor:
     read luma (005:142-212) -> tile (005:353-457) -> /1023 (data_hub.py:70-77); frames concatenated."""

@@ -18,8 +18,9 @@ def main():
     from cnn_av1_research_b200.testing import build_pipeline, frames_tensor
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
-    w, h = 3840, 2160
-    n = frames * (w // 16) * (h // 16)
+    w = int(sys.argv[3]) if len(sys.argv) > 3 else 3840
+    h = int(sys.argv[4]) if len(sys.argv) > 4 else 2160
+    n = frames * (-(-w // 16)) * (-(-h // 16))
     fr = frames_tensor(synth.synth_frames(frames, w, h, seed=77), dev)
     pipe = build_pipeline(seed=0, threshold=0.45, device=dev, capacity_blocks=n)
     first = None
