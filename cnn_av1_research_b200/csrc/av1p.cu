@@ -333,7 +333,7 @@ extern "C" int av1p_model_create(const void* blob, size_t bytes, av1p_model** ou
     }
     if (op.type == AV1P_OP_FC) {
       if (op.n_tiles < 1 || op.n_tiles > FC_MAX_NT || op.block_n < 32 || op.block_n > FC_MAX_N || op.block_n % 32 ||
-          op.n_kb_total < 1 || op.n_kb_total > FC_MAX_KB || op.tail_n > FC_TAIL_MAX || op.n_w_chunks < 1 ||
+          op.n_kb_total < 1 || op.n_kb_total > AV1P_BLOB_MAX_KB || op.tail_n > FC_TAIL_MAX || op.n_w_chunks < 1 ||
           op.w_off + uint64_t(op.n_w_chunks) * op.block_n * 128 > bytes) {
         delete m;
         return fail(AV1P_EINVAL, "malformed FC op");

@@ -43,7 +43,7 @@ constexpr int FC2_W_BYTES = FC_W_BYTES / 2;                  // 16 KB
 constexpr int FC2_STAGE_BYTES = FC_A_BYTES + FC2_W_BYTES;    // 32 KB
 static_assert(FC2_STAGES * FC2_STAGE_BYTES == FC_STAGES * FC_STAGE_BYTES, "both variants share one shared-memory layout");
 constexpr int FC_MAX_NT = 8;           // N tiles per layer
-constexpr int FC_MAX_KB = 128;         // scheduled K blocks per layer (sum over N tiles)
+constexpr int FC_MAX_KB = 192;         // scheduled K blocks per layer (sum over N tiles), incl. the residual entries added at plan time
 constexpr int FC_MAX_SRC = 4;          // activation sources per layer
 constexpr int FC_TAIL_MAX = 8;         // outputs of the in-epilogue final linear (7 for the flatten head)
 constexpr int FC_EPI_WARPS = 16;         // four per TMEM lane quadrant: 8 of every 32 staged columns each

@@ -143,8 +143,12 @@ class HierarchicalPipelineV6:
         consumed = [None, None]
         with torch.cuda.device(dev):
             self._copy_stream.wait_stream(main)
-            for ci, f0 in enumerate(range(0, n_frames, chunk)):
-                nf = min(chunk, n_frames - f0)
+            # Ramp: the first cascade cannot start before its frames have crossed PCIe, so the first chunk is a quarter of
+            # the regular size (its upload is the only one that is not hidden behind a cascade).
+            first = max(1, chunk // 4) if n_frames > chunk else chunk
+            starts = [0] + list(range(first, n_frames, chunk))
+            for ci, f0 in enumerate(starts):
+                nf = min(first if ci == 0 else chunk, n_frames - f0)
                 b = ci & 1
                 if consumed[b] is not None:
                     self._copy_stream.wait_event(consumed[b])          # the cascade that read this buffer has finished
