@@ -7,7 +7,7 @@ from .fileio import (load_block_file, predict_yuv_file, read_frames_yuv420p10, r
                      save_blocks_binary_10bit)
 from .flatten import (FlattenPipeline, evaluate_with_threshold, remap_flatten_to_original, run_pipeline_inference,
                       sweep_thresholds)
-from .models import (CosineClassifier, FGVCModel, ImprovedBackbone, SEBlock, SpatialAttention, Stage1BinaryHead,
+from .models import (AdapterModule, Stage2ModelWithAdapters, CosineClassifier, FGVCModel, ImprovedBackbone, SEBlock, SpatialAttention, Stage1BinaryHead,
                      Stage1Model, Stage2FlatModel, Stage2Model, Stage2ThreeWayHead, Stage3ABHead, Stage3ABModel,
                      Stage3RectHead, Stage3RectModel)
 from .pipeline import HierarchicalPipelineV6, evaluate_pipeline
@@ -19,5 +19,6 @@ __all__ = [
     "Stage3ABModel", "Stage3RectHead", "Stage3RectModel", "HierarchicalPipelineV6", "evaluate_pipeline",
     "Stage2FlatModel", "FlattenPipeline", "run_pipeline_inference", "remap_flatten_to_original",
     "evaluate_with_threshold", "sweep_thresholds", "read_y_component_10bit_lossless", "read_frames_yuv420p10",
-    "predict_yuv_file", "save_blocks_binary_10bit", "load_block_file", "ABEnsemble", "WeightedEnsemble",
+    "predict_yuv_file", "save_blocks_binary_10bit", "load_block_file", "ABEnsemble", "WeightedEnsemble", "AdapterModule",
+    "Stage2ModelWithAdapters",
 ]

@@ -455,7 +455,8 @@ int plan_stage(const av1p_model* m, const ActLayout& L, uint8_t* act_base, av1p_
         f.block_n = op.block_n;
         f.epi = op.epi;
         f.bias = reinterpret_cast<const float*>(at(op.bias_off));
-        f.row_scale = op.use_row_scale ? s->row_scale : nullptr;
+        f.row_scale = (op.use_row_scale & 1) ? s->row_scale : nullptr;
+        f.aux_row_scale = (op.use_row_scale & 2) ? s->row_scale : nullptr;
         f.acc_scale = op.f0;
         f.pair_mode = op.pair_mode;
         if (op.pair_mode) {
@@ -474,7 +475,7 @@ int plan_stage(const av1p_model* m, const ActLayout& L, uint8_t* act_base, av1p_
         f.tail_b = reinterpret_cast<const float*>(at(op.tail_b_off));
         f.tail_n = op.tail_n;
         f.err_flag = g_ctx.watchdog_dev;
-        if ((op.epi == FC_EPI_ADD_RELU || op.epi == FC_EPI_GATE) && !f.aux) return fail(AV1P_EINVAL, "FC op needs aux");
+        if ((op.epi == FC_EPI_ADD_RELU || op.epi == FC_EPI_GATE || op.epi == FC_EPI_ADD) && !f.aux) return fail(AV1P_EINVAL, "FC op needs aux");
         if (op.epi == FC_EPI_HEAD && (!f.tail_w || !f.tail_b || op.n_tiles != 1 || op.tail_n < 1))
           return fail(AV1P_EINVAL, "malformed head op");
         if (op.epi != FC_EPI_HEAD && op.n_tiles * op.block_n > f.out_kb * 64) return fail(AV1P_EINVAL, "FC output wider than its buffer");
@@ -492,7 +493,7 @@ int plan_stage(const av1p_model* m, const ActLayout& L, uint8_t* act_base, av1p_
           if (op.out_lo >= 0)
             if (int rc = make_act_map(&f.out_map[1], buf(op.out_lo), L.cols[op.out_lo], L.cap, true)) return rc;
         }
-        if (op.epi == FC_EPI_GATE) {
+        if (op.epi == FC_EPI_GATE || op.epi == FC_EPI_ADD) {
           if (op.n_tiles * op.block_n > int(L.cols[op.aux])) return fail(AV1P_EINVAL, "gate input narrower than the FC output");
           if (int rc = make_act_map(&f.aux_map[0], buf(op.aux), L.cols[op.aux], L.cap, true)) return rc;
           if (op.aux_lo >= 0)
@@ -1159,7 +1160,7 @@ extern "C" int av1p_fc_forward(const av1p_fc_desc* d, void* stream) {
     if (d->out_lo_dev)
       if (int rc = make_act_map(&f.out_map[1], d->out_lo_dev, uint64_t(d->out_ld), uint64_t(d->rows), true)) return rc;
   }
-  if (d->epi == FC_EPI_GATE) {
+  if (d->epi == FC_EPI_GATE || d->epi == FC_EPI_ADD) {
     if (!d->aux_dev || d->aux_ld < d->n_tiles * d->block_n) return fail(AV1P_EINVAL, "gate input missing or too narrow");
     if (int rc = make_act_map(&f.aux_map[0], d->aux_dev, uint64_t(d->aux_ld), uint64_t(d->rows), true)) return rc;
     if (d->aux_lo_dev)

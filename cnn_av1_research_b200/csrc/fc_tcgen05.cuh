@@ -88,6 +88,8 @@ enum FcEpilogue : int {
                         // or, with aux_epi = 1, the residual arrives through the aux ring and is added here (A/B knob)
   FC_EPI_GATE = 3,      // out = aux * sigmoid(acc)             (SE excitation)
   FC_EPI_HEAD = 4,      // h = relu(s*acc + b); logits = h . tail_w^T + tail_b   (fp32, no fp16 store)
+  FC_EPI_ADD = 5,       // out = s*acc + b + r * aux, no ReLU (adapter up-projection + skip, models.py:292-310); aux arrives
+                        // through the aux ring; r = aux_row_scale[row] (the spatial-attention scalar) or 1
 };
 
 struct FcParams {
@@ -104,6 +106,7 @@ struct FcParams {
   int epi;
   const float* bias;           // [n_tiles*block_n] or nullptr
   const float* row_scale;      // [rows] or nullptr (spatial-attention scalar folded into the next linear)
+  const float* aux_row_scale;  // FC_EPI_ADD: [rows] scale of the aux operand, or nullptr
   float acc_scale;             // power of two undoing the weight pre-scale
   const __half* aux;           // gate input rows (FC_EPI_GATE only)
   const __half* aux_lo;        // split mode: low part of aux (nullptr otherwise)
@@ -249,11 +252,13 @@ __device__ __forceinline__ void epi_tile_store(const P& p, const EpiStage& es, u
   const bool skip_out = (epi_debug(p) & 2) != 0;
   const bool staged = (mt + 1) * FC_TILE_M <= n_rows && !skip_out;
   const bool gate = p.epi == FC_EPI_GATE && gx != nullptr;
-  const bool resid = p.epi == FC_EPI_ADD_RELU && gx != nullptr;      // residual through the aux ring
+  const bool resid = (p.epi == FC_EPI_ADD_RELU || p.epi == FC_EPI_ADD) && gx != nullptr;      // residual through the aux ring
   const bool aux_on = gate || resid;
   const bool relu = p.epi == FC_EPI_RELU || p.epi == FC_EPI_ADD_RELU;
   const bool has_lo = p.out_lo != nullptr;
   const float rs = ((p.row_scale && row_ok) ? p.row_scale[row] : 1.0f) * p.acc_scale;
+  float ars = 1.0f;                 // scale of the aux operand (FC_EPI_ADD after spatial attention)
+  if constexpr (requires { p.aux_row_scale; }) ars = (p.aux_row_scale && row_ok) ? p.aux_row_scale[row] : 1.0f;
   const int n_chunks = block_n / EPI_CHUNK;
   const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
   mbar_wait(full, full_phase, p.err_flag, tag);
@@ -325,8 +330,8 @@ __device__ __forceinline__ void epi_tile_store(const P& p, const EpiStage& es, u
             f[2 * i] = (a.x + al.x) * fast_sigmoid(f[2 * i]);
             f[2 * i + 1] = (a.y + al.y) * fast_sigmoid(f[2 * i + 1]);
           } else {
-            f[2 * i] += a.x + al.x;
-            f[2 * i + 1] += a.y + al.y;
+            f[2 * i] = fmaf(ars, a.x + al.x, f[2 * i]);
+            f[2 * i + 1] = fmaf(ars, a.y + al.y, f[2 * i + 1]);
           }
         }
         if (h == 1) {             // both halves' aux registers have been consumed: the loads are complete
@@ -470,7 +475,7 @@ __global__ void __launch_bounds__(FC_THREADS, 1) fc_tcgen05_kernel(const __grid_
   const int lane = threadIdx.x & 31;
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
   const bool leader = rank == 0u;
-  const bool gate = p.epi == FC_EPI_GATE || (p.epi == FC_EPI_ADD_RELU && p.aux_epi);    // layers that use the aux ring
+  const bool gate = p.epi == FC_EPI_GATE || p.epi == FC_EPI_ADD || (p.epi == FC_EPI_ADD_RELU && p.aux_epi);    // layers that use the aux ring
   const int stages = gate ? (PAIR ? FC2_GATE_STAGES : FC_GATE_STAGES) : STAGES;   // operand ring depth of this layer
   const int worker = PAIR ? int(blockIdx.x >> 1) : int(blockIdx.x);        // index of this CTA (pair) among the workers
   const int n_workers = PAIR ? int(gridDim.x >> 1) : int(gridDim.x);

@@ -231,6 +231,49 @@ class Stage2Model(_NativeStageModule):
         return self._native_forward(x)
 
 
+class AdapterModule(nn.Module):
+    """models.py:258-310: residual adapter x + up(relu(down(mean_hw(x)))).  Keys: down_proj.{weight,bias}, up_proj.{weight,bias}."""
+
+    def __init__(self, in_dim: int, bottleneck_dim: int = 64, dropout: float = 0.1):
+        super().__init__()
+        self.down_proj = nn.Linear(in_dim, bottleneck_dim)
+        self.activation = nn.ReLU()
+        self.dropout = nn.Dropout(dropout)
+        self.up_proj = nn.Linear(bottleneck_dim, in_dim)
+        nn.init.normal_(self.down_proj.weight, std=1e-3)          # near-identity start, as the reference (:287-292)
+        nn.init.normal_(self.up_proj.weight, std=1e-3)
+        nn.init.zeros_(self.down_proj.bias)
+        nn.init.zeros_(self.up_proj.bias)
+
+
+class Stage2ModelWithAdapters(_NativeStageModule):
+    """models.py:313-433: Stage-2 network with an adapter after every backbone layer (eval-mode inference only: the
+    freezing / parameter counting of the reference's constructor concerns training).  bottleneck_dim <= 64."""
+    _kind = "stage2_adapters"
+
+    def __init__(self, pretrained: bool = True, bottleneck_dim: int = 64, adapter_dropout: float = 0.1,
+                 load_stage1_backbone: Optional[str] = None):
+        super().__init__()
+        if bottleneck_dim > 64:
+            raise ValueError("the B200 path supports adapter bottlenecks up to 64")
+        self.backbone = ImprovedBackbone(pretrained)
+        if load_stage1_backbone:                                  # models.py:347-366
+            ckpt = torch.load(load_stage1_backbone, map_location="cpu", weights_only=False)
+            state = ckpt["model_state_dict"] if isinstance(ckpt, dict) and "model_state_dict" in ckpt else ckpt
+            self.backbone.load_state_dict({k.replace("backbone.", ""): v for k, v in state.items() if k.startswith("backbone.")},
+                                          strict=False)
+        for param in self.backbone.parameters():
+            param.requires_grad = False
+        self.adapter_layer1 = AdapterModule(64, bottleneck_dim, adapter_dropout)
+        self.adapter_layer2 = AdapterModule(128, bottleneck_dim, adapter_dropout)
+        self.adapter_layer3 = AdapterModule(256, bottleneck_dim, adapter_dropout)
+        self.adapter_layer4 = AdapterModule(512, bottleneck_dim, adapter_dropout)
+        self.head = Stage2ThreeWayHead()
+
+    def forward(self, x):
+        return self._native_forward(x)
+
+
 class Stage3RectModel(_NativeStageModule):
     """models.py:230-239."""
     _kind = "rect"

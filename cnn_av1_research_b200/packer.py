@@ -33,10 +33,10 @@ MAX_KB = 128
 TILE_K = 64
 
 OP_STEM, OP_FC, OP_SAM, OP_FGVC_TAIL, OP_SE, OP_CONV_RES = 0, 1, 2, 3, 4, 5
-EPI_LINEAR, EPI_RELU, EPI_ADD_RELU, EPI_GATE, EPI_HEAD = 0, 1, 2, 3, 4
+EPI_LINEAR, EPI_RELU, EPI_ADD_RELU, EPI_GATE, EPI_HEAD, EPI_ADD = 0, 1, 2, 3, 4, 5
 
-STAGE_KINDS = {"stage1": 0, "stage2": 1, "rect": 2, "ab_fgvc": 3, "ab": 4, "flat7": 5}
-NUM_OUTPUTS = {"stage1": 1, "stage2": 3, "rect": 2, "ab_fgvc": 4, "ab": 4, "flat7": 7}
+STAGE_KINDS = {"stage1": 0, "stage2": 1, "rect": 2, "ab_fgvc": 3, "ab": 4, "flat7": 5, "stage2_adapters": 6}
+NUM_OUTPUTS = {"stage1": 1, "stage2": 3, "rect": 2, "ab_fgvc": 4, "ab": 4, "flat7": 7, "stage2_adapters": 3}
 
 BN_EPS = 1e-5
 
@@ -120,7 +120,7 @@ class _Op:
 
 
 def _make_fc_op_n(name: str, dense: Sequence[np.ndarray], srcs: Sequence[str], out: Optional[str], bias: Optional[np.ndarray],
-                  epi: int, block_n: int, precision: str, aux: Optional[str] = None, use_row_scale: bool = False,
+                  epi: int, block_n: int, precision: str, aux: Optional[str] = None, use_row_scale: int = 0,
                tail_w: Optional[np.ndarray] = None, tail_b: Optional[np.ndarray] = None) -> _Op:
     """Tile dense matrices D_s [N, K_s] (one per activation source) into the block-sparse schedule.
 
@@ -239,8 +239,16 @@ def _block_n(n: int) -> int:
     return 256 if n >= 256 else -(-n // 32) * 32
 
 
-def backbone_ops(sd, precision: str = "fp16x3", prefix: str = "backbone.", layer1_fc: bool = False) -> List[_Op]:
-    """Op program for ImprovedBackbone.forward (models.py:104-121).  Result: x4' in C1, SAM scalar in row_scale."""
+def backbone_ops(sd, precision: str = "fp16x3", prefix: str = "backbone.", layer1_fc: bool = False,
+                 adapters: bool = False) -> List[_Op]:
+    """Op program for ImprovedBackbone.forward (models.py:104-121).  Result: x4' in C1, SAM scalar in row_scale.
+
+    adapters=True: Stage2ModelWithAdapters.forward (models.py:380-433) - an AdapterModule (:258-310) after every layer's
+    SE block (after spatial attention for layer4): x + up(relu(down(mean_hw(x)))), the same vector added at every
+    position.  Two FC ops per adapter: the spatial mean is folded into the down-projection (as for squeeze-excite), the
+    up-projection is tiled over the positions and its epilogue adds the skip from the aux ring (EPI_ADD, no ReLU).  After
+    layer4 the skip is the attention-scaled map, so the down-projection reads its input with the row scale and the
+    epilogue scales the aux operand with it (use_row_scale bit 1); the result (no row scale left) is in C2."""
     p = prefix
     ops: List[_Op] = []
     # --- stem: conv1 + bn1 (+ relu + maxpool in the kernel's epilogue).  The 64 x 49 folded weights are the
@@ -301,15 +309,36 @@ def backbone_ops(sd, precision: str = "fp16x3", prefix: str = "backbone.", layer
             return make_fc_op(f"{unit}.{conv}", [d], [src], out, np.tile(bf, ho * ho), epi, 256, precision, **kw)
         return make_conv_res_op(f"{unit}.{conv}", wf, bf, src, out, epi, precision, aux=aux)
 
+    def adapter(layer: int, grid: int, src: str, dst: str, scaled: bool = False):
+        a = f"adapter_layer{layer}"
+        wd, bd = _np64(sd[a + ".down_proj.weight"]), _np64(sd[a + ".down_proj.bias"])      # [bott, C], [bott]
+        wu, bu = _np64(sd[a + ".up_proj.weight"]), _np64(sd[a + ".up_proj.bias"])          # [C, bott], [C]
+        npos = grid * grid
+        assert wd.shape[0] <= 64, "adapter bottleneck wider than the 64-column scratch buffer"
+        d1 = np.zeros((64, npos * wd.shape[1]))
+        d1[: wd.shape[0]] = np.tile(wd / npos, (1, npos))
+        b1 = np.zeros(64)
+        b1[: wd.shape[0]] = bd
+        d2 = np.zeros((npos * wu.shape[0], 64))
+        d2[:, : wu.shape[1]] = np.tile(wu, (npos, 1))
+        ops.append(make_fc_op(a + ".down", [d1], [src], "H", b1, EPI_RELU, 64, precision, use_row_scale=1 if scaled else 0))
+        ops.append(make_fc_op(a + ".up+skip", [d2], ["H"], dst, np.tile(bu, npos), EPI_ADD, _block_n(d2.shape[0]), precision, aux=src,
+                              use_row_scale=2 if scaled else 0))
+
     ops.append(l1(p + "layer1.0", "conv1", "bn1", "B0", "B1", EPI_RELU))
     ops.append(l1(p + "layer1.0", "conv2", "bn2", "B1", "B2", EPI_ADD_RELU, aux="B0"))
     ops.append(l1(p + "layer1.1", "conv1", "bn1", "B2", "B1", EPI_RELU))
     ops.append(l1(p + "layer1.1", "conv2", "bn2", "B1", "B0", EPI_ADD_RELU, aux="B2"))
     se(1, 4, "B0", "B1")                                         # x1 = B1
+    x1 = "B1"
+    if adapters:
+        adapter(1, 4, "B1", "B2")
+        x1 = "B2"
 
     # --- layers 2..4: (input buffer, grid in, three scratch buffers of the output width)
-    plan = ((2, "B1", 4, ("C0", "C1", "C2")), (3, "C0", 2, ("D0", "D1", "D2")), (4, "D0", 1, ("C1", "C2", "C0")))
-    for layer, x_in, grid, (t0, t1, t2) in plan:
+    x_next = x1
+    for layer, grid, (t0, t1, t2) in ((2, 4, ("C0", "C1", "C2")), (3, 2, ("D0", "D1", "D2")), (4, 1, ("C1", "C2", "C0"))):
+        x_in = x_next
         u = f"{p}layer{layer}.0"
         d, b, g_out = conv_bn(u, "conv1", "bn1", grid, 2)
         ops.append(make_fc_op(u + ".conv1", [d], [x_in], t0, b, EPI_RELU, _block_n(d.shape[0]), precision))
@@ -322,11 +351,17 @@ def backbone_ops(sd, precision: str = "fp16x3", prefix: str = "backbone.", layer
         d, b, _ = conv_bn(u, "conv2", "bn2", g_out, 1)
         ops.append(make_fc_op(u + ".conv2", [d], [t0], t2, b, EPI_ADD_RELU, _block_n(d.shape[0]), precision, aux=t1))
         se(layer, g_out, t2, t0)                                 # x_layer = t0
+        x_next = t0
+        if adapters and layer < 4:
+            adapter(layer, g_out, t0, t1)                        # x_layer + adapter = t1
+            x_next = t1
     # after layer4: x4' = C1 (t0 of the last plan row)
     # --- spatial attention at 1x1: centre tap of the 7x7 kernel only (models.py:56-61)
     wsa = _np64(sd[p + "spatial_attn.conv.weight"])
     ops.append(_Op(OP_SAM, src=[_hi("C1"), _lo("C1", precision), -1, -1], f0=float(wsa[0, 0, 3, 3]), f1=float(wsa[0, 1, 3, 3]),
                    name="spatial_attn"))
+    if adapters:
+        adapter(4, 1, "C1", "C2", scaled=True)                   # s * x4' + adapter(s * x4') = C2, no row scale left
     return ops
 
 
@@ -337,23 +372,24 @@ def head_ops(kind: str, sd, precision: str = "fp16x3") -> List[_Op]:
     if kind == "stage1":
         w0, b0 = lin(0)
         w1, b1 = lin(3)
-        ops.append(make_fc_op("head.0+3", [w0], ["C1"], None, b0, EPI_HEAD, 256, precision, use_row_scale=True, tail_w=w1, tail_b=b1))
-    elif kind in ("stage2", "ab", "rect"):
+        ops.append(make_fc_op("head.0+3", [w0], ["C1"], None, b0, EPI_HEAD, 256, precision, use_row_scale=1, tail_w=w1, tail_b=b1))
+    elif kind in ("stage2", "ab", "rect", "stage2_adapters"):
         w0, b0 = lin(0)
         w1, b1 = lin(3)
         w2, b2 = lin(6)
-        ops.append(make_fc_op("head.0", [w0], ["C1"], "D0", b0, EPI_RELU, _block_n(w0.shape[0]), precision, use_row_scale=True))
+        feat, scaled = ("C2", 0) if kind == "stage2_adapters" else ("C1", 1)    # the last adapter already applied the attention scalar
+        ops.append(make_fc_op("head.0", [w0], [feat], "D0", b0, EPI_RELU, _block_n(w0.shape[0]), precision, use_row_scale=scaled))
         # head.3 reads the first w0.shape[0] columns of D0
         ops.append(make_fc_op("head.3+6", [w1], ["D0"], None, b1, EPI_HEAD, _block_n(w1.shape[0]), precision, tail_w=w2, tail_b=b2))
     elif kind == "flat7":
         # Stage2FlatModel head (008b_run_pipeline_flatten_eval.py:120-127): Dropout, Linear(512,256), BN1d, ReLU, Dropout, Linear(256,7)
         w0, b0 = fold_bn(_np64(sd["head.1.weight"]), _np64(sd["head.1.bias"]), sd, "head.2")
         w1, b1 = _np64(sd["head.5.weight"]), _np64(sd["head.5.bias"])
-        ops.append(make_fc_op("head.1+2+5", [w0], ["C1"], None, b0, EPI_HEAD, 256, precision, use_row_scale=True, tail_w=w1, tail_b=b1))
+        ops.append(make_fc_op("head.1+2+5", [w0], ["C1"], None, b0, EPI_HEAD, 256, precision, use_row_scale=1, tail_w=w1, tail_b=b1))
     elif kind == "ab_fgvc":
         w0, b0 = fold_bn(_np64(sd["feat_proj.0.weight"]), _np64(sd["feat_proj.0.bias"]), sd, "feat_proj.1")
         w1, b1 = fold_bn(_np64(sd["feat_proj.4.weight"]), _np64(sd["feat_proj.4.bias"]), sd, "feat_proj.5")
-        ops.append(make_fc_op("feat_proj.0+1", [w0], ["C1"], "C0", b0, EPI_RELU, 256, precision, use_row_scale=True))
+        ops.append(make_fc_op("feat_proj.0+1", [w0], ["C1"], "C0", b0, EPI_RELU, 256, precision, use_row_scale=1))
         ops.append(make_fc_op("feat_proj.4+5", [w1], ["C0"], "C2", b1, EPI_RELU, 256, precision))
         wc = _np64(sd["classifier.weight"])
         wc = wc / np.maximum(np.linalg.norm(wc, axis=1, keepdims=True), 1e-12)    # F.normalize(weight)
@@ -421,7 +457,8 @@ def pack_stage(kind: str, state_dict, precision: str = "fp16x3", layer1_fc: bool
         raise ValueError(f"unknown stage kind {kind!r}")
     if precision not in PRECISIONS:
         raise ValueError(f"unknown precision {precision!r}")
-    return serialise(kind, backbone_ops(state_dict, precision, layer1_fc=layer1_fc) + head_ops(kind, state_dict, precision), precision)
+    return serialise(kind, backbone_ops(state_dict, precision, layer1_fc=layer1_fc, adapters=kind == "stage2_adapters")
+                     + head_ops(kind, state_dict, precision), precision)
 
 
 def blob_stats(blob: bytes) -> Dict[str, float]:

@@ -135,3 +135,25 @@ def ensemble_state_dicts(n_models: int = 3, seed: int = 0):
             sd[key] = torch.from_numpy((v + 0.3 * max(float(v.std()), 1e-3) * rng.standard_normal(v.shape)).astype(np.float32))
         out.append(sd)
     return out
+
+
+def adapter_state_dict(seed: int = 0):
+    """Checkpoint for Stage2ModelWithAdapters (models.py:313-433): the calibrated-random Stage-2 network plus seeded adapter
+    weights large enough to matter (the reference initialises adapters near zero, :287-292, i.e. as the identity)."""
+    from . import models as M
+    sd = dict(calibrated_state_dict("stage2", seed))
+    rng = np.random.Generator(np.random.PCG64(4000 + seed))
+    ref = M.Stage2ModelWithAdapters(pretrained=False).state_dict()
+    for key, t in ref.items():
+        if not key.startswith("adapter_layer"):
+            assert key in sd, key
+            continue
+        shape = tuple(t.shape)
+        if key.endswith("down_proj.weight"):
+            v = rng.normal(0.0, 1.0 / np.sqrt(shape[1]), shape)
+        elif key.endswith("up_proj.weight"):
+            v = rng.normal(0.0, 0.5 / np.sqrt(shape[1]), shape)
+        else:
+            v = rng.normal(0.0, 0.05, shape)
+        sd[key] = torch.from_numpy(v.astype(np.float32))
+    return sd

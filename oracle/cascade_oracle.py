@@ -97,8 +97,17 @@ def _squeeze_excite(x: torch.Tensor, sd: StateDict, name: str) -> torch.Tensor:
     return x * s[:, :, None, None]
 
 
-def backbone_features(sd: StateDict, x: torch.Tensor, prefix: str = "backbone.") -> torch.Tensor:
-    """ImprovedBackbone.forward (models.py:104-126): [B,1,16,16] fp32 -> [B,512]."""
+def _adapter(x: torch.Tensor, sd: StateDict, name: str) -> torch.Tensor:
+    """AdapterModule.forward (models.py:294-310), eval mode: x + up(relu(down(mean_hw(x)))) broadcast over the positions."""
+    a = F.linear(x.mean(dim=[2, 3]), sd[name + ".down_proj.weight"], sd[name + ".down_proj.bias"])
+    a = F.linear(F.relu(a), sd[name + ".up_proj.weight"], sd[name + ".up_proj.bias"])
+    return x + a.view(x.shape[0], x.shape[1], 1, 1)
+
+
+def backbone_features(sd: StateDict, x: torch.Tensor, prefix: str = "backbone.", adapters: bool = False) -> torch.Tensor:
+    """ImprovedBackbone.forward (models.py:104-126): [B,1,16,16] fp32 -> [B,512].
+    adapters=True: the layer sequence of Stage2ModelWithAdapters.forward (models.py:380-433) - an adapter after se1..se3 and
+    after the spatial attention."""
     p = prefix
     x = F.conv2d(x, sd[p + "conv1.weight"], None, stride=2, padding=3)
     x = F.relu(_bn(x, sd, p + "bn1"))
@@ -107,10 +116,14 @@ def backbone_features(sd: StateDict, x: torch.Tensor, prefix: str = "backbone.")
         x = _residual_unit(x, sd, f"{p}layer{layer}.0", stride)
         x = _residual_unit(x, sd, f"{p}layer{layer}.1", 1)
         x = _squeeze_excite(x, sd, f"{p}se{layer}")
+        if adapters and layer < 4:
+            x = _adapter(x, sd, f"adapter_layer{layer}")
     # SpatialAttention (models.py:56-61)
     att = torch.cat([x.mean(dim=1, keepdim=True), x.max(dim=1, keepdim=True).values], dim=1)
     att = F.conv2d(att, sd[p + "spatial_attn.conv.weight"], None, padding=3)
     x = x * torch.sigmoid(att)
+    if adapters:
+        x = _adapter(x, sd, "adapter_layer4")
     return torch.flatten(F.adaptive_avg_pool2d(x, 1), 1)
 
 
@@ -129,10 +142,13 @@ def stage_logits(kind: str, sd: StateDict, x: torch.Tensor) -> torch.Tensor:
     kind: 'stage1' (models.py:129-149,206-215; apply_temp=False so no temperature division),
           'stage2' (:152-167), 'rect' (:170-185), 'ab' (Stage3ABModel :188-203),
           'ab_fgvc' (scripts/006_train_stage3_ab_fgvc.py:217-297),
-          'flat7' (Stage2FlatModel, scripts/008b_run_pipeline_flatten_eval.py:110-132).
+          'flat7' (Stage2FlatModel, scripts/008b_run_pipeline_flatten_eval.py:110-132),
+          'stage2_adapters' (Stage2ModelWithAdapters, models.py:313-433).
     """
     with torch.no_grad():
-        f = backbone_features(sd, x)
+        f = backbone_features(sd, x, adapters=kind == "stage2_adapters")
+        if kind == "stage2_adapters":
+            return _mlp_head(sd, f, (0, 3, 6))
         if kind == "stage1":
             return _mlp_head(sd, f, (0, 3))
         if kind in ("stage2", "rect", "ab"):

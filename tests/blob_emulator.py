@@ -85,13 +85,16 @@ def run(blob: bytes, images: np.ndarray) -> np.ndarray:
                         out += a_hi @ w_hi.T
                         out += a_hi @ w_lo.T
                         out += a_lo @ w_hi.T
-            acc *= (row_scale[:, None] if op["use_row_scale"] else 1.0) * np.float32(op["f0"])
+            acc *= (row_scale[:, None] if op["use_row_scale"] & 1 else 1.0) * np.float32(op["f0"])
             if op["bias_off"]:
                 acc += _arr(blob, op["bias_off"], np.float32, nt * bn)[None, :]
             epi = op["epi"]
-            if epi in (2, 3):
+            if epi in (2, 3, 5):
                 aux = load(op["aux"], op["aux_lo"])[:, : nt * bn]
-                acc = acc + aux if epi == 2 else aux / (1.0 + np.exp(-acc))
+                if epi == 5:        # adapter skip, optionally scaled by the spatial-attention scalar; no ReLU
+                    acc = acc + aux * (row_scale[:, None] if op["use_row_scale"] & 2 else 1.0)
+                else:
+                    acc = acc + aux if epi == 2 else aux / (1.0 + np.exp(-acc))
             if epi in (1, 2, 4):
                 acc = np.maximum(acc, 0.0)
             if epi == 4:

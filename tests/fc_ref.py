@@ -91,9 +91,9 @@ def ref_fc(srcs, w_chunks, kb_begin, kb_src, kb_w, block_n, epi, bias=None, row_
         acc = acc * row_scale.double()[:, None]
     if bias is not None:
         acc = acc + bias.double()[None, :]
-    if epi in (2, 3):
+    if epi in (2, 3, 5):
         a = aux.double() + (aux_lo.double() if aux_lo is not None else 0.0)
-        acc = acc + a if epi == 2 else a * torch.sigmoid(acc)
+        acc = a * torch.sigmoid(acc) if epi == 3 else acc + a        # 5 = FC_EPI_ADD: skip connection without ReLU
     if epi in (1, 2, 4):
         acc = acc.clamp_min(0.0)
     if epi == 4:

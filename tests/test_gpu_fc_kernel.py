@@ -99,6 +99,10 @@ def test_residual_gate_and_row_scale(cuda_device):
     _check(out, ref_fc([a], w, kb_begin, kb_src, kb_w, block_n, 2, bias=bias, aux=aux, aux_lo=aux_lo), "add+relu")
     out, _, _ = run_fc([a], w, kb_begin, kb_src, kb_w, block_n, 3, aux=aux)
     _check(out, ref_fc([a], w, kb_begin, kb_src, kb_w, block_n, 3, aux=aux), "gate")
+    out, _, _ = run_fc([a], w, kb_begin, kb_src, kb_w, block_n, 5, bias=bias, aux=aux, aux_lo=aux_lo)
+    ref = ref_fc([a], w, kb_begin, kb_src, kb_w, block_n, 5, bias=bias, aux=aux, aux_lo=aux_lo)
+    assert (ref < 0).any()
+    _check(out, ref, "add (no ReLU)")
     out, _, _ = run_fc([a], w, kb_begin, kb_src, kb_w, block_n, 1, bias=bias, row_scale=rs)
     _check(out, ref_fc([a], w, kb_begin, kb_src, kb_w, block_n, 1, bias=bias, row_scale=rs), "row scale")
 
