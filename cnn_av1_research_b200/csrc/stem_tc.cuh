@@ -285,11 +285,19 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_tc_kernel(const __grid_con
         tmem_ld_32x32(t_addr + uint32_t(blk * 64 + 32), v1);   // conv rows 4..7
         tmem_ld_wait();
         if (r < n) {
-        float cv[64];
+        // max-pool the raw accumulators first: relu(s * a + b) is monotonic in a (s = 2^-k > 0), so
+        // max_window relu(s * a + b) = relu(s * max_window a + b) - 16 affine + ReLU evaluations instead of 64, and the
+        // 3x3 window is separable (row maxima, then column maxima)
+        float rm[8][4];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          cv[i] = fmaxf(fmaf(__uint_as_float(v0[i]), p.acc_scale, bias), 0.f);
-          cv[32 + i] = fmaxf(fmaf(__uint_as_float(v1[i]), p.acc_scale, bias), 0.f);
+        for (int y = 0; y < 8; ++y) {
+#pragma unroll
+          for (int qx = 0; qx < 4; ++qx) {
+            auto at = [&](int x) { return __uint_as_float(y < 4 ? v0[y * 8 + x] : v1[(y - 4) * 8 + x]); };
+            float m = fmaxf(at(2 * qx), at(2 * qx + 1));
+            if (qx > 0) m = fmaxf(m, at(2 * qx - 1));
+            rm[y][qx] = m;
+          }
         }
         // tiled activation layout (act_off): position q is the 64-column block q of row r
         const size_t obase = act_off(r, ch, 16);
@@ -299,15 +307,9 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_tc_kernel(const __grid_con
         for (int qy = 0; qy < 4; ++qy) {
 #pragma unroll
           for (int qx = 0; qx < 4; ++qx) {
-            float m = 0.f;                             // post-ReLU inputs: 0 is the identity of max
-#pragma unroll
-            for (int dy = -1; dy <= 1; ++dy) {
-#pragma unroll
-              for (int dx = -1; dx <= 1; ++dx) {
-                const int y = 2 * qy + dy, x = 2 * qx + dx;
-                if (y >= 0 && y < 8 && x >= 0 && x < 8) m = fmaxf(m, cv[y * 8 + x]);
-              }
-            }
+            float a = fmaxf(rm[2 * qy][qx], rm[2 * qy + 1][qx]);
+            if (qy > 0) a = fmaxf(a, rm[2 * qy - 1][qx]);
+            const float m = fmaxf(fmaf(a, p.acc_scale, bias), 0.f);
             const __half h = __float2half_rn(m);
             o[size_t(qy * 4 + qx) << 13] = h;
             if (ol) ol[size_t(qy * 4 + qx) << 13] = __float2half_rn(m - __half2float(h));
