@@ -136,7 +136,9 @@ def run_reference(args, rank, world, log):
             "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * n / fps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "blocks_per_sec": fps * BPF,
-            "config": {"workload": "full cascade, synthetic 3840x2160 YUV420p10le frames (extraction + /1023 + Stage1->Stage2->Stage3)",
+            "config": {"workload": "full cascade on a 4K 10-bit synthetic sequence (BASELINE configs[3]), block extraction included",
+                       "sample": "bounded sample of that workload: 1 synthetic 3840x2160 YUV420p10le frame per step "
+                                 "(extraction + /1023 + Stage1->Stage2->Stage3), the metric is per frame",
                        "frames_per_step": n, "blocks_per_frame": BPF, "threshold": THRESHOLD, "weights": "calibrated-random seed 0"},
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
                              "sample": f"{n} 4K frame ({BPF} blocks) per step, whole-frame predict, torch fp32 CPU ops identical to the reference's"},
