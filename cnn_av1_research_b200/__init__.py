@@ -2,7 +2,7 @@
 chiarorosa/cnn-av1-research).  See DESIGN.md and INTEGRATION.md at the repository root."""
 from .ensemble import ABEnsemble, WeightedEnsemble
 from .extraction import (BlockRecord, TorchBlockRecord, calculate_yuv420_10bit_sizes, extract_blocks_device,
-                         extract_blocks_with_validation)
+                         extract_blocks_with_validation, extract_frames_device)
 from .fileio import (load_block_file, predict_yuv_file, read_frames_yuv420p10, read_y_component_10bit_lossless,
                      save_blocks_binary_10bit)
 from .flatten import (FlattenPipeline, evaluate_with_threshold, remap_flatten_to_original, run_pipeline_inference,
@@ -19,6 +19,6 @@ __all__ = [
     "Stage3ABModel", "Stage3RectHead", "Stage3RectModel", "HierarchicalPipelineV6", "evaluate_pipeline",
     "Stage2FlatModel", "FlattenPipeline", "run_pipeline_inference", "remap_flatten_to_original",
     "evaluate_with_threshold", "sweep_thresholds", "read_y_component_10bit_lossless", "read_frames_yuv420p10",
-    "predict_yuv_file", "save_blocks_binary_10bit", "load_block_file", "ABEnsemble", "WeightedEnsemble", "AdapterModule",
+    "predict_yuv_file", "save_blocks_binary_10bit", "load_block_file", "ABEnsemble", "WeightedEnsemble", "AdapterModule", "extract_frames_device",
     "Stage2ModelWithAdapters",
 ]

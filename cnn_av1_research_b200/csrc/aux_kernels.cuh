@@ -290,16 +290,34 @@ __global__ void __launch_bounds__(256) fgvc_tail_kernel(const __half* __restrict
 // consecutive luma samples (one 16-byte load) of one block row; blocks are emitted in row-major
 // grid order, out-of-frame samples are zero.  OUT = uint16_t: raw tiles; OUT = float: tiles / 1023.
 template <typename OUT>
-__global__ void __launch_bounds__(256) extract_blocks_kernel(const uint16_t* __restrict__ y, int width, int height,
+__global__ void __launch_bounds__(256) extract_blocks_kernel(const uint16_t* __restrict__ y0, int width, int height,
                                                              int pitch, int bs, int blocks_x, int blocks_y,
-                                                             OUT* __restrict__ out) {
+                                                             OUT* __restrict__ out0, int n_frames, long long frame_stride) {
+  // n_frames luma planes `frame_stride` samples apart (planar YUV 4:2:0 sequences: 005:166-172), one launch; frame f's
+  // tiles follow frame f-1's in `out`
   const int chunks_x = blocks_x * bs / 8;                       // 8-sample chunks per padded row
-  const long long total = (long long)chunks_x * blocks_y * bs;
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
-       t += (long long)gridDim.x * blockDim.x) {
-    const int cx = int(t % chunks_x);
-    const int py = int(t / chunks_x);                           // padded-frame row
-    const int x0 = cx * 8;
+  const long long per_frame = (long long)chunks_x * blocks_y * bs;
+  const long long total = per_frame * n_frames;
+  for (long long tt = blockIdx.x * (long long)blockDim.x + threadIdx.x; tt < total;
+       tt += (long long)gridDim.x * blockDim.x) {
+    const long long f = tt / per_frame, t = tt - f * per_frame;
+    const uint16_t* __restrict__ y = y0 + f * frame_stride;
+    OUT* __restrict__ out = out0 + f * ((long long)blocks_x * blocks_y * bs * bs);
+    int py, x0;                                                 // padded-frame row, first sample of the 8-sample chunk
+    if constexpr (sizeof(OUT) == 2) {
+      // uint16 output: as many bytes read as written - work items in INPUT order (coalesced row reads; measured
+      // 4.59 TB/s for 32 4K frames vs 3.57 TB/s in output order)
+      py = int(t / chunks_x);
+      x0 = int(t % chunks_x) * 8;
+    } else {
+      // float output: twice as many bytes written as read - work items in OUTPUT order (tile, row, chunk), so a warp
+      // writes whole tiles contiguously (3.97 vs 3.53 TB/s)
+      const int cpr = bs / 8;                                   // chunks per tile row
+      const long long q = t / cpr;
+      const long long blk = q / bs;
+      py = int(blk / blocks_x) * bs + int(q % bs);
+      x0 = int(blk % blocks_x) * bs + int(t % cpr) * 8;
+    }
     uint16_t v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (py < height) {
       const uint16_t* src = y + size_t(py) * pitch + x0;

@@ -858,14 +858,16 @@ extern "C" int av1p_ensemble_vote(const float* logits, int32_t n_models, int32_t
 
 // ------------------------------------------------------------------------------ extraction ABI
 template <typename OUT>
-static int launch_extract(const uint16_t* y, int w, int h, int pitch, int bs, OUT* out, void* stream) {
-  if (!y || !out || w <= 0 || h <= 0 || pitch < w) return fail(AV1P_EINVAL, "bad frame geometry");
+static int launch_extract(const uint16_t* y, int w, int h, int pitch, int bs, OUT* out, void* stream, int n_frames = 1,
+                          long long frame_stride = 0) {
+  if (!y || !out || w <= 0 || h <= 0 || pitch < w || n_frames < 1 || (n_frames > 1 && frame_stride < (long long)pitch * (h - 1) + w))
+    return fail(AV1P_EINVAL, "bad frame geometry");
   if (bs != 8 && bs != 16 && bs != 32 && bs != 64) return fail(AV1P_EINVAL, "unsupported block size %d", bs);
   if (int rc = ensure_ctx()) return rc;
   const int bx = ceil_div(w, bs), by = ceil_div(h, bs);
-  const long long chunks = (long long)bx * bs / 8 * by * bs;
+  const long long chunks = (long long)bx * bs / 8 * by * bs * n_frames;
   const int grid = int(std::min<long long>((chunks + 255) / 256, (long long)g_ctx.sms * 16));
-  extract_blocks_kernel<OUT><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(y, w, h, pitch, bs, bx, by, out);
+  extract_blocks_kernel<OUT><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(y, w, h, pitch, bs, bx, by, out, n_frames, frame_stride);
   CUDA_TRY(cudaGetLastError());
   return AV1P_OK;
 }
@@ -874,6 +876,14 @@ extern "C" int av1p_extract_u16(const uint16_t* y, int32_t w, int32_t h, int32_t
 }
 extern "C" int av1p_extract_norm_u16(const uint16_t* y, int32_t w, int32_t h, int32_t pitch, int32_t bs, float* out, void* stream) {
   return launch_extract<float>(y, w, h, pitch, bs, out, stream);
+}
+extern "C" int av1p_extract_frames_u16(const uint16_t* frames, int32_t n_frames, int64_t frame_stride, int32_t w, int32_t h,
+                                       int32_t pitch, int32_t bs, uint16_t* out, void* stream) {
+  return launch_extract<uint16_t>(frames, w, h, pitch, bs, out, stream, n_frames, frame_stride);
+}
+extern "C" int av1p_extract_frames_norm_u16(const uint16_t* frames, int32_t n_frames, int64_t frame_stride, int32_t w, int32_t h,
+                                            int32_t pitch, int32_t bs, float* out, void* stream) {
+  return launch_extract<float>(frames, w, h, pitch, bs, out, stream, n_frames, frame_stride);
 }
 
 // ------------------------------------------------------------------------------ cascade

@@ -12,7 +12,7 @@ from __future__ import annotations
 
 import math
 from dataclasses import dataclass
-from typing import Dict, Tuple
+from typing import Optional, Dict, Tuple
 
 import numpy as np
 import torch
@@ -53,6 +53,33 @@ def extract_blocks_device(y_plane, block_size: int = 16, normalise: bool = False
         else:
             out = torch.empty((n, block_size, block_size), dtype=torch.uint16, device=y.device)
             N.check(lib.av1p_extract_u16(N.ptr(y), w, h, w, block_size, N.ptr(out), N.stream_handle(y.device)))
+    return out
+
+
+def extract_frames_device(frames: torch.Tensor, width: int, height: int, n_frames: int, block_size: int = 16,
+                          normalise: bool = True, frame_stride: Optional[int] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """A planar YUV 4:2:0 10-bit sequence resident on the device (flat 16-bit tensor, frame n at n * frame_stride samples:
+    005:166-172) -> the blocks of every frame's luma plane in ONE launch: [n_frames * N, 1, b, b] float32 / 1023 (or
+    [n_frames * N, b, b] uint16), frame after frame in the reference's row-major block order."""
+    if not frames.is_cuda or frames.dtype not in (torch.uint16, torch.int16) or not frames.is_contiguous():
+        raise N.Av1pError("frames must be a contiguous 16-bit CUDA tensor")
+    if frame_stride is None:
+        frame_stride = width * height + 2 * ((width // 2) * (height // 2))
+    if frames.numel() < (n_frames - 1) * frame_stride + width * height:
+        raise ValueError("frame tensor is smaller than the geometry implies")
+    n = n_frames * math.ceil(height / block_size) * math.ceil(width / block_size)
+    lib = N.lib()
+    with torch.cuda.device(frames.device):
+        if normalise:
+            if out is None:
+                out = torch.empty((n, 1, block_size, block_size), dtype=torch.float32, device=frames.device)
+            N.check(lib.av1p_extract_frames_norm_u16(N.ptr(frames), n_frames, frame_stride, width, height, width, block_size, N.ptr(out),
+                                                     N.stream_handle(frames.device)))
+        else:
+            if out is None:
+                out = torch.empty((n, block_size, block_size), dtype=torch.uint16, device=frames.device)
+            N.check(lib.av1p_extract_frames_u16(N.ptr(frames), n_frames, frame_stride, width, height, width, block_size, N.ptr(out),
+                                                N.stream_handle(frames.device)))
     return out
 
 

@@ -98,6 +98,12 @@ int av1p_extract_u16(const uint16_t* y_dev, int32_t width, int32_t height, int32
                      uint16_t* out_dev, void* stream);
 int av1p_extract_norm_u16(const uint16_t* y_dev, int32_t width, int32_t height, int32_t pitch, int32_t block,
                           float* out_dev, void* stream);
+/* Same tiling for n_frames luma planes `frame_stride_elems` samples apart (a planar YUV 4:2:0 sequence resident in HBM,
+ * 005:166-172 `frame_offset = n * frame_size`) in ONE launch; frame f's blocks follow frame f-1's in `out_dev`. */
+int av1p_extract_frames_u16(const uint16_t* frames_dev, int32_t n_frames, int64_t frame_stride_elems, int32_t width, int32_t height,
+                            int32_t pitch_elems, int32_t block_size, uint16_t* out_dev, void* stream);
+int av1p_extract_frames_norm_u16(const uint16_t* frames_dev, int32_t n_frames, int64_t frame_stride_elems, int32_t width,
+                                 int32_t height, int32_t pitch_elems, int32_t block_size, float* out_dev, void* stream);
 
 /* ---- routing operators (008:77-125), exposed on their own so they can be checked bit-exactly on
  *      reference logits.  scratch_dev: av1p_route_scratch_bytes() bytes, zero-initialised once.

@@ -7,6 +7,8 @@ import torch
 
 from cnn_av1_research_b200 import _native as N
 from cnn_av1_research_b200 import extraction as X
+from cnn_av1_research_b200 import synth
+from cnn_av1_research_b200.testing import frames_tensor
 from oracle import cascade_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -43,6 +45,23 @@ def test_extraction_full_size_vs_oracle(cuda_device, w, h):
     assert meta["num_blocks"] == blocks.shape[0] and meta["grid_shape"] == (-(-h // 16), -(-w // 16))
     norm = X.extract_blocks_device(y, 16, normalise=True, device=cuda_device).cpu().numpy()
     assert np.array_equal(norm.view(np.uint32), O.normalise_blocks(O.extract_blocks(y, 16)).view(np.uint32))
+
+
+@pytest.mark.parametrize("w,h,nf,bs", [(640, 360, 3, 16), (1001, 333, 2, 16), (1920, 1080, 2, 32), (200, 120, 4, 8)])
+def test_multi_frame_extraction_in_one_launch(cuda_device, w, h, nf, bs):
+    """av1p_extract_frames_*: every frame of a resident planar sequence in one launch == the per-plane oracle, bit-exact
+    (padded right / bottom edges, odd sizes, chroma skipped)."""
+    words = synth.synth_frames(nf, w, h, seed=w + h)
+    fw = synth.frame_words(w, h)
+    fr = frames_tensor(words, cuda_device)
+    raw = _u16(X.extract_frames_device(fr, w, h, nf, bs, normalise=False))
+    norm = X.extract_frames_device(fr, w, h, nf, bs, normalise=True).cpu().numpy()
+    per = -(-w // bs) * -(-h // bs)
+    for f in range(nf):
+        y = words[f * fw: f * fw + w * h].reshape(h, w)
+        ref = O.extract_blocks(y, bs)
+        assert np.array_equal(raw[f * per:(f + 1) * per], ref), f"frame {f}"
+        assert np.array_equal(norm[f * per:(f + 1) * per].view(np.uint32), O.normalise_blocks(ref).view(np.uint32)), f"frame {f}"
 
 
 def _route1(logits, thr, dev):

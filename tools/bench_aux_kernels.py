@@ -69,6 +69,18 @@ def main():
     ms = timed(lambda: X.extract_blocks_device(y, 16, normalise=False, device=dev), args.reps)
     report("extract_blocks_kernel<u16> (4K frame)", bpf * (512 + 512), ms, "512 B read + 512 B written per block")
 
+    # ---- the same for a whole resident sequence in one launch (av1p_extract_frames_*)
+    from cnn_av1_research_b200.testing import frames_tensor
+    nfx = min(args.frames, 32)
+    seq = frames_tensor(synth.synth_frames(nfx, w, h, seed=4), dev)
+    outf = torch.empty((nfx * bpf, 1, 16, 16), dtype=torch.float32, device=dev)
+    ms = timed(lambda: X.extract_frames_device(seq, w, h, nfx, 16, normalise=True, out=outf), args.reps)
+    report(f"extract_blocks_kernel<float> ({nfx} 4K frames, one launch)", nfx * bpf * (512 + 1024), ms, "512 B read + 1024 B written per block")
+    outu = torch.empty((nfx * bpf, 16, 16), dtype=torch.uint16, device=dev)
+    ms = timed(lambda: X.extract_frames_device(seq, w, h, nfx, 16, normalise=False, out=outu), args.reps)
+    report(f"extract_blocks_kernel<u16> ({nfx} 4K frames, one launch)", nfx * bpf * (512 + 512), ms, "512 B read + 512 B written per block")
+    del seq, outf, outu
+
     # ---- stage-1 routing over `frames` 4K frames of logits
     z = torch.from_numpy(rng.normal(0, 2, n).astype(np.float32)).to(dev)
     scratch = torch.zeros(lib.av1p_route_scratch_bytes(), dtype=torch.uint8, device=dev)
