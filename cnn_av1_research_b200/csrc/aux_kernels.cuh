@@ -2,6 +2,7 @@
 // tail, standalone block extraction / normalisation, and the inter-stage routing (threshold /
 // argmax + stable stream compaction + label scatter).
 #pragma once
+#include <cuda.h>
 #include "ptx_sm100.cuh"
 
 namespace av1p {
@@ -342,6 +343,86 @@ __global__ void __launch_bounds__(256) extract_blocks_kernel(const uint16_t* __r
       b.z = __fdiv_rn(float(v[6]), 1023.0f); b.w = __fdiv_rn(float(v[7]), 1023.0f);
       reinterpret_cast<float4*>(dst)[0] = a;
       reinterpret_cast<float4*>(dst)[1] = b;
+    }
+  }
+}
+
+// Same operation with TMA staging (used whenever the plane pitch / frame stride are 16-byte multiples): the luma planes
+// are a 3-D tensor [frames][H][W] of uint16; a CTA walks [64 rows x 64 samples] boxes (= (64/bs)^2 tiles), each brought
+// into shared memory by ONE cp.async.bulk.tensor load in the SWIZZLE_128B layout (out-of-frame samples arrive as zeros:
+// the reference's right / bottom zero padding comes for free), EX_STAGES boxes in flight per CTA.  Threads read 16-byte
+// chunks conflict-free and write every tile as one contiguous piece of the output.
+constexpr int EX_STAGES = 6;
+constexpr int EX_THREADS = 256;
+constexpr int EX_BOX_BYTES = 64 * 128;
+constexpr int EX_SMEM_BYTES = EX_STAGES * EX_BOX_BYTES + 1024;
+template <typename OUT>
+__global__ void __launch_bounds__(EX_THREADS) extract_blocks_tma_kernel(const __grid_constant__ CUtensorMap map, int bs, int blocks_x,
+                                                                        int blocks_y, int n_frames, OUT* __restrict__ out0) {
+  extern __shared__ uint8_t ex_smem_raw[];
+  const uint32_t base = (smem_u32(ex_smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = ex_smem_raw + (base - smem_u32(ex_smem_raw));
+  __shared__ uint64_t full[EX_STAGES];
+  const int tpb = 64 / bs;                                          // tiles per box side
+  const int tiles_x = (blocks_x + tpb - 1) / tpb, tiles_y = (blocks_y + tpb - 1) / tpb;
+  const long long total = (long long)n_frames * tiles_y * tiles_x;
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&map);
+    for (int s = 0; s < EX_STAGES; ++s) mbar_init(&full[s], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  auto issue = [&](long long tile, int s) {
+    const int tx = int(tile % tiles_x);
+    const long long q = tile / tiles_x;
+    mbar_arrive_expect_tx(&full[s], uint32_t(EX_BOX_BYTES));
+    tma_load_3d(smem + s * EX_BOX_BYTES, &map, &full[s], tx * 64, int(q % tiles_y) * 64, int(q / tiles_y));
+  };
+  if (threadIdx.x == 0)
+    for (int s = 0; s < EX_STAGES; ++s) {
+      const long long tile = blockIdx.x + (long long)s * gridDim.x;
+      if (tile < total) issue(tile, s);
+    }
+  const int cpr = bs / 8;                                          // 16-byte chunks per tile row
+  long long it = 0;
+  for (long long tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+    const int s = int(it % EX_STAGES);
+    mbar_wait(&full[s], uint32_t(it / EX_STAGES) & 1u, nullptr, 0);
+    const uint8_t* box = smem + s * EX_BOX_BYTES;
+    const int tx = int(tile % tiles_x);
+    const long long q = tile / tiles_x;
+    const int ty = int(q % tiles_y);
+    const long long f = q / tiles_y;
+    OUT* __restrict__ out = out0 + f * ((long long)blocks_x * blocks_y * bs * bs);
+#pragma unroll 2
+    for (int i = threadIdx.x; i < 512; i += EX_THREADS) {
+      // output order inside the box: tile b (row-major), row r, chunk c
+      const int c = i % cpr, r = (i / cpr) % bs, b = i / (cpr * bs);
+      const int bry = b / tpb, bcx = b - bry * tpb;
+      const int by = ty * tpb + bry, bx = tx * tpb + bcx;
+      const int row = bry * bs + r;                                // box row
+      const int chunk16 = bcx * cpr + c;                           // 16-byte chunk of the 128-byte box row
+      const uint4 raw = *reinterpret_cast<const uint4*>(box + row * 128 + ((chunk16 ^ (row & 7)) << 4));
+      if (bx < blocks_x && by < blocks_y) {
+        OUT* dst = out + ((size_t(by) * blocks_x + bx) * bs + r) * bs + c * 8;
+        if constexpr (sizeof(OUT) == 2) {
+          *reinterpret_cast<uint4*>(dst) = raw;
+        } else {
+          const uint16_t* v = reinterpret_cast<const uint16_t*>(&raw);
+          float4 lo4, hi4;
+          lo4.x = __fdiv_rn(float(v[0]), 1023.0f); lo4.y = __fdiv_rn(float(v[1]), 1023.0f);
+          lo4.z = __fdiv_rn(float(v[2]), 1023.0f); lo4.w = __fdiv_rn(float(v[3]), 1023.0f);
+          hi4.x = __fdiv_rn(float(v[4]), 1023.0f); hi4.y = __fdiv_rn(float(v[5]), 1023.0f);
+          hi4.z = __fdiv_rn(float(v[6]), 1023.0f); hi4.w = __fdiv_rn(float(v[7]), 1023.0f);
+          reinterpret_cast<float4*>(dst)[0] = lo4;
+          reinterpret_cast<float4*>(dst)[1] = hi4;
+        }
+      }
+    }
+    __syncthreads();                    // every thread has USED its shared-memory loads: the stage may be refilled
+    if (threadIdx.x == 0) {
+      const long long next = tile + (long long)EX_STAGES * gridDim.x;
+      if (next < total) issue(next, s);
     }
   }
 }

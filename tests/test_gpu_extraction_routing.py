@@ -47,10 +47,12 @@ def test_extraction_full_size_vs_oracle(cuda_device, w, h):
     assert np.array_equal(norm.view(np.uint32), O.normalise_blocks(O.extract_blocks(y, 16)).view(np.uint32))
 
 
-@pytest.mark.parametrize("w,h,nf,bs", [(640, 360, 3, 16), (1001, 333, 2, 16), (1920, 1080, 2, 32), (200, 120, 4, 8)])
-def test_multi_frame_extraction_in_one_launch(cuda_device, w, h, nf, bs):
+@pytest.mark.parametrize("tma", ["0", "1"])
+@pytest.mark.parametrize("w,h,nf,bs", [(640, 360, 3, 16), (1001, 333, 2, 16), (1920, 1080, 2, 32), (200, 120, 4, 8), (1280, 720, 2, 64)])
+def test_multi_frame_extraction_in_one_launch(cuda_device, monkeypatch, w, h, nf, bs, tma):
     """av1p_extract_frames_*: every frame of a resident planar sequence in one launch == the per-plane oracle, bit-exact
     (padded right / bottom edges, odd sizes, chroma skipped)."""
+    monkeypatch.setenv("AV1P_EXTRACT_TMA", tma)       # "1": the TMA-staged kernel (falls back when the pitch is not a 16-byte multiple)
     words = synth.synth_frames(nf, w, h, seed=w + h)
     fw = synth.frame_words(w, h)
     fr = frames_tensor(words, cuda_device)
