@@ -8,6 +8,8 @@ extraction fused into the first kernel, straight from planar YUV 4:2:0 10-bit fr
 from __future__ import annotations
 
 import math
+import os
+from collections import OrderedDict
 from typing import List, Optional
 
 import torch
@@ -42,6 +44,11 @@ class HierarchicalPipelineV6:
         self._cascade: Optional[NativeCascade] = None
         self._cascade_key = None
         self._min_capacity = int(capacity_blocks)
+        # predict() on small batches (the reference's evaluate_pipeline feeds 256 blocks per call, 008:278-284) is bound by
+        # the ~110 kernel launches of a cascade, not by the GPU: such calls replay a CUDA graph of the whole cascade,
+        # captured once per (batch size, threshold) with static input / output buffers.  AV1P_GRAPHS=0 disables.
+        self._graphs: "OrderedDict" = OrderedDict()
+        self._graphs_on = os.environ.get("AV1P_GRAPHS", "1") != "0"
 
     # -------------------------------------------------------------------------------------------
     def _models(self) -> List:
@@ -76,9 +83,49 @@ class HierarchicalPipelineV6:
             self.cascade(n).predict(N.images_input(images), n, self.stage1_threshold, out_u8, out_i64)
         return out_i64 if out_i64 is not None else out_u8
 
+    GRAPH_MAX_BLOCKS = 16384          # above this a cascade is GPU-bound and the launches hide behind it
+    GRAPH_CACHE = 8
+
+    def _predict_graph(self, images: torch.Tensor) -> Optional[torch.Tensor]:
+        """Replay (capturing on first use) the CUDA graph of one cascade over `n` blocks; None if graphs are unavailable."""
+        n = images.shape[0]
+        cascade = self.cascade(max(n, 256))
+        key = (n, float(self.stage1_threshold), id(cascade))
+        entry = self._graphs.get(key)
+        if entry is None:
+            static_in = torch.empty((n, 1, 16, 16), dtype=torch.float32, device=self.device)
+            static_out = torch.empty(n, dtype=torch.int64, device=self.device)
+            static_in.copy_(images)
+            try:
+                with torch.cuda.device(self.device):
+                    cascade.predict(N.images_input(static_in), n, self.stage1_threshold, None, static_out)   # warm-up, not captured
+                    torch.cuda.synchronize(self.device)
+                    graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(graph):
+                        cascade.predict(N.images_input(static_in), n, self.stage1_threshold, None, static_out)
+            except Exception:
+                self._graphs_on = False             # direct enqueue from now on (same kernels, no graph)
+                torch.cuda.synchronize(self.device)
+                return None
+            entry = (graph, static_in, static_out, cascade)
+            self._graphs[key] = entry
+            while len(self._graphs) > self.GRAPH_CACHE:
+                self._graphs.popitem(last=False)
+        else:
+            self._graphs.move_to_end(key)
+        graph, static_in, static_out, _ = entry
+        static_in.copy_(images, non_blocking=True)
+        graph.replay()
+        return static_out
+
     @torch.no_grad()
     def predict(self, images: torch.Tensor) -> torch.Tensor:
         """Run full hierarchical prediction (008:69-127): float32 [B,1,16,16] -> int64 [B] on the CPU."""
+        if self._graphs_on and images.dim() == 4 and tuple(images.shape[1:]) == (1, 16, 16) and 0 < images.shape[0] <= self.GRAPH_MAX_BLOCKS:
+            x = images.to(self.device, non_blocking=True).contiguous().float()
+            out = self._predict_graph(x)
+            if out is not None:
+                return out.cpu()
         return self.predict_device(images).cpu()
 
     @torch.no_grad()

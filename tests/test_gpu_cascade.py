@@ -120,6 +120,29 @@ def test_cascade_matches_reference_predict(cuda_device, golden_dir, precision):
         assert same >= AGREE_MIN[precision], f"frame path vs image path agreement {same:.5f}"
 
 
+def test_small_batch_predict_replays_a_cuda_graph(cuda_device):
+    """predict() on small batches (008's evaluate_pipeline feeds 256 blocks per call) replays a CUDA graph of the cascade
+    with static buffers: the labels must equal the directly enqueued cascade for fresh data, for another batch size and
+    after a threshold change (the threshold is baked into the captured launches, so it is part of the cache key)."""
+    g = torch.Generator().manual_seed(3)
+    words = synth.synth_frames(1, 640, 368, seed=8)
+    images = O.frames_to_images(words, 1, 640, 368)
+    pipe = build_pipeline(seed=0, threshold=0.45, device=cuda_device)
+    x1, x2 = images[:256], images[256:512]
+    a1 = pipe.predict(x1)
+    a2 = pipe.predict(x2)                                  # replay with new data
+    assert pipe._graphs_on and len(pipe._graphs) == 1, "the second call should have replayed the captured graph"
+    assert torch.equal(a1, pipe.predict_device(x1).cpu()) and torch.equal(a2, pipe.predict_device(x2).cpu())
+    assert a1.dtype == torch.int64 and a1.device.type == "cpu"
+    a3 = pipe.predict(images[:77])                         # another batch size: a second graph
+    assert len(pipe._graphs) == 2 and torch.equal(a3, pipe.predict_device(images[:77]).cpu())
+    pipe.stage1_threshold = 0.9
+    hi = build_pipeline(seed=0, threshold=0.9, device=cuda_device)
+    assert torch.equal(pipe.predict(x1), hi.predict_device(x1).cpu())
+    assert not torch.equal(pipe.predict(x1), a1)
+    del g
+
+
 def test_predict_edge_cases(cuda_device):
     pipe = build_pipeline(seed=0, device=cuda_device)
     assert pipe.predict(torch.zeros(0, 1, 16, 16)).shape == (0,)
