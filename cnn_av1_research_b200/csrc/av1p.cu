@@ -644,7 +644,7 @@ int run_stage(av1p_stage* s, const StemInput& si, const int32_t* idx, const int3
       case AV1P_OP_CONV_RES: {
         P.cr.n_rows_dev = n_dev;
         P.cr.n_rows = n;
-        const int grid = std::min(g_ctx.sms, ceil_div(n, FC_TILE_M));
+        const int grid = 2 * std::max(1, std::min(g_ctx.sms / 2, ceil_div(n, FC_TILE_M)));      // (M tile, half) items, even grid
         ProfScope ps(PROF_CONV, st);
         conv_res_kernel_for(P.cr)<<<grid, CR_THREADS, CR_SMEM_BYTES, st>>>(P.cr);
         break;
@@ -1254,7 +1254,7 @@ extern "C" int av1p_conv_res_forward(const av1p_conv_res_desc* d, void* stream) 
   f.err_flag = g_ctx.watchdog_dev;
   if (!conv_res_build_schedule(f)) return fail(AV1P_EINVAL, "resident-conv schedule does not fit its tables");
   if (const char* dbg = getenv("AV1P_CR_DEBUG")) f.debug = atoi(dbg);   // kernel-development switch of this test hook only
-  const int grid = std::min(g_ctx.sms, ceil_div(d->rows, FC_TILE_M));
+  const int grid = 2 * std::max(1, std::min(g_ctx.sms / 2, ceil_div(d->rows, FC_TILE_M)));
   conv_res_kernel_for(f)<<<grid, CR_THREADS, CR_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(f);
   CUDA_TRY(cudaGetLastError());
   return AV1P_OK;

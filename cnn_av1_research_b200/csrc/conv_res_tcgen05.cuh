@@ -73,6 +73,7 @@ struct ConvResParams {
   int has_aux_lo;              // residual has a lo plane
   int debug;                   // test hook only (AV1P_CR_DEBUG): 1 skip MMA issue, 2 skip staging/stores, 4 skip TMA loads, 8 skip L2 prefetch, 16 skip the epilogue
   int n_ring;
+  int ring_begin[3];           // ring entries of half h: [ring_begin[h], ring_begin[h + 1])
   uint8_t ring[CR_MAX_RING];
   // epilogue members (names shared with FcParams, see epi_tile_store)
   int epi;
@@ -107,10 +108,11 @@ struct CrPipe {
   uint32_t acc_phase;      // bit s: parity of position slot s (0..7)
 };
 
-// MMA issue for one M tile, straight-line (every loop below has compile-time bounds and unrolls completely).
-template <bool SPLIT, bool RESID, bool AUX_LO>
-__device__ __forceinline__ void cr_issue_mtile(CrPipe& q, uint32_t base, uint32_t tmem_base, uint64_t id_desc, int* err_flag,
-                                               bool skip_mma) {
+// MMA issue for one work item = half H of an M tile (output rows 2H, 2H + 1), straight-line (every loop below has
+// compile-time bounds and unrolls completely).
+template <bool SPLIT, bool RESID, bool AUX_LO, int H>
+__device__ __forceinline__ void cr_issue_half(CrPipe& q, uint32_t base, uint32_t tmem_base, uint64_t id_desc, int* err_flag,
+                                              bool skip_mma) {
   constexpr int PLANES = SPLIT ? 2 : 1;
   constexpr int AUX_PLANES = AUX_LO ? 2 : 1;
   const uint32_t w_lo0 = umma_desc_lo_sw128(base + CR_OFF_W);
@@ -125,8 +127,8 @@ __device__ __forceinline__ void cr_issue_mtile(CrPipe& q, uint32_t base, uint32_
       q.phase ^= 1u;
     }
   };
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
+  {
+    constexpr int h = H;
 #pragma unroll
     for (int iyi = 0; iyi < 3; ++iyi) {
       const int iy = h + iyi;
@@ -263,6 +265,12 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_res_tcgen05_kernel(const _
   const int m_tiles = (n_rows + FC_TILE_M - 1) / FC_TILE_M;
   constexpr int planes = SPLIT ? 2 : 1;
   constexpr bool residual = RESID;
+  // Work item = (M tile, half): the grid is even, CTA b always takes half b & 1 of the M tiles b >> 1, b >> 1 + grid / 2, ...
+  // so that (a) the wave quantisation of a launch is in half tiles, (b) few-tile launches spread over twice as many SMs and
+  // (c) the two CTAs that need input rows 1 and 2 of an M tile read them at the same time (one DRAM read, one L2 hit).
+  const int half = int(blockIdx.x & 1u);
+  const int mt0 = int(blockIdx.x >> 1);
+  const int mt_step = int(gridDim.x >> 1);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.a_map[0]);
@@ -302,7 +310,7 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_res_tcgen05_kernel(const _
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (warp-uniform loop, one lane issues)
-    if (blockIdx.x < m_tiles) {
+    if (mt0 < m_tiles) {
       // resident weights first: planes x 9 tiles of 8 KB on one barrier
       if (elect_one_sync()) {
         mbar_arrive_expect_tx(w_bar, uint32_t(planes * CR_W_PLANE_BYTES));
@@ -313,20 +321,21 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_res_tcgen05_kernel(const _
       int stage = 0;
       uint32_t phase = 0;
       // L2 prefetch cursor: runs CR_PREFETCH ring tiles ahead of the loads (into the next M tile of this CTA)
-      int pf_mt = blockIdx.x, pf_i = 0;
+      const int rb = p.ring_begin[half], re = p.ring_begin[half + 1];
+      int pf_mt = mt0, pf_i = rb;
       auto prefetch_next = [&]() {
         if (pf_mt >= m_tiles) return;
         const uint32_t e = p.ring[pf_i];
         if (!(p.debug & 8) && elect_one_sync()) tma_prefetch_l2_2d(&p.a_map[e >> 4], 0, (pf_mt * 16 + int(e & 15u)) * FC_TILE_M);
         __syncwarp();
-        if (++pf_i == p.n_ring) {
-          pf_i = 0;
-          pf_mt += gridDim.x;
+        if (++pf_i == re) {
+          pf_i = rb;
+          pf_mt += mt_step;
         }
       };
       for (int i = 0; i < CR_PREFETCH; ++i) prefetch_next();
-      for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x) {
-        for (int i = 0; i < p.n_ring; ++i) {
+      for (int mt = mt0; mt < m_tiles; mt += mt_step) {
+        for (int i = rb; i < re; ++i) {
           const uint32_t e = p.ring[i];
           prefetch_next();
           mbar_wait(&empty_bar[stage], phase ^ 1u, p.err_flag, 100 + stage);
@@ -348,22 +357,27 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_res_tcgen05_kernel(const _
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (warp-uniform, one lane issues)
-    if (blockIdx.x < m_tiles) {
+    if (mt0 < m_tiles) {
       CrPipe q{full_bar, empty_bar, acc_full, acc_empty, 0, 0u, 0u};
       const uint64_t id_desc = ident_desc(base + CR_OFF_IDENT);
       mbar_wait(w_bar, 0u, p.err_flag, 500);
       tc_fence_after_sync();
-      for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x)
-        cr_issue_mtile<SPLIT, RESID, AUX_LO>(q, base, tmem_base, id_desc, p.err_flag, (p.debug & 1) != 0);
+      if (half == 0) {
+        for (int mt = mt0; mt < m_tiles; mt += mt_step)
+          cr_issue_half<SPLIT, RESID, AUX_LO, 0>(q, base, tmem_base, id_desc, p.err_flag, (p.debug & 1) != 0);
+      } else {
+        for (int mt = mt0; mt < m_tiles; mt += mt_step)
+          cr_issue_half<SPLIT, RESID, AUX_LO, 1>(q, base, tmem_base, id_desc, p.err_flag, (p.debug & 1) != 0);
+      }
     }
   } else if (warp < FC_STORE_WARP) {
     // ------------------------------------------------------------ epilogue (warps 2..9): output rows 0..3 -> slots 0,1,0,1
     uint32_t acc_phase = 0u;      // bit s: parity of position slot s
     uint32_t g = 0;
-    for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x) {
+    for (int mt = mt0; mt < m_tiles; mt += mt_step) {
 #pragma unroll 1
-      for (int i = 0; i < 16; ++i) {
-        const int pos = CR_DRAIN[i];
+      for (int i = 0; i < 8; ++i) {
+        const int pos = CR_DRAIN[8 * half + i];
         const int slot = pos & 7;
         epi_tile_store(p, es, g, n_rows, mt, pos * 64, 64, tmem_base + uint32_t(slot * 64), &acc_full[slot],
                        (acc_phase >> slot) & 1u, &acc_empty[slot], warp, lane, 400 + slot);
@@ -373,11 +387,11 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_res_tcgen05_kernel(const _
   } else {
     // ------------------------------------------------------------ store warp
     uint32_t g = 0;
-    for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x) {
+    for (int mt = mt0; mt < m_tiles; mt += mt_step) {
       if ((mt + 1) * FC_TILE_M > n_rows || (p.debug & 18)) continue;
 #pragma unroll 1
-      for (int i = 0; i < 16; ++i)
-        epi_store_chunks(es, g, &p.out_map[0], &p.out_map[1], p.out_lo != nullptr, int(CR_DRAIN[i]) * 64, 64 / EPI_CHUNK, mt, 16,
+      for (int i = 0; i < 8; ++i)
+        epi_store_chunks(es, g, &p.out_map[0], &p.out_map[1], p.out_lo != nullptr, int(CR_DRAIN[8 * half + i]) * 64, 64 / EPI_CHUNK, mt, 16,
                          p.err_flag, uint32_t(warp - FC_STORE_WARP));
     }
     epi_store_drain();
@@ -401,6 +415,7 @@ inline bool conv_res_build_schedule(ConvResParams& f) {
   static const int ix_order[4] = {1, 0, 2, 3};
   int n = 0;
   for (int h = 0; h < 2; ++h) {
+    f.ring_begin[h] = n;
     for (int iy = h; iy < h + 3; ++iy) {
       for (int xi = 0; xi < 4; ++xi) {
         for (int pl = 0; pl < planes; ++pl) {
@@ -418,6 +433,7 @@ inline bool conv_res_build_schedule(ConvResParams& f) {
     }
   }
   f.n_ring = n;
+  f.ring_begin[2] = n;
   return true;
 }
 
