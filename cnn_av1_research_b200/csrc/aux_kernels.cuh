@@ -53,6 +53,23 @@ __device__ __forceinline__ void load_row16(const __half* __restrict__ hi, const 
   }
 }
 
+// Spatial attention from the partial statistics the producing FC layer left behind (FcParams::sam_part): per row the
+// sum and the maximum over `slots` partials, then the same scalar as sam_gate_kernel.
+__global__ void __launch_bounds__(256) sam_finish_kernel(const float* __restrict__ part, int slots, const int* n_dev, int n,
+                                                         float w_avg, float w_max, float* __restrict__ row_scale) {
+  const int rows = n_dev ? *n_dev : n;
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += gridDim.x * blockDim.x) {
+    const float2* q = reinterpret_cast<const float2*>(part) + size_t(r) * slots;
+    float s = 0.f, m = -INFINITY;
+    for (int i = 0; i < slots; ++i) {
+      const float2 v = q[i];
+      s += v.x;
+      m = fmaxf(m, v.y);
+    }
+    row_scale[r] = 1.0f / (1.0f + expf(-(w_avg * (s * (1.0f / 512.0f)) + w_max * m)));
+  }
+}
+
 __global__ void __launch_bounds__(256) sam_gate_kernel(const __half* __restrict__ x, const __half* __restrict__ x_lo,
                                                        int ld, const int* n_dev, int n, float w_avg, float w_max,
                                                        float* __restrict__ row_scale) {

@@ -378,10 +378,11 @@ struct PlannedOp {
 };
 
 // Activation region shared by every stage of a cascade: buffer i has max-over-models cols.
+constexpr int SAM_PART_SLOTS = 8;      // se4.fc2: 2 N tiles x 2 epilogue groups x 2 column halves
 struct ActLayout {
   std::vector<uint32_t> cols;
   std::vector<size_t> off;
-  size_t row_scale_off = 0, bytes = 0;
+  size_t row_scale_off = 0, sam_part_off = 0, bytes = 0;
   int cap = 0;
 };
 
@@ -399,7 +400,9 @@ ActLayout make_act_layout(const av1p_model* const* models, int n_models, int cap
     o += align_up(size_t(L.cap) * L.cols[b] * 2, 1024);
   }
   L.row_scale_off = o;
+  L.sam_part_off = o + align_up(size_t(L.cap) * 4, 1024);
   o += align_up(size_t(L.cap) * 4, 1024);
+  o += align_up(size_t(L.cap) * SAM_PART_SLOTS * 2 * 4, 1024);        // spatial-attention partials (FcParams::sam_part)
   L.bytes = o;
   return L;
 }
@@ -411,6 +414,7 @@ struct av1p_stage {
   int cap = 0;
   std::vector<PlannedOp> ops;
   float* row_scale = nullptr;
+  float* sam_part = nullptr;
   float* own_logits = nullptr;   // unused by the cascade (it passes its own logits buffers)
 };
 
@@ -420,6 +424,7 @@ int plan_stage(const av1p_model* m, const ActLayout& L, uint8_t* act_base, av1p_
   s->model = m;
   s->cap = L.cap;
   s->row_scale = reinterpret_cast<float*>(act_base + L.row_scale_off);
+  s->sam_part = reinterpret_cast<float*>(act_base + L.sam_part_off);
   auto buf = [&](int id) -> __half* { return id < 0 ? nullptr : reinterpret_cast<__half*>(act_base + L.off[id]); };
   auto at = [&](uint64_t off) -> const uint8_t* { return off ? m->dev + off : nullptr; };
   for (const Av1pBlobOp& op : m->ops) {
@@ -457,6 +462,11 @@ int plan_stage(const av1p_model* m, const ActLayout& L, uint8_t* act_base, av1p_
         f.bias = reinterpret_cast<const float*>(at(op.bias_off));
         f.row_scale = (op.use_row_scale & 1) ? s->row_scale : nullptr;
         f.aux_row_scale = (op.use_row_scale & 2) ? s->row_scale : nullptr;
+        if (op.use_row_scale & 4) {        // leave the spatial-attention partials of this layer's output behind
+          if (op.n_tiles * 4 != SAM_PART_SLOTS || (op.block_n / EPI_CHUNK) % 2 || op.n_tiles * op.block_n != 512)
+            return fail(AV1P_EINVAL, "spatial-attention partials need a 512-wide output in 2 N tiles of 256");
+          f.sam_part = s->sam_part;
+        }
         f.acc_scale = op.f0;
         f.pair_mode = op.pair_mode;
         if (op.pair_mode) {
@@ -552,6 +562,7 @@ int plan_stage(const av1p_model* m, const ActLayout& L, uint8_t* act_base, av1p_
       }
       case AV1P_OP_SAM:
       case AV1P_OP_FGVC_TAIL: {
+        P.se_npos = (op.type == AV1P_OP_SAM && op.tail_n == 1) ? SAM_PART_SLOTS : 0;     // SAM from partials
         P.src = buf(op.src[0]);
         P.src_lo = buf(op.src[1]);
         if (!P.src || L.cols[op.src[0]] != 512 || (op.src[1] >= 0 && L.cols[op.src[1]] != 512)) return fail(AV1P_EINVAL, "SAM/FGVC op needs a 512-wide source");
@@ -650,9 +661,13 @@ int run_stage(av1p_stage* s, const StemInput& si, const int32_t* idx, const int3
         break;
       }
       case AV1P_OP_SAM: {
-        const int grid = std::min(ceil_div(n, 8), g_ctx.sms * 8);
         ProfScope ps(PROF_SAM, st);
-        sam_gate_kernel<<<grid, 256, 0, st>>>(P.src, P.src_lo, P.ld, n_dev, n, P.f0, P.f1, s->row_scale);
+        if (P.se_npos > 0) {
+          sam_finish_kernel<<<std::min(ceil_div(n, 256), g_ctx.sms * 8), 256, 0, st>>>(s->sam_part, P.se_npos, n_dev, n, P.f0, P.f1, s->row_scale);
+        } else {
+          const int grid = std::min(ceil_div(n, 8), g_ctx.sms * 8);
+          sam_gate_kernel<<<grid, 256, 0, st>>>(P.src, P.src_lo, P.ld, n_dev, n, P.f0, P.f1, s->row_scale);
+        }
         break;
       }
       case AV1P_OP_SE: {

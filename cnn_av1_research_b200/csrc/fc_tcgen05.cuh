@@ -107,6 +107,9 @@ struct FcParams {
   const float* bias;           // [n_tiles*block_n] or nullptr
   const float* row_scale;      // [rows] or nullptr (spatial-attention scalar folded into the next linear)
   const float* aux_row_scale;  // FC_EPI_ADD: [rows] scale of the aux operand, or nullptr
+  float* sam_part;             // optional [rows][n_tiles * 4][2]: per-thread partial (sum, max) of this layer's OUTPUT over the
+                               // columns a thread handles - the spatial-attention statistics (models.py:56-61) of se4's
+                               // output without a second pass over it (sam_finish_kernel reduces the partials per row)
   float acc_scale;             // power of two undoing the weight pre-scale
   const __half* aux;           // gate input rows (FC_EPI_GATE only)
   const __half* aux_lo;        // split mode: low part of aux (nullptr otherwise)
@@ -271,6 +274,7 @@ __device__ __forceinline__ void epi_tile_store(const P& p, const EpiStage& es, u
   }
   const uint32_t g0 = g;
   const uint32_t ga0 = aux_on ? gx->ga : 0u;
+  float ssum = 0.f, smax = -INFINITY;         // sam_part partials of this thread (columns of its chunks in this tile)
   const int c_first = int((g0 & 1u) ^ grp);                  // first chunk of this tile with (g0 + c) & 1 == grp
   const uint32_t t_addr = t_col + (uint32_t(quad * 32) << 16) + uint32_t(sub * 16);
   uint32_t v[8];
@@ -343,6 +347,15 @@ __device__ __forceinline__ void epi_tile_store(const P& p, const EpiStage& es, u
 #pragma unroll
         for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
       }
+      if constexpr (requires { p.sam_part; }) {
+        if (p.sam_part) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            ssum += f[i];
+            smax = fmaxf(smax, f[i]);
+          }
+        }
+      }
       __align__(16) __half2 hi[4], lo[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -373,6 +386,15 @@ __device__ __forceinline__ void epi_tile_store(const P& p, const EpiStage& es, u
     tc_fence_before_sync();
     __syncwarp();
     if (lane == 0) acc_release(empty, empty_remote);
+  }
+  if constexpr (requires { p.sam_part; }) {
+    if (p.sam_part && row_ok && c_first < n_chunks) {
+      // slot (N tile, group, sub): every (row, slot) is written by exactly one thread
+      const int slots = p.n_tiles * 4;
+      float* d = p.sam_part + (size_t(row) * slots + size_t((col0 / block_n) * 4 + int(grp) * 2 + sub)) * 2;
+      d[0] = ssum;
+      d[1] = smax;
+    }
   }
   if (staged) g = g0 + uint32_t(n_chunks);
   if (aux_on) gx->ga = ga0 + uint32_t(n_chunks);

@@ -39,6 +39,7 @@ STAGE_KINDS = {"stage1": 0, "stage2": 1, "rect": 2, "ab_fgvc": 3, "ab": 4, "flat
 NUM_OUTPUTS = {"stage1": 1, "stage2": 3, "rect": 2, "ab_fgvc": 4, "ab": 4, "flat7": 7, "stage2_adapters": 3}
 
 BN_EPS = 1e-5
+SAM_FUSED = os.environ.get("AV1P_SAM_FUSED", "1") != "0"     # A/B knob: 0 = separate pass over se4's output (sam_gate_kernel)
 
 # activation buffers (fp16 columns per block row).  In split precision every buffer X has a twin X_lo
 # holding fp16(x - fp16(x)); the twins get ids len(BUF_COLS) + id(X).
@@ -297,7 +298,9 @@ def backbone_ops(sd, precision: str = "fp16x3", prefix: str = "backbone.", layer
         d2 = np.zeros((npos * w2.shape[0], 64))
         d2[:, : w2.shape[1]] = np.tile(w2, (npos, 1))
         ops.append(make_fc_op(f"se{layer}.fc1", [d1], [src], "H", None, EPI_RELU, 64, precision))
-        ops.append(make_fc_op(f"se{layer}.fc2", [d2], ["H"], dst, None, EPI_GATE, _block_n(d2.shape[0]), precision, aux=src))
+        # se4.fc2 also leaves the spatial-attention statistics of its output behind (use_row_scale bit 2), see OP_SAM below
+        ops.append(make_fc_op(f"se{layer}.fc2", [d2], ["H"], dst, None, EPI_GATE, _block_n(d2.shape[0]), precision, aux=src,
+                              use_row_scale=4 if (layer == 4 and SAM_FUSED) else 0))
 
     # --- layer1: 4x4 grid, 64 ch.  a0=B0.  Resident-weight conv kernel by default; `layer1_fc=True` keeps the
     #     generic block-Toeplitz FC form (used by the kernel-level comparison tests).
@@ -358,8 +361,12 @@ def backbone_ops(sd, precision: str = "fp16x3", prefix: str = "backbone.", layer
     # after layer4: x4' = C1 (t0 of the last plan row)
     # --- spatial attention at 1x1: centre tap of the 7x7 kernel only (models.py:56-61)
     wsa = _np64(sd[p + "spatial_attn.conv.weight"])
+    # tail_n = 1: the channel mean / max come from the partials se4.fc2's epilogue wrote (no second pass over C1)
+    fused = SAM_FUSED and ops[-1].type == OP_FC and ops[-1].use_row_scale == 4 and ops[-1].n_tiles == 2 and ops[-1].block_n == 256
+    if not fused and ops[-1].type == OP_FC:
+        ops[-1].use_row_scale = 0
     ops.append(_Op(OP_SAM, src=[_hi("C1"), _lo("C1", precision), -1, -1], f0=float(wsa[0, 0, 3, 3]), f1=float(wsa[0, 1, 3, 3]),
-                   name="spatial_attn"))
+                   tail_n=1 if fused else 0, name="spatial_attn"))
     if adapters:
         adapter(4, 1, "C1", "C2", scaled=True)                   # s * x4' + adapter(s * x4') = C2, no row scale left
     return ops
