@@ -8,7 +8,7 @@
 #include <stdint.h>
 
 #define AV1P_BLOB_MAGIC 0x50315641u   /* "AV1P" */
-#define AV1P_BLOB_VERSION 9u
+#define AV1P_BLOB_VERSION 10u
 #define AV1P_BLOB_MAX_NT 8
 #define AV1P_BLOB_MAX_KB 128
 
@@ -17,7 +17,8 @@ enum Av1pOpType : int32_t {
                           // hi/lo weights for float blocks (f0 = acc_scale), planes 2,3 = hi/lo of w / 1023 for integer
                           // frame samples (f1 = acc_scale)
   AV1P_OP_FC = 1,         // block-Toeplitz linear layer on tensor cores
-  AV1P_OP_SAM = 2,        // spatial-attention scalar of `src0` (512 cols) -> row_scale
+  AV1P_OP_SAM = 2,        // spatial-attention scalar of `src0` (512 cols) -> row_scale; tail_n = 1: from the partials of the
+                          // preceding FC op (use_row_scale bit 2) instead of a pass over src0
   AV1P_OP_FGVC_TAIL = 3,  // L2-normalise `src0` (512 cols) + cosine classifier -> logits[4]
   AV1P_OP_SE = 4,         // squeeze-excite on CUDA cores: block_n = channels (64/128/256), n_tiles = positions
   AV1P_OP_CONV_RES = 5,   // 3x3 s1 conv 64->64 on the 4x4 map with SMEM-resident weights (csrc/conv_res_tcgen05.cuh):
@@ -40,7 +41,8 @@ struct Av1pBlobOp {
   int32_t src[4];                   // activation sources (buffer ids, -1 = none).  Split precision: {x_hi, x_lo, y_hi, y_lo}
   int32_t aux, aux_lo, out, out_lo; // buffer ids, -1 = none
   int32_t n_tiles, block_n, epi, tail_n;
-  int32_t use_row_scale;
+  int32_t use_row_scale;            // bit 0: scale the accumulator with the spatial-attention scalar; bit 1: scale the aux operand
+                                    // (FC_EPI_ADD); bit 2: leave the spatial-attention partials of the output behind (se4.fc2)
   int32_t n_kb_total;               // schedule entries
   int32_t n_w_chunks;               // [block_n x 64] fp16 weight tiles stored at w_off
   int32_t pair_mode;                // 1: entries are (x_hi,w_hi),(x_lo,w_lo) pairs; three products per pair

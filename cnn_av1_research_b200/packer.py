@@ -27,7 +27,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import numpy as np
 
 BLOB_MAGIC = 0x50315641
-BLOB_VERSION = 9
+BLOB_VERSION = 10
 MAX_NT = 8
 MAX_KB = 128
 TILE_K = 64
