@@ -937,17 +937,39 @@ struct av1p_cascade {
   int32_t* idx_ab = nullptr;
   int32_t* counts = nullptr;     // [0]=n2, [1]=scratch, [2]=nR, [3]=nA
   RouteScratch* scratch = nullptr;
+  // The two stage-3 specialists are independent (008:105-125): with a second activation region the AB network runs on a
+  // side stream next to the RECT network, so one stage's last (partial) wave and launch gaps overlap the other's work.
+  bool overlap3 = false;
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  ~av1p_cascade() {
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    if (ev_join) cudaEventDestroy(ev_join);
+    if (side) cudaStreamDestroy(side);
+  }
 };
 
 namespace {
 struct CascadeLayout {
   ActLayout act;
+  size_t act2_off;               // second activation region (0 = none: the specialists run back to back)
   size_t logits_off[4], idx_off[3], counts_off, scratch_off, bytes;
 };
+// second region only while it stays small next to 180 GB of HBM (AV1P_STAGE3_OVERLAP=0 disables)
+inline bool stage3_overlap_wanted(size_t act_bytes) {
+  const char* e = getenv("AV1P_STAGE3_OVERLAP");
+  if (e && atoi(e) == 0) return false;
+  return act_bytes <= (size_t(24) << 30);
+}
 CascadeLayout make_cascade_layout(const av1p_model* const models[4], int capacity) {
   CascadeLayout C;
   C.act = make_act_layout(models, 4, capacity);
   size_t o = C.act.bytes;
+  C.act2_off = 0;
+  if (stage3_overlap_wanted(C.act.bytes)) {
+    C.act2_off = align_up(o, 1024);
+    o = C.act2_off + C.act.bytes;
+  }
   const int outs[4] = {1, 3, 2, 4};
   for (int i = 0; i < 4; ++i) {
     C.logits_off[i] = o;
@@ -990,12 +1012,22 @@ extern "C" int av1p_cascade_create(const av1p_model* const models[4], int32_t ca
   av1p_cascade* c = new (std::nothrow) av1p_cascade();
   if (!c) return fail(AV1P_ENOMEM, "host allocation failed");
   c->cap = C.act.cap;
+  c->overlap3 = C.act2_off != 0;
   for (int i = 0; i < 4; ++i) {
-    if (int rc = plan_stage(models[i], C.act, base, &c->stage[i])) {
+    uint8_t* region = (i == 3 && c->overlap3) ? base + C.act2_off : base;
+    if (int rc = plan_stage(models[i], C.act, region, &c->stage[i])) {
       delete c;
       return rc;
     }
     c->logits[i] = reinterpret_cast<float*>(base + C.logits_off[i]);
+  }
+  if (c->overlap3) {
+    if (cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+      delete c;
+      return fail(AV1P_ECUDA, "side stream / events for the stage-3 overlap could not be created");
+    }
   }
   c->idx2 = reinterpret_cast<int32_t*>(base + C.idx_off[0]);
   c->idx_rect = reinterpret_cast<int32_t*>(base + C.idx_off[1]);
@@ -1054,12 +1086,23 @@ extern "C" int av1p_cascade_predict(av1p_cascade* c, const av1p_input* in, int32
   if (int rc = av1p_route_stage2(c->logits[1], c->idx2, n2, n_blocks, c->idx_rect, c->idx_ab, n_rect, l8, l64,
                                  c->scratch, st))
     return rc;
-  // Stage 3 specialists (008:105-125)
-  if (int rc = run_stage(&c->stage[2], si, c->idx_rect, n_rect, n_blocks, c->logits[2], st)) return rc;
-  if (int rc = av1p_finalize_labels(c->logits[2], 2, 2, c->idx_rect, n_rect, n_blocks, l8, l64, st)) return rc;
-  if (int rc = run_stage(&c->stage[3], si, c->idx_ab, n_ab, n_blocks, c->logits[3], st)) return rc;
-  if (int rc = av1p_finalize_labels(c->logits[3], 4, 4, c->idx_ab, n_ab, n_blocks, l8, l64, st)) return rc;
-  return AV1P_OK;
+  // Stage 3 specialists (008:105-125): independent networks on disjoint blocks - AB on the side stream when it has its own
+  // activation region (fork / join with events, which also works under stream capture)
+  cudaStream_t st_ab = st;
+  if (c->overlap3) {
+    CUDA_TRY(cudaEventRecord(c->ev_fork, st));
+    CUDA_TRY(cudaStreamWaitEvent(c->side, c->ev_fork, 0));
+    st_ab = c->side;
+  }
+  int rc = run_stage(&c->stage[2], si, c->idx_rect, n_rect, n_blocks, c->logits[2], st);
+  if (!rc) rc = av1p_finalize_labels(c->logits[2], 2, 2, c->idx_rect, n_rect, n_blocks, l8, l64, st);
+  if (!rc) rc = run_stage(&c->stage[3], si, c->idx_ab, n_ab, n_blocks, c->logits[3], st_ab);
+  if (!rc) rc = av1p_finalize_labels(c->logits[3], 4, 4, c->idx_ab, n_ab, n_blocks, l8, l64, st_ab);
+  if (c->overlap3) {        // always join, also after an error, so that the side stream never outlives the call's ordering
+    cudaEventRecord(c->ev_join, c->side);
+    cudaStreamWaitEvent(st, c->ev_join, 0);
+  }
+  return rc;
 }
 
 // ------------------------------------------------------------------------------ flatten cascade
