@@ -157,6 +157,7 @@ def main():
     ap.add_argument("--precision", default="fp16x3", choices=["fp16x3", "fp16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--chunk", type=int, default=SUB, help="frames per cascade launch")
+    ap.add_argument("--serial-chunks", action="store_true", help="run the chunks of a step back to back on one stream (A/B)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -199,8 +200,11 @@ def main():
     labels_host = torch.empty(F * BPF, dtype=torch.uint8).pin_memory()
 
     def step_resident():
-        for c in range(F // sub):
-            pipe.predict_frames(dev_frames[c * sub * fw:], W4K, H4K, sub, out_u8=labels_dev[c * sub * BPF:(c + 1) * sub * BPF])
+        if args.serial_chunks:
+            for c in range(F // sub):
+                pipe.predict_frames(dev_frames[c * sub * fw:], W4K, H4K, sub, out_u8=labels_dev[c * sub * BPF:(c + 1) * sub * BPF])
+        else:       # consecutive chunks alternate between two cascade plans on two streams (fills partial waves / launch gaps)
+            pipe.predict_frames_pipelined(dev_frames, W4K, H4K, F, chunk_frames=sub, out_u8=labels_dev)
         if world > 1:
             gather_labels(labels_dev, F * world, BPF, rank, world)
 
@@ -316,9 +320,10 @@ def main():
                 "vs_baseline": None, "dtype": "f16 operands (split hi/lo), f32 accumulate" if args.precision == "fp16x3" else "f16 operands, f32 accumulate",
                 "data": "synthetic", "blocks_per_sec": value * BPF,
                 "config": {"workload": "full cascade on a 4K 10-bit synthetic sequence (BASELINE configs[3]), block extraction included",
-                           "frames_per_gpu_per_step": F, "frames_per_launch": sub, "blocks_per_frame": BPF, "threshold": THRESHOLD,
+                           "frames_per_gpu_per_step": F, "frames_per_launch": sub,
+                           "chunk_schedule": "serial, one stream" if args.serial_chunks else "chunks alternate between two cascade plans on two streams", "blocks_per_frame": BPF, "threshold": THRESHOLD,
                            "precision": args.precision, "weights": "calibrated-random seed 0", "routing_mix": mix,
-                           "l2": f"inputs larger than L2: {F * fw * 2 / 1e6:.0f} MB of frames + {pipe.cascade(sub * BPF).workspace.numel() / 1e6:.0f} MB of activations per pass",
+                           "l2": f"inputs larger than L2: {F * fw * 2 / 1e6:.0f} MB of frames + {pipe.cascade(sub * BPF).workspace.numel() * (1 if args.serial_chunks else 2) / 1e6:.0f} MB of workspaces",
                            "label_gather": "torch.distributed gather to rank 0 inside the timed region" if world > 1 else "none (1 GPU)"},
                 "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(F * W4K * H4K * 2 * world),
                         "d2h_bytes_per_step": int(F * BPF * world), "ms_per_step": ms_e2e, "labels_match_resident_path": same},

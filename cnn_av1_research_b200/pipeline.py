@@ -54,14 +54,27 @@ class HierarchicalPipelineV6:
     def _models(self) -> List:
         return [self.stage1_model, self.stage2_model, self.stage3_rect_model, self.stage3_ab_model]
 
-    def cascade(self, n_blocks: int) -> NativeCascade:
+    def cascade(self, n_blocks: int, slot: int = 0) -> NativeCascade:
+        """The cascade plan (and its workspace) with room for n_blocks.  slot 1 is a second, independent plan over the same
+        packed weights: chunked calls alternate between the two on two streams (see predict_frames_pipelined)."""
         natives = [m.native_model(self.device) for m in self._models()]
         key = tuple(id(nm) for nm in natives)
-        if self._cascade is None or self._cascade_key != key or self._cascade.capacity < n_blocks:
-            cap = max(n_blocks, self._min_capacity, 256)
-            self._cascade = NativeCascade(natives, cap)
-            self._cascade_key = key
-        return self._cascade
+        if slot == 0:
+            if self._cascade is None or self._cascade_key != key or self._cascade.capacity < n_blocks:
+                cap = max(n_blocks, self._min_capacity, 256)
+                self._cascade = NativeCascade(natives, cap)
+                self._cascade_key = key
+            return self._cascade
+        twin = getattr(self, "_cascade2", None)
+        if twin is None or self._cascade2_key != key or twin.capacity < n_blocks:
+            self._cascade2 = NativeCascade(natives, max(n_blocks, 256))
+            self._cascade2_key = key
+        return self._cascade2
+
+    def _compute_streams(self):
+        if getattr(self, "_streams2", None) is None:
+            self._streams2 = [torch.cuda.Stream(device=self.device), torch.cuda.Stream(device=self.device)]
+        return self._streams2
 
     @property
     def launches_per_predict(self) -> int:
@@ -150,6 +163,40 @@ class HierarchicalPipelineV6:
 
 
     @torch.no_grad()
+    def predict_frames_pipelined(self, frames: torch.Tensor, width: int, height: int, n_frames: int, chunk_frames: int = 16,
+                                 out_u8: Optional[torch.Tensor] = None, frame_stride: Optional[int] = None) -> torch.Tensor:
+        """predict_frames over a long resident sequence, `chunk_frames` frames per cascade, consecutive chunks alternating
+        between two cascade plans on two streams.  Chunks are independent, so the last (partial) wave and the launch gaps of
+        one chunk's ~110 kernels are filled with the other chunk's work (persistent kernels on 128-row tiles: a stage rarely
+        ends on a full wave).  Same labels as predict_frames; ordered after prior work and before later work of the current
+        stream."""
+        bpf = math.ceil(height / 16) * math.ceil(width / 16)
+        if frame_stride is None:
+            frame_stride = width * height + 2 * ((width // 2) * (height // 2))
+        frames = frames.to(self.device, non_blocking=True)
+        if out_u8 is None:
+            out_u8 = torch.empty(n_frames * bpf, dtype=torch.uint8, device=self.device)
+        chunk = max(1, min(chunk_frames, n_frames))
+        if n_frames <= chunk:
+            return self.predict_frames(frames, width, height, n_frames, out_u8=out_u8, frame_stride=frame_stride)
+        main = torch.cuda.current_stream(self.device)
+        streams = self._compute_streams()
+        for st in streams:
+            st.wait_stream(main)
+        for ci, f0 in enumerate(range(0, n_frames, chunk)):
+            nf = min(chunk, n_frames - f0)
+            k = ci & 1
+            with torch.cuda.stream(streams[k]):
+                inp = N.frames_input(frames[f0 * frame_stride:], width, height, nf, None, frame_stride)
+                self.cascade(chunk * bpf, k).predict(inp, nf * bpf, self.stage1_threshold, out_u8[f0 * bpf:(f0 + nf) * bpf], None)
+        for st in streams:
+            main.wait_stream(st)
+        for t in (frames, out_u8):
+            t.record_stream(streams[0])
+            t.record_stream(streams[1])
+        return out_u8
+
+    @torch.no_grad()
     def predict_frames_host(self, frames_host: torch.Tensor, width: int, height: int, n_frames: int,
                             out_host: Optional[torch.Tensor] = None, chunk_frames: int = 8,
                             frame_stride: Optional[int] = None) -> torch.Tensor:
@@ -183,13 +230,15 @@ class HierarchicalPipelineV6:
         if out_host is None:
             out_host = torch.empty(n_frames * bpf, dtype=torch.uint8).pin_memory()
         main = torch.cuda.current_stream(dev)
-        cascade = self.cascade(chunk * bpf)
+        compute = self._compute_streams()          # consecutive chunks alternate between two cascade plans on two streams
         lib = N.lib()
         esz = frames_host.element_size()
         uploaded = [torch.cuda.Event(), torch.cuda.Event()]
         consumed = [None, None]
         with torch.cuda.device(dev):
             self._copy_stream.wait_stream(main)
+            for st in compute:
+                st.wait_stream(main)
             # Ramp: the first cascade cannot start before its frames have crossed PCIe, so the first chunk is a quarter of
             # the regular size (its upload is the only one that is not hidden behind a cascade).
             first = max(1, chunk // 4) if n_frames > chunk else chunk
@@ -202,11 +251,14 @@ class HierarchicalPipelineV6:
                 N.check(lib.av1p_upload_luma(C.c_void_p(frames_host.data_ptr() + f0 * frame_stride * esz), nf, width, height,
                                              frame_stride, N.ptr(self._staging[b]), self._copy_stream.cuda_stream))
                 uploaded[b].record(self._copy_stream)
-                main.wait_event(uploaded[b])
+                compute[b].wait_event(uploaded[b])
                 inp = N.frames_input(self._staging[b], width, height, nf, width, luma)
-                cascade.predict(inp, nf * bpf, self.stage1_threshold, labels[f0 * bpf:(f0 + nf) * bpf], None)
+                with torch.cuda.stream(compute[b]):
+                    self.cascade(chunk * bpf, b).predict(inp, nf * bpf, self.stage1_threshold, labels[f0 * bpf:(f0 + nf) * bpf], None)
                 consumed[b] = torch.cuda.Event()
-                consumed[b].record(main)
+                consumed[b].record(compute[b])
+            for st in compute:
+                main.wait_stream(st)
             out_host.copy_(labels, non_blocking=True)
         torch.cuda.current_stream(dev).synchronize()
         return out_host

@@ -240,6 +240,19 @@ def test_host_frames_end_to_end_matches_resident(cuda_device):
         pipe.predict_frames_host(host.to(cuda_device), w, h, nf)
 
 
+def test_two_stream_chunk_schedule_matches_single_stream(cuda_device):
+    """predict_frames_pipelined (chunks alternate between two cascade plans on two streams) == predict_frames on the whole
+    sequence, bit for bit: odd chunk count, ragged last chunk, repeated to catch cross-stream races on the shared weights."""
+    w, h, nf = 1280, 720, 7
+    fr = frames_tensor(synth.synth_frames(nf, w, h, seed=55), cuda_device)
+    pipe = build_pipeline(seed=0, threshold=0.45, device=cuda_device)
+    ref = pipe.predict_frames(fr, w, h, nf).cpu()
+    for chunk in (2, 3, 7, 16):
+        for _ in range(3):
+            got = pipe.predict_frames_pipelined(fr, w, h, nf, chunk_frames=chunk).cpu()
+            assert torch.equal(got, ref), f"chunk {chunk}: labels differ from the single-stream pass"
+
+
 def test_config3_full_cascade_on_a_1080p_frame(cuda_device):
     """BASELINE configs[2]: full cascade on one 1920x1080 frame, extraction included (68 x 120 = 8,160 blocks, the last grid
     row is half padding) - every label against the CPU oracle on the same frame."""
