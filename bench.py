@@ -158,6 +158,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--chunk", type=int, default=SUB, help="frames per cascade launch")
     ap.add_argument("--serial-chunks", action="store_true", help="run the chunks of a step back to back on one stream (A/B)")
+    ap.add_argument("--streams", type=int, default=2, help="cascade plans / streams the chunks of a resident step rotate over")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -204,7 +205,7 @@ def main():
             for c in range(F // sub):
                 pipe.predict_frames(dev_frames[c * sub * fw:], W4K, H4K, sub, out_u8=labels_dev[c * sub * BPF:(c + 1) * sub * BPF])
         else:       # consecutive chunks alternate between two cascade plans on two streams (fills partial waves / launch gaps)
-            pipe.predict_frames_pipelined(dev_frames, W4K, H4K, F, chunk_frames=sub, out_u8=labels_dev)
+            pipe.predict_frames_pipelined(dev_frames, W4K, H4K, F, chunk_frames=sub, out_u8=labels_dev, n_streams=args.streams)
         if world > 1:
             gather_labels(labels_dev, F * world, BPF, rank, world)
 
@@ -321,9 +322,9 @@ def main():
                 "data": "synthetic", "blocks_per_sec": value * BPF,
                 "config": {"workload": "full cascade on a 4K 10-bit synthetic sequence (BASELINE configs[3]), block extraction included",
                            "frames_per_gpu_per_step": F, "frames_per_launch": sub,
-                           "chunk_schedule": "serial, one stream" if args.serial_chunks else "chunks alternate between two cascade plans on two streams", "blocks_per_frame": BPF, "threshold": THRESHOLD,
+                           "chunk_schedule": "serial, one stream" if args.serial_chunks else f"chunks rotate over {args.streams} cascade plans, one stream each (host path: two)", "blocks_per_frame": BPF, "threshold": THRESHOLD,
                            "precision": args.precision, "weights": "calibrated-random seed 0", "routing_mix": mix,
-                           "l2": f"inputs larger than L2: {F * fw * 2 / 1e6:.0f} MB of frames + {pipe.cascade(sub * BPF).workspace.numel() * (1 if args.serial_chunks else 2) / 1e6:.0f} MB of workspaces",
+                           "l2": f"inputs larger than L2: {F * fw * 2 / 1e6:.0f} MB of frames + {pipe.cascade(sub * BPF).workspace.numel() * (1 if args.serial_chunks else args.streams) / 1e6:.0f} MB of workspaces",
                            "label_gather": "torch.distributed gather to rank 0 inside the timed region" if world > 1 else "none (1 GPU)"},
                 "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(F * W4K * H4K * 2 * world),
                         "d2h_bytes_per_step": int(F * BPF * world), "ms_per_step": ms_e2e, "labels_match_resident_path": same},

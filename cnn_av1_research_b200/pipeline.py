@@ -44,6 +44,8 @@ class HierarchicalPipelineV6:
         self._cascade: Optional[NativeCascade] = None
         self._cascade_key = None
         self._min_capacity = int(capacity_blocks)
+        self._twins = {}                # slot -> (plan, weights key): extra cascade plans of the multi-stream chunk schedule
+        self._streams: List = []        # their streams
         # predict() on small batches (the reference's evaluate_pipeline feeds 256 blocks per call, 008:278-284) is bound by
         # the ~110 kernel launches of a cascade, not by the GPU: such calls replay a CUDA graph of the whole cascade,
         # captured once per (batch size, threshold) with static input / output buffers.  AV1P_GRAPHS=0 disables.
@@ -55,8 +57,8 @@ class HierarchicalPipelineV6:
         return [self.stage1_model, self.stage2_model, self.stage3_rect_model, self.stage3_ab_model]
 
     def cascade(self, n_blocks: int, slot: int = 0) -> NativeCascade:
-        """The cascade plan (and its workspace) with room for n_blocks.  slot 1 is a second, independent plan over the same
-        packed weights: chunked calls alternate between the two on two streams (see predict_frames_pipelined)."""
+        """The cascade plan (and its workspace) with room for n_blocks.  Slots >= 1 are further, independent plans over the
+        same packed weights: chunked calls rotate over them, one stream each (see predict_frames_pipelined)."""
         natives = [m.native_model(self.device) for m in self._models()]
         key = tuple(id(nm) for nm in natives)
         if slot == 0:
@@ -65,16 +67,16 @@ class HierarchicalPipelineV6:
                 self._cascade = NativeCascade(natives, cap)
                 self._cascade_key = key
             return self._cascade
-        twin = getattr(self, "_cascade2", None)
-        if twin is None or self._cascade2_key != key or twin.capacity < n_blocks:
-            self._cascade2 = NativeCascade(natives, max(n_blocks, 256))
-            self._cascade2_key = key
-        return self._cascade2
+        twin, twin_key = self._twins.get(slot, (None, None))
+        if twin is None or twin_key != key or twin.capacity < n_blocks:
+            twin = NativeCascade(natives, max(n_blocks, 256))
+            self._twins[slot] = (twin, key)
+        return twin
 
-    def _compute_streams(self):
-        if getattr(self, "_streams2", None) is None:
-            self._streams2 = [torch.cuda.Stream(device=self.device), torch.cuda.Stream(device=self.device)]
-        return self._streams2
+    def _compute_streams(self, n: int = 2):
+        while len(self._streams) < n:
+            self._streams.append(torch.cuda.Stream(device=self.device))
+        return self._streams[:n]
 
     @property
     def launches_per_predict(self) -> int:
@@ -164,9 +166,10 @@ class HierarchicalPipelineV6:
 
     @torch.no_grad()
     def predict_frames_pipelined(self, frames: torch.Tensor, width: int, height: int, n_frames: int, chunk_frames: int = 16,
-                                 out_u8: Optional[torch.Tensor] = None, frame_stride: Optional[int] = None) -> torch.Tensor:
-        """predict_frames over a long resident sequence, `chunk_frames` frames per cascade, consecutive chunks alternating
-        between two cascade plans on two streams.  Chunks are independent, so the last (partial) wave and the launch gaps of
+                                 out_u8: Optional[torch.Tensor] = None, frame_stride: Optional[int] = None,
+                                 n_streams: int = 2) -> torch.Tensor:
+        """predict_frames over a long resident sequence, `chunk_frames` frames per cascade, consecutive chunks rotating
+        over `n_streams` (default two) cascade plans, one stream each.  Chunks are independent, so the last (partial) wave and the launch gaps of
         one chunk's ~110 kernels are filled with the other chunk's work (persistent kernels on 128-row tiles: a stage rarely
         ends on a full wave).  Same labels as predict_frames; ordered after prior work and before later work of the current
         stream."""
@@ -180,20 +183,20 @@ class HierarchicalPipelineV6:
         if n_frames <= chunk:
             return self.predict_frames(frames, width, height, n_frames, out_u8=out_u8, frame_stride=frame_stride)
         main = torch.cuda.current_stream(self.device)
-        streams = self._compute_streams()
+        streams = self._compute_streams(max(1, int(n_streams)))
         for st in streams:
             st.wait_stream(main)
         for ci, f0 in enumerate(range(0, n_frames, chunk)):
             nf = min(chunk, n_frames - f0)
-            k = ci & 1
+            k = ci % len(streams)
             with torch.cuda.stream(streams[k]):
                 inp = N.frames_input(frames[f0 * frame_stride:], width, height, nf, None, frame_stride)
                 self.cascade(chunk * bpf, k).predict(inp, nf * bpf, self.stage1_threshold, out_u8[f0 * bpf:(f0 + nf) * bpf], None)
         for st in streams:
             main.wait_stream(st)
         for t in (frames, out_u8):
-            t.record_stream(streams[0])
-            t.record_stream(streams[1])
+            for st in streams:
+                t.record_stream(st)
         return out_u8
 
     @torch.no_grad()
@@ -230,7 +233,7 @@ class HierarchicalPipelineV6:
         if out_host is None:
             out_host = torch.empty(n_frames * bpf, dtype=torch.uint8).pin_memory()
         main = torch.cuda.current_stream(dev)
-        compute = self._compute_streams()          # consecutive chunks alternate between two cascade plans on two streams
+        compute = self._compute_streams(2)         # consecutive chunks alternate between two cascade plans on two streams
         lib = N.lib()
         esz = frames_host.element_size()
         uploaded = [torch.cuda.Event(), torch.cuda.Event()]

@@ -251,6 +251,8 @@ def test_two_stream_chunk_schedule_matches_single_stream(cuda_device):
         for _ in range(3):
             got = pipe.predict_frames_pipelined(fr, w, h, nf, chunk_frames=chunk).cpu()
             assert torch.equal(got, ref), f"chunk {chunk}: labels differ from the single-stream pass"
+    got = pipe.predict_frames_pipelined(fr, w, h, nf, chunk_frames=1, n_streams=3).cpu()
+    assert torch.equal(got, ref), "three streams: labels differ from the single-stream pass"
 
 
 def test_config3_full_cascade_on_a_1080p_frame(cuda_device):
