@@ -609,6 +609,8 @@ int convert_input(const av1p_input* in, StemInput* si) {
     si->pitch = in->pitch;
     si->blocks_x = ceil_div(in->width, 16);
     si->blocks_per_frame = si->blocks_x * ceil_div(in->height, 16);
+    si->inv_bx = ~0ULL / (unsigned long long)si->blocks_x + 1ULL;              // unused when the divisor is 1
+    si->inv_bpf = ~0ULL / (unsigned long long)si->blocks_per_frame + 1ULL;
   } else if (in->kind == 1) {
     if (!in->images_dev) return fail(AV1P_EINVAL, "null image tensor");
     si->images = in->images_dev;

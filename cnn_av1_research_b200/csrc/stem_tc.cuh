@@ -51,6 +51,7 @@ struct StemInput {
   long long frame_stride;   // elements between consecutive frames (Y + U + V)
   int width, height, pitch; // luma geometry, pitch in elements
   int blocks_x, blocks_per_frame;
+  unsigned long long inv_bx, inv_bpf;   // floor(2^64 / d) + 1: __umul64hi(g, inv) == g / d for every 32-bit g (d > 1)
   const float* images;
 };
 
@@ -139,9 +140,12 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_tc_kernel(const __grid_con
       if (tile >= tiles || r >= n) return;
       const int g = p.idx ? __ldg(p.idx + r) : r;
       if (p.in.kind == 0) {
-        const int f = g / p.in.blocks_per_frame;
+        // two divisions per thread per tile as multiply-high by the host's reciprocals (exact, see StemInput)
+        const unsigned ug = unsigned(g);
+        const int f = p.in.blocks_per_frame == 1 ? int(ug) : int(__umul64hi((unsigned long long)ug, p.in.inv_bpf));
         const int gb = g - f * p.in.blocks_per_frame;
-        const int by = gb / p.in.blocks_x, bx = gb - by * p.in.blocks_x;
+        const int by = p.in.blocks_x == 1 ? gb : int(__umul64hi((unsigned long long)unsigned(gb), p.in.inv_bx));
+        const int bx = gb - by * p.in.blocks_x;
         const int y = by * 16 + ppy, x0 = bx * 16 + ppx0;
         if (y < p.in.height) {
           const uint16_t* src = p.in.frames + size_t(f) * p.in.frame_stride + size_t(y) * p.in.pitch + x0;
@@ -201,7 +205,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_tc_kernel(const __grid_con
       uint8_t* s_hi = stages + stage * ST_STAGE_BYTES;
       uint8_t* s_lo = s_hi + ST_P_BYTES;
       const __half* ph_base = pix_hi + cur * 2 * ST_PIX_PLANE;
-#pragma unroll 4
+#pragma unroll
       for (int i = 0; i < (ST_N * 8) / ST_PRODUCERS; ++i) {
         const int row = (tid >> 3) + (ST_PRODUCERS / 8) * i;   // im2col row = block * 64 + conv position
         const int b = row >> 6, pos = row & 63;
