@@ -133,3 +133,19 @@ def test_label_gather_two_ranks_gloo(n_frames):
         assert p.exitcode == 0
     exp = (np.arange(n_frames * bpf) * 7 % 8).astype(np.uint8)
     assert np.array_equal(got, exp)
+
+
+def test_block_coordinate_reciprocals_are_exact():
+    """The stem kernel turns a block id into (frame, grid row, grid column) with __umul64hi(g, floor(2^64 / d) + 1)
+    (csrc/stem_tc.cuh, av1p.cu convert_input) instead of integer division: exact for every 32-bit g and every divisor > 1."""
+    rng = np.random.default_rng(5)
+    divisors = [2, 3, 5, 7, 16, 23, 68, 120, 240, 255, 256, 8160, 32400, 32401, 65535, 65536, 1 << 20, (1 << 31) - 1]
+    divisors += [int(d) for d in rng.integers(2, 1 << 22, size=50)]
+    for d in divisors:
+        inv = ((1 << 64) - 1) // d + 1
+        assert inv < (1 << 64)
+        gs = [0, 1, d - 1, d, d + 1, 2 * d - 1, (1 << 31) - 1, (1 << 32) - 1, ((1 << 32) - 1) // d * d, ((1 << 32) - 1) // d * d - 1]
+        gs += [int(g) for g in rng.integers(0, 1 << 32, size=200)]
+        for g in gs:
+            if 0 <= g < (1 << 32):
+                assert (g * inv) >> 64 == g // d, (g, d)
