@@ -46,6 +46,8 @@ SIGNATURES = {
     "av1p_last_error": (C.c_char_p, []),
     "av1p_version": (C.c_int, []),
     "av1p_debug_watchdog": (C.c_int, []),
+    "av1p_set_option": (C.c_int, [C.c_char_p, C.c_int32]),
+    "av1p_get_option": (C.c_int, [C.c_char_p]),
     "av1p_model_create": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
     "av1p_model_destroy": (None, [C.c_void_p]),
     "av1p_model_num_outputs": (C.c_int, [C.c_void_p]),
@@ -54,6 +56,7 @@ SIGNATURES = {
     "av1p_stage_destroy": (None, [C.c_void_p]),
     "av1p_stage_forward": (C.c_int, [C.c_void_p, C.POINTER(Input), C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "av1p_stage_launches_per_forward": (C.c_int, [C.c_void_p]),
+    "av1p_stage_set_features_out": (C.c_int, [C.c_void_p, C.c_void_p]),
     "av1p_cascade_workspace_bytes": (C.c_size_t, [C.POINTER(C.c_void_p), C.c_int32]),
     "av1p_cascade_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int32, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
     "av1p_cascade_destroy": (None, [C.c_void_p]),

@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(256) se_kernel(const __half* __restrict__ x, c
 __global__ void __launch_bounds__(256) fgvc_tail_kernel(const __half* __restrict__ h, const __half* __restrict__ h_lo,
                                                         int ld, const int* n_dev, int n,
                                                         const float* __restrict__ what, float scale,
-                                                        float* __restrict__ logits) {
+                                                        float* __restrict__ logits, float* __restrict__ features) {
   const int rows = n_dev ? *n_dev : n;
   const int lane = threadIdx.x & 31;
   const int warps_per_grid = (gridDim.x * blockDim.x) >> 5;
@@ -296,6 +296,14 @@ __global__ void __launch_bounds__(256) fgvc_tail_kernel(const __half* __restrict
     ss = warp_sum(ss);
 #pragma unroll
     for (int c = 0; c < 4; ++c) d[c] = warp_sum(d[c]);
+    if (features) {
+      // FGVCModel.forward(x, return_features=True) (006...fgvc.py:290, 294-296): the L2-normalised features, fp32 [rows][512]
+      const float invn = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+      float4* f4 = reinterpret_cast<float4*>(features + size_t(r) * 512 + lane * 16);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        f4[i] = make_float4(x[4 * i] * invn, x[4 * i + 1] * invn, x[4 * i + 2] * invn, x[4 * i + 3] * invn);
+    }
     if (lane == 0) {
       const float inv = scale / fmaxf(sqrtf(ss), 1e-12f);
       *reinterpret_cast<float4*>(logits + size_t(r) * 4) = make_float4(d[0] * inv, d[1] * inv, d[2] * inv, d[3] * inv);

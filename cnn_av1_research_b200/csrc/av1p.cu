@@ -4,6 +4,7 @@
 // every entry point fails with AV1P_ENODEV / AV1P_ECUDA.
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <algorithm>
 #include <cstdarg>
@@ -54,6 +55,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 struct DeviceCtx {
   bool ok = false;
   int sms = 0;
+  int grid_sms = 0;               // SMs a persistent grid may occupy (= sms unless av1p_set_option("grid_sms") / AV1P_GRID_SMS lowers it:
+                                  // two cascades on two streams, each on half of the SMs, run side by side instead of back to back)
   EncodeTiledFn encode = nullptr;
   bool fc_pair = true;            // FC layers on CTA pairs (tcgen05 cta_group::2); AV1P_FC_PAIR=0 selects the single-CTA kernel
   bool fc_resid_epi = false;      // AV1P_FC_RESID_EPI=1: residual FC layers add the identity branch in the epilogue (aux ring)
@@ -62,27 +65,46 @@ struct DeviceCtx {
   int* watchdog_host = nullptr;   // mapped pinned memory: survives a kernel trap
   int* watchdog_dev = nullptr;
 };
-DeviceCtx g_ctx;
+// One context per device ordinal: the >48 KB dynamic shared-memory opt-in (cudaFuncSetAttribute) and the SM count are per
+// device, so a process that builds pipelines on cuda:0 and then on cuda:1 initialises each device on its first use.
+constexpr int MAX_DEVICES = 64;
+DeviceCtx g_ctxs[MAX_DEVICES];
 std::mutex g_ctx_mu;
 
+inline int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEVICES) return 0;
+  return dev;
+}
+inline DeviceCtx& cur_ctx() { return g_ctxs[current_device()]; }
+#define g_ctx (cur_ctx())
+
 int ensure_ctx() {
-  std::lock_guard<std::mutex> lk(g_ctx_mu);
-  if (g_ctx.ok) return AV1P_OK;
   int dev = 0, cc_major = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return fail(AV1P_ENODEV, "no CUDA device: %s", cudaGetErrorString(e));
+  if (dev < 0 || dev >= MAX_DEVICES) return fail(AV1P_ENODEV, "device ordinal %d outside [0, %d)", dev, MAX_DEVICES);
+  std::lock_guard<std::mutex> lk(g_ctx_mu);
+  DeviceCtx& c = g_ctxs[dev];
+  if (c.ok) return AV1P_OK;
   CUDA_TRY(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, dev));
   if (cc_major != 10) return fail(AV1P_ENODEV, "libav1p is built for sm_100a only; device has compute capability %d.x", cc_major);
-  CUDA_TRY(cudaDeviceGetAttribute(&g_ctx.sms, cudaDevAttrMultiProcessorCount, dev));
+  CUDA_TRY(cudaDeviceGetAttribute(&c.sms, cudaDevAttrMultiProcessorCount, dev));
+  c.grid_sms = c.sms;
+  if (const char* e = getenv("AV1P_GRID_SMS")) {
+    const int v = atoi(e);
+    if (v >= 2 && v <= c.sms) c.grid_sms = v & ~1;
+  }
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
   CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
   if (!fn || qres != cudaDriverEntryPointSuccess) return fail(AV1P_ECUDA, "cuTensorMapEncodeTiled not available");
-  g_ctx.encode = reinterpret_cast<EncodeTiledFn>(fn);
+  c.encode = reinterpret_cast<EncodeTiledFn>(fn);
+  // function attributes are per device: set them on THIS device
   CUDA_TRY(cudaFuncSetAttribute(fc_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FC_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(fc_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FC_SMEM_BYTES));
-  if (const char* e = getenv("AV1P_FC_PAIR")) g_ctx.fc_pair = atoi(e) != 0;
-  if (const char* e = getenv("AV1P_FC_RESID_EPI")) g_ctx.fc_resid_epi = atoi(e) != 0;
+  if (const char* e = getenv("AV1P_FC_PAIR")) c.fc_pair = atoi(e) != 0;
+  if (const char* e = getenv("AV1P_FC_RESID_EPI")) c.fc_resid_epi = atoi(e) != 0;
   {
     int n_k = 0;
     const ConvResKernel* ks = conv_res_all_kernels(&n_k);
@@ -90,10 +112,12 @@ int ensure_ctx() {
   }
   CUDA_TRY(cudaFuncSetAttribute(stem_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(stem_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM_BYTES));
-  CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&g_ctx.watchdog_host), sizeof(int), cudaHostAllocMapped));
-  *g_ctx.watchdog_host = 0;
-  CUDA_TRY(cudaHostGetDevicePointer(reinterpret_cast<void**>(&g_ctx.watchdog_dev), g_ctx.watchdog_host, 0));
-  g_ctx.ok = true;
+  CUDA_TRY(cudaFuncSetAttribute(extract_blocks_tma_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, EX_SMEM_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(extract_blocks_tma_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, EX_SMEM_BYTES));
+  CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&c.watchdog_host), sizeof(int), cudaHostAllocMapped));
+  *c.watchdog_host = 0;
+  CUDA_TRY(cudaHostGetDevicePointer(reinterpret_cast<void**>(&c.watchdog_dev), c.watchdog_host, 0));
+  c.ok = true;
   return AV1P_OK;
 }
 
@@ -176,6 +200,33 @@ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 }  // namespace
 
+// Runtime switches of the CURRENT device's context (kernel-development / scheduling experiments; defaults are the product
+// configuration).  "grid_sms": SMs a persistent kernel's grid may occupy (even, 2 .. SM count; 0 restores the SM count).
+extern "C" int av1p_set_option(const char* name, int32_t value) {
+  if (!name) return fail(AV1P_EINVAL, "null option name");
+  if (int rc = ensure_ctx()) return rc;
+  DeviceCtx& c = cur_ctx();
+  if (!strcmp(name, "grid_sms")) {
+    if (value == 0) value = c.sms;
+    if (value < 2 || value > c.sms) return fail(AV1P_EINVAL, "grid_sms %d outside [2, %d]", value, c.sms);
+    c.grid_sms = value & ~1;
+    return AV1P_OK;
+  }
+  if (!strcmp(name, "fc_pair")) {
+    c.fc_pair = value != 0;
+    return AV1P_OK;
+  }
+  return fail(AV1P_EINVAL, "unknown option '%s'", name);
+}
+extern "C" int av1p_get_option(const char* name) {
+  if (!name || ensure_ctx()) return -1;
+  DeviceCtx& c = cur_ctx();
+  if (!strcmp(name, "grid_sms")) return c.grid_sms;
+  if (!strcmp(name, "sms")) return c.sms;
+  if (!strcmp(name, "fc_pair")) return c.fc_pair ? 1 : 0;
+  return -1;
+}
+
 extern "C" int av1p_debug_watchdog(void) { return g_ctx.watchdog_host ? *g_ctx.watchdog_host : 0; }
 
 // One FC layer: `rows` is the host-side upper bound on block rows (sizes the grid).  CTA-pair variant: clusters of two
@@ -183,7 +234,7 @@ extern "C" int av1p_debug_watchdog(void) { return g_ctx.watchdog_host ? *g_ctx.w
 static int launch_fc(const FcParams& f, int rows, cudaStream_t st) {
   const int m_tiles = ceil_div(rows, FC_TILE_M);
   if (g_ctx.fc_pair && f.block_n % 16 == 0) {
-    const int pairs = std::min(g_ctx.sms / 2, ceil_div(m_tiles, 2) * f.n_tiles);
+    const int pairs = std::min(g_ctx.grid_sms / 2, ceil_div(m_tiles, 2) * f.n_tiles);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(unsigned(2 * std::max(pairs, 1)));
     cfg.blockDim = dim3(FC_THREADS);
@@ -198,7 +249,7 @@ static int launch_fc(const FcParams& f, int rows, cudaStream_t st) {
     cfg.numAttrs = 1;
     CUDA_TRY(cudaLaunchKernelEx(&cfg, fc_tcgen05_kernel<true>, f));
   } else {
-    const int grid = std::min(g_ctx.sms, m_tiles * f.n_tiles);
+    const int grid = std::min(g_ctx.grid_sms, m_tiles * f.n_tiles);
     fc_tcgen05_kernel<false><<<grid, FC_THREADS, FC_SMEM_BYTES, st>>>(f);
   }
   return AV1P_OK;
@@ -222,11 +273,15 @@ struct Profiler {
   }
 };
 thread_local Profiler g_prof;
+// NVTX range per kernel class around every launch (a no-op unless a tool such as ncu / nsys is attached): SURVEY.md section 5.
+const char* const PROF_NAMES[PROF_CLASSES] = {"av1p:stem", "av1p:fc_tcgen05", "av1p:spatial_attention", "av1p:fgvc_tail",
+                                              "av1p:route", "av1p:finalize_labels", "av1p:squeeze_excite", "av1p:conv_res_tcgen05"};
 struct ProfScope {
   cudaStream_t st;
   bool active;
   ProfRec r;
   ProfScope(int cls, cudaStream_t s) : st(s), active(g_prof.on) {
+    nvtxRangePushA(PROF_NAMES[cls]);
     if (!active) return;
     r.cls = cls;
     r.a = g_prof.get();
@@ -234,6 +289,7 @@ struct ProfScope {
     cudaEventRecord(r.a, st);
   }
   ~ProfScope() {
+    nvtxRangePop();
     if (!active) return;
     cudaEventRecord(r.b, st);
     g_prof.recs.push_back(r);
@@ -304,6 +360,7 @@ struct av1p_model {
   Av1pBlobHeader hdr;
   std::vector<Av1pBlobOp> ops;
   std::vector<uint32_t> buf_cols;
+  int device = 0;                   // ordinal of the device holding `dev`
 };
 
 extern "C" int av1p_model_create(const void* blob, size_t bytes, av1p_model** out) {
@@ -320,6 +377,7 @@ extern "C" int av1p_model_create(const void* blob, size_t bytes, av1p_model** ou
   av1p_model* m = new (std::nothrow) av1p_model();
   if (!m) return fail(AV1P_ENOMEM, "host allocation failed");
   m->hdr = h;
+  m->device = current_device();
   m->ops.resize(h.n_ops);
   memcpy(m->ops.data(), static_cast<const uint8_t*>(blob) + h.ops_off, h.n_ops * sizeof(Av1pBlobOp));
   m->buf_cols.resize(h.n_bufs);
@@ -337,6 +395,17 @@ extern "C" int av1p_model_create(const void* blob, size_t bytes, av1p_model** ou
           op.w_off + uint64_t(op.n_w_chunks) * op.block_n * 128 > bytes) {
         delete m;
         return fail(AV1P_EINVAL, "malformed FC op");
+      }
+      // the device kernels walk kb_begin[t] .. kb_begin[t + 1] and index kb_src / kb_w with those values: a truncated or
+      // corrupt blob must be rejected here, not turn into out-of-bounds schedule reads and arbitrary TMA coordinates
+      bool sched_ok = op.kb_begin[0] == 0 && op.kb_begin[op.n_tiles] == op.n_kb_total;
+      for (int t = 0; t < op.n_tiles && sched_ok; ++t)
+        sched_ok = op.kb_begin[t] >= 0 && op.kb_begin[t] <= op.kb_begin[t + 1] && op.kb_begin[t + 1] <= op.n_kb_total &&
+                   (!op.pair_mode || ((op.kb_begin[t] | op.kb_begin[t + 1]) & 1) == 0);
+      for (int i = 0; i < op.n_kb_total && sched_ok; ++i) sched_ok = int(op.kb_w[i]) < op.n_w_chunks && (op.kb_src[i] >> 14) < FC_MAX_SRC;
+      if (!sched_ok) {
+        delete m;
+        return fail(AV1P_EINVAL, "malformed FC op: K-block schedule is not monotonic / in range");
       }
     }
   }
@@ -416,6 +485,7 @@ struct av1p_stage {
   float* row_scale = nullptr;
   float* sam_part = nullptr;
   float* own_logits = nullptr;   // unused by the cascade (it passes its own logits buffers)
+  float* features_out = nullptr; // FGVC models: optional fp32 [rows][512] L2-normalised features (av1p_stage_set_features_out)
 };
 
 namespace {
@@ -626,6 +696,9 @@ int run_stage(av1p_stage* s, const StemInput& si, const int32_t* idx, const int3
               cudaStream_t st) {
   if (n <= 0) return AV1P_OK;
   if (n > s->cap) return fail(AV1P_EINVAL, "n=%d exceeds the stage capacity %d", n, s->cap);
+  if (s->model && s->model->device != current_device())
+    return fail(AV1P_EINVAL, "stage was planned on device %d but device %d is current", s->model->device, current_device());
+  int op_index = 0;
   for (PlannedOp& P : s->ops) {
     switch (P.type) {
       case AV1P_OP_STEM: {
@@ -634,7 +707,7 @@ int run_stage(av1p_stage* s, const StemInput& si, const int32_t* idx, const int3
         sp.idx = idx;
         sp.n_dev = n_dev;
         sp.n = n;
-        const int grid = std::min(ceil_div(n, ST_BLOCKS), g_ctx.sms);
+        const int grid = std::min(ceil_div(n, ST_BLOCKS), g_ctx.grid_sms);
         ProfScope ps(PROF_STEM, st);
         if (si.kind == 0) {
           // frames: integer pixel plane + the / 1023 weight set (see stem_tc.cuh, INT_PIX)
@@ -657,7 +730,7 @@ int run_stage(av1p_stage* s, const StemInput& si, const int32_t* idx, const int3
       case AV1P_OP_CONV_RES: {
         P.cr.n_rows_dev = n_dev;
         P.cr.n_rows = n;
-        const int grid = 2 * std::max(1, std::min(g_ctx.sms / 2, ceil_div(n, FC_TILE_M)));      // (M tile, half) items, even grid
+        const int grid = 2 * std::max(1, std::min(g_ctx.grid_sms / 2, ceil_div(n, FC_TILE_M)));      // (M tile, half) items, even grid
         ProfScope ps(PROF_CONV, st);
         conv_res_kernel_for(P.cr)<<<grid, CR_THREADS, CR_SMEM_BYTES, st>>>(P.cr);
         break;
@@ -688,12 +761,15 @@ int run_stage(av1p_stage* s, const StemInput& si, const int32_t* idx, const int3
       case AV1P_OP_FGVC_TAIL: {
         const int grid = std::min(ceil_div(n, 8), g_ctx.sms * 8);
         ProfScope ps(PROF_FGVC, st);
-        fgvc_tail_kernel<<<grid, 256, 0, st>>>(P.src, P.src_lo, P.ld, n_dev, n, P.w, P.f0, logits);
+        fgvc_tail_kernel<<<grid, 256, 0, st>>>(P.src, P.src_lo, P.ld, n_dev, n, P.w, P.f0, logits, s->features_out);
         break;
       }
     }
+    // a launch that fails (bad configuration, missing shared-memory opt-in ...) is reported at the op that caused it
+    if (cudaError_t e = cudaGetLastError(); e != cudaSuccess)
+      return fail(AV1P_ECUDA, "launch of op %d (type %d) failed: %s", op_index, P.type, cudaGetErrorString(e));
+    ++op_index;
   }
-  CUDA_TRY(cudaGetLastError());
   return AV1P_OK;
 }
 
@@ -722,6 +798,17 @@ extern "C" int av1p_stage_create(const av1p_model* m, int32_t capacity_rows, voi
 }
 extern "C" void av1p_stage_destroy(av1p_stage* s) { delete s; }
 extern "C" int av1p_stage_launches_per_forward(const av1p_stage* s) { return s ? int(s->ops.size()) : 0; }
+
+// FGVCModel.forward(x, return_features=True) (scripts/006_train_stage3_ab_fgvc.py:277-296): the next forwards of this stage
+// also write the L2-normalised 512-wide features (fp32 [rows][512], caller-owned); nullptr switches it off.
+extern "C" int av1p_stage_set_features_out(av1p_stage* s, float* features_dev) {
+  if (!s) return fail(AV1P_EINVAL, "null stage");
+  bool has_tail = false;
+  for (const PlannedOp& P : s->ops) has_tail |= P.type == AV1P_OP_FGVC_TAIL;
+  if (features_dev && !has_tail) return fail(AV1P_EINVAL, "this model has no FGVC tail: no features to return");
+  s->features_out = features_dev;
+  return AV1P_OK;
+}
 
 extern "C" int av1p_stage_forward(av1p_stage* s, const av1p_input* in, const int32_t* idx_dev, const int32_t* n_dev,
                                   int32_t n, float* logits_dev, void* stream) {
@@ -902,7 +989,6 @@ static int launch_extract(const uint16_t* y, int w, int h, int pitch, int bs, OU
       const int tpb = 64 / bs;
       const long long tiles = (long long)n_frames * ceil_div(by, tpb) * ceil_div(bx, tpb);
       const int grid = int(std::min<long long>(tiles, (long long)g_ctx.sms * 4));
-      CUDA_TRY(cudaFuncSetAttribute(extract_blocks_tma_kernel<OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, EX_SMEM_BYTES));
       extract_blocks_tma_kernel<OUT><<<grid, EX_THREADS, EX_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(map, bs, bx, by, n_frames, out);
       CUDA_TRY(cudaGetLastError());
       return AV1P_OK;
@@ -1314,7 +1400,7 @@ extern "C" int av1p_conv_res_forward(const av1p_conv_res_desc* d, void* stream) 
   f.err_flag = g_ctx.watchdog_dev;
   if (!conv_res_build_schedule(f)) return fail(AV1P_EINVAL, "resident-conv schedule does not fit its tables");
   if (const char* dbg = getenv("AV1P_CR_DEBUG")) f.debug = atoi(dbg);   // kernel-development switch of this test hook only
-  const int grid = 2 * std::max(1, std::min(g_ctx.sms / 2, ceil_div(d->rows, FC_TILE_M)));
+  const int grid = 2 * std::max(1, std::min(g_ctx.grid_sms / 2, ceil_div(d->rows, FC_TILE_M)));
   conv_res_kernel_for(f)<<<grid, CR_THREADS, CR_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(f);
   CUDA_TRY(cudaGetLastError());
   return AV1P_OK;

@@ -124,6 +124,18 @@ def stage1_logits(model, dataloader, device) -> Tuple[torch.Tensor, torch.Tensor
     return torch.cat(logits), torch.cat(labels)
 
 
+def comparison_threshold(t) -> float:
+    """The value `all_probs >= t` (007:47) actually compares a float32 probability with.
+
+    NumPy decides by the threshold's TYPE: an np.float64 (what 007's `np.arange` grid yields) is a strong double, the
+    float32 probabilities are widened and compared exactly against it; a Python float (evaluate_with_threshold(..., 0.45))
+    is a weak scalar, the comparison happens in float32, i.e. against float32(t) - the same value the cascade's own
+    fp32 stage-1 threshold uses.  np.float32 / np.float16 scalars compare in float32 as well."""
+    if isinstance(t, np.floating) and t.dtype == np.float64:
+        return float(t)
+    return float(np.float32(t))
+
+
 def sweep_counts(logits: torch.Tensor, labels: torch.Tensor, thresholds: Sequence[float],
                  want_probs: bool = False) -> Tuple[np.ndarray, Optional[torch.Tensor]]:
     """Confusion counts int64 [T,4] = {tn, fp, fn, tp} for every threshold, one kernel pass per 32 thresholds."""
@@ -133,7 +145,7 @@ def sweep_counts(logits: torch.Tensor, labels: torch.Tensor, thresholds: Sequenc
     labels = labels.contiguous().reshape(-1).to(torch.uint8)
     if logits.numel() != labels.numel():
         raise ValueError("logits and labels differ in length")
-    thr = np.asarray(list(thresholds), dtype=np.float64)
+    thr = np.asarray([comparison_threshold(t) for t in thresholds], dtype=np.float64)
     dev = logits.device
     out = np.zeros((len(thr), 4), dtype=np.int64)
     probs = torch.empty_like(logits) if want_probs else None

@@ -187,7 +187,7 @@ class _NativeStageModule(nn.Module):
             self._native_key = key
         return self._native_model
 
-    def _native_forward(self, x: torch.Tensor) -> torch.Tensor:
+    def _native_forward(self, x: torch.Tensor, want_features: bool = False):
         if self.training:
             raise RuntimeError(f"{type(self).__name__}: only eval-mode inference is implemented on the B200 path; call .eval()")
         if not x.is_cuda:
@@ -199,7 +199,11 @@ class _NativeStageModule(nn.Module):
         model = self.native_model(x.device)
         if self._native_stage is None or self._native_stage.capacity < n:
             self._native_stage = NativeStage(model, max(n, 256))
-        return self._native_stage.forward(N.images_input(x), n)
+        if not want_features:
+            return self._native_stage.forward(N.images_input(x), n)
+        features = torch.empty((n, 512), dtype=torch.float32, device=x.device)
+        logits = self._native_stage.forward(N.images_input(x), n, features=features)
+        return logits, features
 
 
 class Stage1Model(_NativeStageModule):
@@ -331,6 +335,5 @@ class FGVCModel(_NativeStageModule):
         self.feat_dim = feat_dim
 
     def forward(self, x, return_features: bool = False):
-        if return_features:
-            raise NotImplementedError("return_features=True is a training-time (center loss) option; not on the inference path")
-        return self._native_forward(x)
+        # 006...fgvc.py:294-296: (logits, L2-normalised features) when return_features is set
+        return self._native_forward(x, want_features=bool(return_features))

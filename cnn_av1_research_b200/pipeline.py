@@ -268,13 +268,17 @@ class HierarchicalPipelineV6:
 
 
 def evaluate_pipeline(pipeline, dataloader, class_names=None):
-    """Batch loop of 008:130-147: returns {'predictions', 'labels'} as numpy arrays.
-
-    The sklearn report / confusion-matrix post-processing of 008:149-163 is host-side analysis outside
-    the hot path and is left to the caller.
-    """
+    """Evaluate the pipeline over a dataset (008:130-163): the batch loop over {'image', 'label_stage0'} batches and the
+    reference's result dictionary with its five keys - 'predictions', 'labels' (numpy), 'metrics'
+    (metrics.compute_metrics), 'classification_report' (text) and 'confusion_matrix' (nested list)."""
+    from .metrics import classification_report_text, compute_metrics, confusion_counts
     preds, labels = [], []
     for batch in dataloader:
         preds.append(pipeline.predict(batch["image"]))
         labels.append(batch["label_stage0"])
-    return {"predictions": torch.cat(preds).numpy(), "labels": torch.cat(labels).numpy()}
+    all_preds = torch.cat(preds).numpy()
+    all_labels = torch.cat(labels).cpu().numpy()
+    return {"predictions": all_preds, "labels": all_labels,
+            "metrics": compute_metrics(all_labels, all_preds, labels=class_names),
+            "classification_report": classification_report_text(all_labels, all_preds, target_names=class_names),
+            "confusion_matrix": confusion_counts(all_labels, all_preds)[1].tolist()}

@@ -57,7 +57,9 @@ class NativeStage:
         self.launches_per_forward = N.lib().av1p_stage_launches_per_forward(handle)
 
     def forward(self, inp: N.Input, n: int, idx: Optional[torch.Tensor] = None, n_dev: Optional[torch.Tensor] = None,
-                out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                out: Optional[torch.Tensor] = None, features: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Logits [n, outputs].  `features` (FGVC models only): float32 [n, 512] buffer that receives the L2-normalised
+        features of 006...fgvc.py:290."""
         if n > self.capacity:
             raise N.Av1pError(f"{n} rows exceed the stage capacity {self.capacity}")
         dev = self.model.device
@@ -65,9 +67,18 @@ class NativeStage:
             out = torch.empty((n, self.model.num_outputs), dtype=torch.float32, device=dev)
         if n == 0:
             return out
+        if features is not None and (features.dtype != torch.float32 or features.numel() < n * 512):
+            raise N.Av1pError("features must be a float32 buffer of at least n * 512 elements")
         with torch.cuda.device(dev):
-            N.check(N.lib().av1p_stage_forward(self.handle, C.byref(inp), N.ptr(idx), N.ptr(n_dev), n, N.ptr(out),
+            lib = N.lib()
+            if features is not None:
+                N.check(lib.av1p_stage_set_features_out(self.handle, N.ptr(features)))
+            try:
+                N.check(lib.av1p_stage_forward(self.handle, C.byref(inp), N.ptr(idx), N.ptr(n_dev), n, N.ptr(out),
                                                N.stream_handle(dev)))
+            finally:
+                if features is not None:
+                    lib.av1p_stage_set_features_out(self.handle, None)
         return out
 
     def __del__(self):

@@ -48,6 +48,13 @@ const char* av1p_last_error(void);
 int av1p_version(void);
 /* Value written by a kernel watchdog (pipeline barrier that never completed), 0 if none. */
 int av1p_debug_watchdog(void);
+/* Per-device runtime switches (the reference has no counterpart: scheduling knobs of this build).  Every device
+ * ordinal has its own context, initialised on first use while that device is current (cudaSetDevice / torch.cuda.device).
+ *   "grid_sms": SMs a persistent kernel's grid may occupy (even, 2 .. SM count; 0 restores the SM count);
+ *   "fc_pair" : 1 = FC layers on CTA pairs (default), 0 = single-CTA kernel.
+ * av1p_get_option also answers "sms"; it returns -1 for an unknown name. */
+int av1p_set_option(const char* name, int32_t value);
+int av1p_get_option(const char* name);
 
 /* ---- model: replaces nn.Module construction + load_state_dict + .to(device).eval()
  *      (pesquisa_v6/scripts/008_run_pipeline_eval_v6.py:219-250, models.py:206-251,
@@ -71,6 +78,9 @@ void av1p_stage_destroy(av1p_stage* s);
  * logits_dev: float32 [n][num_outputs]. */
 int av1p_stage_forward(av1p_stage* s, const av1p_input* in, const int32_t* idx_dev, const int32_t* n_dev, int32_t n,
                        float* logits_dev, void* stream);
+/* FGVCModel.forward(x, return_features=True) (scripts/006_train_stage3_ab_fgvc.py:277-296): when set, forwards of an
+ * FGVC stage also write the L2-normalised features, fp32 [rows][512], into the caller's buffer; NULL switches it off. */
+int av1p_stage_set_features_out(av1p_stage* s, float* features_dev);
 
 /* ---- full cascade: replaces HierarchicalPipelineV6.__init__/predict (008:41-127).
  *      models[] = {stage1, stage2, stage3_rect, stage3_ab}.  Labels use predict()'s label space:

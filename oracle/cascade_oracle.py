@@ -136,8 +136,8 @@ def _mlp_head(sd: StateDict, f: torch.Tensor, linear_ids) -> torch.Tensor:
     return f
 
 
-def stage_logits(kind: str, sd: StateDict, x: torch.Tensor) -> torch.Tensor:
-    """Logits of one stage network.
+def stage_logits(kind: str, sd: StateDict, x: torch.Tensor, return_features: bool = False):
+    """Logits of one stage network ('ab_fgvc' with return_features: (logits, L2-normalised features), 006...fgvc.py:294-296).
 
     kind: 'stage1' (models.py:129-149,206-215; apply_temp=False so no temperature division),
           'stage2' (:152-167), 'rect' (:170-185), 'ab' (Stage3ABModel :188-203),
@@ -164,7 +164,8 @@ def stage_logits(kind: str, sd: StateDict, x: torch.Tensor) -> torch.Tensor:
                 f = F.relu(_bn(f, sd, f"feat_proj.{bn}"))
             f = F.normalize(f, p=2, dim=1)                                   # eps 1e-12
             w = F.normalize(sd["classifier.weight"], p=2, dim=1)
-            return 20.0 * F.linear(f, w)
+            logits = 20.0 * F.linear(f, w)
+            return (logits, f) if return_features else logits
         raise ValueError(kind)
 
 
@@ -175,6 +176,18 @@ def route_stage1(logits: torch.Tensor, threshold: float) -> torch.Tensor:
     """008:77-85: sigmoid (fp32) -> squeeze -> >= thr -> ascending indices of PARTITION blocks."""
     probs = torch.sigmoid(logits.float()).reshape(-1)
     return (probs >= threshold).nonzero(as_tuple=True)[0]
+
+
+def stage1_filter(sd_stage1: StateDict, samples: torch.Tensor, threshold: float, batch_size: int = 256):
+    """filter_dataset_through_stage1 (scripts/004c_train_stage2_pipeline_aware.py:181-201): batches of `batch_size` through
+    Stage 1, probs = sigmoid(logits.squeeze()), keep prob >= threshold.  Returns (original_indices int64, stage1_probs float32)."""
+    idx, probs = [], []
+    for b0 in range(0, samples.shape[0], batch_size):
+        p = torch.sigmoid(stage_logits("stage1", sd_stage1, samples[b0:b0 + batch_size]).reshape(-1))
+        mask = p >= threshold
+        idx.append(torch.where(mask)[0] + b0)
+        probs.append(p[mask])
+    return torch.cat(idx).numpy().astype(np.int64), torch.cat(probs).numpy().astype(np.float32)
 
 
 def argmax_softmax(logits: torch.Tensor) -> torch.Tensor:
@@ -247,12 +260,13 @@ def flatten_predict(sd_stage1: StateDict, sd_flat: StateDict, images: torch.Tens
 
 def threshold_confusion(logits1: torch.Tensor, labels_stage1: np.ndarray, thresholds) -> np.ndarray:
     """Confusion counts {tn, fp, fn, tp} per threshold as evaluate_with_threshold computes them
-    (scripts/007_optimize_thresholds.py:36-58): float32 sigmoid probabilities as a numpy array compared with np.float64
-    thresholds (np.arange, :153) - a float64 comparison under NumPy >= 2."""
+    (scripts/007_optimize_thresholds.py:36-58): float32 sigmoid probabilities as a numpy array compared with each
+    threshold AS GIVEN - np.float64 grid values (np.arange, :153) compare in float64, a Python float compares in float32
+    (NumPy's scalar promotion decides, exactly as in the reference's `all_probs >= threshold`)."""
     probs = torch.sigmoid(logits1.float()).reshape(-1).numpy()
     lab = np.asarray(labels_stage1).reshape(-1).astype(np.int64)
     out = np.zeros((len(thresholds), 4), dtype=np.int64)
-    for i, t in enumerate(np.asarray(thresholds, dtype=np.float64)):
+    for i, t in enumerate(thresholds):
         pred = (probs >= t).astype(np.int64)
         for c in range(4):
             out[i, c] = int(np.sum(lab * 2 + pred == c))
