@@ -114,8 +114,9 @@ int ensure_ctx() {
   CUDA_TRY(cudaFuncSetAttribute(stem_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(extract_blocks_tma_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, EX_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(extract_blocks_tma_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, EX_SMEM_BYTES));
-  CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&c.watchdog_host), sizeof(int), cudaHostAllocMapped));
-  *c.watchdog_host = 0;
+  CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&c.watchdog_host), 2 * sizeof(int), cudaHostAllocMapped));
+  c.watchdog_host[0] = 0;      // [0] watchdog tag of a pipeline barrier that never completed
+  c.watchdog_host[1] = 0;      // [1] a frame sample above 2048 reached the integer-pixel stem (see stem_tc.cuh, INT_PIX)
   CUDA_TRY(cudaHostGetDevicePointer(reinterpret_cast<void**>(&c.watchdog_dev), c.watchdog_host, 0));
   c.ok = true;
   return AV1P_OK;
@@ -228,6 +229,15 @@ extern "C" int av1p_get_option(const char* name) {
 }
 
 extern "C" int av1p_debug_watchdog(void) { return g_ctx.watchdog_host ? *g_ctx.watchdog_host : 0; }
+// 1 if a frame-input cascade on the current device met a luma sample above 2048 since the last call (reads and clears; the
+// caller synchronises the stream first).  Such content is not 10-bit: the frame path rounds it, predict(images) does not.
+extern "C" int av1p_input_range_flag(void) {
+  DeviceCtx& c = cur_ctx();
+  if (!c.watchdog_host) return 0;
+  const int v = c.watchdog_host[1];
+  c.watchdog_host[1] = 0;
+  return v;
+}
 
 // One FC layer: `rows` is the host-side upper bound on block rows (sizes the grid).  CTA-pair variant: clusters of two
 // CTAs, each pair takes two M tiles of an item.

@@ -18,8 +18,9 @@
 //   INT_PIX   : frame input (kind 0).  A 10-bit sample is an integer that fp16 holds exactly, so the pixel tile keeps the
 //               raw integers in ONE plane and the /1023 moves into a second weight set (w / 1023 folded in float64 by the
 //               packer, split hi/lo): two products W_hi.P + W_lo.P instead of three and half the im2col traffic.
-//               (Exact for samples < 2048; a sample above that is rounded to fp16's 11 bits - such a value is outside
-//               the 10-bit format the reference's reader warns about, 005:198-204.)
+//               (Exact for samples <= 2048; a sample above that is rounded to fp16's 11 bits - such a value is outside
+//               the 10-bit format the reference's reader warns about, 005:198-204.  The kernel raises a sticky flag,
+//               av1p_input_range_flag(), and the Python frame entry points that synchronise turn it into an error.)
 // Because the channels are the accumulator rows (TMEM lanes), one epilogue thread owns a channel and sees all
 // 64 conv positions of a block in its columns: bias, ReLU and the 3x3/s2 max-pool run in registers, and a warp
 // stores 32 consecutive channels (64 contiguous bytes) per pooled position.
@@ -182,6 +183,12 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_tc_kernel(const __grid_con
       } else {
 #pragma unroll
         for (int j = 0; j < 4; ++j) x[j] = __uint_as_float(raw[j]);
+      }
+      if (INT_PIX && fmaxf(fmaxf(x[0], x[1]), fmaxf(x[2], x[3])) > 2048.0f && p.err_flag) {
+        // outside the 10-bit format (the reference's reader warns above 1023, 005:198-204, and passes the value on): the
+        // single integer plane is exact only up to 2048, so the caller is told (sticky flag next to the watchdog word,
+        // read by av1p_input_range_flag) instead of silently diverging from predict(images)
+        p.err_flag[1] = 1;
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {                   // o is odd: scalar fp16 stores

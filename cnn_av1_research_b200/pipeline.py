@@ -167,12 +167,13 @@ class HierarchicalPipelineV6:
     @torch.no_grad()
     def predict_frames_pipelined(self, frames: torch.Tensor, width: int, height: int, n_frames: int, chunk_frames: int = 16,
                                  out_u8: Optional[torch.Tensor] = None, frame_stride: Optional[int] = None,
-                                 n_streams: int = 2) -> torch.Tensor:
+                                 n_streams: int = 2, on_chunk=None) -> torch.Tensor:
         """predict_frames over a long resident sequence, `chunk_frames` frames per cascade, consecutive chunks rotating
         over `n_streams` (default two) cascade plans, one stream each.  Chunks are independent, so the last (partial) wave and the launch gaps of
         one chunk's ~110 kernels are filled with the other chunk's work (persistent kernels on 128-row tiles: a stage rarely
         ends on a full wave).  Same labels as predict_frames; ordered after prior work and before later work of the current
-        stream."""
+        stream.  `on_chunk(first_frame, n_frames)` is called on the chunk's stream right after its cascade has been enqueued
+        (the sharded bench hangs the per-chunk label gather there, sharding.ChunkedLabelGather)."""
         bpf = math.ceil(height / 16) * math.ceil(width / 16)
         if frame_stride is None:
             frame_stride = width * height + 2 * ((width // 2) * (height // 2))
@@ -181,7 +182,10 @@ class HierarchicalPipelineV6:
             out_u8 = torch.empty(n_frames * bpf, dtype=torch.uint8, device=self.device)
         chunk = max(1, min(chunk_frames, n_frames))
         if n_frames <= chunk:
-            return self.predict_frames(frames, width, height, n_frames, out_u8=out_u8, frame_stride=frame_stride)
+            out = self.predict_frames(frames, width, height, n_frames, out_u8=out_u8, frame_stride=frame_stride)
+            if on_chunk is not None:
+                on_chunk(0, n_frames)
+            return out
         main = torch.cuda.current_stream(self.device)
         streams = self._compute_streams(max(1, int(n_streams)))
         for st in streams:
@@ -192,6 +196,8 @@ class HierarchicalPipelineV6:
             with torch.cuda.stream(streams[k]):
                 inp = N.frames_input(frames[f0 * frame_stride:], width, height, nf, None, frame_stride)
                 self.cascade(chunk * bpf, k).predict(inp, nf * bpf, self.stage1_threshold, out_u8[f0 * bpf:(f0 + nf) * bpf], None)
+                if on_chunk is not None:
+                    on_chunk(f0, nf)
         for st in streams:
             main.wait_stream(st)
         for t in (frames, out_u8):
@@ -264,7 +270,20 @@ class HierarchicalPipelineV6:
                 main.wait_stream(st)
             out_host.copy_(labels, non_blocking=True)
         torch.cuda.current_stream(dev).synchronize()
+        self.check_input_range(synchronize=False)
         return out_host
+
+    def check_input_range(self, synchronize: bool = True) -> None:
+        """Raise if a frame-input call since the last check met a luma sample above 2048.  The reference never masks samples
+        (read_y_component only warns above 1023, 005:198-204; to_torch divides whatever uint16 it gets); the fused frame path
+        keeps a sample as one fp16 integer, exact up to 2048, so 12-bit or corrupt content must go through
+        predict(images) (float blocks, no such limit) instead of silently diverging."""
+        if synchronize:
+            torch.cuda.synchronize(self.device)
+        with torch.cuda.device(self.device):
+            if N.lib().av1p_input_range_flag():
+                raise N.Av1pError("frame input holds luma samples above 2048 (not 10-bit content): the fused frame path is exact "
+                                  "for samples <= 2048 only - extract the blocks and call predict(images) for such data")
 
 
 def evaluate_pipeline(pipeline, dataloader, class_names=None):

@@ -48,6 +48,11 @@ const char* av1p_last_error(void);
 int av1p_version(void);
 /* Value written by a kernel watchdog (pipeline barrier that never completed), 0 if none. */
 int av1p_debug_watchdog(void);
+/* Frame input (kind 0) is 10-bit content (005:198-204 warns above 1023).  The fused extraction keeps a sample as one fp16
+ * integer, exact up to 2048; larger values (12-bit / corrupt data) are rounded, where the reference would divide the exact
+ * value.  Returns 1 - and clears the flag - if such a sample was met on the current device since the last call; synchronise
+ * the stream first.  Callers with out-of-range content use the float-block entry (kind 1), which has no such limit. */
+int av1p_input_range_flag(void);
 /* Per-device runtime switches (the reference has no counterpart: scheduling knobs of this build).  Every device
  * ordinal has its own context, initialised on first use while that device is current (cudaSetDevice / torch.cuda.device).
  *   "grid_sms": SMs a persistent kernel's grid may occupy (even, 2 .. SM count; 0 restores the SM count);

@@ -214,12 +214,13 @@ def cascade_predict(sds: Dict[str, StateDict], images: torch.Tensor, threshold: 
         return torch.cat([stage_logits(kind, sds[kind], x[i:i + chunk]) for i in range(0, x.shape[0], chunk)])
 
     n = images.shape[0]
-    out = {"labels": torch.zeros(n, dtype=torch.int64)}
+    dev = images.device                 # the reference builds final_preds on the pipeline's device (008:82), .cpu() at the end
+    out = {"labels": torch.zeros(n, dtype=torch.int64, device=dev)}
     l1 = run("stage1", images)
     idx2 = route_stage1(l1, threshold)
     out.update(logits1=l1, idx2=idx2)
-    empty_f = lambda k: torch.zeros(0, k)
-    empty_i = torch.zeros(0, dtype=torch.int64)
+    empty_f = lambda k: torch.zeros(0, k, device=dev)
+    empty_i = torch.zeros(0, dtype=torch.int64, device=dev)
     out.update(logits2=empty_f(3), idx_rect=empty_i, idx_ab=empty_i, logits_rect=empty_f(2), logits_ab=empty_f(4))
     if idx2.numel() == 0:
         return out

@@ -135,6 +135,51 @@ def test_label_gather_two_ranks_gloo(n_frames):
     assert np.array_equal(got, exp)
 
 
+def _gloo_chunk_worker(rank, world, port, n_frames, bpf, chunk, q):
+    import torch.distributed as dist
+    from cnn_av1_research_b200.sharding import ChunkedLabelGather
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    g = ChunkedLabelGather(n_frames, bpf, rank, world, "cpu")
+    results = []
+    for step in range(2):                                   # buffers are reused across steps
+        # every rank loops over the LARGEST shard in chunks (equal-sized collectives), filling only its own frames
+        for f0 in range(0, g.max_count, chunk):
+            nf = min(chunk, g.max_count - f0)
+            own = max(0, min(nf, g.count - f0))
+            ids = torch.arange((g.first + f0) * bpf, (g.first + f0 + own) * bpf)
+            g.local[f0 * bpf:(f0 + own) * bpf] = ((ids + step) * 7 % 8).to(torch.uint8)
+            g.gather_chunk(f0, nf)
+        full = g.finish()
+        if rank == 0:
+            results.append(full.numpy().copy())
+        else:
+            assert full is None
+    if rank == 0:
+        q.put(results)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_frames,chunk", [(8, 2), (5, 2), (3, 4)])
+def test_chunked_label_gather_two_ranks_gloo(n_frames, chunk):
+    """sharding.ChunkedLabelGather (one async gather per cascade chunk, the strong-scaling bench's result path): global frame
+    order on rank 0, uneven shards, a chunk larger than the shard, buffers reused by a second step."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000 + 10 * n_frames + chunk
+    bpf = 23 * 40
+    procs = [ctx.Process(target=_gloo_chunk_worker, args=(r, 2, port, n_frames, bpf, chunk, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    for step, full in enumerate(got):
+        assert np.array_equal(full, ((np.arange(n_frames * bpf) + step) * 7 % 8).astype(np.uint8)), step
+
+
 def test_block_coordinate_reciprocals_are_exact():
     """The stem kernel turns a block id into (frame, grid row, grid column) with __umul64hi(g, floor(2^64 / d) + 1)
     (csrc/stem_tc.cuh, av1p.cu convert_input) instead of integer division: exact for every 32-bit g and every divisor > 1."""
