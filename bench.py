@@ -24,8 +24,8 @@ Keys of the JSON line beyond the base contract:
                 own; strong scaling additionally compares the gathered 64-frame vector with a 1-GPU pass on rank 0.
 `cpu_baseline`  the oracle port of the reference's PyTorch CPU path (identical torch fp32 ops, all host threads) on one
                 4K frame: whole-frame calls (`value`) and the reference's default 256-block batches (`batch256_value`).
-`gpu_reference` the same oracle-port modules on THIS B200 through PyTorch (cuDNN / cuBLAS): eager fp32 with TF32 off and
-                bf16 + channels_last, whole-frame and 256-block batches - the "kernel to beat on the same box".
+`gpu_reference` the same oracle-port modules on THIS B200 through PyTorch (cuDNN / cuBLAS): eager fp32 (PyTorch defaults and
+                TF32 off) and bf16 + channels_last, whole-frame and 256-block batches - the "kernel to beat on the same box".
 `configs`       BASELINE configs 1-3 measured in the same run (Stage-1 B = 256; Stage-2 on routed blocks; one 1080p frame).
 """
 import argparse
@@ -120,6 +120,16 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def workload_config(args, world):
+    """The `config` both arms print: the workload only, nothing run-dependent (measured details go under `details`)."""
+    strong = args.scaling == "strong"
+    return {"workload": "full cascade on a 4K 10-bit synthetic sequence (BASELINE configs[3]), block extraction included",
+            "frames_per_step_whole_job": args.frames if strong else args.frames * world,
+            "sharding": "one sequence, contiguous frame ranges per rank" if strong else "every rank has its own sequence",
+            "frame": "3840x2160 YUV420p10le", "blocks_per_frame": BPF, "threshold": THRESHOLD,
+            "weights": "calibrated-random seed 0", "l2": "inputs larger than L2 (1.6 GB of frames per rank per step)"}
+
+
 # ------------------------------------------------------------------------------------------------ CPU reference arm
 def oracle_cpu_pass(words, n_frames, chunk):
     """One pass of the reference's CPU path (oracle port): extraction + /1023 + cascade; chunk = blocks per predict call."""
@@ -155,21 +165,19 @@ def run_reference(args, rank, world, log):
     if rank != 0:
         return
     n = 1
-    warm = min(args.warmup, 1)
+    warm = args.warmup
     fps, cores, _ = oracle_cpu_frames_per_sec(n, args.steps, warm, log)
     fps256, _, _ = oracle_cpu_frames_per_sec(n, 1, 0, log, chunk=256)
     line = {"impl": "reference", "metric": "4k_10bit_frames_per_sec_full_cascade", "value": fps, "unit": "frames/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": warm, "ms_per_step": 1e3 * n / fps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "blocks_per_sec": fps * BPF,
-            "config": {"workload": "full cascade on a 4K 10-bit synthetic sequence (BASELINE configs[3]), block extraction included",
-                       "sample": "bounded sample of that workload: 1 synthetic 3840x2160 YUV420p10le frame per step "
-                                 "(extraction + /1023 + Stage1->Stage2->Stage3), the metric is per frame",
-                       "frames_per_step": n, "blocks_per_frame": BPF, "threshold": THRESHOLD, "weights": "calibrated-random seed 0",
-                       "batching": "whole-frame predict (the faster of the two); batch256_value = the reference's default "
-                                   "256-block evaluate_pipeline batches (008:192), one timed pass"},
+            "config": workload_config(args, world),
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "batch256_value": fps256,
-                             "sample": f"{n} 4K frame ({BPF} blocks) per step, whole-frame predict, torch fp32 CPU ops identical to the reference's"},
+                             "sample": f"bounded sample of the workload: {n} synthetic 4K frame ({BPF} blocks) per step (extraction + /1023 + "
+                                       "Stage1->Stage2->Stage3; the metric is per frame), whole-frame predict = the faster batching; "
+                                       "batch256_value = one pass in the reference's default 256-block evaluate_pipeline batches (008:192); "
+                                       "torch fp32 CPU ops identical to the reference's, all host threads"},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -191,10 +199,12 @@ def gpu_reference_leg(dev, log):
            "unit": "frames/s", "note": "PyTorch eager through the oracle port's functional modules (cuDNN/cuBLAS kernels)"}
     old_tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
     try:
-        for mode in ("eager_fp32_tf32off", "bf16_channels_last"):
-            if mode == "eager_fp32_tf32off":
+        for mode in ("eager_fp32_default", "eager_fp32_tf32off", "bf16_channels_last"):
+            if mode.startswith("eager_fp32"):
+                # "default" = what the reference gets on a GPU without touching any switch (008:206): PyTorch's defaults,
+                # i.e. cuDNN convolutions may use TF32, matmuls stay fp32; "tf32off" = strict fp32 everywhere
                 torch.backends.cuda.matmul.allow_tf32 = False
-                torch.backends.cudnn.allow_tf32 = False
+                torch.backends.cudnn.allow_tf32 = mode == "eager_fp32_default"
                 sds = {k: {n: t.to(dev) for n, t in sd.items()} for k, sd in sds_cpu.items()}
                 images = images_cpu.to(dev)
             else:
@@ -576,10 +586,8 @@ def main():
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling,
                 "vs_baseline": None, "dtype": "f16 operands (split hi/lo), f32 accumulate" if args.precision == "fp16x3" else "f16 operands, f32 accumulate",
                 "data": "synthetic", "blocks_per_sec": value * BPF,
-                "config": {"workload": "full cascade on a 4K 10-bit synthetic sequence (BASELINE configs[3]), block extraction included",
-                           "frames_per_gpu_per_step": F, "frames_per_step_whole_job": total_frames, "frames_per_launch": sub,
-                           "sharding": ("one sequence of %d frames, contiguous frame ranges per rank" % total_frames) if strong
-                                       else "every rank has its own %d-frame sequence" % F,
+                "config": workload_config(args, world),
+                "details": {"frames_per_gpu_per_step": F, "frames_per_launch": sub,
                            "chunk_schedule": "serial, one stream" if args.serial_chunks else f"chunks rotate over {args.streams} cascade plans, one stream each (host path: two)", "blocks_per_frame": BPF, "threshold": THRESHOLD,
                            "precision": args.precision, "weights": "calibrated-random seed 0", "routing_mix": mix,
                            "grid_sms": int(args.grid_sms) or "all",

@@ -10,7 +10,9 @@ from .flatten import (FlattenPipeline, evaluate_with_threshold, remap_flatten_to
 from .models import (AdapterModule, Stage2ModelWithAdapters, CosineClassifier, FGVCModel, ImprovedBackbone, SEBlock, SpatialAttention, Stage1BinaryHead,
                      Stage1Model, Stage2FlatModel, Stage2Model, Stage2ThreeWayHead, Stage3ABHead, Stage3ABModel,
                      Stage3RectHead, Stage3RectModel)
+from .metrics import compute_metrics
 from .pipeline import HierarchicalPipelineV6, evaluate_pipeline
+from .stage1_filter import filter_dataset_through_stage1
 
 __all__ = [
     "BlockRecord", "TorchBlockRecord", "calculate_yuv420_10bit_sizes", "extract_blocks_device",
@@ -20,5 +22,5 @@ __all__ = [
     "Stage2FlatModel", "FlattenPipeline", "run_pipeline_inference", "remap_flatten_to_original",
     "evaluate_with_threshold", "sweep_thresholds", "read_y_component_10bit_lossless", "read_frames_yuv420p10",
     "predict_yuv_file", "save_blocks_binary_10bit", "load_block_file", "ABEnsemble", "WeightedEnsemble", "AdapterModule", "extract_frames_device",
-    "Stage2ModelWithAdapters",
+    "Stage2ModelWithAdapters", "compute_metrics", "filter_dataset_through_stage1",
 ]

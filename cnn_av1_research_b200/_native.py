@@ -46,7 +46,6 @@ SIGNATURES = {
     "av1p_last_error": (C.c_char_p, []),
     "av1p_version": (C.c_int, []),
     "av1p_debug_watchdog": (C.c_int, []),
-    "av1p_input_range_flag": (C.c_int, []),
     "av1p_set_option": (C.c_int, [C.c_char_p, C.c_int32]),
     "av1p_get_option": (C.c_int, [C.c_char_p]),
     "av1p_model_create": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),

@@ -229,15 +229,6 @@ extern "C" int av1p_get_option(const char* name) {
 }
 
 extern "C" int av1p_debug_watchdog(void) { return g_ctx.watchdog_host ? *g_ctx.watchdog_host : 0; }
-// 1 if a frame-input cascade on the current device met a luma sample above 2048 since the last call (reads and clears; the
-// caller synchronises the stream first).  Such content is not 10-bit: the frame path rounds it, predict(images) does not.
-extern "C" int av1p_input_range_flag(void) {
-  DeviceCtx& c = cur_ctx();
-  if (!c.watchdog_host) return 0;
-  const int v = c.watchdog_host[1];
-  c.watchdog_host[1] = 0;
-  return v;
-}
 
 // One FC layer: `rows` is the host-side upper bound on block rows (sizes the grid).  CTA-pair variant: clusters of two
 // CTAs, each pair takes two M tiles of an item.
@@ -495,6 +486,8 @@ struct av1p_stage {
   float* row_scale = nullptr;
   float* sam_part = nullptr;
   float* own_logits = nullptr;   // unused by the cascade (it passes its own logits buffers)
+  int* range_flag = nullptr;     // frame input: word the stem sets when a sample above 2048 is met (cascade plans point it
+                                 // into their workspace, av1p_cascade_buffer(c, 8); standalone stages leave it null)
   float* features_out = nullptr; // FGVC models: optional fp32 [rows][512] L2-normalised features (av1p_stage_set_features_out)
 };
 
@@ -717,6 +710,7 @@ int run_stage(av1p_stage* s, const StemInput& si, const int32_t* idx, const int3
         sp.idx = idx;
         sp.n_dev = n_dev;
         sp.n = n;
+        sp.range_flag = s->range_flag;
         const int grid = std::min(ceil_div(n, ST_BLOCKS), g_ctx.grid_sms);
         ProfScope ps(PROF_STEM, st);
         if (si.kind == 0) {
@@ -1118,6 +1112,7 @@ extern "C" int av1p_cascade_create(const av1p_model* const models[4], int32_t ca
       return rc;
     }
     c->logits[i] = reinterpret_cast<float*>(base + C.logits_off[i]);
+    c->stage[i].range_flag = reinterpret_cast<int*>(base + C.counts_off) + 8;
   }
   if (c->overlap3) {
     if (cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking) != cudaSuccess ||
@@ -1157,6 +1152,7 @@ extern "C" const void* av1p_cascade_buffer(const av1p_cascade* c, int32_t which)
     case 5: return c->idx_rect;
     case 6: return c->idx_ab;
     case 7: return c->counts;
+    case 8: return c->counts + 8;      // int32: 1 once a frame sample above 2048 was met (the caller zeroes / reads it in stream order)
   }
   return nullptr;
 }
@@ -1264,6 +1260,7 @@ extern "C" int av1p_flat_cascade_create(const av1p_model* const models[2], int32
       return rc;
     }
     c->logits[i] = reinterpret_cast<float*>(base + C.logits_off[i]);
+    c->stage[i].range_flag = reinterpret_cast<int*>(base + C.counts_off) + 8;
   }
   c->idx2 = reinterpret_cast<int32_t*>(base + C.idx_off);
   c->counts = reinterpret_cast<int32_t*>(base + C.counts_off);
@@ -1284,6 +1281,7 @@ extern "C" const void* av1p_flat_cascade_buffer(const av1p_flat_cascade* c, int3
     case 0: case 1: return c->logits[which];
     case 2: return c->idx2;
     case 3: return c->counts;
+    case 4: return c->counts + 8;      // input-range flag, see av1p_cascade_buffer(c, 8)
   }
   return nullptr;
 }

@@ -19,8 +19,8 @@
 //               raw integers in ONE plane and the /1023 moves into a second weight set (w / 1023 folded in float64 by the
 //               packer, split hi/lo): two products W_hi.P + W_lo.P instead of three and half the im2col traffic.
 //               (Exact for samples <= 2048; a sample above that is rounded to fp16's 11 bits - such a value is outside
-//               the 10-bit format the reference's reader warns about, 005:198-204.  The kernel raises a sticky flag,
-//               av1p_input_range_flag(), and the Python frame entry points that synchronise turn it into an error.)
+//               the 10-bit format the reference's reader warns about, 005:198-204.  The kernel raises a flag in the
+//               plan's workspace and the Python frame entry points that synchronise turn it into an error.)
 // Because the channels are the accumulator rows (TMEM lanes), one epilogue thread owns a channel and sees all
 // 64 conv positions of a block in its columns: bias, ReLU and the 3x3/s2 max-pool run in registers, and a warp
 // stores 32 consecutive channels (64 contiguous bytes) per pooled position.
@@ -68,6 +68,7 @@ struct StemParams {
   __half* out;              // [rows][1024] in the tiled activation layout (act_off, 16 blocks per row)
   __half* out_lo;           // split precision: fp16(x - fp16(x)), nullptr otherwise
   int* err_flag;
+  int* range_flag;          // optional: set to 1 when a frame sample above 2048 is met (INT_PIX)
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int threads) {
@@ -184,11 +185,11 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_tc_kernel(const __grid_con
 #pragma unroll
         for (int j = 0; j < 4; ++j) x[j] = __uint_as_float(raw[j]);
       }
-      if (INT_PIX && fmaxf(fmaxf(x[0], x[1]), fmaxf(x[2], x[3])) > 2048.0f && p.err_flag) {
+      if (INT_PIX && fmaxf(fmaxf(x[0], x[1]), fmaxf(x[2], x[3])) > 2048.0f && p.range_flag) {
         // outside the 10-bit format (the reference's reader warns above 1023, 005:198-204, and passes the value on): the
-        // single integer plane is exact only up to 2048, so the caller is told (sticky flag next to the watchdog word,
-        // read by av1p_input_range_flag) instead of silently diverging from predict(images)
-        p.err_flag[1] = 1;
+        // single integer plane is exact only up to 2048, so the caller is told (a word in the plan's workspace, see
+        // av1p_cascade_buffer) instead of silently diverging from predict(images)
+        *p.range_flag = 1;
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {                   // o is odd: scalar fp16 stores

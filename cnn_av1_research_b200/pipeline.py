@@ -270,20 +270,29 @@ class HierarchicalPipelineV6:
                 main.wait_stream(st)
             out_host.copy_(labels, non_blocking=True)
         torch.cuda.current_stream(dev).synchronize()
-        self.check_input_range(synchronize=False)
+        self.check_input_range(synchronize=False)      # 4-byte reads after the sync; content above 2048 must not pass silently
         return out_host
 
+    def _plans(self):
+        return ([self._cascade] if self._cascade is not None else []) + [t for t, _ in self._twins.values()]
+
     def check_input_range(self, synchronize: bool = True) -> None:
-        """Raise if a frame-input call since the last check met a luma sample above 2048.  The reference never masks samples
-        (read_y_component only warns above 1023, 005:198-204; to_torch divides whatever uint16 it gets); the fused frame path
-        keeps a sample as one fp16 integer, exact up to 2048, so 12-bit or corrupt content must go through
-        predict(images) (float blocks, no such limit) instead of silently diverging."""
+        """Raise if a frame-input call on this pipeline since the last check met a luma sample above 2048.  The reference
+        never masks samples (read_y_component only warns above 1023, 005:198-204; to_torch divides whatever uint16 it gets);
+        the fused frame path keeps a sample as one fp16 integer, exact up to 2048, so 12-bit or corrupt content must go
+        through predict(images) (float blocks, no such limit) instead of silently diverging.  Reads - and clears - the flag
+        word of every cascade plan of this pipeline."""
         if synchronize:
             torch.cuda.synchronize(self.device)
-        with torch.cuda.device(self.device):
-            if N.lib().av1p_input_range_flag():
-                raise N.Av1pError("frame input holds luma samples above 2048 (not 10-bit content): the fused frame path is exact "
-                                  "for samples <= 2048 only - extract the blocks and call predict(images) for such data")
+        hit = False
+        for plan in self._plans():
+            flag = plan.range_flag
+            if int(flag.item()):
+                hit = True
+                flag.zero_()
+        if hit:
+            raise N.Av1pError("frame input holds luma samples above 2048 (not 10-bit content): the fused frame path is exact "
+                              "for samples <= 2048 only - extract the blocks and call predict(images) for such data")
 
 
 def evaluate_pipeline(pipeline, dataloader, class_names=None):

@@ -119,6 +119,12 @@ class NativeCascade:
             N.check(N.lib().av1p_cascade_predict(self.handle, C.byref(inp), n_blocks, float(threshold), N.ptr(labels_u8),
                                                  N.ptr(labels_i64), N.stream_handle(self.device)))
 
+    @property
+    def range_flag(self) -> torch.Tensor:
+        """int32[1] view into the workspace: set to 1 by a frame-input predict that met a luma sample above 2048."""
+        off = N.lib().av1p_cascade_buffer(self.handle, 8) - self.workspace.data_ptr()
+        return self.workspace[off:off + 4].view(torch.int32)
+
     def intermediates(self, n_blocks: int) -> Dict[str, torch.Tensor]:
         """Copies of the routing lists and per-stage logits of the last predict() (synchronises)."""
         torch.cuda.synchronize(self.device)

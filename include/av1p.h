@@ -48,11 +48,6 @@ const char* av1p_last_error(void);
 int av1p_version(void);
 /* Value written by a kernel watchdog (pipeline barrier that never completed), 0 if none. */
 int av1p_debug_watchdog(void);
-/* Frame input (kind 0) is 10-bit content (005:198-204 warns above 1023).  The fused extraction keeps a sample as one fp16
- * integer, exact up to 2048; larger values (12-bit / corrupt data) are rounded, where the reference would divide the exact
- * value.  Returns 1 - and clears the flag - if such a sample was met on the current device since the last call; synchronise
- * the stream first.  Callers with out-of-range content use the float-block entry (kind 1), which has no such limit. */
-int av1p_input_range_flag(void);
 /* Per-device runtime switches (the reference has no counterpart: scheduling knobs of this build).  Every device
  * ordinal has its own context, initialised on first use while that device is current (cudaSetDevice / torch.cuda.device).
  *   "grid_sms": SMs a persistent kernel's grid may occupy (even, 2 .. SM count; 0 restores the SM count);
@@ -99,7 +94,11 @@ int av1p_cascade_predict(av1p_cascade* c, const av1p_input* in, int32_t n_blocks
                          uint8_t* labels_u8_dev, int64_t* labels_i64_dev, void* stream);
 /* Introspection for the parity tests (device pointers into the workspace, valid after predict):
  * which: 0 stage-1 logits [n][1], 1 stage-2 logits [n2][3], 2 RECT logits [nR][2], 3 AB logits [nA][4],
- *        4 idx2 [n2], 5 idxR [nR], 6 idxA [nA], 7 counts int32[4] = {n2, unused, nR, nA}. */
+ *        4 idx2 [n2], 5 idxR [nR], 6 idxA [nA], 7 counts int32[4] = {n2, unused, nR, nA},
+ *        8 input-range flag int32[1]: frame input (kind 0) is 10-bit content (005:198-204 warns above 1023); the fused
+ *          extraction keeps a sample as one fp16 integer, exact up to 2048, and sets this word to 1 when it meets a larger
+ *          one (12-bit / corrupt data), where the reference would divide the exact value.  The caller zeroes and reads it
+ *          in stream order; such content belongs on the float-block entry (kind 1), which has no limit. */
 const void* av1p_cascade_buffer(const av1p_cascade* c, int32_t which);
 /* Number of kernels one predict() call enqueues (for launch accounting). */
 int av1p_cascade_launches_per_predict(const av1p_cascade* c);

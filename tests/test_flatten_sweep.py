@@ -121,6 +121,43 @@ def test_gpu_flatten_cascade_matches_reference(cuda_device, flat_fix):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("w,h", [(1920, 1080), (3840, 2160)])
+def test_gpu_flatten_cascade_full_size_frames(cuda_device, w, h):
+    """The flatten cascade (008b:177-229) at full size, extraction fused: a 1080p frame (68 x 120 blocks, the last grid row
+    half padding, 005:380-383) and a whole 4K frame (32,400 blocks) against the CPU oracle - >= 99.9 % labels, every miss
+    within 1e-2 of a tie in the reference's deciding logits, 7-way logits max-abs <= 5e-3 on the commonly routed blocks."""
+    from cnn_av1_research_b200.testing import frames_tensor
+    words = synth.synth_frames(1, w, h, seed=91)
+    images = O.frames_to_images(words, 1, w, h)
+    n = images.shape[0]
+    assert n == -(-h // 16) * -(-w // 16)
+    ref = O.flatten_predict(synth.calibrated_state_dict("stage1", 0), synth.calibrated_state_dict("flat7", 0), images, THR, chunk=8192)
+    pipe = _flat_pipe(cuda_device)
+    labels = pipe.predict_frames(frames_tensor(words, cuda_device), w, h, 1).cpu().numpy()
+    mid = {k: v.cpu().numpy() for k, v in pipe.cascade(n).intermediates(n).items()}
+    ref_labels = ref["labels"].numpy()
+    agree = float((labels == ref_labels).mean())
+    assert agree >= 0.999, agree
+    ref_idx2, ref_l1, ref_lf = ref["idx2"].numpy(), ref["logits1"].numpy().reshape(-1), ref["logits_flat"].numpy()
+    thr_logit = np.log(THR / (1 - THR))
+    for i in np.nonzero(labels != ref_labels)[0]:
+        m1 = abs(ref_l1[i] - thr_logit)
+        j = np.searchsorted(ref_idx2, i)
+        m2 = np.inf
+        if j < len(ref_idx2) and ref_idx2[j] == i:
+            top = np.sort(ref_lf[j])[-2:]
+            m2 = top[1] - top[0]
+        assert min(m1, m2) < 1e-2, (i, m1, m2)
+    assert np.abs(mid["logits1"].reshape(-1) - ref_l1).max() <= 5e-3
+    common, a, b = np.intersect1d(mid["idx2"], ref_idx2, return_indices=True)
+    assert common.size >= 0.99 * len(ref_idx2)
+    assert np.abs(mid["logits_flat"][a] - ref_lf[b]).max() <= 5e-3
+    if h % 16:        # padded last grid row (zeros below the frame edge): held to the same bar on its own
+        last = slice(n - (-(-w // 16)), n)
+        assert (labels[last] == ref_labels[last]).mean() >= 0.99
+
+
+@pytest.mark.gpu
 def test_gpu_flatten_run_pipeline_inference_api(cuda_device, flat_fix):
     """run_pipeline_inference(stage1, flat, dataloader, thr, device) -> (predictions, ground_truth) as in 008b:177-229."""
     import cnn_av1_research_b200 as P
