@@ -9,9 +9,9 @@ Scope.  The inference cascade is the product of this repository and runs on hand
 is NOT on that path.  This module exists so that the data-parallel configuration of the benchmark list can be run and
 measured: forward/backward are plain PyTorch ops (bf16 autocast on CUDA), written functionally over the SAME
 parameter tensors as the drop-in `Stage1Model` (identical state_dict keys, so a checkpoint trained here loads into
-the inference path and vice versa), and the only communication is ONE flat-bucket all-reduce of the 11,345,444
-gradients per step (NCCL over NVLink on GPUs, gloo in the CPU tests), followed by the identical AdamW update on every
-rank.  BatchNorm uses per-rank batch statistics (plain DDP semantics, as the single-GPU reference would with its own
+the inference path and vice versa), and the only communication is the all-reduce of the 11,345,444 gradients per step
+(NCCL over NVLink on GPUs, gloo in the CPU tests) - bucketed and overlapped with backward, see the trainer class -
+followed by the identical AdamW update on every rank.  BatchNorm uses per-rank batch statistics (plain DDP semantics, as the single-GPU reference would with its own
 batch).
 """
 from __future__ import annotations
@@ -69,10 +69,18 @@ def stage1_forward_torch(sd: Dict[str, torch.Tensor], x: torch.Tensor, training:
 
 class Stage1DataParallelTrainer:
     """One replica of the Stage-1 training step; all replicas stay bit-identical because they apply the same averaged
-    gradient with the same optimiser state."""
+    gradient with the same optimiser state.
+
+    Gradient exchange.  The 11,345,444 fp32 gradients live in ONE flat buffer; every parameter's `.grad` is a view into
+    it, so autograd accumulates straight into the communication buffer (no flatten / unflatten copies).  The buffer is cut
+    into buckets of ~`bucket_mb` MB in REVERSE parameter order - the order backward produces gradients - and a
+    post-accumulate hook launches an asynchronous all-reduce of a bucket as soon as its last gradient has arrived, so the
+    exchange of the head / layer4 gradients runs over NVLink while layer3 ... conv1 are still back-propagating; only the
+    last (smallest, earliest-layer) bucket is exposed.  `bucket_mb=0` restores the single flat all-reduce after backward
+    (the round-1 behaviour, kept for A/B)."""
 
     def __init__(self, model, device, lr: float = 1e-3, weight_decay: float = 1e-4, alpha: float = 0.25, gamma: float = 2.5,
-                 dropout_p: float = 0.3, autocast_bf16: Optional[bool] = None, group=None):
+                 dropout_p: float = 0.3, autocast_bf16: Optional[bool] = None, group=None, bucket_mb: float = 8.0):
         self.model = model.to(device)
         self.device = torch.device(device)
         self.group = group
@@ -85,8 +93,48 @@ class Stage1DataParallelTrainer:
         self.params = [v for _, v in self.named_params]
         self.optimizer = torch.optim.AdamW(self.params, lr=lr, weight_decay=weight_decay)
         n = sum(p.numel() for p in self.params)
-        self.flat_grad = torch.zeros(n, dtype=torch.float32, device=self.device)      # ONE bucket: 11,345,444 fp32 = 45.4 MB
+        self.flat_grad = torch.zeros(n, dtype=torch.float32, device=self.device)      # 11,345,444 fp32 = 45.4 MB
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        # gradient views + buckets.  Layout of the flat buffer = REVERSE parameter order, so that a bucket is a contiguous
+        # range filled front to back while backward walks the network from the head to conv1.
+        self.grad_views = {}
+        self.buckets = []                        # [start, end, n_params] per bucket
+        self._bucket_of = {}
+        cap = int(bucket_mb * (1 << 20) / 4) if bucket_mb and bucket_mb > 0 else n
+        off, start, count = 0, 0, 0
+        for p in reversed(self.params):
+            self.grad_views[p] = self.flat_grad[off:off + p.numel()].view_as(p)
+            self._bucket_of[p] = len(self.buckets)
+            off += p.numel()
+            count += 1
+            if off - start >= cap:
+                self.buckets.append([start, off, count])
+                start, count = off, 0
+        if count:
+            self.buckets.append([start, off, count])
+        self._pending = [0] * len(self.buckets)
+        self._launched = [False] * len(self.buckets)
+        self._works = []
+        self._touched = set()
+        for p in self.params:
+            p.register_post_accumulate_grad_hook(self._on_grad)
+
+    # ---- gradient exchange -------------------------------------------------------------------------------------------
+    def _launch_bucket(self, b: int) -> None:
+        self._launched[b] = True
+        if self.world > 1:
+            lo, hi, _ = self.buckets[b]
+            self._works.append(dist.all_reduce(self.flat_grad[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    def _on_grad(self, p: torch.Tensor) -> None:
+        self._touched.add(p)
+        b = self._bucket_of[p]
+        self._pending[b] -= 1
+        # buckets go out in index order on every rank (a collective sequence must be identical everywhere): bucket b is
+        # launched once it and every earlier bucket are complete
+        while b < len(self.buckets) and self._pending[b] == 0 and not self._launched[b] and all(self._launched[:b]):
+            self._launch_bucket(b)
+            b += 1
 
     def forward(self, images: torch.Tensor, training: bool = True) -> torch.Tensor:
         with torch.autocast(self.device.type, dtype=torch.bfloat16, enabled=self.autocast_bf16):
@@ -94,30 +142,33 @@ class Stage1DataParallelTrainer:
 
     def step(self, images: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
         """003:64-73 on this rank's batch, with the gradient averaged over the ranks.  Returns the local loss (detached)."""
-        self.optimizer.zero_grad(set_to_none=True)
+        self.flat_grad.zero_()                                 # optimizer.zero_grad() in one memset
+        for p in self.params:
+            p.grad = self.grad_views[p]
+        self._pending = [c for _, _, c in self.buckets]
+        self._launched = [False] * len(self.buckets)
+        self._works.clear()
+        self._touched.clear()
         logits = self.forward(images.to(self.device, non_blocking=True), training=True)
         loss = focal_loss_binary(logits, labels.to(self.device, non_blocking=True), self.alpha, self.gamma)
-        loss.backward()
-        # flatten -> one all-reduce -> unflatten (parameters without a gradient, e.g. the unused temperature, contribute zeros)
-        off = 0
-        for p in self.params:
-            n = p.numel()
-            if p.grad is None:
-                self.flat_grad[off:off + n].zero_()
-            else:
-                self.flat_grad[off:off + n].copy_(p.grad.reshape(-1))
-            off += n
+        loss.backward()                                        # hooks launch the bucket all-reduces as gradients arrive
+        for b in range(len(self.buckets)):                     # buckets holding a parameter that got no gradient (zeros)
+            if not self._launched[b]:
+                self._launch_bucket(b)
+        for w in self._works:
+            w.wait()
         if self.world > 1:
-            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.group)
             self.flat_grad.div_(self.world)
-        off = 0
-        for p in self.params:
-            n = p.numel()
-            if p.grad is not None:
-                p.grad.copy_(self.flat_grad[off:off + n].view_as(p.grad))
-            off += n
+        for p in self.params:                                  # a parameter outside the graph (the unused temperature) keeps
+            if p not in self._touched:                         # grad None, so AdamW skips it exactly as the reference's does
+                p.grad = None
         self.optimizer.step()
         return loss.detach()
+
+    def gradient_vector(self) -> torch.Tensor:
+        """The (averaged) gradients of the last step in PARAMETER order (the flat buffer itself is laid out in reverse
+        parameter order, the order backward fills it)."""
+        return torch.cat([self.grad_views[p].reshape(-1) for p in self.params])
 
     def allreduce_bytes(self) -> int:
         return self.flat_grad.numel() * self.flat_grad.element_size()

@@ -76,6 +76,29 @@ def test_focal_loss_formula():
     assert torch.allclose(focal_loss_binary(x, y), exp, atol=1e-7)
 
 
+def test_bucketed_exchange_equals_single_flat_allreduce():
+    """The bucketed, backward-overlapped gradient exchange is a re-ordering of the same work: same parameters after two
+    steps as the single flat all-reduce (bucket_mb = 0), the unused temperature keeps grad None (AdamW skips it, as the
+    reference's optimiser does), and the 45 MB of gradients really are cut into several buckets in backward order."""
+    x, y = synthetic_labelled_blocks(16, 5)
+    out = []
+    for mb in (0.0, 2.0):
+        torch.manual_seed(0)
+        tr = Stage1DataParallelTrainer(_model(), "cpu", dropout_p=0.0, autocast_bf16=False, bucket_mb=mb)
+        for _ in range(2):
+            tr.step(x, y)
+        out.append((torch.cat([p.detach().reshape(-1) for p in tr.params]), tr))
+    assert torch.equal(out[0][0], out[1][0])
+    one, many = out[0][1], out[1][1]
+    assert len(one.buckets) == 1 and len(many.buckets) >= 6
+    assert many.buckets[0][0] == 0 and many.buckets[-1][1] == many.flat_grad.numel()
+    assert all(a[1] == b[0] for a, b in zip(many.buckets, many.buckets[1:]))        # contiguous cover
+    # the first bucket holds the LAST parameters (head), i.e. what backward produces first
+    assert many._bucket_of[many.params[-1]] == 0 and many._bucket_of[many.params[0]] == len(many.buckets) - 1
+    assert dict(many.named_params)["head.temperature"].grad is None
+    assert float(dict(many.named_params)["head.temperature"]) == 1.5
+
+
 def _dp_worker(rank, world, port, q):
     import torch.distributed as dist
     torch.set_num_threads(2)
@@ -86,7 +109,7 @@ def _dp_worker(rank, world, port, q):
         x, y = synthetic_labelled_blocks(32, 100 + 10 * step + rank)        # every rank its own batch
         losses.append(float(tr.step(x, y)))
         if step == 0:
-            grad1 = tr.flat_grad[:1000].numpy().copy()
+            grad1 = tr.gradient_vector()[:1000].numpy().copy()
     flat = torch.cat([p.detach().reshape(-1) for p in tr.params])
     gathered = [torch.empty_like(flat) for _ in range(world)] if rank == 0 else None
     dist.gather(flat, gathered, dst=0)
@@ -110,7 +133,7 @@ def test_two_rank_step_keeps_replicas_identical_and_averages_gradients():
         p.join(timeout=120)
         assert p.exitcode == 0
     assert got["same"], "replicas diverged after the data-parallel steps"
-    assert got["bytes"] == 11_345_444 * 4                      # one flat fp32 bucket of every Stage-1 parameter
+    assert got["bytes"] == 11_345_444 * 4                      # every Stage-1 parameter's fp32 gradient, one flat buffer
     assert all(np.isfinite(got["losses"]))
     # single-process emulation of the two ranks: the gradient applied in step 1 is the mean of the per-rank gradients
     # (later steps are not comparable across thread counts: Adam's first update is lr * sign(g), so last-bit gradient

@@ -4,7 +4,8 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P tools/bench_train.py --gpus N
 
 One process per GPU, NCCL; per-GPU batch 128 (reference default, 003:139) of synthetic labelled blocks, bf16 autocast
-forward/backward in PyTorch, ONE flat all-reduce of the 11,345,444 fp32 gradients per step, AdamW.  Weak scaling;
+forward/backward in PyTorch, the 11,345,444 fp32 gradients all-reduced in ~8 MB buckets overlapped with backward
+(--bucket-mb 0: one flat all-reduce after backward), AdamW.  Weak scaling;
 CUDA-event time, max over ranks.  Prints one JSON line on rank 0.
 """
 import argparse
@@ -25,6 +26,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--batch", type=int, default=128)
+    ap.add_argument("--bucket-mb", type=float, default=8.0, help="gradient bucket size; 0 = one flat all-reduce after backward")
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
@@ -36,7 +38,7 @@ def main():
     from cnn_av1_research_b200.training import Stage1DataParallelTrainer, synthetic_labelled_blocks
     model = Stage1Model(pretrained=False)
     model.load_state_dict(synth.calibrated_state_dict("stage1", 0), strict=True)
-    tr = Stage1DataParallelTrainer(model, dev)
+    tr = Stage1DataParallelTrainer(model, dev, bucket_mb=args.bucket_mb)
     batches = [synthetic_labelled_blocks(args.batch, 1000 * rank + i, device=dev) for i in range(4)]
     for i in range(args.warmup):
         tr.step(*batches[i % 4])
@@ -66,7 +68,11 @@ def main():
                           "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms.item(), "scaling": "weak",
                           "dtype": "bf16 autocast (PyTorch fwd/bwd), fp32 gradient all-reduce", "data": "synthetic",
                           "config": {"workload": "Stage1 data-parallel training step (BASELINE configs[4])", "per_gpu_batch": args.batch,
-                                     "allreduce_bytes_per_step": tr.allreduce_bytes(), "optimizer": "AdamW lr 1e-3 wd 1e-4",
+                                     "allreduce_bytes_per_step": tr.allreduce_bytes(),
+                                     "gradient_exchange": (f"{len(tr.buckets)} buckets of ~{args.bucket_mb:g} MB in backward order, async all-reduce "
+                                                           "launched from post-accumulate hooks (overlaps backward)") if args.bucket_mb > 0
+                                                          else "one flat all-reduce after backward",
+                                     "optimizer": "AdamW lr 1e-3 wd 1e-4",
                                      "loss": "FocalLoss alpha 0.25 gamma 2.5"},
                           "replicas_identical": same, "final_loss": float(loss)}), flush=True)
     if world > 1:
