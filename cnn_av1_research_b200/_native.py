@@ -148,8 +148,18 @@ def frames_input(frames: torch.Tensor, width: int, height: int, n_frames: int, p
                  frames_dev=ptr(frames), images_dev=None)
 
 
-def images_input(images: torch.Tensor) -> Input:
-    """float32 blocks [n,1,16,16] (or [n,256]) on the device."""
-    if images.dtype != torch.float32 or images.numel() % 256:
-        raise Av1pError("images must be float32 with 256 samples per block")
-    return Input(kind=1, width=16, height=16, pitch=16, n_frames=0, frame_stride=0, frames_dev=None, images_dev=ptr(images))
+BLOCK_SIZES = (8, 16, 32, 64)          # 005:32; the v6 pipeline itself runs on 16
+
+
+def block_size_of(images: torch.Tensor) -> int:
+    """Block size b of a [B,1,b,b] tensor; raises for anything else."""
+    if images.dim() != 4 or images.shape[1] != 1 or images.shape[2] != images.shape[3] or images.shape[2] not in BLOCK_SIZES:
+        raise ValueError(f"expected blocks [B,1,b,b] with b in {BLOCK_SIZES}, got {tuple(images.shape)}")
+    return int(images.shape[2])
+
+
+def images_input(images: torch.Tensor, block: int = 16) -> Input:
+    """float32 blocks [n,1,b,b] (or [n,b*b]) on the device; b must be the block size the model was packed for."""
+    if images.dtype != torch.float32 or images.numel() % (block * block):
+        raise Av1pError(f"images must be float32 with {block * block} samples per block")
+    return Input(kind=1, width=block, height=block, pitch=block, n_frames=0, frame_stride=0, frames_dev=None, images_dev=ptr(images))

@@ -22,6 +22,7 @@
 #include "fc_tcgen05.cuh"
 #include "conv_res_tcgen05.cuh"
 #include "stem_tc.cuh"
+#include "gen_kernels.cuh"
 
 using namespace av1p;
 
@@ -168,7 +169,7 @@ int add_residual_entries(FcParams& f, bool has_lo) {
     // each; interleave them with the regular entries (after the first one, which initialises the accumulator).
     int next_res = 0;
     auto push_res = [&]() {
-      const uint16_t kb = uint16_t(t * per_tile + next_res++);
+      const uint16_t kb = uint16_t(f.out_col0 / FC_TILE_K + t * per_tile + next_res++);
       src.push_back(uint16_t((2u << 14) | kb));
       w.push_back(FC_W_IDENT);
       if (has_lo) {
@@ -362,6 +363,7 @@ struct av1p_model {
   std::vector<Av1pBlobOp> ops;
   std::vector<uint32_t> buf_cols;
   int device = 0;                   // ordinal of the device holding `dev`
+  int block = 16;                   // luma block size the program was packed for (8 / 16 / 32 / 64)
 };
 
 extern "C" int av1p_model_create(const void* blob, size_t bytes, av1p_model** out) {
@@ -379,6 +381,11 @@ extern "C" int av1p_model_create(const void* blob, size_t bytes, av1p_model** ou
   if (!m) return fail(AV1P_ENOMEM, "host allocation failed");
   m->hdr = h;
   m->device = current_device();
+  m->block = h.block_size ? int(h.block_size) : 16;
+  if (m->block != 8 && m->block != 16 && m->block != 32 && m->block != 64) {
+    delete m;
+    return fail(AV1P_EINVAL, "blob packed for block size %d (8 / 16 / 32 / 64 are supported)", int(h.block_size));
+  }
   m->ops.resize(h.n_ops);
   memcpy(m->ops.data(), static_cast<const uint8_t*>(blob) + h.ops_off, h.n_ops * sizeof(Av1pBlobOp));
   m->buf_cols.resize(h.n_bufs);
@@ -393,6 +400,7 @@ extern "C" int av1p_model_create(const void* blob, size_t bytes, av1p_model** ou
     if (op.type == AV1P_OP_FC) {
       if (op.n_tiles < 1 || op.n_tiles > FC_MAX_NT || op.block_n < 32 || op.block_n > FC_MAX_N || op.block_n % 32 ||
           op.n_kb_total < 1 || op.n_kb_total > AV1P_BLOB_MAX_KB || op.tail_n > FC_TAIL_MAX || op.n_w_chunks < 1 ||
+          op.out_col0 < 0 || op.out_col0 % FC_TILE_K ||
           op.w_off + uint64_t(op.n_w_chunks) * op.block_n * 128 > bytes) {
         delete m;
         return fail(AV1P_EINVAL, "malformed FC op");
@@ -445,6 +453,8 @@ struct PlannedOp {
   int ld = 0;
   float f0 = 0.f, f1 = 0.f;
   const float* w = nullptr;
+  StemGenParams sg;              // AV1P_OP_STEM_GEN
+  int gen_kb_in = 0, gen_kb_out = 0;   // AV1P_OP_SE_GEN / AV1P_OP_SAM_POOL: 64-column blocks per row of source / destination
 };
 
 // Activation region shared by every stage of a cascade: buffer i has max-over-models cols.
@@ -552,6 +562,7 @@ int plan_stage(const av1p_model* m, const ActLayout& L, uint8_t* act_base, av1p_
         f.out = buf(op.out);
         f.out_lo = buf(op.out_lo);
         f.out_kb = op.out >= 0 ? int(L.cols[op.out] / 64) : 0;
+        f.out_col0 = op.out_col0;
         if ((op.aux_lo >= 0 && L.cols[op.aux_lo] != L.cols[op.aux]) || (op.out_lo >= 0 && L.cols[op.out_lo] != L.cols[op.out]))
           return fail(AV1P_EINVAL, "hi/lo buffers differ in width");
         f.tail_w = reinterpret_cast<const float*>(at(op.tail_w_off));
@@ -561,7 +572,9 @@ int plan_stage(const av1p_model* m, const ActLayout& L, uint8_t* act_base, av1p_
         if ((op.epi == FC_EPI_ADD_RELU || op.epi == FC_EPI_GATE || op.epi == FC_EPI_ADD) && !f.aux) return fail(AV1P_EINVAL, "FC op needs aux");
         if (op.epi == FC_EPI_HEAD && (!f.tail_w || !f.tail_b || op.n_tiles != 1 || op.tail_n < 1))
           return fail(AV1P_EINVAL, "malformed head op");
-        if (op.epi != FC_EPI_HEAD && op.n_tiles * op.block_n > f.out_kb * 64) return fail(AV1P_EINVAL, "FC output wider than its buffer");
+        if (op.epi != FC_EPI_HEAD && op.out_col0 + op.n_tiles * op.block_n > f.out_kb * 64) return fail(AV1P_EINVAL, "FC output wider than its buffer");
+        if (op.out_col0 && (op.epi == FC_EPI_GATE || op.epi == FC_EPI_ADD || op.epi == FC_EPI_HEAD || (op.use_row_scale & 4)))
+          return fail(AV1P_EINVAL, "an FC op with a column offset cannot be a gate / adapter / head layer");
         for (int i = 0; i <= op.n_tiles; ++i) f.kb_begin[i] = op.kb_begin[i];
         if (f.kb_begin[0] != 0 || f.kb_begin[op.n_tiles] != op.n_kb_total) return fail(AV1P_EINVAL, "bad K-block schedule");
         for (int i = 0; i < op.n_kb_total; ++i) {
@@ -591,7 +604,7 @@ int plan_stage(const av1p_model* m, const ActLayout& L, uint8_t* act_base, av1p_
           if (op.aux_lo >= 0)
             if (int rc = make_act_map(&f.aux_map[1], buf(op.aux_lo), L.cols[op.aux_lo], L.cap, true)) return rc;
         } else if (op.epi == FC_EPI_ADD_RELU) {
-          if (op.n_tiles * op.block_n > int(L.cols[op.aux])) return fail(AV1P_EINVAL, "residual narrower than the FC output");
+          if (op.out_col0 + op.n_tiles * op.block_n > int(L.cols[op.aux])) return fail(AV1P_EINVAL, "residual narrower than the FC output");
           if (int rc = make_act_map(&f.a_map[2], buf(op.aux), L.cols[op.aux], L.cap, false)) return rc;
           f.src_kb[2] = f.src_kb[3] = int(L.cols[op.aux] / 64);
           if (op.aux_lo >= 0)
@@ -660,6 +673,48 @@ int plan_stage(const av1p_model* m, const ActLayout& L, uint8_t* act_base, av1p_
           return fail(AV1P_EINVAL, "malformed SE op");
         break;
       }
+      case AV1P_OP_STEM_GEN: {
+        memset(&P.sg, 0, sizeof P.sg);
+        const int g1 = op.n_tiles / 4;
+        P.sg.bs = op.n_tiles;
+        P.sg.w = reinterpret_cast<const float*>(at(op.w_off));
+        P.sg.b = reinterpret_cast<const float*>(at(op.bias_off));
+        P.sg.out = buf(op.out);
+        P.sg.out_lo = buf(op.out_lo);
+        P.sg.out_kb = op.out >= 0 ? int(L.cols[op.out] / 64) : 0;
+        if (op.n_tiles != m->block || !P.sg.w || !P.sg.b || !P.sg.out || P.sg.out_kb < g1 * g1)
+          return fail(AV1P_EINVAL, "malformed generic stem op");
+        break;
+      }
+      case AV1P_OP_SE_GEN: {
+        P.src = buf(op.src[0]);
+        P.src_lo = buf(op.src[1]);
+        P.dst = buf(op.out);
+        P.dst_lo = buf(op.out_lo);
+        P.se_c = op.block_n;
+        P.se_npos = op.n_tiles;
+        P.w = reinterpret_cast<const float*>(at(op.w_off));
+        const bool c_ok = P.se_c == 64 || P.se_c == 128 || P.se_c == 256 || P.se_c == 512;
+        if (!P.src || !P.dst || !P.w || !c_ok || P.se_npos < 1 || L.cols[op.src[0]] != L.cols[op.out] ||
+            int(L.cols[op.src[0]]) < P.se_c * P.se_npos || (op.src[1] >= 0) != (op.out_lo >= 0))
+          return fail(AV1P_EINVAL, "malformed generic SE op");
+        P.gen_kb_in = int(L.cols[op.src[0]] / 64);
+        break;
+      }
+      case AV1P_OP_SAM_POOL: {
+        P.src = buf(op.src[0]);
+        P.src_lo = buf(op.src[1]);
+        P.dst = buf(op.out);
+        P.dst_lo = buf(op.out_lo);
+        P.se_npos = op.n_tiles;            // map side g
+        P.w = reinterpret_cast<const float*>(at(op.w_off));
+        if (!P.src || !P.dst || !P.w || P.se_npos < 1 || P.se_npos > 2 || int(L.cols[op.src[0]]) < P.se_npos * P.se_npos * 512 ||
+            L.cols[op.out] < 512 || (op.src[1] >= 0) != (op.out_lo >= 0))
+          return fail(AV1P_EINVAL, "malformed attention / pooling op");
+        P.gen_kb_in = int(L.cols[op.src[0]] / 64);
+        P.gen_kb_out = int(L.cols[op.out] / 64);
+        break;
+      }
       default:
         return fail(AV1P_EINVAL, "unknown op type %d", op.type);
     }
@@ -668,7 +723,7 @@ int plan_stage(const av1p_model* m, const ActLayout& L, uint8_t* act_base, av1p_
   return AV1P_OK;
 }
 
-int convert_input(const av1p_input* in, StemInput* si) {
+int convert_input(const av1p_input* in, StemInput* si, int block = 16) {
   memset(si, 0, sizeof *si);
   if (!in) return fail(AV1P_EINVAL, "null input");
   si->kind = in->kind;
@@ -680,8 +735,8 @@ int convert_input(const av1p_input* in, StemInput* si) {
     si->width = in->width;
     si->height = in->height;
     si->pitch = in->pitch;
-    si->blocks_x = ceil_div(in->width, 16);
-    si->blocks_per_frame = si->blocks_x * ceil_div(in->height, 16);
+    si->blocks_x = ceil_div(in->width, block);
+    si->blocks_per_frame = si->blocks_x * ceil_div(in->height, block);
     si->inv_bx = ~0ULL / (unsigned long long)si->blocks_x + 1ULL;              // unused when the divisor is 1
     si->inv_bpf = ~0ULL / (unsigned long long)si->blocks_per_frame + 1ULL;
   } else if (in->kind == 1) {
@@ -762,6 +817,29 @@ int run_stage(av1p_stage* s, const StemInput& si, const int32_t* idx, const int3
           se_kernel<256, 1, 1><<<std::min(ceil_div(n, 8), g_ctx.sms * 8), 256, smem, st>>>(P.src, P.src_lo, P.dst, P.dst_lo, n_dev, n, P.w);
         break;
       }
+      case AV1P_OP_STEM_GEN: {
+        StemGenParams sp = P.sg;
+        sp.in = si;
+        sp.idx = idx;
+        sp.n_dev = n_dev;
+        sp.n = n;
+        const size_t smem = size_t(sp.bs + 6) * (sp.bs + 7) * sizeof(float);
+        ProfScope ps(PROF_STEM, st);
+        stem_generic_kernel<<<std::min(n, g_ctx.sms * 8), SG_THREADS, smem, st>>>(sp);
+        break;
+      }
+      case AV1P_OP_SE_GEN: {
+        ProfScope ps(PROF_SE, st);
+        se_generic_kernel<<<std::min(n, g_ctx.sms * 8), SEG_THREADS, 0, st>>>(P.src, P.src_lo, P.dst, P.dst_lo, n_dev, n, P.se_c, P.se_npos,
+                                                                             P.gen_kb_in, P.w);
+        break;
+      }
+      case AV1P_OP_SAM_POOL: {
+        ProfScope ps(PROF_SAM, st);
+        sam_pool_kernel<<<std::min(n, g_ctx.sms * 16), SP_THREADS, 0, st>>>(P.src, P.src_lo, P.dst, P.dst_lo, n_dev, n, P.se_npos, P.gen_kb_in,
+                                                                           P.gen_kb_out, P.w);
+        break;
+      }
       case AV1P_OP_FGVC_TAIL: {
         const int grid = std::min(ceil_div(n, 8), g_ctx.sms * 8);
         ProfScope ps(PROF_FGVC, st);
@@ -818,7 +896,7 @@ extern "C" int av1p_stage_forward(av1p_stage* s, const av1p_input* in, const int
                                   int32_t n, float* logits_dev, void* stream) {
   if (!s || !logits_dev) return fail(AV1P_EINVAL, "null argument");
   StemInput si;
-  if (int rc = convert_input(in, &si)) return rc;
+  if (int rc = convert_input(in, &si, s->model ? s->model->block : 16)) return rc;
   return run_stage(s, si, idx_dev, n_dev, n, logits_dev, static_cast<cudaStream_t>(stream));
 }
 
@@ -1095,6 +1173,8 @@ extern "C" int av1p_cascade_create(const av1p_model* const models[4], int32_t ca
     if (!models[i]) return fail(AV1P_EINVAL, "null model %d", i);
     if (int(models[i]->hdr.n_out) != outs[i])
       return fail(AV1P_EINVAL, "model %d has %u outputs, the cascade needs %d", i, models[i]->hdr.n_out, outs[i]);
+    if (models[i]->block != models[0]->block)
+      return fail(AV1P_EINVAL, "the models of a cascade must be packed for one block size (%d vs %d)", models[i]->block, models[0]->block);
   }
   if (int rc = ensure_ctx()) return rc;
   CascadeLayout C = make_cascade_layout(models, capacity);
@@ -1165,7 +1245,7 @@ extern "C" int av1p_cascade_predict(av1p_cascade* c, const av1p_input* in, int32
   if (n_blocks < 0 || n_blocks > c->cap) return fail(AV1P_EINVAL, "n_blocks=%d outside [0, %d]", n_blocks, c->cap);
   if (n_blocks == 0) return AV1P_OK;
   StemInput si;
-  if (int rc = convert_input(in, &si)) return rc;
+  if (int rc = convert_input(in, &si, c->stage[0].model->block)) return rc;
   if (in->kind == 0 && (long long)si.blocks_per_frame * in->n_frames < n_blocks)
     return fail(AV1P_EINVAL, "n_blocks exceeds the blocks in the given frames");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -1246,6 +1326,7 @@ extern "C" int av1p_flat_cascade_create(const av1p_model* const models[2], int32
   if (!models || !models[0] || !models[1] || !ws || !out || capacity <= 0) return fail(AV1P_EINVAL, "bad argument");
   if (models[0]->hdr.n_out != 1 || models[1]->hdr.n_out != 7)
     return fail(AV1P_EINVAL, "the flatten cascade needs a 1-output stage-1 model and a 7-output flat model");
+  if (models[0]->block != models[1]->block) return fail(AV1P_EINVAL, "the models of a cascade must be packed for one block size");
   if (int rc = ensure_ctx()) return rc;
   FlatLayout C = make_flat_layout(models, capacity);
   uint8_t* base = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<uintptr_t>(ws), 1024));
@@ -1292,7 +1373,7 @@ extern "C" int av1p_flat_cascade_predict(av1p_flat_cascade* c, const av1p_input*
   if (n_blocks < 0 || n_blocks > c->cap) return fail(AV1P_EINVAL, "n_blocks=%d outside [0, %d]", n_blocks, c->cap);
   if (n_blocks == 0) return AV1P_OK;
   StemInput si;
-  if (int rc = convert_input(in, &si)) return rc;
+  if (int rc = convert_input(in, &si, c->stage[0].model->block)) return rc;
   if (in->kind == 0 && (long long)si.blocks_per_frame * in->n_frames < n_blocks)
     return fail(AV1P_EINVAL, "n_blocks exceeds the blocks in the given frames");
   cudaStream_t st = static_cast<cudaStream_t>(stream);

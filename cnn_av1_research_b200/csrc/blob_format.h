@@ -8,7 +8,7 @@
 #include <stdint.h>
 
 #define AV1P_BLOB_MAGIC 0x50315641u   /* "AV1P" */
-#define AV1P_BLOB_VERSION 10u
+#define AV1P_BLOB_VERSION 11u
 #define AV1P_BLOB_MAX_NT 8
 #define AV1P_BLOB_MAX_KB 128
 
@@ -24,6 +24,11 @@ enum Av1pOpType : int32_t {
   AV1P_OP_CONV_RES = 5,   // 3x3 s1 conv 64->64 on the 4x4 map with SMEM-resident weights (csrc/conv_res_tcgen05.cuh):
                           // src = {x_hi, x_lo}, w = fp16 [planes][ky][kx = 2,1,0][64 co][64 ci], bias[1024], f0 = acc_scale,
                           // pair_mode = 1 for hi/lo planes (three products)
+  // generic block sizes (8 / 32 / 64; csrc/gen_kernels.cuh) - every conv / linear layer stays an AV1P_OP_FC
+  AV1P_OP_STEM_GEN = 6,   // gather + /1023 + conv1/bn/relu/maxpool in fp32: n_tiles = block size, w = fp32 [64][49], bias[64]
+  AV1P_OP_SE_GEN = 7,     // squeeze-excite, any shape: block_n = channels, n_tiles = positions, w as AV1P_OP_SE
+  AV1P_OP_SAM_POOL = 8,   // spatial attention (7x7 conv over [mean_c, max_c]) + global average pool: src0 = [g*g][512],
+                          // n_tiles = g, w = fp32 [2][49] -> out (512 cols)
 };
 
 #pragma pack(push, 1)
@@ -31,7 +36,8 @@ struct Av1pBlobHeader {
   uint32_t magic, version;
   uint32_t stage_kind;    // informational (0 stage1, 1 stage2, 2 rect, 3 ab-fgvc, 4 ab-plain, 5 flat7)
   uint32_t n_ops, n_bufs, n_out;
-  uint32_t reserved[2];
+  uint32_t precision;     // 0 fp16x3, 1 fp16 (informational)
+  uint32_t block_size;    // luma block size the program was packed for: 8 / 16 / 32 / 64 (0 reads as 16)
   uint64_t ops_off, bufs_off, total_bytes;
   uint64_t reserved2;
 };  // 64 bytes
@@ -51,5 +57,7 @@ struct Av1pBlobOp {
   int32_t kb_begin[AV1P_BLOB_MAX_NT + 1];
   uint16_t kb_src[AV1P_BLOB_MAX_KB];   // bits 14..15: index into src[], bits 0..13: K offset / 64
   uint16_t kb_w[AV1P_BLOB_MAX_KB];     // weight chunk index
-};  // 17*4 + 2*4 + 4*8 + 9*4 + 2*128*2 = 656 bytes
+  int32_t out_col0;                    // FC: first output column of this op (a wide layer is cut into several ops)
+  int32_t reserved;
+};  // 17*4 + 2*4 + 4*8 + 9*4 + 2*128*2 + 2*4 = 664 bytes
 #pragma pack(pop)

@@ -118,6 +118,7 @@ struct FcParams {
   __half* out;
   __half* out_lo;              // split mode: low part of the output (nullptr otherwise)
   int out_kb;                  // 64-column blocks per row of the output buffer
+  int out_col0;                // first output column of this op (multiple of 64; bias / schedule are op-local, buffers are not)
   const float* tail_w;         // [tail_n][block_n]
   const float* tail_b;         // [tail_n]
   float* logits;               // [rows][tail_n]
@@ -304,8 +305,10 @@ __device__ __forceinline__ void epi_tile_store(const P& p, const EpiStage& es, u
       const int col = col0 + c * EPI_CHUNK + sub * 16 + h * 8;
       float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
       if (p.bias) {
-        b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-        b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col) + 1);
+        int bcol = col;                                       // the bias vector is local to the op
+        if constexpr (requires { p.out_col0; }) bcol -= p.out_col0;
+        b0 = __ldg(reinterpret_cast<const float4*>(p.bias + bcol));
+        b1 = __ldg(reinterpret_cast<const float4*>(p.bias + bcol) + 1);
       }
       tmem_ld_wait();
       float f[8];
@@ -391,7 +394,7 @@ __device__ __forceinline__ void epi_tile_store(const P& p, const EpiStage& es, u
     if (p.sam_part && row_ok && c_first < n_chunks) {
       // slot (N tile, group, sub): every (row, slot) is written by exactly one thread
       const int slots = p.n_tiles * 4;
-      float* d = p.sam_part + (size_t(row) * slots + size_t((col0 / block_n) * 4 + int(grp) * 2 + sub)) * 2;
+      float* d = p.sam_part + (size_t(row) * slots + size_t((col0 / block_n) * 4 + int(grp) * 2 + sub)) * 2;   // out_col0 = 0 here
       d[0] = ssum;
       d[1] = smax;
     }
@@ -598,7 +601,7 @@ __global__ void __launch_bounds__(FC_THREADS, 1) fc_tcgen05_kernel(const __grid_
           const uint32_t set = ga % GATE_AUX_SETS;
           mbar_wait(&aux_empty[set], ((ga / GATE_AUX_SETS) & 1u) ^ 1u, p.err_flag, 150 + int(set));
           if (elect_one_sync()) {
-            const int col = nt * p.block_n + c * EPI_CHUNK;
+            const int col = p.out_col0 + nt * p.block_n + c * EPI_CHUNK;
             const int trow = (mt * p.aux_kb + (col >> 6)) * FC_TILE_M;
             uint8_t* dst = smem + FC_OFF_GATE_AUX + set * GATE_AUX_SET_BYTES;
             mbar_arrive_expect_tx(&aux_full[set], p.aux_lo ? 2u * EPI_UNIT_BYTES : uint32_t(EPI_UNIT_BYTES));
@@ -648,7 +651,7 @@ __global__ void __launch_bounds__(FC_THREADS, 1) fc_tcgen05_kernel(const __grid_
             if (ident) {
               // residual K block: acc[:, c0 .. c0+63] += A . (S I), 16 columns per instruction.  These entries
               // close a tile's schedule, so the accumulator already holds data.
-              const uint32_t c0 = (uint32_t(p.kb_src[kb]) & 0x3FFFu) * FC_TILE_K - uint32_t(nt * p.block_n);
+              const uint32_t c0 = (uint32_t(p.kb_src[kb]) & 0x3FFFu) * FC_TILE_K - uint32_t(p.out_col0 + nt * p.block_n);
 #pragma unroll
               for (int j = 0; j < FC_TILE_K / 16; ++j) {
                 const uint64_t a_desc = (uint64_t(0x40004040u) << 32) | uint64_t(a_lo + 2 * j);
@@ -713,8 +716,8 @@ __global__ void __launch_bounds__(FC_THREADS, 1) fc_tcgen05_kernel(const __grid_
       if (p.epi == FC_EPI_HEAD)
         epi_tile_head(p, n_rows, mt, p.block_n, t_col, &acc_full[acc], acc_phase, &acc_empty[acc], tail_w_s, warp, lane, 400 + acc, rem);
       else
-        epi_tile_store(p, es, g, n_rows, mt, nt * p.block_n, p.block_n, t_col, &acc_full[acc], acc_phase, &acc_empty[acc], warp,
-                       lane, 400 + acc, rem, gate ? &gx : nullptr);
+        epi_tile_store(p, es, g, n_rows, mt, p.out_col0 + nt * p.block_n, p.block_n, t_col, &acc_full[acc], acc_phase, &acc_empty[acc],
+                       warp, lane, 400 + acc, rem, gate ? &gx : nullptr);
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1u;
@@ -728,7 +731,7 @@ __global__ void __launch_bounds__(FC_THREADS, 1) fc_tcgen05_kernel(const __grid_
         const int mt = item_mt(item);
         const int nt = item % p.n_tiles;
         if ((mt + 1) * FC_TILE_M > n_rows) continue;      // partial tile: the epilogue stores it directly
-        epi_store_chunks(es, g, &p.out_map[0], &p.out_map[1], p.out_lo != nullptr, nt * p.block_n, p.block_n / EPI_CHUNK,
+        epi_store_chunks(es, g, &p.out_map[0], &p.out_map[1], p.out_lo != nullptr, p.out_col0 + nt * p.block_n, p.block_n / EPI_CHUNK,
                          mt, p.out_kb, p.err_flag, uint32_t(warp - FC_STORE_WARP));
       }
       epi_store_drain();

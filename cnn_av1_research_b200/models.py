@@ -170,39 +170,40 @@ class _NativeStageModule(nn.Module):
 
     def __init__(self):
         super().__init__()
-        self._native_model: Optional[NativeModel] = None
-        self._native_stage: Optional[NativeStage] = None
-        self._native_key = None
+        # packed program + stage plan per block size (16 for the v6 pipeline; 8 / 32 / 64: the other sizes the reference's
+        # dataset tools cut, 005:32 - its networks take any of them thanks to the adaptive pooling, models.py:100-124)
+        self._natives: dict = {}      # block -> [NativeModel, key, Optional[NativeStage]]
 
     def _param_key(self, device):
         return (str(device),) + tuple((t.data_ptr(), t._version) for t in self.state_dict(keep_vars=True).values())
 
-    def native_model(self, device) -> NativeModel:
+    def native_model(self, device, block: int = 16) -> NativeModel:
         key = (self.precision,) + self._param_key(device)
-        if self._native_model is None or self._native_key != key:
+        entry = self._natives.get(block)
+        if entry is None or entry[1] != key:
             sd = {k: v.detach().to("cpu", torch.float32) if v.is_floating_point() else v.detach().cpu()
                   for k, v in self.state_dict().items()}
-            self._native_model = NativeModel(self._kind, sd, device, self.precision)
-            self._native_stage = None
-            self._native_key = key
-        return self._native_model
+            entry = [NativeModel(self._kind, sd, device, self.precision, block=block), key, None]
+            self._natives[block] = entry
+        return entry[0]
 
     def _native_forward(self, x: torch.Tensor, want_features: bool = False):
         if self.training:
             raise RuntimeError(f"{type(self).__name__}: only eval-mode inference is implemented on the B200 path; call .eval()")
         if not x.is_cuda:
             raise RuntimeError(f"{type(self).__name__}.forward needs a CUDA tensor: this package has no CPU path")
-        if x.dim() != 4 or tuple(x.shape[1:]) != (1, 16, 16):
-            raise ValueError(f"expected input [B,1,16,16], got {tuple(x.shape)}")
+        block = N.block_size_of(x)
         x = x.contiguous().float()
         n = x.shape[0]
-        model = self.native_model(x.device)
-        if self._native_stage is None or self._native_stage.capacity < n:
-            self._native_stage = NativeStage(model, max(n, 256))
+        model = self.native_model(x.device, block)
+        entry = self._natives[block]
+        if entry[2] is None or entry[2].capacity < n:
+            entry[2] = NativeStage(model, max(n, 256))
+        stage = entry[2]
         if not want_features:
-            return self._native_stage.forward(N.images_input(x), n)
+            return stage.forward(N.images_input(x, block), n)
         features = torch.empty((n, 512), dtype=torch.float32, device=x.device)
-        logits = self._native_stage.forward(N.images_input(x), n, features=features)
+        logits = stage.forward(N.images_input(x, block), n, features=features)
         return logits, features
 
 

@@ -27,12 +27,13 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import numpy as np
 
 BLOB_MAGIC = 0x50315641
-BLOB_VERSION = 10
+BLOB_VERSION = 11
 MAX_NT = 8
 MAX_KB = 128
+MAX_KB_PLANNED = 192      # FC_MAX_KB of the kernel: blob entries + the residual entries av1p.cu adds at plan time
 TILE_K = 64
 
-OP_STEM, OP_FC, OP_SAM, OP_FGVC_TAIL, OP_SE, OP_CONV_RES = 0, 1, 2, 3, 4, 5
+OP_STEM, OP_FC, OP_SAM, OP_FGVC_TAIL, OP_SE, OP_CONV_RES, OP_STEM_GEN, OP_SE_GEN, OP_SAM_POOL = 0, 1, 2, 3, 4, 5, 6, 7, 8
 EPI_LINEAR, EPI_RELU, EPI_ADD_RELU, EPI_GATE, EPI_HEAD, EPI_ADD = 0, 1, 2, 3, 4, 5
 
 STAGE_KINDS = {"stage1": 0, "stage2": 1, "rect": 2, "ab_fgvc": 3, "ab": 4, "flat7": 5, "stage2_adapters": 6}
@@ -43,9 +44,43 @@ SAM_FUSED = os.environ.get("AV1P_SAM_FUSED", "1") != "0"     # A/B knob: 0 = sep
 
 # activation buffers (fp16 columns per block row).  In split precision every buffer X has a twin X_lo
 # holding fp16(x - fp16(x)); the twins get ids len(BUF_COLS) + id(X).
-BUF_COLS = {"B0": 1024, "B1": 1024, "B2": 1024, "C0": 512, "C1": 512, "C2": 512, "D0": 256, "D1": 256, "D2": 256, "H": 64}
+BUF_COLS_16 = {"B0": 1024, "B1": 1024, "B2": 1024, "C0": 512, "C1": 512, "C2": 512, "D0": 256, "D1": 256, "D2": 256, "H": 64}
+BUF_COLS = dict(BUF_COLS_16)        # the plan of the program being packed (pack_stage installs the plan of its block size)
 BUF_IDS = {name: i for i, name in enumerate(BUF_COLS)}
 PRECISIONS = ("fp16x3", "fp16")
+BLOCK_SIZES = (8, 16, 32, 64)       # 005:32, 001_prepare_v6_dataset.py:198
+
+
+def layer_grids(block: int) -> Tuple[int, int, int, int]:
+    """Side of the layer1..layer4 feature maps for a block x block input: conv1 (s2) and max-pool (s2) leave block / 4,
+    every later layer's first 3x3 / stride-2 / pad-1 conv maps g to (g - 1) // 2 + 1 (models.py:104-121)."""
+    g1 = block // 4
+    g2 = (g1 - 1) // 2 + 1
+    g3 = (g2 - 1) // 2 + 1
+    g4 = (g3 - 1) // 2 + 1
+    return g1, g2, g3, g4
+
+
+def buffer_plan(block: int, generic: bool = False) -> Dict[str, int]:
+    """Activation buffers (fp16 columns per block row) of the program for `block`.  16: the specialised plan above.  Other
+    sizes (and the generic program for 16): three rotating buffers per layer width, the pooled 512 features + head scratch,
+    the 64-wide SE / adapter scratch."""
+    if block == 16 and not generic:
+        return dict(BUF_COLS_16)
+    g = layer_grids(block)
+    cols = {}
+    for tag, width in zip("BCDE", (g[0] * g[0] * 64, g[1] * g[1] * 128, g[2] * g[2] * 256, g[3] * g[3] * 512)):
+        for i in range(3):
+            cols[f"{tag}{i}"] = max(width, 64)
+    cols.update({"P0": 512, "P1": 512, "P2": 512, "Q0": 256, "H": 64})
+    return cols
+
+
+def _install_plan(block: int, generic: bool = False) -> None:
+    BUF_COLS.clear()
+    BUF_COLS.update(buffer_plan(block, generic))
+    BUF_IDS.clear()
+    BUF_IDS.update({name: i for i, name in enumerate(BUF_COLS)})
 
 
 def _hi(name: Optional[str]) -> int:
@@ -118,6 +153,7 @@ class _Op:
     tail_w: Optional[np.ndarray] = None   # float32 [tail_n, block_n]
     tail_b: Optional[np.ndarray] = None   # float32 [tail_n]
     name: str = ""
+    out_col0: int = 0                     # FC: first output column of this op (a wide layer is cut into several ops)
 
 
 def _make_fc_op_n(name: str, dense: Sequence[np.ndarray], srcs: Sequence[str], out: Optional[str], bias: Optional[np.ndarray],
@@ -234,6 +270,126 @@ def make_conv_res_op(name: str, wf: np.ndarray, bf: np.ndarray, src: str, out: s
     return _Op(OP_CONV_RES, src=[_hi(src), _lo(src, precision), -1, -1], aux=_hi(aux), aux_lo=_lo(aux, precision),
                out=_hi(out), out_lo=_lo(out, precision), n_tiles=16, block_n=64, epi=epi, pair_mode=int(split), f0=1.0 / scale,
                w=w.reshape(-1, 64), bias=np.tile(bf, 16).astype(np.float32), name=name)
+
+
+# ------------------------------------------------------------------------------------------------
+# Generic block sizes (8 / 32 / 64): a conv layer on a g x g map is the same block-Toeplitz GEMM, but its matrix no longer
+# fits one op (layer1 of a 64x64 block is 16384 x 16384), so it is generated tile by tile straight from the taps - never
+# as a dense matrix -, identical weight tiles are stored once per layer (translation invariance: all interior tiles of a
+# layer share their tap arrangement) and the N tiles are grouped into as many ops as the schedule limits require
+# (out_col0 = first output column of an op).
+def _conv_tile_entries(convs, grid_out: int, c_out: int, block_n: int, t: int):
+    """Non-zero [block_n x 64] weight tiles of N tile `t`: {(source, kb): float64 tile}.  convs = [(wf, grid_in, stride, pad)];
+    output columns are (position row-major, channel); K blocks of a source are (input position, 64-channel block)."""
+    r0 = t * block_n
+    n_total = grid_out * grid_out * c_out
+    r1 = min(r0 + block_n, n_total)
+    out: Dict[Tuple[int, int], np.ndarray] = {}
+    r = r0
+    while r < r1:
+        pos, co0 = divmod(r, c_out)
+        co1 = min(c_out, co0 + (r1 - r))
+        oy, ox = divmod(pos, grid_out)
+        for s, (wf, grid_in, stride, pad) in enumerate(convs):
+            c_in, kh, kw = wf.shape[1], wf.shape[2], wf.shape[3]
+            assert c_in % TILE_K == 0
+            for ky in range(kh):
+                iy = oy * stride - pad + ky
+                if not 0 <= iy < grid_in:
+                    continue
+                for kx in range(kw):
+                    ix = ox * stride - pad + kx
+                    if not 0 <= ix < grid_in:
+                        continue
+                    ip = iy * grid_in + ix
+                    for cb in range(c_in // TILE_K):
+                        blk = wf[co0:co1, cb * TILE_K:(cb + 1) * TILE_K, ky, kx]
+                        if not np.any(blk != 0.0):
+                            continue
+                        key = (s, ip * (c_in // TILE_K) + cb)
+                        tile = out.get(key)
+                        if tile is None:
+                            tile = out[key] = np.zeros((block_n, TILE_K), dtype=np.float64)
+                        tile[r - r0:r - r0 + (co1 - co0)] = blk
+        r += co1 - co0
+    return out
+
+
+def make_conv_layer_ops(name: str, convs, srcs: Sequence[str], grid_out: int, c_out: int, out: str, bias_c: np.ndarray, epi: int,
+                        precision: str, aux: Optional[str] = None) -> List[_Op]:
+    """One conv layer (optionally K-concatenated with a second conv: the downsample branch) on a grid_out x grid_out map as a
+    list of FC ops.  bias_c: per output channel (tiled over the positions)."""
+    n = grid_out * grid_out * c_out
+    block_n = _block_n(n)
+    n_tiles_total = -(-n // block_n)
+    split = precision == "fp16x3"
+    wmax = max(float(np.abs(c[0]).max()) for c in convs)
+    scale = 2.0 ** int(np.clip(np.floor(np.log2(8192.0 / wmax)), 0, 15)) if wmax > 0 else 1.0
+    for s, nm in enumerate(srcs):
+        wf, grid_in = convs[s][0], convs[s][1]
+        assert grid_in * grid_in * wf.shape[1] <= BUF_COLS[nm], (name, nm)
+    chunks: List[np.ndarray] = []
+    index: Dict[bytes, int] = {}
+    tiles = []                                        # per N tile: [(source, kb, chunk index)]
+    for t in range(n_tiles_total):
+        ent = []
+        for (s, kb), tile in sorted(_conv_tile_entries(convs, grid_out, c_out, block_n, t).items()):
+            tile = tile * scale
+            key = tile.tobytes()
+            ci = index.get(key)
+            if ci is None:
+                ci = index[key] = len(chunks)
+                chunks.append(tile)
+            ent.append((s, kb, ci))
+        if not ent:                                   # an all-zero tile still needs one K block so that the accumulator is defined
+            z = np.zeros((block_n, TILE_K))
+            ci = index.setdefault(z.tobytes(), len(chunks))
+            if ci == len(chunks):
+                chunks.append(z)
+            ent.append((0, 0, ci))
+        tiles.append(ent)
+    w64 = np.concatenate(chunks, axis=0)
+    if np.abs(w64).max() >= 65504.0:
+        raise ValueError(f"{name}: folded weight {np.abs(w64).max():.3e} does not fit fp16")
+    w_hi = w64.astype(np.float16)
+    w = np.concatenate([w_hi, (w64 - w_hi.astype(np.float64)).astype(np.float16)], axis=0) if split else w_hi
+    n_chunks = len(chunks)
+    assert (2 if split else 1) * n_chunks < 0xFFFF, name
+    bias_full = np.zeros(n_tiles_total * block_n, dtype=np.float32)
+    bias_full[:n] = np.tile(bias_c, grid_out * grid_out).astype(np.float32)
+    src = [-1, -1, -1, -1]
+    for i, nm in enumerate(srcs):
+        src[2 * i], src[2 * i + 1] = _hi(nm), _lo(nm, precision)
+    per_entry = 2 if split else 1
+    resid_per_tile = (block_n // TILE_K) * per_entry if epi == EPI_ADD_RELU else 0
+    ops: List[_Op] = []
+    t = 0
+    while t < n_tiles_total:
+        t_end, entries = t, 0
+        while t_end < n_tiles_total and t_end - t < MAX_NT:
+            e = len(tiles[t_end]) * per_entry
+            if t_end > t and (entries + e > MAX_KB or entries + e + (t_end + 1 - t) * resid_per_tile > MAX_KB_PLANNED):
+                break
+            entries += e
+            t_end += 1
+        assert entries <= MAX_KB and entries + (t_end - t) * resid_per_tile <= MAX_KB_PLANNED, f"{name}: one N tile needs {entries} entries"
+        kb_begin, kb_src, kb_w = [0], [], []
+        for tt in range(t, t_end):
+            for s, kb, ci in tiles[tt]:
+                assert kb < (1 << 14)
+                kb_src.append(((2 * s) << 14) | kb)
+                kb_w.append(ci)
+                if split:
+                    kb_src.append(((2 * s + 1) << 14) | kb)
+                    kb_w.append(n_chunks + ci)
+            kb_begin.append(len(kb_src))
+        ops.append(_Op(OP_FC, src=list(src), aux=_hi(aux), aux_lo=_lo(aux, precision), out=_hi(out), out_lo=_lo(out, precision),
+                       n_tiles=t_end - t, block_n=block_n, epi=epi, n_w_chunks=w.shape[0] // block_n, pair_mode=int(split),
+                       f0=1.0 / scale, kb_begin=kb_begin, kb_src=kb_src, kb_w=kb_w, w=w, bias=bias_full[t * block_n:t_end * block_n].copy(),
+                       name=name if n_tiles_total <= MAX_NT and t == 0 and t_end == n_tiles_total else f"{name}[{t}:{t_end}]",
+                       out_col0=t * block_n))
+        t = t_end
+    return ops
 
 
 def _block_n(n: int) -> int:
@@ -372,35 +528,86 @@ def backbone_ops(sd, precision: str = "fp16x3", prefix: str = "backbone.", layer
     return ops
 
 
-def head_ops(kind: str, sd, precision: str = "fp16x3") -> List[_Op]:
-    """Stage heads (models.py:129-203) and the FGVC tail (006:261-293); input x4' in C1 (+ row_scale)."""
+def backbone_ops_generic(sd, block: int, precision: str = "fp16x3", prefix: str = "backbone.") -> List[_Op]:
+    """Op program of ImprovedBackbone.forward (models.py:104-124) for a block x block input, block in {8, 32, 64} (16 has the
+    specialised program above; this one also packs 16 for cross-checks).  Result: the 512 pooled features in P0."""
+    p = prefix
+    g1, g2, g3, g4 = layer_grids(block)
+    ops: List[_Op] = []
+    w, b = fold_bn(_np64(sd[p + "conv1.weight"]), None, sd, p + "bn1")
+    ops.append(_Op(OP_STEM_GEN, out=_hi("B0"), out_lo=_lo("B0", precision), n_tiles=block, block_n=64,
+                   w=w.reshape(64, 49).astype(np.float32), bias=b.astype(np.float32), name="stem"))
+
+    def folded(unit: str, conv: str, bn: str):
+        return fold_bn(_np64(sd[f"{unit}.{conv}.weight"]), None, sd, f"{unit}.{bn}")
+
+    def se(layer: int, grid: int, src: str, dst: str):
+        w1 = _np64(sd[f"{p}se{layer}.excitation.0.weight"])     # [C/16, C]
+        w2 = _np64(sd[f"{p}se{layer}.excitation.2.weight"])     # [C, C/16]
+        ops.append(_Op(OP_SE_GEN, src=[_hi(src), _lo(src, precision), -1, -1], out=_hi(dst), out_lo=_lo(dst, precision),
+                       n_tiles=grid * grid, block_n=w1.shape[1], w=np.concatenate([w1, w2.T], axis=0).astype(np.float32),
+                       name=f"se{layer}"))
+
+    x_in, g_in = "B0", g1
+    for layer, g_out, c_out, (t0, t1, t2) in ((1, g1, 64, ("B1", "B2", "B0")), (2, g2, 128, ("C0", "C1", "C2")),
+                                             (3, g3, 256, ("D0", "D1", "D2")), (4, g4, 512, ("E0", "E1", "E2"))):
+        stride = 1 if layer == 1 else 2
+        u = f"{p}layer{layer}.0"
+        wf, bf = folded(u, "conv1", "bn1")
+        ops += make_conv_layer_ops(u + ".conv1", [(wf, g_in, stride, 1)], [x_in], g_out, c_out, t0, bf, EPI_RELU, precision)
+        wf2, bf2 = folded(u, "conv2", "bn2")
+        if layer == 1:          # identity shortcut (torchvision BasicBlock without downsample)
+            ops += make_conv_layer_ops(u + ".conv2", [(wf2, g_out, 1, 1)], [t0], g_out, c_out, t1, bf2, EPI_ADD_RELU, precision, aux=x_in)
+        else:                   # 1x1 / stride-2 downsample branch K-concatenated into conv2
+            wd, bd = folded(u, "downsample.0", "downsample.1")
+            ops += make_conv_layer_ops(u + ".conv2+downsample", [(wf2, g_out, 1, 1), (wd, g_in, 2, 0)], [t0, x_in], g_out, c_out, t1,
+                                       bf2 + bd, EPI_RELU, precision)
+        u = f"{p}layer{layer}.1"
+        wf, bf = folded(u, "conv1", "bn1")
+        ops += make_conv_layer_ops(u + ".conv1", [(wf, g_out, 1, 1)], [t1], g_out, c_out, t0, bf, EPI_RELU, precision)
+        wf, bf = folded(u, "conv2", "bn2")
+        ops += make_conv_layer_ops(u + ".conv2", [(wf, g_out, 1, 1)], [t0], g_out, c_out, t2, bf, EPI_ADD_RELU, precision, aux=t1)
+        se(layer, g_out, t2, t0)
+        x_in, g_in = t0, g_out
+    # spatial attention (7x7 conv over the [mean_c, max_c] map, models.py:56-61) + global average pool (:122-124)
+    wsa = _np64(sd[p + "spatial_attn.conv.weight"])             # [1, 2, 7, 7]
+    ops.append(_Op(OP_SAM_POOL, src=[_hi(x_in), _lo(x_in, precision), -1, -1], out=_hi("P0"), out_lo=_lo("P0", precision),
+                   n_tiles=g4, block_n=512, w=wsa.reshape(2, 49).astype(np.float32), name="spatial_attn+avgpool"))
+    return ops
+
+
+def head_ops(kind: str, sd, precision: str = "fp16x3", feat: str = "C1", scaled: int = 1, hid: str = "D0",
+             fp: Tuple[str, str] = ("C0", "C2")) -> List[_Op]:
+    """Stage heads (models.py:129-203) and the FGVC tail (006:261-293).  16x16 program: input x4' in C1 (+ the attention
+    scalar as a row scale); generic block sizes: the pooled, attention-weighted features in `feat`, no row scale."""
     ops: List[_Op] = []
     lin = lambda k: (_np64(sd[f"head.head.{k}.weight"]), _np64(sd[f"head.head.{k}.bias"]))
     if kind == "stage1":
         w0, b0 = lin(0)
         w1, b1 = lin(3)
-        ops.append(make_fc_op("head.0+3", [w0], ["C1"], None, b0, EPI_HEAD, 256, precision, use_row_scale=1, tail_w=w1, tail_b=b1))
+        ops.append(make_fc_op("head.0+3", [w0], [feat], None, b0, EPI_HEAD, 256, precision, use_row_scale=scaled, tail_w=w1, tail_b=b1))
     elif kind in ("stage2", "ab", "rect", "stage2_adapters"):
         w0, b0 = lin(0)
         w1, b1 = lin(3)
         w2, b2 = lin(6)
-        feat, scaled = ("C2", 0) if kind == "stage2_adapters" else ("C1", 1)    # the last adapter already applied the attention scalar
-        ops.append(make_fc_op("head.0", [w0], [feat], "D0", b0, EPI_RELU, _block_n(w0.shape[0]), precision, use_row_scale=scaled))
-        # head.3 reads the first w0.shape[0] columns of D0
-        ops.append(make_fc_op("head.3+6", [w1], ["D0"], None, b1, EPI_HEAD, _block_n(w1.shape[0]), precision, tail_w=w2, tail_b=b2))
+        if kind == "stage2_adapters":
+            feat, scaled = "C2", 0                                # the last adapter already applied the attention scalar
+        ops.append(make_fc_op("head.0", [w0], [feat], hid, b0, EPI_RELU, _block_n(w0.shape[0]), precision, use_row_scale=scaled))
+        # head.3 reads the first w0.shape[0] columns of the hidden buffer
+        ops.append(make_fc_op("head.3+6", [w1], [hid], None, b1, EPI_HEAD, _block_n(w1.shape[0]), precision, tail_w=w2, tail_b=b2))
     elif kind == "flat7":
         # Stage2FlatModel head (008b_run_pipeline_flatten_eval.py:120-127): Dropout, Linear(512,256), BN1d, ReLU, Dropout, Linear(256,7)
         w0, b0 = fold_bn(_np64(sd["head.1.weight"]), _np64(sd["head.1.bias"]), sd, "head.2")
         w1, b1 = _np64(sd["head.5.weight"]), _np64(sd["head.5.bias"])
-        ops.append(make_fc_op("head.1+2+5", [w0], ["C1"], None, b0, EPI_HEAD, 256, precision, use_row_scale=1, tail_w=w1, tail_b=b1))
+        ops.append(make_fc_op("head.1+2+5", [w0], [feat], None, b0, EPI_HEAD, 256, precision, use_row_scale=scaled, tail_w=w1, tail_b=b1))
     elif kind == "ab_fgvc":
         w0, b0 = fold_bn(_np64(sd["feat_proj.0.weight"]), _np64(sd["feat_proj.0.bias"]), sd, "feat_proj.1")
         w1, b1 = fold_bn(_np64(sd["feat_proj.4.weight"]), _np64(sd["feat_proj.4.bias"]), sd, "feat_proj.5")
-        ops.append(make_fc_op("feat_proj.0+1", [w0], ["C1"], "C0", b0, EPI_RELU, 256, precision, use_row_scale=1))
-        ops.append(make_fc_op("feat_proj.4+5", [w1], ["C0"], "C2", b1, EPI_RELU, 256, precision))
+        ops.append(make_fc_op("feat_proj.0+1", [w0], [feat], fp[0], b0, EPI_RELU, 256, precision, use_row_scale=scaled))
+        ops.append(make_fc_op("feat_proj.4+5", [w1], [fp[0]], fp[1], b1, EPI_RELU, 256, precision))
         wc = _np64(sd["classifier.weight"])
         wc = wc / np.maximum(np.linalg.norm(wc, axis=1, keepdims=True), 1e-12)    # F.normalize(weight)
-        ops.append(_Op(OP_FGVC_TAIL, src=[_hi("C2"), _lo("C2", precision), -1, -1], f0=20.0, w=wc.astype(np.float32),
+        ops.append(_Op(OP_FGVC_TAIL, src=[_hi(fp[1]), _lo(fp[1], precision), -1, -1], f0=20.0, w=wc.astype(np.float32),
                        name="cosine_classifier"))
     else:
         raise ValueError(f"unknown stage kind {kind!r}")
@@ -411,13 +618,13 @@ def _align(n: int, a: int = 256) -> int:
     return -(-n // a) * a
 
 
-OP_FMT = "<17i2f4Q9i128H128H"
+OP_FMT = "<17i2f4Q9i128H128H2i"
 OP_BYTES = struct.calcsize(OP_FMT)
 
 
-def serialise(kind: str, ops: List[_Op], precision: str) -> bytes:
+def serialise(kind: str, ops: List[_Op], precision: str, block: int = 16) -> bytes:
     header_fmt = "<8I4Q"
-    assert struct.calcsize(header_fmt) == 64 and OP_BYTES == 656
+    assert struct.calcsize(header_fmt) == 64 and OP_BYTES == 664
     cols = list(BUF_COLS.values()) * (2 if precision == "fp16x3" else 1)
     n_bufs = len(cols)
     ops_off = 64
@@ -425,14 +632,19 @@ def serialise(kind: str, ops: List[_Op], precision: str) -> bytes:
     cursor = _align(bufs_off + 4 * n_bufs)
     data = []
 
+    placed: Dict[int, int] = {}            # the ops of one wide layer share their weight array: store it once
+
     def put(arr: Optional[np.ndarray]) -> int:
         nonlocal cursor
         if arr is None:
             return 0
+        if id(arr) in placed:
+            return placed[id(arr)]
         raw = np.ascontiguousarray(arr).tobytes()
         off = cursor
         data.append((off, raw))
         cursor = _align(cursor + len(raw))
+        placed[id(arr)] = off
         return off
 
     table = b""
@@ -443,11 +655,11 @@ def serialise(kind: str, ops: List[_Op], precision: str) -> bytes:
         kbw = list(op.kb_w) + [0] * (MAX_KB - len(op.kb_w))
         table += struct.pack(OP_FMT, op.type, *op.src, op.aux, op.aux_lo, op.out, op.out_lo, op.n_tiles, op.block_n,
                              op.epi, op.tail_n, op.use_row_scale, len(op.kb_src), op.n_w_chunks, op.pair_mode, op.f0, op.f1,
-                             w_off, b_off, tw_off, tb_off, *kbb, *kbs, *kbw)
+                             w_off, b_off, tw_off, tb_off, *kbb, *kbs, *kbw, op.out_col0, 0)
     total = cursor
     blob = bytearray(total)
     blob[0:64] = struct.pack(header_fmt, BLOB_MAGIC, BLOB_VERSION, STAGE_KINDS[kind], len(ops), n_bufs, NUM_OUTPUTS[kind],
-                             PRECISIONS.index(precision), 0, ops_off, bufs_off, total, 0)
+                             PRECISIONS.index(precision), block, ops_off, bufs_off, total, 0)
     blob[ops_off:ops_off + len(table)] = table
     blob[bufs_off:bufs_off + 4 * n_bufs] = struct.pack(f"<{n_bufs}I", *cols)
     for off, raw in data:
@@ -455,17 +667,39 @@ def serialise(kind: str, ops: List[_Op], precision: str) -> bytes:
     return bytes(blob)
 
 
-def pack_stage(kind: str, state_dict, precision: str = "fp16x3", layer1_fc: bool = False) -> bytes:
+_PACK_LOCK = __import__("threading").Lock()      # the buffer plan is module state while a program is being packed
+
+
+def pack_stage(kind: str, state_dict, precision: str = "fp16x3", layer1_fc: bool = False, block: int = 16,
+               generic: bool = False) -> bytes:
     """`state_dict` of Stage1Model / Stage2Model / Stage3RectModel / Stage3ABModel / FGVCModel -> blob.
 
     precision: "fp16x3" (default; split fp16 operands, fp32-grade logits) or "fp16" (single product).
+    block: luma block size the network is applied to - 16 (the v6 pipeline's, specialised program) or 8 / 32 / 64 (generic
+    program: same tensor-core FC kernel, generic stem / squeeze-excite / attention kernels).  generic=True packs the generic
+    program for 16 as well (cross-check of the two programs).
     """
     if kind not in STAGE_KINDS:
         raise ValueError(f"unknown stage kind {kind!r}")
     if precision not in PRECISIONS:
         raise ValueError(f"unknown precision {precision!r}")
-    return serialise(kind, backbone_ops(state_dict, precision, layer1_fc=layer1_fc, adapters=kind == "stage2_adapters")
-                     + head_ops(kind, state_dict, precision), precision)
+    if block not in BLOCK_SIZES:
+        raise ValueError(f"block size must be one of {BLOCK_SIZES}, got {block}")
+    with _PACK_LOCK:
+        try:
+            if block == 16 and not generic:
+                _install_plan(16)
+                ops = backbone_ops(state_dict, precision, layer1_fc=layer1_fc, adapters=kind == "stage2_adapters") \
+                    + head_ops(kind, state_dict, precision)
+            else:
+                if kind == "stage2_adapters":
+                    raise ValueError("Stage2ModelWithAdapters is packed for 16x16 blocks only")
+                _install_plan(block, generic=True)
+                ops = backbone_ops_generic(state_dict, block, precision) \
+                    + head_ops(kind, state_dict, precision, feat="P0", scaled=0, hid="Q0", fp=("P1", "P2"))
+            return serialise(kind, ops, precision, block)
+        finally:
+            _install_plan(16)
 
 
 def blob_stats(blob: bytes) -> Dict[str, float]:

@@ -45,6 +45,7 @@ class HierarchicalPipelineV6:
         self._cascade_key = None
         self._min_capacity = int(capacity_blocks)
         self._twins = {}                # slot -> (plan, weights key): extra cascade plans of the multi-stream chunk schedule
+        self._sized = {}                # block size (8 / 32 / 64) -> (plan, weights key): plans of the other block sizes
         self._streams: List = []        # their streams
         # predict() on small batches (the reference's evaluate_pipeline feeds 256 blocks per call, 008:278-284) is bound by
         # the ~110 kernel launches of a cascade, not by the GPU: such calls replay a CUDA graph of the whole cascade,
@@ -56,11 +57,18 @@ class HierarchicalPipelineV6:
     def _models(self) -> List:
         return [self.stage1_model, self.stage2_model, self.stage3_rect_model, self.stage3_ab_model]
 
-    def cascade(self, n_blocks: int, slot: int = 0) -> NativeCascade:
+    def cascade(self, n_blocks: int, slot: int = 0, block: int = 16) -> NativeCascade:
         """The cascade plan (and its workspace) with room for n_blocks.  Slots >= 1 are further, independent plans over the
-        same packed weights: chunked calls rotate over them, one stream each (see predict_frames_pipelined)."""
-        natives = [m.native_model(self.device) for m in self._models()]
+        same packed weights: chunked calls rotate over them, one stream each (see predict_frames_pipelined).  block: luma
+        block size - 16 is the v6 pipeline's; 8 / 32 / 64 get their own packed programs and one plan each."""
+        natives = [m.native_model(self.device, block) for m in self._models()]
         key = tuple(id(nm) for nm in natives)
+        if block != 16:
+            plan, plan_key = self._sized.get(block, (None, None))
+            if plan is None or plan_key != key or plan.capacity < n_blocks:
+                plan = NativeCascade(natives, max(n_blocks, 256))
+                self._sized[block] = (plan, key)
+            return plan
         if slot == 0:
             if self._cascade is None or self._cascade_key != key or self._cascade.capacity < n_blocks:
                 cap = max(n_blocks, self._min_capacity, 256)
@@ -88,14 +96,13 @@ class HierarchicalPipelineV6:
                        out_i64: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Labels on the device.  Returns out_i64 if given (or created when out_u8 is None), else out_u8."""
         images = images.to(self.device, non_blocking=True)
-        if images.dim() != 4 or tuple(images.shape[1:]) != (1, 16, 16):
-            raise ValueError(f"expected images [B,1,16,16], got {tuple(images.shape)}")
+        block = N.block_size_of(images)                         # [B,1,b,b], b in {8, 16, 32, 64}
         images = images.contiguous().float()
         n = images.shape[0]
         if out_u8 is None and out_i64 is None:
             out_i64 = torch.empty(n, dtype=torch.int64, device=self.device)
         if n:
-            self.cascade(n).predict(N.images_input(images), n, self.stage1_threshold, out_u8, out_i64)
+            self.cascade(n, block=block).predict(N.images_input(images, block), n, self.stage1_threshold, out_u8, out_i64)
         return out_i64 if out_i64 is not None else out_u8
 
     GRAPH_MAX_BLOCKS = 16384          # above this a cascade is GPU-bound and the launches hide behind it
@@ -146,21 +153,24 @@ class HierarchicalPipelineV6:
     @torch.no_grad()
     def predict_frames(self, frames: torch.Tensor, width: int, height: int, n_frames: int,
                        out_u8: Optional[torch.Tensor] = None, pitch: Optional[int] = None,
-                       frame_stride: Optional[int] = None) -> torch.Tensor:
-        """Partition labels for every 16x16 luma block of `n_frames` planar YUV 4:2:0 10-bit LE frames.
+                       frame_stride: Optional[int] = None, block_size: int = 16) -> torch.Tensor:
+        """Partition labels for every block_size x block_size (default 16x16) luma block of `n_frames` planar YUV 4:2:0
+        10-bit LE frames.
 
         frames: flat uint16 tensor (device, or host - it is copied).  Block order: frame-major, then the
         row-major grid of 005_rearrange_video_YUV_420_10bit_LOSSLESS.py:402-433; the zero padding of
         :380-383 applies at the bottom/right edge.  Returns uint8 labels [n_frames * blocks_per_frame] on
         the device, in predict()'s label space.
         """
+        if block_size not in N.BLOCK_SIZES:
+            raise ValueError(f"block_size must be one of {N.BLOCK_SIZES}")
         frames = frames.to(self.device, non_blocking=True)
-        bpf = math.ceil(height / 16) * math.ceil(width / 16)
+        bpf = math.ceil(height / block_size) * math.ceil(width / block_size)
         n = bpf * n_frames
         if out_u8 is None:
             out_u8 = torch.empty(n, dtype=torch.uint8, device=self.device)
         inp = N.frames_input(frames, width, height, n_frames, pitch, frame_stride)
-        self.cascade(n).predict(inp, n, self.stage1_threshold, out_u8, None)
+        self.cascade(n, block=block_size).predict(inp, n, self.stage1_threshold, out_u8, None)
         return out_u8
 
 
@@ -274,7 +284,8 @@ class HierarchicalPipelineV6:
         return out_host
 
     def _plans(self):
-        return ([self._cascade] if self._cascade is not None else []) + [t for t, _ in self._twins.values()]
+        return ([self._cascade] if self._cascade is not None else []) + [t for t, _ in self._twins.values()] + \
+            [t for t, _ in self._sized.values()]
 
     def check_input_range(self, synchronize: bool = True) -> None:
         """Raise if a frame-input call on this pipeline since the last check met a luma sample above 2048.  The reference

@@ -18,13 +18,14 @@ from .packer import NUM_OUTPUTS, pack_stage, blob_stats
 class NativeModel:
     """One packed stage network resident in HBM (av1p_model)."""
 
-    def __init__(self, kind: str, state_dict, device: torch.device, precision: str = "fp16x3"):
+    def __init__(self, kind: str, state_dict, device: torch.device, precision: str = "fp16x3", block: int = 16):
         self.kind = kind
         self.precision = precision
+        self.block = int(block)
         self.device = torch.device(device)
         # AV1P_LAYER1_FC=1: run layer1 on the generic block-Toeplitz FC kernel instead of the resident-weight conv kernel
         # (A/B measurements only; both are tcgen05 device paths)
-        blob = pack_stage(kind, state_dict, precision, layer1_fc=os.environ.get("AV1P_LAYER1_FC", "0") == "1")
+        blob = pack_stage(kind, state_dict, precision, layer1_fc=os.environ.get("AV1P_LAYER1_FC", "0") == "1", block=self.block)
         self.stats = blob_stats(blob)
         self.num_outputs = NUM_OUTPUTS[kind]
         handle = C.c_void_p()

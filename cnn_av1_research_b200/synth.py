@@ -100,10 +100,14 @@ def random_state_dict(kind: str, seed: int) -> Dict[str, torch.Tensor]:
     return sd
 
 
-def calibrated_state_dict(kind: str, seed: int = 0) -> Dict[str, torch.Tensor]:
-    """random_state_dict + the stored calibration (BN running statistics, last-layer gain and bias)."""
+def calibrated_state_dict(kind: str, seed: int = 0, block: int = 16) -> Dict[str, torch.Tensor]:
+    """random_state_dict + the stored calibration (BN running statistics, last-layer gain and bias).  `block`: the block
+    size the BatchNorm statistics were calibrated at (random weights keep O(1) activations only on inputs of the size their
+    statistics come from; tools/make_golden_blocksizes.py produced the 8 / 32 / 64 files)."""
     sd = random_state_dict(kind, seed)
     path = _CAL_FLAT_PATH if kind in EXTRA_KINDS else _CAL_PATH
+    if block != 16:
+        path = os.path.join(os.path.dirname(_CAL_PATH), f"synth_calibration_b{block}.npz")
     if not os.path.exists(path):
         raise FileNotFoundError(f"{path} is missing (generated by tools/make_golden*.py)")
     cal = np.load(path)
@@ -118,8 +122,8 @@ def calibrated_state_dict(kind: str, seed: int = 0) -> Dict[str, torch.Tensor]:
     return sd
 
 
-def calibrated_cascade(seed: int = 0) -> Dict[str, Dict[str, torch.Tensor]]:
-    return {k: calibrated_state_dict(k, seed) for k in ("stage1", "stage2", "rect", "ab_fgvc")}
+def calibrated_cascade(seed: int = 0, block: int = 16) -> Dict[str, Dict[str, torch.Tensor]]:
+    return {k: calibrated_state_dict(k, seed, block) for k in ("stage1", "stage2", "rect", "ab_fgvc")}
 
 
 def ensemble_state_dicts(n_models: int = 3, seed: int = 0):

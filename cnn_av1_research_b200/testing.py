@@ -9,9 +9,10 @@ from .models import FGVCModel, Stage1Model, Stage2Model, Stage3ABModel, Stage3Re
 from .pipeline import HierarchicalPipelineV6
 
 
-def build_models(seed: int = 0, calibrated: bool = True):
-    """The four stage networks the pipeline uses (008:219-242), loaded from synthetic state dicts."""
-    make_sd = synth.calibrated_state_dict if calibrated else synth.random_state_dict
+def build_models(seed: int = 0, calibrated: bool = True, block: int = 16):
+    """The four stage networks the pipeline uses (008:219-242), loaded from synthetic state dicts (`block`: the block size the
+    calibrated BatchNorm statistics were taken at)."""
+    make_sd = (lambda kind, s: synth.calibrated_state_dict(kind, s, block)) if calibrated else synth.random_state_dict
     nets = {"stage1": Stage1Model(pretrained=False), "stage2": Stage2Model(pretrained=False),
             "rect": Stage3RectModel(pretrained=False), "ab_fgvc": FGVCModel(Stage3ABModel(pretrained=False))}
     for kind, net in nets.items():
@@ -21,8 +22,8 @@ def build_models(seed: int = 0, calibrated: bool = True):
 
 
 def build_pipeline(seed: int = 0, threshold: float = 0.45, device="cuda", precision: str = "fp16x3",
-                   capacity_blocks: int = 0) -> HierarchicalPipelineV6:
-    nets = build_models(seed)
+                   capacity_blocks: int = 0, block: int = 16) -> HierarchicalPipelineV6:
+    nets = build_models(seed, block=block)
     return HierarchicalPipelineV6(nets["stage1"], nets["stage2"], nets["rect"], nets["ab_fgvc"], stage1_threshold=threshold,
                                   device=device, capacity_blocks=capacity_blocks, precision=precision)
 

@@ -305,8 +305,9 @@ def ensemble_vote(all_logits: torch.Tensor, mode: str = "hard", weights: Optiona
     return out
 
 
-def frames_to_images(frame_words: np.ndarray, n_frames: int, width: int, height: int) -> torch.Tensor:
+def frames_to_images(frame_words: np.ndarray, n_frames: int, width: int, height: int, block: int = 16) -> torch.Tensor:
     """Reference data path from a planar YUV420p10le buffer to predict()'s input tensor:
-    read luma (005:142-212) -> tile (005:353-457) -> /1023 (data_hub.py:70-77); frames concatenated."""
-    tiles = [normalise_blocks(extract_blocks(luma_plane(frame_words, f, width, height), 16)) for f in range(n_frames)]
+    read luma (005:142-212) -> tile at `block` (005:353-457; 8 / 16 / 32 / 64, :32) -> /1023 (data_hub.py:70-77); frames
+    concatenated."""
+    tiles = [normalise_blocks(extract_blocks(luma_plane(frame_words, f, width, height), block)) for f in range(n_frames)]
     return torch.from_numpy(np.concatenate(tiles, axis=0))

@@ -11,13 +11,14 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-OP_FMT = "<17i2f4Q9i128H128H"
+OP_FMT = "<17i2f4Q9i128H128H2i"
 OP_BYTES = struct.calcsize(OP_FMT)
 
 
 def parse(blob: bytes):
-    magic, version, kind, n_ops, n_bufs, n_out, prec, _, ops_off, bufs_off, total, _ = struct.unpack_from("<8I4Q", blob, 0)
-    assert magic == 0x50315641 and version == 10 and total == len(blob)
+    magic, version, kind, n_ops, n_bufs, n_out, prec, _, ops_off, bufs_off, total, _r2 = struct.unpack_from("<8I4Q", blob, 0)
+    assert magic == 0x50315641 and version == 11 and total == len(blob)
+    block = _ or 16
     cols = struct.unpack_from(f"<{n_bufs}I", blob, bufs_off)
     ops = []
     for i in range(n_ops):
@@ -25,8 +26,8 @@ def parse(blob: bytes):
         ops.append(dict(type=f[0], src=f[1:5], aux=f[5], aux_lo=f[6], out=f[7], out_lo=f[8], n_tiles=f[9], block_n=f[10],
                         epi=f[11], tail_n=f[12], use_row_scale=f[13], n_kb=f[14], n_w_chunks=f[15], pair_mode=f[16], f0=f[17],
                         f1=f[18], w_off=f[19], bias_off=f[20], tail_w_off=f[21], tail_b_off=f[22], kb_begin=f[23:32],
-                        kb_src=f[32:160], kb_w=f[160:288]))
-    return dict(kind=kind, n_out=n_out, cols=cols, ops=ops, precision=prec)
+                        kb_src=f[32:160], kb_w=f[160:288], out_col0=f[288]))
+    return dict(kind=kind, n_out=n_out, cols=cols, ops=ops, precision=prec, block=block)
 
 
 def _arr(blob, off, dtype, count):
@@ -38,18 +39,18 @@ def _h16(a):
 
 
 def run(blob: bytes, images: np.ndarray) -> np.ndarray:
-    """images: float32 [n,1,16,16] -> logits float32 [n, n_out] as the device program computes them."""
+    """images: float32 [n,1,b,b] (b = the blob's block size) -> logits float32 [n, n_out] as the device program computes them."""
     P = parse(blob)
     n = images.shape[0]
     bufs = [np.zeros((n, c), dtype=np.float32) for c in P["cols"]]
     row_scale = np.ones(n, dtype=np.float32)
     logits = None
 
-    def store(op, val, width):
+    def store(op, val, width, col0=0):
         hi = _h16(val)
-        bufs[op["out"]][:, :width] = hi
+        bufs[op["out"]][:, col0:col0 + width] = hi
         if op["out_lo"] >= 0:
-            bufs[op["out_lo"]][:, :width] = _h16(val - hi)
+            bufs[op["out_lo"]][:, col0:col0 + width] = _h16(val - hi)
 
     def load(hi_id, lo_id):
         return bufs[hi_id] + (bufs[lo_id] if lo_id >= 0 else 0.0)
@@ -89,8 +90,9 @@ def run(blob: bytes, images: np.ndarray) -> np.ndarray:
             if op["bias_off"]:
                 acc += _arr(blob, op["bias_off"], np.float32, nt * bn)[None, :]
             epi = op["epi"]
+            c0 = op["out_col0"]
             if epi in (2, 3, 5):
-                aux = load(op["aux"], op["aux_lo"])[:, : nt * bn]
+                aux = load(op["aux"], op["aux_lo"])[:, c0:c0 + nt * bn]
                 if epi == 5:        # adapter skip, optionally scaled by the spatial-attention scalar; no ReLU
                     acc = acc + aux * (row_scale[:, None] if op["use_row_scale"] & 2 else 1.0)
                 else:
@@ -102,7 +104,8 @@ def run(blob: bytes, images: np.ndarray) -> np.ndarray:
                 tb = _arr(blob, op["tail_b_off"], np.float32, op["tail_n"])
                 logits = acc @ tw.T + tb[None, :]
             else:
-                store(op, acc, nt * bn)
+                width = min(nt * bn, P["cols"][op["out"]] - c0)
+                store(op, acc[:, :width], width, c0)
         elif t == 2:  # spatial attention scalar
             x = load(op["src"][0], op["src"][1])
             a = op["f0"] * x.mean(axis=1) + op["f1"] * x.max(axis=1)
@@ -142,6 +145,30 @@ def run(blob: bytes, images: np.ndarray) -> np.ndarray:
             if op["epi"] in (1, 2):
                 acc = np.maximum(acc, 0.0)
             store(op, acc, 1024)
+        elif t == 6:  # generic stem (fp32 on CUDA cores): conv1 + folded BN + ReLU + maxpool, any block size
+            b = op["n_tiles"]
+            g1 = b // 4
+            w = _arr(blob, op["w_off"], np.float32, 64 * 49).reshape(64, 1, 7, 7)
+            bias = _arr(blob, op["bias_off"], np.float32, 64)
+            x = F.conv2d(torch.from_numpy(images), torch.from_numpy(w.copy()), torch.from_numpy(bias.copy()), stride=2, padding=3)
+            x = F.max_pool2d(F.relu(x), 3, 2, 1)
+            assert x.shape[2] == g1
+            store(op, x.permute(0, 2, 3, 1).reshape(n, g1 * g1 * 64).numpy(), g1 * g1 * 64)
+        elif t == 7:  # generic squeeze-excite
+            c, npos = op["block_n"], op["n_tiles"]
+            hdim = c // 16
+            wt = _arr(blob, op["w_off"], np.float32, 2 * hdim * c).reshape(2, hdim, c)
+            x = load(op["src"][0], op["src"][1])[:, : npos * c].reshape(n, npos, c)
+            hid = np.maximum(x.mean(axis=1) @ wt[0].T, 0.0)
+            sgate = 1.0 / (1.0 + np.exp(-(hid @ wt[1])))
+            store(op, (x * sgate[:, None, :]).reshape(n, npos * c), npos * c)
+        elif t == 8:  # spatial attention (7x7 conv over [mean_c, max_c]) + global average pool
+            g = op["n_tiles"]
+            kern = _arr(blob, op["w_off"], np.float32, 98).reshape(1, 2, 7, 7)
+            x = torch.from_numpy(load(op["src"][0], op["src"][1])[:, : g * g * 512].reshape(n, g, g, 512)).permute(0, 3, 1, 2)
+            att = torch.cat([x.mean(dim=1, keepdim=True), x.max(dim=1, keepdim=True).values], dim=1)
+            att = torch.sigmoid(F.conv2d(att, torch.from_numpy(kern.copy()), padding=3))
+            store(op, (x * att).mean(dim=(2, 3)).numpy(), 512)
         else:
             raise ValueError(t)
     return logits.astype(np.float32)

@@ -96,7 +96,7 @@ def test_bucketed_exchange_equals_single_flat_allreduce():
     # the first bucket holds the LAST parameters (head), i.e. what backward produces first
     assert many._bucket_of[many.params[-1]] == 0 and many._bucket_of[many.params[0]] == len(many.buckets) - 1
     assert dict(many.named_params)["head.temperature"].grad is None
-    assert float(dict(many.named_params)["head.temperature"]) == 1.5
+    assert dict(many.named_params)["head.temperature"].item() == 1.5
 
 
 def _dp_worker(rank, world, port, q):
