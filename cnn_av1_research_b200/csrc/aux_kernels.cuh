@@ -57,6 +57,8 @@ __device__ __forceinline__ void load_row16(const __half* __restrict__ hi, const 
 // sum and the maximum over `slots` partials, then the same scalar as sam_gate_kernel.
 __global__ void __launch_bounds__(256) sam_finish_kernel(const float* __restrict__ part, int slots, const int* n_dev, int n,
                                                          float w_avg, float w_max, float* __restrict__ row_scale) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int rows = n_dev ? *n_dev : n;
   for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += gridDim.x * blockDim.x) {
     const float2* q = reinterpret_cast<const float2*>(part) + size_t(r) * slots;
@@ -73,6 +75,8 @@ __global__ void __launch_bounds__(256) sam_finish_kernel(const float* __restrict
 __global__ void __launch_bounds__(256) sam_gate_kernel(const __half* __restrict__ x, const __half* __restrict__ x_lo,
                                                        int ld, const int* n_dev, int n, float w_avg, float w_max,
                                                        float* __restrict__ row_scale) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int rows = n_dev ? *n_dev : n;
   const int lane = threadIdx.x & 31;
   const int warps_per_grid = (gridDim.x * blockDim.x) >> 5;
@@ -148,11 +152,13 @@ __global__ void __launch_bounds__(256) se_kernel(const __half* __restrict__ x, c
   // smem copy of [W1 ; W2^T], each row permuted to [half][group][4] so that the lanes of a warp (one channel
   // group each) read consecutive 16-byte words: channel g*8 + h*4 + k  ->  h*(C/2) + g*4 + k
   extern __shared__ __align__(16) float se_w[];
-  for (int i = threadIdx.x; i < 2 * H * C; i += blockDim.x) {
+  pdl_launch_dependents();
+  for (int i = threadIdx.x; i < 2 * H * C; i += blockDim.x) {      // constant weights: overlaps the previous kernel's tail
     const int row = i / C, ch = i - row * C;
     se_w[row * C + ((ch >> 2) & 1) * (C / 2) + (ch >> 3) * 4 + (ch & 3)] = w[i];
   }
   __syncthreads();
+  pdl_wait();
   const float* w1 = se_w;
   const float* w2t = se_w + H * C;
   const int wg = (threadIdx.x & 31) % GROUPS * 4;      // this lane's word offset inside a half row
@@ -272,6 +278,8 @@ __global__ void __launch_bounds__(256) fgvc_tail_kernel(const __half* __restrict
                                                         int ld, const int* n_dev, int n,
                                                         const float* __restrict__ what, float scale,
                                                         float* __restrict__ logits, float* __restrict__ features) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int rows = n_dev ? *n_dev : n;
   const int lane = threadIdx.x & 31;
   const int warps_per_grid = (gridDim.x * blockDim.x) >> 5;

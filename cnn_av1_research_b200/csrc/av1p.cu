@@ -60,6 +60,7 @@ struct DeviceCtx {
                                   // two cascades on two streams, each on half of the SMs, run side by side instead of back to back)
   EncodeTiledFn encode = nullptr;
   bool fc_pair = true;            // FC layers on CTA pairs (tcgen05 cta_group::2); AV1P_FC_PAIR=0 selects the single-CTA kernel
+  bool pdl = true;                // programmatic dependent launch between the kernels of an op program (AV1P_PDL=0: plain stream order)
   bool fc_resid_epi = false;      // AV1P_FC_RESID_EPI=1: residual FC layers add the identity branch in the epilogue (aux ring)
                                   // instead of on the tensor core (FC_W_IDENT schedule entries).  Measured slower (layer2.1.conv2
                                   // 859 vs 740 us on 518 k rows): the aux ring costs two of the six operand-ring stages.
@@ -106,6 +107,7 @@ int ensure_ctx() {
   CUDA_TRY(cudaFuncSetAttribute(fc_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FC_SMEM_BYTES));
   if (const char* e = getenv("AV1P_FC_PAIR")) c.fc_pair = atoi(e) != 0;
   if (const char* e = getenv("AV1P_FC_RESID_EPI")) c.fc_resid_epi = atoi(e) != 0;
+  if (const char* e = getenv("AV1P_PDL")) c.pdl = atoi(e) != 0;
   {
     int n_k = 0;
     const ConvResKernel* ks = conv_res_all_kernels(&n_k);
@@ -231,28 +233,46 @@ extern "C" int av1p_get_option(const char* name) {
 
 extern "C" int av1p_debug_watchdog(void) { return g_ctx.watchdog_host ? *g_ctx.watchdog_host : 0; }
 
+// Launch of an op-program kernel.  These kernels call pdl_wait() before they touch anything a predecessor produced, so they
+// may be launched with programmatic stream serialization: their prologue (barrier init, TMEM allocation, weight loads)
+// overlaps the previous kernel's tail instead of following its last CTA (ptx_sm100.cuh).  `cluster` > 1: CTA clusters.
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_op(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st, unsigned cluster,
+                             Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  unsigned n = 0;
+  if (cluster > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = cluster;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (g_ctx.pdl) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
 // One FC layer: `rows` is the host-side upper bound on block rows (sizes the grid).  CTA-pair variant: clusters of two
 // CTAs, each pair takes two M tiles of an item.
 static int launch_fc(const FcParams& f, int rows, cudaStream_t st) {
   const int m_tiles = ceil_div(rows, FC_TILE_M);
   if (g_ctx.fc_pair && f.block_n % 16 == 0) {
     const int pairs = std::min(g_ctx.grid_sms / 2, ceil_div(m_tiles, 2) * f.n_tiles);
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(unsigned(2 * std::max(pairs, 1)));
-    cfg.blockDim = dim3(FC_THREADS);
-    cfg.dynamicSmemBytes = FC_SMEM_BYTES;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    CUDA_TRY(cudaLaunchKernelEx(&cfg, fc_tcgen05_kernel<true>, f));
+    CUDA_TRY(launch_op(fc_tcgen05_kernel<true>, unsigned(2 * std::max(pairs, 1)), FC_THREADS, FC_SMEM_BYTES, st, 2, f));
   } else {
     const int grid = std::min(g_ctx.grid_sms, m_tiles * f.n_tiles);
-    fc_tcgen05_kernel<false><<<grid, FC_THREADS, FC_SMEM_BYTES, st>>>(f);
+    CUDA_TRY(launch_op(fc_tcgen05_kernel<false>, unsigned(grid), FC_THREADS, FC_SMEM_BYTES, st, 1, f));
   }
   return AV1P_OK;
 }
@@ -772,9 +792,9 @@ int run_stage(av1p_stage* s, const StemInput& si, const int32_t* idx, const int3
           // frames: integer pixel plane + the / 1023 weight set (see stem_tc.cuh, INT_PIX)
           sp.w = P.stem_w_int;
           sp.acc_scale = P.stem_scale_int;
-          stem_tc_kernel<true><<<grid, ST_THREADS, ST_SMEM_BYTES, st>>>(sp);
+          CUDA_TRY(launch_op(stem_tc_kernel<true>, unsigned(grid), ST_THREADS, ST_SMEM_BYTES, st, 1, sp));
         } else {
-          stem_tc_kernel<false><<<grid, ST_THREADS, ST_SMEM_BYTES, st>>>(sp);
+          CUDA_TRY(launch_op(stem_tc_kernel<false>, unsigned(grid), ST_THREADS, ST_SMEM_BYTES, st, 1, sp));
         }
         break;
       }
@@ -791,16 +811,18 @@ int run_stage(av1p_stage* s, const StemInput& si, const int32_t* idx, const int3
         P.cr.n_rows = n;
         const int grid = 2 * std::max(1, std::min(g_ctx.grid_sms / 2, ceil_div(n, FC_TILE_M)));      // (M tile, half) items, even grid
         ProfScope ps(PROF_CONV, st);
-        conv_res_kernel_for(P.cr)<<<grid, CR_THREADS, CR_SMEM_BYTES, st>>>(P.cr);
+        CUDA_TRY(launch_op(conv_res_kernel_for(P.cr), unsigned(grid), CR_THREADS, CR_SMEM_BYTES, st, 1, P.cr));
         break;
       }
       case AV1P_OP_SAM: {
         ProfScope ps(PROF_SAM, st);
         if (P.se_npos > 0) {
-          sam_finish_kernel<<<std::min(ceil_div(n, 256), g_ctx.sms * 8), 256, 0, st>>>(s->sam_part, P.se_npos, n_dev, n, P.f0, P.f1, s->row_scale);
+          CUDA_TRY(launch_op(sam_finish_kernel, unsigned(std::min(ceil_div(n, 256), g_ctx.sms * 8)), 256, 0, st, 1,
+                             (const float*)s->sam_part, P.se_npos, n_dev, n, P.f0, P.f1, s->row_scale));
         } else {
           const int grid = std::min(ceil_div(n, 8), g_ctx.sms * 8);
-          sam_gate_kernel<<<grid, 256, 0, st>>>(P.src, P.src_lo, P.ld, n_dev, n, P.f0, P.f1, s->row_scale);
+          CUDA_TRY(launch_op(sam_gate_kernel, unsigned(grid), 256, 0, st, 1, (const __half*)P.src, (const __half*)P.src_lo, P.ld, n_dev, n,
+                             P.f0, P.f1, s->row_scale));
         }
         break;
       }
@@ -810,11 +832,14 @@ int run_stage(av1p_stage* s, const StemInput& si, const int32_t* idx, const int3
         // rows per warp iteration (template R): sharing one pass over the shared-memory weights between two rows measured
         // slower (fewer warps in flight), so every shape runs with R = 1
         if (P.se_c == 64)
-          se_kernel<64, 16, 1><<<std::min(ceil_div(n, 8), g_ctx.sms * 8), 256, smem, st>>>(P.src, P.src_lo, P.dst, P.dst_lo, n_dev, n, P.w);
+          CUDA_TRY(launch_op(se_kernel<64, 16, 1>, unsigned(std::min(ceil_div(n, 8), g_ctx.sms * 8)), 256, smem, st, 1, (const __half*)P.src,
+                             (const __half*)P.src_lo, P.dst, P.dst_lo, n_dev, n, (const float*)P.w));
         else if (P.se_c == 128)
-          se_kernel<128, 4, 1><<<std::min(ceil_div(n, 8), g_ctx.sms * 8), 256, smem, st>>>(P.src, P.src_lo, P.dst, P.dst_lo, n_dev, n, P.w);
+          CUDA_TRY(launch_op(se_kernel<128, 4, 1>, unsigned(std::min(ceil_div(n, 8), g_ctx.sms * 8)), 256, smem, st, 1, (const __half*)P.src,
+                             (const __half*)P.src_lo, P.dst, P.dst_lo, n_dev, n, (const float*)P.w));
         else
-          se_kernel<256, 1, 1><<<std::min(ceil_div(n, 8), g_ctx.sms * 8), 256, smem, st>>>(P.src, P.src_lo, P.dst, P.dst_lo, n_dev, n, P.w);
+          CUDA_TRY(launch_op(se_kernel<256, 1, 1>, unsigned(std::min(ceil_div(n, 8), g_ctx.sms * 8)), 256, smem, st, 1, (const __half*)P.src,
+                             (const __half*)P.src_lo, P.dst, P.dst_lo, n_dev, n, (const float*)P.w));
         break;
       }
       case AV1P_OP_STEM_GEN: {
@@ -843,7 +868,8 @@ int run_stage(av1p_stage* s, const StemInput& si, const int32_t* idx, const int3
       case AV1P_OP_FGVC_TAIL: {
         const int grid = std::min(ceil_div(n, 8), g_ctx.sms * 8);
         ProfScope ps(PROF_FGVC, st);
-        fgvc_tail_kernel<<<grid, 256, 0, st>>>(P.src, P.src_lo, P.ld, n_dev, n, P.w, P.f0, logits, s->features_out);
+        CUDA_TRY(launch_op(fgvc_tail_kernel, unsigned(grid), 256, 0, st, 1, (const __half*)P.src, (const __half*)P.src_lo, P.ld, n_dev, n,
+                           (const float*)P.w, P.f0, logits, s->features_out));
         break;
       }
     }

@@ -261,9 +261,8 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_res_tcgen05_kernel(const _
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int n_rows = p.n_rows_dev ? *p.n_rows_dev : p.n_rows;
-  const int m_tiles = (n_rows + FC_TILE_M - 1) / FC_TILE_M;
   constexpr int planes = SPLIT ? 2 : 1;
+  pdl_launch_dependents();
   constexpr bool residual = RESID;
   // Work item = (M tile, half): the grid is even, CTA b always takes half b & 1 of the M tiles b >> 1, b >> 1 + grid / 2, ...
   // so that (a) the wave quantisation of a launch is in half tiles, (b) few-tile launches spread over twice as many SMs and
@@ -309,15 +308,22 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_res_tcgen05_kernel(const _
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
+    // resident weights first: planes x 9 tiles of 8 KB on one barrier.  They are constant data, so the load is issued
+    // before pdl_wait() and overlaps the previous kernel's tail (the MMA warp always waits for it, work or no work).
+    if (elect_one_sync()) {
+      mbar_arrive_expect_tx(w_bar, uint32_t(planes * CR_W_PLANE_BYTES));
+      for (int t = 0; t < planes * 9; ++t)
+        tma_load_2d(smem + CR_OFF_W + t * CR_W_TILE_BYTES, &p.w_map, w_bar, 0, t * 64);
+    }
+    __syncwarp();
+  }
+  pdl_wait();      // the previous kernel's activations and the device-side row count are visible from here on
+  const int n_rows = p.n_rows_dev ? *p.n_rows_dev : p.n_rows;
+  const int m_tiles = (n_rows + FC_TILE_M - 1) / FC_TILE_M;
+
+  if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (warp-uniform loop, one lane issues)
     if (mt0 < m_tiles) {
-      // resident weights first: planes x 9 tiles of 8 KB on one barrier
-      if (elect_one_sync()) {
-        mbar_arrive_expect_tx(w_bar, uint32_t(planes * CR_W_PLANE_BYTES));
-        for (int t = 0; t < planes * 9; ++t)
-          tma_load_2d(smem + CR_OFF_W + t * CR_W_TILE_BYTES, &p.w_map, w_bar, 0, t * 64);
-      }
-      __syncwarp();
       int stage = 0;
       uint32_t phase = 0;
       // L2 prefetch cursor: runs CR_PREFETCH ring tiles ahead of the loads (into the next M tile of this CTA)
@@ -357,10 +363,10 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_res_tcgen05_kernel(const _
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (warp-uniform, one lane issues)
+    mbar_wait(w_bar, 0u, p.err_flag, 500);      // also when this CTA has no work: it must not exit under its own TMA load
     if (mt0 < m_tiles) {
       CrPipe q{full_bar, empty_bar, acc_full, acc_empty, 0, 0u, 0u};
       const uint64_t id_desc = ident_desc(base + CR_OFF_IDENT);
-      mbar_wait(w_bar, 0u, p.err_flag, 500);
       tc_fence_after_sync();
       if (half == 0) {
         for (int mt = mt0; mt < m_tiles; mt += mt_step)

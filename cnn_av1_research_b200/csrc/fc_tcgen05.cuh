@@ -505,12 +505,7 @@ __global__ void __launch_bounds__(FC_THREADS, 1) fc_tcgen05_kernel(const __grid_
   const int worker = PAIR ? int(blockIdx.x >> 1) : int(blockIdx.x);        // index of this CTA (pair) among the workers
   const int n_workers = PAIR ? int(gridDim.x >> 1) : int(gridDim.x);
 
-  const int n_rows = p.n_rows_dev ? *p.n_rows_dev : p.n_rows;
-  const int m_tiles = (n_rows + FC_TILE_M - 1) / FC_TILE_M;
-  const int m_groups = PAIR ? (m_tiles + 1) / 2 : m_tiles;                  // M tiles (pairs of M tiles) to process
-  const int n_items = m_groups * p.n_tiles;
-  auto item_mt = [&](int item) { return PAIR ? 2 * (item / p.n_tiles) + int(rank) : item / p.n_tiles; };
-
+  pdl_launch_dependents();
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < FC_MAX_SRC; ++i) tma_prefetch_desc(&p.a_map[i]);
     tma_prefetch_desc(PAIR ? &p.w_half_map : &p.w_map);
@@ -556,6 +551,15 @@ __global__ void __launch_bounds__(FC_THREADS, 1) fc_tcgen05_kernel(const __grid_
   else __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+
+  // everything above overlapped the previous kernel's tail (programmatic dependent launch); its results - the activations
+  // and the device-side row count - are visible from here on
+  pdl_wait();
+  const int n_rows = p.n_rows_dev ? *p.n_rows_dev : p.n_rows;
+  const int m_tiles = (n_rows + FC_TILE_M - 1) / FC_TILE_M;
+  const int m_groups = PAIR ? (m_tiles + 1) / 2 : m_tiles;                  // M tiles (pairs of M tiles) to process
+  const int n_items = m_groups * p.n_tiles;
+  auto item_mt = [&](int item) { return PAIR ? 2 * (item / p.n_tiles) + int(rank) : item / p.n_tiles; };
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (warp-uniform loop, one lane issues)

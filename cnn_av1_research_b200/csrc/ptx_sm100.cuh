@@ -210,6 +210,16 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16])
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its predecessor in the stream
+// is still running: everything before pdl_wait() (barrier init, TMEM allocation, descriptor prefetch, loads of CONSTANT
+// data such as weights) overlaps the predecessor's tail; pdl_wait() returns once every prerequisite grid has completed and
+// its memory is visible.  Nothing a predecessor writes (activations, device-side row counts) and nothing it still reads
+// (recycled buffers) may be touched before it.  pdl_launch_dependents() lets the NEXT kernel's CTAs be scheduled as soon
+// as SM resources free up.  Both are no-ops in a kernel launched without the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------- CTA pairs (cta_group::2)
 // Two CTAs of one cluster (same TPC) execute one tcgen05.mma of M = 256: each provides its own 128 rows of A and half
 // of B's N rows from ITS shared memory at the same offsets, and receives its 128 rows of D in ITS tensor memory.

@@ -93,8 +93,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_tc_kernel(const __grid_con
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int n = p.n_dev ? *p.n_dev : p.n;
-  const int tiles = (n + ST_BLOCKS - 1) / ST_BLOCKS;
+  pdl_launch_dependents();
 
   // ---- one-time setup: weights into swizzled smem, zero halo, barriers, TMEM
   for (int q = threadIdx.x; q < 2 * 128 * 8; q += ST_THREADS) {
@@ -123,6 +122,9 @@ __global__ void __launch_bounds__(ST_THREADS, 1) stem_tc_kernel(const __grid_con
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();      // frames / gather list / row count of the previous kernels are visible from here on; the output buffer is free
+  const int n = p.n_dev ? *p.n_dev : p.n;
+  const int tiles = (n + ST_BLOCKS - 1) / ST_BLOCKS;
 
   if (warp < ST_PRODUCERS / 32) {
     // ------------------------------------------------------------ producers: gather + im2col

@@ -38,9 +38,13 @@ def _h16(a):
     return a.astype(np.float16).astype(np.float32)
 
 
-def run(blob: bytes, images: np.ndarray) -> np.ndarray:
-    """images: float32 [n,1,b,b] (b = the blob's block size) -> logits float32 [n, n_out] as the device program computes them."""
+def run(blob: bytes, images: np.ndarray, products=None) -> np.ndarray:
+    """images: float32 [n,1,b,b] (b = the blob's block size) -> logits float32 [n, n_out] as the device program computes them.
+
+    `products` (precision studies only, tools/precision_study.py): {op index: "hh" | "x_hi" | "w_hi"} overrides the three
+    products of a split-precision op - "hh": x_hi.w_hi only, "x_hi": x_hi.(w_hi + w_lo), "w_hi": (x_hi + x_lo).w_hi."""
     P = parse(blob)
+    products = products or {}
     n = images.shape[0]
     bufs = [np.zeros((n, c), dtype=np.float32) for c in P["cols"]]
     row_scale = np.ones(n, dtype=np.float32)
@@ -55,8 +59,9 @@ def run(blob: bytes, images: np.ndarray) -> np.ndarray:
     def load(hi_id, lo_id):
         return bufs[hi_id] + (bufs[lo_id] if lo_id >= 0 else 0.0)
 
-    for op in P["ops"]:
+    for op_index, op in enumerate(P["ops"]):
         t = op["type"]
+        pm = products.get(op_index, "all")
         if t == 0:  # stem
             wp = _arr(blob, op["w_off"], np.float16, 2 * 128 * 64).reshape(2, 128, 64).astype(np.float32)
             w = ((wp[0, :64] + wp[1, :64]) * np.float32(op["f0"])).reshape(64, 8, 8)[:, :7, :7].reshape(64, 1, 7, 7)   # K = ky*8 + kx
@@ -84,8 +89,10 @@ def run(blob: bytes, images: np.ndarray) -> np.ndarray:
                         a_hi, a_lo = a_tile(e_i), a_tile(e_i + 1)
                         w_hi, w_lo = w[op["kb_w"][e_i]], w[op["kb_w"][e_i + 1]]
                         out += a_hi @ w_hi.T
-                        out += a_hi @ w_lo.T
-                        out += a_lo @ w_hi.T
+                        if pm in ("all", "x_hi"):
+                            out += a_hi @ w_lo.T
+                        if pm in ("all", "w_hi"):
+                            out += a_lo @ w_hi.T
             acc *= (row_scale[:, None] if op["use_row_scale"] & 1 else 1.0) * np.float32(op["f0"])
             if op["bias_off"]:
                 acc += _arr(blob, op["bias_off"], np.float32, nt * bn)[None, :]
@@ -136,8 +143,9 @@ def run(blob: bytes, images: np.ndarray) -> np.ndarray:
                             iy, ix = oy + ky - 1, ox + kx - 1
                             if 0 <= iy < 4 and 0 <= ix < 4:
                                 acc[:, oy, ox] += x_hi[:, iy, ix] @ w[0, ky, 2 - kx].T
-                                if planes == 2:
+                                if planes == 2 and pm in ("all", "x_hi"):
                                     acc[:, oy, ox] += x_hi[:, iy, ix] @ w[1, ky, 2 - kx].T
+                                if planes == 2 and pm in ("all", "w_hi"):
                                     acc[:, oy, ox] += x_lo[:, iy, ix] @ w[0, ky, 2 - kx].T
             acc = acc.reshape(n, 1024) * np.float32(op["f0"]) + _arr(blob, op["bias_off"], np.float32, 1024)[None, :]
             if op["epi"] == 2:
