@@ -2,6 +2,7 @@
 // declared in include/av1p.h.  All device work is hand-written sm_100a code from the .cuh files in
 // this directory; there is deliberately no CPU or library fallback - without a Blackwell device
 // every entry point fails with AV1P_ENODEV / AV1P_ECUDA.
+#include <climits>
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <nvtx3/nvToolsExt.h>
@@ -22,6 +23,7 @@
 #include "fc_tcgen05.cuh"
 #include "conv_res_tcgen05.cuh"
 #include "stem_tc.cuh"
+#include "stem_tma.cuh"
 #include "gen_kernels.cuh"
 
 using namespace av1p;
@@ -60,6 +62,8 @@ struct DeviceCtx {
                                   // two cascades on two streams, each on half of the SMs, run side by side instead of back to back)
   EncodeTiledFn encode = nullptr;
   bool fc_pair = true;            // FC layers on CTA pairs (tcgen05 cta_group::2); AV1P_FC_PAIR=0 selects the single-CTA kernel
+  bool stem_tma = true;           // frame input: TMA-staged stem (stem_tma.cuh) when the frame geometry allows a tensor map;
+                                  // AV1P_STEM_TMA=0 keeps the per-thread gather kernel (stem_tc.cuh, INT_PIX)
   bool pdl = true;                // programmatic dependent launch between the kernels of an op program (AV1P_PDL=0: plain stream order)
   bool fc_resid_epi = false;      // AV1P_FC_RESID_EPI=1: residual FC layers add the identity branch in the epilogue (aux ring)
                                   // instead of on the tensor core (FC_W_IDENT schedule entries).  Measured slower (layer2.1.conv2
@@ -115,6 +119,8 @@ int ensure_ctx() {
   }
   CUDA_TRY(cudaFuncSetAttribute(stem_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(stem_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(stem_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_SMEM_BYTES));
+  if (const char* e = getenv("AV1P_STEM_TMA")) c.stem_tma = atoi(e) != 0;
   CUDA_TRY(cudaFuncSetAttribute(extract_blocks_tma_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, EX_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(extract_blocks_tma_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, EX_SMEM_BYTES));
   CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&c.watchdog_host), 2 * sizeof(int), cudaHostAllocMapped));
@@ -465,6 +471,8 @@ struct PlannedOp {
   StemParams stem;      // AV1P_OP_STEM
   const __half* stem_w_int = nullptr;   // integer-pixel weight set (frames input) and its scale
   float stem_scale_int = 0.f;
+  const __half* stem_w_raw = nullptr;   // raw-word weight set of the TMA-staged frame kernel (stem_tma.cuh) and its scale
+  float stem_scale_raw = 0.f;
   const __half* src = nullptr;   // SAM / FGVC
   const __half* src_lo = nullptr;
   __half* dst = nullptr;         // SE
@@ -494,10 +502,51 @@ ActLayout make_act_layout(const av1p_model* const* models, int n_models, int cap
   L.cols.assign(nb, 0);
   for (int i = 0; i < n_models; ++i)
     for (size_t b = 0; b < models[i]->buf_cols.size(); ++b) L.cols[b] = std::max(L.cols[b], models[i]->buf_cols[b]);
+  // Buffers whose live ranges (first .. last op that touches them) never overlap in any of the models share memory: the
+  // three 1024-column layer1 buffers are dead once layer2 runs, so the 512 / 256-column buffers of layers 2..4 live inside
+  // them (21.8 -> ~13 KB per block row).  Two buffers touched by the same op interfere by construction (inclusive
+  // ranges), so no kernel ever reads and writes one piece of memory.  AV1P_ALIAS_BUFFERS=0 gives every buffer its own memory.
+  std::vector<size_t> size(nb);
+  for (size_t b = 0; b < nb; ++b) size[b] = align_up(size_t(L.cap) * L.cols[b] * 2, 1024);
+  std::vector<std::vector<char>> clash(nb, std::vector<char>(nb, 0));
+  const char* alias_env = getenv("AV1P_ALIAS_BUFFERS");
+  const bool alias = !(alias_env && atoi(alias_env) == 0);
+  for (int i = 0; i < n_models; ++i) {
+    std::vector<int> lo(nb, INT_MAX), hi(nb, -1);
+    int k = 0;
+    for (const Av1pBlobOp& op : models[i]->ops) {
+      const int ids[8] = {op.src[0], op.src[1], op.src[2], op.src[3], op.aux, op.aux_lo, op.out, op.out_lo};
+      for (int id : ids)
+        if (id >= 0 && size_t(id) < nb) {
+          lo[id] = std::min(lo[id], k);
+          hi[id] = std::max(hi[id], k);
+        }
+      ++k;
+    }
+    for (size_t a = 0; a < nb; ++a)
+      for (size_t b = 0; b < nb; ++b)
+        if (a != b && hi[a] >= 0 && hi[b] >= 0 && lo[a] <= hi[b] && lo[b] <= hi[a]) clash[a][b] = 1;
+  }
+  std::vector<size_t> order(nb);
+  for (size_t b = 0; b < nb; ++b) order[b] = b;
+  std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return size[a] > size[b]; });
+  L.off.assign(nb, 0);
+  std::vector<char> placed(nb, 0);
   size_t o = 0;
-  for (size_t b = 0; b < nb; ++b) {
-    L.off.push_back(o);
-    o += align_up(size_t(L.cap) * L.cols[b] * 2, 1024);
+  for (size_t b : order) {
+    // lowest offset at which [off, off + size) avoids every placed buffer this one clashes with
+    size_t off = 0;
+    for (bool moved = true; moved;) {
+      moved = false;
+      for (size_t a = 0; a < nb; ++a)
+        if (placed[a] && (!alias || clash[a][b]) && off < L.off[a] + size[a] && L.off[a] < off + size[b]) {
+          off = L.off[a] + size[a];
+          moved = true;
+        }
+    }
+    L.off[b] = off;
+    placed[b] = 1;
+    o = std::max(o, off + size[b]);
   }
   L.row_scale_off = o;
   L.sam_part_off = o + align_up(size_t(L.cap) * 4, 1024);
@@ -540,6 +589,9 @@ int plan_stage(const av1p_model* m, const ActLayout& L, uint8_t* act_base, av1p_
         P.stem.acc_scale = op.f0;
         P.stem_w_int = P.stem.w ? P.stem.w + 2 * 128 * 64 : nullptr;
         P.stem_scale_int = op.f1;
+        P.stem_w_raw = P.stem.w ? P.stem.w + 4 * 128 * 64 : nullptr;
+        P.stem_scale_raw = ldexpf(1.0f, op.tail_n);
+        if (op.tail_n < -16 || op.tail_n > 24) return fail(AV1P_EINVAL, "stem op: raw weight-set exponent %d out of range", op.tail_n);
         if (!(op.f1 > 0.f)) return fail(AV1P_EINVAL, "stem op without the integer-pixel weight set");
         P.stem.err_flag = g_ctx.watchdog_dev;
         P.stem.b = reinterpret_cast<const float*>(at(op.bias_off));
@@ -755,6 +807,7 @@ int convert_input(const av1p_input* in, StemInput* si, int block = 16) {
     si->width = in->width;
     si->height = in->height;
     si->pitch = in->pitch;
+    si->n_frames = std::max(in->n_frames, 1);
     si->blocks_x = ceil_div(in->width, block);
     si->blocks_per_frame = si->blocks_x * ceil_div(in->height, block);
     si->inv_bx = ~0ULL / (unsigned long long)si->blocks_x + 1ULL;              // unused when the divisor is 1
@@ -788,7 +841,24 @@ int run_stage(av1p_stage* s, const StemInput& si, const int32_t* idx, const int3
         sp.range_flag = s->range_flag;
         const int grid = std::min(ceil_div(n, ST_BLOCKS), g_ctx.grid_sms);
         ProfScope ps(PROF_STEM, st);
-        if (si.kind == 0) {
+        // frames whose geometry a tensor map can describe (16-byte aligned base, row and frame strides): TMA-staged kernel
+        if (si.kind == 0 && g_ctx.stem_tma && (reinterpret_cast<uintptr_t>(si.frames) & 15u) == 0 && si.pitch % 8 == 0 &&
+            (si.n_frames == 1 || si.frame_stride % 8 == 0)) {
+          StemTmaParams tp;
+          tp.s = sp;
+          tp.s.w = P.stem_w_raw;
+          tp.s.acc_scale = P.stem_scale_raw;
+          cuuint64_t dims[3] = {cuuint64_t(si.width), cuuint64_t(si.height), cuuint64_t(si.n_frames)};
+          cuuint64_t strides[2] = {cuuint64_t(si.pitch) * 2,
+                                   cuuint64_t(si.n_frames == 1 ? (long long)si.pitch * si.height : si.frame_stride) * 2};
+          cuuint32_t box[3] = {16, 16, 1};
+          cuuint32_t estr[3] = {1, 1, 1};
+          CUresult r = g_ctx.encode(&tp.map, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, const_cast<uint16_t*>(si.frames), dims, strides, box, estr,
+                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+          if (r != CUDA_SUCCESS) return fail(AV1P_ECUDA, "cuTensorMapEncodeTiled (stem frames %dx%dx%d) failed: %d", si.width, si.height, si.n_frames, int(r));
+          CUDA_TRY(launch_op(stem_tma_kernel, unsigned(grid), SM_THREADS, SM_SMEM_BYTES, st, 1, tp));
+        } else if (si.kind == 0) {
           // frames: integer pixel plane + the / 1023 weight set (see stem_tc.cuh, INT_PIX)
           sp.w = P.stem_w_int;
           sp.acc_scale = P.stem_scale_int;

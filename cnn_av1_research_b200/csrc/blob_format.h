@@ -8,14 +8,15 @@
 #include <stdint.h>
 
 #define AV1P_BLOB_MAGIC 0x50315641u   /* "AV1P" */
-#define AV1P_BLOB_VERSION 11u
+#define AV1P_BLOB_VERSION 12u
 #define AV1P_BLOB_MAX_NT 8
 #define AV1P_BLOB_MAX_KB 128
 
 enum Av1pOpType : int32_t {
   AV1P_OP_STEM = 0,       // gather + /1023 + conv1/bn/relu/maxpool -> out buffer (1024 cols); w = fp16 [4][128][64]: planes 0,1 =
                           // hi/lo weights for float blocks (f0 = acc_scale), planes 2,3 = hi/lo of w / 1023 for integer
-                          // frame samples (f1 = acc_scale)
+                          // frame samples (f1 = acc_scale), planes 4,5 = hi/lo of w / 1023 * 2^s for raw uint16 words read
+                          // as fp16 (sample * 2^-24), K = ky * 8 + kx + 1 (stem_tma.cuh; tail_n = 24 - s: acc_scale = 2^tail_n)
   AV1P_OP_FC = 1,         // block-Toeplitz linear layer on tensor cores
   AV1P_OP_SAM = 2,        // spatial-attention scalar of `src0` (512 cols) -> row_scale; tail_n = 1: from the partials of the
                           // preceding FC op (use_row_scale bit 2) instead of a pass over src0

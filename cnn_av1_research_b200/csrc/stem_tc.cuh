@@ -51,6 +51,7 @@ struct StemInput {
   const uint16_t* frames;
   long long frame_stride;   // elements between consecutive frames (Y + U + V)
   int width, height, pitch; // luma geometry, pitch in elements
+  int n_frames;
   int blocks_x, blocks_per_frame;
   unsigned long long inv_bx, inv_bpf;   // floor(2^64 / d) + 1: __umul64hi(g, inv) == g / d for every 32-bit g (d > 1)
   const float* images;

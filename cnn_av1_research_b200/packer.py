@@ -27,7 +27,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import numpy as np
 
 BLOB_MAGIC = 0x50315641
-BLOB_VERSION = 11
+BLOB_VERSION = 12
 MAX_NT = 8
 MAX_KB = 128
 MAX_KB_PLANNED = 192      # FC_MAX_KB of the kernel: blob entries + the residual entries av1p.cu adds at plan time
@@ -424,11 +424,23 @@ def backbone_ops(sd, precision: str = "fp16x3", prefix: str = "backbone.", layer
     wi = wk / scale * scale_i / 1023.0
     wi_hi = wi.astype(np.float16)
     wi_lo = (wi - wi_hi.astype(np.float64)).astype(np.float16)
+    # third set for the TMA-staged frame kernel (csrc/stem_tma.cuh): the operand is the RAW uint16 word read as fp16, i.e.
+    # sample * 2^-24, so the set is w / 1023 * 2^s_raw (no upper clip on s_raw: the 2^-24 of the operand is undone by
+    # acc_scale = 2^(24 - s_raw), stored as the exponent in tail_n), and the kernel row is shifted by one tap: K = ky * 8 +
+    # kx + 1 (the chunk of conv column px starts at the even sample 2 px - 4, so that it is four aligned words of the tile)
+    s_raw = int(np.floor(np.log2(8192.0 / (np.abs(w).max() / 1023.0))))
+    assert 0 < s_raw <= 40
+    wrow_r = np.zeros((64, 8, 8), dtype=np.float64)
+    wrow_r[:, :7, 1:8] = w[:, 0] / 1023.0 * 2.0 ** s_raw
+    wr = np.concatenate([wrow_r.reshape(64, 64)] * 2, axis=0)
+    wr_hi = wr.astype(np.float16)
+    wr_lo = (wr - wr_hi.astype(np.float64)).astype(np.float16)
     if precision != "fp16x3":
         w_lo = np.zeros_like(w_lo)
         wi_lo = np.zeros_like(wi_lo)
-    ops.append(_Op(OP_STEM, out=_hi("B0"), out_lo=_lo("B0", precision), w=np.stack([w_hi, w_lo, wi_hi, wi_lo]),
-                   bias=b.astype(np.float32), f0=1.0 / scale, f1=1.0 / scale_i, name="stem"))
+        wr_lo = np.zeros_like(wr_lo)
+    ops.append(_Op(OP_STEM, out=_hi("B0"), out_lo=_lo("B0", precision), w=np.stack([w_hi, w_lo, wi_hi, wi_lo, wr_hi, wr_lo]),
+                   bias=b.astype(np.float32), f0=1.0 / scale, f1=1.0 / scale_i, tail_n=24 - s_raw, name="stem"))
 
     def conv_bn(unit: str, conv: str, bn: str, grid: int, stride: int):
         wf, bf = fold_bn(_np64(sd[f"{unit}.{conv}.weight"]), None, sd, f"{unit}.{bn}")

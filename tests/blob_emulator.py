@@ -17,7 +17,7 @@ OP_BYTES = struct.calcsize(OP_FMT)
 
 def parse(blob: bytes):
     magic, version, kind, n_ops, n_bufs, n_out, prec, _, ops_off, bufs_off, total, _r2 = struct.unpack_from("<8I4Q", blob, 0)
-    assert magic == 0x50315641 and version == 11 and total == len(blob)
+    assert magic == 0x50315641 and version == 12 and total == len(blob)
     block = _ or 16
     cols = struct.unpack_from(f"<{n_bufs}I", blob, bufs_off)
     ops = []
