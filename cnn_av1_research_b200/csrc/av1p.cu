@@ -119,7 +119,8 @@ int ensure_ctx() {
   }
   CUDA_TRY(cudaFuncSetAttribute(stem_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(stem_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM_BYTES));
-  CUDA_TRY(cudaFuncSetAttribute(stem_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_SMEM_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(stem_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_SMEM_BYTES));
+  CUDA_TRY(cudaFuncSetAttribute(stem_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_SMEM_BYTES));
   if (const char* e = getenv("AV1P_STEM_TMA")) c.stem_tma = atoi(e) != 0;
   CUDA_TRY(cudaFuncSetAttribute(extract_blocks_tma_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, EX_SMEM_BYTES));
   CUDA_TRY(cudaFuncSetAttribute(extract_blocks_tma_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, EX_SMEM_BYTES));
@@ -848,16 +849,27 @@ int run_stage(av1p_stage* s, const StemInput& si, const int32_t* idx, const int3
           tp.s = sp;
           tp.s.w = P.stem_w_raw;
           tp.s.acc_scale = P.stem_scale_raw;
+          {
+            const char* dbg = getenv("AV1P_STEM_DEBUG");
+            tp.debug = dbg ? atoi(dbg) : 0;
+          }
           cuuint64_t dims[3] = {cuuint64_t(si.width), cuuint64_t(si.height), cuuint64_t(si.n_frames)};
           cuuint64_t strides[2] = {cuuint64_t(si.pitch) * 2,
                                    cuuint64_t(si.n_frames == 1 ? (long long)si.pitch * si.height : si.frame_stride) * 2};
-          cuuint32_t box[3] = {16, 16, 1};
+          // unrouted input whose block rows hold a multiple of four blocks: one 64 x 16 box per tile (see stem_tma.cuh, WIDE)
+          // (opt-in, AV1P_STEM_WIDE=1: fewer and larger TMA requests, but its swizzled source addressing costs the builders more
+          // instructions - same box, 518 k rows: 1061 / 1106 us vs 1051 / 1008 us for per-block boxes, 1180 / 1158 us for the
+          // per-thread gather kernel)
+          const char* wide_env = getenv("AV1P_STEM_WIDE");
+          const bool wide = idx == nullptr && si.blocks_x % ST_BLOCKS == 0 && wide_env && atoi(wide_env) != 0;
+          cuuint32_t box[3] = {wide ? 64u : 16u, 16, 1};
           cuuint32_t estr[3] = {1, 1, 1};
           CUresult r = g_ctx.encode(&tp.map, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, const_cast<uint16_t*>(si.frames), dims, strides, box, estr,
-                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                                    CU_TENSOR_MAP_INTERLEAVE_NONE, wide ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
           if (r != CUDA_SUCCESS) return fail(AV1P_ECUDA, "cuTensorMapEncodeTiled (stem frames %dx%dx%d) failed: %d", si.width, si.height, si.n_frames, int(r));
-          CUDA_TRY(launch_op(stem_tma_kernel, unsigned(grid), SM_THREADS, SM_SMEM_BYTES, st, 1, tp));
+          if (wide) CUDA_TRY(launch_op(stem_tma_kernel<true>, unsigned(grid), SM_THREADS, SM_SMEM_BYTES, st, 1, tp));
+          else CUDA_TRY(launch_op(stem_tma_kernel<false>, unsigned(grid), SM_THREADS, SM_SMEM_BYTES, st, 1, tp));
         } else if (si.kind == 0) {
           // frames: integer pixel plane + the / 1023 weight set (see stem_tc.cuh, INT_PIX)
           sp.w = P.stem_w_int;

@@ -7,9 +7,10 @@
 // No conversion: the bit pattern of a 10-bit sample v, read as fp16, IS the number v * 2^-24 (fp16 subnormals for v < 1024,
 // the first normal binade for 1024..2047 - both with ulp 2^-24; tcgen05.mma does not flush subnormal operands,
 // tests/test_gpu_fc_kernel.py).  So the raw uint16 words are a valid fp16 operand plane and the factor 2^24 / 1023 lives in
-// the weights ("raw" weight set of the stem op: w / 1023 * 2^s, hi + lo planes, acc_scale = 2^(24 - s)).  A sample above
-// 2048 is outside the linear range (and outside the 10-bit format, 005:198-204): the builders check the words they copy and
-// raise the plan's range flag, exactly like the integer-pixel kernel does.
+// the weights ("raw" weight set of the stem op: w / 1023 * 2^s, hi + lo planes, acc_scale = 2^(24 - s)).  A sample of
+// 2048 or more is outside the linear range (and outside the 10-bit format, 005:198-204): the builders test the words they
+// copy and convert such samples explicitly (fp16(v) * 2^-24, i.e. the integer-pixel kernel's 11-bit rounding), raising
+// the plan's range flag above 2048 exactly like that kernel does.
 //
 // K layout: k = ky * 8 + kxx, kxx = kx + 1 (kxx = 0 and ky = 7 carry zero weights), i.e. the 16-byte K chunk `ky` of conv
 // position (py, px) is the eight consecutive samples x = 2 px - 4 .. 2 px + 3 of row y = 2 py + ky - 3 of the block: four
@@ -38,10 +39,50 @@ static_assert((2 * SM_RAW_STAGES + 2 * SM_OP_STAGES + 4) * 8 + 4 <= 256, "barrie
 static_assert(SM_SMEM_BYTES <= 232448, "stem_tma shared memory exceeds the 227 KB opt-in limit");
 
 struct StemTmaParams {
-  CUtensorMap map;          // frames as uint16 [n_frames][height][width] (strides: frame_stride, pitch), box {16, 16, 1}, no swizzle
+  CUtensorMap map;          // frames as uint16 [n_frames][height][width] (strides: frame_stride, pitch).  WIDE = false: box
+                            // {16, 16, 1} (one block), no swizzle; WIDE = true: box {64, 16, 1} (the four horizontally adjacent
+                            // blocks of a tile, 128-byte rows), SWIZZLE_128B
   StemParams s;             // s.in.kind == 0; s.w = the raw weight set [2][128][64]; s.acc_scale = 2^(24 - s)
+  int debug;                // development switch (AV1P_STEM_DEBUG): 1 skip the MMAs, 2 skip the epilogue's math and stores,
+                            // 4 skip the im2col copy, 8 skip the TMA loads - isolates what paces the kernel
 };
 
+// Slow path of a builder thread (kept out of line so that none of it is if-converted into the copy loop): re-reads the
+// eight chunks the thread has just stored, converts every sample >= 2048 like the integer-pixel kernel does - fp16(v),
+// i.e. rounded to 11 bits, times the operand's 2^-24 (exponent field - 24; fp16(v) >= 2^11 keeps the result normal) - and
+// zeroes the chunks of blocks past the end of the list.  Returns non-zero when a sample ABOVE 2048 was met (range flag).
+__device__ __noinline__ uint32_t stem_tma_fix_tile(uint8_t* dst, int n_blk) {
+  uint32_t bad = 0u;
+  for (int i = 0; i < 8; ++i) {
+    const int b = i >> 1, h = i & 1;
+    uint4* slot = reinterpret_cast<uint4*>(dst + (b * 64 + h * 32) * 128);
+    uint4 v = *slot;
+    uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    for (int m = 0; m < 4; ++m) {
+      if (b >= n_blk) {
+        w[m] = 0u;
+        continue;
+      }
+      bad |= __vcmpgtu2(w[m], 0x08000800u);
+      uint32_t hw[2] = {w[m] & 0xFFFFu, w[m] >> 16};
+      for (int j = 0; j < 2; ++j)
+        if (hw[j] >= 2048u) {
+          const uint32_t bits = __half_as_ushort(__ushort2half_rn(static_cast<unsigned short>(hw[j])));
+          hw[j] = bits >= 0x7C00u ? 0x7C00u : bits - 0x6000u;
+        }
+      w[m] = hw[0] | (hw[1] << 16);
+    }
+    *slot = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+  return bad;
+}
+
+// WIDE (opt-in): unrouted input (no gather list) whose block rows hold a multiple of four blocks - the four blocks of a tile
+// are neighbours in the frame, so ONE box of 16 rows x 128 bytes fetches them (a 16-sample box row is a 32-byte request;
+// with everything but the loads switched off the per-block boxes take 350 us for 518 k blocks, the wide boxes 221 us).  The
+// loads are not what paces the kernel though, and the swizzled source addressing costs the builders two more instructions
+// per word: measured equal or slower than the per-block variant, which is the default.
+template <bool WIDE>
 __global__ void __launch_bounds__(SM_THREADS, 1) stem_tma_kernel(const __grid_constant__ StemTmaParams q) {
   const StemParams& p = q.s;
   extern __shared__ uint8_t sm_smem_raw[];
@@ -99,17 +140,41 @@ __global__ void __launch_bounds__(SM_THREADS, 1) stem_tma_kernel(const __grid_co
   const int tiles = (n + ST_BLOCKS - 1) / ST_BLOCKS;
 
   if (warp == 0) {
-    // ------------------------------------------------------------ TMA issuer: lanes 0..3 fetch one block each
+    // ------------------------------------------------------------ TMA issuer: lanes 0..3 fetch one block each (WIDE: lane 0 all four)
     int rs = 0;
     uint32_t rphase = 0;
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
       mbar_wait(&raw_empty[rs], rphase ^ 1u, p.err_flag, 100 + rs);
+      if constexpr (WIDE) {
+        if (lane == 0) {
+          if (q.debug & 8) {
+            mbar_arrive(&raw_full[rs]);
+          } else {
+            const unsigned ug = unsigned(tile * ST_BLOCKS);
+            const int f = int(__umul64hi((unsigned long long)ug, p.in.inv_bpf));
+            const int gb = int(ug) - f * p.in.blocks_per_frame;
+            const int by = int(__umul64hi((unsigned long long)unsigned(gb), p.in.inv_bx));
+            const int bx = gb - by * p.in.blocks_x;
+            mbar_arrive_expect_tx(&raw_full[rs], uint32_t(SM_RAW_BYTES));      // bytes past the frame edge arrive as zeros and count
+            tma_load_3d(raw + rs * SM_RAW_BYTES, &q.map, &raw_full[rs], bx * 16, by * 16, f);
+          }
+        }
+        __syncwarp();
+        if (++rs == SM_RAW_STAGES) {
+          rs = 0;
+          rphase ^= 1u;
+        }
+        continue;
+      }
       const int r = tile * ST_BLOCKS + lane;
       const bool valid = lane < ST_BLOCKS && r < n;
       const unsigned n_valid = __popc(__ballot_sync(0xFFFFFFFFu, valid));
-      if (lane == 0) mbar_arrive_expect_tx(&raw_full[rs], 512u * n_valid);
+      if (lane == 0) {
+        if (q.debug & 8) mbar_arrive(&raw_full[rs]);
+        else mbar_arrive_expect_tx(&raw_full[rs], 512u * n_valid);
+      }
       __syncwarp();
-      if (valid) {
+      if (valid && !(q.debug & 8)) {
         const int g = p.idx ? __ldg(p.idx + r) : r;
         const unsigned ug = unsigned(g);
         const int f = p.in.blocks_per_frame == 1 ? int(ug) : int(__umul64hi((unsigned long long)ug, p.in.inv_bpf));
@@ -137,10 +202,12 @@ __global__ void __launch_bounds__(SM_THREADS, 1) stem_tma_kernel(const __grid_co
       if (elect_one_sync()) {
         const uint32_t d_tmem = tmem_base + uint32_t(acc * ST_N);
         const uint32_t b_lo = umma_desc_lo_sw128(smem_u32(ops + stage * ST_P_BYTES));
+        if (!(q.debug & 1)) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_f16_ss_lo(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, k > 0 ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) umma_f16_ss_lo(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, k > 0 ? 1u : 0u);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_f16_ss_lo(d_tmem, a_lo + 2 * k, b_lo + 2 * k, idesc, 1u);
+          for (int k = 0; k < 4; ++k) umma_f16_ss_lo(d_tmem, a_lo + 2 * k, b_lo + 2 * k, idesc, 1u);
+        }
         umma_commit(&op_empty[stage]);
         umma_commit(&acc_full[acc]);
       }
@@ -156,26 +223,33 @@ __global__ void __launch_bounds__(SM_THREADS, 1) stem_tma_kernel(const __grid_co
     }
   } else if (warp < 2 + SM_BUILD_WARPS) {
     // ------------------------------------------------------------ builders: raw tile -> im2col operand tile
+    // A warp covers 8 conv columns x 4 kernel rows: the 16-byte chunks it stores (chunk index ky ^ px of eight consecutive
+    // operand rows) and its 32 word loads are free of bank conflicts - per-block tiles (32-byte rows): bank = 8 ky + px +
+    // const with four CONSECUTIVE kernel rows; WIDE tiles (128-byte rows, SWIZZLE_128B): the chunk index is XORed with
+    // y & 7, and four kernel rows TWO apart land in four different chunk pairs.
     const int tid = threadIdx.x - 64;                // 0..255
-    const int c = tid & 7;                           // K chunk = kernel row ky (7: zero weights)
-    const int px = (tid >> 3) & 7;                   // conv column of every row this thread writes
-    const int pyb = tid >> 6;                        // conv rows pyb and pyb + 4
-    // the chunk's four words are samples 2 px - 4 + 2 m, + 1 of the block row (m = 0..3): word px - 2 + m of the raw row
-    uint32_t woff[4], wmask[4];
-#pragma unroll
-    for (int m = 0; m < 4; ++m) {
-      const int wi = px - 2 + m;
-      wmask[m] = (wi >= 0 && wi < 8 && c < 7) ? 0xFFFFFFFFu : 0u;
-      woff[m] = uint32_t(min(max(wi, 0), 7) * 4);
-    }
-    uint32_t yoff[2], ymask[2];
+    const int wv = tid >> 5;
+    const int c = WIDE ? 2 * (lane >> 3) + (wv & 1) : (lane >> 3) + 4 * (wv & 1);   // K chunk = kernel row ky (7: zero weights)
+    const int px = lane & 7;                         // conv column of every row this thread writes (eight consecutive lanes = eight
+                                                     // columns of one kernel row: a 128-bit store phase hits eight different chunks)
+    const int pyb = wv >> 1;                         // conv rows pyb and pyb + 4
+    // the chunk's four words are samples 2 px - 4 + 2 m, + 1 of the block row (m = 0..3): word px - 2 + m of the raw row.
+    // Source of (block b, half h, word m):  per-block tiles  src + 512 b + off[h][m];
+    //                                       WIDE tiles        src + off[h][m] + ((32 b) ^ xsw[h][m])   (swizzled chunk index)
+    uint32_t off[2][4], xsw[2][4], msk[2][4];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int y = 2 * (pyb + 4 * h) + c - 3;
-      ymask[h] = (y >= 0 && y < 16) ? 0xFFFFFFFFu : 0u;
-      yoff[h] = uint32_t(min(max(y, 0), 15) * 32);
+      const int yc = min(max(y, 0), 15);
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        const int wi = px - 2 + m;
+        const int wc = min(max(wi, 0), 7);
+        msk[h][m] = (wi >= 0 && wi < 8 && c < 7 && y >= 0 && y < 16) ? 0xFFFFFFFFu : 0u;
+        off[h][m] = WIDE ? uint32_t(yc * 128 + (wc & 3) * 4) : uint32_t(yc * 32 + wc * 4);
+        xsw[h][m] = uint32_t(((wc >> 2) ^ (yc & 7)) << 4);
+      }
     }
-    const bool checker = c == 3 || c == 4;           // rows 2 py and 2 py + 1, samples 2 px .. 2 px + 3: every sample of the block
     const uint32_t dst_c = uint32_t((c ^ px) << 4);  // swizzled 16-byte chunk inside the 128-byte operand row (row & 7 == px)
     uint32_t bad = 0u;
     int rs = 0, os = 0;
@@ -185,19 +259,24 @@ __global__ void __launch_bounds__(SM_THREADS, 1) stem_tma_kernel(const __grid_co
       mbar_wait(&op_empty[os], ophase ^ 1u, p.err_flag, 300 + os);
       const uint32_t src = smem_u32(raw + rs * SM_RAW_BYTES);
       uint8_t* dst = ops + os * ST_P_BYTES + (pyb * 8 + px) * 128 + dst_c;
-      const int n_blk = min(ST_BLOCKS, n - tile * ST_BLOCKS);
+      uint32_t seen = 0u;                             // OR of every word this thread copied
+      if (!(q.debug & 4)) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int b = i >> 1, h = i & 1;
-        const uint32_t a = src + uint32_t(b * 512) + yoff[h];
-        const uint32_t live = b < n_blk ? ymask[h] : 0u;      // blocks past the end of the list were not loaded: zeros
-        uint4 v;
-        v.x = lds_u32(a + woff[0]) & wmask[0] & live;
-        v.y = lds_u32(a + woff[1]) & wmask[1] & live;
-        v.z = lds_u32(a + woff[2]) & wmask[2] & live;
-        v.w = lds_u32(a + woff[3]) & wmask[3] & live;
-        if (checker) bad |= __vcmpgtu2(v.z, 0x08000800u) | __vcmpgtu2(v.w, 0x08000800u);
-        *reinterpret_cast<uint4*>(dst + (b * 64 + h * 32) * 128) = v;
+        for (int i = 0; i < 8; ++i) {
+          const int b = i >> 1, h = i & 1;
+          uint4 v;
+          v.x = lds_u32(WIDE ? src + off[h][0] + (uint32_t(b * 32) ^ xsw[h][0]) : src + uint32_t(b * 512) + off[h][0]) & msk[h][0];
+          v.y = lds_u32(WIDE ? src + off[h][1] + (uint32_t(b * 32) ^ xsw[h][1]) : src + uint32_t(b * 512) + off[h][1]) & msk[h][1];
+          v.z = lds_u32(WIDE ? src + off[h][2] + (uint32_t(b * 32) ^ xsw[h][2]) : src + uint32_t(b * 512) + off[h][2]) & msk[h][2];
+          v.w = lds_u32(WIDE ? src + off[h][3] + (uint32_t(b * 32) ^ xsw[h][3]) : src + uint32_t(b * 512) + off[h][3]) & msk[h][3];
+          seen |= v.x | v.y;
+          seen |= v.z | v.w;
+          *reinterpret_cast<uint4*>(dst + (b * 64 + h * 32) * 128) = v;
+        }
+        // Rare, out of line: a sample >= 2048 (outside the range in which the bit pattern is linear - and outside the 10-bit
+        // format), or the last tile of a list that is not a multiple of four blocks (its missing blocks were not loaded).
+        const int n_blk = n - tile * ST_BLOCKS;
+        if ((seen & 0xF800F800u) || n_blk < ST_BLOCKS) bad |= stem_tma_fix_tile(dst, n_blk);
       }
       fence_proxy_async_smem();                       // generic-proxy stores -> visible to tcgen05.mma
       __syncwarp();
@@ -235,7 +314,7 @@ __global__ void __launch_bounds__(SM_THREADS, 1) stem_tma_kernel(const __grid_co
         tmem_ld_32x32(t_addr + uint32_t(blk * 64), v0);        // conv rows 0..3
         tmem_ld_32x32(t_addr + uint32_t(blk * 64 + 32), v1);   // conv rows 4..7
         tmem_ld_wait();
-        if (r < n) {
+        if (r < n && !(q.debug & 2)) {
           // max-pool the raw accumulators first (relu(s * a + b) is monotonic in a), separable 3x3 window
           float rm[8][4];
 #pragma unroll
