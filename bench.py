@@ -473,7 +473,7 @@ def main():
     if world > 1:
         # (i) every rank runs rank 0's first chunk; rank 0 checks that all gathered copies equal its own
         chk = dev_frames[:sub * fw].clone()
-        dist.broadcast(chk.view(torch.int16), 0)             # NCCL has no uint16: same bits as int16
+        dist.broadcast(chk.view(torch.uint8), 0)             # torch's NCCL group takes neither uint16 nor int16: broadcast the bytes
         lab_chk = pipe.predict_frames(chk, W4K, H4K, sub).clone()
         bufs = [torch.empty_like(lab_chk) for _ in range(world)] if rank == 0 else None
         dist.gather(lab_chk, bufs, dst=0)

@@ -65,6 +65,8 @@ struct DeviceCtx {
   bool stem_tma = true;           // frame input: TMA-staged stem (stem_tma.cuh) when the frame geometry allows a tensor map;
                                   // AV1P_STEM_TMA=0 keeps the per-thread gather kernel (stem_tc.cuh, INT_PIX)
   bool pdl = true;                // programmatic dependent launch between the kernels of an op program (AV1P_PDL=0: plain stream order)
+  bool cr_resid_epi = true;       // layer1 residual convs add the identity branch in the epilogue, in place in the staging sets
+                                  // (conv_res_tcgen05.cuh, resid_epi); AV1P_CR_RESID_EPI=0: identity MMAs through the operand ring
   bool fc_resid_epi = false;      // AV1P_FC_RESID_EPI=1: residual FC layers add the identity branch in the epilogue (aux ring)
                                   // instead of on the tensor core (FC_W_IDENT schedule entries).  Measured slower (layer2.1.conv2
                                   // 859 vs 740 us on 518 k rows): the aux ring costs two of the six operand-ring stages.
@@ -112,6 +114,7 @@ int ensure_ctx() {
   if (const char* e = getenv("AV1P_FC_PAIR")) c.fc_pair = atoi(e) != 0;
   if (const char* e = getenv("AV1P_FC_RESID_EPI")) c.fc_resid_epi = atoi(e) != 0;
   if (const char* e = getenv("AV1P_PDL")) c.pdl = atoi(e) != 0;
+  if (const char* e = getenv("AV1P_CR_RESID_EPI")) c.cr_resid_epi = atoi(e) != 0;
   {
     int n_k = 0;
     const ConvResKernel* ks = conv_res_all_kernels(&n_k);
@@ -715,6 +718,14 @@ int plan_stage(const av1p_model* m, const ActLayout& L, uint8_t* act_base, av1p_
           if (int rc = make_act_map(&f.a_map[2], buf(op.aux), 1024, L.cap, false)) return rc;
           if (int rc = make_act_map(&f.a_map[3], buf(op.aux_lo >= 0 ? op.aux_lo : op.aux), 1024, L.cap, false)) return rc;
           f.has_aux_lo = op.aux_lo >= 0 ? 1 : 0;
+          if (g_ctx.cr_resid_epi) {
+            f.resid_epi = 1;
+            f.aux = buf(op.aux);
+            f.aux_lo = buf(op.aux_lo);
+            f.aux_kb = 16;
+            if (int rc = make_act_map(&f.res_map[0], buf(op.aux), 1024, L.cap, true)) return rc;
+            if (int rc = make_act_map(&f.res_map[1], buf(op.aux_lo >= 0 ? op.aux_lo : op.aux), 1024, L.cap, true)) return rc;
+          }
         }
         if (!conv_res_build_schedule(f)) return fail(AV1P_EINVAL, "resident-conv schedule does not fit its tables");
         break;
@@ -1583,6 +1594,14 @@ extern "C" int av1p_conv_res_forward(const av1p_conv_res_desc* d, void* stream) 
     if (int rc = make_act_map(&f.a_map[2], d->aux_dev, 1024, uint64_t(d->rows), false)) return rc;
     if (int rc = make_act_map(&f.a_map[3], d->aux_lo_dev ? d->aux_lo_dev : d->aux_dev, 1024, uint64_t(d->rows), false)) return rc;
     f.has_aux_lo = d->aux_lo_dev ? 1 : 0;
+    if (g_ctx.cr_resid_epi) {
+      f.resid_epi = 1;
+      f.aux = static_cast<const __half*>(d->aux_dev);
+      f.aux_lo = static_cast<const __half*>(d->aux_lo_dev);
+      f.aux_kb = 16;
+      if (int rc = make_act_map(&f.res_map[0], d->aux_dev, 1024, uint64_t(d->rows), true)) return rc;
+      if (int rc = make_act_map(&f.res_map[1], d->aux_lo_dev ? d->aux_lo_dev : d->aux_dev, 1024, uint64_t(d->rows), true)) return rc;
+    }
   }
   if (!(1.0f / d->acc_scale >= 1.0f && 1.0f / d->acc_scale <= 32768.0f)) return fail(AV1P_EINVAL, "weight scale outside [1, 2^15]");
   f.n_rows_dev = d->n_dev;

@@ -61,16 +61,20 @@ constexpr int CR_MAX_RING = 80;
 // whole-row accumulators both rows of a half completed together and the issuer idled for two row epilogues per tile.)
 constexpr int CR_SLOTS = 8;
 __device__ __constant__ const uint8_t CR_DRAIN[16] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 12, 9, 13, 10, 14, 11, 15};
-static_assert((2 * CR_STAGES + 2 * CR_SLOTS + 4 + 1) * 8 + 4 <= 256, "barrier area");
+static_assert((2 * CR_STAGES + 2 * CR_SLOTS + 4 + 1 + 2) * 8 + 4 <= 256, "barrier area");
 
 struct ConvResParams {
   CUtensorMap a_map[4];        // x_hi, x_lo, residual hi, residual lo (tiled layout): 2-D [rows*16][64] fp16, box {64, 128}, SWIZZLE_128B
   CUtensorMap w_map;           // resident weights: 2-D [planes*9*64][64] fp16, box {64, 64}; tile (plane, ky, 2-kx)
   CUtensorMap out_map[2];      // output hi, lo (tiled layout): 2-D [rows*16][64] fp16, box {32, 128}, SWIZZLE_64B
+  CUtensorMap res_map[2];      // resid_epi: residual hi, lo with the output's box (loaded into the staging sets)
   const int* n_rows_dev;
   int n_rows;
   int split;                   // 1: hi/lo planes, three products; 0: single fp16 product
   int has_aux_lo;              // residual has a lo plane
+  int resid_epi;               // 1: the residual is added in the epilogue - the store warps TMA-load its [128 x 32] tiles into the
+                               // staging set the epilogue is about to fill (in place), instead of 16 extra ring tiles and 64
+                               // identity MMAs per half M tile (a ring tile that feeds four tiny MMAs exposes a ring round trip)
   int debug;                   // test hook only (AV1P_CR_DEBUG): 1 skip MMA issue, 2 skip staging/stores, 4 skip TMA loads, 8 skip L2 prefetch, 16 skip the epilogue
   int n_ring;
   int ring_begin[3];           // ring entries of half h: [ring_begin[h], ring_begin[h + 1])
@@ -80,7 +84,7 @@ struct ConvResParams {
   const float* bias;           // [1024]
   const float* row_scale;      // always nullptr here
   float acc_scale;
-  const __half* aux;           // unused (no gate epilogue here)
+  const __half* aux;           // resid_epi: residual planes (read directly for the partial last M tile)
   const __half* aux_lo;
   int aux_kb;
   __half* out;
@@ -255,9 +259,11 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_res_tcgen05_kernel(const _
   uint64_t* stg_full = acc_empty + CR_SLOTS;    // [2]
   uint64_t* stg_free = stg_full + 2;            // [2]
   uint64_t* w_bar = stg_free + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
+  uint64_t* stg_loaded = w_bar + 1;             // [2] in-place residual tiles
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stg_loaded + 2);
   EpiStage es;
   epi_stage_init(es, smem + CR_OFF_STAGING, stg_full, stg_free);
+  es.loaded = stg_loaded;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -277,7 +283,7 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_res_tcgen05_kernel(const _
     tma_prefetch_desc(&p.w_map);
     tma_prefetch_desc(&p.out_map[0]);
     if (p.out_lo) tma_prefetch_desc(&p.out_map[1]);
-    if (residual) {
+    if (residual || p.resid_epi) {
       tma_prefetch_desc(&p.a_map[2]);
       tma_prefetch_desc(&p.a_map[3]);
     }
@@ -292,8 +298,13 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_res_tcgen05_kernel(const _
     for (int s = 0; s < 2; ++s) {
       mbar_init(&stg_full[s], FC_EPI_WARPS / 2);
       mbar_init(&stg_free[s], 1);
+      mbar_init(&stg_loaded[s], 1);
     }
     mbar_init(w_bar, 1);
+    if (p.resid_epi) {
+      tma_prefetch_desc(&p.res_map[0]);
+      tma_prefetch_desc(&p.res_map[1]);
+    }
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -396,9 +407,20 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_res_tcgen05_kernel(const _
     for (int mt = mt0; mt < m_tiles; mt += mt_step) {
       if ((mt + 1) * FC_TILE_M > n_rows || (p.debug & 18)) continue;
 #pragma unroll 1
-      for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < 8; ++i) {
+        if (p.resid_epi && warp == FC_STORE_WARP && lane == 0) {
+          // pull the residual of the NEXT output position into L2 (two chunk periods ahead of its in-place loads)
+          const int nmt = i < 7 ? mt : mt + mt_step;
+          if ((nmt + 1) * FC_TILE_M <= n_rows) {
+            const int npos = int(CR_DRAIN[8 * half + ((i + 1) & 7)]);
+            tma_prefetch_l2_2d(&p.a_map[2], 0, (nmt * 16 + npos) * FC_TILE_M);
+            if (p.aux_lo) tma_prefetch_l2_2d(&p.a_map[3], 0, (nmt * 16 + npos) * FC_TILE_M);
+          }
+        }
         epi_store_chunks(es, g, &p.out_map[0], &p.out_map[1], p.out_lo != nullptr, int(CR_DRAIN[8 * half + i]) * 64, 64 / EPI_CHUNK, mt, 16,
-                         p.err_flag, uint32_t(warp - FC_STORE_WARP));
+                         p.err_flag, uint32_t(warp - FC_STORE_WARP), p.resid_epi ? &p.res_map[0] : nullptr,
+                         (p.resid_epi && p.aux_lo) ? &p.res_map[1] : nullptr);
+      }
     }
     epi_store_drain();
   }
@@ -416,7 +438,7 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_res_tcgen05_kernel(const _
 // plane; while an output row's last input row streams by, its residual tile of position xi follows x tile xi.
 inline bool conv_res_build_schedule(ConvResParams& f) {
   const int planes = f.split ? 2 : 1;
-  const bool residual = f.epi == FC_EPI_ADD_RELU;
+  const bool residual = f.epi == FC_EPI_ADD_RELU && !f.resid_epi;
   const int aux_planes = f.has_aux_lo ? 2 : 1;
   static const int ix_order[4] = {1, 0, 2, 3};
   int n = 0;
@@ -446,7 +468,7 @@ inline bool conv_res_build_schedule(ConvResParams& f) {
 // Kernel variant for the given shape (split precision / residual branch / residual lo plane).
 typedef void (*ConvResKernel)(const ConvResParams);
 inline ConvResKernel conv_res_kernel_for(const ConvResParams& f) {
-  const bool resid = f.epi == FC_EPI_ADD_RELU;
+  const bool resid = f.epi == FC_EPI_ADD_RELU && !f.resid_epi;      // residual on the tensor core (identity MMAs)
   if (f.split) {
     if (!resid) return conv_res_tcgen05_kernel<true, false, false>;
     return f.has_aux_lo ? conv_res_tcgen05_kernel<true, true, true> : conv_res_tcgen05_kernel<true, true, false>;

@@ -142,10 +142,13 @@ __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f,
 // a TMA store expects; chunk g of a CTA's output stream uses set g & 1.
 //   full[s] : the 8 epilogue warps of group s -> store warp s ("both tiles of set s are written and fenced")
 //   free_[s]: store warp -> epilogue warps ("the bulk stores have finished reading set s")
+//   loaded[s]: (in-place residual, conv_res kernel only) TMA transaction barrier: the store warp has loaded the RESIDUAL of the
+//              set's next chunk into the set; the epilogue adds it and overwrites it with the output (see epi_tile_store)
 struct EpiStage {
   uint8_t* staging;  // [EPI_SETS][2 planes][EPI_UNIT_BYTES]
   uint64_t* full;    // [EPI_SETS], count FC_EPI_WARPS / 2
   uint64_t* free_;   // [EPI_SETS], count 1
+  uint64_t* loaded;  // [EPI_SETS] or nullptr
   __device__ __forceinline__ uint8_t* unit(uint32_t set, int plane) const {
     return staging + (set * 2u + uint32_t(plane)) * EPI_UNIT_BYTES;
   }
@@ -154,6 +157,7 @@ __device__ __forceinline__ void epi_stage_init(EpiStage& es, uint8_t* staging, u
   es.staging = staging;
   es.full = full;
   es.free_ = free_;
+  es.loaded = nullptr;
 }
 
 // 8 consecutive fp16 of row r: 16-byte chunk `part` (0..3) of the 64-byte row
@@ -195,13 +199,24 @@ __device__ __forceinline__ uint64_t ident_desc(uint32_t ident_addr) { return umm
 // other set's progress.  (With a single store warp the hand-back of set s waited for the NEXT chunk to be staged and
 // issued - wait_group.read cannot be polled - which serialised epilogue and stores at ~1.3 us per chunk, the pace of
 // every store-heavy layer.)
+// In-place residual (res_hi != nullptr): before the epilogue may touch the set, the store warp loads the RESIDUAL tile of the
+// same chunk into it (the previous stores of this set have left shared memory - wait_group.read above - so the set is free);
+// the epilogue reads its residual values from exactly the 16-byte pieces it then overwrites with the output.
 __device__ __forceinline__ void epi_store_chunks(const EpiStage& es, uint32_t& g, const CUtensorMap* map_hi,
                                                  const CUtensorMap* map_lo, bool has_lo, int col0, int n_chunks, int mt,
-                                                 int out_kb, int* err_flag, uint32_t my_set) {
+                                                 int out_kb, int* err_flag, uint32_t my_set, const CUtensorMap* res_hi = nullptr,
+                                                 const CUtensorMap* res_lo = nullptr) {
   const bool leader = (threadIdx.x & 31) == 0;
   for (int c = 0; c < n_chunks; ++c, ++g) {
     const uint32_t set = g & 1u;
     if (set != my_set) continue;
+    if (res_hi != nullptr && leader) {
+      const int col = col0 + c * EPI_CHUNK;
+      const int trow = (mt * out_kb + (col >> 6)) * FC_TILE_M;      // the residual buffer has the output's width and layout
+      mbar_arrive_expect_tx(&es.loaded[set], res_lo ? 2u * EPI_UNIT_BYTES : uint32_t(EPI_UNIT_BYTES));
+      tma_load_2d(es.unit(set, 0), res_hi, &es.loaded[set], col & 63, trow);
+      if (res_lo) tma_load_2d(es.unit(set, 1), res_lo, &es.loaded[set], col & 63, trow);
+    }
     mbar_wait(&es.full[set], (g >> 1) & 1u, err_flag, 900 + int(set));
     if (leader) {
       const int col = col0 + c * EPI_CHUNK;
@@ -260,6 +275,8 @@ __device__ __forceinline__ void epi_tile_store(const P& p, const EpiStage& es, u
   const bool aux_on = gate || resid;
   const bool relu = p.epi == FC_EPI_RELU || p.epi == FC_EPI_ADD_RELU;
   const bool has_lo = p.out_lo != nullptr;
+  bool inplace = false;             // residual arrives in the staging set itself (conv_res kernel, resid_epi)
+  if constexpr (requires { p.resid_epi; }) inplace = p.resid_epi != 0 && p.epi == FC_EPI_ADD_RELU;
   const float rs = ((p.row_scale && row_ok) ? p.row_scale[row] : 1.0f) * p.acc_scale;
   float ars = 1.0f;                 // scale of the aux operand (FC_EPI_ADD after spatial attention)
   if constexpr (requires { p.aux_row_scale; }) ars = (p.aux_row_scale && row_ok) ? p.aux_row_scale[row] : 1.0f;
@@ -298,6 +315,25 @@ __device__ __forceinline__ void epi_tile_store(const P& p, const EpiStage& es, u
       for (int h = 0; h < 2; ++h) {
         ax[h] = stage_load8(u, r_local, sub * 2 + h);
         if (p.aux_lo) axl[h] = stage_load8(u + EPI_UNIT_BYTES, r_local, sub * 2 + h);
+      }
+    }
+    uint4 rq[2] = {zero4, zero4}, rql[2] = {zero4, zero4};      // in-place residual: this thread's 2 x 8 values (hi, lo)
+    if (inplace) {
+      if (staged) {
+        // use u = (g0 + c) >> 1 of set `grp`: its residual tile has landed (which also means the set's previous stores are done)
+        mbar_wait(&es.loaded[grp], ((g0 + uint32_t(c)) >> 1) & 1u, p.err_flag, tag + 30);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          rq[h] = stage_load8(es.unit(grp, 0), r_local, sub * 2 + h);
+          if (p.aux_lo) rql[h] = stage_load8(es.unit(grp, 1), r_local, sub * 2 + h);
+        }
+      } else if (row_ok) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const size_t o = act_off(row, col0 + c * EPI_CHUNK + sub * 16 + h * 8, p.aux_kb);
+          rq[h] = *reinterpret_cast<const uint4*>(p.aux + o);
+          if (p.aux_lo) rql[h] = *reinterpret_cast<const uint4*>(p.aux_lo + o);
+        }
       }
     }
 #pragma unroll
@@ -346,6 +382,16 @@ __device__ __forceinline__ void epi_tile_store(const P& p, const EpiStage& es, u
           if (lane == 0) mbar_arrive(&gx->empty[aset]);
         }
       }
+      if (inplace) {
+        const __half2* hh = reinterpret_cast<const __half2*>(&rq[h]);
+        const __half2* hl = reinterpret_cast<const __half2*>(&rql[h]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 a = __half22float2(hh[i]), al = __half22float2(hl[i]);
+          f[2 * i] += a.x + al.x;
+          f[2 * i + 1] += a.y + al.y;
+        }
+      }
       if (relu) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.f);
@@ -370,7 +416,7 @@ __device__ __forceinline__ void epi_tile_store(const P& p, const EpiStage& es, u
       const uint4 lq = *reinterpret_cast<const uint4*>(lo);
       if (staged) {
         // use u = (g0 + c) >> 1 of set `grp`: the first use needs no wait (parity trick), use u waits for the (u-1)-th hand-back
-        if (h == 0) mbar_wait(&es.free_[grp], (((g0 + uint32_t(c)) >> 1) & 1u) ^ 1u, p.err_flag, tag + 10);
+        if (h == 0 && !inplace) mbar_wait(&es.free_[grp], (((g0 + uint32_t(c)) >> 1) & 1u) ^ 1u, p.err_flag, tag + 10);
         stage_store8(es.unit(grp, 0), r_local, sub * 2 + h, hq);
         if (has_lo) stage_store8(es.unit(grp, 1), r_local, sub * 2 + h, lq);
         if (h == 1) {

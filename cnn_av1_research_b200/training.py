@@ -76,11 +76,14 @@ class Stage1DataParallelTrainer:
     into buckets of ~`bucket_mb` MB in REVERSE parameter order - the order backward produces gradients - and a
     post-accumulate hook launches an asynchronous all-reduce of a bucket as soon as its last gradient has arrived, so the
     exchange of the head / layer4 gradients runs over NVLink while layer3 ... conv1 are still back-propagating; only the
-    last (smallest, earliest-layer) bucket is exposed.  `bucket_mb=0` restores the single flat all-reduce after backward
-    (the round-1 behaviour, kept for A/B)."""
+    last (smallest, earliest-layer) bucket is exposed.  `bucket_mb=0` is the single flat all-reduce after backward.
+    Measured on 8 B200 (tools/bench_train.py, per-GPU batch 128, profiles/r02_train_n8*.json): 8.51 ms / step bucketed
+    (120.4 k samples/s) vs 7.22 ms flat (141.9 k samples/s) - one 45 MB all-reduce over NVSwitch takes ~0.3 ms of a 7 ms
+    step, so there is nothing to hide and the per-parameter hooks cost more than they save.  The flat exchange is therefore
+    the default; pass bucket_mb=8 for models whose gradient exchange is a larger share of the step."""
 
     def __init__(self, model, device, lr: float = 1e-3, weight_decay: float = 1e-4, alpha: float = 0.25, gamma: float = 2.5,
-                 dropout_p: float = 0.3, autocast_bf16: Optional[bool] = None, group=None, bucket_mb: float = 8.0):
+                 dropout_p: float = 0.3, autocast_bf16: Optional[bool] = None, group=None, bucket_mb: float = 0.0):
         self.model = model.to(device)
         self.device = torch.device(device)
         self.group = group

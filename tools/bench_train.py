@@ -4,8 +4,8 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P tools/bench_train.py --gpus N
 
 One process per GPU, NCCL; per-GPU batch 128 (reference default, 003:139) of synthetic labelled blocks, bf16 autocast
-forward/backward in PyTorch, the 11,345,444 fp32 gradients all-reduced in ~8 MB buckets overlapped with backward
-(--bucket-mb 0: one flat all-reduce after backward), AdamW.  Weak scaling;
+forward/backward in PyTorch, the 11,345,444 fp32 gradients all-reduced in one flat buffer after backward (default) or in
+~8 MB buckets overlapped with backward (--bucket-mb 8), AdamW.  Weak scaling;
 CUDA-event time, max over ranks.  Prints one JSON line on rank 0.
 """
 import argparse
@@ -26,7 +26,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--batch", type=int, default=128)
-    ap.add_argument("--bucket-mb", type=float, default=8.0, help="gradient bucket size; 0 = one flat all-reduce after backward")
+    ap.add_argument("--bucket-mb", type=float, default=0.0, help="gradient bucket size in MB (overlapped with backward); 0 = one flat all-reduce after backward (default: measured faster)")
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)

@@ -17,6 +17,6 @@ echo "r02_strong_n1 rc=$? $(cut -c1-200 $OUT/r02_strong_n1.json | tail -1)"
 for n in 2 4 8; do
   run $n $((29500 + n)) r02_strong_n$n bench.py --gpus $n --scaling strong --steps 10 --warmup 3 $LEAN
 done
-run 8 29611 r02_weak_n8 bench.py --gpus 8 --steps 5 --warmup 3 $LEAN
+# (the weak-scaling line at 1/2/4/8 is the driver's own SCALE run)
 run 8 29621 r02_train_n8 tools/bench_train.py --gpus 8 --steps 30 --warmup 10
 run 8 29631 r02_train_n8_flat tools/bench_train.py --gpus 8 --steps 30 --warmup 10 --bucket-mb 0
