@@ -21,10 +21,10 @@ sys.path.insert(0, ROOT)
 
 
 def short(name):
-    for k in ("conv_res_tcgen05_kernel", "fc_tcgen05_kernel", "stem_tc_kernel", "se_kernel", "sam_gate_kernel", "fgvc_tail_kernel",
-              "route_count_kernel", "route_scatter_kernel", "finalize_labels_kernel", "extract_blocks_kernel"):
+    for k in ("conv_res_tcgen05_kernel", "fc_tcgen05_kernel", "stem_tma_kernel", "stem_tc_kernel", "se_kernel", "sam_finish_kernel", "sam_gate_kernel",
+              "fgvc_tail_kernel", "route_count_kernel", "route_scatter_kernel", "finalize_labels_kernel", "extract_blocks_kernel"):
         if k in name:
-            if k in ("conv_res_tcgen05_kernel", "se_kernel", "stem_tc_kernel", "fc_tcgen05_kernel") and "<" in name:
+            if k in ("conv_res_tcgen05_kernel", "se_kernel", "stem_tc_kernel", "stem_tma_kernel", "fc_tcgen05_kernel") and "<" in name:
                 return k + name[name.index("<"):name.index(">") + 1]
             return k
     return name.split("(")[0]
