@@ -230,6 +230,18 @@ extern "C" int av1p_set_option(const char* name, int32_t value) {
     c.fc_pair = value != 0;
     return AV1P_OK;
   }
+  if (!strcmp(name, "stem_tma")) {          // read at every launch
+    c.stem_tma = value != 0;
+    return AV1P_OK;
+  }
+  if (!strcmp(name, "pdl")) {               // read at every launch
+    c.pdl = value != 0;
+    return AV1P_OK;
+  }
+  if (!strcmp(name, "cr_resid_epi")) {      // read when a stage is planned (and by av1p_conv_res_forward)
+    c.cr_resid_epi = value != 0;
+    return AV1P_OK;
+  }
   return fail(AV1P_EINVAL, "unknown option '%s'", name);
 }
 extern "C" int av1p_get_option(const char* name) {
@@ -238,6 +250,9 @@ extern "C" int av1p_get_option(const char* name) {
   if (!strcmp(name, "grid_sms")) return c.grid_sms;
   if (!strcmp(name, "sms")) return c.sms;
   if (!strcmp(name, "fc_pair")) return c.fc_pair ? 1 : 0;
+  if (!strcmp(name, "stem_tma")) return c.stem_tma ? 1 : 0;
+  if (!strcmp(name, "pdl")) return c.pdl ? 1 : 0;
+  if (!strcmp(name, "cr_resid_epi")) return c.cr_resid_epi ? 1 : 0;
   return -1;
 }
 

@@ -51,7 +51,13 @@ int av1p_debug_watchdog(void);
 /* Per-device runtime switches (the reference has no counterpart: scheduling knobs of this build).  Every device
  * ordinal has its own context, initialised on first use while that device is current (cudaSetDevice / torch.cuda.device).
  *   "grid_sms": SMs a persistent kernel's grid may occupy (even, 2 .. SM count; 0 restores the SM count);
- *   "fc_pair" : 1 = FC layers on CTA pairs (default), 0 = single-CTA kernel.
+ *   "fc_pair" : 1 = FC layers on CTA pairs (default), 0 = single-CTA kernel;
+ *   "stem_tma": 1 = frame input goes through the TMA-staged stem when a tensor map can describe the frames (default),
+ *               0 = per-thread gather stem (read at every launch);
+ *   "pdl"     : 1 = programmatic dependent launch between the kernels of a stage (default), 0 = plain stream order
+ *               (read at every launch);
+ *   "cr_resid_epi": 1 = layer1 residual convolutions add the identity branch in the epilogue (default), 0 = on the
+ *               tensor core (read when a stage / cascade is created).
  * av1p_get_option also answers "sms"; it returns -1 for an unknown name. */
 int av1p_set_option(const char* name, int32_t value);
 int av1p_get_option(const char* name);

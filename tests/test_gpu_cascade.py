@@ -298,6 +298,43 @@ def test_two_stream_chunk_schedule_matches_single_stream(cuda_device):
     assert torch.equal(got, ref), "three streams: labels differ from the single-stream pass"
 
 
+def test_launch_and_stem_variants_agree(cuda_device):
+    """The runtime switches select between implementations of the same arithmetic: the TMA-staged
+    frame stem vs the per-thread gather stem (same products, the weight sets differ by a power of two), programmatic
+    dependent launch vs plain stream order (identical kernels: bitwise), the wide-box variant of the TMA stem."""
+    from cnn_av1_research_b200.runtime import NativeModel, NativeStage
+    lib = N.lib()
+    w, h, nf = 1280, 720, 3                    # 80 blocks per block row: a multiple of four (the wide-box stem applies)
+    n = nf * (w // 16) * (h // 16)
+    words = synth.synth_frames(nf, w, h, seed=21)
+    fr = frames_tensor(words, cuda_device)
+    sd = synth.calibrated_state_dict("stage1", 0)
+    with torch.cuda.device(cuda_device):
+        stage = NativeStage(NativeModel("stage1", sd, torch.device(cuda_device)), n)
+        inp = N.frames_input(fr, w, h, nf)
+        base = stage.forward(inp, n).clone()
+        try:
+            N.check(lib.av1p_set_option(b"pdl", 0))
+            assert torch.equal(stage.forward(inp, n), base), "plain stream order must give the same bits as dependent launch"
+            N.check(lib.av1p_set_option(b"pdl", 1))
+            N.check(lib.av1p_set_option(b"stem_tma", 0))
+            gather = stage.forward(inp, n).clone()
+        finally:
+            N.check(lib.av1p_set_option(b"pdl", 1))
+            N.check(lib.av1p_set_option(b"stem_tma", 1))
+        assert lib.av1p_get_option(b"stem_tma") == 1 and lib.av1p_get_option(b"pdl") == 1
+    err = float((gather - base).abs().max())
+    print(f"TMA-staged vs gather stem: max-abs stage-1 logit difference {err:.3g}")
+    assert err <= 2e-4
+    ref = O.stage_logits("stage1", sd, O.frames_to_images(words, nf, w, h)).numpy()
+    assert np.abs(base.cpu().numpy() - ref).max() <= LOGIT_TOL["fp16x3"]
+    # a gather list (routed stages use one box per listed block): every third block in descending order, partial last tile
+    idx = torch.arange(n - 1, -1, -3, device=cuda_device, dtype=torch.int32)
+    with torch.cuda.device(cuda_device):
+        got = stage.forward(inp, int(idx.numel()), idx=idx)
+    assert np.abs(got.cpu().numpy() - ref[idx.cpu().numpy()]).max() <= LOGIT_TOL["fp16x3"]
+
+
 def test_config3_full_cascade_on_a_1080p_frame(cuda_device):
     """BASELINE configs[2]: full cascade on one 1920x1080 frame, extraction included (68 x 120 = 8,160 blocks, the last grid
     row is half padding) - every label against the CPU oracle on the same frame."""

@@ -59,6 +59,16 @@ def _split(t):
     return hi, (t - hi.double()).half()
 
 
+@pytest.fixture(params=[1, 0], ids=["resid_in_epilogue", "resid_on_tensor_core"])
+def resid_mode(request, cuda_device):
+    """Both forms of the identity branch: added in place in the epilogue's staging tiles (default) and
+    accumulated on the tensor core through the operand ring."""
+    with torch.cuda.device(cuda_device):
+        N.check(N.lib().av1p_set_option(b"cr_resid_epi", request.param))
+        yield request.param
+        N.check(N.lib().av1p_set_option(b"cr_resid_epi", 1))
+
+
 def test_single_tap_routes_every_position(cuda_device):
     """One tap at a time with identity channel mixing: the output must be the input shifted by that tap,
     zero at the border - catches any error in the tap order, the N = 128/192 merged MMAs and the accumulate flags."""
@@ -76,7 +86,7 @@ def test_single_tap_routes_every_position(cuda_device):
 
 
 @pytest.mark.parametrize("rows,epi", [(128, 1), (1000, 2), (77, 0), (148 * 128 * 2 + 5, 2)])
-def test_fp16_conv(cuda_device, rows, epi):
+def test_fp16_conv(cuda_device, rows, epi, resid_mode):
     dev = cuda_device
     g = torch.Generator(device=dev).manual_seed(rows)
     x = torch.randn((rows, 1024), device=dev, generator=g).half()
@@ -90,7 +100,7 @@ def test_fp16_conv(cuda_device, rows, epi):
 
 
 @pytest.mark.parametrize("rows,epi", [(300, 1), (4096 + 17, 2), (148 * 128 * 3 + 77, 1), (148 * 128 * 4 + 300, 2)])
-def test_split_precision_conv(cuda_device, rows, epi):
+def test_split_precision_conv(cuda_device, rows, epi, resid_mode):
     """hi/lo planes, three products: the result (hi + lo) must be fp32-grade."""
     dev = cuda_device
     g = torch.Generator(device=dev).manual_seed(rows + 1)

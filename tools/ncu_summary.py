@@ -60,7 +60,10 @@ def launches(path, out, title):
 
 
 def full(rep, out, traffic_json, rows_per_launch, title):
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    # `rep` may also be the raw page already exported on the GPU box (`ncu -i capture.ncu-rep --page raw --csv > capture.csv`):
+    # a --set full capture of 25 launches is larger than what gpurun copies back
+    raw = open(rep).read() if rep.endswith(".csv") else \
+        subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units, data = rows[0], rows[1], rows[2:]
     col = {h: i for i, h in enumerate(hdr)}
