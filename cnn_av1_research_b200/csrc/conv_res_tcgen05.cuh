@@ -75,7 +75,8 @@ struct ConvResParams {
   int resid_epi;               // 1: the residual is added in the epilogue - the store warps TMA-load its [128 x 32] tiles into the
                                // staging set the epilogue is about to fill (in place), instead of 16 extra ring tiles and 64
                                // identity MMAs per half M tile (a ring tile that feeds four tiny MMAs exposes a ring round trip)
-  int debug;                   // test hook only (AV1P_CR_DEBUG): 1 skip MMA issue, 2 skip staging/stores, 4 skip TMA loads, 8 skip L2 prefetch, 16 skip the epilogue
+  int debug;                   // test hook only (AV1P_CR_DEBUG): 1 skip MMA issue, 2 skip staging/stores, 4 skip TMA loads, 8 skip L2 prefetch, 16 skip the epilogue,
+                               // 32 skip the L2 prefetch of the in-place residual tiles
   int n_ring;
   int ring_begin[3];           // ring entries of half h: [ring_begin[h], ring_begin[h + 1])
   uint8_t ring[CR_MAX_RING];
@@ -408,7 +409,7 @@ __global__ void __launch_bounds__(CR_THREADS, 1) conv_res_tcgen05_kernel(const _
       if ((mt + 1) * FC_TILE_M > n_rows || (p.debug & 18)) continue;
 #pragma unroll 1
       for (int i = 0; i < 8; ++i) {
-        if (p.resid_epi && warp == FC_STORE_WARP && lane == 0) {
+        if (p.resid_epi && !(p.debug & 32) && warp == FC_STORE_WARP && lane == 0) {
           // pull the residual of the NEXT output position into L2 (two chunk periods ahead of its in-place loads)
           const int nmt = i < 7 ? mt : mt + mt_step;
           if ((nmt + 1) * FC_TILE_M <= n_rows) {
