@@ -65,7 +65,7 @@ struct DeviceCtx {
   bool stem_tma = true;           // frame input: TMA-staged stem (stem_tma.cuh) when the frame geometry allows a tensor map;
                                   // AV1P_STEM_TMA=0 keeps the per-thread gather kernel (stem_tc.cuh, INT_PIX)
   bool pdl = true;                // programmatic dependent launch between the kernels of an op program (AV1P_PDL=0: plain stream order)
-  bool cr_resid_epi = true;       // layer1 residual convs add the identity branch in the epilogue, in place in the staging sets
+  int cr_resid_epi = 1;           // layer1 residual convs add the identity branch in the epilogue, in place in the staging sets
                                   // (conv_res_tcgen05.cuh, resid_epi); AV1P_CR_RESID_EPI=0: identity MMAs through the operand ring
   bool fc_resid_epi = false;      // AV1P_FC_RESID_EPI=1: residual FC layers add the identity branch in the epilogue (aux ring)
                                   // instead of on the tensor core (FC_W_IDENT schedule entries).  Measured slower (layer2.1.conv2
@@ -114,7 +114,7 @@ int ensure_ctx() {
   if (const char* e = getenv("AV1P_FC_PAIR")) c.fc_pair = atoi(e) != 0;
   if (const char* e = getenv("AV1P_FC_RESID_EPI")) c.fc_resid_epi = atoi(e) != 0;
   if (const char* e = getenv("AV1P_PDL")) c.pdl = atoi(e) != 0;
-  if (const char* e = getenv("AV1P_CR_RESID_EPI")) c.cr_resid_epi = atoi(e) != 0;
+  if (const char* e = getenv("AV1P_CR_RESID_EPI")) c.cr_resid_epi = std::max(0, std::min(2, atoi(e)));
   {
     int n_k = 0;
     const ConvResKernel* ks = conv_res_all_kernels(&n_k);
@@ -239,7 +239,8 @@ extern "C" int av1p_set_option(const char* name, int32_t value) {
     return AV1P_OK;
   }
   if (!strcmp(name, "cr_resid_epi")) {      // read when a stage is planned (and by av1p_conv_res_forward)
-    c.cr_resid_epi = value != 0;
+    if (value < 0 || value > 2) return fail(AV1P_EINVAL, "cr_resid_epi %d outside 0..2", value);
+    c.cr_resid_epi = value;
     return AV1P_OK;
   }
   return fail(AV1P_EINVAL, "unknown option '%s'", name);
@@ -252,7 +253,7 @@ extern "C" int av1p_get_option(const char* name) {
   if (!strcmp(name, "fc_pair")) return c.fc_pair ? 1 : 0;
   if (!strcmp(name, "stem_tma")) return c.stem_tma ? 1 : 0;
   if (!strcmp(name, "pdl")) return c.pdl ? 1 : 0;
-  if (!strcmp(name, "cr_resid_epi")) return c.cr_resid_epi ? 1 : 0;
+  if (!strcmp(name, "cr_resid_epi")) return c.cr_resid_epi;
   return -1;
 }
 
@@ -734,7 +735,7 @@ int plan_stage(const av1p_model* m, const ActLayout& L, uint8_t* act_base, av1p_
           if (int rc = make_act_map(&f.a_map[3], buf(op.aux_lo >= 0 ? op.aux_lo : op.aux), 1024, L.cap, false)) return rc;
           f.has_aux_lo = op.aux_lo >= 0 ? 1 : 0;
           if (g_ctx.cr_resid_epi) {
-            f.resid_epi = 1;
+            f.resid_epi = g_ctx.cr_resid_epi;
             f.aux = buf(op.aux);
             f.aux_lo = buf(op.aux_lo);
             f.aux_kb = 16;
@@ -1610,7 +1611,7 @@ extern "C" int av1p_conv_res_forward(const av1p_conv_res_desc* d, void* stream) 
     if (int rc = make_act_map(&f.a_map[3], d->aux_lo_dev ? d->aux_lo_dev : d->aux_dev, 1024, uint64_t(d->rows), false)) return rc;
     f.has_aux_lo = d->aux_lo_dev ? 1 : 0;
     if (g_ctx.cr_resid_epi) {
-      f.resid_epi = 1;
+      f.resid_epi = g_ctx.cr_resid_epi;
       f.aux = static_cast<const __half*>(d->aux_dev);
       f.aux_lo = static_cast<const __half*>(d->aux_lo_dev);
       f.aux_kb = 16;

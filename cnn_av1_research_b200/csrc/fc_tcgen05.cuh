@@ -275,13 +275,30 @@ __device__ __forceinline__ void epi_tile_store(const P& p, const EpiStage& es, u
   const bool aux_on = gate || resid;
   const bool relu = p.epi == FC_EPI_RELU || p.epi == FC_EPI_ADD_RELU;
   const bool has_lo = p.out_lo != nullptr;
-  bool inplace = false;             // residual arrives in the staging set itself (conv_res kernel, resid_epi)
-  if constexpr (requires { p.resid_epi; }) inplace = p.resid_epi != 0 && p.epi == FC_EPI_ADD_RELU;
+  bool inplace = false;             // residual added here (conv_res kernel, resid_epi): 1 = it arrives in the staging set itself,
+  bool direct = false;              // 2 = every thread loads its 2 x 16 bytes per plane straight from global memory (L2-prefetched)
+  if constexpr (requires { p.resid_epi; }) {
+    inplace = p.resid_epi != 0 && p.epi == FC_EPI_ADD_RELU;
+    direct = inplace && p.resid_epi == 2;
+  }
   const float rs = ((p.row_scale && row_ok) ? p.row_scale[row] : 1.0f) * p.acc_scale;
   float ars = 1.0f;                 // scale of the aux operand (FC_EPI_ADD after spatial attention)
   if constexpr (requires { p.aux_row_scale; }) ars = (p.aux_row_scale && row_ok) ? p.aux_row_scale[row] : 1.0f;
   const int n_chunks = block_n / EPI_CHUNK;
   const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+  const uint32_t g0 = g;
+  const int c_first = int((g0 & 1u) ^ grp);                  // first chunk of this tile with (g0 + c) & 1 == grp
+  // direct residual: this thread's residual values of its first chunk are requested BEFORE the wait for the accumulator, so
+  // that their (L2) latency overlaps the time the epilogue spends waiting for the tensor pipe anyway
+  uint4 pre_q[2] = {zero4, zero4}, pre_l[2] = {zero4, zero4};
+  if (direct && row_ok && c_first < n_chunks) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const size_t o = act_off(row, col0 + c_first * EPI_CHUNK + sub * 16 + h * 8, p.aux_kb);
+      pre_q[h] = __ldg(reinterpret_cast<const uint4*>(p.aux + o));
+      if (p.aux_lo) pre_l[h] = __ldg(reinterpret_cast<const uint4*>(p.aux_lo + o));
+    }
+  }
   mbar_wait(full, full_phase, p.err_flag, tag);
   tc_fence_after_sync();
   if (epi_debug(p) & 16) {        // development switch: hand the accumulator straight back
@@ -290,10 +307,8 @@ __device__ __forceinline__ void epi_tile_store(const P& p, const EpiStage& es, u
     if (lane == 0) acc_release(empty, empty_remote);
     return;
   }
-  const uint32_t g0 = g;
   const uint32_t ga0 = aux_on ? gx->ga : 0u;
   float ssum = 0.f, smax = -INFINITY;         // sam_part partials of this thread (columns of its chunks in this tile)
-  const int c_first = int((g0 & 1u) ^ grp);                  // first chunk of this tile with (g0 + c) & 1 == grp
   const uint32_t t_addr = t_col + (uint32_t(quad * 32) << 16) + uint32_t(sub * 16);
   uint32_t v[8];
   bool released = false;
@@ -319,7 +334,13 @@ __device__ __forceinline__ void epi_tile_store(const P& p, const EpiStage& es, u
     }
     uint4 rq[2] = {zero4, zero4}, rql[2] = {zero4, zero4};      // in-place residual: this thread's 2 x 8 values (hi, lo)
     if (inplace) {
-      if (staged) {
+      if (direct && c == c_first) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          rq[h] = pre_q[h];
+          rql[h] = pre_l[h];
+        }
+      } else if (staged && !direct) {
         // use u = (g0 + c) >> 1 of set `grp`: its residual tile has landed (which also means the set's previous stores are done)
         mbar_wait(&es.loaded[grp], ((g0 + uint32_t(c)) >> 1) & 1u, p.err_flag, tag + 30);
 #pragma unroll
@@ -416,7 +437,7 @@ __device__ __forceinline__ void epi_tile_store(const P& p, const EpiStage& es, u
       const uint4 lq = *reinterpret_cast<const uint4*>(lo);
       if (staged) {
         // use u = (g0 + c) >> 1 of set `grp`: the first use needs no wait (parity trick), use u waits for the (u-1)-th hand-back
-        if (h == 0 && !inplace) mbar_wait(&es.free_[grp], (((g0 + uint32_t(c)) >> 1) & 1u) ^ 1u, p.err_flag, tag + 10);
+        if (h == 0 && (!inplace || direct)) mbar_wait(&es.free_[grp], (((g0 + uint32_t(c)) >> 1) & 1u) ^ 1u, p.err_flag, tag + 10);
         stage_store8(es.unit(grp, 0), r_local, sub * 2 + h, hq);
         if (has_lo) stage_store8(es.unit(grp, 1), r_local, sub * 2 + h, lq);
         if (h == 1) {

@@ -59,7 +59,7 @@ def _split(t):
     return hi, (t - hi.double()).half()
 
 
-@pytest.fixture(params=[1, 0], ids=["resid_in_epilogue", "resid_on_tensor_core"])
+@pytest.fixture(params=[1, 2, 0], ids=["resid_in_place", "resid_direct_loads", "resid_on_tensor_core"])
 def resid_mode(request, cuda_device):
     """Both forms of the identity branch: added in place in the epilogue's staging tiles (default) and
     accumulated on the tensor core through the operand ring."""
