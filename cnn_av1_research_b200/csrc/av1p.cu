@@ -65,8 +65,9 @@ struct DeviceCtx {
   bool stem_tma = true;           // frame input: TMA-staged stem (stem_tma.cuh) when the frame geometry allows a tensor map;
                                   // AV1P_STEM_TMA=0 keeps the per-thread gather kernel (stem_tc.cuh, INT_PIX)
   bool pdl = true;                // programmatic dependent launch between the kernels of an op program (AV1P_PDL=0: plain stream order)
-  int cr_resid_epi = 1;           // layer1 residual convs add the identity branch in the epilogue, in place in the staging sets
-                                  // (conv_res_tcgen05.cuh, resid_epi); AV1P_CR_RESID_EPI=0: identity MMAs through the operand ring
+  int cr_resid_epi = 1;           // layer1 residual convs add the identity branch in the epilogue: 1 = in place in the staging sets,
+                                  // 2 = from per-thread global loads (conv_res_tcgen05.cuh, resid_epi); AV1P_CR_RESID_EPI=0: identity
+                                  // MMAs through the operand ring
   bool fc_resid_epi = false;      // AV1P_FC_RESID_EPI=1: residual FC layers add the identity branch in the epilogue (aux ring)
                                   // instead of on the tensor core (FC_W_IDENT schedule entries).  Measured slower (layer2.1.conv2
                                   // 859 vs 740 us on 518 k rows): the aux ring costs two of the six operand-ring stages.

@@ -56,8 +56,9 @@ int av1p_debug_watchdog(void);
  *               0 = per-thread gather stem (read at every launch);
  *   "pdl"     : 1 = programmatic dependent launch between the kernels of a stage (default), 0 = plain stream order
  *               (read at every launch);
- *   "cr_resid_epi": 1 = layer1 residual convolutions add the identity branch in the epilogue (default), 0 = on the
- *               tensor core (read when a stage / cascade is created).
+ *   "cr_resid_epi": layer1 residual convolutions add the identity branch 1 = in the epilogue, in place in the TMA-store
+ *               staging tiles (default), 2 = in the epilogue from per-thread global loads, 0 = on the tensor core (read
+ *               when a stage / cascade is created).
  * av1p_get_option also answers "sms"; it returns -1 for an unknown name. */
 int av1p_set_option(const char* name, int32_t value);
 int av1p_get_option(const char* name);
