@@ -664,6 +664,18 @@ __global__ void __launch_bounds__(256) finalize_labels_kernel(const float* __res
   }
 }
 
+// Rows of `k` floats picked by an index list with a device-side count: dst[j] = src[idx[j]], j < *n_dev.  The speculative
+// small-batch cascade (av1p.cu) runs every stage on every block and then compacts the logits of the routed blocks with this,
+// so that the routing kernels and every cascade output (logits, index lists, counts) are those of the routed path.
+__global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ src, const int* __restrict__ idx,
+                                                          const int* n_dev, int n, int k, float* __restrict__ dst) {
+  const int rows = n_dev ? *n_dev : n;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < rows * k; t += gridDim.x * blockDim.x) {
+    const int j = t / k, c = t - j * k;
+    dst[t] = src[size_t(idx[j]) * k + c];
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // Stage-1 threshold sweep (reference scripts/007_optimize_thresholds.py:24-71): prob = sigmoid(logit) in fp32,
 // pred_t = prob >= thr[t], and for every threshold the confusion counts against the binary stage-1 label:

@@ -64,6 +64,7 @@ struct DeviceCtx {
   bool fc_pair = true;            // FC layers on CTA pairs (tcgen05 cta_group::2); AV1P_FC_PAIR=0 selects the single-CTA kernel
   bool stem_tma = true;           // frame input: TMA-staged stem (stem_tma.cuh) when the frame geometry allows a tensor map;
                                   // AV1P_STEM_TMA=0 keeps the per-thread gather kernel (stem_tc.cuh, INT_PIX)
+  bool speculate = true;          // small batches: run all four stages on every block side by side (av1p_cascade_predict); AV1P_SPECULATE=0
   bool pdl = true;                // programmatic dependent launch between the kernels of an op program (AV1P_PDL=0: plain stream order)
   int cr_resid_epi = 1;           // layer1 residual convs add the identity branch in the epilogue: 1 = in place in the staging sets,
                                   // 2 = from per-thread global loads (conv_res_tcgen05.cuh, resid_epi); AV1P_CR_RESID_EPI=0: identity
@@ -115,6 +116,7 @@ int ensure_ctx() {
   if (const char* e = getenv("AV1P_FC_PAIR")) c.fc_pair = atoi(e) != 0;
   if (const char* e = getenv("AV1P_FC_RESID_EPI")) c.fc_resid_epi = atoi(e) != 0;
   if (const char* e = getenv("AV1P_PDL")) c.pdl = atoi(e) != 0;
+  if (const char* e = getenv("AV1P_SPECULATE")) c.speculate = atoi(e) != 0;
   if (const char* e = getenv("AV1P_CR_RESID_EPI")) c.cr_resid_epi = std::max(0, std::min(2, atoi(e)));
   {
     int n_k = 0;
@@ -239,6 +241,10 @@ extern "C" int av1p_set_option(const char* name, int32_t value) {
     c.pdl = value != 0;
     return AV1P_OK;
   }
+  if (!strcmp(name, "speculate")) {         // read at every cascade call
+    c.speculate = value != 0;
+    return AV1P_OK;
+  }
   if (!strcmp(name, "cr_resid_epi")) {      // read when a stage is planned (and by av1p_conv_res_forward)
     if (value < 0 || value > 2) return fail(AV1P_EINVAL, "cr_resid_epi %d outside 0..2", value);
     c.cr_resid_epi = value;
@@ -254,6 +260,7 @@ extern "C" int av1p_get_option(const char* name) {
   if (!strcmp(name, "fc_pair")) return c.fc_pair ? 1 : 0;
   if (!strcmp(name, "stem_tma")) return c.stem_tma ? 1 : 0;
   if (!strcmp(name, "pdl")) return c.pdl ? 1 : 0;
+  if (!strcmp(name, "speculate")) return c.speculate ? 1 : 0;
   if (!strcmp(name, "cr_resid_epi")) return c.cr_resid_epi;
   return -1;
 }
@@ -1248,18 +1255,33 @@ struct av1p_cascade {
   bool overlap3 = false;
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  // Speculative small-batch path (av1p_cascade_predict, n <= spec_cap): stages 2 / RECT / AB get their own small activation
+  // regions and streams and run on EVERY block next to stage 1; their logits are compacted by the routing lists afterwards.
+  int spec_cap = 0;
+  av1p_stage spec_stage[3];      // stage 2, RECT, AB planned on the speculative regions
+  float* spec_logits[3] = {nullptr, nullptr, nullptr};   // full (uncompacted) logits [spec_cap][3 | 2 | 4]
+  cudaStream_t spec_stream[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t spec_fork = nullptr, spec_join[3] = {nullptr, nullptr, nullptr};
   ~av1p_cascade() {
     if (ev_fork) cudaEventDestroy(ev_fork);
     if (ev_join) cudaEventDestroy(ev_join);
     if (side) cudaStreamDestroy(side);
+    if (spec_fork) cudaEventDestroy(spec_fork);
+    for (int i = 0; i < 3; ++i) {
+      if (spec_join[i]) cudaEventDestroy(spec_join[i]);
+      if (spec_stream[i]) cudaStreamDestroy(spec_stream[i]);
+    }
   }
 };
 
 namespace {
+constexpr int SPEC_MAX_BLOCKS = 4096;      // 32 M tiles per stage: four stages side by side still fit one wave of 148 SMs
 struct CascadeLayout {
   ActLayout act;
   size_t act2_off;               // second activation region (0 = none: the specialists run back to back)
   size_t logits_off[4], idx_off[3], counts_off, scratch_off, bytes;
+  ActLayout spec;                // activation layout of one speculative region (capacity spec.cap rows)
+  size_t spec_off[3], spec_logits_off[3];
 };
 // second region only while it stays small next to 180 GB of HBM (AV1P_STAGE3_OVERLAP=0 disables)
 inline bool stage3_overlap_wanted(size_t act_bytes) {
@@ -1284,6 +1306,14 @@ CascadeLayout make_cascade_layout(const av1p_model* const models[4], int capacit
   for (int i = 0; i < 3; ++i) {
     C.idx_off[i] = o;
     o += align_up(size_t(C.act.cap) * 4, 1024);
+  }
+  // speculative small-batch regions (12.4 KB per row: 3 x 51 MB at the full 4,096 rows)
+  C.spec = make_act_layout(models, 4, std::min(capacity, SPEC_MAX_BLOCKS));
+  for (int i = 0; i < 3; ++i) {
+    C.spec_off[i] = align_up(o, 1024);
+    o = C.spec_off[i] + C.spec.bytes;
+    C.spec_logits_off[i] = o;
+    o += align_up(size_t(C.spec.cap) * outs[i + 1] * 4, 1024);
   }
   C.counts_off = o;
   o += 1024;
@@ -1338,6 +1368,24 @@ extern "C" int av1p_cascade_create(const av1p_model* const models[4], int32_t ca
       return fail(AV1P_ECUDA, "side stream / events for the stage-3 overlap could not be created");
     }
   }
+  c->spec_cap = C.spec.cap;
+  for (int i = 0; i < 3; ++i) {
+    if (int rc = plan_stage(models[i + 1], C.spec, base + C.spec_off[i], &c->spec_stage[i])) {
+      delete c;
+      return rc;
+    }
+    c->spec_stage[i].range_flag = reinterpret_cast<int*>(base + C.counts_off) + 8;
+    c->spec_logits[i] = reinterpret_cast<float*>(base + C.spec_logits_off[i]);
+    if (cudaStreamCreateWithFlags(&c->spec_stream[i], cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->spec_join[i], cudaEventDisableTiming) != cudaSuccess) {
+      delete c;
+      return fail(AV1P_ECUDA, "streams / events of the speculative small-batch path could not be created");
+    }
+  }
+  if (cudaEventCreateWithFlags(&c->spec_fork, cudaEventDisableTiming) != cudaSuccess) {
+    delete c;
+    return fail(AV1P_ECUDA, "fork event of the speculative small-batch path could not be created");
+  }
   c->idx2 = reinterpret_cast<int32_t*>(base + C.idx_off[0]);
   c->idx_rect = reinterpret_cast<int32_t*>(base + C.idx_off[1]);
   c->idx_ab = reinterpret_cast<int32_t*>(base + C.idx_off[2]);
@@ -1388,6 +1436,38 @@ extern "C" int av1p_cascade_predict(av1p_cascade* c, const av1p_input* in, int32
   int32_t* n2 = c->counts + 0;
   int32_t* n_rect = c->counts + 2;
   int32_t* n_ab = c->counts + 3;
+  if (g_ctx.speculate && n_blocks <= c->spec_cap) {
+    // Small batch (what the reference's evaluate_pipeline feeds: 256 blocks per call, 008:278-284): a stage forward on a
+    // few M tiles occupies a handful of SMs for ~0.4 ms of dependent launches, and the routed cascade runs four of them
+    // one after the other.  Here stages 2 / RECT / AB run on EVERY block on three side streams next to stage 1 (their own
+    // activation regions), then the usual routing kernels run on logits compacted by the index lists they produce.  A row's
+    // logits do not depend on which other rows share its batch (the kernels are row-independent: bitwise, see the block
+    // independence test), so logits, index lists, counts and labels are exactly those of the routed path.
+    CUDA_TRY(cudaEventRecord(c->spec_fork, st));
+    int rc = AV1P_OK;
+    for (int i = 0; i < 3 && !rc; ++i) {
+      CUDA_TRY(cudaStreamWaitEvent(c->spec_stream[i], c->spec_fork, 0));
+      rc = run_stage(&c->spec_stage[i], si, nullptr, nullptr, n_blocks, c->spec_logits[i], c->spec_stream[i]);
+    }
+    if (!rc) rc = run_stage(&c->stage[0], si, nullptr, nullptr, n_blocks, c->logits[0], st);
+    for (int i = 0; i < 3; ++i) {      // always join, also after an error
+      cudaEventRecord(c->spec_join[i], c->spec_stream[i]);
+      cudaStreamWaitEvent(st, c->spec_join[i], 0);
+    }
+    if (rc) return rc;
+    auto gather = [&](const float* src, const int32_t* idx, const int32_t* n_dev, int k, float* dst) -> int {
+      gather_rows_kernel<<<std::min(ceil_div(n_blocks * k, 256), g_ctx.sms * 4), 256, 0, st>>>(src, idx, n_dev, n_blocks, k, dst);
+      CUDA_TRY(cudaGetLastError());
+      return AV1P_OK;
+    };
+    if ((rc = av1p_route_stage1(c->logits[0], nullptr, n_blocks, thr, c->idx2, n2, l8, l64, c->scratch, st))) return rc;
+    if ((rc = gather(c->spec_logits[0], c->idx2, n2, 3, c->logits[1]))) return rc;
+    if ((rc = av1p_route_stage2(c->logits[1], c->idx2, n2, n_blocks, c->idx_rect, c->idx_ab, n_rect, l8, l64, c->scratch, st))) return rc;
+    if ((rc = gather(c->spec_logits[1], c->idx_rect, n_rect, 2, c->logits[2]))) return rc;
+    if ((rc = av1p_finalize_labels(c->logits[2], 2, 2, c->idx_rect, n_rect, n_blocks, l8, l64, st))) return rc;
+    if ((rc = gather(c->spec_logits[2], c->idx_ab, n_ab, 4, c->logits[3]))) return rc;
+    return av1p_finalize_labels(c->logits[3], 4, 4, c->idx_ab, n_ab, n_blocks, l8, l64, st);
+  }
   // Stage 1 on every block, then threshold + compaction (008:76-85)
   if (int rc = run_stage(&c->stage[0], si, nullptr, nullptr, n_blocks, c->logits[0], st)) return rc;
   if (int rc = av1p_route_stage1(c->logits[0], nullptr, n_blocks, thr, c->idx2, n2, l8, l64, c->scratch, st)) return rc;

@@ -175,7 +175,36 @@ class _NativeStageModule(nn.Module):
         self._natives: dict = {}      # block -> [NativeModel, key, Optional[NativeStage]]
 
     def _param_key(self, device):
-        return (str(device),) + tuple((t.data_ptr(), t._version) for t in self.state_dict(keep_vars=True).values())
+        """Fingerprint of every parameter and buffer: (storage address, version counter).  It is evaluated on EVERY call of
+        the pipeline (a changed weight must re-pack the program), so it must be cheap: walking `state_dict()` costs ~0.4 ms per
+        model - more than the whole small-batch cascade on the GPU.  The (owner dict, name) slot of every tensor is collected
+        once; each check is then one dictionary lookup per tensor (~40 us per model), which still sees in-place updates
+        (version), re-allocations (`.to()`, `.half()`: address) and replaced buffer objects (`module._buffers[name] = ...`).
+        `_apply` and `load_state_dict` rebuild the slot list; adding or removing sub-modules after the first forward is not
+        supported (call `_invalidate_native()`)."""
+        slots = self.__dict__.get("_tensor_slots")
+        if slots is None:
+            slots = []
+            for mod in self.modules():
+                slots += [(mod._parameters, k) for k in mod._parameters]
+                slots += [(mod._buffers, k) for k in mod._buffers if k not in mod._non_persistent_buffers_set]
+            self.__dict__["_tensor_slots"] = slots
+        key = [str(device)]
+        for d, k in slots:
+            t = d.get(k)
+            key.append((t.data_ptr(), t._version) if t is not None else None)
+        return tuple(key)
+
+    def _invalidate_native(self):
+        self.__dict__["_tensor_slots"] = None
+
+    def _apply(self, fn, *args, **kwargs):
+        self._invalidate_native()
+        return super()._apply(fn, *args, **kwargs)
+
+    def load_state_dict(self, *args, **kwargs):
+        self._invalidate_native()
+        return super().load_state_dict(*args, **kwargs)
 
     def native_model(self, device, block: int = 16) -> NativeModel:
         key = (self.precision,) + self._param_key(device)

@@ -56,6 +56,9 @@ int av1p_debug_watchdog(void);
  *               0 = per-thread gather stem (read at every launch);
  *   "pdl"     : 1 = programmatic dependent launch between the kernels of a stage (default), 0 = plain stream order
  *               (read at every launch);
+ *   "speculate": 1 = av1p_cascade_predict runs calls of up to 4,096 blocks speculatively - every stage on every block,
+ *               side by side on four streams, results compacted by the routing lists; bit-identical outputs (default),
+ *               0 = always the routed order (read at every call);
  *   "cr_resid_epi": layer1 residual convolutions add the identity branch 1 = in the epilogue, in place in the TMA-store
  *               staging tiles (default), 2 = in the epilogue from per-thread global loads, 0 = on the tensor core (read
  *               when a stage / cascade is created).

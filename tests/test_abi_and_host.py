@@ -194,3 +194,33 @@ def test_block_coordinate_reciprocals_are_exact():
         for g in gs:
             if 0 <= g < (1 << 32):
                 assert (g * inv) >> 64 == g // d, (g, d)
+
+
+def test_parameter_fingerprint_sees_every_kind_of_weight_change():
+    """The drop-in modules re-pack their program whenever a parameter or buffer changes; the fingerprint that decides it is
+    evaluated on every call, so it walks cached (owner dict, name) slots instead of `state_dict()` - it must still notice
+    in-place updates, re-allocations, replaced buffer objects and `load_state_dict`."""
+    import torch
+    from cnn_av1_research_b200 import FGVCModel, Stage1Model, Stage3ABModel, synth
+    m = Stage1Model(pretrained=False).eval()
+    k0 = m._param_key("cuda:0")
+    assert m._param_key("cuda:0") == k0 and m._param_key("cuda:1") != k0
+    with torch.no_grad():
+        m.backbone.layer3[1].conv2.weight.mul_(1.5)                 # in-place: version counter
+    k1 = m._param_key("cuda:0")
+    assert k1 != k0
+    m.backbone.bn1.running_var = torch.ones(64)                     # buffer object replaced behind the module's back
+    k2 = m._param_key("cuda:0")
+    assert k2 != k1
+    m.load_state_dict(synth.calibrated_state_dict("stage1", 0))
+    k3 = m._param_key("cuda:0")
+    assert k3 != k2
+    m.double()                                                      # _apply: new storage
+    assert m._param_key("cuda:0") != k3
+    n_tensors = len(list(m.parameters())) + len(list(m.buffers()))
+    assert sum(e is not None for e in k3[1:]) == n_tensors          # (bias=False layers register a None parameter)
+    f = FGVCModel(Stage3ABModel(pretrained=False)).eval()
+    kf = f._param_key("cuda:0")
+    with torch.no_grad():
+        f.classifier.weight.add_(0.1)
+    assert f._param_key("cuda:0") != kf

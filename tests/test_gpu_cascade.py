@@ -335,6 +335,50 @@ def test_launch_and_stem_variants_agree(cuda_device):
     assert np.abs(got.cpu().numpy() - ref[idx.cpu().numpy()]).max() <= LOGIT_TOL["fp16x3"]
 
 
+def test_speculative_small_batch_path_equals_the_routed_cascade(cuda_device):
+    """Small batches (<= 4,096 blocks) run all four stages on every block side by side and compact the logits by the routing
+    lists afterwards (av1p_cascade_predict): labels, index lists, counts and per-stage logits must be bit-identical to the
+    routed cascade, through direct enqueue and through the replayed CUDA graph, for float blocks and for frames."""
+    lib = N.lib()
+    pipe = build_pipeline(seed=0, threshold=0.45, device=cuda_device, capacity_blocks=8192)
+    frames = synth.synth_frames(3, 640, 368, seed=77)
+    all_images = O.frames_to_images(frames, 3, 640, 368)                       # 2,760 blocks with the calibrated routing mix
+    g = torch.Generator().manual_seed(5)
+    extra = torch.rand(4097 - all_images.shape[0], 1, 16, 16, generator=g)
+    pool = torch.cat([all_images, extra]).to(cuda_device)
+    with torch.cuda.device(cuda_device):
+        assert lib.av1p_get_option(b"speculate") == 1
+        for n in (1, 5, 127, 256, 1000, 2760, 4096, 4097):
+            x = pool[:n].contiguous()
+            try:
+                N.check(lib.av1p_set_option(b"speculate", 0))
+                routed = pipe.predict_device(x).clone()
+                ref = pipe.cascade(n).intermediates(n)
+            finally:
+                N.check(lib.av1p_set_option(b"speculate", 1))
+            for rep in range(2):
+                spec = pipe.predict_device(x).clone()
+                got = pipe.cascade(n).intermediates(n)
+                assert torch.equal(spec, routed), f"n={n}: labels differ"
+                for k in ref:
+                    assert torch.equal(got[k], ref[k]), f"n={n}: {k} differs"
+        # the graph-replayed predict() of the reference API takes the same path
+        x = pool[:256].cpu()
+        a = pipe.predict(x)
+        b = pipe.predict(x)
+        assert torch.equal(a, b) and torch.equal(a, pipe.predict_device(pool[:256]).cpu())
+        # frames through the small-batch path (920 blocks per frame)
+        fr = frames_tensor(frames, cuda_device)
+        lab = pipe.predict_frames(fr, 640, 368, 3).cpu()
+        try:
+            N.check(lib.av1p_set_option(b"speculate", 0))
+            assert torch.equal(lab, pipe.predict_frames(fr, 640, 368, 3).cpu())
+        finally:
+            N.check(lib.av1p_set_option(b"speculate", 1))
+    ref_labels = O.cascade_predict(synth.calibrated_cascade(0), all_images, 0.45)["labels"]
+    assert (lab.long() == ref_labels).float().mean() >= 0.999
+
+
 def test_config3_full_cascade_on_a_1080p_frame(cuda_device):
     """BASELINE configs[2]: full cascade on one 1920x1080 frame, extraction included (68 x 120 = 8,160 blocks, the last grid
     row is half padding) - every label against the CPU oracle on the same frame."""
