@@ -349,6 +349,20 @@ def configs_leg(pipe, dev, log):
     ref3 = O.cascade_predict(synth.calibrated_cascade(0), O.frames_to_images(words_hd, 1, w, h), THRESHOLD)["labels"].numpy()
     out["config3_cascade_1080p"] = {"blocks": n_hd, "b200_ms_per_frame": ms3, "b200_frames_per_sec": 1e3 / ms3,
                                     "label_agreement_vs_oracle": float((lab.cpu().numpy() == ref3).mean())}
+    # (extra) the reference API on the reference's own batch: HierarchicalPipelineV6.predict on 256 blocks (what
+    # evaluate_pipeline calls, 008:278-284) - wall clock, device tensor in, int64 labels on the CPU out
+    x_cascade = images[:256].contiguous().to(dev)
+    for _ in range(5):
+        pipe.predict(x_cascade)
+    ts = []
+    for _ in range(30):
+        t0 = time.perf_counter()
+        lab256 = pipe.predict(x_cascade)
+        ts.append(time.perf_counter() - t0)
+    ref256 = O.cascade_predict(synth.calibrated_cascade(0), images[:256], THRESHOLD)["labels"]
+    out["predict_b256_reference_api"] = {"b200_ms_median": float(np.median(ts)) * 1e3, "b200_ms_min": float(np.min(ts)) * 1e3,
+                                         "b200_blocks_per_sec": 256 / float(np.median(ts)),
+                                         "label_agreement_vs_oracle": float((lab256 == ref256).float().mean())}
     log(f"[configs] {json.dumps(out)}")
     return out
 

@@ -1276,6 +1276,11 @@ struct av1p_cascade {
 
 namespace {
 constexpr int SPEC_MAX_BLOCKS = 4096;      // 32 M tiles per stage: four stages side by side still fit one wave of 148 SMs
+inline int spec_max_blocks() {             // AV1P_SPEC_MAX overrides (experiments; read when a cascade is sized / created)
+  const char* e = getenv("AV1P_SPEC_MAX");
+  const int v = e ? atoi(e) : SPEC_MAX_BLOCKS;
+  return std::max(1, std::min(v, 1 << 16));
+}
 struct CascadeLayout {
   ActLayout act;
   size_t act2_off;               // second activation region (0 = none: the specialists run back to back)
@@ -1308,7 +1313,7 @@ CascadeLayout make_cascade_layout(const av1p_model* const models[4], int capacit
     o += align_up(size_t(C.act.cap) * 4, 1024);
   }
   // speculative small-batch regions (12.4 KB per row: 3 x 51 MB at the full 4,096 rows)
-  C.spec = make_act_layout(models, 4, std::min(capacity, SPEC_MAX_BLOCKS));
+  C.spec = make_act_layout(models, 4, std::min(capacity, spec_max_blocks()));
   for (int i = 0; i < 3; ++i) {
     C.spec_off[i] = align_up(o, 1024);
     o = C.spec_off[i] + C.spec.bytes;
