@@ -1510,12 +1510,25 @@ struct av1p_flat_cascade {
   int32_t* idx2 = nullptr;
   int32_t* counts = nullptr;
   RouteScratch* scratch = nullptr;
+  // speculative small-batch path, as in av1p_cascade: the flat model on every block on a side stream next to stage 1
+  int spec_cap = 0;
+  av1p_stage spec_stage;
+  float* spec_logits = nullptr;
+  cudaStream_t spec_stream = nullptr;
+  cudaEvent_t spec_fork = nullptr, spec_join = nullptr;
+  ~av1p_flat_cascade() {
+    if (spec_fork) cudaEventDestroy(spec_fork);
+    if (spec_join) cudaEventDestroy(spec_join);
+    if (spec_stream) cudaStreamDestroy(spec_stream);
+  }
 };
 
 namespace {
 struct FlatLayout {
   ActLayout act;
   size_t logits_off[2], idx_off, counts_off, scratch_off, bytes;
+  ActLayout spec;
+  size_t spec_off, spec_logits_off;
 };
 FlatLayout make_flat_layout(const av1p_model* const models[2], int capacity) {
   FlatLayout C;
@@ -1528,6 +1541,11 @@ FlatLayout make_flat_layout(const av1p_model* const models[2], int capacity) {
   }
   C.idx_off = o;
   o += align_up(size_t(C.act.cap) * 4, 1024);
+  C.spec = make_act_layout(models, 2, std::min(capacity, spec_max_blocks()));
+  C.spec_off = align_up(o, 1024);
+  o = C.spec_off + C.spec.bytes;
+  C.spec_logits_off = o;
+  o += align_up(size_t(C.spec.cap) * 7 * 4, 1024);
   C.counts_off = o;
   o += 1024;
   C.scratch_off = o;
@@ -1564,6 +1582,19 @@ extern "C" int av1p_flat_cascade_create(const av1p_model* const models[2], int32
     c->logits[i] = reinterpret_cast<float*>(base + C.logits_off[i]);
     c->stage[i].range_flag = reinterpret_cast<int*>(base + C.counts_off) + 8;
   }
+  c->spec_cap = C.spec.cap;
+  if (int rc = plan_stage(models[1], C.spec, base + C.spec_off, &c->spec_stage)) {
+    delete c;
+    return rc;
+  }
+  c->spec_stage.range_flag = reinterpret_cast<int*>(base + C.counts_off) + 8;
+  c->spec_logits = reinterpret_cast<float*>(base + C.spec_logits_off);
+  if (cudaStreamCreateWithFlags(&c->spec_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->spec_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->spec_join, cudaEventDisableTiming) != cudaSuccess) {
+    delete c;
+    return fail(AV1P_ECUDA, "stream / events of the speculative small-batch path could not be created");
+  }
   c->idx2 = reinterpret_cast<int32_t*>(base + C.idx_off);
   c->counts = reinterpret_cast<int32_t*>(base + C.counts_off);
   c->scratch = reinterpret_cast<RouteScratch*>(base + C.scratch_off);
@@ -1599,6 +1630,20 @@ extern "C" int av1p_flat_cascade_predict(av1p_flat_cascade* c, const av1p_input*
     return fail(AV1P_EINVAL, "n_blocks exceeds the blocks in the given frames");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int32_t* n2 = c->counts;
+  if (g_ctx.speculate && n_blocks <= c->spec_cap) {
+    // small batch: the flat model runs on every block on the side stream while stage 1 runs here (see av1p_cascade_predict)
+    CUDA_TRY(cudaEventRecord(c->spec_fork, st));
+    CUDA_TRY(cudaStreamWaitEvent(c->spec_stream, c->spec_fork, 0));
+    int rc = run_stage(&c->spec_stage, si, nullptr, nullptr, n_blocks, c->spec_logits, c->spec_stream);
+    if (!rc) rc = run_stage(&c->stage[0], si, nullptr, nullptr, n_blocks, c->logits[0], st);
+    cudaEventRecord(c->spec_join, c->spec_stream);
+    cudaStreamWaitEvent(st, c->spec_join, 0);
+    if (rc) return rc;
+    if ((rc = av1p_route_stage1(c->logits[0], nullptr, n_blocks, thr, c->idx2, n2, l8, l64, c->scratch, st))) return rc;
+    gather_rows_kernel<<<std::min(ceil_div(n_blocks * 7, 256), g_ctx.sms * 4), 256, 0, st>>>(c->spec_logits, c->idx2, n2, n_blocks, 7, c->logits[1]);
+    CUDA_TRY(cudaGetLastError());
+    return av1p_finalize_labels_argmax(c->logits[1], 7, 1, c->idx2, n2, n_blocks, l8, l64, st);
+  }
   if (int rc = run_stage(&c->stage[0], si, nullptr, nullptr, n_blocks, c->logits[0], st)) return rc;
   if (int rc = av1p_route_stage1(c->logits[0], nullptr, n_blocks, thr, c->idx2, n2, l8, l64, c->scratch, st)) return rc;
   if (int rc = run_stage(&c->stage[1], si, c->idx2, n2, n_blocks, c->logits[1], st)) return rc;

@@ -122,6 +122,31 @@ def test_gpu_flatten_cascade_matches_reference(cuda_device, flat_fix):
 
 
 @pytest.mark.gpu
+def test_gpu_flatten_speculative_small_batch_equals_routed(cuda_device, flat_fix):
+    """Calls of up to 4,096 blocks run the flat model on every block next to stage 1 and compact its logits by the routing
+    list (av1p_flat_cascade_predict): labels, list and logits bit-identical to the routed order."""
+    from cnn_av1_research_b200 import _native as N
+    lib = N.lib()
+    words, w, h, nf = _frames(flat_fix)
+    images = O.frames_to_images(words, nf, w, h)
+    pipe = _flat_pipe(cuda_device)
+    with torch.cuda.device(cuda_device):
+        for n in (1, 300, images.shape[0]):
+            x = images[:n]
+            try:
+                N.check(lib.av1p_set_option(b"speculate", 0))
+                routed = pipe.predict(x)
+                ref = pipe.cascade(n).intermediates(n)
+            finally:
+                N.check(lib.av1p_set_option(b"speculate", 1))
+            spec = pipe.predict(x)
+            got = pipe.cascade(n).intermediates(n)
+            assert torch.equal(spec, routed), n
+            for k in ref:
+                assert torch.equal(got[k], ref[k]), (n, k)
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("w,h", [(1920, 1080), (3840, 2160)])
 def test_gpu_flatten_cascade_full_size_frames(cuda_device, w, h):
     """The flatten cascade (008b:177-229) at full size, extraction fused: a 1080p frame (68 x 120 blocks, the last grid row
