@@ -77,8 +77,8 @@ def test_stage2_flat_state_dict_keys_match_reference():
     if ref_import.available():          # build container: the reference's own loader accepts our checkpoint
         import os
         import tempfile
+        ref_import.load()               # first: installs the matplotlib / seaborn stubs the reference's imports need
         ref008b = ref_import._load("ref_flat008b_t", ref_import.REF / "pesquisa_v6/scripts/008b_run_pipeline_flatten_eval.py")
-        ref_import.load()
         with tempfile.TemporaryDirectory() as tmp:
             path = os.path.join(tmp, "flat.pt")
             torch.save({"model_state_dict": mine.state_dict()}, path)
