@@ -92,6 +92,9 @@ SIGNATURES = {
     "av1p_profile_end": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
     "av1p_profile_end_launches": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32)]),
     "av1p_upload_luma": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]),
+    "av1p_focal_loss_binary": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "av1p_adamw_flat": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double,
+                                  C.c_double, C.c_double, C.c_void_p, C.c_int32, C.c_void_p]),
 }
 
 

@@ -25,6 +25,7 @@
 #include "stem_tc.cuh"
 #include "stem_tma.cuh"
 #include "gen_kernels.cuh"
+#include "train_kernels.cuh"
 
 using namespace av1p;
 
@@ -1765,6 +1766,50 @@ extern "C" int av1p_conv_res_forward(const av1p_conv_res_desc* d, void* stream) 
   if (const char* dbg = getenv("AV1P_CR_DEBUG")) f.debug = atoi(dbg);   // kernel-development switch of this test hook only
   const int grid = 2 * std::max(1, std::min(g_ctx.grid_sms / 2, ceil_div(d->rows, FC_TILE_M)));
   conv_res_kernel_for(f)<<<grid, CR_THREADS, CR_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(f);
+  CUDA_TRY(cudaGetLastError());
+  return AV1P_OK;
+}
+
+// ------------------------------------------------------------------------------ training step (BASELINE configs[4])
+// The two non-convolution pieces of the data-parallel Stage-1 training step as single launches (train_kernels.cuh).
+extern "C" int av1p_focal_loss_binary(const float* logits_dev, const int64_t* targets_dev, int32_t n, float alpha, float gamma,
+                                      float* loss_dev, float* dlogits_dev, void* stream) {
+  if (!logits_dev || !targets_dev || !loss_dev) return fail(AV1P_EINVAL, "null argument");
+  if (n <= 0) return fail(AV1P_EINVAL, "focal loss over %d logits", n);
+  if (!(gamma >= 0.f) || !(alpha >= 0.f && alpha <= 1.f)) return fail(AV1P_EINVAL, "focal loss: alpha %g / gamma %g out of range", double(alpha), double(gamma));
+  if (int rc = ensure_ctx()) return rc;
+  static_assert(sizeof(long long) == sizeof(int64_t), "int64 targets");
+  focal_loss_binary_kernel<<<1, FOCAL_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+      logits_dev, reinterpret_cast<const long long*>(targets_dev), n, alpha, gamma, loss_dev, dlogits_dev);
+  CUDA_TRY(cudaGetLastError());
+  return AV1P_OK;
+}
+
+extern "C" int av1p_adamw_flat(float* param_dev, const float* grad_dev, float* exp_avg_dev, float* exp_avg_sq_dev, int64_t n, double lr,
+                               double beta1, double beta2, double eps, double weight_decay, double grad_scale, int32_t* step_dev,
+                               int32_t advance_step, void* stream) {
+  if (!param_dev || !grad_dev || !exp_avg_dev || !exp_avg_sq_dev || !step_dev) return fail(AV1P_EINVAL, "null argument");
+  if (n <= 0) return fail(AV1P_EINVAL, "AdamW over %lld parameters", (long long)n);
+  {
+    const uintptr_t a0 = reinterpret_cast<uintptr_t>(param_dev) & 15u;
+    if ((a0 & 3u) || (reinterpret_cast<uintptr_t>(grad_dev) & 15u) != a0 || (reinterpret_cast<uintptr_t>(exp_avg_dev) & 15u) != a0 ||
+        (reinterpret_cast<uintptr_t>(exp_avg_sq_dev) & 15u) != a0)
+      return fail(AV1P_EINVAL, "AdamW buffers must be 4-byte aligned and share their address modulo 16");
+  }
+  if (!(beta1 >= 0.0 && beta1 < 1.0) || !(beta2 >= 0.0 && beta2 < 1.0) || !(eps >= 0.0) || !(lr >= 0.0) || !(weight_decay >= 0.0))
+    return fail(AV1P_EINVAL, "AdamW hyper-parameters out of range");
+  if (int rc = ensure_ctx()) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (advance_step) {
+    train_step_inc_kernel<<<1, 1, 0, st>>>(step_dev);
+    CUDA_TRY(cudaGetLastError());
+  }
+  AdamWArgs a{param_dev, grad_dev, exp_avg_dev, exp_avg_sq_dev, (long long)n, lr, beta1, beta2, float(1.0 - lr * weight_decay),
+              float(1.0 - beta1), float(beta2), float(1.0 - beta2), float(eps), float(grad_scale), step_dev};
+  // HBM-bound streaming pass: a whole number of waves, at most eight resident CTAs of 256 threads per SM
+  const long long want = ((n >> 2) + TRAIN_THREADS - 1) / TRAIN_THREADS;
+  const int grid = int(std::max<long long>(1, std::min<long long>(want, (long long)g_ctx.sms * 8)));
+  adamw_flat_kernel<<<grid, TRAIN_THREADS, 0, st>>>(a);
   CUDA_TRY(cudaGetLastError());
   return AV1P_OK;
 }

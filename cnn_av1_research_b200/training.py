@@ -7,12 +7,14 @@ per process (003:139).
 
 Scope.  The inference cascade is the product of this repository and runs on hand-written sm_100a kernels; training
 is NOT on that path.  This module exists so that the data-parallel configuration of the benchmark list can be run and
-measured: forward/backward are plain PyTorch ops (bf16 autocast on CUDA), written functionally over the SAME
-parameter tensors as the drop-in `Stage1Model` (identical state_dict keys, so a checkpoint trained here loads into
-the inference path and vice versa), and the only communication is the all-reduce of the 11,345,444 gradients per step
-(NCCL over NVLink on GPUs, gloo in the CPU tests) - bucketed and overlapped with backward, see the trainer class -
-followed by the identical AdamW update on every rank.  BatchNorm uses per-rank batch statistics (plain DDP semantics, as the single-GPU reference would with its own
-batch).
+measured.  Convolution / BatchNorm forward and backward are plain PyTorch ops (bf16 autocast on CUDA, cuDNN kernels),
+written functionally over the SAME parameter tensors as the drop-in `Stage1Model` (identical state_dict keys, so a
+checkpoint trained here loads into the inference path and vice versa).  What is native (libav1p, csrc/train_kernels.cuh):
+the focal loss with its gradient in one launch, the AdamW update of all parameters in one launch over flat buffers, and
+the step replayed from a CUDA graph - at 128 blocks per GPU the eager step is bound by the host issuing ~650 tiny
+launches, not by the device.  The only communication is the all-reduce of the 11,345,444 gradients per step (NCCL over
+NVLink on GPUs, gloo in the CPU tests), followed by the identical AdamW update on every rank.  BatchNorm uses per-rank
+batch statistics (plain DDP semantics, as the single-GPU reference would with its own batch).
 """
 from __future__ import annotations
 
@@ -67,6 +69,49 @@ def stage1_forward_torch(sd: Dict[str, torch.Tensor], x: torch.Tensor, training:
     return F.linear(h, sd["head.head.3.weight"], sd["head.head.3.bias"])
 
 
+def focal_loss_binary_grad(logits: torch.Tensor, targets: torch.Tensor, alpha: float = 0.25, gamma: float = 2.5) -> torch.Tensor:
+    """Closed form of d focal_loss_binary / d logits that `focal_loss_binary_kernel` (csrc/train_kernels.cuh) evaluates:
+    sign * a_t * (1 - pt)^gamma * (gamma * pt * log(pt) - (1 - pt)) / N.  Host-side restatement for the CPU tests (checked
+    against autograd through the reference formula above)."""
+    x = logits.float().reshape(-1)
+    pos = targets.reshape(-1) != 0
+    z = torch.where(pos, x, -x)
+    log_pt = F.logsigmoid(z)
+    pt, one_m_pt = torch.sigmoid(z), torch.sigmoid(-z)
+    a_t = torch.where(pos, torch.full_like(x, alpha), torch.full_like(x, 1.0 - alpha))
+    sign = torch.where(pos, torch.ones_like(x), -torch.ones_like(x))
+    return (sign * a_t * one_m_pt ** gamma * (gamma * pt * log_pt - one_m_pt) / x.numel()).reshape(logits.shape)
+
+
+class _FocalLossNative(torch.autograd.Function):
+    """losses.py:29-38 + :48-49 and their backward in one launch (av1p_focal_loss_binary)."""
+
+    @staticmethod
+    def forward(ctx, logits, targets, alpha, gamma):
+        from . import _native as N
+        x = logits.reshape(-1).float().contiguous()
+        t = targets.reshape(-1).to(torch.int64).contiguous()
+        if t.numel() != x.numel():
+            raise ValueError(f"focal loss: {x.numel()} logits but {t.numel()} targets")
+        loss = torch.empty((), dtype=torch.float32, device=x.device)
+        dx = torch.empty_like(x)
+        N.check(N.lib().av1p_focal_loss_binary(N.ptr(x), N.ptr(t), x.numel(), float(alpha), float(gamma), N.ptr(loss), N.ptr(dx),
+                                               N.stream_handle(x.device)))
+        ctx.save_for_backward(dx)
+        ctx.shape, ctx.dtype = logits.shape, logits.dtype
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (dx,) = ctx.saved_tensors
+        return (dx * grad_out).reshape(ctx.shape).to(ctx.dtype), None, None, None
+
+
+def focal_loss_binary_native(logits: torch.Tensor, targets: torch.Tensor, alpha: float = 0.25, gamma: float = 2.5) -> torch.Tensor:
+    """`focal_loss_binary` on the device in one launch (and one more tiny one in backward).  CUDA tensors only."""
+    return _FocalLossNative.apply(logits, targets, alpha, gamma)
+
+
 class Stage1DataParallelTrainer:
     """One replica of the Stage-1 training step; all replicas stay bit-identical because they apply the same averaged
     gradient with the same optimiser state.
@@ -80,33 +125,61 @@ class Stage1DataParallelTrainer:
     Measured on 8 B200 (tools/bench_train.py, per-GPU batch 128, profiles/r02_train_n8*.json): 8.51 ms / step bucketed
     (120.4 k samples/s) vs 7.22 ms flat (141.9 k samples/s) - one 45 MB all-reduce over NVSwitch takes ~0.3 ms of a 7 ms
     step, so there is nothing to hide and the per-parameter hooks cost more than they save.  The flat exchange is therefore
-    the default; pass bucket_mb=8 for models whose gradient exchange is a larger share of the step."""
+    the default; pass bucket_mb=8 for models whose gradient exchange is a larger share of the step.
+
+    Native step (`native=True`, the default on CUDA).  A batch of 128 blocks is ~650 tiny launches in eager PyTorch and the
+    step is bound by the host issuing them, not by the GPU.  The native step therefore (i) keeps parameters, gradients and
+    both AdamW moments in one flat fp32 buffer each (same layout; `p.data` becomes a view) and updates ALL parameters with
+    one `av1p_adamw_flat` launch per contiguous range of parameters that received a gradient (the averaging `1 / world` is
+    folded into it; a parameter without gradient - the unused temperature - is skipped exactly like torch.optim.AdamW skips
+    it), (ii) evaluates the focal loss and its gradient in one launch (`av1p_focal_loss_binary`), and (iii) with
+    `graph=True` (default when native) records zero-grad + forward + loss + backward once into a CUDA graph after
+    `graph_warmup` eager steps and replays it afterwards: per step the host then issues two input copies, one graph launch,
+    the all-reduce and the update.  The all-reduce stays outside the graph (one eager NCCL call on the flat buffer).  The
+    convolutions' forward / backward themselves remain cuDNN kernels - training is not the product path of this package.
+    `native=False` keeps the plain PyTorch step (torch.optim.AdamW), which is also the only one available on the CPU."""
 
     def __init__(self, model, device, lr: float = 1e-3, weight_decay: float = 1e-4, alpha: float = 0.25, gamma: float = 2.5,
-                 dropout_p: float = 0.3, autocast_bf16: Optional[bool] = None, group=None, bucket_mb: float = 0.0):
+                 dropout_p: float = 0.3, autocast_bf16: Optional[bool] = None, group=None, bucket_mb: float = 0.0,
+                 native: Optional[bool] = None, graph: Optional[bool] = None, graph_warmup: int = 3,
+                 betas=(0.9, 0.999), eps: float = 1e-8):
         self.model = model.to(device)
         self.device = torch.device(device)
         self.group = group
         self.alpha, self.gamma, self.dropout_p = alpha, gamma, dropout_p
+        self.lr, self.weight_decay, self.betas, self.eps = float(lr), float(weight_decay), (float(betas[0]), float(betas[1])), float(eps)
         self.autocast_bf16 = (self.device.type == "cuda") if autocast_bf16 is None else autocast_bf16
+        self.native = (self.device.type == "cuda") if native is None else bool(native)
+        if self.native and self.device.type != "cuda":
+            raise RuntimeError("the native training step needs a CUDA device (libav1p has no CPU path); pass native=False")
+        self.use_graph = self.native if graph is None else bool(graph)
+        if self.use_graph and not self.native:
+            raise ValueError("graph=True needs native=True (torch.optim.AdamW's host-side step count cannot be captured)")
+        if self.use_graph and bucket_mb and bucket_mb > 0:
+            raise ValueError("graph=True replays backward without its Python hooks: use bucket_mb=0 (one flat all-reduce)")
+        self.graph_warmup = max(int(graph_warmup), 1)
         # parameters (trainable, the reference's AdamW covers model.parameters() incl. the unused temperature) + buffers
         self.named_params = [(k, v) for k, v in model.named_parameters()]
         self.sd = {k: v for k, v in model.named_parameters()}
         self.sd.update({k: v for k, v in model.named_buffers()})
         self.params = [v for _, v in self.named_params]
-        self.optimizer = torch.optim.AdamW(self.params, lr=lr, weight_decay=weight_decay)
+        self._buffers = [v for _, v in model.named_buffers()]
         n = sum(p.numel() for p in self.params)
         self.flat_grad = torch.zeros(n, dtype=torch.float32, device=self.device)      # 11,345,444 fp32 = 45.4 MB
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
-        # gradient views + buckets.  Layout of the flat buffer = REVERSE parameter order, so that a bucket is a contiguous
-        # range filled front to back while backward walks the network from the head to conv1.
+        # Layout of the flat buffers = REVERSE parameter order, so that a bucket is a contiguous range filled front to back
+        # while backward walks the network from the head to conv1; the three tensors whose size is not a multiple of four
+        # (two scalars and the 2x7x7 attention filter) go last, which keeps every other view 16-byte aligned.
+        self.layout = sorted(reversed(self.params), key=lambda p: p.numel() % 4 != 0)
         self.grad_views = {}
+        self._offset = {}
         self.buckets = []                        # [start, end, n_params] per bucket
         self._bucket_of = {}
         cap = int(bucket_mb * (1 << 20) / 4) if bucket_mb and bucket_mb > 0 else n
         off, start, count = 0, 0, 0
-        for p in reversed(self.params):
+        for p in self.layout:
             self.grad_views[p] = self.flat_grad[off:off + p.numel()].view_as(p)
+            self._offset[p] = off
             self._bucket_of[p] = len(self.buckets)
             off += p.numel()
             count += 1
@@ -119,6 +192,24 @@ class Stage1DataParallelTrainer:
         self._launched = [False] * len(self.buckets)
         self._works = []
         self._touched = set()
+        self._capturing = False
+        if self.native:
+            self.flat_param = torch.empty(n, dtype=torch.float32, device=self.device)
+            with torch.no_grad():
+                for p in self.layout:
+                    view = self.flat_param[self._offset[p]:self._offset[p] + p.numel()].view_as(p)
+                    view.copy_(p.data)
+                    p.data = view                # same Parameter objects, same state_dict keys; the storage is the flat buffer
+            self.flat_exp_avg = torch.zeros_like(self.flat_param)
+            self.flat_exp_avg_sq = torch.zeros_like(self.flat_param)
+            self.step_dev = torch.zeros(1, dtype=torch.int32, device=self.device)
+            self.optimizer = None
+            self._segments = None                # [(start, end)] ranges of the flat buffers that received gradients
+            self._segments_for = None
+            self._graphs = {}                    # (batch shape) -> [graph, static images, static labels, static loss]
+            self._steps_done = 0
+        else:
+            self.optimizer = torch.optim.AdamW(self.params, lr=lr, weight_decay=weight_decay, betas=betas, eps=eps)
         for p in self.params:
             p.register_post_accumulate_grad_hook(self._on_grad)
 
@@ -131,6 +222,8 @@ class Stage1DataParallelTrainer:
 
     def _on_grad(self, p: torch.Tensor) -> None:
         self._touched.add(p)
+        if self._capturing:                      # a collective must not be recorded into the step graph
+            return
         b = self._bucket_of[p]
         self._pending[b] -= 1
         # buckets go out in index order on every rank (a collective sequence must be identical everywhere): bucket b is
@@ -140,11 +233,17 @@ class Stage1DataParallelTrainer:
             b += 1
 
     def forward(self, images: torch.Tensor, training: bool = True) -> torch.Tensor:
-        with torch.autocast(self.device.type, dtype=torch.bfloat16, enabled=self.autocast_bf16):
+        # weight casts are not cached when the step is recorded into a graph (a cached cast would outlive the capture)
+        with torch.autocast(self.device.type, dtype=torch.bfloat16, enabled=self.autocast_bf16, cache_enabled=not self._capturing):
             return stage1_forward_torch(self.sd, images, training, self.dropout_p)
 
-    def step(self, images: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
-        """003:64-73 on this rank's batch, with the gradient averaged over the ranks.  Returns the local loss (detached)."""
+    def _loss(self, logits: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+        if self.native:
+            return focal_loss_binary_native(logits, labels, self.alpha, self.gamma)
+        return focal_loss_binary(logits, labels, self.alpha, self.gamma)
+
+    def _forward_backward(self, images: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+        """003:66-71: zero_grad, forward in train mode, loss, backward (gradients land in the flat buffer)."""
         self.flat_grad.zero_()                                 # optimizer.zero_grad() in one memset
         for p in self.params:
             p.grad = self.grad_views[p]
@@ -152,29 +251,120 @@ class Stage1DataParallelTrainer:
         self._launched = [False] * len(self.buckets)
         self._works.clear()
         self._touched.clear()
-        logits = self.forward(images.to(self.device, non_blocking=True), training=True)
-        loss = focal_loss_binary(logits, labels.to(self.device, non_blocking=True), self.alpha, self.gamma)
+        loss = self._loss(self.forward(images, training=True), labels)
         loss.backward()                                        # hooks launch the bucket all-reduces as gradients arrive
+        return loss.detach()
+
+    def _exchange(self) -> None:
         for b in range(len(self.buckets)):                     # buckets holding a parameter that got no gradient (zeros)
             if not self._launched[b]:
                 self._launch_bucket(b)
         for w in self._works:
             w.wait()
-        if self.world > 1:
-            self.flat_grad.div_(self.world)
-        for p in self.params:                                  # a parameter outside the graph (the unused temperature) keeps
-            if p not in self._touched:                         # grad None, so AdamW skips it exactly as the reference's does
+        self._works.clear()
+
+    def _grad_segments(self):
+        """Contiguous ranges of the flat buffers whose parameters received a gradient (recomputed when that set changes)."""
+        key = frozenset(id(p) for p in self._touched)
+        if self._segments is None or self._segments_for != key:
+            segs = []
+            for p in self.layout:
+                if p in self._touched:
+                    lo, hi = self._offset[p], self._offset[p] + p.numel()
+                    if segs and segs[-1][1] == lo:
+                        segs[-1][1] = hi
+                    else:
+                        segs.append([lo, hi])
+            self._segments, self._segments_for = [tuple(s) for s in segs], key
+        return self._segments
+
+    def _update(self) -> None:
+        """003:73 optimizer.step() on the averaged gradient."""
+        if not self.native:
+            if self.world > 1:
+                self.flat_grad.div_(self.world)
+            for p in self.params:                              # a parameter outside the graph (the unused temperature) keeps
+                if p not in self._touched:                     # grad None, so AdamW skips it exactly as the reference's does
+                    p.grad = None
+            self.optimizer.step()
+            return
+        from . import _native as N
+        lib, st = N.lib(), N.stream_handle(self.device)
+        b = self.flat_param.data_ptr(), self.flat_grad.data_ptr(), self.flat_exp_avg.data_ptr(), self.flat_exp_avg_sq.data_ptr()
+        for i, (lo, hi) in enumerate(self._grad_segments()):
+            N.check(lib.av1p_adamw_flat(b[0] + 4 * lo, b[1] + 4 * lo, b[2] + 4 * lo, b[3] + 4 * lo, hi - lo, self.lr, self.betas[0],
+                                        self.betas[1], self.eps, self.weight_decay, 1.0 / self.world, N.ptr(self.step_dev),
+                                        1 if i == 0 else 0, st))
+        for p in self.params:
+            if p not in self._touched:
                 p.grad = None
-        self.optimizer.step()
-        return loss.detach()
+        # the kernel wrote through raw pointers: tell autograd (and the inference path's weight fingerprint, models._param_key)
+        # (a replayed graph does not bump the BatchNorm running statistics' version counters either)
+        torch.autograd.graph.increment_version(self.params + self._buffers)
+
+    def _graph_step(self, images: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+        key = (tuple(images.shape), images.dtype, tuple(labels.shape), labels.dtype)
+        entry = self._graphs.get(key)
+        if entry is None:
+            static_x, static_y = torch.empty_like(images), torch.empty_like(labels)
+            static_x.copy_(images)
+            static_y.copy_(labels)
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            touched_before = set(self._touched)
+            self._capturing = True
+            try:
+                # thread_local: the NCCL watchdog thread of a multi-rank job may call into CUDA while this thread records
+                with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                    static_loss = self._forward_backward(static_x, static_y)
+            finally:
+                self._capturing = False
+            if touched_before and self._touched != touched_before:
+                raise RuntimeError("the set of parameters that receive gradients changed between the eager steps and the capture")
+            entry = [g, static_x, static_y, static_loss]
+            self._graphs[key] = entry
+        else:
+            entry[1].copy_(images, non_blocking=True)
+            entry[2].copy_(labels, non_blocking=True)
+        entry[0].replay()
+        self._launched = [False] * len(self.buckets)           # the replayed backward launched no collective
+        return entry[3].clone()
+
+    def step(self, images: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+        """003:64-73 on this rank's batch, with the gradient averaged over the ranks.  Returns the local loss (detached)."""
+        images = images.to(self.device, non_blocking=True)
+        labels = labels.to(self.device, non_blocking=True)
+        if self.native and self.use_graph and self._steps_done >= self.graph_warmup:
+            loss = self._graph_step(images, labels)
+        else:
+            loss = self._forward_backward(images, labels)
+        self._exchange()
+        self._update()
+        if self.native:
+            self._steps_done += 1
+        return loss
 
     def gradient_vector(self) -> torch.Tensor:
-        """The (averaged) gradients of the last step in PARAMETER order (the flat buffer itself is laid out in reverse
+        """The (averaged, on the plain PyTorch path; summed over the ranks on the native path, which folds the 1 / world
+        into the update) gradients of the last step in PARAMETER order (the flat buffer itself is laid out in reverse
         parameter order, the order backward fills it)."""
         return torch.cat([self.grad_views[p].reshape(-1) for p in self.params])
 
     def allreduce_bytes(self) -> int:
         return self.flat_grad.numel() * self.flat_grad.element_size()
+
+    def optimizer_state(self) -> Dict[str, torch.Tensor]:
+        """AdamW state in PARAMETER order ('step', 'exp_avg', 'exp_avg_sq' as flat vectors) for checkpoints / tests."""
+        if self.native:
+            def gather(flat):
+                return torch.cat([flat[self._offset[p]:self._offset[p] + p.numel()] for p in self.params])
+            return {"step": self.step_dev.clone(), "exp_avg": gather(self.flat_exp_avg), "exp_avg_sq": gather(self.flat_exp_avg_sq)}
+        st = self.optimizer.state
+        z = lambda p: torch.zeros(p.numel(), dtype=torch.float32, device=self.device)
+        steps = [int(st[p]["step"]) for p in self.params if p in st and "step" in st[p]]
+        return {"step": torch.tensor([max(steps) if steps else 0], dtype=torch.int32),
+                "exp_avg": torch.cat([st[p]["exp_avg"].reshape(-1) if p in st and "exp_avg" in st[p] else z(p) for p in self.params]),
+                "exp_avg_sq": torch.cat([st[p]["exp_avg_sq"].reshape(-1) if p in st and "exp_avg_sq" in st[p] else z(p) for p in self.params])}
 
 
 def synthetic_labelled_blocks(n: int, seed: int, positive_rate: float = 0.42, device=None):

@@ -242,6 +242,23 @@ typedef struct av1p_conv_res_desc {
 } av1p_conv_res_desc;
 int av1p_conv_res_forward(const av1p_conv_res_desc* d, void* stream);
 
+/* ---- Stage-1 training step (BASELINE configs[4]): the two non-convolution pieces as single launches.
+ *      av1p_focal_loss_binary replaces FocalLoss.forward's binary branch + mean (pesquisa_v6/v6_pipeline/losses.py:29-38,
+ *      48-49) AND its autograd backward: *loss_dev = mean_i a_t (1 - pt)^gamma bce_i, dlogits_dev[i] = d loss / d logit_i
+ *      (dlogits_dev may be NULL).  logits float32 [n], targets int64 [n] in {0, 1}.
+ *      av1p_adamw_flat replaces optimizer.step() of torch.optim.AdamW(lr, weight_decay)
+ *      (pesquisa_v6/scripts/003_train_stage1_improved.py:73, 250-254; betas / eps are torch's defaults there) for ALL
+ *      parameters at once: param / grad / exp_avg / exp_avg_sq are flat float32 arrays of n elements (same address modulo 16),
+ *      grad is multiplied by grad_scale first (1 / world size after a summing all-reduce); *step_dev is the device-side
+ *      step counter: incremented by this call when advance_step != 0 (the first segment of a step; parameters that got
+ *      no gradient are skipped like torch does, so a step may update several ranges), then used for the bias corrections -
+ *      a captured CUDA graph of the step therefore replays correctly. */
+int av1p_focal_loss_binary(const float* logits_dev, const int64_t* targets_dev, int32_t n, float alpha, float gamma,
+                           float* loss_dev, float* dlogits_dev, void* stream);
+int av1p_adamw_flat(float* param_dev, const float* grad_dev, float* exp_avg_dev, float* exp_avg_sq_dev, int64_t n, double lr,
+                    double beta1, double beta2, double eps, double weight_decay, double grad_scale, int32_t* step_dev, int32_t advance_step,
+                    void* stream);
+
 #ifdef __cplusplus
 }
 #endif

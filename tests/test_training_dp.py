@@ -9,8 +9,8 @@ import torch
 
 from cnn_av1_research_b200 import synth
 from cnn_av1_research_b200.models import Stage1Model
-from cnn_av1_research_b200.training import (Stage1DataParallelTrainer, focal_loss_binary, stage1_forward_torch,
-                                            synthetic_labelled_blocks)
+from cnn_av1_research_b200.training import (Stage1DataParallelTrainer, focal_loss_binary, focal_loss_binary_grad,
+                                            focal_loss_binary_native, stage1_forward_torch, synthetic_labelled_blocks)
 from oracle import cascade_oracle as O
 
 
@@ -76,6 +76,28 @@ def test_focal_loss_formula():
     assert torch.allclose(focal_loss_binary(x, y), exp, atol=1e-7)
 
 
+def test_focal_loss_closed_form_gradient_equals_autograd():
+    """The gradient formula the device kernel evaluates (csrc/train_kernels.cuh), restated on the host, against autograd
+    through the reference's formula (losses.py:29-38) - including saturated logits on both sides."""
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(300, 1, generator=g) * 5
+    x[0], x[1], x[2], x[3] = 60.0, -60.0, 0.0, -0.0
+    y = (torch.rand(300, generator=g) < 0.42).long()
+    for alpha, gamma in ((0.25, 2.5), (0.25, 2.0), (0.5, 0.0), (0.9, 1.0)):
+        xa = x.clone().requires_grad_(True)
+        focal_loss_binary(xa, y, alpha, gamma).backward()
+        got = focal_loss_binary_grad(x, y, alpha, gamma)
+        assert got.shape == x.shape
+        assert (got - xa.grad).abs().max() <= 1e-7 + 1e-5 * xa.grad.abs().max()
+
+
+def test_native_step_refuses_the_cpu():
+    with pytest.raises(RuntimeError, match="CUDA"):
+        Stage1DataParallelTrainer(_model(), "cpu", native=True)
+    with pytest.raises(ValueError, match="native"):
+        Stage1DataParallelTrainer(_model(), "cpu", native=False, graph=True)
+
+
 def test_bucketed_exchange_equals_single_flat_allreduce():
     """The bucketed, backward-overlapped gradient exchange is a re-ordering of the same work: same parameters after two
     steps as the single flat all-reduce (bucket_mb = 0), the unused temperature keeps grad None (AdamW skips it, as the
@@ -93,8 +115,13 @@ def test_bucketed_exchange_equals_single_flat_allreduce():
     assert len(one.buckets) == 1 and len(many.buckets) >= 6
     assert many.buckets[0][0] == 0 and many.buckets[-1][1] == many.flat_grad.numel()
     assert all(a[1] == b[0] for a, b in zip(many.buckets, many.buckets[1:]))        # contiguous cover
-    # the first bucket holds the LAST parameters (head), i.e. what backward produces first
-    assert many._bucket_of[many.params[-1]] == 0 and many._bucket_of[many.params[0]] == len(many.buckets) - 1
+    # the first bucket holds the LAST parameters (head), i.e. what backward produces first; the three tensors whose size is
+    # not a multiple of four close the buffer so that every other view stays 16-byte aligned
+    names = dict((id(v), k) for k, v in many.named_params)
+    assert names[id(many.layout[0])] == "head.head.3.weight" and many._bucket_of[many.layout[0]] == 0
+    assert [names[id(q)] for q in many.layout[-3:]] == ["head.head.3.bias", "head.temperature", "backbone.spatial_attn.conv.weight"]
+    assert all(many._offset[q] % 4 == 0 for q in many.layout[:-3])
+    assert many._bucket_of[many.params[0]] == len(many.buckets) - 1
     assert dict(many.named_params)["head.temperature"].grad is None
     assert dict(many.named_params)["head.temperature"].item() == 1.5
 
@@ -161,3 +188,105 @@ def test_gpu_bf16_training_step_reduces_the_loss(cuda_device):
     # the trained parameters still drive the inference path (same state_dict keys)
     tr.model.eval()
     assert tr.model(x[:4]).shape == (4, 1)
+
+
+@pytest.mark.gpu
+def test_gpu_focal_loss_kernel_matches_the_reference_formula(cuda_device):
+    """av1p_focal_loss_binary: loss and d loss / d logits in one launch vs autograd through losses.py:29-38 (fp32; tolerance
+    1e-6 absolute on a loss of ~0.05 / gradients of ~1e-3: different but equivalent evaluation orders of exp / log)."""
+    g = torch.Generator().manual_seed(3)
+    for n in (1, 128, 1000, 5000):
+        x = (torch.randn(n, 1, generator=g) * 4).to(cuda_device)
+        if n >= 4:
+            x[0], x[1], x[2] = 50.0, -50.0, 0.0
+        y = (torch.rand(n, generator=g) < 0.42).long().to(cuda_device)
+        for alpha, gamma in ((0.25, 2.5), (0.25, 2.0), (0.75, 0.0)):
+            xa = x.clone().requires_grad_(True)
+            ref = focal_loss_binary(xa, y, alpha, gamma)
+            ref.backward()
+            xb = x.clone().requires_grad_(True)
+            got = focal_loss_binary_native(xb, y, alpha, gamma)
+            (got * 3.0).backward()                       # the upstream gradient is applied
+            assert abs(float(got.detach()) - float(ref.detach())) <= 1e-6 + 1e-5 * abs(float(ref.detach()))
+            assert (xb.grad / 3.0 - xa.grad).abs().max().item() <= 1e-7 + 2e-5 * xa.grad.abs().max().item()
+    # bitwise run-to-run reproducibility (fixed-order reduction)
+    a = focal_loss_binary_native(x, y)
+    b = focal_loss_binary_native(x, y)
+    assert torch.equal(a, b)
+
+
+@pytest.mark.gpu
+def test_gpu_adamw_flat_kernel_matches_torch_adamw(cuda_device):
+    """av1p_adamw_flat over a range that starts and ends off a 16-byte boundary, three steps, against torch.optim.AdamW on the
+    same numbers (fp32 tolerance: the two evaluate the same formula with different fused-multiply-add contraction); elements
+    outside the range are untouched; grad_scale averages."""
+    from cnn_av1_research_b200 import _native as N
+    g = torch.Generator().manual_seed(11)
+    n_all, lo, hi = 100_003, 5, 100_000
+    p0 = torch.randn(n_all, generator=g)
+    flat_p = p0.clone().to(cuda_device)
+    flat_m, flat_v = torch.zeros_like(flat_p), torch.zeros_like(flat_p)
+    step = torch.zeros(1, dtype=torch.int32, device=cuda_device)
+    ref_p = torch.nn.Parameter(p0[lo:hi].clone().to(cuda_device))
+    opt = torch.optim.AdamW([ref_p], lr=1e-3, weight_decay=1e-2)
+    world = 4
+    for it in range(3):
+        grad = (torch.randn(n_all, generator=g) * 10 ** (it - 2)).to(cuda_device)
+        ref_p.grad = grad[lo:hi] / world
+        opt.step()
+        N.check(N.lib().av1p_adamw_flat(flat_p.data_ptr() + 4 * lo, grad.data_ptr() + 4 * lo, flat_m.data_ptr() + 4 * lo,
+                                        flat_v.data_ptr() + 4 * lo, hi - lo, 1e-3, 0.9, 0.999, 1e-8, 1e-2, 1.0 / world, N.ptr(step), 1,
+                                        N.stream_handle(flat_p.device)))
+    torch.cuda.synchronize()
+    assert int(step.item()) == 3
+    assert torch.equal(flat_p[:lo].cpu(), p0[:lo]) and torch.equal(flat_p[hi:].cpu(), p0[hi:])
+    diff = (flat_p[lo:hi] - ref_p.detach()).abs().max().item()
+    assert diff <= 2e-6, diff
+    st = opt.state[ref_p]
+    assert (flat_m[lo:hi] - st["exp_avg"]).abs().max().item() <= 2e-6 * st["exp_avg"].abs().max().item()
+    assert (flat_v[lo:hi] - st["exp_avg_sq"]).abs().max().item() <= 2e-6 * st["exp_avg_sq"].abs().max().item()
+    # mismatched alignment of the four buffers is refused, not mis-computed
+    rc = N.lib().av1p_adamw_flat(flat_p.data_ptr() + 4, grad.data_ptr(), flat_m.data_ptr(), flat_v.data_ptr(), 16, 1e-3, 0.9, 0.999,
+                                 1e-8, 0.0, 1.0, N.ptr(step), 0, N.stream_handle(flat_p.device))
+    assert rc == -1
+
+
+@pytest.mark.gpu
+def test_gpu_native_and_graph_steps_follow_the_plain_pytorch_step(cuda_device):
+    """Same initial weights, same batches, no dropout, fp32: the plain PyTorch step (torch.optim.AdamW), the native eager step
+    and the native step replayed from a CUDA graph follow one trajectory.  Not bitwise: cuDNN's backward kernels are not
+    run-to-run deterministic and Adam's first updates are ~lr * sign(g), so individual weights may differ by a few lr;
+    the bulk must agree closely, the loss curves must coincide at first, and the unused temperature must stay untouched."""
+    batches = [synthetic_labelled_blocks(128, 40 + i, device=cuda_device) for i in range(3)]
+    runs = {}
+    for mode, kw in (("torch", dict(native=False)), ("native", dict(native=True, graph=False)),
+                     ("graph", dict(native=True, graph=True, graph_warmup=2))):
+        tr = Stage1DataParallelTrainer(_model(), cuda_device, dropout_p=0.0, autocast_bf16=False, **kw)
+        losses = [float(tr.step(*batches[i % 3])) for i in range(6)]
+        runs[mode] = (torch.cat([p.detach().reshape(-1) for p in tr.params]).cpu(), losses, tr)
+    ref_p, ref_l, _ = runs["torch"]
+    for mode in ("native", "graph"):
+        p, l, tr = runs[mode]
+        d = (p - ref_p).abs()
+        assert d.median().item() <= 1e-5 and d.max().item() <= 6 * 2e-3, (mode, d.median().item(), d.max().item())
+        # lr 1e-3 on these weights is a rough ride (the loss jumps 0.28 -> 1.95 -> 1.08 -> 0.35), so rounding-level differences
+        # grow: the first steps must agree closely, the later ones only stay on the same curve
+        assert l[0] == ref_l[0] and np.allclose(l[:3], ref_l[:3], rtol=2e-2) and np.allclose(l, ref_l, rtol=0.35), (mode, l, ref_l)
+        named = dict(tr.named_params)
+        assert named["head.temperature"].grad is None and named["head.temperature"].item() == 1.5
+        assert int(tr.step_dev.item()) == 6
+        assert len(tr._grad_segments()) == 2                         # everything but the temperature, which sits near the end
+    assert len(runs["graph"][2]._graphs) == 1
+    # the parameters are views of the flat buffer and the inference path notices the in-place updates
+    tr = runs["graph"][2]
+    assert all(p.data_ptr() == tr.flat_param.data_ptr() + 4 * tr._offset[p] for p in tr.params)
+    tr.model.eval()
+    x = batches[0][0][:8]
+    before = tr.model(x).clone()
+    tr.step(*batches[0])
+    after = tr.model(x)
+    assert not torch.equal(before, after)
+    sd = {k: v.detach().cpu() for k, v in tr.model.state_dict().items()}
+    with torch.no_grad():
+        want = stage1_forward_torch({k: v.to(cuda_device) for k, v in sd.items()}, x, training=False)
+    assert (after - want).abs().max().item() <= 5e-3

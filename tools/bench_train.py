@@ -5,7 +5,8 @@
 
 One process per GPU, NCCL; per-GPU batch 128 (reference default, 003:139) of synthetic labelled blocks, bf16 autocast
 forward/backward in PyTorch, the 11,345,444 fp32 gradients all-reduced in one flat buffer after backward (default) or in
-~8 MB buckets overlapped with backward (--bucket-mb 8), AdamW.  Weak scaling;
+~8 MB buckets overlapped with backward (--bucket-mb 8), AdamW.  --mode graph (default) replays the step from a CUDA graph
+with the native loss / AdamW kernels, --mode native launches them eagerly, --mode torch is the plain PyTorch step.  Weak scaling;
 CUDA-event time, max over ranks.  Prints one JSON line on rank 0.
 """
 import argparse
@@ -26,6 +27,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--batch", type=int, default=128)
+    ap.add_argument("--mode", choices=("graph", "native", "torch"), default="graph",
+                    help="graph: native loss / AdamW kernels + the step replayed from a CUDA graph (default); native: the same kernels, "
+                         "eager launches; torch: plain PyTorch step with torch.optim.AdamW (round-1 path)")
     ap.add_argument("--bucket-mb", type=float, default=0.0, help="gradient bucket size in MB (overlapped with backward); 0 = one flat all-reduce after backward (default: measured faster)")
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
@@ -38,9 +42,9 @@ def main():
     from cnn_av1_research_b200.training import Stage1DataParallelTrainer, synthetic_labelled_blocks
     model = Stage1Model(pretrained=False)
     model.load_state_dict(synth.calibrated_state_dict("stage1", 0), strict=True)
-    tr = Stage1DataParallelTrainer(model, dev, bucket_mb=args.bucket_mb)
+    tr = Stage1DataParallelTrainer(model, dev, bucket_mb=args.bucket_mb, native=args.mode != "torch", graph=args.mode == "graph")
     batches = [synthetic_labelled_blocks(args.batch, 1000 * rank + i, device=dev) for i in range(4)]
-    for i in range(args.warmup):
+    for i in range(max(args.warmup, 5 if args.mode == "graph" else 0)):      # the graph is recorded at the 4th step
         tr.step(*batches[i % 4])
     torch.cuda.synchronize(dev)
     if world > 1:
@@ -66,7 +70,10 @@ def main():
     if rank == 0:
         print(json.dumps({"metric": "stage1_dp_training_samples_per_sec", "value": args.batch * world / (ms.item() * 1e-3), "unit": "samples/s",
                           "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms.item(), "scaling": "weak",
-                          "dtype": "bf16 autocast (PyTorch fwd/bwd), fp32 gradient all-reduce", "data": "synthetic",
+                          "dtype": "bf16 autocast (PyTorch fwd/bwd), fp32 gradient all-reduce", "data": "synthetic", "mode": args.mode,
+                          "step": {"graph": "libav1p focal-loss + flat AdamW kernels, zero-grad + forward + loss + backward replayed from one CUDA graph",
+                                   "native": "libav1p focal-loss + flat AdamW kernels, eager launches",
+                                   "torch": "plain PyTorch ops + torch.optim.AdamW"}[args.mode],
                           "config": {"workload": "Stage1 data-parallel training step (BASELINE configs[4])", "per_gpu_batch": args.batch,
                                      "allreduce_bytes_per_step": tr.allreduce_bytes(),
                                      "gradient_exchange": (f"{len(tr.buckets)} buckets of ~{args.bucket_mb:g} MB in backward order, async all-reduce "
