@@ -271,7 +271,7 @@ def test_gpu_native_and_graph_steps_follow_the_plain_pytorch_step(cuda_device):
         assert d.median().item() <= 1e-5 and d.max().item() <= 6 * 2e-3, (mode, d.median().item(), d.max().item())
         # lr 1e-3 on these weights is a rough ride (the loss jumps 0.28 -> 1.95 -> 1.08 -> 0.35), so rounding-level differences
         # grow: the first steps must agree closely, the later ones only stay on the same curve
-        assert l[0] == ref_l[0] and np.allclose(l[:3], ref_l[:3], rtol=2e-2) and np.allclose(l, ref_l, rtol=0.35), (mode, l, ref_l)
+        assert np.isclose(l[0], ref_l[0], rtol=1e-5) and np.allclose(l[:3], ref_l[:3], rtol=2e-2) and np.allclose(l, ref_l, rtol=0.35), (mode, l, ref_l)
         named = dict(tr.named_params)
         assert named["head.temperature"].grad is None and named["head.temperature"].item() == 1.5
         assert int(tr.step_dev.item()) == 6
