@@ -1,5 +1,8 @@
 """B200-native AV1 partition-prediction cascade (drop-in for the v6 inference path of
 chiarorosa/cnn-av1-research).  See DESIGN.md and INTEGRATION.md at the repository root."""
+from .data_hub import (FlattenEvalDataset, HierarchicalBlockDatasetV6, build_hierarchical_dataset_v6, compute_pipeline_metrics,
+                       load_pipeline, load_stage1_model, load_stage2_flat_model, map_to_stage1_v6, map_to_stage2_v6,
+                       map_to_stage3_v6, record_from_dataset_file)
 from .ensemble import ABEnsemble, WeightedEnsemble
 from .extraction import (BlockRecord, TorchBlockRecord, calculate_yuv420_10bit_sizes, extract_blocks_device,
                          extract_blocks_with_validation, extract_frames_device)
@@ -22,5 +25,7 @@ __all__ = [
     "Stage2FlatModel", "FlattenPipeline", "run_pipeline_inference", "remap_flatten_to_original",
     "evaluate_with_threshold", "sweep_thresholds", "read_y_component_10bit_lossless", "read_frames_yuv420p10",
     "predict_yuv_file", "save_blocks_binary_10bit", "load_block_file", "ABEnsemble", "WeightedEnsemble", "AdapterModule", "extract_frames_device",
-    "Stage2ModelWithAdapters", "compute_metrics", "filter_dataset_through_stage1",
+    "Stage2ModelWithAdapters", "compute_metrics", "filter_dataset_through_stage1", "HierarchicalBlockDatasetV6",
+    "FlattenEvalDataset", "build_hierarchical_dataset_v6", "compute_pipeline_metrics", "load_pipeline", "load_stage1_model",
+    "load_stage2_flat_model", "map_to_stage1_v6", "map_to_stage2_v6", "map_to_stage3_v6", "record_from_dataset_file",
 ]
