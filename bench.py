@@ -363,6 +363,32 @@ def configs_leg(pipe, dev, log):
     out["predict_b256_reference_api"] = {"b200_ms_median": float(np.median(ts)) * 1e3, "b200_ms_min": float(np.min(ts)) * 1e3,
                                          "b200_blocks_per_sec": 256 / float(np.median(ts)),
                                          "label_agreement_vs_oracle": float((lab256 == ref256).float().mean())}
+    # (5, single-GPU share) Stage-1 training step at the reference's per-GPU batch of 128 (003:139): the native step
+    # (libav1p focal-loss / flat AdamW kernels, the step replayed from a CUDA graph) next to the plain PyTorch step;
+    # the data-parallel runs at 2 / 8 GPUs are tools/bench_train.py (profiles/r02_train_n*_mode_*.json)
+    try:
+        from cnn_av1_research_b200.models import Stage1Model
+        from cnn_av1_research_b200.training import Stage1DataParallelTrainer, synthetic_labelled_blocks
+        batches = [synthetic_labelled_blocks(128, 7000 + i, device=dev) for i in range(4)]
+        train = {}
+        for mode, kw in (("graph", dict(native=True, graph=True)), ("torch", dict(native=False))):
+            model = Stage1Model(pretrained=False)
+            model.load_state_dict(synth.calibrated_state_dict("stage1", 0), strict=True)
+            tr = Stage1DataParallelTrainer(model, dev, **kw)
+            for i in range(6):
+                tr.step(*batches[i % 4])
+            it = [0]
+
+            def one():
+                tr.step(*batches[it[0] % 4])
+                it[0] += 1
+            train[mode + "_ms_per_step"] = gpu_ms(one, reps=30, warm=2)
+            del tr, model
+        train["samples_per_sec"] = 128 / train["graph_ms_per_step"] * 1e3
+        train["per_gpu_batch"] = 128
+        out["config5_stage1_train_step_1gpu"] = train
+    except Exception as exc:                                  # never let the side leg take the headline down
+        out["config5_stage1_train_step_1gpu"] = {"unavailable": f"{type(exc).__name__}: {exc}"}
     log(f"[configs] {json.dumps(out)}")
     return out
 

@@ -287,6 +287,6 @@ def test_gpu_native_and_graph_steps_follow_the_plain_pytorch_step(cuda_device):
     after = tr.model(x)
     assert not torch.equal(before, after)
     sd = {k: v.detach().cpu() for k, v in tr.model.state_dict().items()}
-    with torch.no_grad():
-        want = stage1_forward_torch({k: v.to(cuda_device) for k, v in sd.items()}, x, training=False)
-    assert (after - want).abs().max().item() <= 5e-3
+    with torch.no_grad():                                 # fp32 on the CPU (cuDNN's default TF32 convolutions are ~1e-2 off on these logits)
+        want = stage1_forward_torch(sd, x.cpu(), training=False)
+    assert (after.cpu() - want).abs().max().item() <= 5e-3
