@@ -142,7 +142,7 @@ class Stage1DataParallelTrainer:
     def __init__(self, model, device, lr: float = 1e-3, weight_decay: float = 1e-4, alpha: float = 0.25, gamma: float = 2.5,
                  dropout_p: float = 0.3, autocast_bf16: Optional[bool] = None, group=None, bucket_mb: float = 0.0,
                  native: Optional[bool] = None, graph: Optional[bool] = None, graph_warmup: int = 3,
-                 betas=(0.9, 0.999), eps: float = 1e-8):
+                 betas=(0.9, 0.999), eps: float = 1e-8, channels_last: Optional[bool] = None):
         self.model = model.to(device)
         self.device = torch.device(device)
         self.group = group
@@ -158,6 +158,12 @@ class Stage1DataParallelTrainer:
         if self.use_graph and bucket_mb and bucket_mb > 0:
             raise ValueError("graph=True replays backward without its Python hooks: use bucket_mb=0 (one flat all-reduce)")
         self.graph_warmup = max(int(graph_warmup), 1)
+        # channels_last (native step only): the 4-D weights - and their gradient / moment slots - are laid out [O][H][W][I] inside
+        # the flat buffers and the activations run NHWC, so cuDNN's tensor-core kernels need no layout-conversion launches
+        # around every convolution (forward, dgrad and wgrad); logical shapes, state_dict keys and values are unchanged
+        self.channels_last = self.native if channels_last is None else bool(channels_last)
+        if self.channels_last and not self.native:
+            raise ValueError("channels_last=True is part of the native step (flat parameter buffer); pass native=True")
         # parameters (trainable, the reference's AdamW covers model.parameters() incl. the unused temperature) + buffers
         self.named_params = [(k, v) for k, v in model.named_parameters()]
         self.sd = {k: v for k, v in model.named_parameters()}
@@ -178,7 +184,7 @@ class Stage1DataParallelTrainer:
         cap = int(bucket_mb * (1 << 20) / 4) if bucket_mb and bucket_mb > 0 else n
         off, start, count = 0, 0, 0
         for p in self.layout:
-            self.grad_views[p] = self.flat_grad[off:off + p.numel()].view_as(p)
+            self.grad_views[p] = self._view(self.flat_grad, off, p)
             self._offset[p] = off
             self._bucket_of[p] = len(self.buckets)
             off += p.numel()
@@ -197,7 +203,7 @@ class Stage1DataParallelTrainer:
             self.flat_param = torch.empty(n, dtype=torch.float32, device=self.device)
             with torch.no_grad():
                 for p in self.layout:
-                    view = self.flat_param[self._offset[p]:self._offset[p] + p.numel()].view_as(p)
+                    view = self._view(self.flat_param, self._offset[p], p)
                     view.copy_(p.data)
                     p.data = view                # same Parameter objects, same state_dict keys; the storage is the flat buffer
             self.flat_exp_avg = torch.zeros_like(self.flat_param)
@@ -212,6 +218,14 @@ class Stage1DataParallelTrainer:
             self.optimizer = torch.optim.AdamW(self.params, lr=lr, weight_decay=weight_decay, betas=betas, eps=eps)
         for p in self.params:
             p.register_post_accumulate_grad_hook(self._on_grad)
+
+    def _view(self, flat: torch.Tensor, off: int, p: torch.Tensor) -> torch.Tensor:
+        """The slot of parameter `p` inside a flat buffer, shaped like `p` (4-D weights in channels_last order if enabled)."""
+        piece = flat[off:off + p.numel()]
+        if self.channels_last and p.dim() == 4:
+            o, i, h, w = p.shape
+            return piece.view(o, h, w, i).permute(0, 3, 1, 2)
+        return piece.view_as(p)
 
     # ---- gradient exchange -------------------------------------------------------------------------------------------
     def _launch_bucket(self, b: int) -> None:
@@ -234,6 +248,8 @@ class Stage1DataParallelTrainer:
 
     def forward(self, images: torch.Tensor, training: bool = True) -> torch.Tensor:
         # weight casts are not cached when the step is recorded into a graph (a cached cast would outlive the capture)
+        if self.channels_last:
+            images = images.contiguous(memory_format=torch.channels_last)
         with torch.autocast(self.device.type, dtype=torch.bfloat16, enabled=self.autocast_bf16, cache_enabled=not self._capturing):
             return stage1_forward_torch(self.sd, images, training, self.dropout_p)
 
@@ -357,7 +373,7 @@ class Stage1DataParallelTrainer:
         """AdamW state in PARAMETER order ('step', 'exp_avg', 'exp_avg_sq' as flat vectors) for checkpoints / tests."""
         if self.native:
             def gather(flat):
-                return torch.cat([flat[self._offset[p]:self._offset[p] + p.numel()] for p in self.params])
+                return torch.cat([self._view(flat, self._offset[p], p).reshape(-1) for p in self.params])
             return {"step": self.step_dev.clone(), "exp_avg": gather(self.flat_exp_avg), "exp_avg_sq": gather(self.flat_exp_avg_sq)}
         st = self.optimizer.state
         z = lambda p: torch.zeros(p.numel(), dtype=torch.float32, device=self.device)

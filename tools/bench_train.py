@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--mode", choices=("graph", "native", "torch"), default="graph",
                     help="graph: native loss / AdamW kernels + the step replayed from a CUDA graph (default); native: the same kernels, "
                          "eager launches; torch: plain PyTorch step with torch.optim.AdamW (round-1 path)")
+    ap.add_argument("--nchw", action="store_true", help="native / graph modes: keep NCHW weights and activations (default: channels_last)")
     ap.add_argument("--bucket-mb", type=float, default=0.0, help="gradient bucket size in MB (overlapped with backward); 0 = one flat all-reduce after backward (default: measured faster)")
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
@@ -42,7 +43,8 @@ def main():
     from cnn_av1_research_b200.training import Stage1DataParallelTrainer, synthetic_labelled_blocks
     model = Stage1Model(pretrained=False)
     model.load_state_dict(synth.calibrated_state_dict("stage1", 0), strict=True)
-    tr = Stage1DataParallelTrainer(model, dev, bucket_mb=args.bucket_mb, native=args.mode != "torch", graph=args.mode == "graph")
+    tr = Stage1DataParallelTrainer(model, dev, bucket_mb=args.bucket_mb, native=args.mode != "torch", graph=args.mode == "graph",
+                                   channels_last=(args.mode != "torch" and not args.nchw))
     batches = [synthetic_labelled_blocks(args.batch, 1000 * rank + i, device=dev) for i in range(4)]
     for i in range(max(args.warmup, 5 if args.mode == "graph" else 0)):      # the graph is recorded at the 4th step
         tr.step(*batches[i % 4])
@@ -70,7 +72,7 @@ def main():
     if rank == 0:
         print(json.dumps({"metric": "stage1_dp_training_samples_per_sec", "value": args.batch * world / (ms.item() * 1e-3), "unit": "samples/s",
                           "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms.item(), "scaling": "weak",
-                          "dtype": "bf16 autocast (PyTorch fwd/bwd), fp32 gradient all-reduce", "data": "synthetic", "mode": args.mode,
+                          "dtype": "bf16 autocast (PyTorch fwd/bwd), fp32 gradient all-reduce", "data": "synthetic", "mode": args.mode, "channels_last": tr.channels_last,
                           "step": {"graph": "libav1p focal-loss + flat AdamW kernels, zero-grad + forward + loss + backward replayed from one CUDA graph",
                                    "native": "libav1p focal-loss + flat AdamW kernels, eager launches",
                                    "torch": "plain PyTorch ops + torch.optim.AdamW"}[args.mode],
