@@ -1,7 +1,8 @@
 """Callers and dataset formats on either side of the cascade: the v6 label spaces and the
 hierarchical label maps, the evaluation datasets the two pipeline scripts iterate, and their checkpoint loaders.
 
-Reference: pesquisa_v6/v6_pipeline/data_hub.py:25-52 (partition ids and names), :201-281 (stage groups and the three label
+Reference: pesquisa_v6/v6_pipeline/data_hub.py:25-52 (partition ids and names), :89-199 (dataset
+directories: `index_sequences`, `load_block_records`, `train_test_split`), :201-281 (stage groups and the three label
 maps), :288-358 (`HierarchicalBlockDatasetV6`, `build_hierarchical_dataset_v6`); pesquisa_v6/scripts/
 008_run_pipeline_eval_v6.py:219-284 (checkpoint loading, dataset construction and the batch loop of `main`);
 pesquisa_v6/scripts/008b_run_pipeline_flatten_eval.py:62-145 (its own dataset class over a `.pt` file and the two model
@@ -27,6 +28,7 @@ import torch
 from torch.utils.data import Dataset
 
 from .extraction import BlockRecord, TorchBlockRecord
+from .fileio import load_block_file
 
 PARTITION_ID_TO_NAME: Dict[int, str] = dict(enumerate((
     "PARTITION_NONE", "PARTITION_HORZ", "PARTITION_VERT", "PARTITION_SPLIT", "PARTITION_HORZ_A", "PARTITION_HORZ_B",
@@ -45,6 +47,57 @@ STAGE2_GROUPS_V6: Dict[str, Tuple[str, ...]] = {
 STAGE3_GROUPS_V6: Dict[str, Tuple[str, ...]] = {k: STAGE2_GROUPS_V6[k] for k in ("RECT", "AB")}
 STAGE2_NAME_TO_ID_V6 = {name: i for i, name in enumerate(STAGE2_GROUPS_V6)}
 STAGE3_NAME_TO_ID_V6 = {head: {label: i for i, label in enumerate(group)} for head, group in STAGE3_GROUPS_V6.items()}
+
+
+# ---------------------------------------------------------------------------------------------- raw dataset directories
+_SUBDIRS = {"sample": "intra_raw_blocks", "label": "labels", "qps": "qps"}
+_FILE_PATTERNS = {"sample": "{seq}_sample_{b}.txt", "label": "{seq}_labels_{b}_intra.txt", "qps": "{seq}_qps_{b}_intra.txt"}
+
+
+def index_sequences(base_path: Union[str, Path]) -> Dict[str, Dict[str, Dict[str, Optional[str]]]]:
+    """data_hub.py:89-130: {sequence: {block size: {'sample' | 'label' | 'qps': file name or None}}} for a dataset root
+    with `intra_raw_blocks/`, `labels/`, `qps/`.  Sequences are discovered from the `<seq>_sample_<b>.txt` block files."""
+    base = Path(base_path).expanduser().resolve()
+    for kind, sub in _SUBDIRS.items():
+        if not (base / sub).is_dir():
+            raise FileNotFoundError(f"Required directory missing: {base / sub} ({kind})")
+    sequences = sorted({f.name[:-4].split("_sample_")[0] for f in (base / _SUBDIRS["sample"]).iterdir()
+                        if f.suffix == ".txt" and "_sample_" in f.name})
+    inventory: Dict[str, Dict[str, Dict[str, Optional[str]]]] = {}
+    for seq in sequences:
+        inventory[seq] = {}
+        for b in BLOCK_SIZES:
+            names = {kind: pattern.format(seq=seq, b=b) for kind, pattern in _FILE_PATTERNS.items()}
+            inventory[seq][b] = {kind: (name if (base / _SUBDIRS[kind] / name).exists() else None) for kind, name in names.items()}
+    return inventory
+
+
+def load_block_records(base_path: Union[str, Path], block_size: str) -> BlockRecord:
+    """data_hub.py:133-179: every sequence that has all three files for `block_size` ("8" / "16" / "32" / "64"), concatenated
+    in sequence-name order: raw `<u2` blocks (fileio.load_block_file), labels and QPs as whitespace-separated uint8 text."""
+    if block_size not in BLOCK_SIZES:
+        raise ValueError(f"block_size must be one of {BLOCK_SIZES}, got {block_size}")
+    base = Path(base_path)
+    samples, labels, qps = [], [], []
+    for entry in (blocks.get(block_size) for blocks in index_sequences(base).values()):
+        if not entry or not all(entry.get(k) for k in _SUBDIRS):
+            continue
+        samples.append(load_block_file(base / _SUBDIRS["sample"] / entry["sample"], int(block_size)))
+        labels.append(np.fromfile(base / _SUBDIRS["label"] / entry["label"], dtype=np.uint8, sep=" ").reshape(-1))
+        qps.append(np.fromfile(base / _SUBDIRS["qps"] / entry["qps"], dtype=np.uint8, sep=" ").reshape(-1, 1))
+    if not samples:
+        raise RuntimeError(f"No samples found for block size {block_size}")
+    return BlockRecord(samples=np.concatenate(samples), labels=np.concatenate(labels), qps=np.concatenate(qps))
+
+
+def train_test_split(record: BlockRecord, test_ratio: float = 0.2, seed: int = 42) -> Tuple[BlockRecord, BlockRecord]:
+    """data_hub.py:181-199: one `default_rng(seed).permutation`, the first int(N (1 - ratio)) indices train, the rest test."""
+    if not 0 < test_ratio < 1:
+        raise ValueError("test_ratio must be between 0 and 1")
+    order = np.random.default_rng(seed).permutation(record.samples.shape[0])
+    cut = int(order.size * (1 - test_ratio))
+    pick = lambda idx: BlockRecord(samples=record.samples[idx], labels=record.labels[idx], qps=record.qps[idx])
+    return pick(order[:cut]), pick(order[cut:])
 
 
 def _lut(assign: Dict[str, int], dtype) -> np.ndarray:

@@ -53,6 +53,57 @@ def test_label_maps_match_the_live_reference():
     assert D.STAGE3_NAME_TO_ID_V6 == dh.STAGE3_NAME_TO_ID_V6 and D.STAGE2_GROUPS_V6 == dh.STAGE2_GROUPS_V6
 
 
+def _write_dataset_dir(root, rng):
+    """A dataset root as 005 / the label tools leave it: two sequences, block sizes 16 (both) and 8 (one, labels missing)."""
+    for sub in ("intra_raw_blocks", "labels", "qps"):
+        (root / sub).mkdir(parents=True)
+    truth = {}
+    for seq, n in (("seqB_1920x1080", 7), ("seqA_832x480", 5)):
+        blocks = rng.integers(0, 1024, size=(n, 16, 16)).astype("<u2")
+        labels = rng.integers(0, 10, size=n).astype(np.uint8)
+        qps = rng.choice(np.array([22, 27, 32, 37], dtype=np.uint8), size=n)
+        blocks.tofile(root / "intra_raw_blocks" / f"{seq}_sample_16.txt")
+        (root / "labels" / f"{seq}_labels_16_intra.txt").write_text(" ".join(map(str, labels)) + " ")
+        (root / "qps" / f"{seq}_qps_16_intra.txt").write_text(" ".join(map(str, qps)))
+        truth[seq] = (blocks, labels, qps)
+    rng.integers(0, 1024, size=(3, 8, 8)).astype("<u2").tofile(root / "intra_raw_blocks" / "seqA_832x480_sample_8.txt")
+    (root / "qps" / "seqA_832x480_qps_8_intra.txt").write_text("22 22 27")
+    (root / "intra_raw_blocks" / "notes.md").write_text("not a block file")
+    return truth
+
+
+def test_dataset_directory_index_load_and_split(tmp_path):
+    truth = _write_dataset_dir(tmp_path, np.random.Generator(np.random.PCG64(9)))
+    index = D.index_sequences(tmp_path)
+    assert list(index) == ["seqA_832x480", "seqB_1920x1080"] and list(index["seqA_832x480"]) == ["8", "16", "32", "64"]
+    assert index["seqA_832x480"]["8"] == {"sample": "seqA_832x480_sample_8.txt", "label": None, "qps": "seqA_832x480_qps_8_intra.txt"}
+    assert index["seqB_1920x1080"]["32"] == {"sample": None, "label": None, "qps": None}
+    rec = D.load_block_records(tmp_path, "16")
+    assert rec.samples.shape == (12, 16, 16, 1) and rec.samples.dtype == np.uint16 and rec.qps.shape == (12, 1)
+    assert np.array_equal(rec.samples[:5, :, :, 0], truth["seqA_832x480"][0]) and np.array_equal(rec.samples[5:, :, :, 0], truth["seqB_1920x1080"][0])
+    assert np.array_equal(rec.labels, np.concatenate([truth["seqA_832x480"][1], truth["seqB_1920x1080"][1]]))
+    assert np.array_equal(rec.qps[:, 0], np.concatenate([truth["seqA_832x480"][2], truth["seqB_1920x1080"][2]]))
+    with pytest.raises(RuntimeError, match="No samples"):
+        D.load_block_records(tmp_path, "8")                   # its labels file is missing: the sequence is skipped
+    with pytest.raises(ValueError):
+        D.load_block_records(tmp_path, 16)
+    with pytest.raises(FileNotFoundError):
+        D.index_sequences(tmp_path / "labels")
+    train, test = D.train_test_split(rec, test_ratio=0.25, seed=42)
+    assert train.samples.shape[0] == 9 and test.samples.shape[0] == 3
+    order = np.random.default_rng(42).permutation(12)
+    assert np.array_equal(train.labels, rec.labels[order[:9]]) and np.array_equal(test.samples, rec.samples[order[9:]])
+    import ref_import
+    if ref_import.available():                                # build container: the reference's own loaders agree
+        dh = ref_import.load().data_hub
+        assert dh.index_sequences(tmp_path) == index
+        ref = dh.load_block_records(tmp_path, "16")
+        assert all(np.array_equal(getattr(ref, k), getattr(rec, k)) and getattr(ref, k).dtype == getattr(rec, k).dtype
+                   for k in ("samples", "labels", "qps"))
+        r_train, r_test = dh.train_test_split(ref, test_ratio=0.25, seed=42)
+        assert np.array_equal(r_train.samples, train.samples) and np.array_equal(r_test.qps, test.qps)
+
+
 def _cpu_dataset(samples, labels, qps, augmentation=None, stage="eval"):
     """The dataset without the GPU: the normalised samples come from the oracle's `/1023` (a4)."""
     from oracle import cascade_oracle as O
