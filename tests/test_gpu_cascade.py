@@ -143,6 +143,42 @@ def test_small_batch_predict_replays_a_cuda_graph(cuda_device):
     del g
 
 
+def test_optimistic_graph_replay_never_returns_stale_labels(cuda_device):
+    """predict() launches the previous call's graph BEFORE it has checked the weight fingerprint (the check runs while the
+    GPU works).  A weight changed in place, a replaced buffer, a new threshold or another batch size between two calls must
+    therefore be caught behind the launch and the stale result dropped."""
+    images = O.frames_to_images(synth.synth_frames(1, 640, 368, seed=8), 1, 640, 368)
+    x = images[:256].to(cuda_device)
+    pipe = build_pipeline(seed=0, threshold=0.45, device=cuda_device)
+    a = pipe.predict(x)
+    assert pipe._graph_fast is not None and pipe._graph_fast[0] == (256, 0.45)
+    fast_entry = pipe._graph_fast[1]
+    assert torch.equal(pipe.predict(x), a) and pipe._graph_fast[1] is fast_entry          # optimistic replay, same graph
+    assert 0 < int((a > 0).sum()) < 256
+    bias = pipe.stage1_model.head.head[3].bias
+    with torch.no_grad():
+        bias.sub_(100.0)                                    # in place: every block becomes NONE
+    b = pipe.predict(x)
+    assert (b == 0).all() and pipe._graph_fast[1] is not fast_entry                        # stale replay dropped, new graph recorded
+    assert (pipe.predict(x) == 0).all()                                                    # ... and replayed optimistically
+    with torch.no_grad():
+        bias.add_(100.0)
+    assert torch.equal(pipe.predict(x), a)
+    sd = {k: v.clone() for k, v in pipe.stage2_model.state_dict().items()}
+    other = synth.random_state_dict("stage2", 1)
+    pipe.stage2_model.load_state_dict(other)
+    c = pipe.predict(x)
+    ref = build_pipeline(seed=0, threshold=0.45, device=cuda_device)
+    ref.stage2_model.load_state_dict(other)
+    assert torch.equal(c, ref.predict_device(x).cpu()) and not torch.equal(c, a)
+    pipe.stage2_model.load_state_dict(sd)
+    assert torch.equal(pipe.predict(x), a)
+    pipe.stage1_threshold = 0.9                             # same batch size, other threshold: not the fast entry
+    assert torch.equal(pipe.predict(x), build_pipeline(seed=0, threshold=0.9, device=cuda_device).predict_device(x).cpu())
+    pipe.stage1_threshold = 0.45
+    assert torch.equal(pipe.predict(x[:100]), a[:100]) and torch.equal(pipe.predict(x), a)
+
+
 def test_predict_edge_cases(cuda_device):
     pipe = build_pipeline(seed=0, device=cuda_device)
     assert pipe.predict(torch.zeros(0, 1, 16, 16)).shape == (0,)
