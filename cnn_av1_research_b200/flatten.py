@@ -93,9 +93,13 @@ def run_pipeline_inference(stage1_model, stage2_flat_model, dataloader, stage1_t
     pipe = FlattenPipeline(stage1_model, stage2_flat_model, stage1_threshold, device)
     preds, labels = [], []
     for batch in dataloader:
-        preds.append(pipe.predict(batch["sample"]).numpy())
-        labels.append(batch["original_label"].cpu().numpy())
-    return np.concatenate(preds), np.concatenate(labels)
+        # labels stay on the device and no batch waits for its predecessor: the reference's per-batch `.cpu()` (008b:223)
+        # would put one host synchronisation - longer than a 256-block cascade itself - between any two batches
+        preds.append(pipe.predict_device(batch["sample"]))
+        labels.append(batch["original_label"])
+    if not preds:
+        return np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.int64)
+    return torch.cat(preds).cpu().numpy(), torch.cat([t.reshape(-1).cpu() for t in labels]).numpy()
 
 
 # ------------------------------------------------------------------------------------------------
