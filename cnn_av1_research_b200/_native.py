@@ -95,6 +95,14 @@ SIGNATURES = {
     "av1p_focal_loss_binary": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
     "av1p_adamw_flat": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double,
                                   C.c_double, C.c_double, C.c_void_p, C.c_int32, C.c_void_p]),
+    "av1p_dp_adamw_fused": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_int64,
+                                      C.c_int64, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
+                                      C.c_int64, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "av1p_dp_flag_words": (C.c_int, []),
+    "av1p_enable_peer_access": (C.c_int, [C.c_int32]),
+    "av1p_ipc_export": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_int64)]),
+    "av1p_ipc_import": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "av1p_ipc_close": (C.c_int, [C.c_void_p]),
 }
 
 

@@ -1813,3 +1813,100 @@ extern "C" int av1p_adamw_flat(float* param_dev, const float* grad_dev, float* e
   CUDA_TRY(cudaGetLastError());
   return AV1P_OK;
 }
+
+// Reduce-scatter + AdamW + all-gather of the data-parallel step in one kernel over peer memory (train_kernels.cuh).
+extern "C" int av1p_dp_adamw_fused(const float* const* grad_ptrs, float* const* param_ptrs, int32_t* const* flag_ptrs, int32_t rank,
+                                   int32_t world, int64_t n, int64_t shard, float* exp_avg_shard_dev, float* exp_avg_sq_shard_dev,
+                                   double lr, double beta1, double beta2, double eps, double weight_decay, int64_t skip_lo,
+                                   int64_t skip_hi, int32_t* step_dev, int32_t epoch, int32_t* err_dev, void* stream) {
+  if (!grad_ptrs || !param_ptrs || !flag_ptrs || !exp_avg_shard_dev || !exp_avg_sq_shard_dev || !step_dev || !err_dev)
+    return fail(AV1P_EINVAL, "null argument");
+  if (world < 1 || world > DP_MAX_WORLD || rank < 0 || rank >= world) return fail(AV1P_EINVAL, "rank %d / world %d (at most %d ranks)", rank, world, DP_MAX_WORLD);
+  if (n <= 0 || shard <= 0 || shard % 4 || shard * world < n) return fail(AV1P_EINVAL, "shard of %lld elements does not cover %lld over %d ranks (multiple of 4 required)", (long long)shard, (long long)n, world);
+  if (skip_lo > skip_hi) return fail(AV1P_EINVAL, "bad skip range");
+  if (!(beta1 >= 0.0 && beta1 < 1.0) || !(beta2 >= 0.0 && beta2 < 1.0) || !(eps >= 0.0) || !(lr >= 0.0) || !(weight_decay >= 0.0))
+    return fail(AV1P_EINVAL, "AdamW hyper-parameters out of range");
+  if (int rc = ensure_ctx()) return rc;
+  DpAdamWArgs a = {};
+  for (int p = 0; p < world; ++p) {
+    if (!grad_ptrs[p] || !param_ptrs[p] || !flag_ptrs[p]) return fail(AV1P_EINVAL, "null peer pointer for rank %d", p);
+    if ((reinterpret_cast<uintptr_t>(grad_ptrs[p]) | reinterpret_cast<uintptr_t>(param_ptrs[p])) & 15u)
+      return fail(AV1P_EINVAL, "peer buffers must be 16-byte aligned");
+    a.grad[p] = grad_ptrs[p];
+    a.param[p] = param_ptrs[p];
+    a.flags[p] = flag_ptrs[p];
+  }
+  if ((reinterpret_cast<uintptr_t>(exp_avg_shard_dev) | reinterpret_cast<uintptr_t>(exp_avg_sq_shard_dev)) & 15u)
+    return fail(AV1P_EINVAL, "moment shards must be 16-byte aligned");
+  a.m = exp_avg_shard_dev;
+  a.v = exp_avg_sq_shard_dev;
+  a.n = n;
+  a.shard = shard;
+  a.skip_lo = skip_lo;
+  a.skip_hi = skip_hi;
+  a.rank = rank;
+  a.world = world;
+  a.epoch = epoch;
+  a.h = AdamWArgs{nullptr, nullptr, nullptr, nullptr, 0, lr, beta1, beta2, float(1.0 - lr * weight_decay), float(1.0 - beta1),
+                  float(beta2), float(1.0 - beta2), float(eps), float(1.0 / world), step_dev};
+  a.err = err_dev;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  train_step_inc_kernel<<<1, 1, 0, st>>>(step_dev);
+  CUDA_TRY(cudaGetLastError());
+  // every CTA must be resident (phase 0 spins in all of them): at most four CTAs of 256 threads per SM
+  const long long want = ((std::min<long long>(shard, n) >> 2) + TRAIN_THREADS - 1) / TRAIN_THREADS;
+  const int grid = int(std::max<long long>(1, std::min<long long>(want, (long long)g_ctx.sms * 4)));
+  dp_adamw_fused_kernel<<<grid, TRAIN_THREADS, 0, st>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  return AV1P_OK;
+}
+extern "C" int av1p_dp_flag_words(void) { return DP_FLAG_WORDS; }
+// Kernels of the CURRENT device may dereference memory of device `peer_device` afterwards (NVLink / NVSwitch peer mapping).
+extern "C" int av1p_enable_peer_access(int32_t peer_device) {
+  int me = 0, can = 0;
+  CUDA_TRY(cudaGetDevice(&me));
+  if (peer_device == me) return AV1P_OK;
+  CUDA_TRY(cudaDeviceCanAccessPeer(&can, me, peer_device));
+  if (!can) return fail(AV1P_ENODEV, "device %d cannot access device %d as a peer", me, peer_device);
+  const cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+  if (e == cudaErrorPeerAccessAlreadyEnabled) {
+    cudaGetLastError();                      // clear the sticky-free error state
+    return AV1P_OK;
+  }
+  if (e != cudaSuccess) return fail(AV1P_ECUDA, "cudaDeviceEnablePeerAccess(%d): %s", peer_device, cudaGetErrorString(e));
+  return AV1P_OK;
+}
+
+// CUDA IPC plumbing for the peer buffers of av1p_dp_adamw_fused.  Export: handle of the cudaMalloc block that holds
+// `dev_ptr` + the pointer's offset inside it.  Import (with the IMPORTING rank's device current, so that the mapping is
+// made for that device's kernels; peer access is enabled as needed): base address of the block in this process.
+extern "C" int av1p_ipc_export(const void* dev_ptr, uint8_t handle_out[64], int64_t* offset_out) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  if (!dev_ptr || !handle_out || !offset_out) return fail(AV1P_EINVAL, "null argument");
+  CUdeviceptr base = 0;
+  size_t size = 0;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  CUDA_TRY(cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qres));
+  if (!fn || qres != cudaDriverEntryPointSuccess) return fail(AV1P_ECUDA, "cuMemGetAddressRange not available");
+  typedef CUresult (*RangeFn)(CUdeviceptr*, size_t*, CUdeviceptr);
+  const CUresult r = reinterpret_cast<RangeFn>(fn)(&base, &size, reinterpret_cast<CUdeviceptr>(dev_ptr));
+  if (r != CUDA_SUCCESS) return fail(AV1P_ECUDA, "cuMemGetAddressRange failed with %d", int(r));
+  cudaIpcMemHandle_t h;
+  CUDA_TRY(cudaIpcGetMemHandle(&h, reinterpret_cast<void*>(base)));
+  memcpy(handle_out, &h, sizeof h);
+  *offset_out = int64_t(reinterpret_cast<CUdeviceptr>(dev_ptr) - base);
+  return AV1P_OK;
+}
+extern "C" int av1p_ipc_import(const uint8_t handle[64], void** base_out) {
+  if (!handle || !base_out) return fail(AV1P_EINVAL, "null argument");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof h);
+  CUDA_TRY(cudaIpcOpenMemHandle(base_out, h, cudaIpcMemLazyEnablePeerAccess));
+  return AV1P_OK;
+}
+extern "C" int av1p_ipc_close(void* base) {
+  if (!base) return AV1P_OK;
+  CUDA_TRY(cudaIpcCloseMemHandle(base));
+  return AV1P_OK;
+}

@@ -132,4 +132,126 @@ __global__ void __launch_bounds__(FOCAL_THREADS) focal_loss_binary_kernel(const 
   if (threadIdx.x == 0) *loss_out = s_sum[0] * inv_n;
 }
 
+// ---- data-parallel step: gradient reduce-scatter + AdamW + parameter all-gather in ONE kernel over NVLink peer memory.
+//      Every rank owns one contiguous shard of the flat parameter index space (and only that shard's moments).  Per step
+//      each rank launches this kernel after its backward; it
+//        0. tells every peer "my gradients are complete" (one remote flag store per peer) and waits until all peers said so
+//           - from here on nobody is still using the parameters or writing gradients;
+//        1. for its shard: sums the W gradient buffers with peer loads in rank order, applies AdamW (adamw_one above, the
+//           1 / W folded in), and stores the new parameter values into EVERY rank's parameter buffer with peer stores;
+//        2. tells every peer "my shard is written everywhere and I am done reading your gradients" and its last CTA waits
+//           for the same message from all peers, so that when the kernel completes on a rank its whole parameter buffer is
+//           current and its gradient buffer is free for the next backward.
+//      NVLink traffic per rank and step: (W - 1) / W of the gradients in, (W - 1) / W of the parameters out - half of an
+//      all-reduce's, with no separate update pass over HBM afterwards.  Every shard is computed once, by one rank, in one
+//      summation order, so the replicas are bit-identical by construction.  Flags live in each rank's own memory and are
+//      written remotely / polled locally; they carry the step's epoch (monotonic), so they never need resetting.  Every spin
+//      is bounded (~10 s of SM clocks): on a timeout the error word is set and the kernel leaves.
+constexpr int DP_MAX_WORLD = 16;
+constexpr int DP_FLAG_WORDS = 2 * DP_MAX_WORLD + 1;        // [0..15] phase-0 arrivals, [16..31] phase-2 arrivals, [32] finished CTAs
+constexpr long long DP_SPIN_CYCLES = 20000000000ll;      // ~10 s
+
+struct DpAdamWArgs {
+  const float* grad[DP_MAX_WORLD];     // every rank's flat gradient buffer (peer-mapped), n elements
+  float* param[DP_MAX_WORLD];          // every rank's flat parameter buffer
+  int* flags[DP_MAX_WORLD];            // every rank's DP_FLAG_WORDS flag words
+  float* m;                            // this rank's moment shards, indexed from the shard start
+  float* v;
+  long long n, shard;                  // total elements; elements per shard (multiple of 4)
+  long long skip_lo, skip_hi;          // flat range without gradient (left untouched, as torch skips grad-less parameters)
+  int rank, world, epoch;
+  AdamWArgs h;                         // hyper-parameters, step pointer and grad_scale (p / g / m / v / n unused)
+  int* err;
+};
+
+__device__ __forceinline__ void dp_store_flag(int* p, int v) { asm volatile("st.volatile.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ int dp_load_flag(const int* p) {
+  int v;
+  asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// wait until every rank's word in my own flag array has reached `epoch`; false on timeout
+__device__ __forceinline__ bool dp_wait_all(const int* mine, int world, int epoch) {
+  const long long t0 = clock64();
+  for (int p = 0; p < world; ++p)
+    while (dp_load_flag(mine + p) - epoch < 0)
+      if (clock64() - t0 > DP_SPIN_CYCLES) return false;
+  return true;
+}
+
+__global__ void __launch_bounds__(TRAIN_THREADS) dp_adamw_fused_kernel(const DpAdamWArgs a) {
+  __shared__ float s_step_size, s_bc2_sqrt;
+  __shared__ int s_ok;
+  int* mine = a.flags[a.rank];
+  if (blockIdx.x == 0 && int(threadIdx.x) < a.world) {
+    __threadfence_system();
+    dp_store_flag(a.flags[threadIdx.x] + a.rank, a.epoch);            // phase 0: "rank's gradients are complete"
+  }
+  if (threadIdx.x == 0) {
+    const double t = double(*a.h.step);
+    s_step_size = float(a.h.lr / (1.0 - pow(a.h.beta1, t)));
+    s_bc2_sqrt = float(sqrt(1.0 - pow(a.h.beta2, t)));
+    s_ok = dp_wait_all(mine, a.world, a.epoch) ? 1 : 0;
+    __threadfence_system();
+  }
+  __syncthreads();
+  if (!s_ok) {
+    if (threadIdx.x == 0) *a.err = 1;
+    return;
+  }
+  const float step_size = s_step_size, bc2_sqrt = s_bc2_sqrt;
+  const long long lo = min(a.n, (long long)a.rank * a.shard), hi = min(a.n, lo + a.shard);
+  const long long n4 = (hi - lo) >> 2;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const long long e = lo + (i << 2);
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int p = 0; p < a.world; ++p) {                                // fixed rank order: one summation order per element
+      const float4 q = __ldcv(reinterpret_cast<const float4*>(a.grad[p] + e));
+      g.x += q.x; g.y += q.y; g.z += q.z; g.w += q.w;
+    }
+    float4 w = *reinterpret_cast<const float4*>(a.param[a.rank] + e);
+    float4 m = reinterpret_cast<float4*>(a.m)[i];
+    float4 v = reinterpret_cast<float4*>(a.v)[i];
+    if (e + 3 < a.skip_lo || e >= a.skip_hi) {
+      adamw_one(w.x, g.x, m.x, v.x, a.h, step_size, bc2_sqrt);
+      adamw_one(w.y, g.y, m.y, v.y, a.h, step_size, bc2_sqrt);
+      adamw_one(w.z, g.z, m.z, v.z, a.h, step_size, bc2_sqrt);
+      adamw_one(w.w, g.w, m.w, v.w, a.h, step_size, bc2_sqrt);
+    } else {                                                           // the quad overlaps the grad-less range
+      if (e + 0 < a.skip_lo || e + 0 >= a.skip_hi) adamw_one(w.x, g.x, m.x, v.x, a.h, step_size, bc2_sqrt);
+      if (e + 1 < a.skip_lo || e + 1 >= a.skip_hi) adamw_one(w.y, g.y, m.y, v.y, a.h, step_size, bc2_sqrt);
+      if (e + 2 < a.skip_lo || e + 2 >= a.skip_hi) adamw_one(w.z, g.z, m.z, v.z, a.h, step_size, bc2_sqrt);
+      if (e + 3 < a.skip_lo || e + 3 >= a.skip_hi) adamw_one(w.w, g.w, m.w, v.w, a.h, step_size, bc2_sqrt);
+    }
+    reinterpret_cast<float4*>(a.m)[i] = m;
+    reinterpret_cast<float4*>(a.v)[i] = v;
+    for (int p = 0; p < a.world; ++p) *reinterpret_cast<float4*>(a.param[p] + e) = w;      // all-gather by peer stores
+  }
+  if (blockIdx.x == 0 && threadIdx.x < 3) {                            // scalar tail of the last shard (n not a multiple of 4)
+    const long long e = lo + (n4 << 2) + threadIdx.x;
+    if (e < hi) {
+      float g = 0.f;
+      for (int p = 0; p < a.world; ++p) g += __ldcv(a.grad[p] + e);
+      float w = a.param[a.rank][e], m = a.m[e - lo], v = a.v[e - lo];
+      if (e < a.skip_lo || e >= a.skip_hi) adamw_one(w, g, m, v, a.h, step_size, bc2_sqrt);
+      a.m[e - lo] = m;
+      a.v[e - lo] = v;
+      for (int p = 0; p < a.world; ++p) a.param[p][e] = w;
+    }
+  }
+  __threadfence_system();                                              // my peer stores are visible before anyone sees my flag
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int finished = atomicAdd(mine + 2 * DP_MAX_WORLD, 1);
+    if (finished == int(gridDim.x) - 1) {                              // last CTA of this rank
+      mine[2 * DP_MAX_WORLD] = 0;
+      __threadfence_system();
+      for (int p = 0; p < a.world; ++p) dp_store_flag(a.flags[p] + DP_MAX_WORLD + a.rank, a.epoch);   // phase 2
+      if (!dp_wait_all(mine + DP_MAX_WORLD, a.world, a.epoch)) *a.err = 2;
+      __threadfence_system();
+    }
+  }
+}
+
 }  // namespace av1p

@@ -112,6 +112,65 @@ def focal_loss_binary_native(logits: torch.Tensor, targets: torch.Tensor, alpha:
     return _FocalLossNative.apply(logits, targets, alpha, gamma)
 
 
+class PeerBuffers:
+    """Every rank's copy of a set of CUDA tensors, mapped into this process over CUDA IPC (one node, NVLink / NVSwitch peer
+    access).  `pointers[name][r]` is the address - valid in kernels of THIS rank's device - of rank r's tensor `name`.
+    Each rank exports the handle of the device allocation behind a tensor plus the tensor's offset inside it
+    (`av1p_ipc_export`); the handles travel through `all_gather_object`; every rank imports its peers' allocations with its
+    own device current (`av1p_ipc_import`, which also enables peer access), once per allocation.  The owners keep the tensors
+    alive (they are members of the trainer); the mappings are closed when this object goes away."""
+
+    def __init__(self, tensors: Dict[str, torch.Tensor], group=None):
+        import ctypes as C
+        from . import _native as N
+        lib = N.lib()
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.device = next(iter(tensors.values())).device
+        self._bases = {}                                   # handle bytes -> imported base address
+        self._keep = dict(tensors)
+        payload = {}
+        with torch.cuda.device(self.device):
+            for k, t in tensors.items():
+                handle, off = C.create_string_buffer(64), C.c_int64(0)
+                N.check(lib.av1p_ipc_export(N.ptr(t), handle, C.byref(off)))
+                payload[k] = (handle.raw, int(off.value), int(self.device.index))
+            gathered = [None] * self.world
+            dist.all_gather_object(gathered, payload, group=group)
+            self.pointers: Dict[str, list] = {k: [] for k in tensors}
+            for r, item in enumerate(gathered):
+                for k, (handle, off, dev_index) in item.items():
+                    if r == self.rank:
+                        self.pointers[k].append(tensors[k].data_ptr())
+                        continue
+                    if handle not in self._bases:
+                        N.check(lib.av1p_enable_peer_access(dev_index))
+                        base = C.c_void_p()
+                        N.check(lib.av1p_ipc_import(handle, C.byref(base)))
+                        self._bases[handle] = int(base.value)
+                    self.pointers[k].append(self._bases[handle] + off)
+        torch.cuda.synchronize(self.device)
+
+    def pointer_array(self, name: str):
+        import ctypes as C
+        return (C.c_void_p * self.world)(*self.pointers[name])
+
+    def close(self) -> None:
+        from . import _native as N
+        bases, self._bases = self._bases, {}
+        for base in bases.values():
+            try:
+                with torch.cuda.device(self.device):
+                    N.lib().av1p_ipc_close(base)
+            except Exception:
+                pass
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Stage1DataParallelTrainer:
     """One replica of the Stage-1 training step; all replicas stay bit-identical because they apply the same averaged
     gradient with the same optimiser state.
@@ -137,12 +196,23 @@ class Stage1DataParallelTrainer:
     `graph_warmup` eager steps and replays it afterwards: per step the host then issues two input copies, one graph launch,
     the all-reduce and the update.  The all-reduce stays outside the graph (one eager NCCL call on the flat buffer).  The
     convolutions' forward / backward themselves remain cuDNN kernels - training is not the product path of this package.
-    `native=False` keeps the plain PyTorch step (torch.optim.AdamW), which is also the only one available on the CPU."""
+    `native=False` keeps the plain PyTorch step (torch.optim.AdamW), which is also the only one available on the CPU.
+
+    Fused exchange (`fused_exchange`, tried by default when native and more than one rank).  A replicated data-parallel
+    step is "all-reduce the gradients, then every rank runs the same update over all parameters".  On one NVSwitch node the
+    ranks can address each other's memory, so both become ONE kernel per rank (`av1p_dp_adamw_fused`): rank r sums shard r
+    of the W gradient buffers with peer loads, applies AdamW to shard r only (its moments exist on rank r only - 1 / W of
+    the optimiser state per GPU) and stores the new values of shard r into every rank's parameter buffer.  That moves half
+    the NVLink bytes of an all-reduce, drops the separate 318 MB update pass over HBM and makes the replicas bit-identical by
+    construction (one rank computes each element).  The buffers are shared over CUDA IPC (`PeerBuffers`); if that is not
+    possible on a machine the step keeps the NCCL all-reduce + `av1p_adamw_flat` (a warning says so), `fused_exchange=True`
+    turns that into an error."""
 
     def __init__(self, model, device, lr: float = 1e-3, weight_decay: float = 1e-4, alpha: float = 0.25, gamma: float = 2.5,
                  dropout_p: float = 0.3, autocast_bf16: Optional[bool] = None, group=None, bucket_mb: float = 0.0,
                  native: Optional[bool] = None, graph: Optional[bool] = None, graph_warmup: int = 3,
-                 betas=(0.9, 0.999), eps: float = 1e-8, channels_last: Optional[bool] = None):
+                 betas=(0.9, 0.999), eps: float = 1e-8, channels_last: Optional[bool] = None,
+                 fused_exchange: Optional[bool] = None):
         self.model = model.to(device)
         self.device = torch.device(device)
         self.group = group
@@ -210,14 +280,75 @@ class Stage1DataParallelTrainer:
             self.flat_exp_avg_sq = torch.zeros_like(self.flat_param)
             self.step_dev = torch.zeros(1, dtype=torch.int32, device=self.device)
             self.optimizer = None
+            self.fused = False
+            if self.world > 1 and fused_exchange is not False:
+                self._setup_fused(required=bool(fused_exchange))
             self._segments = None                # [(start, end)] ranges of the flat buffers that received gradients
             self._segments_for = None
             self._graphs = {}                    # (batch shape) -> [graph, static images, static labels, static loss]
             self._steps_done = 0
         else:
+            if fused_exchange:
+                raise ValueError("fused_exchange=True is part of the native step; pass native=True")
+            self.fused = False
             self.optimizer = torch.optim.AdamW(self.params, lr=lr, weight_decay=weight_decay, betas=betas, eps=eps)
         for p in self.params:
             p.register_post_accumulate_grad_hook(self._on_grad)
+
+    def _setup_fused(self, required: bool) -> None:
+        """Map every rank's gradient / parameter / flag buffers (CUDA IPC) and shard the optimiser state.  All ranks decide
+        together: if any of them cannot, everyone keeps the NCCL path."""
+        import warnings
+        from . import _native as N
+        n, world = self.flat_grad.numel(), self.world
+        ok, why = 1, ""
+        try:
+            flags = torch.zeros(N.lib().av1p_dp_flag_words(), dtype=torch.int32, device=self.device)
+            peers = PeerBuffers({"grad": self.flat_grad, "param": self.flat_param, "flags": flags}, self.group)
+        except Exception as exc:                 # IPC not permitted, no peer access, ...
+            ok, why = 0, f"{type(exc).__name__}: {exc}"
+        agree = torch.tensor([ok], dtype=torch.int32, device=self.device)
+        dist.all_reduce(agree, op=dist.ReduceOp.MIN, group=self.group)
+        if not int(agree.item()):
+            if required:
+                raise RuntimeError(f"fused gradient exchange is not available on this machine ({why or 'a peer rank failed'})")
+            warnings.warn(f"fused gradient exchange unavailable ({why or 'a peer rank failed'}): NCCL all-reduce + av1p_adamw_flat instead")
+            return
+        self._peers, self._dp_flags = peers, flags
+        self._ptrs = {k: peers.pointer_array(k) for k in ("grad", "param", "flags")}
+        self.shard = (-(-n // world) + 3) // 4 * 4
+        self.rank = dist.get_rank(self.group)
+        self.flat_exp_avg = torch.zeros(self.shard, dtype=torch.float32, device=self.device)        # this rank's shard only
+        self.flat_exp_avg_sq = torch.zeros(self.shard, dtype=torch.float32, device=self.device)
+        self._dp_err = torch.zeros(1, dtype=torch.int32).pin_memory()      # written by the kernel through the mapped host page
+        self._epoch = 0
+        self.fused = True
+        dist.barrier(group=self.group)
+
+    def check_exchange(self) -> None:
+        """Raise if a fused exchange kernel gave up waiting for a peer (it sets a host-visible word; no synchronisation)."""
+        if self.fused and int(self._dp_err[0]):
+            raise RuntimeError(f"fused gradient exchange timed out waiting for a peer rank (code {int(self._dp_err[0])}); parameters are invalid")
+
+    def _update_fused(self) -> None:
+        from . import _native as N
+        n = self.flat_grad.numel()
+        gaps, at = [], 0
+        for lo, hi in self._grad_segments():
+            if lo > at:
+                gaps.append((at, lo))
+            at = hi
+        if at < n:
+            gaps.append((at, n))
+        if len(gaps) > 1:
+            raise RuntimeError(f"the fused exchange supports one grad-less parameter range, this model has {len(gaps)}: pass fused_exchange=False")
+        skip = gaps[0] if gaps else (0, 0)
+        self.check_exchange()
+        self._epoch += 1
+        N.check(N.lib().av1p_dp_adamw_fused(self._ptrs["grad"], self._ptrs["param"], self._ptrs["flags"], self.rank, self.world, n, self.shard,
+                                            N.ptr(self.flat_exp_avg), N.ptr(self.flat_exp_avg_sq), self.lr, self.betas[0], self.betas[1],
+                                            self.eps, self.weight_decay, skip[0], skip[1], N.ptr(self.step_dev), self._epoch,
+                                            self._dp_err.data_ptr(), N.stream_handle(self.device)))
 
     def _view(self, flat: torch.Tensor, off: int, p: torch.Tensor) -> torch.Tensor:
         """The slot of parameter `p` inside a flat buffer, shaped like `p` (4-D weights in channels_last order if enabled)."""
@@ -230,7 +361,7 @@ class Stage1DataParallelTrainer:
     # ---- gradient exchange -------------------------------------------------------------------------------------------
     def _launch_bucket(self, b: int) -> None:
         self._launched[b] = True
-        if self.world > 1:
+        if self.world > 1 and not self.fused:
             lo, hi, _ = self.buckets[b]
             self._works.append(dist.all_reduce(self.flat_grad[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
 
@@ -272,6 +403,8 @@ class Stage1DataParallelTrainer:
         return loss.detach()
 
     def _exchange(self) -> None:
+        if self.fused:                                         # the update kernel reads the peers' gradients itself
+            return
         for b in range(len(self.buckets)):                     # buckets holding a parameter that got no gradient (zeros)
             if not self._launched[b]:
                 self._launch_bucket(b)
@@ -305,12 +438,15 @@ class Stage1DataParallelTrainer:
             self.optimizer.step()
             return
         from . import _native as N
-        lib, st = N.lib(), N.stream_handle(self.device)
-        b = self.flat_param.data_ptr(), self.flat_grad.data_ptr(), self.flat_exp_avg.data_ptr(), self.flat_exp_avg_sq.data_ptr()
-        for i, (lo, hi) in enumerate(self._grad_segments()):
-            N.check(lib.av1p_adamw_flat(b[0] + 4 * lo, b[1] + 4 * lo, b[2] + 4 * lo, b[3] + 4 * lo, hi - lo, self.lr, self.betas[0],
-                                        self.betas[1], self.eps, self.weight_decay, 1.0 / self.world, N.ptr(self.step_dev),
-                                        1 if i == 0 else 0, st))
+        if self.fused:
+            self._update_fused()
+        else:
+            lib, st = N.lib(), N.stream_handle(self.device)
+            b = self.flat_param.data_ptr(), self.flat_grad.data_ptr(), self.flat_exp_avg.data_ptr(), self.flat_exp_avg_sq.data_ptr()
+            for i, (lo, hi) in enumerate(self._grad_segments()):
+                N.check(lib.av1p_adamw_flat(b[0] + 4 * lo, b[1] + 4 * lo, b[2] + 4 * lo, b[3] + 4 * lo, hi - lo, self.lr, self.betas[0],
+                                            self.betas[1], self.eps, self.weight_decay, 1.0 / self.world, N.ptr(self.step_dev),
+                                            1 if i == 0 else 0, st))
         for p in self.params:
             if p not in self._touched:
                 p.grad = None
@@ -362,7 +498,7 @@ class Stage1DataParallelTrainer:
 
     def gradient_vector(self) -> torch.Tensor:
         """The (averaged, on the plain PyTorch path; summed over the ranks on the native path, which folds the 1 / world
-        into the update) gradients of the last step in PARAMETER order (the flat buffer itself is laid out in reverse
+        into the update; this rank's own, un-reduced ones with the fused exchange) gradients of the last step in PARAMETER order (the flat buffer itself is laid out in reverse
         parameter order, the order backward fills it)."""
         return torch.cat([self.grad_views[p].reshape(-1) for p in self.params])
 
@@ -371,6 +507,14 @@ class Stage1DataParallelTrainer:
 
     def optimizer_state(self) -> Dict[str, torch.Tensor]:
         """AdamW state in PARAMETER order ('step', 'exp_avg', 'exp_avg_sq' as flat vectors) for checkpoints / tests."""
+        if self.native and self.fused:
+            def whole(shard):                    # every rank's moment shard, concatenated in rank order = the flat layout
+                parts = [torch.empty_like(shard) for _ in range(self.world)]
+                dist.all_gather(parts, shard, group=self.group)
+                return torch.cat(parts)[:self.flat_grad.numel()]
+            m, v = whole(self.flat_exp_avg), whole(self.flat_exp_avg_sq)
+            pick = lambda flat: torch.cat([self._view(flat, self._offset[p], p).reshape(-1) for p in self.params])
+            return {"step": self.step_dev.clone(), "exp_avg": pick(m), "exp_avg_sq": pick(v)}
         if self.native:
             def gather(flat):
                 return torch.cat([self._view(flat, self._offset[p], p).reshape(-1) for p in self.params])

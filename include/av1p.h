@@ -259,6 +259,33 @@ int av1p_adamw_flat(float* param_dev, const float* grad_dev, float* exp_avg_dev,
                     double beta1, double beta2, double eps, double weight_decay, double grad_scale, int32_t* step_dev, int32_t advance_step,
                     void* stream);
 
+/* ---- data-parallel training step: gradient reduce-scatter + AdamW + parameter all-gather in ONE kernel over NVLink peer
+ *      memory (replaces `dist.all_reduce(grads)` + `optimizer.step()` of a replicated data-parallel step,
+ *      pesquisa_v6/scripts/003_train_stage1_improved.py:71-73 under DDP).  grad_ptrs / param_ptrs / flag_ptrs: HOST arrays
+ *      of `world` device pointers, entry r = rank r's flat gradient buffer / flat parameter buffer (n float32 each, 16-byte
+ *      aligned) / flag words (av1p_dp_flag_words() int32, zero-initialised once), each mapped into this process (CUDA IPC)
+ *      with peer access enabled.  Rank r owns elements [r * shard, min(n, (r + 1) * shard)) (shard a multiple of 4) and
+ *      keeps only that range's moments (exp_avg_shard_dev / exp_avg_sq_shard_dev, `shard` floats each).  [skip_lo, skip_hi):
+ *      flat range that received no gradient on any rank (left untouched, like torch skips grad-less parameters; empty if
+ *      skip_lo == skip_hi).  epoch: 1, 2, 3, ... identical on every rank for the same step.  *err_dev becomes non-zero if a
+ *      peer did not arrive within ~10 s of SM clocks (the kernel then leaves; results are invalid).  All ranks must call this
+ *      for every step, each on its own device / stream; *step_dev is advanced like av1p_adamw_flat does. */
+int av1p_dp_adamw_fused(const float* const* grad_ptrs, float* const* param_ptrs, int32_t* const* flag_ptrs, int32_t rank,
+                        int32_t world, int64_t n, int64_t shard, float* exp_avg_shard_dev, float* exp_avg_sq_shard_dev, double lr,
+                        double beta1, double beta2, double eps, double weight_decay, int64_t skip_lo, int64_t skip_hi,
+                        int32_t* step_dev, int32_t epoch, int32_t* err_dev, void* stream);
+int av1p_dp_flag_words(void);
+/* Enable peer access from the CURRENT device to `peer_device` (idempotent): required before av1p_dp_adamw_fused
+ * dereferences that device's buffers. */
+int av1p_enable_peer_access(int32_t peer_device);
+/* CUDA IPC plumbing for those buffers.  av1p_ipc_export: 64-byte handle of the device allocation that holds dev_ptr + the
+ * pointer's byte offset inside it (send both to the peer processes).  av1p_ipc_import: maps a peer's allocation into this
+ * process for the CURRENT device (peer access is enabled as needed) and returns its base address; a handle may be imported
+ * once per process.  av1p_ipc_close unmaps it.  The exporting process must keep the allocation alive. */
+int av1p_ipc_export(const void* dev_ptr, uint8_t handle_out[64], int64_t* offset_out);
+int av1p_ipc_import(const uint8_t handle[64], void** base_out);
+int av1p_ipc_close(void* base);
+
 #ifdef __cplusplus
 }
 #endif

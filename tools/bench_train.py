@@ -30,6 +30,9 @@ def main():
     ap.add_argument("--mode", choices=("graph", "native", "torch"), default="graph",
                     help="graph: native loss / AdamW kernels + the step replayed from a CUDA graph (default); native: the same kernels, "
                          "eager launches; torch: plain PyTorch step with torch.optim.AdamW (round-1 path)")
+    ap.add_argument("--exchange", choices=("fused", "nccl"), default="fused",
+                    help="native / graph modes on several GPUs: fused = one kernel per rank does reduce-scatter + AdamW + all-gather over "
+                         "NVLink peer memory (default, falls back to nccl if CUDA IPC is unavailable); nccl = all-reduce + flat AdamW kernel")
     ap.add_argument("--nchw", action="store_true", help="native / graph modes: keep NCHW weights and activations (default: channels_last)")
     ap.add_argument("--bucket-mb", type=float, default=0.0, help="gradient bucket size in MB (overlapped with backward); 0 = one flat all-reduce after backward (default: measured faster)")
     args = ap.parse_args()
@@ -44,7 +47,8 @@ def main():
     model = Stage1Model(pretrained=False)
     model.load_state_dict(synth.calibrated_state_dict("stage1", 0), strict=True)
     tr = Stage1DataParallelTrainer(model, dev, bucket_mb=args.bucket_mb, native=args.mode != "torch", graph=args.mode == "graph",
-                                   channels_last=(args.mode != "torch" and not args.nchw))
+                                   channels_last=(args.mode != "torch" and not args.nchw),
+                                   fused_exchange=(None if args.exchange == "fused" else False) if args.mode != "torch" else None)
     batches = [synthetic_labelled_blocks(args.batch, 1000 * rank + i, device=dev) for i in range(4)]
     for i in range(max(args.warmup, 5 if args.mode == "graph" else 0)):      # the graph is recorded at the 4th step
         tr.step(*batches[i % 4])
@@ -60,6 +64,8 @@ def main():
     ms = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    if tr.native:
+        tr.check_exchange()
     # replicas must still be identical
     flat = torch.cat([p.detach().reshape(-1) for p in tr.params])
     same = True
@@ -72,13 +78,13 @@ def main():
     if rank == 0:
         print(json.dumps({"metric": "stage1_dp_training_samples_per_sec", "value": args.batch * world / (ms.item() * 1e-3), "unit": "samples/s",
                           "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms.item(), "scaling": "weak",
-                          "dtype": "bf16 autocast (PyTorch fwd/bwd), fp32 gradient all-reduce", "data": "synthetic", "mode": args.mode, "channels_last": tr.channels_last,
+                          "dtype": "bf16 autocast (PyTorch fwd/bwd), fp32 gradient all-reduce", "data": "synthetic", "mode": args.mode, "channels_last": tr.channels_last, "fused_exchange": tr.fused,
                           "step": {"graph": "libav1p focal-loss + flat AdamW kernels, zero-grad + forward + loss + backward replayed from one CUDA graph",
                                    "native": "libav1p focal-loss + flat AdamW kernels, eager launches",
                                    "torch": "plain PyTorch ops + torch.optim.AdamW"}[args.mode],
                           "config": {"workload": "Stage1 data-parallel training step (BASELINE configs[4])", "per_gpu_batch": args.batch,
                                      "allreduce_bytes_per_step": tr.allreduce_bytes(),
-                                     "gradient_exchange": (f"{len(tr.buckets)} buckets of ~{args.bucket_mb:g} MB in backward order, async all-reduce "
+                                     "gradient_exchange": "one kernel per rank: gradient reduce-scatter + AdamW + parameter all-gather over NVLink peer memory (av1p_dp_adamw_fused)" if tr.fused else (f"{len(tr.buckets)} buckets of ~{args.bucket_mb:g} MB in backward order, async all-reduce "
                                                            "launched from post-accumulate hooks (overlaps backward)") if args.bucket_mb > 0
                                                           else "one flat all-reduce after backward",
                                      "optimizer": "AdamW lr 1e-3 wd 1e-4",
