@@ -112,6 +112,19 @@ def focal_loss_binary_native(logits: torch.Tensor, targets: torch.Tensor, alpha:
     return _FocalLossNative.apply(logits, targets, alpha, gamma)
 
 
+def gradless_ranges(segments, n: int):
+    """Complement of the sorted, disjoint `segments` [(lo, hi), ...] inside [0, n): the flat ranges whose parameters got no
+    gradient (torch.optim.AdamW skips such parameters entirely - no weight decay either)."""
+    gaps, at = [], 0
+    for lo, hi in segments:
+        if lo > at:
+            gaps.append((at, lo))
+        at = max(at, hi)
+    if at < n:
+        gaps.append((at, n))
+    return gaps
+
+
 class PeerBuffers:
     """Every rank's copy of a set of CUDA tensors, mapped into this process over CUDA IPC (one node, NVLink / NVSwitch peer
     access).  `pointers[name][r]` is the address - valid in kernels of THIS rank's device - of rank r's tensor `name`.
@@ -269,6 +282,8 @@ class Stage1DataParallelTrainer:
         self._works = []
         self._touched = set()
         self._capturing = False
+        self._segments, self._segments_for = None, None    # [(start, end)] ranges of the flat buffers that received gradients
+        self.fused = False
         if self.native:
             self.flat_param = torch.empty(n, dtype=torch.float32, device=self.device)
             with torch.no_grad():
@@ -283,8 +298,6 @@ class Stage1DataParallelTrainer:
             self.fused = False
             if self.world > 1 and fused_exchange is not False:
                 self._setup_fused(required=bool(fused_exchange))
-            self._segments = None                # [(start, end)] ranges of the flat buffers that received gradients
-            self._segments_for = None
             self._graphs = {}                    # (batch shape) -> [graph, static images, static labels, static loss]
             self._steps_done = 0
         else:
@@ -333,13 +346,7 @@ class Stage1DataParallelTrainer:
     def _update_fused(self) -> None:
         from . import _native as N
         n = self.flat_grad.numel()
-        gaps, at = [], 0
-        for lo, hi in self._grad_segments():
-            if lo > at:
-                gaps.append((at, lo))
-            at = hi
-        if at < n:
-            gaps.append((at, n))
+        gaps = gradless_ranges(self._grad_segments(), n)
         if len(gaps) > 1:
             raise RuntimeError(f"the fused exchange supports one grad-less parameter range, this model has {len(gaps)}: pass fused_exchange=False")
         skip = gaps[0] if gaps else (0, 0)

@@ -91,6 +91,22 @@ def test_focal_loss_closed_form_gradient_equals_autograd():
         assert (got - xa.grad).abs().max() <= 1e-7 + 1e-5 * xa.grad.abs().max()
 
 
+def test_gradless_ranges_of_the_flat_layout():
+    from cnn_av1_research_b200.training import gradless_ranges
+    assert gradless_ranges([(0, 10)], 10) == []
+    assert gradless_ranges([(0, 4), (5, 10)], 10) == [(4, 5)]
+    assert gradless_ranges([(2, 4), (6, 8)], 10) == [(0, 2), (4, 6), (8, 10)]
+    assert gradless_ranges([], 3) == [(0, 3)]
+    # the real layout: everything but the temperature received a gradient -> exactly one one-element gap near the end
+    tr = Stage1DataParallelTrainer(_model(), "cpu", dropout_p=0.0, autocast_bf16=False)
+    x, y = synthetic_labelled_blocks(8, 1)
+    tr.step(x, y)
+    tr._segments = None
+    gaps = gradless_ranges(tr._grad_segments(), tr.flat_grad.numel())
+    off = tr._offset[dict(tr.named_params)["head.temperature"]]
+    assert gaps == [(off, off + 1)]
+
+
 def test_native_step_refuses_the_cpu():
     with pytest.raises(RuntimeError, match="CUDA"):
         Stage1DataParallelTrainer(_model(), "cpu", native=True)
