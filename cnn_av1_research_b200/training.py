@@ -112,6 +112,16 @@ def focal_loss_binary_native(logits: torch.Tensor, targets: torch.Tensor, alpha:
     return _FocalLossNative.apply(logits, targets, alpha, gamma)
 
 
+def _to_cpu(obj):
+    if torch.is_tensor(obj):
+        return obj.detach().to("cpu", copy=True)
+    if isinstance(obj, dict):
+        return {k: _to_cpu(v) for k, v in obj.items()}
+    if isinstance(obj, (list, tuple)):
+        return type(obj)(_to_cpu(v) for v in obj)
+    return obj
+
+
 def gradless_ranges(segments, n: int):
     """Complement of the sorted, disjoint `segments` [(lo, hi), ...] inside [0, n): the flat ranges whose parameters got no
     gradient (torch.optim.AdamW skips such parameters entirely - no weight decay either)."""
@@ -512,14 +522,90 @@ class Stage1DataParallelTrainer:
     def allreduce_bytes(self) -> int:
         return self.flat_grad.numel() * self.flat_grad.element_size()
 
+    # ---- checkpoint / resume -----------------------------------------------------------------------------------------
+    def _full_moments(self):
+        """(exp_avg, exp_avg_sq) of the native step as whole flat buffers (the fused exchange keeps one shard per rank)."""
+        if not self.fused:
+            return self.flat_exp_avg, self.flat_exp_avg_sq
+
+        def whole(shard):                        # every rank's shard, concatenated in rank order = the flat layout
+            parts = [torch.empty_like(shard) for _ in range(self.world)]
+            dist.all_gather(parts, shard, group=self.group)
+            return torch.cat(parts)[:self.flat_grad.numel()]
+        return whole(self.flat_exp_avg), whole(self.flat_exp_avg_sq)
+
+    def optimizer_state_dict(self) -> Dict:
+        """The optimiser state in `torch.optim.AdamW.state_dict()` format (what 003:297 stores under
+        'optimizer_state_dict'): it loads into a plain `torch.optim.AdamW(model.parameters(), ...)` of the reference's
+        training script and into either step of this class.  Parameters that never received a gradient (the temperature)
+        have no entry, as in torch.  With the fused exchange this is a collective call (the moment shards are gathered)."""
+        if not self.native:
+            return self.optimizer.state_dict()
+        template = torch.optim.AdamW(self.params, lr=self.lr, weight_decay=self.weight_decay, betas=self.betas, eps=self.eps).state_dict()
+        m, v = self._full_moments()
+        step = float(int(self.step_dev.item()))
+        state = {}
+        if step > 0:
+            for i, p in enumerate(self.params):
+                if p in self._touched:
+                    state[i] = {"step": torch.tensor(step), "exp_avg": self._view(m, self._offset[p], p).detach().clone().contiguous(),
+                                "exp_avg_sq": self._view(v, self._offset[p], p).detach().clone().contiguous()}
+        return {"state": state, "param_groups": template["param_groups"]}
+
+    def load_optimizer_state_dict(self, sd: Dict) -> None:
+        """Inverse of `optimizer_state_dict` (also accepts the reference's own `optimizer.state_dict()`, 003:297)."""
+        if not self.native:
+            import copy
+            self.optimizer.load_state_dict(copy.deepcopy(sd))      # torch keeps the 'step' tensors it is handed: do not alias the caller's
+            return
+        group = sd["param_groups"][0]
+        self.lr, self.weight_decay, self.eps = float(group["lr"]), float(group["weight_decay"]), float(group["eps"])
+        self.betas = (float(group["betas"][0]), float(group["betas"][1]))
+        n = self.flat_grad.numel()
+        m = torch.zeros(n, dtype=torch.float32, device=self.device)
+        v = torch.zeros(n, dtype=torch.float32, device=self.device)
+        steps = set()
+        order = list(group["params"])
+        for key, st in sd["state"].items():
+            p = self.params[order.index(int(key))]
+            self._view(m, self._offset[p], p).copy_(st["exp_avg"])
+            self._view(v, self._offset[p], p).copy_(st["exp_avg_sq"])
+            steps.add(int(st["step"]))
+        if len(steps) > 1:
+            raise ValueError(f"parameters with different step counts ({sorted(steps)}): the flat update keeps one counter")
+        self.step_dev.fill_(steps.pop() if steps else 0)
+        if self.fused:
+            lo = self.rank * self.shard
+            for full, mine in ((m, self.flat_exp_avg), (v, self.flat_exp_avg_sq)):
+                mine.zero_()
+                piece = full[lo:lo + self.shard]
+                mine[:piece.numel()].copy_(piece)
+        else:
+            self.flat_exp_avg.copy_(m)
+            self.flat_exp_avg_sq.copy_(v)
+
+    def checkpoint(self, epoch: Optional[int] = None, **extra) -> Dict:
+        """The dictionary 003:294-301 passes to `torch.save`: 'epoch', 'model_state_dict', 'optimizer_state_dict' (+ whatever
+        the caller adds: 'best_f1', 'val_metrics', ...).  Tensors are copies on the CPU; 008 / 008b load the
+        'model_state_dict' of such a file (008:221-223)."""
+        out = {"epoch": epoch, "model_state_dict": {k: v.detach().to("cpu", copy=True) for k, v in self.model.state_dict().items()},
+               "optimizer_state_dict": _to_cpu(self.optimizer_state_dict())}
+        out.update(extra)
+        return out
+
+    def load_checkpoint(self, ckpt: Dict) -> None:
+        """Resume from `checkpoint()` output or from a file the reference's 003 wrote.  Weights are copied INTO the existing
+        parameter tensors (views of the flat buffer on the native step), so every replica must load the same file."""
+        self.model.load_state_dict(ckpt["model_state_dict"])
+        if ckpt.get("optimizer_state_dict") is not None:
+            self.load_optimizer_state_dict(ckpt["optimizer_state_dict"])
+        if self.native:                          # (recorded step graphs stay valid: they address the same buffers)
+            torch.autograd.graph.increment_version(self.params + self._buffers)
+
     def optimizer_state(self) -> Dict[str, torch.Tensor]:
         """AdamW state in PARAMETER order ('step', 'exp_avg', 'exp_avg_sq' as flat vectors) for checkpoints / tests."""
         if self.native and self.fused:
-            def whole(shard):                    # every rank's moment shard, concatenated in rank order = the flat layout
-                parts = [torch.empty_like(shard) for _ in range(self.world)]
-                dist.all_gather(parts, shard, group=self.group)
-                return torch.cat(parts)[:self.flat_grad.numel()]
-            m, v = whole(self.flat_exp_avg), whole(self.flat_exp_avg_sq)
+            m, v = self._full_moments()
             pick = lambda flat: torch.cat([self._view(flat, self._offset[p], p).reshape(-1) for p in self.params])
             return {"step": self.step_dev.clone(), "exp_avg": pick(m), "exp_avg_sq": pick(v)}
         if self.native:

@@ -107,6 +107,70 @@ def test_gradless_ranges_of_the_flat_layout():
     assert gaps == [(off, off + 1)]
 
 
+def test_checkpoint_resume_in_the_reference_format(tmp_path):
+    """checkpoint() is the dictionary 003:294-301 saves ('epoch', 'model_state_dict', 'optimizer_state_dict' in
+    torch.optim.AdamW's own format): a resumed trainer continues bit-identically, the optimiser state loads into a plain
+    torch.optim.AdamW over the drop-in model's parameters, and the grad-less temperature has no optimiser entry."""
+    x, y = synthetic_labelled_blocks(16, 5)
+    torch.manual_seed(0)
+    a = Stage1DataParallelTrainer(_model(), "cpu", dropout_p=0.0, autocast_bf16=False)
+    for _ in range(2):
+        a.step(x, y)
+    ckpt = a.checkpoint(epoch=7, best_f1=0.5)
+    assert set(ckpt) == {"epoch", "model_state_dict", "optimizer_state_dict", "best_f1"} and ckpt["epoch"] == 7
+    torch.save(ckpt, tmp_path / "stage1_model_best.pt")
+    ckpt = torch.load(tmp_path / "stage1_model_best.pt", weights_only=False)
+    b = Stage1DataParallelTrainer(Stage1Model(pretrained=False), "cpu", dropout_p=0.0, autocast_bf16=False)
+    b.load_checkpoint(ckpt)
+    a.step(x, y)
+    b.step(x, y)
+    assert all(torch.equal(p, q) for p, q in zip(a.params, b.params))
+    names = [k for k, _ in a.named_params]
+    assert names.index("head.temperature") not in ckpt["optimizer_state_dict"]["state"]
+    assert len(ckpt["optimizer_state_dict"]["state"]) == len(names) - 1
+    plain = Stage1Model(pretrained=False)
+    opt = torch.optim.AdamW(plain.parameters(), lr=1e-3, weight_decay=1e-4)
+    opt.load_state_dict(ckpt["optimizer_state_dict"])                   # the reference's resume path (its own optimiser class)
+    assert float(opt.state[list(plain.parameters())[0]]["step"]) == 2.0
+    # the drop-in inference model loads the same file (008:221-223)
+    m = Stage1Model(pretrained=False)
+    m.load_state_dict(ckpt["model_state_dict"])
+
+
+def test_flat_moment_buffers_convert_to_and_from_torch_adamw_state():
+    """The native step keeps AdamW's moments in flat buffers (4-D weights in channels_last order); its
+    optimizer_state_dict / load_optimizer_state_dict are pure tensor re-arrangements, exercised here on CPU tensors against
+    the state torch.optim.AdamW built itself."""
+    x, y = synthetic_labelled_blocks(16, 5)
+    torch.manual_seed(0)
+    a = Stage1DataParallelTrainer(_model(), "cpu", dropout_p=0.0, autocast_bf16=False)
+    for _ in range(2):
+        a.step(x, y)
+    want = a.optimizer.state_dict()
+    b = Stage1DataParallelTrainer(_model(), "cpu", dropout_p=0.0, autocast_bf16=False)
+    # dress b up as the native step would be (CPU tensors instead of device buffers; no kernel is launched)
+    b.native, b.channels_last, b.fused = True, True, False
+    n = b.flat_grad.numel()
+    b.flat_exp_avg, b.flat_exp_avg_sq = torch.zeros(n), torch.zeros(n)
+    b.step_dev = torch.zeros(1, dtype=torch.int32)
+    b._buffers, b._graphs = [], {}
+    b.load_optimizer_state_dict(want)
+    assert int(b.step_dev) == 2
+    w = dict(a.named_params)["backbone.layer1.0.conv1.weight"]
+    wb = dict(b.named_params)["backbone.layer1.0.conv1.weight"]
+    slot = b.flat_exp_avg[b._offset[wb]:b._offset[wb] + wb.numel()]
+    assert torch.equal(slot.view(64, 3, 3, 64), a.optimizer.state[w]["exp_avg"].permute(0, 2, 3, 1))       # [O][H][W][I] inside the buffer
+    b._touched = {p for k, p in b.named_params if k != "head.temperature"}
+    got = b.optimizer_state_dict()
+    assert got["param_groups"][0]["params"] == want["param_groups"][0]["params"] and set(got["state"]) == set(want["state"])
+    for i, st in want["state"].items():
+        assert float(got["state"][i]["step"]) == float(st["step"])
+        assert torch.equal(got["state"][i]["exp_avg"], st["exp_avg"]) and torch.equal(got["state"][i]["exp_avg_sq"], st["exp_avg_sq"])
+        assert got["state"][i]["exp_avg"].is_contiguous()
+    for k in ("lr", "betas", "eps", "weight_decay"):
+        assert got["param_groups"][0][k] == want["param_groups"][0][k]
+
+
 def test_native_step_refuses_the_cpu():
     with pytest.raises(RuntimeError, match="CUDA"):
         Stage1DataParallelTrainer(_model(), "cpu", native=True)
