@@ -153,12 +153,18 @@ class PeerBuffers:
         self._keep = dict(tensors)
         payload = {}
         with torch.cuda.device(self.device):
-            for k, t in tensors.items():
-                handle, off = C.create_string_buffer(64), C.c_int64(0)
-                N.check(lib.av1p_ipc_export(N.ptr(t), handle, C.byref(off)))
-                payload[k] = (handle.raw, int(off.value), int(self.device.index))
+            try:
+                for k, t in tensors.items():
+                    handle, off = C.create_string_buffer(64), C.c_int64(0)
+                    N.check(lib.av1p_ipc_export(N.ptr(t), handle, C.byref(off)))
+                    payload[k] = (handle.raw, int(off.value), int(self.device.index))
+            except Exception as exc:               # every rank must still reach the collective below
+                payload = {"__error__": f"{type(exc).__name__}: {exc}"}
             gathered = [None] * self.world
             dist.all_gather_object(gathered, payload, group=group)
+            failed = [(r, item["__error__"]) for r, item in enumerate(gathered) if "__error__" in item]
+            if failed:
+                raise RuntimeError(f"rank {failed[0][0]} could not export its buffers over CUDA IPC ({failed[0][1]})")
             self.pointers: Dict[str, list] = {k: [] for k in tensors}
             for r, item in enumerate(gathered):
                 for k, (handle, off, dev_index) in item.items():
