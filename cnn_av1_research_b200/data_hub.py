@@ -275,6 +275,57 @@ def load_pipeline(stage1_model: Union[str, Path], stage2_model: Union[str, Path]
     return HierarchicalPipelineV6(*models, stage1_threshold=stage1_threshold, device=device)
 
 
+# ---------------------------------------------------------------------------------------------- 008's result files
+CLASS_NAMES_V6 = ["NONE", "SPLIT", "HORZ", "VERT", "HORZ_A", "HORZ_B", "VERT_A", "VERT_B"]     # 008:280, the pipeline's label space
+
+
+def save_pipeline_results(results: Dict, output_dir: Union[str, Path], split: str, threshold: float,
+                          class_names=None, config: Optional[Dict] = None) -> Dict[str, Path]:
+    """008:306-352: the three artefacts `main` leaves behind for an `evaluate_pipeline` result - `pipeline_metrics_{split}.json`
+    ('split', 'threshold', 'metrics', 'confusion_matrix', 'class_names', 'config'), `pipeline_predictions_{split}.npz`
+    ('predictions', 'labels', 'class_names') and `pipeline_report_{split}.txt`.  Returns their paths."""
+    class_names = list(class_names) if class_names is not None else list(CLASS_NAMES_V6)
+    out = Path(output_dir)
+    out.mkdir(parents=True, exist_ok=True)
+    paths = {"metrics": out / f"pipeline_metrics_{split}.json", "predictions": out / f"pipeline_predictions_{split}.npz",
+             "report": out / f"pipeline_report_{split}.txt"}
+    with open(paths["metrics"], "w") as f:
+        json.dump({"split": split, "threshold": threshold, "metrics": results["metrics"], "confusion_matrix": results["confusion_matrix"],
+                   "class_names": class_names, "config": dict(config or {})}, f, indent=2)
+    np.savez(paths["predictions"], predictions=results["predictions"], labels=results["labels"], class_names=class_names)
+    m = results["metrics"]
+    rule = "=" * 70
+    with open(paths["report"], "w") as f:
+        f.write(f"V6 Pipeline Evaluation Report\n{rule}\n\n")
+        f.write(f"Dataset: {split}\nStage 1 Threshold: {threshold}\nSamples: {len(results['labels'])}\n\n")
+        f.write(f"Overall Metrics:\n  Accuracy: {m['accuracy']:.2%}\n  Macro F1: {m['macro_f1']:.2%}\n  Weighted F1: {m['weighted_f1']:.2%}\n\n")
+        f.write("Classification Report:\n")
+        f.write(results["classification_report"])
+    return paths
+
+
+def run_pipeline_evaluation(dataset_dir: Union[str, Path], stage1_model, stage2_model, stage3_rect_model, stage3_ab_model,
+                            output_dir: Union[str, Path], stage1_threshold: float = 0.45, batch_size: int = 256, device="cuda",
+                            use_test: bool = False, class_names=None) -> Dict:
+    """The body of 008's `main` (008:216-352) as one call: four checkpoints -> pipeline, `{split}.pt` (falling back to
+    `val.pt`, 008:256-260) -> BlockRecord -> evaluation dataset -> `evaluate_pipeline` -> the three result files.  The
+    dataset file must hold the raw 10-bit samples (`record_from_dataset_file`)."""
+    from .pipeline import evaluate_pipeline
+    class_names = list(class_names) if class_names is not None else list(CLASS_NAMES_V6)
+    pipeline = load_pipeline(stage1_model, stage2_model, stage3_rect_model, stage3_ab_model, stage1_threshold, device)
+    dataset_dir = Path(dataset_dir)
+    split = "test" if use_test else "val"
+    if not (dataset_dir / f"{split}.pt").exists():
+        split = "val"
+    dataset = build_hierarchical_dataset_v6(record_from_dataset_file(dataset_dir / f"{split}.pt"), augmentation=None, stage="eval",
+                                            device=device)
+    results = evaluate_pipeline(pipeline, dataset.batches(batch_size), class_names)
+    results["files"] = save_pipeline_results(results, output_dir, split, stage1_threshold, class_names,
+                                             {"dataset_dir": str(dataset_dir), "stage1_threshold": stage1_threshold, "batch_size": batch_size,
+                                              "device": str(device), "use_test": bool(use_test)})
+    return results
+
+
 # ---------------------------------------------------------------------------------------------- 008b's result files
 def compute_pipeline_metrics(predictions: np.ndarray, ground_truth: np.ndarray, output_dir: Optional[Union[str, Path]] = None,
                              verbose: bool = True) -> Dict:

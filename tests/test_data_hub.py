@@ -166,6 +166,39 @@ def test_flatten_dataset_file_and_result_files_match_008b(tmp_path):
     assert np.array_equal(np.load(tmp_path / "out" / "confusion_matrix.npy"), GOLD["metrics_confusion"])
 
 
+def test_result_files_of_the_pipeline_evaluation(tmp_path):
+    """008:306-352's three artefacts from an evaluate_pipeline result (built here from seeded label vectors through the
+    package's own metrics: no GPU needed); in the build container the metrics file equals what the reference's
+    compute_metrics / sklearn calls produce for the same vectors."""
+    from cnn_av1_research_b200.metrics import classification_report_text, compute_metrics, confusion_counts
+    _, _, _, _, gt, pred = inputs()
+    gt, pred = np.minimum(gt, 7), np.minimum(pred, 7)
+    names = [D.CLASS_NAMES_V6[c] for c in np.union1d(gt, pred)]
+    results = {"predictions": pred, "labels": gt, "metrics": compute_metrics(gt, pred, labels=names),
+               "classification_report": classification_report_text(gt, pred, target_names=names),
+               "confusion_matrix": confusion_counts(gt, pred)[1].tolist()}
+    paths = D.save_pipeline_results(results, tmp_path / "eval", "val", 0.45, names, {"batch_size": 256})
+    assert sorted(p.name for p in paths.values()) == ["pipeline_metrics_val.json", "pipeline_predictions_val.npz", "pipeline_report_val.txt"]
+    meta = json.load(open(paths["metrics"]))
+    assert list(meta) == ["split", "threshold", "metrics", "confusion_matrix", "class_names", "config"]
+    assert meta["split"] == "val" and meta["threshold"] == 0.45 and meta["class_names"] == names and meta["config"] == {"batch_size": 256}
+    assert meta["metrics"]["accuracy"] == float((gt == pred).mean())
+    z = np.load(paths["predictions"])
+    assert np.array_equal(z["predictions"], pred) and np.array_equal(z["labels"], gt) and z["class_names"].tolist() == names
+    report = open(paths["report"]).read()
+    assert report.startswith("V6 Pipeline Evaluation Report\n" + "=" * 70) and f"Samples: {len(gt)}" in report
+    assert report.endswith(results["classification_report"]) and f"Accuracy: {meta['metrics']['accuracy']:.2%}" in report
+    import ref_import
+    if ref_import.available():
+        ref_metrics = ref_import._load("ref_metrics_dh", ref_import.REF / "pesquisa_v6/v6_pipeline/metrics.py") \
+            if "ref_metrics_dh" not in sys.modules else sys.modules["ref_metrics_dh"]
+        ref_import.load()
+        want = ref_metrics.compute_metrics(gt, pred, labels=names)
+        for k in ("accuracy", "macro_f1", "weighted_f1", "macro_precision", "weighted_recall"):
+            assert abs(want[k] - meta["metrics"][k]) <= 1e-12, k
+        assert want["confusion_matrix"] == meta["confusion_matrix"]
+
+
 def test_raw_dataset_file_to_record_and_checkpoint_loaders(tmp_path):
     _, samples, labels, qps, _, _ = inputs()
     pt = tmp_path / "val.pt"
