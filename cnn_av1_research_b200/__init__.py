@@ -1,6 +1,7 @@
 """B200-native AV1 partition-prediction cascade (drop-in for the v6 inference path of
 chiarorosa/cnn-av1-research).  See DESIGN.md and INTEGRATION.md at the repository root."""
-from .data_hub import (FlattenEvalDataset, HierarchicalBlockDatasetV6, build_hierarchical_dataset_v6, compute_pipeline_metrics,
+from .data_hub import (create_ab_oversampled_dataset, create_balanced_sampler, filter_for_stage2, filter_for_stage3, get_class_weights,
+                       FlattenEvalDataset, HierarchicalBlockDatasetV6, build_hierarchical_dataset_v6, compute_pipeline_metrics,
                        index_sequences, load_block_records, load_pipeline, load_stage1_model, load_stage2_flat_model, map_to_stage1_v6, map_to_stage2_v6,
                        map_to_stage3_v6, record_from_dataset_file, run_pipeline_evaluation, save_pipeline_results)
 from .ensemble import ABEnsemble, WeightedEnsemble
@@ -27,5 +28,6 @@ __all__ = [
     "predict_yuv_file", "save_blocks_binary_10bit", "load_block_file", "ABEnsemble", "WeightedEnsemble", "AdapterModule", "extract_frames_device",
     "Stage2ModelWithAdapters", "compute_metrics", "filter_dataset_through_stage1", "HierarchicalBlockDatasetV6",
     "FlattenEvalDataset", "build_hierarchical_dataset_v6", "compute_pipeline_metrics", "load_pipeline", "load_stage1_model",
-    "load_stage2_flat_model", "map_to_stage1_v6", "map_to_stage2_v6", "map_to_stage3_v6", "record_from_dataset_file", "index_sequences", "load_block_records", "run_pipeline_evaluation", "save_pipeline_results",
+    "load_stage2_flat_model", "map_to_stage1_v6", "map_to_stage2_v6", "map_to_stage3_v6", "record_from_dataset_file", "index_sequences", "load_block_records", "create_balanced_sampler", "create_ab_oversampled_dataset", "filter_for_stage2",
+    "filter_for_stage3", "get_class_weights", "run_pipeline_evaluation", "save_pipeline_results",
 ]

@@ -25,7 +25,7 @@ from typing import Dict, Iterator, Optional, Tuple, Union
 
 import numpy as np
 import torch
-from torch.utils.data import Dataset
+from torch.utils.data import Dataset, WeightedRandomSampler
 
 from .extraction import BlockRecord, TorchBlockRecord
 from .fileio import load_block_file
@@ -133,6 +133,73 @@ def map_to_stage3_v6(label_ids: np.ndarray) -> Dict[str, np.ndarray]:
     """data_hub.py:260-271: per specialist head, the class index inside its group or -1 (int64)."""
     slots = _slots(label_ids)
     return {head: table[slots] for head, table in _STAGE3_LUT.items()}
+
+
+# ---------------------------------------------------------------------------------------------- sampling / filtering
+def _per_sample(labels: np.ndarray, class_values: np.ndarray) -> np.ndarray:
+    """class_values[i] belongs to the i-th distinct label value (sorted): spread them over the samples (float64)."""
+    _, inverse = np.unique(labels, return_inverse=True)
+    return np.asarray(class_values, dtype=np.float64)[inverse.reshape(-1)]
+
+
+def get_class_weights(labels: np.ndarray, beta: float = 0.9999) -> np.ndarray:
+    """data_hub.py:365-383: per-sample weight from the effective number of samples of its class (Cui et al. 2019),
+    (1 - beta) / (1 - beta^count), normalised so that the class weights sum to the number of classes."""
+    _, counts = np.unique(labels, return_counts=True)
+    w = (1.0 - beta) / (1.0 - np.power(beta, counts))
+    return _per_sample(labels, w / w.sum() * len(counts))
+
+
+def create_balanced_sampler(labels: np.ndarray, oversample_factor: Optional[Dict[int, float]] = None) -> WeightedRandomSampler:
+    """data_hub.py:386-417: `WeightedRandomSampler` (with replacement, one epoch = len(labels) draws) over inverse class
+    frequencies, or over the given per-class factors (1.0 for a class the dictionary does not name)."""
+    unique, counts = np.unique(labels, return_counts=True)
+    w = 1.0 / counts if oversample_factor is None else np.array([oversample_factor.get(c, 1.0) for c in unique], dtype=np.float64)
+    weights = _per_sample(labels, w / w.sum() * len(unique))
+    return WeightedRandomSampler(weights=weights, num_samples=len(weights), replacement=True)
+
+
+def _subset(record: BlockRecord, index) -> BlockRecord:
+    return BlockRecord(samples=record.samples[index], labels=record.labels[index], qps=record.qps[index])
+
+
+def create_ab_oversampled_dataset(record: BlockRecord, oversample_factors: Dict[int, int]) -> BlockRecord:
+    """data_hub.py:420-449: the AB blocks of `record`, each repeated `oversample_factors[its AB class]` times (default once),
+    in their original order."""
+    ab = map_to_stage3_v6(record.labels)["AB"]
+    idx = np.flatnonzero(ab >= 0)
+    repeats = np.array([oversample_factors.get(int(c), 1) for c in ab[idx]], dtype=np.int64)
+    return _subset(record, np.repeat(idx, repeats))
+
+
+def filter_for_stage2(record: BlockRecord) -> BlockRecord:
+    """data_hub.py:456-472: drop what Stage 2 never sees - NONE and the 4-way splits."""
+    return _subset(record, map_to_stage2_v6(record.labels)[1])
+
+
+def filter_for_stage3(record: BlockRecord, head: str) -> BlockRecord:
+    """data_hub.py:475-489: the blocks of one specialist ("RECT" or "AB")."""
+    if head not in STAGE3_GROUPS_V6:
+        raise ValueError(f"Unknown head: {head}")
+    return _subset(record, map_to_stage3_v6(record.labels)[head] >= 0)
+
+
+def save_metadata(path: Union[str, Path], info: Dict[str, object]) -> None:
+    """data_hub.py:496-500: sorted, indented JSON; parent directories are created."""
+    path = Path(path)
+    path.parent.mkdir(parents=True, exist_ok=True)
+    with open(path, "w", encoding="utf-8") as f:
+        json.dump(info, f, indent=2, sort_keys=True)
+
+
+def compute_class_distribution_v6(labels) -> Dict[str, float]:
+    """data_hub.py:503-511: share of every partition name among `labels`, in order of first appearance ("UNKNOWN" for ids
+    outside 0..9)."""
+    ids = np.asarray(list(labels)).astype(np.int64).reshape(-1)
+    slots = _slots(ids)
+    _, first = np.unique(slots, return_index=True)
+    names = list(PARTITION_ID_TO_NAME.values()) + ["UNKNOWN"]
+    return {names[slots[i]]: float(np.count_nonzero(slots == slots[i])) / ids.size for i in np.sort(first)}
 
 
 class HierarchicalBlockDatasetV6(Dataset):

@@ -53,6 +53,29 @@ def test_label_maps_match_the_live_reference():
     assert D.STAGE3_NAME_TO_ID_V6 == dh.STAGE3_NAME_TO_ID_V6 and D.STAGE2_GROUPS_V6 == dh.STAGE2_GROUPS_V6
 
 
+def test_sampling_weights_filters_and_distribution_match_the_reference_fixture(tmp_path):
+    _, samples, labels, qps, _, _ = inputs()
+    rec = BlockRecord(samples=samples, labels=labels, qps=qps)
+    assert np.allclose(D.get_class_weights(labels), GOLD["class_weights"], rtol=1e-12, atol=0)
+    s = D.create_balanced_sampler(labels)
+    assert s.num_samples == len(labels) and s.replacement
+    assert np.allclose(np.asarray(s.weights), GOLD["sampler_weights"], rtol=1e-12, atol=0)
+    custom = D.create_balanced_sampler(labels, oversample_factor={0: 1.0, 3: 2.5, 7: 4.0})
+    assert np.allclose(np.asarray(custom.weights), GOLD["sampler_weights_custom"], rtol=1e-12, atol=0)
+    over = D.create_ab_oversampled_dataset(rec, {0: 1, 1: 3, 2: 2})
+    assert np.array_equal(over.labels, GOLD["ab_over_labels"]) and np.array_equal(over.samples[:, 0, 0, 0], GOLD["ab_over_first_pixels"])
+    assert np.array_equal(D.filter_for_stage2(rec).labels, GOLD["stage2_filter_labels"])
+    assert np.array_equal(D.filter_for_stage3(rec, "RECT").qps, GOLD["stage3_rect_filter_qps"])
+    assert np.array_equal(D.filter_for_stage3(rec, "AB").labels, GOLD["stage3_ab_filter_labels"])
+    with pytest.raises(ValueError):
+        D.filter_for_stage3(rec, "SPLIT")
+    dist = D.compute_class_distribution_v6(list(labels) + [11])
+    want = json.loads(str(GOLD["class_distribution_json"]))
+    assert list(dist) == list(want) and all(abs(dist[k] - want[k]) <= 1e-15 for k in want) and "UNKNOWN" in dist
+    D.save_metadata(tmp_path / "a" / "b" / "meta.json", {"z": 1, "a": [1, 2]})
+    assert open(tmp_path / "a" / "b" / "meta.json").read() == json.dumps({"z": 1, "a": [1, 2]}, indent=2, sort_keys=True)
+
+
 def _write_dataset_dir(root, rng):
     """A dataset root as 005 / the label tools leave it: two sequences, block sizes 16 (both) and 8 (one, labels missing)."""
     for sub in ("intra_raw_blocks", "labels", "qps"):

@@ -59,6 +59,18 @@ def main():
     out["const_flatten_names"] = np.array([dh.FLATTEN_ID_TO_NAME[i] for i in range(7)])
     out["const_stage2_ids"] = np.array([dh.STAGE2_NAME_TO_ID_V6[k] for k in ("SPLIT", "RECT", "AB")])
 
+    # sampling weights, stage filters, class distribution (training-side helpers of data_hub.py)
+    out["class_weights"] = dh.get_class_weights(labels)
+    out["sampler_weights"] = np.asarray(dh.create_balanced_sampler(labels, oversample_factor=None).weights)
+    out["sampler_weights_custom"] = np.asarray(dh.create_balanced_sampler(labels, oversample_factor={0: 1.0, 3: 2.5, 7: 4.0}).weights)
+    rec0 = dh.BlockRecord(samples=samples, labels=labels, qps=qps)
+    over = dh.create_ab_oversampled_dataset(rec0, {0: 1, 1: 3, 2: 2})
+    out["ab_over_labels"], out["ab_over_first_pixels"] = over.labels, over.samples[:, 0, 0, 0]
+    out["stage2_filter_labels"] = dh.filter_for_stage2(rec0).labels
+    out["stage3_rect_filter_qps"] = dh.filter_for_stage3(rec0, "RECT").qps
+    out["stage3_ab_filter_labels"] = dh.filter_for_stage3(rec0, "AB").labels
+    out["class_distribution_json"] = np.array(json.dumps(dh.compute_class_distribution_v6(list(labels) + [11])))
+
     # the dataset 008's main builds (008:262-276) and what its DataLoader yields
     record = dh.BlockRecord(samples=samples, labels=labels, qps=qps)
     ds = dh.build_hierarchical_dataset_v6(record, augmentation=None, stage="eval")
