@@ -83,6 +83,34 @@ def focal_loss_binary_grad(logits: torch.Tensor, targets: torch.Tensor, alpha: f
     return (sign * a_t * one_m_pt ** gamma * (gamma * pt * log_pt - one_m_pt) / x.numel()).reshape(logits.shape)
 
 
+class FocalLoss(torch.nn.Module):
+    """Drop-in for `v6_pipeline.losses.FocalLoss` (losses.py:12-53), same constructor and call.  Binary branch (inputs
+    [N, 1]): on CUDA tensors with the default 'mean' reduction the loss and its gradient are ONE launch
+    (av1p_focal_loss_binary); other reductions, CPU tensors and the multi-class branch (losses.py:40-46) evaluate the
+    reference's formula with PyTorch ops."""
+
+    def __init__(self, alpha=0.25, gamma=2.0, reduction="mean"):
+        super().__init__()
+        self.alpha, self.gamma, self.reduction = alpha, gamma, reduction
+
+    def forward(self, inputs: torch.Tensor, targets: torch.Tensor) -> torch.Tensor:
+        if inputs.shape[1] == 1:
+            if inputs.is_cuda and self.reduction == "mean":
+                return focal_loss_binary_native(inputs, targets, self.alpha, self.gamma)
+            x, t = inputs.squeeze(1), targets.float()
+            bce = F.binary_cross_entropy_with_logits(x, t, reduction="none")
+            probs = torch.sigmoid(x)
+            pt = probs * t + (1 - probs) * (1 - t)
+            loss = (self.alpha * t + (1 - self.alpha) * (1 - t)) * (1 - pt) ** self.gamma * bce
+        else:
+            ce = F.cross_entropy(inputs, targets, reduction="none")
+            pt = F.softmax(inputs, dim=1).gather(1, targets.unsqueeze(1)).squeeze(1)
+            loss = (1 - pt) ** self.gamma * ce
+        if self.reduction == "mean":
+            return loss.mean()
+        return loss.sum() if self.reduction == "sum" else loss
+
+
 class _FocalLossNative(torch.autograd.Function):
     """losses.py:29-38 + :48-49 and their backward in one launch (av1p_focal_loss_binary)."""
 

@@ -66,6 +66,23 @@ def test_train_forward_and_focal_loss_match_reference_modules():
             assert torch.allclose(p.grad, g_ref[k].grad, atol=1e-5, rtol=1e-4), k
 
 
+def test_focal_loss_module_matches_the_reference_class():
+    import ref_import
+    from cnn_av1_research_b200.training import FocalLoss
+    g = torch.Generator().manual_seed(2)
+    xb, yb = torch.randn(40, 1, generator=g) * 3, (torch.rand(40, generator=g) < 0.4).long()
+    xm, ym = torch.randn(40, 7, generator=g) * 2, torch.randint(0, 7, (40,), generator=g)
+    assert torch.allclose(FocalLoss(0.25, 2.5)(xb, yb), focal_loss_binary(xb, yb, 0.25, 2.5), atol=1e-8)
+    assert FocalLoss(reduction="none")(xm, ym).shape == (40,) and FocalLoss(reduction="sum")(xb, yb).dim() == 0
+    if not ref_import.available():
+        return
+    ref_import.load()
+    losses = ref_import._load("ref_losses_fl", ref_import.REF / "pesquisa_v6/v6_pipeline/losses.py")
+    for kw in (dict(alpha=0.25, gamma=2.5), dict(alpha=0.5, gamma=2.0, reduction="sum"), dict(gamma=1.0, reduction="none")):
+        for x, y in ((xb, yb), (xm, ym)):
+            assert torch.allclose(FocalLoss(**kw)(x, y), losses.FocalLoss(**kw)(x, y), atol=1e-7), (kw, x.shape)
+
+
 def test_focal_loss_formula():
     x = torch.tensor([[0.3], [-1.2], [2.0], [0.0]])
     y = torch.tensor([1, 0, 0, 1])
