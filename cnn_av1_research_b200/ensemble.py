@@ -1,7 +1,8 @@
 """Drop-in for the Stage-3-AB ensembles of the reference (pesquisa_v6/v6_pipeline/ensemble.py).
 
 `ABEnsemble.predict` (hard / soft voting, :29-81), `ABEnsemble.predict_with_uncertainty` (:83-116), `save_ensemble` /
-`load_ensemble` (:119-153) and `WeightedEnsemble.predict` (:156-183) with the same signatures and return values.  The member
+`load_ensemble` (:119-153), `WeightedEnsemble.predict` (:156-183), `StackingEnsemble` (:186-226), `create_ab_ensemble`
+(:229-249) and `evaluate_ensemble_diversity` (:252-297) with the same signatures and return values.  The member
 models are this package's stage modules (their forwards run on the tcgen05 kernels); the voting itself is one launch of
 `av1p_ensemble_vote` over the stacked logits - the reference's hard voting is a Python loop over the batch.  There is no
 CPU path: without libav1p and an sm_100 device every call raises.
@@ -12,6 +13,7 @@ import json
 import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
+import numpy as np
 import torch
 import torch.nn as nn
 
@@ -96,3 +98,56 @@ class WeightedEnsemble(ABEnsemble):
     def predict(self, x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
         out = _vote(self._all_logits(x), 2, weights=self.weights.contiguous())
         return out["predictions"].to(x.device), out["confidences"].to(x.device)
+
+
+class StackingEnsemble:
+    """ensemble.py:186-226: a meta-model on the concatenated class probabilities of the base models.  The base models'
+    forwards are this package's stage modules; the softmax / concatenation / small meta-model are plain tensor ops on
+    whatever device the logits live on (the meta-model is the caller's nn.Module, not part of the cascade)."""
+
+    def __init__(self, base_models: List[nn.Module], meta_model: nn.Module, device="cuda"):
+        self.base_models, self.meta_model, self.device = base_models, meta_model, device
+        for model in self.base_models:
+            model.to(device)
+            model.eval()
+        self.meta_model.to(device)
+
+    def get_meta_features(self, x: torch.Tensor) -> torch.Tensor:
+        """(B, num_models * num_classes): every base model's softmax, side by side."""
+        with torch.no_grad():
+            return torch.cat([torch.softmax(model(x), dim=-1) for model in self.base_models], dim=-1)
+
+    def predict(self, x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        with torch.no_grad():
+            probs = torch.softmax(self.meta_model(self.get_meta_features(x)), dim=-1)
+        conf, pred = probs.max(dim=-1)
+        return pred, conf
+
+
+def create_ab_ensemble(model_class, num_models=3, device="cuda", pretrained=True) -> ABEnsemble:
+    """ensemble.py:229-249: `num_models` instances of `model_class(pretrained=...)`, model i built under
+    `torch.manual_seed(42 + i)`."""
+    models = []
+    for i in range(num_models):
+        torch.manual_seed(42 + i)
+        models.append(model_class(pretrained=pretrained))
+    return ABEnsemble(models, device=device)
+
+
+def evaluate_ensemble_diversity(ensemble: ABEnsemble, dataloader, device="cuda") -> Dict[str, float]:
+    """ensemble.py:252-297 over (data, targets) batches: mean pairwise disagreement of the members' argmax predictions
+    (one value per model pair per batch, averaged) and mean / std of the majority share per sample.  The reference walks the
+    batch in Python with `torch.unique` per sample; here the vote counts of a batch are one comparison tensor."""
+    disagreements, agreements = [], []
+    m = len(ensemble.models)
+    for data, _ in dataloader:
+        data = data.to(device)
+        with torch.no_grad():
+            preds = torch.stack([model(data).argmax(dim=-1) for model in ensemble.models])          # (M, B)
+        differ = (preds[:, None, :] != preds[None, :, :]).float().mean(dim=-1)                      # (M, M)
+        disagreements += [float(differ[i, j]) for i in range(m) for j in range(i + 1, m)]
+        votes_for_own = (preds[:, None, :] == preds[None, :, :]).sum(dim=0)                          # (M, B): support of each member's vote
+        agreements.append((votes_for_own.max(dim=0).values.double() / m).cpu())
+    agreements = torch.cat(agreements).numpy() if agreements else np.zeros(0)
+    return {"avg_pairwise_disagreement": np.mean(disagreements), "avg_majority_agreement": np.mean(agreements),
+            "std_majority_agreement": np.std(agreements)}

@@ -131,3 +131,60 @@ def test_gpu_ensemble_classes_end_to_end(cuda_device, fix, tmp_path):
     ens.save_ensemble(str(tmp_path / "ens"))
     again = ABEnsemble.load_ensemble(lambda: Stage3ABModel(pretrained=False), str(tmp_path / "ens"), device=cuda_device)
     assert again.num_models == 3 and torch.equal(again.predict(x)[0], hp)
+
+
+def _toy_models(n_models=3, classes=4, seed=0):
+    """Tiny stand-ins with the members' call contract (x -> logits): the helpers under test only compose forwards."""
+    class Toy(torch.nn.Module):
+        def __init__(self, pretrained=True):
+            super().__init__()
+            self.fc = torch.nn.Linear(16, classes)
+
+        def forward(self, x):
+            return self.fc(x.reshape(x.shape[0], -1)[:, :16])
+    torch.manual_seed(seed)
+    return Toy, [Toy() for _ in range(n_models)]
+
+
+def test_stacking_factory_and_diversity_match_the_reference_helpers():
+    """StackingEnsemble, create_ab_ensemble and evaluate_ensemble_diversity (ensemble.py:186-297) only compose member
+    forwards with tensor ops, so they are checked on the CPU with toy members - against the reference's own functions in the
+    build container, against hand-computed numbers everywhere."""
+    from cnn_av1_research_b200.ensemble import ABEnsemble, StackingEnsemble, create_ab_ensemble, evaluate_ensemble_diversity
+    Toy, models = _toy_models()
+    g = torch.Generator().manual_seed(4)
+    batches = [(torch.randn(9, 1, 4, 4, generator=g), torch.zeros(9)), (torch.randn(5, 1, 4, 4, generator=g), torch.zeros(5))]
+    ens = ABEnsemble.__new__(ABEnsemble)               # members stay on the CPU: no voting kernel is involved here
+    ens.models, ens.device, ens.num_models = models, "cpu", len(models)
+    got = evaluate_ensemble_diversity(ens, batches, device="cpu")
+    # by hand: per batch the three pairwise disagreement rates; per sample the share of the most common vote
+    dis, agr = [], []
+    for data, _ in batches:
+        preds = torch.stack([m(data).argmax(-1) for m in models])
+        dis += [float((preds[i] != preds[j]).float().mean()) for i in range(3) for j in range(i + 1, 3)]
+        agr += [max(int((preds[:, b] == c).sum()) for c in range(4)) / 3 for b in range(data.shape[0])]
+    assert abs(got["avg_pairwise_disagreement"] - np.mean(dis)) <= 1e-12
+    assert abs(got["avg_majority_agreement"] - np.mean(agr)) <= 1e-12 and abs(got["std_majority_agreement"] - np.std(agr)) <= 1e-12
+    meta = torch.nn.Linear(12, 4)
+    stack = StackingEnsemble(models, meta, device="cpu")
+    x = batches[0][0]
+    feats = stack.get_meta_features(x)
+    assert feats.shape == (9, 12) and torch.allclose(feats.reshape(9, 3, 4).sum(-1), torch.ones(9, 3), atol=1e-6)
+    pred, conf = stack.predict(x)
+    probs = torch.softmax(meta(feats), -1)
+    assert torch.equal(pred, probs.argmax(-1)) and torch.allclose(conf, probs.max(-1).values)
+    made = create_ab_ensemble(Toy, num_models=2, device="cpu", pretrained=False)
+    torch.manual_seed(43)
+    assert made.num_models == 2 and torch.equal(made.models[1].fc.weight, Toy().fc.weight)
+    import ref_import
+    if ref_import.available():
+        ref_import.load()
+        ref = ref_import._load("ref_ensemble_extra", ref_import.REF / "pesquisa_v6/v6_pipeline/ensemble.py")
+        r_ens = ref.ABEnsemble(models, device="cpu")
+        want = ref.evaluate_ensemble_diversity(r_ens, batches, device="cpu")
+        for k in want:
+            assert abs(want[k] - got[k]) <= 1e-7, k                    # the reference averages float32 batch means
+        r_pred, r_conf = ref.StackingEnsemble(models, meta, device="cpu").predict(x)
+        assert torch.equal(r_pred, pred) and torch.allclose(r_conf, conf)
+        r_made = ref.create_ab_ensemble(Toy, num_models=2, device="cpu", pretrained=False)
+        assert all(torch.equal(a.fc.weight, b.fc.weight) for a, b in zip(r_made.models, made.models))
