@@ -72,6 +72,84 @@ def compute_metrics(y_true: np.ndarray, y_pred: np.ndarray, labels: Optional[Seq
     return out
 
 
+def _binary_counts(y_true: np.ndarray, y_pred: np.ndarray):
+    t = np.asarray(y_true).reshape(-1) != 0
+    p = np.asarray(y_pred).reshape(-1) != 0
+    if t.shape != p.shape:
+        raise ValueError(f"y_true has {t.size} entries, y_pred {p.size}")
+    tp = int(np.count_nonzero(t & p))
+    fp = int(np.count_nonzero(~t & p))
+    fn = int(np.count_nonzero(t & ~p))
+    return int(t.size) - tp - fp - fn, fp, fn, tp
+
+
+def roc_auc(y_true: np.ndarray, y_scores: np.ndarray) -> Optional[float]:
+    """Area under the ROC curve as the Mann-Whitney statistic with mid-ranks for ties (what `sklearn.metrics.roc_auc_score`
+    computes for binary labels); None when only one class is present (sklearn raises there and metrics.py:106-109 stores None)."""
+    t = np.asarray(y_true).reshape(-1) != 0
+    s = np.asarray(y_scores, dtype=np.float64).reshape(-1)
+    n_pos, n_neg = int(t.sum()), int((~t).sum())
+    if n_pos == 0 or n_neg == 0:
+        return None
+    order = np.argsort(s, kind="mergesort")
+    sorted_s = s[order]
+    # mid-rank of every tie group
+    boundaries = np.flatnonzero(np.r_[True, sorted_s[1:] != sorted_s[:-1], True])
+    mid = (boundaries[:-1] + boundaries[1:] - 1) / 2.0 + 1.0
+    ranks = np.empty(s.size, dtype=np.float64)
+    ranks[order] = np.repeat(mid, np.diff(boundaries))
+    return float((ranks[t].sum() - n_pos * (n_pos + 1) / 2.0) / (n_pos * n_neg))
+
+
+def _binary_dict(tn: int, fp: int, fn: int, tp: int) -> Dict:
+    return {"accuracy": float((tp + tn) / (tp + tn + fp + fn)),
+            "precision": float(tp / (tp + fp)) if (tp + fp) > 0 else 0.0,
+            "recall": float(tp / (tp + fn)) if (tp + fn) > 0 else 0.0,
+            "specificity": float(tn / (tn + fp)) if (tn + fp) > 0 else 0.0,
+            "f1": float(2 * tp / (2 * tp + fp + fn)) if (2 * tp + fp + fn) > 0 else 0.0,
+            "true_positives": int(tp), "true_negatives": int(tn), "false_positives": int(fp), "false_negatives": int(fn)}
+
+
+def compute_binary_metrics(y_true: np.ndarray, y_pred: np.ndarray, y_scores: Optional[np.ndarray] = None) -> Dict:
+    """metrics.py:76-110: accuracy / precision / recall / specificity / F1 and the four confusion counts of a binary
+    decision (positive = non-zero), plus 'auc_roc' when scores are given."""
+    out = _binary_dict(*_binary_counts(y_true, y_pred))
+    if y_scores is not None:
+        out["auc_roc"] = roc_auc(y_true, y_scores)
+    return out
+
+
+def find_optimal_threshold(y_true: np.ndarray, y_scores: np.ndarray, metric: str = "f1"):
+    """metrics.py:113-141: the first of the 81 thresholds linspace(0.1, 0.9, 81) with the strictly best `metric`
+    (`score >= threshold` is positive) and the metrics there; (0.5, {}) if no threshold scores above zero.  All 81 confusion
+    tables come from one sort of the scores instead of 81 passes."""
+    thresholds = np.linspace(0.1, 0.9, 81)
+    t = np.asarray(y_true).reshape(-1) != 0
+    s = np.asarray(y_scores).reshape(-1).astype(np.float64)    # `scores >= np.float64 threshold` compares in float64 in the reference too
+    order = np.argsort(s, kind="mergesort")
+    sorted_s = s[order]
+    pos_below = np.r_[0, np.cumsum(t[order])]              # positives among the k smallest scores
+    k = np.searchsorted(sorted_s, thresholds, side="left")
+    n_pos, n = int(t.sum()), int(t.size)
+    fn = pos_below[k]
+    tp = n_pos - fn
+    fp = (n - k) - tp
+    tn = n - tp - fp - fn
+    auc = roc_auc(t, s)
+    best_threshold, best_score, best_metrics = 0.5, 0.0, {}
+    for i, th in enumerate(thresholds):
+        m = _binary_dict(int(tn[i]), int(fp[i]), int(fn[i]), int(tp[i]))
+        if m[metric] > best_score:
+            m["auc_roc"] = auc
+            best_threshold, best_score, best_metrics = th, m[metric], m
+    return best_threshold, best_metrics
+
+
+def compute_stage_metrics(stage_name: str, y_true: np.ndarray, y_pred: np.ndarray, labels: Optional[Sequence[str]]) -> Dict:
+    """metrics.py:144-163: the binary table for 'stage1', `compute_metrics` for every other stage."""
+    return compute_binary_metrics(y_true, y_pred) if stage_name == "stage1" else compute_metrics(y_true, y_pred, labels)
+
+
 def classification_report_text(y_true: np.ndarray, y_pred: np.ndarray, target_names: Optional[List[str]] = None) -> str:
     """The text table of 008:152 (`sklearn.metrics.classification_report(..., zero_division=0)`).  scikit-learn is
     what the reference calls, so the same function formats the table here (imported on use)."""

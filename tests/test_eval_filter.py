@@ -203,3 +203,34 @@ def test_gpu_evaluate_pipeline_end_to_end(cuda_device, eval_fix):
     assert np.abs(np.array(res["confusion_matrix"]) - eval_fix["confusion_matrix"]).sum() <= 4
     if agree == 1.0:
         assert res["classification_report"] == str(eval_fix["report"])
+
+
+def test_binary_metrics_and_threshold_search_match_the_reference_fixture():
+    """compute_binary_metrics / find_optimal_threshold / compute_stage_metrics (v6_pipeline/metrics.py:76-163) against
+    numbers produced by the reference's functions (tools/make_golden_datahub.py), incl. float32 scores that tie with
+    thresholds; AUC = sklearn's roc_auc_score to 1e-12."""
+    import json
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tools"))
+    from make_golden_datahub import binary_inputs
+    from cnn_av1_research_b200 import metrics as M
+    kat = json.loads(str(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "datahub.npz"))["binary_metrics_json"]))
+    y, s64, s32 = binary_inputs()
+
+    def same(a, b):
+        assert a.keys() == b.keys()
+        for k in a:
+            assert (a[k] is None and b[k] is None) or abs(a[k] - b[k]) <= 1e-12, k
+    same(M.compute_binary_metrics(y, (s64 >= 0.45).astype(int), s64), kat["binary"])
+    for name, sc in (("f64", s64), ("f32_ties", s32)):
+        for metric in ("f1", "precision", "accuracy"):
+            th, m = M.find_optimal_threshold(y, sc, metric)
+            assert float(th) == kat[f"optimal_{name}_{metric}"]["threshold"], (name, metric)
+            same(m, kat[f"optimal_{name}_{metric}"]["metrics"])
+    same(M.compute_stage_metrics("stage1", y, (s64 >= 0.5).astype(int), None), kat["stage1"])
+    assert M.compute_stage_metrics("stage2", y, y, ["a", "b"])["accuracy"] == 1.0
+    # degenerate inputs: one class only -> no AUC, nothing scores above zero -> the default threshold
+    assert M.compute_binary_metrics(np.zeros(5, int), np.zeros(5, int), np.linspace(0, 1, 5))["auc_roc"] is None
+    assert M.find_optimal_threshold(np.zeros(10, int), np.zeros(10)) == (0.5, {})
+    assert M.roc_auc(np.array([0, 0, 1, 1]), np.array([0.1, 0.4, 0.35, 0.8])) == 0.75

@@ -45,6 +45,13 @@ def inputs():
     return ids, samples, labels, qps, gt, pred
 
 
+def binary_inputs():
+    g = np.random.Generator(np.random.PCG64(77))
+    y = (g.random(4000) < 0.42).astype(int)
+    s64 = np.clip(g.normal(0.35 + 0.3 * y, 0.2), 0.0, 1.0)
+    return y, s64, np.round(s64, 2).astype(np.float32)
+
+
 def main():
     ns = ref_import.load()
     ref008b = ref_import._load("ref_flat008b_dh", ref_import.REF / "pesquisa_v6/scripts/008b_run_pipeline_flatten_eval.py")
@@ -70,6 +77,17 @@ def main():
     out["stage3_rect_filter_qps"] = dh.filter_for_stage3(rec0, "RECT").qps
     out["stage3_ab_filter_labels"] = dh.filter_for_stage3(rec0, "AB").labels
     out["class_distribution_json"] = np.array(json.dumps(dh.compute_class_distribution_v6(list(labels) + [11])))
+
+    # binary metrics / threshold search (v6_pipeline/metrics.py:76-163) on seeded scores, float64 and float32 with ties
+    rm = ref_import._load("ref_metrics_gold", ref_import.REF / "pesquisa_v6/v6_pipeline/metrics.py")
+    yb, s64, s32 = binary_inputs()
+    kat = {"binary": rm.compute_binary_metrics(yb, (s64 >= 0.45).astype(int), s64)}
+    for name, sc in (("f64", s64), ("f32_ties", s32)):
+        for metric in ("f1", "precision", "accuracy"):
+            th, m = rm.find_optimal_threshold(yb, sc, metric)
+            kat[f"optimal_{name}_{metric}"] = {"threshold": float(th), "metrics": m}
+    kat["stage1"] = rm.compute_stage_metrics("stage1", yb, (s64 >= 0.5).astype(int), None)
+    out["binary_metrics_json"] = np.array(json.dumps(kat, sort_keys=True))
 
     # the dataset 008's main builds (008:262-276) and what its DataLoader yields
     record = dh.BlockRecord(samples=samples, labels=labels, qps=qps)
