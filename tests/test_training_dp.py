@@ -93,6 +93,42 @@ def test_focal_loss_module_matches_the_reference_class():
             assert torch.allclose(FocalLoss(**kw)(x, y), losses.FocalLoss(**kw)(x, y), atol=1e-7), (kw, x.shape)
 
 
+def test_training_kernel_oracle_is_pinned_to_torch_adamw_and_the_reference_focal_loss():
+    """oracle/train_oracle.py (the host restatement of the two native training kernels) against the optimiser class the
+    reference instantiates (torch.optim.AdamW, 003:250-254) over five steps with gradients of very different scales, and
+    against FocalLoss + autograd (the reference's own module when its tree is present)."""
+    from oracle import train_oracle as T
+    g = torch.Generator().manual_seed(21)
+    p0 = torch.randn(5000, generator=g)
+    ref_p = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.AdamW([ref_p], lr=1e-3, weight_decay=1e-4)
+    p, m, v = p0.numpy().copy(), np.zeros(5000, np.float32), np.zeros(5000, np.float32)
+    for step in range(1, 6):
+        grad = torch.randn(5000, generator=g) * 10.0 ** (step - 4)
+        ref_p.grad = grad / 8
+        opt.step()
+        p, m, v = T.adamw_step(p, grad.numpy(), m, v, step, lr=1e-3, weight_decay=1e-4, grad_scale=1 / 8)
+    st = opt.state[ref_p]
+    assert np.abs(p - ref_p.detach().numpy()).max() <= 2e-6
+    assert np.abs(m - st["exp_avg"].numpy()).max() <= 2e-6 * np.abs(m).max()
+    assert np.abs(v - st["exp_avg_sq"].numpy()).max() <= 2e-6 * np.abs(v).max()
+    x = torch.randn(400, 1, generator=g) * 5
+    x[0], x[1], x[2] = 70.0, -70.0, 0.0
+    y = (torch.rand(400, generator=g) < 0.42).long()
+    crit = None
+    import ref_import
+    if ref_import.available():
+        ref_import.load()
+        crit = ref_import._load("ref_losses_oracle", ref_import.REF / "pesquisa_v6/v6_pipeline/losses.py").FocalLoss
+    for alpha, gamma in ((0.25, 2.5), (0.25, 2.0), (0.6, 0.0)):
+        xa = x.clone().requires_grad_(True)
+        want = crit(alpha=alpha, gamma=gamma)(xa, y) if crit is not None else focal_loss_binary(xa, y, alpha, gamma)
+        want.backward()
+        loss, dx = T.focal_loss_binary(x.numpy(), y.numpy(), alpha, gamma)
+        assert abs(float(loss) - float(want.detach())) <= 1e-6 + 1e-5 * abs(float(want.detach()))
+        assert np.abs(dx - xa.grad.numpy().reshape(-1)).max() <= 1e-7 + 2e-5 * float(xa.grad.abs().max())
+
+
 def test_focal_loss_formula():
     x = torch.tensor([[0.3], [-1.2], [2.0], [0.0]])
     y = torch.tensor([1, 0, 0, 1])
