@@ -69,11 +69,40 @@ def read_frames_yuv420p10(yuv_path, width: int, height: int, first_frame: int = 
 
 
 def predict_yuv_file(pipeline, yuv_path, width: int, height: int, first_frame: int = 0, n_frames: Optional[int] = None,
-                     chunk_frames: int = 8) -> torch.Tensor:
-    """Partition labels (uint8, host) of every 16x16 luma block of the given frames of a `.yuv` file."""
-    frames = read_frames_yuv420p10(yuv_path, width, height, first_frame, n_frames)
+                     chunk_frames: int = 8, window_frames: int = 64) -> torch.Tensor:
+    """Partition labels (uint8, host) of every 16x16 luma block of the given frames of a `.yuv` file.
+
+    The file is streamed in windows of `window_frames` frames (1.6 GB of pinned memory per 64 4K frames): while the GPU
+    works on one window (`predict_frames_host`: luma upload double-buffered against the cascades, `chunk_frames` frames
+    each), a reader thread fills the next one, so a sequence longer than host memory costs two windows of it."""
+    total = count_frames(yuv_path, width, height)
+    n = total - first_frame if n_frames is None else n_frames
+    if first_frame < 0 or n <= 0 or first_frame + n > total:
+        raise ValueError(f"frames [{first_frame}, {first_frame + n}) outside the file's {total} frames")
     words = calculate_yuv420_10bit_sizes(width, height)["total_frame_size"] // 2
-    return pipeline.predict_frames_host(frames, width, height, frames.numel() // words, chunk_frames=chunk_frames)
+    window = max(1, int(window_frames))
+    if n <= window:
+        frames = read_frames_yuv420p10(yuv_path, width, height, first_frame, n)
+        return pipeline.predict_frames_host(frames, width, height, frames.numel() // words, chunk_frames=chunk_frames)
+    from concurrent.futures import ThreadPoolExecutor
+    starts = list(range(first_frame, first_frame + n, window))
+    count = lambda f0: min(window, first_frame + n - f0)
+    out = []
+    device = getattr(pipeline, "device", None)
+
+    def read(f0):                                   # reader thread: pin on the pipeline's device, not on the thread's default one
+        if device is not None and torch.cuda.is_available():
+            torch.cuda.set_device(device)
+        return read_frames_yuv420p10(yuv_path, width, height, f0, count(f0))
+    with ThreadPoolExecutor(max_workers=1) as reader:
+        pending = reader.submit(read, starts[0])
+        for i, f0 in enumerate(starts):
+            frames = pending.result()
+            if i + 1 < len(starts):
+                pending = reader.submit(read, starts[i + 1])
+            labels = pipeline.predict_frames_host(frames, width, height, count(f0), chunk_frames=chunk_frames)
+            out.append(labels.clone())              # predict_frames_host may hand back a buffer it reuses
+    return torch.cat(out)
 
 
 def compute_data_hash(data: np.ndarray) -> str:

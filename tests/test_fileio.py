@@ -70,3 +70,34 @@ def test_gpu_predict_from_yuv_file(cuda_device, tmp_path):
     rec = P.BlockRecord(samples=fileio.load_block_file(tmp_path / "blk.raw", 16), labels=np.zeros(len(blocks), np.int64),
                         qps=np.zeros((len(blocks), 1), np.float32)).to_torch(cuda_device)
     assert np.array_equal(pipe.predict(rec.samples).numpy().astype(np.uint8), labels[:len(blocks)])
+
+
+def test_predict_yuv_file_streams_windows_in_order(tmp_path):
+    """Window streaming of predict_yuv_file with a stand-in pipeline (its predict_frames_host returns one value per block:
+    the first luma sample of the block's frame): every frame is read exactly once, in order, windows of the requested
+    size, the last one partial; the result equals the single-window call."""
+    from cnn_av1_research_b200 import fileio
+    from cnn_av1_research_b200.extraction import calculate_yuv420_10bit_sizes
+    w, h, nf = 64, 32, 11
+    words = calculate_yuv420_10bit_sizes(w, h)["total_frame_size"] // 2
+    data = np.zeros(nf * words, dtype="<u2")
+    for f in range(nf):
+        data[f * words:(f + 1) * words] = 100 + f
+    path = tmp_path / "s.yuv"
+    data.tofile(path)
+    calls = []
+
+    class Stub:
+        def predict_frames_host(self, frames, width, height, n_frames, chunk_frames=8):
+            assert frames.numel() == n_frames * words and (width, height) == (w, h)
+            calls.append(n_frames)
+            v = frames.view(torch.int16).reshape(n_frames, words)[:, 0].to(torch.uint8)
+            return v.repeat_interleave((w // 16) * (h // 16))
+    got = fileio.predict_yuv_file(Stub(), path, w, h, first_frame=1, n_frames=9, chunk_frames=2, window_frames=4)
+    assert calls == [4, 4, 1]
+    want = torch.arange(101, 110, dtype=torch.uint8).repeat_interleave(8)
+    assert torch.equal(got, want)
+    calls.clear()
+    assert torch.equal(fileio.predict_yuv_file(Stub(), path, w, h, first_frame=1, n_frames=9, window_frames=64), want) and calls == [9]
+    with pytest.raises(ValueError):
+        fileio.predict_yuv_file(Stub(), path, w, h, first_frame=5, n_frames=7)
